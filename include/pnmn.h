@@ -1,0 +1,120 @@
+/* pnmn.h — C ABI of the B200-native probnmn-clevr hot path.
+ *
+ * The reference (kdexd/probnmn-clevr) has no FFI: its "plugin API" for this path is the python
+ * nn.Module surface of NeuralModuleNetwork / ProgramGenerator.  The python classes in
+ * probnmn_clevr_b200/ keep that surface and call the entry points below through ctypes with raw
+ * device pointers, sizes and a cudaStream_t — no torch types cross this boundary.  Every entry
+ * point cites the reference code it replaces.  Conventions:
+ *   - all functions returning int: 0 = ok, non-zero = error; pnmn_last_error() has the text
+ *   - no device allocation happens inside the library: the caller owns every buffer (sizes are
+ *     reported by pnmn_plan_sizes / pnmn_model_packed_floats)
+ *   - no CPU fallback exists: without a CUDA device every compute entry point fails
+ *   - thread safety: a plan/model is used by one thread at a time; different plans are independent
+ */
+#ifndef PNMN_H_
+#define PNMN_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNMN_VERSION 1
+
+typedef struct pnmn_model pnmn_model;
+typedef struct pnmn_plan pnmn_plan;
+
+int pnmn_version(void);
+const char* pnmn_last_error(void);
+
+/* How NeuralModuleNetwork.__init__/forward classify a program token
+ * (probnmn/models/nmn.py:90-111 and :207-229). */
+enum pnmn_token_kind {
+  PNMN_TOK_SKIP = 0,      /* @@PADDING@@ @@UNKNOWN@@ @start@ @end@ unique            nmn.py:207-208 */
+  PNMN_TOK_SCENE = 1,     /* saved = out; out = ones                                  nmn.py:211-217 */
+  PNMN_TOK_AND = 2,       /* intersect -> AndModule  (torch.min)                      nmn.py:98-99   */
+  PNMN_TOK_OR = 3,        /* union     -> OrModule   (torch.max)                      nmn.py:100-101 */
+  PNMN_TOK_COMPARE = 4,   /* equal_*, less_than, greater_than -> ComparisonModule     nmn.py:102-103 */
+  PNMN_TOK_QUERY = 5,     /* query_*, exist, count -> QueryModule                     nmn.py:104-105 */
+  PNMN_TOK_RELATE = 6,    /* relate[*] -> RelateModule                                nmn.py:106-107 */
+  PNMN_TOK_SAME = 7,      /* same_* -> SameModule                                     nmn.py:108-109 */
+  PNMN_TOK_ATTENTION = 8  /* everything else (filter_*) -> AttentionModule            nmn.py:110-111 */
+};
+
+#define PNMN_MAX_MODULE_PARAMS 12
+
+/* Static description of a NeuralModuleNetwork (replaces the module table built in
+ * probnmn/models/nmn.py:86-115 and the stem of :67-72).  All parameters live in ONE flat fp32
+ * buffer; offsets are in floats.  token_param_off[v*12 + 2*i], [.. + 2*i + 1] are weight / bias
+ * of the i-th conv of token v's module in forward order (conv1..conv6 | projection,conv1,conv2 |
+ * conv), -1 when absent.  stem_param_off = {stem.0.weight, stem.0.bias, stem.2.weight,
+ * stem.2.bias}.  module_channels is fixed at 128 and the feature map at 14x14. */
+pnmn_model* pnmn_model_create(int vocab_size, const int32_t* token_kind, const int64_t* token_param_off,
+                              const int64_t* stem_param_off, int in_channels);
+void pnmn_model_destroy(pnmn_model* m);
+/* floats of scratch needed for the tf32-packed forward + dgrad weight tiles */
+int64_t pnmn_model_packed_floats(const pnmn_model* m);
+
+/* Program compiler: replaces the per-sample python interpreter with its B device->host syncs
+ * (probnmn/models/nmn.py:191-238).  programs_host: int64 [B][L] prefix-order token ids (host).
+ * Validity follows the reference's bare-except semantics exactly. */
+pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* programs_host, int batch, int length,
+                            int need_grad);
+void pnmn_plan_destroy(pnmn_plan* p);
+/* valid[b] = 1 if the reference would execute program b without raising (nmn.py:231-238) */
+int pnmn_plan_valid(const pnmn_plan* p, uint8_t* valid);
+
+enum pnmn_size_slot {
+  PNMN_SZ_ARENA16 = 0, /* floats, P16 plane arena (must be zero-filled when (re)allocated) */
+  PNMN_SZ_ARENA18 = 1, /* floats, P18 plane arena (zero-filled) */
+  PNMN_SZ_ARENA22 = 2, /* floats, P22 plane arena (zero-filled) */
+  PNMN_SZ_MAPS = 3,    /* floats, attention maps (zero-filled) */
+  PNMN_SZ_DMAPS = 4,   /* floats, attention-map gradients */
+  PNMN_SZ_IDX = 5,     /* int32, SameModule argmax slots */
+  PNMN_SZ_BLOB = 6,    /* bytes, device scratch for task tables */
+  PNMN_SZ_COUNT = 8
+};
+int pnmn_plan_sizes(const pnmn_plan* p, int64_t* sizes /* [PNMN_SZ_COUNT] */);
+/* statistics: [0] #valid programs, [1] #3x3 conv instances, [2] #module tokens executed,
+ * [3] forward launches, [4] backward launches, [5] algorithmic forward FLOPs of the module convs */
+int pnmn_plan_stats(const pnmn_plan* p, int64_t* stats /* [8] */);
+
+typedef struct pnmn_buffers {
+  float* arena16;
+  float* arena18;
+  float* arena22;
+  float* maps;
+  float* dmaps;
+  int32_t* idx;
+  void* blob;        /* device */
+  float* packed;     /* device, pnmn_model_packed_floats() floats */
+  const float* params; /* device, flat fp32 parameters */
+  float* grads;      /* device, flat fp32 gradients (same offsets), may be NULL for forward */
+} pnmn_buffers;
+
+/* Forward of stem + module executor: replaces NeuralModuleNetwork.forward up to the tensor that
+ * enters the classifier (probnmn/models/nmn.py:183-241).  features: device fp32 NCHW
+ * [B][in_channels][14][14].  final_out: device fp32 NCHW [B][128][14][14] (zeros for invalid
+ * programs, nmn.py:236).  stream: cudaStream_t. */
+int pnmn_nmn_forward(pnmn_plan* p, const pnmn_buffers* bufs, const float* features, float* final_out,
+                     void* stream);
+/* Backward of the same: grad_final_out is d(loss)/d(final_out) [B][128][14][14]; gradients of all
+ * stem and module parameters are ACCUMULATED into bufs->grads (autograd semantics). */
+int pnmn_nmn_backward(pnmn_plan* p, const pnmn_buffers* bufs, const float* grad_final_out, void* stream);
+
+/* ---- bring-up entry points used by tests/ (kernel-level parity against torch) ---------------- */
+int pnmn_debug_launch_conv(const void* tasks_host, int n_tasks, const void* cfgs_host, int n_cfgs,
+                           int variant, int impl_simt, void* stream);
+int pnmn_debug_launch_wgrad(const void* tasks_host, int n_tasks, const void* insts_host, int n_insts,
+                            int impl_simt, void* stream);
+int pnmn_debug_pack(const void* pack_tasks_host, int n_tasks, int total_tiles, const float* params,
+                    float* packed, void* stream);
+int pnmn_debug_nchw_to_planes(const float* src, float* dst, int batch, int channels,
+                              int64_t dst_sample_stride, void* stream);
+int pnmn_debug_launch_elt(const void* tasks_host, int n_tasks, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PNMN_H_ */

@@ -1,0 +1,91 @@
+// Internal types shared by the host-side program compiler / scheduler and the CUDA kernels of
+// the NMN module executor.  Nothing here is part of the public C ABI (see include/pnmn.h).
+//
+// Activation format ("planes"): a C-channel 14x14 map is stored as C/4 planes; plane kc holds
+// channels 4kc..4kc+3 for every pixel slot, 16 bytes per slot:   buf[kc][slot][4] (fp32).
+// A slot is a position of a zero-padded SxR grid, slot = y*S + x; only y,x < 14 carry data,
+// every other slot is a permanent zero (written once when the arena is created).  The zero
+// slots are what makes a 3x3 (dilated) convolution a plain *row shift* of the MMA A operand:
+// tap (ty,tx) of dilation d reads slot + (ty*S + tx)*d, and every out-of-image read lands on a
+// zero slot of the same plane, of the previous plane, or of the staging buffer's lead gap.
+//   P16: S=16, 256 slots  (dilation 1, 2)      P18: S=18, 324 slots (dilation 4)
+//   P22: S=22, 484 slots  (dilation 8)
+#pragma once
+#include <cstdint>
+
+namespace pnmn {
+
+constexpr int kHW = 14;          // spatial size of the ResNet-101 stage-3 feature map
+constexpr int kC = 128;          // module channels
+constexpr int kKC = kC / 4;      // planes per 128-channel activation
+constexpr int NSMAX = 2;         // samples per conv CTA (share one weight stream)
+
+struct PlaneFmt {
+  int S;  // row stride in slots
+  int P;  // slots per plane
+};
+constexpr PlaneFmt kP16{16, 256};
+constexpr PlaneFmt kP18{18, 324};
+constexpr PlaneFmt kP22{22, 484};
+
+inline PlaneFmt fmt_for_dilation(int d) {
+  return d <= 2 ? PlaneFmt{16, 256} : (d == 4 ? PlaneFmt{18, 324} : PlaneFmt{22, 484});
+}
+
+// ---- conv (forward / dgrad) --------------------------------------------------------------------
+enum ConvFlags : int {
+  F_BIAS = 1,     // y = acc + bias[n]
+  F_RELU = 2,     // y = max(y, 0)
+  F_STORE = 4,    // write y (tf32-rounded) to out[]
+  F_DOTSIG = 8,   // map_out[slot] = sigmoid(sum_n y[n]*w3[n] + b3)   (fused 1x1 conv + sigmoid)
+  F_MASK = 16,    // y = aux[n] > 0 ? y : 0                            (ReLU backward)
+  F_ACCUM = 32,   // y += out[] (existing contents)
+};
+
+struct ConvCfg {
+  int n_kb;        // number of 16-channel k-blocks (K = n_kb*16*ntaps)
+  int kb_per_in;   // k-blocks taken from each input tensor (n_kb / kb_per_in inputs, <= 2)
+  int ntaps;       // 9 (3x3) or 1 (1x1)
+  int dil;         // dilation
+  int S_in, P_in;  // plane format of the input(s)
+  int S_out, P_out;
+  int S_aux, P_aux;
+  int flags;
+  int lead;        // zero lead gap (slots) in front of each sample's staged planes
+};
+
+struct ConvTask {
+  const float* in[2][NSMAX];  // [input][sample] -> plane 0 of that input
+  float* out[NSMAX];
+  const float* aux[NSMAX];    // ReLU-mask source
+  float* map_out[NSMAX];      // P16 attention map (F_DOTSIG)
+  const float* w;             // packed weight tiles: [kb][tap][kc(4)][n(128)][4]
+  const float* bias;          // [128]
+  const float* w3;            // [128]
+  const float* b3;            // [1]
+  int cfg;
+  int n_samp;
+  int64_t pad_;
+};
+static_assert(sizeof(ConvTask) == 128, "ConvTask must stay 128 bytes");
+
+// ---- wgrad ---------------------------------------------------------------------------------------
+struct WgradInst {
+  const float* dz;  // gradient wrt the conv's pre-activation, input-format planes [32][P][4]
+  const float* x;   // the conv's input, same plane format, plane 0 of the cin tile
+};
+struct WgradTask {
+  const WgradInst* inst;  // device array
+  int n_inst;
+  int tap_row;      // 0..2 (ty+1) for 3x3, 0 for 1x1
+  int ntaps_x;      // 3 or 1
+  int dil;
+  int S, P;         // plane format of dz and x
+  int cin_total;    // Cin of the weight tensor (row stride of dW in the reference layout)
+  int cin0;         // first input channel of this 128-wide tile
+  int ksize;        // 3 or 1
+  float* dw;        // reference-layout gradient: [cout][cin_total][k][k]
+  int pad_;
+};
+
+}  // namespace pnmn

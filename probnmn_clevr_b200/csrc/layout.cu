@@ -1,0 +1,76 @@
+// Layout kernels: reference-layout parameters / NCHW features  <->  executor formats.
+#include "executor.h"
+#include "layout.h"
+#include "tcgen05.cuh"
+
+namespace pnmn {
+
+// Packed weight tile (the tcgen05 B operand, K-major, no swizzle):
+//   dst[((kb*ntaps + tap)*4 + kc)*128*4 + n*4 + e] = tf32( src[(k_off + kb*16 + kc*4 + e)*k_stride
+//                                                           + (n_off + n)*n_stride + tap'*tap_stride] )
+// with tap' = flip ? ntaps-1-tap : tap.  Forward conv: k = cin, n = cout; dgrad: k = cout, n = cin and
+// the taps are mirrored (a correlation with the transposed, flipped kernel).
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackTask* __restrict__ tasks,
+                                                           const float* __restrict__ params,
+                                                           float* __restrict__ packed, int n_tasks) {
+  // blockIdx.x enumerates tiles of all tasks; tasks carry their first global tile index (sorted)
+  int task = 0;
+  int tile = blockIdx.x;
+  {
+    int lo = 0, hi = n_tasks;
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (tasks[mid].first_tile <= tile) lo = mid; else hi = mid;
+    }
+    task = lo;
+  }
+  const PackTask t = tasks[task];
+  tile -= t.first_tile;
+  const int kb = tile / t.ntaps, tap = tile % t.ntaps;
+  const int tp = t.flip ? t.ntaps - 1 - tap : tap;
+  const float* src = params + t.src_off;
+  float* dst = packed + t.dst_off + static_cast<size_t>(tile) * 2048;
+  for (int i = threadIdx.x; i < 2048; i += 256) {
+    const int e = i & 3, n = (i >> 2) & 127, kc = i >> 9;
+    const int k = t.k_off + kb * 16 + kc * 4 + e;
+    dst[i] = to_tf32(src[static_cast<size_t>(k) * t.k_stride + static_cast<size_t>(t.n_off + n) * t.n_stride +
+                         static_cast<size_t>(tp) * t.tap_stride]);
+  }
+}
+
+cudaError_t launch_pack(const PackTask* d_tasks, int n_tasks, int total_tiles, const float* params,
+                        float* packed, cudaStream_t stream) {
+  if (total_tiles <= 0) return cudaSuccess;
+  pack_weights_kernel<<<total_tiles, 256, 0, stream>>>(d_tasks, params, packed, n_tasks);
+  return cudaGetLastError();
+}
+
+// NCHW fp32 features [B][C][14][14]  ->  planes [C/4][P16][4] (tf32-rounded, valid slots only).
+// dst_off[b] = float offset of sample b's first plane inside `dst`, or < 0 to skip the sample
+// (invalid program: its stem is never executed).
+__global__ void __launch_bounds__(256) nchw_to_planes_kernel(const float* __restrict__ src, float* __restrict__ dst,
+                                                             int C, const int64_t* __restrict__ dst_off) {
+  const int b = blockIdx.y;
+  const int kc = blockIdx.x;  // plane
+  const int64_t off = dst_off[b];
+  if (off < 0) return;
+  const float* s = src + (static_cast<size_t>(b) * C + kc * 4) * 196;
+  float* d = dst + off + static_cast<size_t>(kc) * 256 * 4;
+  __shared__ float tile[4 * 196];
+  for (int i = threadIdx.x; i < 4 * 196; i += 256) tile[i] = s[i];
+  __syncthreads();
+  if (threadIdx.x < 196) {
+    const int p = threadIdx.x, slot = (p / kHW) * 16 + (p % kHW);
+    float4 v = make_float4(to_tf32(tile[p]), to_tf32(tile[196 + p]), to_tf32(tile[392 + p]), to_tf32(tile[588 + p]));
+    *reinterpret_cast<float4*>(d + slot * 4) = v;
+  }
+}
+
+cudaError_t launch_nchw_to_planes(const float* src, float* dst, int B, int C, const int64_t* dst_off,
+                                  cudaStream_t stream) {
+  if (B <= 0) return cudaSuccess;
+  nchw_to_planes_kernel<<<dim3(C / 4, B), 256, 0, stream>>>(src, dst, C, dst_off);
+  return cudaGetLastError();
+}
+
+}  // namespace pnmn

@@ -1,0 +1,994 @@
+// Host side of the NMN module executor: model description, program compiler, level scheduler and
+// the C ABI (include/pnmn.h).
+//
+// The reference walks every sample's program in python, one tiny batch-1 kernel at a time, with a
+// device->host sync per sample (probnmn/models/nmn.py:191-238).  Here the whole batch is compiled
+// once on the host into task tables: every sample becomes a chain of stages (elementwise op, conv
+// on the tensor cores), chains are aligned into global steps, conv stages of the same step that
+// use the SAME weights are paired into one CTA (shared weight stream), and each step is at most
+// three launches.  The backward chain is derived from the same symbolic execution; weight
+// gradients are batched per weight tensor over all its instances in the batch.
+#include <algorithm>
+#include <array>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pnmn.h"
+#include "layout.h"
+
+using namespace pnmn;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(const std::string& s) {
+  g_err = s;
+  return 1;
+}
+#define CUDA_OK(x)                                                                  \
+  do {                                                                              \
+    cudaError_t e_ = (x);                                                           \
+    if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+// ---- symbolic pointers: (arena id << 56) | byte offset, resolved at launch time ----------------
+enum ArenaId : int {
+  AR_NULL = 0, AR_A16, AR_A18, AR_A22, AR_MAPS, AR_DMAPS, AR_IDX, AR_PACKED, AR_PARAMS, AR_GRADS,
+  AR_BLOB, AR_FINAL, AR_GRADOUT, AR_COUNT
+};
+template <class T>
+T* sym(int arena, int64_t byte_off) {
+  return reinterpret_cast<T*>((static_cast<uint64_t>(arena) << 56) | static_cast<uint64_t>(byte_off));
+}
+template <class T>
+void resolve(T*& p, const uint64_t* base) {
+  const uint64_t v = reinterpret_cast<uint64_t>(p);
+  if (v == 0) return;
+  p = reinterpret_cast<T*>(base[v >> 56] + (v & ((1ull << 56) - 1)));
+}
+
+constexpr int64_t kGuard = 16384;  // zero bytes in front of unit 0 of every plane arena
+constexpr int64_t kUnit16 = 32ll * 256 * 16;
+constexpr int64_t kUnit18 = 32ll * 324 * 16;
+constexpr int64_t kUnit22 = 32ll * 484 * 16;
+constexpr int kInstChunk = 16;     // instances per wgrad CTA
+constexpr int kBiasSplit = 8;
+
+struct ConvW {
+  int64_t w_off = -1, b_off = -1;  // floats into the flat parameter buffer
+  int cin = 128, ksize = 3;
+  int64_t pk_fwd = -1, pk_bwd = -1;  // floats into the packed buffer
+};
+struct ModuleDesc {
+  int kind = PNMN_TOK_SKIP;
+  std::vector<int> convs;          // ids into pnmn_model::convs (MMA convs, forward order)
+  int64_t head_w = -1, head_b = -1;  // 1x1 -> 1 head (Attention/Relate) or SameModule.conv
+};
+
+}  // namespace
+
+struct pnmn_model {
+  int V = 0, in_ch = 1024;
+  std::vector<ModuleDesc> mods;
+  std::vector<ConvW> convs;
+  int stem1 = -1, stem2 = -1;
+  std::vector<PackTask> pack;
+  int total_tiles = 0;
+  int64_t packed_floats = 0;
+};
+
+namespace {
+
+int add_conv_w(pnmn_model* m, int64_t w, int64_t b, int cin, int ksize, bool need_bwd) {
+  ConvW c;
+  c.w_off = w; c.b_off = b; c.cin = cin; c.ksize = ksize;
+  const int kk = ksize * ksize;
+  auto add_pack = [&](int n_kb, int flip, int k_off, int n_off, int ks, int ns, int ts) {
+    PackTask t{};
+    t.src_off = w; t.dst_off = m->packed_floats; t.first_tile = m->total_tiles;
+    t.n_kb = n_kb; t.ntaps = kk; t.flip = flip; t.k_off = k_off; t.n_off = n_off;
+    t.k_stride = ks; t.n_stride = ns; t.tap_stride = ts;
+    m->pack.push_back(t);
+    const int64_t off = m->packed_floats;
+    m->total_tiles += n_kb * kk;
+    m->packed_floats += static_cast<int64_t>(n_kb) * kk * 2048;
+    return off;
+  };
+  // forward: k = cin, n = cout.  W[n][k][tap]
+  c.pk_fwd = add_pack(cin / 16, 0, 0, 0, kk, cin * kk, kk == 1 ? 0 : 1);
+  if (need_bwd) {
+    // dgrad: k = cout (128), n = cin tile; one 8-k-block pack per 128 input channels
+    c.pk_bwd = m->packed_floats;
+    for (int h = 0; h < cin / 128; ++h) add_pack(8, 1, 0, 128 * h, cin * kk, kk, kk == 1 ? 0 : 1);
+  }
+  m->convs.push_back(c);
+  return static_cast<int>(m->convs.size()) - 1;
+}
+
+}  // namespace
+
+extern "C" int pnmn_version(void) { return PNMN_VERSION; }
+extern "C" const char* pnmn_last_error(void) { return g_err.c_str(); }
+
+extern "C" pnmn_model* pnmn_model_create(int vocab_size, const int32_t* token_kind,
+                                         const int64_t* token_param_off, const int64_t* stem_param_off,
+                                         int in_channels) {
+  if (in_channels % 128 != 0) { g_err = "in_channels must be a multiple of 128"; return nullptr; }
+  auto* m = new pnmn_model();
+  m->V = vocab_size;
+  m->in_ch = in_channels;
+  m->mods.resize(vocab_size);
+  m->stem1 = add_conv_w(m, stem_param_off[0], stem_param_off[1], in_channels, 3, false);
+  m->stem2 = add_conv_w(m, stem_param_off[2], stem_param_off[3], 128, 3, true);
+  for (int v = 0; v < vocab_size; ++v) {
+    ModuleDesc& d = m->mods[v];
+    d.kind = token_kind[v];
+    const int64_t* po = token_param_off + static_cast<size_t>(v) * PNMN_MAX_MODULE_PARAMS;
+    auto conv3 = [&](int i) { d.convs.push_back(add_conv_w(m, po[2 * i], po[2 * i + 1], 128, 3, true)); };
+    switch (d.kind) {
+      case PNMN_TOK_ATTENTION: conv3(0); conv3(1); d.head_w = po[4]; d.head_b = po[5]; break;
+      case PNMN_TOK_QUERY: conv3(0); conv3(1); break;
+      case PNMN_TOK_RELATE: for (int i = 0; i < 5; ++i) conv3(i); d.head_w = po[10]; d.head_b = po[11]; break;
+      case PNMN_TOK_SAME: d.head_w = po[0]; d.head_b = po[1]; break;
+      case PNMN_TOK_COMPARE:
+        d.convs.push_back(add_conv_w(m, po[0], po[1], 256, 1, true));
+        conv3(1); conv3(2);
+        break;
+      default: break;
+    }
+  }
+  return m;
+}
+extern "C" void pnmn_model_destroy(pnmn_model* m) { delete m; }
+extern "C" int64_t pnmn_model_packed_floats(const pnmn_model* m) { return m->packed_floats; }
+
+// =================================================================================================
+// Plan
+// =================================================================================================
+namespace {
+
+enum ValKind { VK_FEAT, VK_ONES, VK_MAP, VK_BUF };
+struct Val {
+  int kind = VK_BUF;
+  int ch = 128;
+  int unit = -1;        // A16 unit (FEAT/BUF) or map index (MAP/ONES)
+  bool relu_out = false;
+  int ncons = 0;        // live consumers (backward)
+  int gunit = -1;       // A16 unit of the gradient (128-ch values)
+  bool gwritten = false;
+  bool live = false;
+  bool cons_minmax = false;
+};
+struct OpRec {
+  int kind = 0, tok = 0;
+  int in0 = -1, in1 = -1, out = -1;  // value ids
+  bool x0_is_feat = false;
+  int x0_unit = -1;                  // attended features (A16)
+  int nconv = 0;
+  int y_unit[5] = {-1, -1, -1, -1, -1};  // conv outputs (arena of the NEXT conv's input format)
+  int idx_slot = -1;
+};
+
+enum LaunchKind { LK_ELT = 0, LK_CONV0 = 1, LK_CONV1 = 2, LK_WGRAD = 3, LK_BIAS = 4 };
+struct LaunchItem { int kind; int64_t off; int count; };
+
+struct ConvProto {
+  ConvTask t;
+  int sample;
+};
+
+struct Sched {
+  std::vector<int> step, last;
+  std::vector<std::array<std::vector<int>, 3>> buckets;  // indices into elts / protos
+  std::vector<EltTask> elts;
+  std::vector<ConvProto> protos;
+  explicit Sched(int B) : step(B, 0), last(B, -1) {}
+  int place(int s, int kind) {
+    if (kind <= last[s]) step[s]++;
+    last[s] = kind;
+    if (static_cast<int>(buckets.size()) <= step[s]) buckets.resize(step[s] + 1);
+    return step[s];
+  }
+  void add_elt(int s, const EltTask& t) {
+    const int st = place(s, LK_ELT);
+    buckets[st][LK_ELT].push_back(static_cast<int>(elts.size()));
+    elts.push_back(t);
+  }
+  void add_conv(int s, const ConvTask& t, int variant) {
+    const int kind = variant == 0 ? LK_CONV0 : LK_CONV1;
+    const int st = place(s, kind);
+    buckets[st][kind].push_back(static_cast<int>(protos.size()));
+    protos.push_back(ConvProto{t, s});
+  }
+  // Flatten into launch order; conv tasks of one step that share (cfg, weights) are paired.
+  void flatten(std::vector<EltTask>& out_elt, std::vector<ConvTask>& out_conv, std::vector<LaunchItem>& launches) {
+    for (auto& b : buckets) {
+      if (!b[LK_ELT].empty()) {
+        launches.push_back({LK_ELT, static_cast<int64_t>(out_elt.size()), static_cast<int>(b[LK_ELT].size())});
+        for (int i : b[LK_ELT]) out_elt.push_back(elts[i]);
+      }
+      for (int kind = LK_CONV0; kind <= LK_CONV1; ++kind) {
+        auto& v = b[kind];
+        if (v.empty()) continue;
+        std::stable_sort(v.begin(), v.end(), [&](int x, int y) {
+          const ConvTask& a = protos[x].t; const ConvTask& c = protos[y].t;
+          if (a.cfg != c.cfg) return a.cfg < c.cfg;
+          return reinterpret_cast<uint64_t>(a.w) < reinterpret_cast<uint64_t>(c.w);
+        });
+        const int64_t off = static_cast<int64_t>(out_conv.size());
+        const int cap = kind == LK_CONV0 ? NSMAX : 1;
+        size_t i = 0;
+        while (i < v.size()) {
+          ConvTask t = protos[v[i]].t;
+          t.n_samp = 1;
+          size_t j = i + 1;
+          while (j < v.size() && t.n_samp < cap && protos[v[j]].t.cfg == t.cfg && protos[v[j]].t.w == t.w) {
+            const ConvTask& o = protos[v[j]].t;
+            const int k = t.n_samp++;
+            t.in[0][k] = o.in[0][0]; t.in[1][k] = o.in[1][0];
+            t.out[k] = o.out[0]; t.aux[k] = o.aux[0]; t.map_out[k] = o.map_out[0];
+            ++j;
+          }
+          out_conv.push_back(t);
+          i = j;
+        }
+        launches.push_back({kind, off, static_cast<int>(out_conv.size() - off)});
+      }
+    }
+  }
+};
+
+}  // namespace
+
+struct pnmn_plan {
+  const pnmn_model* m = nullptr;
+  int B = 0, L = 0;
+  bool need_grad = false;
+  std::vector<uint8_t> valid;
+  int64_t n16 = 0, n18 = 0, n22 = 0, nmaps = 0, nidx = 0;
+  std::vector<ConvCfg> cfgs;
+  std::vector<ConvTask> fconv, bconv;
+  std::vector<EltTask> felt, belt;
+  std::vector<LaunchItem> flaunch, blaunch;
+  std::vector<WgradInst> insts;
+  std::vector<WgradTask> wtasks;
+  std::vector<BiasGradTaskH> btasks;
+  std::vector<int> xin_unit;  // per sample, -1 if the stem is skipped (invalid program)
+  // blob layout (bytes)
+  int64_t off_cfg = 0, off_xin = 0, off_fconv = 0, off_felt = 0, off_bconv = 0, off_belt = 0, off_inst = 0, off_wt = 0,
+          off_bt = 0, blob_bytes = 0;
+  int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<uint8_t> host_blob;
+};
+
+namespace {
+
+struct Builder {
+  pnmn_plan& p;
+  const pnmn_model& m;
+  std::vector<Val> vals;
+  std::vector<std::vector<WgradInst>> conv_insts;  // per model conv id
+  std::vector<PlaneFmt> conv_inst_fmt;
+  std::vector<int> conv_inst_dil;
+
+  Builder(pnmn_plan& plan) : p(plan), m(*plan.m), conv_insts(plan.m->convs.size()),
+                             conv_inst_fmt(plan.m->convs.size(), kP16), conv_inst_dil(plan.m->convs.size(), 1) {}
+
+  int alloc16(int n = 1) { const int u = static_cast<int>(p.n16); p.n16 += n; return u; }
+  int alloc_fmt(PlaneFmt f) {
+    if (f.P == kP16.P) return alloc16();
+    if (f.P == kP18.P) return static_cast<int>(p.n18++);
+    return static_cast<int>(p.n22++);
+  }
+  float* pfmt(PlaneFmt f, int unit) const {
+    if (f.P == kP16.P) return sym<float>(AR_A16, kGuard + unit * kUnit16);
+    if (f.P == kP18.P) return sym<float>(AR_A18, kGuard + unit * kUnit18);
+    return sym<float>(AR_A22, kGuard + unit * kUnit22);
+  }
+  float* p16(int unit) const { return pfmt(kP16, unit); }
+  float* mapp(int i) const { return sym<float>(AR_MAPS, static_cast<int64_t>(i) * 1024); }
+  float* dmapp(int i) const { return sym<float>(AR_DMAPS, static_cast<int64_t>(i) * 1024); }
+  const float* param(int64_t off) const { return sym<const float>(AR_PARAMS, off * 4); }
+  float* grad(int64_t off) const { return sym<float>(AR_GRADS, off * 4); }
+  const float* packed(int64_t off) const { return sym<const float>(AR_PACKED, off * 4); }
+
+  int cfg_id(const ConvCfg& c) {
+    for (size_t i = 0; i < p.cfgs.size(); ++i)
+      if (std::memcmp(&p.cfgs[i], &c, sizeof(ConvCfg)) == 0) return static_cast<int>(i);
+    p.cfgs.push_back(c);
+    return static_cast<int>(p.cfgs.size()) - 1;
+  }
+  int make_cfg(int n_kb, int kb_per_in, int ntaps, int dil, PlaneFmt in, PlaneFmt out, PlaneFmt aux, int flags) {
+    ConvCfg c;
+    std::memset(&c, 0, sizeof(c));
+    c.n_kb = n_kb; c.kb_per_in = kb_per_in; c.ntaps = ntaps; c.dil = dil;
+    c.S_in = in.S; c.P_in = in.P; c.S_out = out.S; c.P_out = out.P; c.S_aux = aux.S; c.P_aux = aux.P;
+    c.flags = flags;
+    c.lead = ntaps == 9 ? ((dil * in.S + dil + 7) / 8) * 8 : 8;
+    return cfg_id(c);
+  }
+
+  int new_val(int kind, int ch, int unit, bool relu_out) {
+    Val v; v.kind = kind; v.ch = ch; v.unit = unit; v.relu_out = relu_out;
+    vals.push_back(v);
+    return static_cast<int>(vals.size()) - 1;
+  }
+};
+
+static const int kRelateDil[5] = {1, 2, 4, 8, 1};
+
+}  // namespace
+
+extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* programs, int B, int L, int need_grad) {
+  auto* plan = new pnmn_plan();
+  pnmn_plan& p = *plan;
+  p.m = m; p.B = B; p.L = L; p.need_grad = need_grad != 0;
+  p.valid.assign(B, 0);
+  p.xin_unit.assign(B, -1);
+  Builder bd(p);
+  Sched fs(B), bs(B);
+  const int in_units = m->in_ch / 128;
+
+  p.nmaps = 1;  // map 0 = the constant all-ones attention of `scene` (nmn.py:216)
+  const int ones_val = bd.new_val(VK_ONES, 1, 0, false);
+  bool ones_emitted = false;
+
+  std::vector<int> feat_unit(B, -1), y1s_unit(B, -1), dfeat_unit(B, -1);
+  int64_t n_conv3 = 0, n_tokens = 0, flops = 0;
+
+  for (int n = 0; n < B; ++n) {
+    // ---------------- symbolic execution (nmn.py:198-233) ----------------
+    const size_t val_mark = bd.vals.size();
+    const int feat_val = bd.new_val(VK_FEAT, 128, -1, true);
+    std::vector<OpRec> ops;
+    int out = feat_val, saved = -1;
+    bool ok = true;
+    for (int i = L - 1; i >= 0 && ok; --i) {
+      const int64_t tok = programs[static_cast<size_t>(n) * L + i];
+      if (tok < 0 || tok >= m->V) { ok = false; break; }  // vocabulary lookup raises -> invalid
+      const ModuleDesc& md = m->mods[tok];
+      switch (md.kind) {
+        case PNMN_TOK_SKIP: break;
+        case PNMN_TOK_SCENE: saved = out; out = ones_val; break;
+        case PNMN_TOK_AND:
+        case PNMN_TOK_OR: {
+          if (saved < 0) { ok = false; break; }
+          OpRec r; r.kind = md.kind; r.tok = static_cast<int>(tok); r.in0 = out; r.in1 = saved;
+          const int ch = std::max(bd.vals[out].ch, bd.vals[saved].ch);
+          r.out = bd.new_val(ch == 1 ? VK_MAP : VK_BUF, ch, -1, false);
+          ops.push_back(r); out = r.out;
+        } break;
+        case PNMN_TOK_COMPARE: {
+          if (saved < 0 || bd.vals[out].ch != 128 || bd.vals[saved].ch != 128) { ok = false; break; }
+          OpRec r; r.kind = md.kind; r.tok = static_cast<int>(tok); r.in0 = out; r.in1 = saved; r.nconv = 3;
+          r.out = bd.new_val(VK_BUF, 128, -1, true);
+          ops.push_back(r); out = r.out;
+        } break;
+        case PNMN_TOK_QUERY:
+        case PNMN_TOK_RELATE:
+        case PNMN_TOK_SAME:
+        case PNMN_TOK_ATTENTION: {
+          if (bd.vals[out].ch != 1) { ok = false; break; }
+          OpRec r; r.kind = md.kind; r.tok = static_cast<int>(tok); r.in0 = out;
+          r.nconv = md.kind == PNMN_TOK_RELATE ? 5 : (md.kind == PNMN_TOK_SAME ? 0 : 2);
+          r.out = md.kind == PNMN_TOK_QUERY ? bd.new_val(VK_BUF, 128, -1, true) : bd.new_val(VK_MAP, 1, -1, false);
+          ops.push_back(r); out = r.out;
+        } break;
+        default: ok = false; break;
+      }
+    }
+    if (ok && bd.vals[out].ch != 128) ok = false;  // nmn.py:231-232
+    if (!ok) {
+      bd.vals.resize(val_mark);
+      EltTask g{}; g.op = OP_GATHER; g.a = nullptr;
+      g.o = sym<float>(AR_FINAL, static_cast<int64_t>(n) * 128 * 196 * 4);
+      fs.add_elt(n, g);
+      continue;
+    }
+    p.valid[n] = 1;
+    p.stats[0]++;
+
+    // ---------------- stem (nmn.py:67-72,183) ----------------
+    const int xin = bd.alloc16(in_units);
+    p.xin_unit[n] = xin;
+    y1s_unit[n] = bd.alloc16();
+    feat_unit[n] = bd.alloc16();
+    bd.vals[feat_val].unit = feat_unit[n];
+    if (!ones_emitted) {
+      ones_emitted = true;  // the all-ones map is (re)written by the first valid sample's chain
+    }
+    {
+      const ConvW& c1 = m->convs[m->stem1];
+      ConvTask t{};
+      t.cfg = bd.make_cfg(m->in_ch / 16, m->in_ch / 16, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE);
+      t.in[0][0] = bd.p16(xin); t.out[0] = bd.p16(y1s_unit[n]);
+      t.w = bd.packed(c1.pk_fwd); t.bias = bd.param(c1.b_off);
+      fs.add_conv(n, t, 0);
+      const ConvW& c2 = m->convs[m->stem2];
+      ConvTask u{};
+      u.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE);
+      u.in[0][0] = bd.p16(y1s_unit[n]); u.out[0] = bd.p16(feat_unit[n]);
+      u.w = bd.packed(c2.pk_fwd); u.bias = bd.param(c2.b_off);
+      fs.add_conv(n, u, 0);
+    }
+    const float* featp = bd.p16(feat_unit[n]);
+
+    // ---------------- forward stages ----------------
+    for (OpRec& r : ops) {
+      const ModuleDesc& md = m->mods[r.tok];
+      n_tokens++;
+      switch (r.kind) {
+        case PNMN_TOK_AND:
+        case PNMN_TOK_OR: {
+          Val& vo = bd.vals[r.out];
+          const Val& a = bd.vals[r.in0]; const Val& b = bd.vals[r.in1];
+          EltTask e{}; e.op = OP_MINMAX;
+          e.flags = (r.kind == PNMN_TOK_OR ? EF_MAX : 0) | (a.ch == 1 ? EF_A_MAP : 0) | (b.ch == 1 ? EF_B_MAP : 0);
+          e.a = a.ch == 1 ? bd.mapp(a.unit) : bd.p16(a.unit);
+          e.b = b.ch == 1 ? bd.mapp(b.unit) : bd.p16(b.unit);
+          if (vo.ch == 1) { vo.unit = static_cast<int>(p.nmaps++); e.o = bd.mapp(vo.unit); }
+          else { vo.unit = bd.alloc16(); e.o = bd.p16(vo.unit); }
+          fs.add_elt(n, e);
+        } break;
+        case PNMN_TOK_SAME: {
+          Val& vo = bd.vals[r.out];
+          vo.unit = static_cast<int>(p.nmaps++);
+          r.idx_slot = static_cast<int>(p.nidx++);
+          EltTask e{}; e.op = OP_SAME;
+          e.a = featp; e.b = bd.mapp(bd.vals[r.in0].unit);
+          e.w = bd.param(md.head_w); e.c = bd.param(md.head_b);
+          e.o = bd.mapp(vo.unit); e.idx = sym<int>(AR_IDX, static_cast<int64_t>(r.idx_slot) * 4);
+          fs.add_elt(n, e);
+        } break;
+        case PNMN_TOK_COMPARE: {
+          Val& vo = bd.vals[r.out];
+          const ConvW& pj = m->convs[md.convs[0]];
+          r.y_unit[0] = bd.alloc16(); r.y_unit[1] = bd.alloc16(); r.y_unit[2] = bd.alloc16();
+          vo.unit = r.y_unit[2];
+          ConvTask t{};
+          t.cfg = bd.make_cfg(16, 8, 1, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE);
+          t.in[0][0] = bd.p16(bd.vals[r.in0].unit); t.in[1][0] = bd.p16(bd.vals[r.in1].unit);
+          t.out[0] = bd.p16(r.y_unit[0]); t.w = bd.packed(pj.pk_fwd); t.bias = bd.param(pj.b_off);
+          fs.add_conv(n, t, 0);
+          flops += 2ll * 196 * 128 * 256;
+          for (int i = 1; i < 3; ++i) {
+            const ConvW& cw = m->convs[md.convs[i]];
+            ConvTask u{};
+            u.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE);
+            u.in[0][0] = bd.p16(r.y_unit[i - 1]); u.out[0] = bd.p16(r.y_unit[i]);
+            u.w = bd.packed(cw.pk_fwd); u.bias = bd.param(cw.b_off);
+            fs.add_conv(n, u, 0);
+            n_conv3++;
+          }
+        } break;
+        default: {  // ATTENTION / QUERY / RELATE
+          const Val& a = bd.vals[r.in0];
+          const float* x = featp;
+          if (a.kind == VK_ONES) {
+            r.x0_is_feat = true;  // feats * ones == feats: feed the stem output straight in
+          } else {
+            r.x0_unit = bd.alloc16();
+            EltTask e{}; e.op = OP_ATTEND; e.a = featp; e.b = bd.mapp(a.unit); e.o = bd.p16(r.x0_unit);
+            fs.add_elt(n, e);
+            x = bd.p16(r.x0_unit);
+          }
+          const bool head = r.kind != PNMN_TOK_QUERY;
+          Val& vo = bd.vals[r.out];
+          for (int i = 0; i < r.nconv; ++i) {
+            const int d = r.kind == PNMN_TOK_RELATE ? kRelateDil[i] : 1;
+            const int dn = (r.kind == PNMN_TOK_RELATE && i + 1 < r.nconv) ? kRelateDil[i + 1] : 1;
+            const PlaneFmt fin = fmt_for_dilation(d), fout = fmt_for_dilation(dn);
+            const ConvW& cw = m->convs[md.convs[i]];
+            const bool last = i + 1 == r.nconv;
+            r.y_unit[i] = bd.alloc_fmt(fout);
+            ConvTask t{};
+            t.cfg = bd.make_cfg(8, 8, 9, d, fin, fout, fout, F_BIAS | F_RELU | F_STORE | ((last && head) ? F_DOTSIG : 0));
+            t.in[0][0] = x; t.out[0] = bd.pfmt(fout, r.y_unit[i]);
+            t.w = bd.packed(cw.pk_fwd); t.bias = bd.param(cw.b_off);
+            if (last && head) {
+              vo.unit = static_cast<int>(p.nmaps++);
+              t.map_out[0] = bd.mapp(vo.unit);
+              t.w3 = bd.param(md.head_w); t.b3 = bd.param(md.head_b);
+              flops += 2ll * 196 * 128;
+            }
+            fs.add_conv(n, t, fin.P == kP22.P ? 1 : 0);
+            x = t.out[0];
+            n_conv3++;
+          }
+          if (!head) vo.unit = r.y_unit[r.nconv - 1];
+        } break;
+      }
+    }
+    {
+      EltTask g{}; g.op = OP_GATHER; g.a = bd.p16(bd.vals[out].unit);
+      g.o = sym<float>(AR_FINAL, static_cast<int64_t>(n) * 128 * 196 * 4);
+      fs.add_elt(n, g);
+    }
+    if (!p.need_grad) continue;
+
+    // ---------------- liveness / consumer counts ----------------
+    bd.vals[out].live = true; bd.vals[out].ncons = 1;
+    for (int k = static_cast<int>(ops.size()) - 1; k >= 0; --k) {
+      const OpRec& r = ops[k];
+      if (!bd.vals[r.out].live) continue;
+      for (int in : {r.in0, r.in1}) {
+        if (in < 0 || bd.vals[in].kind == VK_ONES) continue;
+        bd.vals[in].live = true;
+        bd.vals[in].ncons++;
+        if (r.kind == PNMN_TOK_AND || r.kind == PNMN_TOK_OR) bd.vals[in].cons_minmax = true;
+      }
+    }
+    dfeat_unit[n] = bd.alloc16();
+    bd.vals[feat_val].gunit = dfeat_unit[n];
+    const float* dfeatp = bd.p16(dfeat_unit[n]);
+    auto fused_mask = [&](const Val& v) { return v.relu_out && v.kind == VK_BUF && v.ncons == 1 && !v.cons_minmax; };
+    auto gbuf = [&](Val& v) -> float* {
+      if (v.gunit < 0) v.gunit = bd.alloc16();
+      return bd.p16(v.gunit);
+    };
+    auto add_inst = [&](int conv_id, const float* dz, const float* x, PlaneFmt f, int dil) {
+      bd.conv_insts[conv_id].push_back(WgradInst{dz, x});
+      bd.conv_inst_fmt[conv_id] = f;
+      bd.conv_inst_dil[conv_id] = dil;
+    };
+
+    // ---------------- backward stages ----------------
+    {  // d(final module output) arrives as NCHW from the classifier
+      Val& v = bd.vals[out];
+      EltTask e{}; e.op = OP_SCATTER;
+      e.a = sym<const float>(AR_GRADOUT, static_cast<int64_t>(n) * 128 * 196 * 4);
+      e.b = fused_mask(v) ? bd.p16(v.unit) : nullptr;
+      e.o = gbuf(v); e.flags = v.gwritten ? EF_ACCUM : 0;
+      v.gwritten = true;
+      bs.add_elt(n, e);
+    }
+    for (int k = static_cast<int>(ops.size()) - 1; k >= 0; --k) {
+      OpRec& r = ops[k];
+      Val& vo = bd.vals[r.out];
+      if (!vo.live) continue;
+      const ModuleDesc& md = m->mods[r.tok];
+      // 128-channel outputs whose gradient was accumulated unmasked need the ReLU mask now
+      if (vo.kind == VK_BUF && vo.relu_out && !fused_mask(vo)) {
+        EltTask e{}; e.op = OP_RELU_MASK; e.a = bd.p16(vo.gunit); e.b = bd.p16(vo.unit); e.o = bd.p16(vo.gunit);
+        bs.add_elt(n, e);
+      }
+      switch (r.kind) {
+        case PNMN_TOK_AND:
+        case PNMN_TOK_OR: {
+          Val& a = bd.vals[r.in0]; Val& b = bd.vals[r.in1];
+          EltTask e{}; e.op = OP_MINMAX_BWD;
+          e.flags = (r.kind == PNMN_TOK_OR ? EF_MAX : 0) | (a.ch == 1 ? EF_A_MAP : 0) | (b.ch == 1 ? EF_B_MAP : 0);
+          e.a = a.ch == 1 ? bd.mapp(a.unit) : bd.p16(a.unit);
+          e.b = b.ch == 1 ? bd.mapp(b.unit) : bd.p16(b.unit);
+          e.g = vo.ch == 1 ? bd.dmapp(vo.unit) : bd.p16(vo.gunit);
+          if (a.kind != VK_ONES) {
+            if (a.ch == 1) e.o = bd.dmapp(a.unit);
+            else { e.o = gbuf(a); if (a.gwritten) e.flags |= EF_ACCUM; a.gwritten = true; }
+          }
+          if (b.kind != VK_ONES) {
+            if (b.ch == 1) e.o2 = bd.dmapp(b.unit);
+            else { e.o2 = gbuf(b); if (b.gwritten) e.flags |= EF_ACCUM2; b.gwritten = true; }
+          }
+          bs.add_elt(n, e);
+        } break;
+        case PNMN_TOK_SAME: {
+          const Val& a = bd.vals[r.in0];
+          Val& fv = bd.vals[feat_val];
+          EltTask e{}; e.op = OP_SAME_BWD;
+          e.a = featp; e.b = bd.mapp(a.unit); e.c = bd.mapp(vo.unit); e.g = bd.dmapp(vo.unit);
+          e.o = a.kind == VK_ONES ? nullptr : bd.dmapp(a.unit);
+          e.o2 = const_cast<float*>(dfeatp); e.flags = fv.gwritten ? EF_ACCUM : 0; fv.gwritten = true;
+          e.w = bd.param(md.head_w); e.dw = bd.grad(md.head_w); e.dw2 = bd.grad(md.head_b);
+          e.idx = sym<int>(AR_IDX, static_cast<int64_t>(r.idx_slot) * 4);
+          bs.add_elt(n, e);
+        } break;
+        case PNMN_TOK_COMPARE: {
+          // dZ of conv2 is the (masked) gradient of the output value
+          const float* dz = bd.p16(vo.gunit);
+          for (int i = 2; i >= 1; --i) {
+            const ConvW& cw = m->convs[md.convs[i]];
+            add_inst(md.convs[i], dz, bd.p16(r.y_unit[i - 1]), kP16, 1);
+            const int du = bd.alloc16();
+            ConvTask t{};
+            t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_STORE | F_MASK);
+            t.in[0][0] = dz; t.out[0] = bd.p16(du); t.aux[0] = bd.p16(r.y_unit[i - 1]);
+            t.w = bd.packed(cw.pk_bwd);
+            bs.add_conv(n, t, 0);
+            dz = bd.p16(du);
+          }
+          const ConvW& pj = m->convs[md.convs[0]];
+          const int ins[2] = {r.in0, r.in1};
+          for (int h = 0; h < 2; ++h) {
+            Val& v = bd.vals[ins[h]];
+            // projection wgrad: dW[:, 128h:128h+128] += dZp (x) in_h
+            bd.conv_insts[md.convs[0]].push_back(WgradInst{dz, bd.p16(v.unit)});  // even = in0, odd = in1
+            const bool fm = fused_mask(v);
+            ConvTask t{};
+            t.cfg = bd.make_cfg(8, 8, 1, 1, kP16, kP16, kP16, F_STORE | (fm ? F_MASK : 0) | (v.gwritten ? F_ACCUM : 0));
+            t.in[0][0] = dz; t.out[0] = gbuf(v); t.aux[0] = fm ? bd.p16(v.unit) : nullptr;
+            t.w = bd.packed(pj.pk_bwd + static_cast<int64_t>(h) * 8 * 2048);
+            v.gwritten = true;
+            bs.add_conv(n, t, 0);
+          }
+        } break;
+        default: {  // ATTENTION / QUERY / RELATE
+          const Val& a = bd.vals[r.in0];
+          const bool head = r.kind != PNMN_TOK_QUERY;
+          const int nc = r.nconv;
+          auto dil_of = [&](int i) { return r.kind == PNMN_TOK_RELATE ? kRelateDil[i] : 1; };
+          const float* dz;
+          if (head) {
+            const int du = bd.alloc16();
+            EltTask e{}; e.op = OP_DOTSIG_BWD;
+            e.g = bd.dmapp(vo.unit); e.c = bd.mapp(vo.unit); e.a = bd.p16(r.y_unit[nc - 1]);
+            e.w = bd.param(md.head_w); e.dw = bd.grad(md.head_w); e.dw2 = bd.grad(md.head_b);
+            e.o = bd.p16(du);
+            bs.add_elt(n, e);
+            dz = bd.p16(du);
+          } else {
+            dz = bd.p16(vo.gunit);
+          }
+          for (int i = nc - 1; i >= 0; --i) {
+            const int d = dil_of(i);
+            const PlaneFmt f = fmt_for_dilation(d);  // format of dZ_i and of conv i's input
+            const ConvW& cw = m->convs[md.convs[i]];
+            const float* xin_i = i == 0 ? (r.x0_is_feat ? featp : bd.p16(r.x0_unit)) : bd.pfmt(f, r.y_unit[i - 1]);
+            add_inst(md.convs[i], dz, xin_i, f, d);
+            ConvTask t{};
+            t.in[0][0] = dz; t.w = bd.packed(cw.pk_bwd);
+            if (i > 0) {
+              const PlaneFmt fprev = fmt_for_dilation(dil_of(i - 1));
+              const int du = bd.alloc_fmt(fprev);
+              t.cfg = bd.make_cfg(8, 8, 9, d, f, fprev, f, F_STORE | F_MASK);
+              t.out[0] = bd.pfmt(fprev, du); t.aux[0] = xin_i;
+              bs.add_conv(n, t, f.P == kP22.P ? 1 : 0);
+              dz = t.out[0];
+            } else if (r.x0_is_feat) {
+              Val& fv = bd.vals[feat_val];
+              t.cfg = bd.make_cfg(8, 8, 9, d, f, kP16, kP16, F_STORE | (fv.gwritten ? F_ACCUM : 0));
+              t.out[0] = const_cast<float*>(dfeatp);
+              fv.gwritten = true;
+              bs.add_conv(n, t, 0);
+            } else {
+              const int du = bd.alloc16();
+              t.cfg = bd.make_cfg(8, 8, 9, d, f, kP16, kP16, F_STORE);
+              t.out[0] = bd.p16(du);
+              bs.add_conv(n, t, 0);
+              Val& fv = bd.vals[feat_val];
+              EltTask e{}; e.op = OP_ATTEND_BWD;
+              e.a = bd.p16(du); e.b = featp; e.c = bd.mapp(a.unit);
+              e.o = bd.dmapp(a.unit); e.o2 = const_cast<float*>(dfeatp);
+              e.flags = fv.gwritten ? EF_ACCUM : 0; fv.gwritten = true;
+              bs.add_elt(n, e);
+            }
+          }
+        } break;
+      }
+    }
+    // ---------------- stem backward ----------------
+    if (bd.vals[feat_val].gwritten) {
+      EltTask e{}; e.op = OP_RELU_MASK; e.a = dfeatp; e.b = featp; e.o = const_cast<float*>(dfeatp);
+      bs.add_elt(n, e);
+      const int dz1 = bd.alloc16();
+      const ConvW& c2 = m->convs[m->stem2];
+      ConvTask t{};
+      t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_STORE | F_MASK);
+      t.in[0][0] = dfeatp; t.out[0] = bd.p16(dz1); t.aux[0] = bd.p16(y1s_unit[n]);
+      t.w = bd.packed(c2.pk_bwd);
+      bs.add_conv(n, t, 0);
+      add_inst(m->stem2, dfeatp, bd.p16(y1s_unit[n]), kP16, 1);
+      add_inst(m->stem1, bd.p16(dz1), bd.p16(xin), kP16, 1);
+    }
+  }
+
+  // ---------------- flatten ----------------
+  fs.flatten(p.felt, p.fconv, p.flaunch);
+  if (p.need_grad) {
+    bs.flatten(p.belt, p.bconv, p.blaunch);
+    // wgrad / bias-grad tasks per weight tensor
+    const int64_t inst_base = 0;
+    (void)inst_base;
+    for (size_t c = 0; c < m->convs.size(); ++c) {
+      const auto& v = bd.conv_insts[c];
+      if (v.empty()) continue;
+      const ConvW& cw = m->convs[c];
+      const PlaneFmt f = bd.conv_inst_fmt[c];
+      if (cw.ksize == 1) {
+        // projection: instances alternate (dz,in0),(dz,in1); split into the two 128-channel halves
+        for (int h = 0; h < 2; ++h) {
+          const int64_t first = static_cast<int64_t>(p.insts.size());
+          for (size_t i = h; i < v.size(); i += 2) p.insts.push_back(v[i]);
+          const int n_inst = static_cast<int>(p.insts.size() - first);
+          for (int i0 = 0; i0 < n_inst; i0 += kInstChunk) {
+            WgradTask t{};
+            t.inst = sym<const WgradInst>(AR_BLOB, (first + i0) * static_cast<int64_t>(sizeof(WgradInst)));
+            t.n_inst = std::min(kInstChunk, n_inst - i0);
+            t.tap_row = 0; t.ntaps_x = 1; t.dil = 1; t.S = f.S; t.P = f.P;
+            t.cin_total = 256; t.cin0 = 128 * h; t.ksize = 1; t.dw = bd.grad(cw.w_off);
+            p.wtasks.push_back(t);
+          }
+          if (h == 0) {
+            BiasGradTaskH b{};
+            b.inst = sym<const WgradInst>(AR_BLOB, first * static_cast<int64_t>(sizeof(WgradInst)));
+            b.n_inst = n_inst; b.P = f.P; b.db = bd.grad(cw.b_off);
+            p.btasks.push_back(b);
+          }
+        }
+        continue;
+      }
+      const int tiles = cw.cin / 128;
+      for (int tile = 0; tile < tiles; ++tile) {
+        const int64_t first = static_cast<int64_t>(p.insts.size());
+        for (const WgradInst& wi : v) {
+          WgradInst x = wi;
+          x.x = reinterpret_cast<const float*>(reinterpret_cast<uint64_t>(wi.x) + static_cast<uint64_t>(tile) * kUnit16);
+          p.insts.push_back(x);
+        }
+        const int n_inst = static_cast<int>(v.size());
+        for (int i0 = 0; i0 < n_inst; i0 += kInstChunk)
+          for (int ty = 0; ty < 3; ++ty) {
+            WgradTask t{};
+            t.inst = sym<const WgradInst>(AR_BLOB, (first + i0) * static_cast<int64_t>(sizeof(WgradInst)));
+            t.n_inst = std::min(kInstChunk, n_inst - i0);
+            t.tap_row = ty; t.ntaps_x = 3; t.dil = bd.conv_inst_dil[c]; t.S = f.S; t.P = f.P;
+            t.cin_total = cw.cin; t.cin0 = 128 * tile; t.ksize = 3; t.dw = bd.grad(cw.w_off);
+            p.wtasks.push_back(t);
+          }
+        if (tile == 0) {
+          BiasGradTaskH b{};
+          b.inst = sym<const WgradInst>(AR_BLOB, first * static_cast<int64_t>(sizeof(WgradInst)));
+          b.n_inst = n_inst; b.P = f.P; b.db = bd.grad(cw.b_off);
+          p.btasks.push_back(b);
+        }
+      }
+    }
+    p.blaunch.push_back({LK_WGRAD, 0, static_cast<int>(p.wtasks.size())});
+    p.blaunch.push_back({LK_BIAS, 0, static_cast<int>(p.btasks.size())});
+  }
+
+  // ---------------- blob layout ----------------
+  auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
+  int64_t o = 0;
+  p.off_cfg = o; o = align(o + static_cast<int64_t>(p.cfgs.size() * sizeof(ConvCfg)));
+  p.off_xin = o; o = align(o + static_cast<int64_t>(B) * 8);
+  p.off_fconv = o; o = align(o + static_cast<int64_t>(p.fconv.size() * sizeof(ConvTask)));
+  p.off_felt = o; o = align(o + static_cast<int64_t>(p.felt.size() * sizeof(EltTask)));
+  p.off_bconv = o; o = align(o + static_cast<int64_t>(p.bconv.size() * sizeof(ConvTask)));
+  p.off_belt = o; o = align(o + static_cast<int64_t>(p.belt.size() * sizeof(EltTask)));
+  p.off_inst = o; o = align(o + static_cast<int64_t>(p.insts.size() * sizeof(WgradInst)));
+  p.off_wt = o; o = align(o + static_cast<int64_t>(p.wtasks.size() * sizeof(WgradTask)));
+  p.off_bt = o; o = align(o + static_cast<int64_t>(p.btasks.size() * sizeof(BiasGradTaskH)));
+  p.blob_bytes = std::max<int64_t>(o, 256);
+  // instance pointers inside wgrad/bias tasks were relative to the instance table
+  for (auto& t : p.wtasks)
+    t.inst = reinterpret_cast<const WgradInst*>(reinterpret_cast<uint64_t>(t.inst) + static_cast<uint64_t>(p.off_inst));
+  for (auto& t : p.btasks)
+    t.inst = reinterpret_cast<const WgradInst*>(reinterpret_cast<uint64_t>(t.inst) + static_cast<uint64_t>(p.off_inst));
+
+  p.stats[1] = n_conv3;
+  p.stats[2] = n_tokens;
+  p.stats[3] = static_cast<int64_t>(p.flaunch.size());
+  p.stats[4] = static_cast<int64_t>(p.blaunch.size());
+  p.stats[5] = flops + n_conv3 * 2ll * 196 * 128 * 128 * 9;
+  p.stats[6] = static_cast<int64_t>(p.fconv.size());
+  p.stats[7] = static_cast<int64_t>(p.wtasks.size());
+  return plan;
+}
+
+extern "C" void pnmn_plan_destroy(pnmn_plan* p) { delete p; }
+
+extern "C" int pnmn_plan_valid(const pnmn_plan* p, uint8_t* valid) {
+  std::memcpy(valid, p->valid.data(), p->valid.size());
+  return 0;
+}
+
+extern "C" int pnmn_plan_sizes(const pnmn_plan* p, int64_t* s) {
+  for (int i = 0; i < PNMN_SZ_COUNT; ++i) s[i] = 0;
+  s[PNMN_SZ_ARENA16] = (2 * kGuard + std::max<int64_t>(p->n16, 1) * kUnit16) / 4;
+  s[PNMN_SZ_ARENA18] = (2 * kGuard + std::max<int64_t>(p->n18, 1) * kUnit18) / 4;
+  s[PNMN_SZ_ARENA22] = (2 * kGuard + std::max<int64_t>(p->n22, 1) * kUnit22) / 4;
+  s[PNMN_SZ_MAPS] = p->nmaps * 256;
+  s[PNMN_SZ_DMAPS] = p->nmaps * 256;
+  s[PNMN_SZ_IDX] = std::max<int64_t>(p->nidx, 1);
+  s[PNMN_SZ_BLOB] = p->blob_bytes;
+  return 0;
+}
+
+extern "C" int pnmn_plan_stats(const pnmn_plan* p, int64_t* stats) {
+  std::memcpy(stats, p->stats, sizeof(p->stats));
+  return 0;
+}
+
+namespace {
+
+void fill_bases(uint64_t* base, const pnmn_buffers* b, const void* final_out, const void* grad_out) {
+  std::memset(base, 0, sizeof(uint64_t) * AR_COUNT);
+  base[AR_A16] = reinterpret_cast<uint64_t>(b->arena16);
+  base[AR_A18] = reinterpret_cast<uint64_t>(b->arena18);
+  base[AR_A22] = reinterpret_cast<uint64_t>(b->arena22);
+  base[AR_MAPS] = reinterpret_cast<uint64_t>(b->maps);
+  base[AR_DMAPS] = reinterpret_cast<uint64_t>(b->dmaps);
+  base[AR_IDX] = reinterpret_cast<uint64_t>(b->idx);
+  base[AR_PACKED] = reinterpret_cast<uint64_t>(b->packed);
+  base[AR_PARAMS] = reinterpret_cast<uint64_t>(b->params);
+  base[AR_GRADS] = reinterpret_cast<uint64_t>(b->grads);
+  base[AR_BLOB] = reinterpret_cast<uint64_t>(b->blob);
+  base[AR_FINAL] = reinterpret_cast<uint64_t>(final_out);
+  base[AR_GRADOUT] = reinterpret_cast<uint64_t>(grad_out);
+}
+
+void resolve_conv(ConvTask& t, const uint64_t* base) {
+  for (int i = 0; i < 2; ++i)
+    for (int s = 0; s < NSMAX; ++s) resolve(t.in[i][s], base);
+  for (int s = 0; s < NSMAX; ++s) { resolve(t.out[s], base); resolve(t.aux[s], base); resolve(t.map_out[s], base); }
+  resolve(t.w, base); resolve(t.bias, base); resolve(t.w3, base); resolve(t.b3, base);
+}
+void resolve_elt(EltTask& t, const uint64_t* base) {
+  resolve(t.a, base); resolve(t.b, base); resolve(t.c, base); resolve(t.g, base);
+  resolve(t.o, base); resolve(t.o2, base); resolve(t.w, base); resolve(t.dw, base); resolve(t.dw2, base);
+  resolve(t.idx, base);
+}
+
+int conv_impl_simt() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = std::getenv("PNMN_CONV_IMPL");
+    v = (e && std::string(e) == "simt") ? 1 : 0;
+  }
+  return v;
+}
+
+__global__ void fill_ones_map_kernel(float* map) {
+  const int i = threadIdx.x;
+  if (i < 256) map[i] = ((i >> 4) < kHW && (i & 15) < kHW) ? 1.f : 0.f;
+}
+
+int run_launches(const pnmn_plan& p, const std::vector<LaunchItem>& ls, const uint8_t* blob, bool bwd, cudaStream_t st) {
+  const ConvCfg* cfgs = reinterpret_cast<const ConvCfg*>(blob + p.off_cfg);
+  const ConvTask* conv = reinterpret_cast<const ConvTask*>(blob + (bwd ? p.off_bconv : p.off_fconv));
+  const EltTask* elt = reinterpret_cast<const EltTask*>(blob + (bwd ? p.off_belt : p.off_felt));
+  const int simt = conv_impl_simt();
+  for (const LaunchItem& l : ls) {
+    switch (l.kind) {
+      case LK_ELT: CUDA_OK(launch_elt(elt + l.off, l.count, st)); break;
+      case LK_CONV0: CUDA_OK(launch_conv(conv + l.off, l.count, cfgs, 0, simt, st)); break;
+      case LK_CONV1: CUDA_OK(launch_conv(conv + l.off, l.count, cfgs, 1, simt, st)); break;
+      case LK_WGRAD: CUDA_OK(launch_wgrad(reinterpret_cast<const WgradTask*>(blob + p.off_wt), l.count, simt, st)); break;
+      case LK_BIAS: CUDA_OK(launch_bias_grad(blob + p.off_bt, l.count, kBiasSplit, st)); break;
+      default: break;
+    }
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const float* features, float* final_out,
+                                void* stream) {
+  pnmn_plan& p = *pp;
+  const pnmn_model& m = *p.m;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint64_t base[AR_COUNT];
+  fill_bases(base, bufs, final_out, nullptr);
+  // resolve + upload the forward part of the blob (cfgs, conv tasks, elt tasks, pack tasks)
+  const int64_t fwd_bytes = p.off_bconv;
+  p.host_blob.assign(static_cast<size_t>(p.blob_bytes), 0);
+  std::memcpy(p.host_blob.data() + p.off_cfg, p.cfgs.data(), p.cfgs.size() * sizeof(ConvCfg));
+  {
+    ConvTask* d = reinterpret_cast<ConvTask*>(p.host_blob.data() + p.off_fconv);
+    for (size_t i = 0; i < p.fconv.size(); ++i) { d[i] = p.fconv[i]; resolve_conv(d[i], base); }
+    EltTask* e = reinterpret_cast<EltTask*>(p.host_blob.data() + p.off_felt);
+    for (size_t i = 0; i < p.felt.size(); ++i) { e[i] = p.felt[i]; resolve_elt(e[i], base); }
+    int64_t* x = reinterpret_cast<int64_t*>(p.host_blob.data() + p.off_xin);
+    for (int n = 0; n < p.B; ++n) x[n] = p.xin_unit[n] < 0 ? -1 : (kGuard + p.xin_unit[n] * kUnit16) / 4;
+  }
+  CUDA_OK(cudaMemcpyAsync(bufs->blob, p.host_blob.data(), static_cast<size_t>(fwd_bytes), cudaMemcpyHostToDevice, st));
+  // pack weights (tf32, MMA tile order): the packed buffer's head holds the pack-task table
+  {
+    // pack tasks are static per model; upload them behind the packed floats is not possible (caller
+    // sized the buffer exactly), so they travel in a small persistent device allocation.
+    static std::map<const pnmn_model*, PackTask*> cache;
+    PackTask*& d_tasks = cache[&m];
+    if (!d_tasks) {
+      CUDA_OK(cudaMalloc(&d_tasks, m.pack.size() * sizeof(PackTask)));
+      CUDA_OK(cudaMemcpy(d_tasks, m.pack.data(), m.pack.size() * sizeof(PackTask), cudaMemcpyHostToDevice));
+    }
+    CUDA_OK(launch_pack(d_tasks, static_cast<int>(m.pack.size()), m.total_tiles, bufs->params, bufs->packed, st));
+  }
+  fill_ones_map_kernel<<<1, 256, 0, st>>>(bufs->maps);
+  // features -> planes for every valid sample
+  CUDA_OK(launch_nchw_to_planes(features, bufs->arena16, p.B, m.in_ch,
+                                reinterpret_cast<const int64_t*>(static_cast<const uint8_t*>(bufs->blob) + p.off_xin), st));
+  return run_launches(p, p.flaunch, static_cast<const uint8_t*>(bufs->blob), false, st);
+}
+
+extern "C" int pnmn_nmn_backward(pnmn_plan* pp, const pnmn_buffers* bufs, const float* grad_final_out, void* stream) {
+  pnmn_plan& p = *pp;
+  if (!p.need_grad) return fail("plan was created with need_grad = 0");
+  if (!bufs->grads) return fail("grads buffer is NULL");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  uint64_t base[AR_COUNT];
+  fill_bases(base, bufs, nullptr, grad_final_out);
+  {
+    ConvTask* d = reinterpret_cast<ConvTask*>(p.host_blob.data() + p.off_bconv);
+    for (size_t i = 0; i < p.bconv.size(); ++i) { d[i] = p.bconv[i]; resolve_conv(d[i], base); }
+    EltTask* e = reinterpret_cast<EltTask*>(p.host_blob.data() + p.off_belt);
+    for (size_t i = 0; i < p.belt.size(); ++i) { e[i] = p.belt[i]; resolve_elt(e[i], base); }
+    WgradInst* wi = reinterpret_cast<WgradInst*>(p.host_blob.data() + p.off_inst);
+    for (size_t i = 0; i < p.insts.size(); ++i) { wi[i] = p.insts[i]; resolve(wi[i].dz, base); resolve(wi[i].x, base); }
+    WgradTask* wt = reinterpret_cast<WgradTask*>(p.host_blob.data() + p.off_wt);
+    for (size_t i = 0; i < p.wtasks.size(); ++i) { wt[i] = p.wtasks[i]; resolve(wt[i].inst, base); resolve(wt[i].dw, base); }
+    BiasGradTaskH* bt = reinterpret_cast<BiasGradTaskH*>(p.host_blob.data() + p.off_bt);
+    for (size_t i = 0; i < p.btasks.size(); ++i) { bt[i] = p.btasks[i]; resolve(bt[i].inst, base); resolve(bt[i].db, base); }
+  }
+  CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t*>(bufs->blob) + p.off_bconv, p.host_blob.data() + p.off_bconv,
+                          static_cast<size_t>(p.blob_bytes - p.off_bconv), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemsetAsync(bufs->dmaps, 0, static_cast<size_t>(p.nmaps) * 1024, st));
+  return run_launches(p, p.blaunch, static_cast<const uint8_t*>(bufs->blob), true, st);
+}
+
+// ---- bring-up entry points -----------------------------------------------------------------------
+namespace {
+template <class T>
+int upload(const void* host, size_t n, T** dev) {
+  CUDA_OK(cudaMalloc(dev, std::max<size_t>(n, 1) * sizeof(T)));
+  CUDA_OK(cudaMemcpy(*dev, host, n * sizeof(T), cudaMemcpyHostToDevice));
+  return 0;
+}
+}  // namespace
+
+extern "C" int pnmn_debug_launch_conv(const void* tasks_host, int n_tasks, const void* cfgs_host, int n_cfgs,
+                                      int variant, int impl_simt, void* stream) {
+  ConvTask* dt = nullptr; ConvCfg* dc = nullptr;
+  if (upload(tasks_host, n_tasks, &dt)) return 1;
+  if (upload(cfgs_host, n_cfgs, &dc)) return 1;
+  CUDA_OK(launch_conv(dt, n_tasks, dc, variant, impl_simt, static_cast<cudaStream_t>(stream)));
+  CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  cudaFree(dt); cudaFree(dc);
+  return 0;
+}
+extern "C" int pnmn_debug_launch_wgrad(const void* tasks_host, int n_tasks, const void* insts_host, int n_insts,
+                                       int impl_simt, void* stream) {
+  // task.inst holds an INDEX into insts_host; it is rebased onto the uploaded table here
+  WgradInst* di = nullptr;
+  if (upload(insts_host, n_insts, &di)) return 1;
+  std::vector<WgradTask> t(static_cast<const WgradTask*>(tasks_host), static_cast<const WgradTask*>(tasks_host) + n_tasks);
+  for (auto& x : t) x.inst = di + reinterpret_cast<uint64_t>(x.inst);
+  WgradTask* dt = nullptr;
+  if (upload(t.data(), t.size(), &dt)) return 1;
+  CUDA_OK(launch_wgrad(dt, n_tasks, impl_simt, static_cast<cudaStream_t>(stream)));
+  CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  cudaFree(dt); cudaFree(di);
+  return 0;
+}
+extern "C" int pnmn_debug_pack(const void* pack_tasks_host, int n_tasks, int total_tiles, const float* params,
+                               float* packed, void* stream) {
+  PackTask* dt = nullptr;
+  if (upload(pack_tasks_host, n_tasks, &dt)) return 1;
+  CUDA_OK(launch_pack(dt, n_tasks, total_tiles, params, packed, static_cast<cudaStream_t>(stream)));
+  CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  cudaFree(dt);
+  return 0;
+}
+extern "C" int pnmn_debug_nchw_to_planes(const float* src, float* dst, int batch, int channels,
+                                         int64_t dst_sample_stride, void* stream) {
+  std::vector<int64_t> off(batch);
+  for (int b = 0; b < batch; ++b) off[b] = b * dst_sample_stride;
+  int64_t* d = nullptr;
+  if (upload(off.data(), off.size(), &d)) return 1;
+  CUDA_OK(launch_nchw_to_planes(src, dst, batch, channels, d, static_cast<cudaStream_t>(stream)));
+  CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  cudaFree(d);
+  return 0;
+}
+extern "C" int pnmn_debug_launch_elt(const void* tasks_host, int n_tasks, void* stream) {
+  EltTask* dt = nullptr;
+  if (upload(tasks_host, n_tasks, &dt)) return 1;
+  CUDA_OK(launch_elt(dt, n_tasks, static_cast<cudaStream_t>(stream)));
+  CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  cudaFree(dt);
+  return 0;
+}

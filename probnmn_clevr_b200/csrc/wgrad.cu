@@ -1,0 +1,199 @@
+// Weight gradient of the shift-GEMM convolutions:
+//
+//   dW[cout][cin][ty][tx] += sum_{instances} sum_{slot} dZ[cout][slot] * X[cin][slot + shift(ty,tx)]
+//
+// "Instance" = one (sample, step) at which this conv ran in the forward pass; a module that was
+// used by 37 samples of the batch contributes 37 instances to the same dW (reference: autograd
+// accumulating into one nn.Conv2d.weight.grad, probnmn/models/nmn.py:114-115,229).
+//
+// GEMM view per tap: M = cout (128, from dZ), N = cin (128, from X), K = pixel slots.  Both
+// operands are "MN-major" in the plane format (4 channels contiguous per slot), so the planes
+// are consumed as they are; a tap is again just a different start address of the X descriptor.
+// One CTA owns one tap ROW (3 taps -> 3 accumulators of 128 TMEM columns) of one weight tensor
+// and walks a list of instances, streaming 64-slot chunks of dZ and X through an mbarrier ring.
+#include "executor.h"
+#include "tcgen05.cuh"
+
+namespace pnmn {
+
+constexpr int kWgThreads = 256;
+constexpr int kWgChunk = 64;        // slots (K) per stage
+constexpr int kWgStages = 3;
+constexpr int kWgHeader = 1024;
+constexpr int kWgSmemTotal = 227 * 1024;
+constexpr int kWgMaxXS = kWgChunk + 16;  // chunk + 2*dil halo, dil <= 8
+constexpr int kWgStageBytes = kKC * kWgChunk * 16 + kKC * kWgMaxXS * 16;  // 32 KB + 40 KB
+static_assert(kWgHeader + kWgStages * kWgStageBytes <= kWgSmemTotal, "wgrad smem");
+
+struct WgSmemHeader {
+  uint64_t full[kWgStages];
+  uint64_t empty[kWgStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  WgSmemHeader* hdr = reinterpret_cast<WgSmemHeader*>(smem);
+  uint8_t* ring = smem + kWgHeader;
+  const WgradTask t = tasks[blockIdx.x];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int halo = t.ntaps_x == 3 ? t.dil : 0;
+  const int xs = kWgChunk + 2 * halo;                 // X slots per plane per stage
+  const int n_chunks = (kHW * t.S + kWgChunk - 1) / kWgChunk;
+  const int row_shift = t.ntaps_x == 3 ? (t.tap_row - 1) * t.dil * t.S : 0;
+  const uint32_t dz_bytes = kKC * kWgChunk * 16;
+  const int total = t.n_inst * n_chunks;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(smem_u32(&hdr->full[i]), 1);
+      mbar_init(smem_u32(&hdr->empty[i]), 1);
+    }
+    mbar_init(smem_u32(&hdr->tmem_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(smem_u32(&hdr->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+
+  if (warp == 0) {
+    // producer: lane = plane index
+    for (int it = 0; it < total; ++it) {
+      const int st = it % kWgStages;
+      const uint32_t ph = (it / kWgStages) & 1;
+      const int inst = it / n_chunks, ch = it % n_chunks;
+      const uint32_t bar = smem_u32(&hdr->full[st]);
+      if (lane == 0) {
+        mbar_wait(smem_u32(&hdr->empty[st]), ph ^ 1);
+        mbar_arrive_expect_tx(bar, dz_bytes + kKC * xs * 16);
+      }
+      __syncwarp();
+      const WgradInst wi = t.inst[inst];
+      const int c0 = ch * kWgChunk;
+      uint8_t* sdz = ring + st * kWgStageBytes;
+      uint8_t* sx = sdz + dz_bytes;
+      bulk_g2s(smem_u32(sdz + lane * kWgChunk * 16), wi.dz + (static_cast<ptrdiff_t>(lane) * t.P + c0) * 4,
+               kWgChunk * 16, bar);
+      bulk_g2s(smem_u32(sx + lane * xs * 16),
+               wi.x + (static_cast<ptrdiff_t>(lane) * t.P + c0 + row_shift - halo) * 4, xs * 16, bar);
+    }
+  } else if (warp == 2) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(128, 128, 1, 1);
+      for (int it = 0; it < total; ++it) {
+        const int st = it % kWgStages;
+        mbar_wait(smem_u32(&hdr->full[st]), (it / kWgStages) & 1);
+        tc_fence_after();
+        const uint32_t sdz = smem_u32(ring + st * kWgStageBytes);
+        const uint32_t sx = sdz + dz_bytes;
+        for (int tx = 0; tx < t.ntaps_x; ++tx) {
+#pragma unroll
+          for (int k8 = 0; k8 < kWgChunk / 8; ++k8) {
+            const uint64_t ad = make_smem_desc(sdz + k8 * 128u, 128u, kWgChunk * 16u);
+            const uint64_t bd = make_smem_desc(sx + (k8 * 8u + static_cast<uint32_t>(halo * tx)) * 16u, 128u,
+                                               static_cast<uint32_t>(xs) * 16u);
+            umma_tf32(tmem_base + tx * 128, ad, bd, idesc, (it | k8) != 0);
+          }
+        }
+        umma_commit(smem_u32(&hdr->empty[st]));
+      }
+      umma_commit(smem_u32(&hdr->tmem_full));
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int cout = q * 32 + lane;
+    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    tc_fence_after();
+    const int kk = t.ksize * t.ksize;
+    for (int tx = 0; tx < t.ntaps_x; ++tx) {
+      const int tap = t.ksize == 3 ? t.tap_row * 3 + tx : 0;
+      for (int chunk = 0; chunk < 4; ++chunk) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + tx * 128 + chunk * 32, v);
+        tmem_ld_wait();
+        if (total > 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int cin = t.cin0 + chunk * 32 + j;
+            atomicAdd(t.dw + (static_cast<size_t>(cout) * t.cin_total + cin) * kk + tap, __uint_as_float(v[j]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+// CUDA-core twin with identical task semantics (bring-up / debugging only, PNMN_CONV_IMPL=simt).
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgradTask* __restrict__ tasks) {
+  const WgradTask t = tasks[blockIdx.x];
+  const int kk = t.ksize * t.ksize;
+  const int nslots = kHW * t.S;
+  for (int idx = threadIdx.x; idx < t.ntaps_x * 128 * 128; idx += blockDim.x) {
+    const int cin = idx % 128, cout = (idx / 128) % 128, tx = idx / (128 * 128);
+    const int shift = t.ntaps_x == 3 ? ((t.tap_row - 1) * t.S + (tx - 1)) * t.dil : 0;
+    float acc = 0.f;
+    for (int i = 0; i < t.n_inst; ++i) {
+      const WgradInst wi = t.inst[i];
+      const float* dz = wi.dz + static_cast<size_t>(cout / 4) * t.P * 4 + (cout % 4);
+      const float* x = wi.x + static_cast<ptrdiff_t>(cin / 4) * t.P * 4 + (cin % 4);
+      for (int p = 0; p < nslots; ++p) {
+        const float g = dz[p * 4];
+        if (g != 0.f) acc = fmaf(g, x[static_cast<ptrdiff_t>(p + shift) * 4], acc);
+      }
+    }
+    const int tap = t.ksize == 3 ? t.tap_row * 3 + tx : 0;
+    if (t.n_inst > 0)
+      atomicAdd(t.dw + (static_cast<size_t>(cout) * t.cin_total + t.cin0 + cin) * kk + tap, acc);
+  }
+}
+
+// db[n] += sum over instances and slots of dZ[n][slot]      (one CTA per weight tensor)
+struct BiasGradTask {
+  const WgradInst* inst;
+  int n_inst;
+  int P;
+  float* db;
+};
+__global__ void __launch_bounds__(128) bias_grad_kernel(const BiasGradTask* __restrict__ tasks) {
+  const BiasGradTask t = tasks[blockIdx.x];
+  const int n = threadIdx.x;  // output channel
+  const int i0 = blockIdx.y, di = gridDim.y;
+  float acc = 0.f;
+  for (int i = i0; i < t.n_inst; i += di) {
+    const float* dz = t.inst[i].dz + static_cast<size_t>(n / 4) * t.P * 4 + (n % 4);
+    for (int p = 0; p < t.P; ++p) acc += dz[p * 4];
+  }
+  if (t.n_inst > i0) atomicAdd(t.db + n, acc);
+}
+
+cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, cudaStream_t stream) {
+  if (n_tasks <= 0) return cudaSuccess;
+  if (impl_simt) {
+    wgrad_simt_kernel<<<n_tasks, 256, 0, stream>>>(d_tasks);
+    return cudaGetLastError();
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmemTotal);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  wgrad_tc_kernel<<<n_tasks, kWgThreads, kWgSmemTotal, stream>>>(d_tasks);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bias_grad(const void* d_tasks, int n_tasks, int split, cudaStream_t stream) {
+  if (n_tasks <= 0) return cudaSuccess;
+  bias_grad_kernel<<<dim3(n_tasks, split), 128, 0, stream>>>(static_cast<const BiasGradTask*>(d_tasks));
+  return cudaGetLastError();
+}
+
+}  // namespace pnmn

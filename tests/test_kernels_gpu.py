@@ -1,0 +1,240 @@
+"""Kernel-level parity of the tcgen05 conv / wgrad kernels against plain PyTorch fp32 (GPU only).
+
+Inputs and weights are pre-rounded to tf32 so that the only difference between the tensor-core
+kernel and the fp32 torch reference is accumulation order: tolerance 2e-5 relative to the output
+scale (written next to each assert).
+"""
+import ctypes
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from probnmn_clevr_b200 import _lib as L
+from probnmn_clevr_b200.planes import GUARD_FLOATS, fmt_for_dilation, from_planes, map_from_slots, round_tf32, to_planes
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _pack(W, n_kb, ntaps, flip, k_off, n_off, k_stride, n_stride, tap_stride):
+    """run the library's pack kernel on one weight tensor -> packed float tensor"""
+    lib = L.lib()
+    t = L.PackTask(0, 0, 0, n_kb, ntaps, flip, k_off, n_off, k_stride, n_stride, tap_stride, 0)
+    packed = torch.zeros(n_kb * ntaps * 2048, device="cuda")
+    L.check(lib.pnmn_debug_pack(ctypes.byref(t), 1, n_kb * ntaps, _ptr(W), _ptr(packed), _stream()))
+    return packed
+
+
+def _arena(planes_list):
+    """concatenate plane tensors into one zero-guarded arena; return (arena, [float offsets])"""
+    total = 2 * GUARD_FLOATS + sum(p.numel() for p in planes_list)
+    arena = torch.zeros(total, device="cuda")
+    offs, o = [], GUARD_FLOATS
+    for p in planes_list:
+        arena[o:o + p.numel()] = p.reshape(-1)
+        offs.append(o)
+        o += p.numel()
+    return arena, offs
+
+
+def _conv_cfg(n_kb, kb_per_in, ntaps, dil, fin, fout, faux, flags):
+    lead = ((dil * fin[0] + dil + 7) // 8) * 8 if ntaps == 9 else 8
+    return L.ConvCfg(n_kb, kb_per_in, ntaps, dil, fin[0], fin[1], fout[0], fout[1], faux[0], faux[1], flags, lead)
+
+
+def _run_conv(cfg, variant, impl, ins, w_packed, bias=None, aux=None, w3=None, b3=None, out_init=None):
+    """ins: list over samples of list over inputs of (C,14,14) tensors. returns (outs nchw, maps)"""
+    lib = L.lib()
+    ns = len(ins)
+    S_in, S_out = cfg.S_in, cfg.S_out
+    in_planes = [to_planes(x, S_in) for smp in ins for x in smp]
+    arena_in, offs_in = _arena(in_planes)
+    out_planes = [to_planes(out_init[s], S_out) if out_init is not None else torch.zeros(32, S_out * S_out, 4, device="cuda")
+                  for s in range(ns)]
+    arena_out, offs_out = _arena(out_planes)
+    arena_aux, offs_aux = (None, None)
+    if aux is not None:
+        arena_aux, offs_aux = _arena([to_planes(a, cfg.S_aux) for a in aux])
+    maps = torch.zeros(ns, 256, device="cuda")
+    t = L.ConvTask()
+    n_in = len(ins[0])
+    for s in range(ns):
+        for i in range(n_in):
+            t.in_[i][s] = arena_in.data_ptr() + 4 * offs_in[s * n_in + i]
+        t.out[s] = arena_out.data_ptr() + 4 * offs_out[s]
+        if aux is not None:
+            t.aux[s] = arena_aux.data_ptr() + 4 * offs_aux[s]
+        t.map_out[s] = maps.data_ptr() + 4 * 256 * s
+    t.w = w_packed.data_ptr()
+    t.bias = bias.data_ptr() if bias is not None else None
+    t.w3 = w3.data_ptr() if w3 is not None else None
+    t.b3 = b3.data_ptr() if b3 is not None else None
+    t.cfg = 0
+    t.n_samp = ns
+    L.check(lib.pnmn_debug_launch_conv(ctypes.byref(t), 1, ctypes.byref(cfg), 1, variant, impl, _stream()))
+    torch.cuda.synchronize()
+    outs = []
+    for s in range(ns):
+        n = 32 * S_out * S_out * 4
+        outs.append(from_planes(arena_out[offs_out[s]:offs_out[s] + n].view(32, S_out * S_out, 4), S_out))
+    return outs, [map_from_slots(maps[s]) for s in range(ns)]
+
+
+def _relerr(a, b):
+    return (a - b).abs().max().item() / (b.abs().max().item() + 1e-30)
+
+
+def _mk(shape, gen, scale=1.0):
+    return round_tf32(torch.randn(shape, generator=gen, device="cuda") * scale)
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("dil,ns", [(1, 2), (1, 1), (2, 2), (4, 2), (8, 1)])
+def test_conv3x3_forward(impl, dil, ns):
+    g = torch.Generator(device="cuda").manual_seed(dil * 10 + ns)
+    W = _mk((128, 128, 3, 3), g, 0.05)
+    b = torch.randn(128, generator=g, device="cuda")
+    xs = [_mk((128, 14, 14), g) for _ in range(ns)]
+    fin = fmt_for_dilation(dil)
+    fout = fmt_for_dilation({1: 2, 2: 4, 4: 8, 8: 1}[dil])  # Relate chain: next conv's input format
+    cfg = _conv_cfg(8, 8, 9, dil, fin, fout, fout, L.F_BIAS | L.F_RELU | L.F_STORE)
+    wp = _pack(W, 8, 9, 0, 0, 0, 9, 128 * 9, 1)
+    outs, _ = _run_conv(cfg, 1 if fin[0] == 22 else 0, impl, [[x] for x in xs], wp, bias=b)
+    for x, o in zip(xs, outs):
+        ref = F.relu(F.conv2d(x[None], W, b, padding=dil, dilation=dil))[0]
+        err = _relerr(o, round_tf32(ref))
+        print(f"conv3x3 impl={impl} dil={dil} ns={ns}: rel err {err:.3e}")
+        assert err < 1e-3  # output is stored tf32-rounded: 2^-11 = 4.9e-4 worst case
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+def test_conv_dotsig_head(impl):
+    g = torch.Generator(device="cuda").manual_seed(7)
+    W = _mk((128, 128, 3, 3), g, 0.05)
+    b = torch.randn(128, generator=g, device="cuda")
+    w3 = torch.randn(128, generator=g, device="cuda") * 0.05
+    b3 = torch.randn(1, generator=g, device="cuda")
+    xs = [_mk((128, 14, 14), g) for _ in range(2)]
+    f16 = fmt_for_dilation(1)
+    cfg = _conv_cfg(8, 8, 9, 1, f16, f16, f16, L.F_BIAS | L.F_RELU | L.F_STORE | L.F_DOTSIG)
+    wp = _pack(W, 8, 9, 0, 0, 0, 9, 128 * 9, 1)
+    _, maps = _run_conv(cfg, 0, impl, [[x] for x in xs], wp, bias=b, w3=w3, b3=b3)
+    for x, m in zip(xs, maps):
+        y = F.relu(F.conv2d(x[None], W, b, padding=1))
+        ref = torch.sigmoid(F.conv2d(y, w3.view(1, 128, 1, 1), b3))[0, 0]
+        err = (m - ref).abs().max().item()
+        print(f"dotsig impl={impl}: abs err {err:.3e}")
+        assert err < 1e-5  # fp32 epilogue on exact tf32 products
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("dil", [1, 8])
+def test_conv_dgrad_mask_accum(impl, dil):
+    """dgrad = same kernel on the transposed/flipped pack; epilogue masks with Y>0 and accumulates"""
+    g = torch.Generator(device="cuda").manual_seed(11 + dil)
+    W = _mk((128, 128, 3, 3), g, 0.05)
+    ns = 1 if dil == 8 else 2
+    dz = [_mk((128, 14, 14), g) for _ in range(ns)]
+    yprev = [_mk((128, 14, 14), g) for _ in range(ns)]
+    old = [_mk((128, 14, 14), g) for _ in range(ns)]
+    fin = fmt_for_dilation(dil)
+    f16 = fmt_for_dilation(1)
+    cfg = _conv_cfg(8, 8, 9, dil, fin, f16, fin, L.F_STORE | L.F_MASK | L.F_ACCUM)
+    wp = _pack(W, 8, 9, 1, 0, 0, 128 * 9, 9, 1)
+    outs, _ = _run_conv(cfg, 1 if fin[0] == 22 else 0, impl, [[d] for d in dz], wp, aux=yprev, out_init=old)
+    for d, y, o0, o in zip(dz, yprev, old, outs):
+        gi = torch.nn.grad.conv2d_input((1, 128, 14, 14), W, d[None], padding=dil, dilation=dil)[0]
+        ref = torch.where(y > 0, gi, torch.zeros_like(gi)) + o0
+        err = _relerr(o, ref)
+        print(f"dgrad impl={impl} dil={dil}: rel err {err:.3e}")
+        assert err < 1e-3  # tf32-rounded store
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+def test_conv_projection_two_inputs(impl):
+    g = torch.Generator(device="cuda").manual_seed(5)
+    W = _mk((128, 256, 1, 1), g, 0.05)
+    b = torch.randn(128, generator=g, device="cuda")
+    ins = [[_mk((128, 14, 14), g), _mk((128, 14, 14), g)] for _ in range(2)]
+    f16 = fmt_for_dilation(1)
+    cfg = _conv_cfg(16, 8, 1, 1, f16, f16, f16, L.F_BIAS | L.F_RELU | L.F_STORE)
+    wp = _pack(W, 16, 1, 0, 0, 0, 1, 256, 0)
+    outs, _ = _run_conv(cfg, 0, impl, ins, wp, bias=b)
+    for (a, c), o in zip(ins, outs):
+        ref = F.relu(F.conv2d(torch.cat([a, c])[None], W, b))[0]
+        err = _relerr(o, ref)
+        print(f"projection impl={impl}: rel err {err:.3e}")
+        assert err < 1e-3
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+def test_conv_stem_1024(impl):
+    g = torch.Generator(device="cuda").manual_seed(3)
+    W = _mk((128, 1024, 3, 3), g, 0.02)
+    b = torch.randn(128, generator=g, device="cuda")
+    xs = [_mk((1024, 14, 14), g).relu() for _ in range(2)]
+    f16 = fmt_for_dilation(1)
+    cfg = _conv_cfg(64, 64, 9, 1, f16, f16, f16, L.F_BIAS | L.F_RELU | L.F_STORE)
+    wp = _pack(W, 64, 9, 0, 0, 0, 9, 1024 * 9, 1)
+    outs, _ = _run_conv(cfg, 0, impl, [[x] for x in xs], wp, bias=b)
+    for x, o in zip(xs, outs):
+        ref = F.relu(F.conv2d(x[None], W, b, padding=1))[0]
+        err = _relerr(o, ref)
+        print(f"stem impl={impl}: rel err {err:.3e}")
+        assert err < 1e-3
+
+
+def _run_wgrad(impl, dzs, xs, dil, ksize, cin_total, cin0):
+    lib = L.lib()
+    fin = fmt_for_dilation(dil)
+    S, P = fin
+    n = len(dzs)
+    arena_dz, offs_dz = _arena([to_planes(d, S) for d in dzs])
+    arena_x, offs_x = _arena([to_planes(x, S) for x in xs])
+    insts = (L.WgradInst * n)()
+    for i in range(n):
+        insts[i].dz = arena_dz.data_ptr() + 4 * offs_dz[i]
+        insts[i].x = arena_x.data_ptr() + 4 * offs_x[i]
+    dw = torch.zeros(128, cin_total, ksize, ksize, device="cuda")
+    rows = 3 if ksize == 3 else 1
+    tasks = (L.WgradTask * rows)()
+    for r in range(rows):
+        tasks[r] = L.WgradTask(0, n, r, 3 if ksize == 3 else 1, dil, S, P, cin_total, cin0, ksize, dw.data_ptr(), 0)
+    L.check(lib.pnmn_debug_launch_wgrad(tasks, rows, insts, n, impl, _stream()))
+    torch.cuda.synchronize()
+    return dw
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+@pytest.mark.parametrize("dil,n_inst", [(1, 3), (2, 1), (4, 2), (8, 2)])
+def test_wgrad3x3(impl, dil, n_inst):
+    g = torch.Generator(device="cuda").manual_seed(21 + dil)
+    dzs = [_mk((128, 14, 14), g) for _ in range(n_inst)]
+    xs = [_mk((128, 14, 14), g) for _ in range(n_inst)]
+    dw = _run_wgrad(impl, dzs, xs, dil, 3, 128, 0)
+    ref = sum(torch.nn.grad.conv2d_weight(x[None], (128, 128, 3, 3), d[None], padding=dil, dilation=dil)
+              for x, d in zip(xs, dzs))
+    err = _relerr(dw, ref)
+    print(f"wgrad impl={impl} dil={dil}: rel err {err:.3e}")
+    assert err < 2e-5  # exact tf32 products, fp32 accumulation
+
+
+@pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
+def test_wgrad_projection_half(impl):
+    g = torch.Generator(device="cuda").manual_seed(31)
+    dzs = [_mk((128, 14, 14), g) for _ in range(2)]
+    xs = [_mk((128, 14, 14), g) for _ in range(2)]
+    dw = _run_wgrad(impl, dzs, xs, 1, 1, 256, 128)
+    ref = sum(torch.einsum("ohw,ihw->oi", d, x) for x, d in zip(xs, dzs))
+    err = _relerr(dw[:, 128:, 0, 0], ref)
+    print(f"wgrad proj impl={impl}: rel err {err:.3e}")
+    assert err < 2e-5
+    assert dw[:, :128].abs().max().item() == 0.0
