@@ -66,13 +66,15 @@ void pnmn_plan_destroy(pnmn_plan* p);
 int pnmn_plan_valid(const pnmn_plan* p, uint8_t* valid);
 
 enum pnmn_size_slot {
-  PNMN_SZ_ARENA16 = 0, /* floats, P16 plane arena (must be zero-filled when (re)allocated) */
+  PNMN_SZ_ARENA16 = 0, /* floats, P16 plane arena (must be zero-filled when (re)allocated); units hold
+                          32 fp32 planes + 16 fp16 shadow half planes */
   PNMN_SZ_ARENA18 = 1, /* floats, P18 plane arena (zero-filled) */
   PNMN_SZ_ARENA22 = 2, /* floats, P22 plane arena (zero-filled) */
   PNMN_SZ_MAPS = 3,    /* floats, attention maps (zero-filled) */
   PNMN_SZ_DMAPS = 4,   /* floats, attention-map gradients */
   PNMN_SZ_IDX = 5,     /* int32, SameModule argmax slots */
   PNMN_SZ_BLOB = 6,    /* bytes, device scratch for task tables */
+  PNMN_SZ_AIN = 7,     /* floats, stem-input arena (features as planes + fp16 shadow; zero-filled) */
   PNMN_SZ_COUNT = 8
 };
 int pnmn_plan_sizes(const pnmn_plan* p, int64_t* sizes /* [PNMN_SZ_COUNT] */);
@@ -91,6 +93,8 @@ typedef struct pnmn_buffers {
   float* packed;     /* device, pnmn_model_packed_floats() floats */
   const float* params; /* device, flat fp32 parameters */
   float* grads;      /* device, flat fp32 gradients (same offsets), may be NULL for forward */
+  float* ain;        /* device, PNMN_SZ_AIN floats */
+  float* scratch;    /* device, >= 64 floats (loss scale of the backward pass) */
 } pnmn_buffers;
 
 /* Forward of stem + module executor: replaces NeuralModuleNetwork.forward up to the tensor that

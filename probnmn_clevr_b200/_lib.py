@@ -20,11 +20,11 @@ MAX_MODULE_PARAMS = 12
 TOK_SKIP, TOK_SCENE, TOK_AND, TOK_OR, TOK_COMPARE, TOK_QUERY, TOK_RELATE, TOK_SAME, TOK_ATTENTION = range(9)
 
 # pnmn_size_slot
-SZ_ARENA16, SZ_ARENA18, SZ_ARENA22, SZ_MAPS, SZ_DMAPS, SZ_IDX, SZ_BLOB = range(7)
+SZ_ARENA16, SZ_ARENA18, SZ_ARENA22, SZ_MAPS, SZ_DMAPS, SZ_IDX, SZ_BLOB, SZ_AIN = range(8)
 SZ_COUNT = 8
 
 # ConvFlags (csrc/executor.h)
-F_BIAS, F_RELU, F_STORE, F_DOTSIG, F_MASK, F_ACCUM = 1, 2, 4, 8, 16, 32
+F_BIAS, F_RELU, F_STORE, F_DOTSIG, F_MASK, F_ACCUM, F_HALF = 1, 2, 4, 8, 16, 32, 64
 
 
 class Buffers(Structure):
@@ -32,6 +32,7 @@ class Buffers(Structure):
         ("arena16", c_void_p), ("arena18", c_void_p), ("arena22", c_void_p),
         ("maps", c_void_p), ("dmaps", c_void_p), ("idx", c_void_p),
         ("blob", c_void_p), ("packed", c_void_p), ("params", c_void_p), ("grads", c_void_p),
+        ("ain", c_void_p), ("scratch", c_void_p),
     ]
 
 
@@ -57,7 +58,7 @@ class WgradTask(Structure):
     _fields_ = [
         ("inst", c_void_p), ("n_inst", c_int), ("tap_row", c_int), ("ntaps_x", c_int), ("dil", c_int),
         ("S", c_int), ("P", c_int), ("cin_total", c_int), ("cin0", c_int), ("ksize", c_int),
-        ("dw", c_void_p), ("pad_", c_int),
+        ("dw", c_void_p), ("scale", c_void_p),
     ]
 
 
@@ -73,7 +74,7 @@ class EltTask(Structure):
     _fields_ = [
         ("op", c_int), ("flags", c_int), ("a", c_void_p), ("b", c_void_p), ("c", c_void_p), ("g", c_void_p),
         ("o", c_void_p), ("o2", c_void_p), ("w", c_void_p), ("dw", c_void_p), ("dw2", c_void_p), ("idx", c_void_p),
-        ("pad_", c_int64 * 5),
+        ("scale", c_void_p), ("pad_", c_int64 * 4),
     ]
 
 

@@ -17,6 +17,8 @@
 //
 // Reference semantics: nn.Conv2d(128,128,3,padding=d,dilation=d) + F.relu and the 1x1 + sigmoid
 // heads of probnmn/modules/nmn_modules.py:82-87,119-123,160-168,239-244; stem nmn.py:67-72.
+#include <cuda_fp16.h>
+
 #include "executor.h"
 #include "tcgen05.cuh"
 
@@ -46,8 +48,13 @@ __device__ __forceinline__ int tap_shift(const ConvCfg& c, int tap) {
 }
 
 // Fused epilogue for one output row (pixel slot) and 4 consecutive output channels.
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+
 __device__ __forceinline__ void epilogue4(const ConvTask& t, const ConvCfg& c, int s, int kc, int so,
-                                          int sx, float4 o, float& dot) {
+                                          int sx, float4& o, float& dot) {
   const int n0 = kc * 4;
   if (c.flags & F_BIAS) {
     const float4 b = __ldg(reinterpret_cast<const float4*>(t.bias + n0));
@@ -205,10 +212,20 @@ conv_tc_kernel(const ConvTask* __restrict__ tasks, const ConvCfg* __restrict__ c
           tmem_ld_wait();
           if (valid) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 o = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                     __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-              epilogue4(t, c, s, chunk * 8 + j, so, sx, o, dot);
+            for (int j = 0; j < 4; ++j) {
+              float4 o0 = make_float4(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]),
+                                      __uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
+              float4 o1 = make_float4(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]),
+                                      __uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
+              const int kc = chunk * 8 + 2 * j;
+              epilogue4(t, c, s, kc, so, sx, o0, dot);
+              epilogue4(t, c, s, kc + 1, so, sx, o1, dot);
+              if (c.flags & F_HALF) {
+                uint4 h = make_uint4(pack_half2(o0.x, o0.y), pack_half2(o0.z, o0.w), pack_half2(o1.x, o1.y),
+                                     pack_half2(o1.z, o1.w));
+                uint8_t* hb = reinterpret_cast<uint8_t*>(t.out[s]) + shadow_bytes(c.P_out);
+                *reinterpret_cast<uint4*>(hb + (static_cast<size_t>(kc >> 1) * c.P_out + so) * 16) = h;
+              }
             }
           }
         }
@@ -263,7 +280,14 @@ conv_simt_kernel(const ConvTask* __restrict__ tasks, const ConvCfg* __restrict__
       }
     }
     float dot = 0.f;
-    epilogue4(t, c, s, kc_out, y * c.S_out + x, y * c.S_aux + x, make_float4(acc[0], acc[1], acc[2], acc[3]), dot);
+    float4 o = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    const int so = y * c.S_out + x;
+    epilogue4(t, c, s, kc_out, so, y * c.S_aux + x, o, dot);
+    if (c.flags & F_HALF) {
+      uint8_t* hb = reinterpret_cast<uint8_t*>(t.out[s]) + shadow_bytes(c.P_out);
+      *reinterpret_cast<uint2*>(hb + (static_cast<size_t>(kc_out >> 1) * c.P_out + so) * 16 + (kc_out & 1) * 8) =
+          make_uint2(pack_half2(o.x, o.y), pack_half2(o.z, o.w));
+    }
     if (c.flags & F_DOTSIG) atomicAdd(&dots[s * 512 + r], dot);
   }
   __syncthreads();

@@ -8,6 +8,8 @@
 //   MINMAX      torch.min / torch.max (broadcasting)   probnmn/modules/nmn_modules.py:25-27,43-45
 //   DOTSIG_BWD  backward of sigmoid(conv1x1(relu(.)))  probnmn/modules/nmn_modules.py:86,167
 //   GATHER      torch.cat(final_module_outputs) / zeros for invalid programs   probnmn/models/nmn.py:233-241
+#include <cuda_fp16.h>
+
 #include "elt.h"
 #include "tcgen05.cuh"
 
@@ -15,6 +17,17 @@ namespace pnmn {
 
 __device__ __forceinline__ int valid_slot16(int i) {  // i in [0,196) -> P16 slot
   return (i / kHW) * 16 + (i % kHW);
+}
+
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+// fp16 shadow of 4 channels (plane kc) of P16 slot s, stored behind the 32 fp32 planes of `base`
+__device__ __forceinline__ void st_half4(float* base, int kc, int s, float4 v) {
+  uint8_t* hb = reinterpret_cast<uint8_t*>(base) + shadow_bytes(256);
+  *reinterpret_cast<uint2*>(hb + (static_cast<size_t>(kc >> 1) * 256 + s) * 16 + (kc & 1) * 8) =
+      make_uint2(pack_half2(v.x, v.y), pack_half2(v.z, v.w));
 }
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
@@ -46,6 +59,7 @@ __global__ void __launch_bounds__(256) elt_kernel(const EltTask* __restrict__ ta
         float4 v = ld4(t.a + (kc * 256 + s) * 4);
         v.x = to_tf32(v.x * m); v.y = to_tf32(v.y * m); v.z = to_tf32(v.z * m); v.w = to_tf32(v.w * m);
         st4(t.o + (kc * 256 + s) * 4, v);
+        if (t.flags & EF_HALF) st_half4(t.o, kc, s, v);
       }
     } break;
 
@@ -124,7 +138,8 @@ __global__ void __launch_bounds__(256) elt_kernel(const EltTask* __restrict__ ta
       sh[tid] = gp;
       const float sum_g = block_sum(gp, red);
       const float sum_ga = block_sum(tid < 196 ? gp * t.b[s] : 0.f, red);
-      if (tid == 0) { atomicAdd(t.dw2, sum_g); atomicAdd(t.dw + 128, sum_ga); }
+      const float unscale = t.scale[1];
+      if (tid == 0) { atomicAdd(t.dw2, sum_g * unscale); atomicAdd(t.dw + 128, sum_ga * unscale); }
       __syncthreads();
       if (tid < 128) {
         // channel tid: q = sum_p g[p]*feat[c][p];  dw_c += q*v_c;  dfeat[c][p] (+)= g[p]*w_c*v_c; dfeat[c][is] += q*w_c
@@ -139,7 +154,7 @@ __global__ void __launch_bounds__(256) elt_kernel(const EltTask* __restrict__ ta
           const float val = gi * wc * v;
           *d = (t.flags & EF_ACCUM) ? *d + val : val;
         }
-        atomicAdd(t.dw + tid, q * v);
+        atomicAdd(t.dw + tid, q * v * unscale);
         t.o2[(kc * 256 + is) * 4 + e] += q * wc;
       }
     } break;
@@ -161,6 +176,7 @@ __global__ void __launch_bounds__(256) elt_kernel(const EltTask* __restrict__ ta
           r.x = mx ? fmaxf(x.x, y.x) : fminf(x.x, y.x); r.y = mx ? fmaxf(x.y, y.y) : fminf(x.y, y.y);
           r.z = mx ? fmaxf(x.z, y.z) : fminf(x.z, y.z); r.w = mx ? fmaxf(x.w, y.w) : fminf(x.w, y.w);
           st4(t.o + (kc * 256 + s) * 4, r);
+          if (t.flags & EF_HALF) st_half4(t.o, kc, s, r);
         }
       }
     } break;
@@ -217,7 +233,8 @@ __global__ void __launch_bounds__(256) elt_kernel(const EltTask* __restrict__ ta
       }
       sh[tid] = gp;
       const float sum_g = block_sum(gp, red);
-      if (tid == 0) atomicAdd(t.dw2, sum_g);
+      const float unscale = t.scale[1];
+      if (tid == 0) atomicAdd(t.dw2, sum_g * unscale);
       __syncthreads();
       for (int i = tid; i < kKC * 196; i += 256) {
         const int kc = i / 196, p = i % 196, s = valid_slot16(p);
@@ -228,12 +245,13 @@ __global__ void __launch_bounds__(256) elt_kernel(const EltTask* __restrict__ ta
         d.x = y.x > 0.f ? to_tf32(gi * w.x) : 0.f; d.y = y.y > 0.f ? to_tf32(gi * w.y) : 0.f;
         d.z = y.z > 0.f ? to_tf32(gi * w.z) : 0.f; d.w = y.w > 0.f ? to_tf32(gi * w.w) : 0.f;
         st4(t.o + (kc * 256 + s) * 4, d);
+        st_half4(t.o, kc, s, d);
       }
       if (tid < 128) {
         const int kc = tid >> 2, e = tid & 3;
         float q = 0.f;
         for (int p = 0; p < 196; ++p) q = fmaf(sh[p], t.a[(kc * 256 + valid_slot16(p)) * 4 + e], q);
-        atomicAdd(t.dw + tid, q);
+        atomicAdd(t.dw + tid, q * unscale);
       }
     } break;
 
@@ -245,14 +263,16 @@ __global__ void __launch_bounds__(256) elt_kernel(const EltTask* __restrict__ ta
         g.x = y.x > 0.f ? to_tf32(g.x) : 0.f; g.y = y.y > 0.f ? to_tf32(g.y) : 0.f;
         g.z = y.z > 0.f ? to_tf32(g.z) : 0.f; g.w = y.w > 0.f ? to_tf32(g.w) : 0.f;
         st4(t.o + (kc * 256 + s) * 4, g);
+        st_half4(t.o, kc, s, g);
       }
     } break;
 
-    case OP_SCATTER: {  // a = NCHW [128][196] grad, b = Y planes (mask, optional) -> o planes
+    case OP_SCATTER: {  // a = NCHW [128][196] grad (times loss scale), b = Y planes (mask, optional) -> o planes
+      const float sc = t.scale[0];
       for (int i = tid; i < kKC * 196; i += 256) {
         const int kc = i / 196, p = i % 196, s = valid_slot16(p);
-        float4 g = make_float4(t.a[(kc * 4) * 196 + p], t.a[(kc * 4 + 1) * 196 + p], t.a[(kc * 4 + 2) * 196 + p],
-                               t.a[(kc * 4 + 3) * 196 + p]);
+        float4 g = make_float4(sc * t.a[(kc * 4) * 196 + p], sc * t.a[(kc * 4 + 1) * 196 + p],
+                               sc * t.a[(kc * 4 + 2) * 196 + p], sc * t.a[(kc * 4 + 3) * 196 + p]);
         float* d = t.o + (kc * 256 + s) * 4;
         if (t.flags & EF_ACCUM) { const float4 old = ld4(d); g.x += old.x; g.y += old.y; g.z += old.z; g.w += old.w; }
         if (t.b) {
@@ -261,6 +281,7 @@ __global__ void __launch_bounds__(256) elt_kernel(const EltTask* __restrict__ ta
           g.z = y.z > 0.f ? to_tf32(g.z) : 0.f; g.w = y.w > 0.f ? to_tf32(g.w) : 0.f;
         }
         st4(d, g);
+        st_half4(t.o, kc, s, g);
       }
     } break;
 
@@ -273,6 +294,36 @@ __global__ void __launch_bounds__(256) elt_kernel(const EltTask* __restrict__ ta
 
     default: break;
   }
+}
+
+// Loss scale of one backward pass: the largest power of two that brings max|d(final)| to <= 2^10,
+// so that the fp16 shadow copies of the gradients stay in the normal fp16 range (fp32 planes carry
+// the same scaled values; every parameter gradient is multiplied by scale[1] = 1/scale on its way out).
+__global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, size_t n, unsigned int* amax_bits) {
+  float m = 0.f;
+  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(amax_bits, __float_as_uint(m));
+}
+__global__ void scale_kernel(float* scale /* [0]=scale [1]=1/scale, [2]=amax bits */) {
+  const float amax = __uint_as_float(reinterpret_cast<unsigned int*>(scale)[2]);
+  float s = 1.f;
+  if (amax > 0.f) {
+    int e;
+    frexpf(amax, &e);  // amax = f * 2^e, f in [0.5, 1)
+    s = ldexpf(1.f, 10 - e);
+  }
+  scale[0] = s;
+  scale[1] = 1.f / s;
+}
+
+cudaError_t launch_loss_scale(const float* grad, size_t n, float* scale, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(scale, 0, 16, stream);
+  if (e != cudaSuccess) return e;
+  amax_kernel<<<296, 256, 0, stream>>>(grad, n, reinterpret_cast<unsigned int*>(scale) + 2);
+  scale_kernel<<<1, 1, 0, stream>>>(scale);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_elt(const EltTask* d_tasks, int n_tasks, cudaStream_t stream) {

@@ -23,6 +23,7 @@ enum EltFlags : int {
   EF_MAX = 4,      // OP_MINMAX*: max instead of min
   EF_A_MAP = 8,    // operand a is a 1-channel map (broadcast over channels)
   EF_B_MAP = 16,   // operand b is a 1-channel map
+  EF_HALF = 32,    // also write the fp16 shadow behind the plane-typed output `o`
 };
 
 struct EltTask {
@@ -38,7 +39,8 @@ struct EltTask {
   float* dw;
   float* dw2;
   int* idx;
-  int64_t pad_[5];
+  const float* scale;  // {loss scale, 1/loss scale} of this backward pass (backward ops only)
+  int64_t pad_[4];
 };
 static_assert(sizeof(EltTask) == 128, "EltTask must stay 128 bytes");
 

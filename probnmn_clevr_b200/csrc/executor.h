@@ -10,6 +10,13 @@
 // zero slot of the same plane, of the previous plane, or of the staging buffer's lead gap.
 //   P16: S=16, 256 slots  (dilation 1, 2)      P18: S=18, 324 slots (dilation 4)
 //   P22: S=22, 484 slots  (dilation 8)
+//
+// fp16 shadow ("half planes"): a buffer that takes part in a weight gradient (conv inputs X and
+// pre-activation gradients dZ) is followed in memory by an fp16 copy hbuf[c/8][slot][8] (16 bytes
+// per slot again, so taps stay row shifts).  The wgrad GEMM contracts over SLOTS, which makes both
+// operands "MN-major"; tcgen05 offers no unswizzled MN-major layout for tf32, but it does for
+// 16-bit types, and fp16 has the same 10-bit mantissa as tf32.  Gradients are kept in fp16 range by
+// one power-of-two loss scale per backward pass (see scale_kernel in elementwise.cu).
 #pragma once
 #include <cstdint>
 
@@ -40,7 +47,11 @@ enum ConvFlags : int {
   F_DOTSIG = 8,   // map_out[slot] = sigmoid(sum_n y[n]*w3[n] + b3)   (fused 1x1 conv + sigmoid)
   F_MASK = 16,    // y = aux[n] > 0 ? y : 0                            (ReLU backward)
   F_ACCUM = 32,   // y += out[] (existing contents)
+  F_HALF = 64,    // also write the fp16 shadow copy behind out[]
 };
+
+// byte offset of the fp16 shadow behind a 128-channel fp32 plane buffer of P slots per plane
+__host__ __device__ inline size_t shadow_bytes(int P) { return static_cast<size_t>(kKC) * P * 16; }
 
 struct ConvCfg {
   int n_kb;        // number of 16-channel k-blocks (K = n_kb*16*ntaps)
@@ -71,8 +82,8 @@ static_assert(sizeof(ConvTask) == 128, "ConvTask must stay 128 bytes");
 
 // ---- wgrad ---------------------------------------------------------------------------------------
 struct WgradInst {
-  const float* dz;  // gradient wrt the conv's pre-activation, input-format planes [32][P][4]
-  const float* x;   // the conv's input, same plane format, plane 0 of the cin tile
+  const void* dz;  // fp16 half planes [16][P][8] of the (loss-scaled) pre-activation gradient
+  const void* x;   // fp16 half planes of the conv's input (half plane 0 of the 128-channel cin tile)
 };
 struct WgradTask {
   const WgradInst* inst;  // device array
@@ -85,7 +96,7 @@ struct WgradTask {
   int cin0;         // first input channel of this 128-wide tile
   int ksize;        // 3 or 1
   float* dw;        // reference-layout gradient: [cout][cin_total][k][k]
-  int pad_;
+  const float* scale;  // {loss scale, 1/loss scale}; dW is accumulated times scale[1]
 };
 
 }  // namespace pnmn

@@ -1,4 +1,6 @@
 // Layout kernels: reference-layout parameters / NCHW features  <->  executor formats.
+#include <cuda_fp16.h>
+
 #include "executor.h"
 #include "layout.h"
 #include "tcgen05.cuh"
@@ -63,6 +65,12 @@ __global__ void __launch_bounds__(256) nchw_to_planes_kernel(const float* __rest
     const int p = threadIdx.x, slot = (p / kHW) * 16 + (p % kHW);
     float4 v = make_float4(to_tf32(tile[p]), to_tf32(tile[196 + p]), to_tf32(tile[392 + p]), to_tf32(tile[588 + p]));
     *reinterpret_cast<float4*>(d + slot * 4) = v;
+    // fp16 shadow [C/8][256][8] behind the C/4 fp32 planes (operand of the stem conv1 weight gradient)
+    uint8_t* hb = reinterpret_cast<uint8_t*>(dst + off) + static_cast<size_t>(C / 4) * 256 * 16;
+    const __half2 h0 = __floats2half2_rn(fminf(v.x, 65504.f), fminf(v.y, 65504.f));
+    const __half2 h1 = __floats2half2_rn(fminf(v.z, 65504.f), fminf(v.w, 65504.f));
+    *reinterpret_cast<uint2*>(hb + (static_cast<size_t>(kc >> 1) * 256 + slot) * 16 + (kc & 1) * 8) =
+        make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
   }
 }
 

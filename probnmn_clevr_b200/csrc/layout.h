@@ -22,6 +22,7 @@ struct BiasGradTaskH {  // mirrors BiasGradTask in wgrad.cu
   int n_inst;
   int P;
   float* db;
+  const float* scale;
 };
 
 cudaError_t launch_pack(const PackTask* d_tasks, int n_tasks, int total_tiles, const float* params,
@@ -33,5 +34,6 @@ cudaError_t launch_conv(const ConvTask* d_tasks, int n_tasks, const ConvCfg* d_c
 cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, cudaStream_t stream);
 cudaError_t launch_bias_grad(const void* d_tasks, int n_tasks, int split, cudaStream_t stream);
 cudaError_t launch_elt(const EltTask* d_tasks, int n_tasks, cudaStream_t stream);
+cudaError_t launch_loss_scale(const float* grad, size_t n, float* scale, cudaStream_t stream);
 
 }  // namespace pnmn

@@ -37,7 +37,7 @@ int fail(const std::string& s) {
 // ---- symbolic pointers: (arena id << 56) | byte offset, resolved at launch time ----------------
 enum ArenaId : int {
   AR_NULL = 0, AR_A16, AR_A18, AR_A22, AR_MAPS, AR_DMAPS, AR_IDX, AR_PACKED, AR_PARAMS, AR_GRADS,
-  AR_BLOB, AR_FINAL, AR_GRADOUT, AR_COUNT
+  AR_BLOB, AR_FINAL, AR_GRADOUT, AR_AIN, AR_SCRATCH, AR_COUNT
 };
 template <class T>
 T* sym(int arena, int64_t byte_off) {
@@ -51,9 +51,10 @@ void resolve(T*& p, const uint64_t* base) {
 }
 
 constexpr int64_t kGuard = 16384;  // zero bytes in front of unit 0 of every plane arena
-constexpr int64_t kUnit16 = 32ll * 256 * 16;
-constexpr int64_t kUnit18 = 32ll * 324 * 16;
-constexpr int64_t kUnit22 = 32ll * 484 * 16;
+// arena unit = 32 fp32 planes followed by their fp16 shadow (16 half planes), see executor.h
+constexpr int64_t kUnit16 = 48ll * 256 * 16;
+constexpr int64_t kUnit18 = 48ll * 324 * 16;
+constexpr int64_t kUnit22 = 48ll * 484 * 16;
 constexpr int kInstChunk = 16;     // instances per wgrad CTA
 constexpr int kBiasSplit = 8;
 
@@ -289,6 +290,13 @@ struct Builder {
     return sym<float>(AR_A22, kGuard + unit * kUnit22);
   }
   float* p16(int unit) const { return pfmt(kP16, unit); }
+  // fp16 shadow behind a 128-channel plane buffer (symbolic pointer arithmetic on the byte offset)
+  static const void* shadow(const float* p, PlaneFmt f) {
+    return reinterpret_cast<const void*>(reinterpret_cast<uint64_t>(p) + shadow_bytes(f.P));
+  }
+  const float* scalep() const { return sym<const float>(AR_SCRATCH, 0); }
+  int64_t ain_unit_bytes() const { return static_cast<int64_t>(m.in_ch / 4) * 256 * 16 * 3 / 2; }
+  float* ainp(int k) const { return sym<float>(AR_AIN, kGuard + k * ain_unit_bytes()); }
   float* mapp(int i) const { return sym<float>(AR_MAPS, static_cast<int64_t>(i) * 1024); }
   float* dmapp(int i) const { return sym<float>(AR_DMAPS, static_cast<int64_t>(i) * 1024); }
   const float* param(int64_t off) const { return sym<const float>(AR_PARAMS, off * 4); }
@@ -330,8 +338,10 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   p.xin_unit.assign(B, -1);
   Builder bd(p);
   Sched fs(B), bs(B);
-  const int in_units = m->in_ch / 128;
+  int n_ain = 0;  // valid samples so far (index into the stem-input arena)
 
+  const int HF = p.need_grad ? F_HALF : 0;      // conv outputs also feed weight gradients
+  const int EHF = p.need_grad ? EF_HALF : 0;
   p.nmaps = 1;  // map 0 = the constant all-ones attention of `scene` (nmn.py:216)
   const int ones_val = bd.new_val(VK_ONES, 1, 0, false);
   bool ones_emitted = false;
@@ -392,7 +402,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
     p.stats[0]++;
 
     // ---------------- stem (nmn.py:67-72,183) ----------------
-    const int xin = bd.alloc16(in_units);
+    const int xin = n_ain++;
     p.xin_unit[n] = xin;
     y1s_unit[n] = bd.alloc16();
     feat_unit[n] = bd.alloc16();
@@ -403,13 +413,13 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
     {
       const ConvW& c1 = m->convs[m->stem1];
       ConvTask t{};
-      t.cfg = bd.make_cfg(m->in_ch / 16, m->in_ch / 16, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE);
-      t.in[0][0] = bd.p16(xin); t.out[0] = bd.p16(y1s_unit[n]);
+      t.cfg = bd.make_cfg(m->in_ch / 16, m->in_ch / 16, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE | HF);
+      t.in[0][0] = bd.ainp(xin); t.out[0] = bd.p16(y1s_unit[n]);
       t.w = bd.packed(c1.pk_fwd); t.bias = bd.param(c1.b_off);
       fs.add_conv(n, t, 0);
       const ConvW& c2 = m->convs[m->stem2];
       ConvTask u{};
-      u.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE);
+      u.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE | HF);
       u.in[0][0] = bd.p16(y1s_unit[n]); u.out[0] = bd.p16(feat_unit[n]);
       u.w = bd.packed(c2.pk_fwd); u.bias = bd.param(c2.b_off);
       fs.add_conv(n, u, 0);
@@ -426,7 +436,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           Val& vo = bd.vals[r.out];
           const Val& a = bd.vals[r.in0]; const Val& b = bd.vals[r.in1];
           EltTask e{}; e.op = OP_MINMAX;
-          e.flags = (r.kind == PNMN_TOK_OR ? EF_MAX : 0) | (a.ch == 1 ? EF_A_MAP : 0) | (b.ch == 1 ? EF_B_MAP : 0);
+          e.flags = EHF | (r.kind == PNMN_TOK_OR ? EF_MAX : 0) | (a.ch == 1 ? EF_A_MAP : 0) | (b.ch == 1 ? EF_B_MAP : 0);
           e.a = a.ch == 1 ? bd.mapp(a.unit) : bd.p16(a.unit);
           e.b = b.ch == 1 ? bd.mapp(b.unit) : bd.p16(b.unit);
           if (vo.ch == 1) { vo.unit = static_cast<int>(p.nmaps++); e.o = bd.mapp(vo.unit); }
@@ -449,7 +459,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           r.y_unit[0] = bd.alloc16(); r.y_unit[1] = bd.alloc16(); r.y_unit[2] = bd.alloc16();
           vo.unit = r.y_unit[2];
           ConvTask t{};
-          t.cfg = bd.make_cfg(16, 8, 1, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE);
+          t.cfg = bd.make_cfg(16, 8, 1, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE | HF);
           t.in[0][0] = bd.p16(bd.vals[r.in0].unit); t.in[1][0] = bd.p16(bd.vals[r.in1].unit);
           t.out[0] = bd.p16(r.y_unit[0]); t.w = bd.packed(pj.pk_fwd); t.bias = bd.param(pj.b_off);
           fs.add_conv(n, t, 0);
@@ -457,7 +467,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           for (int i = 1; i < 3; ++i) {
             const ConvW& cw = m->convs[md.convs[i]];
             ConvTask u{};
-            u.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE);
+            u.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE | HF);
             u.in[0][0] = bd.p16(r.y_unit[i - 1]); u.out[0] = bd.p16(r.y_unit[i]);
             u.w = bd.packed(cw.pk_fwd); u.bias = bd.param(cw.b_off);
             fs.add_conv(n, u, 0);
@@ -471,7 +481,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             r.x0_is_feat = true;  // feats * ones == feats: feed the stem output straight in
           } else {
             r.x0_unit = bd.alloc16();
-            EltTask e{}; e.op = OP_ATTEND; e.a = featp; e.b = bd.mapp(a.unit); e.o = bd.p16(r.x0_unit);
+            EltTask e{}; e.op = OP_ATTEND; e.flags = EHF; e.a = featp; e.b = bd.mapp(a.unit); e.o = bd.p16(r.x0_unit);
             fs.add_elt(n, e);
             x = bd.p16(r.x0_unit);
           }
@@ -485,7 +495,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             const bool last = i + 1 == r.nconv;
             r.y_unit[i] = bd.alloc_fmt(fout);
             ConvTask t{};
-            t.cfg = bd.make_cfg(8, 8, 9, d, fin, fout, fout, F_BIAS | F_RELU | F_STORE | ((last && head) ? F_DOTSIG : 0));
+            t.cfg = bd.make_cfg(8, 8, 9, d, fin, fout, fout, F_BIAS | F_RELU | F_STORE | HF | ((last && head) ? F_DOTSIG : 0));
             t.in[0][0] = x; t.out[0] = bd.pfmt(fout, r.y_unit[i]);
             t.w = bd.packed(cw.pk_fwd); t.bias = bd.param(cw.b_off);
             if (last && head) {
@@ -530,7 +540,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
       return bd.p16(v.gunit);
     };
     auto add_inst = [&](int conv_id, const float* dz, const float* x, PlaneFmt f, int dil) {
-      bd.conv_insts[conv_id].push_back(WgradInst{dz, x});
+      bd.conv_insts[conv_id].push_back(WgradInst{Builder::shadow(dz, f), Builder::shadow(x, f)});
       bd.conv_inst_fmt[conv_id] = f;
       bd.conv_inst_dil[conv_id] = dil;
     };
@@ -538,7 +548,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
     // ---------------- backward stages ----------------
     {  // d(final module output) arrives as NCHW from the classifier
       Val& v = bd.vals[out];
-      EltTask e{}; e.op = OP_SCATTER;
+      EltTask e{}; e.op = OP_SCATTER; e.scale = bd.scalep();
       e.a = sym<const float>(AR_GRADOUT, static_cast<int64_t>(n) * 128 * 196 * 4);
       e.b = fused_mask(v) ? bd.p16(v.unit) : nullptr;
       e.o = gbuf(v); e.flags = v.gwritten ? EF_ACCUM : 0;
@@ -577,7 +587,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
         case PNMN_TOK_SAME: {
           const Val& a = bd.vals[r.in0];
           Val& fv = bd.vals[feat_val];
-          EltTask e{}; e.op = OP_SAME_BWD;
+          EltTask e{}; e.op = OP_SAME_BWD; e.scale = bd.scalep();
           e.a = featp; e.b = bd.mapp(a.unit); e.c = bd.mapp(vo.unit); e.g = bd.dmapp(vo.unit);
           e.o = a.kind == VK_ONES ? nullptr : bd.dmapp(a.unit);
           e.o2 = const_cast<float*>(dfeatp); e.flags = fv.gwritten ? EF_ACCUM : 0; fv.gwritten = true;
@@ -593,7 +603,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             add_inst(md.convs[i], dz, bd.p16(r.y_unit[i - 1]), kP16, 1);
             const int du = bd.alloc16();
             ConvTask t{};
-            t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_STORE | F_MASK);
+            t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_STORE | F_MASK | F_HALF);
             t.in[0][0] = dz; t.out[0] = bd.p16(du); t.aux[0] = bd.p16(r.y_unit[i - 1]);
             t.w = bd.packed(cw.pk_bwd);
             bs.add_conv(n, t, 0);
@@ -604,10 +614,11 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           for (int h = 0; h < 2; ++h) {
             Val& v = bd.vals[ins[h]];
             // projection wgrad: dW[:, 128h:128h+128] += dZp (x) in_h
-            bd.conv_insts[md.convs[0]].push_back(WgradInst{dz, bd.p16(v.unit)});  // even = in0, odd = in1
+            bd.conv_insts[md.convs[0]].push_back(
+                WgradInst{Builder::shadow(dz, kP16), Builder::shadow(bd.p16(v.unit), kP16)});  // even = in0, odd = in1
             const bool fm = fused_mask(v);
             ConvTask t{};
-            t.cfg = bd.make_cfg(8, 8, 1, 1, kP16, kP16, kP16, F_STORE | (fm ? F_MASK : 0) | (v.gwritten ? F_ACCUM : 0));
+            t.cfg = bd.make_cfg(8, 8, 1, 1, kP16, kP16, kP16, F_STORE | (fm ? (F_MASK | F_HALF) : 0) | (v.gwritten ? F_ACCUM : 0));
             t.in[0][0] = dz; t.out[0] = gbuf(v); t.aux[0] = fm ? bd.p16(v.unit) : nullptr;
             t.w = bd.packed(pj.pk_bwd + static_cast<int64_t>(h) * 8 * 2048);
             v.gwritten = true;
@@ -622,7 +633,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           const float* dz;
           if (head) {
             const int du = bd.alloc16();
-            EltTask e{}; e.op = OP_DOTSIG_BWD;
+            EltTask e{}; e.op = OP_DOTSIG_BWD; e.scale = bd.scalep();
             e.g = bd.dmapp(vo.unit); e.c = bd.mapp(vo.unit); e.a = bd.p16(r.y_unit[nc - 1]);
             e.w = bd.param(md.head_w); e.dw = bd.grad(md.head_w); e.dw2 = bd.grad(md.head_b);
             e.o = bd.p16(du);
@@ -642,7 +653,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             if (i > 0) {
               const PlaneFmt fprev = fmt_for_dilation(dil_of(i - 1));
               const int du = bd.alloc_fmt(fprev);
-              t.cfg = bd.make_cfg(8, 8, 9, d, f, fprev, f, F_STORE | F_MASK);
+              t.cfg = bd.make_cfg(8, 8, 9, d, f, fprev, f, F_STORE | F_MASK | F_HALF);
               t.out[0] = bd.pfmt(fprev, du); t.aux[0] = xin_i;
               bs.add_conv(n, t, f.P == kP22.P ? 1 : 0);
               dz = t.out[0];
@@ -675,12 +686,14 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
       const int dz1 = bd.alloc16();
       const ConvW& c2 = m->convs[m->stem2];
       ConvTask t{};
-      t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_STORE | F_MASK);
+      t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_STORE | F_MASK | F_HALF);
       t.in[0][0] = dfeatp; t.out[0] = bd.p16(dz1); t.aux[0] = bd.p16(y1s_unit[n]);
       t.w = bd.packed(c2.pk_bwd);
       bs.add_conv(n, t, 0);
       add_inst(m->stem2, dfeatp, bd.p16(y1s_unit[n]), kP16, 1);
-      add_inst(m->stem1, bd.p16(dz1), bd.p16(xin), kP16, 1);
+      bd.conv_insts[m->stem1].push_back(WgradInst{
+          Builder::shadow(bd.p16(dz1), kP16),
+          reinterpret_cast<const void*>(reinterpret_cast<uint64_t>(bd.ainp(xin)) + static_cast<uint64_t>(m->in_ch / 4) * 256 * 16)});
     }
   }
 
@@ -707,13 +720,13 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             t.inst = sym<const WgradInst>(AR_BLOB, (first + i0) * static_cast<int64_t>(sizeof(WgradInst)));
             t.n_inst = std::min(kInstChunk, n_inst - i0);
             t.tap_row = 0; t.ntaps_x = 1; t.dil = 1; t.S = f.S; t.P = f.P;
-            t.cin_total = 256; t.cin0 = 128 * h; t.ksize = 1; t.dw = bd.grad(cw.w_off);
+            t.cin_total = 256; t.cin0 = 128 * h; t.ksize = 1; t.dw = bd.grad(cw.w_off); t.scale = bd.scalep();
             p.wtasks.push_back(t);
           }
           if (h == 0) {
             BiasGradTaskH b{};
             b.inst = sym<const WgradInst>(AR_BLOB, first * static_cast<int64_t>(sizeof(WgradInst)));
-            b.n_inst = n_inst; b.P = f.P; b.db = bd.grad(cw.b_off);
+            b.n_inst = n_inst; b.P = f.P; b.db = bd.grad(cw.b_off); b.scale = bd.scalep();
             p.btasks.push_back(b);
           }
         }
@@ -724,7 +737,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
         const int64_t first = static_cast<int64_t>(p.insts.size());
         for (const WgradInst& wi : v) {
           WgradInst x = wi;
-          x.x = reinterpret_cast<const float*>(reinterpret_cast<uint64_t>(wi.x) + static_cast<uint64_t>(tile) * kUnit16);
+          x.x = reinterpret_cast<const void*>(reinterpret_cast<uint64_t>(wi.x) + static_cast<uint64_t>(tile) * 16 * 256 * 16);
           p.insts.push_back(x);
         }
         const int n_inst = static_cast<int>(v.size());
@@ -734,13 +747,13 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             t.inst = sym<const WgradInst>(AR_BLOB, (first + i0) * static_cast<int64_t>(sizeof(WgradInst)));
             t.n_inst = std::min(kInstChunk, n_inst - i0);
             t.tap_row = ty; t.ntaps_x = 3; t.dil = bd.conv_inst_dil[c]; t.S = f.S; t.P = f.P;
-            t.cin_total = cw.cin; t.cin0 = 128 * tile; t.ksize = 3; t.dw = bd.grad(cw.w_off);
+            t.cin_total = cw.cin; t.cin0 = 128 * tile; t.ksize = 3; t.dw = bd.grad(cw.w_off); t.scale = bd.scalep();
             p.wtasks.push_back(t);
           }
         if (tile == 0) {
           BiasGradTaskH b{};
           b.inst = sym<const WgradInst>(AR_BLOB, first * static_cast<int64_t>(sizeof(WgradInst)));
-          b.n_inst = n_inst; b.P = f.P; b.db = bd.grad(cw.b_off);
+          b.n_inst = n_inst; b.P = f.P; b.db = bd.grad(cw.b_off); b.scale = bd.scalep();
           p.btasks.push_back(b);
         }
       }
@@ -794,6 +807,11 @@ extern "C" int pnmn_plan_sizes(const pnmn_plan* p, int64_t* s) {
   s[PNMN_SZ_DMAPS] = p->nmaps * 256;
   s[PNMN_SZ_IDX] = std::max<int64_t>(p->nidx, 1);
   s[PNMN_SZ_BLOB] = p->blob_bytes;
+  {
+    int64_t n_valid = 0;
+    for (uint8_t v : p->valid) n_valid += v;
+    s[PNMN_SZ_AIN] = (2 * kGuard + std::max<int64_t>(n_valid, 1) * (static_cast<int64_t>(p->m->in_ch / 4) * 256 * 16 * 3 / 2)) / 4;
+  }
   return 0;
 }
 
@@ -818,6 +836,8 @@ void fill_bases(uint64_t* base, const pnmn_buffers* b, const void* final_out, co
   base[AR_BLOB] = reinterpret_cast<uint64_t>(b->blob);
   base[AR_FINAL] = reinterpret_cast<uint64_t>(final_out);
   base[AR_GRADOUT] = reinterpret_cast<uint64_t>(grad_out);
+  base[AR_AIN] = reinterpret_cast<uint64_t>(b->ain);
+  base[AR_SCRATCH] = reinterpret_cast<uint64_t>(b->scratch);
 }
 
 void resolve_conv(ConvTask& t, const uint64_t* base) {
@@ -829,7 +849,7 @@ void resolve_conv(ConvTask& t, const uint64_t* base) {
 void resolve_elt(EltTask& t, const uint64_t* base) {
   resolve(t.a, base); resolve(t.b, base); resolve(t.c, base); resolve(t.g, base);
   resolve(t.o, base); resolve(t.o2, base); resolve(t.w, base); resolve(t.dw, base); resolve(t.dw2, base);
-  resolve(t.idx, base);
+  resolve(t.idx, base); resolve(t.scale, base);
 }
 
 int conv_impl_simt() {
@@ -883,7 +903,8 @@ extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const f
     EltTask* e = reinterpret_cast<EltTask*>(p.host_blob.data() + p.off_felt);
     for (size_t i = 0; i < p.felt.size(); ++i) { e[i] = p.felt[i]; resolve_elt(e[i], base); }
     int64_t* x = reinterpret_cast<int64_t*>(p.host_blob.data() + p.off_xin);
-    for (int n = 0; n < p.B; ++n) x[n] = p.xin_unit[n] < 0 ? -1 : (kGuard + p.xin_unit[n] * kUnit16) / 4;
+    const int64_t ain_unit = static_cast<int64_t>(m.in_ch / 4) * 256 * 16 * 3 / 2;
+    for (int n = 0; n < p.B; ++n) x[n] = p.xin_unit[n] < 0 ? -1 : (kGuard + p.xin_unit[n] * ain_unit) / 4;
   }
   CUDA_OK(cudaMemcpyAsync(bufs->blob, p.host_blob.data(), static_cast<size_t>(fwd_bytes), cudaMemcpyHostToDevice, st));
   // pack weights (tf32, MMA tile order): the packed buffer's head holds the pack-task table
@@ -900,7 +921,7 @@ extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const f
   }
   fill_ones_map_kernel<<<1, 256, 0, st>>>(bufs->maps);
   // features -> planes for every valid sample
-  CUDA_OK(launch_nchw_to_planes(features, bufs->arena16, p.B, m.in_ch,
+  CUDA_OK(launch_nchw_to_planes(features, bufs->ain, p.B, m.in_ch,
                                 reinterpret_cast<const int64_t*>(static_cast<const uint8_t*>(bufs->blob) + p.off_xin), st));
   return run_launches(p, p.flaunch, static_cast<const uint8_t*>(bufs->blob), false, st);
 }
@@ -920,13 +941,14 @@ extern "C" int pnmn_nmn_backward(pnmn_plan* pp, const pnmn_buffers* bufs, const 
     WgradInst* wi = reinterpret_cast<WgradInst*>(p.host_blob.data() + p.off_inst);
     for (size_t i = 0; i < p.insts.size(); ++i) { wi[i] = p.insts[i]; resolve(wi[i].dz, base); resolve(wi[i].x, base); }
     WgradTask* wt = reinterpret_cast<WgradTask*>(p.host_blob.data() + p.off_wt);
-    for (size_t i = 0; i < p.wtasks.size(); ++i) { wt[i] = p.wtasks[i]; resolve(wt[i].inst, base); resolve(wt[i].dw, base); }
+    for (size_t i = 0; i < p.wtasks.size(); ++i) { wt[i] = p.wtasks[i]; resolve(wt[i].inst, base); resolve(wt[i].dw, base); resolve(wt[i].scale, base); }
     BiasGradTaskH* bt = reinterpret_cast<BiasGradTaskH*>(p.host_blob.data() + p.off_bt);
-    for (size_t i = 0; i < p.btasks.size(); ++i) { bt[i] = p.btasks[i]; resolve(bt[i].inst, base); resolve(bt[i].db, base); }
+    for (size_t i = 0; i < p.btasks.size(); ++i) { bt[i] = p.btasks[i]; resolve(bt[i].inst, base); resolve(bt[i].db, base); resolve(bt[i].scale, base); }
   }
   CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t*>(bufs->blob) + p.off_bconv, p.host_blob.data() + p.off_bconv,
                           static_cast<size_t>(p.blob_bytes - p.off_bconv), cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemsetAsync(bufs->dmaps, 0, static_cast<size_t>(p.nmaps) * 1024, st));
+  CUDA_OK(launch_loss_scale(grad_final_out, static_cast<size_t>(p.B) * 128 * 196, bufs->scratch, st));
   return run_launches(p, p.blaunch, static_cast<const uint8_t*>(bufs->blob), true, st);
 }
 

@@ -7,10 +7,15 @@
 // accumulating into one nn.Conv2d.weight.grad, probnmn/models/nmn.py:114-115,229).
 //
 // GEMM view per tap: M = cout (128, from dZ), N = cin (128, from X), K = pixel slots.  Both
-// operands are "MN-major" in the plane format (4 channels contiguous per slot), so the planes
-// are consumed as they are; a tap is again just a different start address of the X descriptor.
+// operands are "MN-major" (channels contiguous per slot).  tcgen05 has no unswizzled MN-major
+// layout for tf32 (measured: such an MMA returns zeros), so the operands are the fp16 shadow
+// copies ("half planes", 8 channels = 16 B per slot; executor.h) and the MMA is kind::f16 with
+// fp32 accumulation: same 10-bit mantissa as tf32, twice the tensor rate, half the bytes.  A tap is
+// again just a different start address of the X descriptor.
 // One CTA owns one tap ROW (3 taps -> 3 accumulators of 128 TMEM columns) of one weight tensor
 // and walks a list of instances, streaming 64-slot chunks of dZ and X through an mbarrier ring.
+#include <cuda_fp16.h>
+
 #include "executor.h"
 #include "tcgen05.cuh"
 
@@ -18,11 +23,12 @@ namespace pnmn {
 
 constexpr int kWgThreads = 256;
 constexpr int kWgChunk = 64;        // slots (K) per stage
-constexpr int kWgStages = 3;
+constexpr int kWgStages = 5;
 constexpr int kWgHeader = 1024;
 constexpr int kWgSmemTotal = 227 * 1024;
+constexpr int kHP = kC / 8;              // fp16 half planes per 128-channel tensor
 constexpr int kWgMaxXS = kWgChunk + 16;  // chunk + 2*dil halo, dil <= 8
-constexpr int kWgStageBytes = kKC * kWgChunk * 16 + kKC * kWgMaxXS * 16;  // 32 KB + 40 KB
+constexpr int kWgStageBytes = kHP * kWgChunk * 16 + kHP * kWgMaxXS * 16;  // 16 KB + 20 KB
 static_assert(kWgHeader + kWgStages * kWgStageBytes <= kWgSmemTotal, "wgrad smem");
 
 struct WgSmemHeader {
@@ -41,10 +47,11 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int halo = t.ntaps_x == 3 ? t.dil : 0;
-  const int xs = kWgChunk + 2 * halo;                 // X slots per plane per stage
-  const int n_chunks = (kHW * t.S + kWgChunk - 1) / kWgChunk;
+  const int xs = kWgChunk + 2 * halo;                 // X slots per half plane per stage
+  const int n_valid = kHW * t.S;                      // slots that can carry a non-zero dZ
+  const int n_chunks = (n_valid + kWgChunk - 1) / kWgChunk;
   const int row_shift = t.ntaps_x == 3 ? (t.tap_row - 1) * t.dil * t.S : 0;
-  const uint32_t dz_bytes = kKC * kWgChunk * 16;
+  const uint32_t dz_bytes = kHP * kWgChunk * 16;
   const int total = t.n_inst * n_chunks;
 
   if (threadIdx.x == 0) {
@@ -62,7 +69,7 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
   const uint32_t tmem_base = hdr->tmem_base;
 
   if (warp == 0) {
-    // producer: lane = plane index
+    // producer: lane = half plane index (lanes 16..31 idle)
     for (int it = 0; it < total; ++it) {
       const int st = it % kWgStages;
       const uint32_t ph = (it / kWgStages) & 1;
@@ -70,34 +77,41 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
       const uint32_t bar = smem_u32(&hdr->full[st]);
       if (lane == 0) {
         mbar_wait(smem_u32(&hdr->empty[st]), ph ^ 1);
-        mbar_arrive_expect_tx(bar, dz_bytes + kKC * xs * 16);
+        mbar_arrive_expect_tx(bar, dz_bytes + kHP * xs * 16);
       }
       __syncwarp();
-      const WgradInst wi = t.inst[inst];
-      const int c0 = ch * kWgChunk;
-      uint8_t* sdz = ring + st * kWgStageBytes;
-      uint8_t* sx = sdz + dz_bytes;
-      bulk_g2s(smem_u32(sdz + lane * kWgChunk * 16), wi.dz + (static_cast<ptrdiff_t>(lane) * t.P + c0) * 4,
-               kWgChunk * 16, bar);
-      bulk_g2s(smem_u32(sx + lane * xs * 16),
-               wi.x + (static_cast<ptrdiff_t>(lane) * t.P + c0 + row_shift - halo) * 4, xs * 16, bar);
+      if (lane < kHP) {
+        const WgradInst wi = t.inst[inst];
+        const int c0 = ch * kWgChunk;
+        uint8_t* sdz = ring + st * kWgStageBytes;
+        uint8_t* sx = sdz + dz_bytes;
+        const uint8_t* gdz = static_cast<const uint8_t*>(wi.dz);
+        const uint8_t* gx = static_cast<const uint8_t*>(wi.x);
+        bulk_g2s(smem_u32(sdz + lane * kWgChunk * 16), gdz + (static_cast<ptrdiff_t>(lane) * t.P + c0) * 16,
+                 kWgChunk * 16, bar);
+        bulk_g2s(smem_u32(sx + lane * xs * 16),
+                 gx + (static_cast<ptrdiff_t>(lane) * t.P + c0 + row_shift - halo) * 16, xs * 16, bar);
+      }
     }
   } else if (warp == 2) {
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(128, 128, 1, 1);
+      const uint32_t idesc = make_idesc_f16(128, 128, 1, 1);
       for (int it = 0; it < total; ++it) {
         const int st = it % kWgStages;
         mbar_wait(smem_u32(&hdr->full[st]), (it / kWgStages) & 1);
         tc_fence_after();
         const uint32_t sdz = smem_u32(ring + st * kWgStageBytes);
         const uint32_t sx = sdz + dz_bytes;
+        const int c0 = (it % n_chunks) * kWgChunk;
+        int nk = (n_valid - c0 + 15) / 16;  // 16-slot MMA steps that can still see a non-zero dZ
+        nk = nk > kWgChunk / 16 ? kWgChunk / 16 : nk;
         for (int tx = 0; tx < t.ntaps_x; ++tx) {
-#pragma unroll
-          for (int k8 = 0; k8 < kWgChunk / 8; ++k8) {
-            const uint64_t ad = make_smem_desc(sdz + k8 * 128u, 128u, kWgChunk * 16u);
-            const uint64_t bd = make_smem_desc(sx + (k8 * 8u + static_cast<uint32_t>(halo * tx)) * 16u, 128u,
+          for (int k16 = 0; k16 < nk; ++k16) {
+            // MN-major, no swizzle: LBO = next 8-slot K group (128 B), SBO = next half plane
+            const uint64_t ad = make_smem_desc(sdz + k16 * 256u, 128u, kWgChunk * 16u);
+            const uint64_t bd = make_smem_desc(sx + (k16 * 16u + static_cast<uint32_t>(halo * tx)) * 16u, 128u,
                                                static_cast<uint32_t>(xs) * 16u);
-            umma_tf32(tmem_base + tx * 128, ad, bd, idesc, (it | k8) != 0);
+            umma_f16(tmem_base + tx * 128, ad, bd, idesc, (it | k16) != 0);
           }
         }
         umma_commit(smem_u32(&hdr->empty[st]));
@@ -110,6 +124,7 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
     mbar_wait(smem_u32(&hdr->tmem_full), 0);
     tc_fence_after();
     const int kk = t.ksize * t.ksize;
+    const float unscale = t.scale ? __ldg(t.scale + 1) : 1.f;
     for (int tx = 0; tx < t.ntaps_x; ++tx) {
       const int tap = t.ksize == 3 ? t.tap_row * 3 + tx : 0;
       for (int chunk = 0; chunk < 4; ++chunk) {
@@ -120,7 +135,8 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int cin = t.cin0 + chunk * 32 + j;
-            atomicAdd(t.dw + (static_cast<size_t>(cout) * t.cin_total + cin) * kk + tap, __uint_as_float(v[j]));
+            atomicAdd(t.dw + (static_cast<size_t>(cout) * t.cin_total + cin) * kk + tap,
+                      __uint_as_float(v[j]) * unscale);
           }
         }
       }
@@ -136,22 +152,23 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgradTask* __rest
   const WgradTask t = tasks[blockIdx.x];
   const int kk = t.ksize * t.ksize;
   const int nslots = kHW * t.S;
+  const float unscale = t.scale ? t.scale[1] : 1.f;
   for (int idx = threadIdx.x; idx < t.ntaps_x * 128 * 128; idx += blockDim.x) {
     const int cin = idx % 128, cout = (idx / 128) % 128, tx = idx / (128 * 128);
     const int shift = t.ntaps_x == 3 ? ((t.tap_row - 1) * t.S + (tx - 1)) * t.dil : 0;
     float acc = 0.f;
     for (int i = 0; i < t.n_inst; ++i) {
       const WgradInst wi = t.inst[i];
-      const float* dz = wi.dz + static_cast<size_t>(cout / 4) * t.P * 4 + (cout % 4);
-      const float* x = wi.x + static_cast<ptrdiff_t>(cin / 4) * t.P * 4 + (cin % 4);
+      const __half* dz = static_cast<const __half*>(wi.dz) + static_cast<size_t>(cout / 8) * t.P * 8 + (cout % 8);
+      const __half* x = static_cast<const __half*>(wi.x) + static_cast<ptrdiff_t>(cin / 8) * t.P * 8 + (cin % 8);
       for (int p = 0; p < nslots; ++p) {
-        const float g = dz[p * 4];
-        if (g != 0.f) acc = fmaf(g, x[static_cast<ptrdiff_t>(p + shift) * 4], acc);
+        const float g = __half2float(dz[p * 8]);
+        if (g != 0.f) acc = fmaf(g, __half2float(x[static_cast<ptrdiff_t>(p + shift) * 8]), acc);
       }
     }
     const int tap = t.ksize == 3 ? t.tap_row * 3 + tx : 0;
     if (t.n_inst > 0)
-      atomicAdd(t.dw + (static_cast<size_t>(cout) * t.cin_total + t.cin0 + cin) * kk + tap, acc);
+      atomicAdd(t.dw + (static_cast<size_t>(cout) * t.cin_total + t.cin0 + cin) * kk + tap, acc * unscale);
   }
 }
 
@@ -161,6 +178,7 @@ struct BiasGradTask {
   int n_inst;
   int P;
   float* db;
+  const float* scale;
 };
 __global__ void __launch_bounds__(128) bias_grad_kernel(const BiasGradTask* __restrict__ tasks) {
   const BiasGradTask t = tasks[blockIdx.x];
@@ -168,10 +186,10 @@ __global__ void __launch_bounds__(128) bias_grad_kernel(const BiasGradTask* __re
   const int i0 = blockIdx.y, di = gridDim.y;
   float acc = 0.f;
   for (int i = i0; i < t.n_inst; i += di) {
-    const float* dz = t.inst[i].dz + static_cast<size_t>(n / 4) * t.P * 4 + (n % 4);
-    for (int p = 0; p < t.P; ++p) acc += dz[p * 4];
+    const __half* dz = static_cast<const __half*>(t.inst[i].dz) + static_cast<size_t>(n / 8) * t.P * 8 + (n % 8);
+    for (int p = 0; p < t.P; ++p) acc += __half2float(dz[p * 8]);
   }
-  if (t.n_inst > i0) atomicAdd(t.db + n, acc);
+  if (t.n_inst > i0) atomicAdd(t.db + n, acc * (t.scale ? t.scale[1] : 1.f));
 }
 
 cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, cudaStream_t stream) {

@@ -1,0 +1,405 @@
+"""Drop-in ``NeuralModuleNetwork`` (reference: probnmn/models/nmn.py) whose stem + module executor run in
+hand-written sm_100a CUDA behind the C ABI of ``include/pnmn.h``.
+
+Same constructor, ``from_config``, ``forward(features, programs, answers=None)`` -> ``{"predictions",
+"loss"[, "metrics"]}``, ``get_metrics`` and state-dict keys / shapes as the reference
+(SURVEY.md §8b, appendix B), so ``JointTrainingTrainer`` / ``ModuleTrainingTrainer``,
+``CheckpointManager.load`` and Adam work unchanged.  What differs is how the work is done:
+
+* the reference interprets every sample's program in python at batch size 1 with a device->host sync
+  per sample (nmn.py:191-238); here ONE copy of the token matrix goes to the host, the C++ program
+  compiler turns the batch into task tables, and the tensor-core executor runs them level by level;
+* all parameters are views into one flat fp32 buffer (reference names and shapes are kept), so the
+  library sees a base pointer + offsets and the gradient all-reduce is a single NCCL call.
+
+There is no CPU or eager fallback: without the CUDA library / a CUDA device ``forward`` raises.
+"""
+import ctypes
+from typing import Dict, List, Optional, Tuple
+
+import torch
+from torch import nn
+from torch.nn import functional as F
+
+from . import _lib as L
+from .vocabulary import Vocabulary
+
+SKIP_TOKENS = ("@@PADDING@@", "@@UNKNOWN@@", "@start@", "@end@", "unique")
+
+
+def module_class_of(token: str) -> Optional[str]:
+    """token -> module family; the substring rules (and their order) of nmn.py:90-111."""
+    if token in SKIP_TOKENS:
+        return None
+    if token == "scene":
+        return "scene"
+    if token == "intersect":
+        return "and"
+    if token == "union":
+        return "or"
+    if "equal" in token or token in ("less_than", "greater_than"):
+        return "comparison"
+    if "query" in token or token in ("exist", "count"):
+        return "query"
+    if "relate" in token:
+        return "relate"
+    if "same" in token:
+        return "same"
+    return "attention"
+
+
+_KIND = {None: L.TOK_SKIP, "scene": L.TOK_SCENE, "and": L.TOK_AND, "or": L.TOK_OR, "comparison": L.TOK_COMPARE,
+         "query": L.TOK_QUERY, "relate": L.TOK_RELATE, "same": L.TOK_SAME, "attention": L.TOK_ATTENTION}
+
+# (attribute name, out_ch, in_ch, kernel, kaiming-normal init?) per family, in forward order.
+# Shapes / names: nmn_modules.py:71-79 (Attention), 110-116 (Query), 144-157 (Relate), 194-197 (Same),
+# 231-237 (Comparison: `projection` keeps nn.Conv2d's default init).
+def _family_spec(family: str, d: int):
+    c3 = lambda n: (n, d, d, 3, True)
+    return {
+        "attention": [c3("conv1"), c3("conv2"), ("conv3", 1, d, 1, True)],
+        "query": [c3("conv1"), c3("conv2")],
+        "relate": [c3(f"conv{i}") for i in range(1, 6)] + [("conv6", 1, d, 1, True)],
+        "same": [("conv", 1, d + 1, 1, True)],
+        "comparison": [("projection", d, 2 * d, 1, False), c3("conv1"), c3("conv2")],
+    }[family]
+
+
+class _ModuleParameters(nn.Module):
+    """Parameter holder of one neural module; the math runs in the CUDA executor, not in ``forward``."""
+
+    def __init__(self, family: str, dim: int):
+        super().__init__()
+        self.family = family
+        for name, cout, cin, k, kaiming in _family_spec(family, dim):
+            conv = nn.Conv2d(cin, cout, kernel_size=k)
+            if kaiming:
+                nn.init.kaiming_normal_(conv.weight)
+            setattr(self, name, conv)
+
+    def forward(self, *args):  # pragma: no cover
+        raise RuntimeError("neural modules are executed by the CUDA program executor (NeuralModuleNetwork.forward)")
+
+
+class _Flatten(nn.Module):
+    def forward(self, x):
+        return x.reshape(x.size(0), -1)
+
+
+class _Average:
+    def __init__(self):
+        self.total, self.count = 0.0, 0
+
+    def __call__(self, v):
+        self.total += float(v)
+        self.count += 1
+
+    def get_metric(self, reset=False):
+        out = self.total / self.count if self.count else 0.0
+        if reset:
+            self.total, self.count = 0.0, 0
+        return out
+
+
+class _Accuracy(_Average):
+    def __call__(self, correct, total):
+        self.total += float(correct)
+        self.count += int(total)
+
+
+# ------------------------------------------------------------------------------------------------
+# workspaces: persistent, zero-initialised arenas (the executor relies on permanent zero padding)
+# ------------------------------------------------------------------------------------------------
+class _Workspace:
+    ARENAS = {L.SZ_ARENA16: "arena16", L.SZ_ARENA18: "arena18", L.SZ_ARENA22: "arena22", L.SZ_MAPS: "maps",
+              L.SZ_DMAPS: "dmaps", L.SZ_AIN: "ain"}
+
+    def __init__(self, device):
+        self.device = device
+        self.t: Dict[str, torch.Tensor] = {}
+        self.scratch = torch.zeros(64, device=device)
+
+    def ensure(self, sizes):
+        for slot, name in self.ARENAS.items():
+            need = int(sizes[slot])
+            cur = self.t.get(name)
+            if cur is None or cur.numel() < need:
+                self.t[name] = None  # free first
+                self.t[name] = torch.zeros(int(need * 1.25) + 1024, dtype=torch.float32, device=self.device)
+        need = int(sizes[L.SZ_IDX])
+        if self.t.get("idx") is None or self.t["idx"].numel() < need:
+            self.t["idx"] = torch.zeros(need * 2 + 16, dtype=torch.int32, device=self.device)
+        need = int(sizes[L.SZ_BLOB])
+        if self.t.get("blob") is None or self.t["blob"].numel() < need:
+            self.t["blob"] = torch.zeros(int(need * 1.5) + 4096, dtype=torch.uint8, device=self.device)
+
+
+class _WorkspacePool:
+    def __init__(self):
+        self.free: Dict[torch.device, List[_Workspace]] = {}
+
+    def acquire(self, device) -> _Workspace:
+        lst = self.free.setdefault(device, [])
+        return lst.pop() if lst else _Workspace(device)
+
+    def release(self, ws: _Workspace):
+        self.free.setdefault(ws.device, []).append(ws)
+
+
+_POOL = _WorkspacePool()
+
+
+class _Run:
+    """One forward's plan + workspace; released after backward (or when dropped)."""
+
+    def __init__(self, plan, ws, bufs):
+        self.plan, self.ws, self.bufs = plan, ws, bufs
+
+    def close(self):
+        if self.plan is not None:
+            L.lib().pnmn_plan_destroy(self.plan)
+            self.plan = None
+        if self.ws is not None:
+            _POOL.release(self.ws)
+            self.ws = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class _ExecutorFn(torch.autograd.Function):
+    """final_module_outputs = executor(features, programs; stem + module parameters)"""
+
+    @staticmethod
+    def forward(ctx, features, run, flat, exec_slices, *params):
+        B = features.shape[0]
+        final = torch.empty(B, 128, 14, 14, dtype=torch.float32, device=features.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(features.device).cuda_stream)
+        L.check(L.lib().pnmn_nmn_forward(run.plan, ctypes.byref(run.bufs), ctypes.c_void_p(features.data_ptr()),
+                                         ctypes.c_void_p(final.data_ptr()), stream), "pnmn_nmn_forward")
+        ctx.run, ctx.flat, ctx.exec_slices = run, flat, exec_slices
+        return final
+
+    @staticmethod
+    def backward(ctx, grad_final):
+        run, flat = ctx.run, ctx.flat
+        grad_final = grad_final.contiguous()
+        gflat = torch.zeros_like(flat)
+        run.bufs.grads = gflat.data_ptr()
+        stream = ctypes.c_void_p(torch.cuda.current_stream(grad_final.device).cuda_stream)
+        L.check(L.lib().pnmn_nmn_backward(run.plan, ctypes.byref(run.bufs), ctypes.c_void_p(grad_final.data_ptr()),
+                                          stream), "pnmn_nmn_backward")
+        grads = tuple(gflat[o:o + n].view(shape) for (o, n, shape) in ctx.exec_slices)
+        run.close()
+        return (None, None, None, None) + grads
+
+
+class NeuralModuleNetwork(nn.Module):
+    r"""
+    Holds a stem, one neural module per program token and a classifier, and answers a batch of questions
+    by executing their programs over image features (reference: probnmn/models/nmn.py:25-124).
+
+    Parameters
+    ----------
+    vocabulary:
+        Any object with AllenNLP's ``Vocabulary`` lookup methods (see ``vocabulary.py``), namespaces
+        "programs" and "answers".
+    image_feature_size: tuple (K, R, C), optional (default = (1024, 14, 14))
+    module_channels: int, optional (default = 128) -- the CUDA executor is specialised for 128
+    class_projection_channels: int, optional (default = 1024)
+    classifier_linear_size: int, optional (default = 1024)
+    """
+
+    def __init__(
+        self,
+        vocabulary,
+        image_feature_size: Tuple[int, int, int] = (1024, 14, 14),
+        module_channels: int = 128,
+        class_projection_channels: int = 1024,
+        classifier_linear_size: int = 1024,
+    ):
+        super().__init__()
+        if module_channels != 128 or tuple(image_feature_size[1:]) != (14, 14) or image_feature_size[0] % 128:
+            raise ValueError("the B200 executor is built for module_channels=128 and (128k, 14, 14) features")
+        self.vocabulary = vocabulary
+        channels, height, width = image_feature_size
+        self._in_channels = channels
+        # "@@UNKNOWN@@" is never produced by the classifier (nmn.py:57-63)
+        num_answers = len(vocabulary.get_index_to_token_vocabulary(namespace="answers")) - 1
+        self._unknown_answer = vocabulary.get_token_index("@@UNKNOWN@@", namespace="answers")
+
+        self.stem = nn.Sequential(
+            nn.Conv2d(channels, module_channels, kernel_size=3, padding=1), nn.ReLU(),
+            nn.Conv2d(module_channels, module_channels, kernel_size=3, padding=1), nn.ReLU(),
+        )
+        self.classifier = nn.Sequential(
+            nn.Conv2d(module_channels, class_projection_channels, kernel_size=1), nn.ReLU(),
+            nn.MaxPool2d(kernel_size=2, stride=2), _Flatten(),
+            nn.Linear(class_projection_channels * height * width // 4, classifier_linear_size), nn.ReLU(),
+            nn.Linear(classifier_linear_size, num_answers),
+        )
+        # one parameter holder per program token, registered under the token's name (nmn.py:86-115)
+        self._token_family: Dict[str, Optional[str]] = {}
+        for token in vocabulary.get_token_to_index_vocabulary("programs"):
+            family = module_class_of(token)
+            self._token_family[token] = family
+            if family in ("attention", "query", "relate", "same", "comparison"):
+                self.add_module(token, _ModuleParameters(family, module_channels))
+
+        self._answer_accuracy = _Accuracy()
+        self._average_invalid_programs = _Average()
+        self._flat: Optional[torch.Tensor] = None
+        self._layout: Optional[List[Tuple[str, int, int, torch.Size]]] = None
+        self._model_handle = None
+        self._packed: Optional[torch.Tensor] = None
+        self.last_plan_stats: Optional[List[int]] = None
+
+    @classmethod
+    def from_config(cls, config):
+        r"""Instantiate from a reference-style ``Config`` (duck-typed: ``_C.DATA.VOCABULARY``, ``_C.NMN.*``;
+        nmn.py:126-137)."""
+        _C = config
+        return cls(
+            vocabulary=Vocabulary.from_files(_C.DATA.VOCABULARY),
+            image_feature_size=tuple(_C.NMN.IMAGE_FEATURE_SIZE),
+            module_channels=_C.NMN.MODULE_CHANNELS,
+            class_projection_channels=_C.NMN.CLASS_PROJECTION_CHANNELS,
+            classifier_linear_size=_C.NMN.CLASSIFIER_LINEAR_SIZE,
+        )
+
+    # ---- flat parameter buffer ---------------------------------------------------------------------
+    def _exec_named_parameters(self):
+        """stem + module parameters, i.e. everything the CUDA executor reads (classifier excluded)."""
+        return [(n, p) for n, p in self.named_parameters() if not n.startswith("classifier.")]
+
+    def _ensure_flat(self):
+        named = self._exec_named_parameters()
+        dev = named[0][1].device
+        ok = self._flat is not None and self._flat.device == dev
+        if ok:
+            base = self._flat.data_ptr()
+            for (name, off, n, _), (_, p) in zip(self._layout, named):
+                if p.data_ptr() != base + 4 * off or p.device != dev or not p.is_contiguous():
+                    ok = False
+                    break
+        if ok:
+            return
+        layout, off = [], 0
+        for name, p in named:
+            layout.append((name, off, p.numel(), p.shape))
+            off += (p.numel() + 63) // 64 * 64
+        flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        for (name, o, n, shape), (_, p) in zip(layout, named):
+            flat[o:o + n].copy_(p.data.reshape(-1))
+            p.data = flat[o:o + n].view(shape)
+        self._flat, self._layout = flat, layout
+        self._packed = None
+        if self._model_handle is None:
+            self._model_handle = self._create_model_handle()
+
+    def _create_model_handle(self):
+        offs = {name: o for name, o, _, _ in self._layout}
+        tokens = self.vocabulary.get_index_to_token_vocabulary(namespace="programs")
+        V = max(tokens.keys()) + 1
+        kinds = (ctypes.c_int32 * V)()
+        table = (ctypes.c_int64 * (V * L.MAX_MODULE_PARAMS))(*([-1] * (V * L.MAX_MODULE_PARAMS)))
+        for idx, token in tokens.items():
+            family = module_class_of(token)
+            kinds[idx] = _KIND[family]
+            if family in ("attention", "query", "relate", "same", "comparison"):
+                for i, (name, *_rest) in enumerate(_family_spec(family, 128)):
+                    table[idx * L.MAX_MODULE_PARAMS + 2 * i] = offs[f"{token}.{name}.weight"]
+                    table[idx * L.MAX_MODULE_PARAMS + 2 * i + 1] = offs[f"{token}.{name}.bias"]
+        stem = (ctypes.c_int64 * 4)(offs["stem.0.weight"], offs["stem.0.bias"], offs["stem.2.weight"], offs["stem.2.bias"])
+        handle = L.lib().pnmn_model_create(V, kinds, table, stem, self._in_channels)
+        if not handle:
+            raise RuntimeError("pnmn_model_create failed: " + L.lib().pnmn_last_error().decode())
+        return handle
+
+    def __del__(self):
+        try:
+            if self._model_handle is not None:
+                L.lib().pnmn_model_destroy(self._model_handle)
+        except Exception:
+            pass
+
+    # ---- forward -------------------------------------------------------------------------------------
+    def forward(self, features: torch.Tensor, programs: torch.Tensor, answers: Optional[torch.Tensor] = None):
+        r"""
+        Same contract as the reference (nmn.py:139-275): ``features`` (B, C, 14, 14) float, ``programs``
+        (B, L) prefix-order token ids, optional ``answers`` (B,).  Returns ``{"predictions": (B,) int64,
+        "loss": (B,) float32}`` plus ``"metrics"`` in training mode.  A program the reference could not
+        execute never raises: its prediction is ``@@UNKNOWN@@`` and its loss the constant 3.33.
+        """
+        if not features.is_cuda:
+            raise RuntimeError("NeuralModuleNetwork (B200) needs CUDA tensors; there is no CPU fallback")
+        lib = L.lib()
+        self._ensure_flat()
+        features = features.contiguous().float()
+        B, Lp = programs.shape
+        programs_host = programs.detach().to("cpu", torch.int64).contiguous()  # the single D2H of the forward
+        need_grad = torch.is_grad_enabled() and any(p.requires_grad for _, p in self._exec_named_parameters())
+        plan = lib.pnmn_plan_create(self._model_handle, ctypes.cast(programs_host.data_ptr(), ctypes.POINTER(ctypes.c_int64)),
+                                    B, Lp, 1 if need_grad else 0)
+        if not plan:
+            raise RuntimeError("pnmn_plan_create failed: " + lib.pnmn_last_error().decode())
+        valid_host = torch.empty(B, dtype=torch.uint8)
+        lib.pnmn_plan_valid(plan, ctypes.cast(valid_host.data_ptr(), ctypes.POINTER(ctypes.c_uint8)))
+        sizes = (ctypes.c_int64 * L.SZ_COUNT)()
+        lib.pnmn_plan_sizes(plan, sizes)
+        stats = (ctypes.c_int64 * 8)()
+        lib.pnmn_plan_stats(plan, stats)
+        self.last_plan_stats = list(stats)
+
+        ws = _POOL.acquire(features.device)
+        ws.ensure(sizes)
+        if self._packed is None or self._packed.device != features.device:
+            self._packed = torch.empty(lib.pnmn_model_packed_floats(self._model_handle), dtype=torch.float32,
+                                       device=features.device)
+        bufs = L.Buffers(ws.t["arena16"].data_ptr(), ws.t["arena18"].data_ptr(), ws.t["arena22"].data_ptr(),
+                         ws.t["maps"].data_ptr(), ws.t["dmaps"].data_ptr(), ws.t["idx"].data_ptr(),
+                         ws.t["blob"].data_ptr(), self._packed.data_ptr(), self._flat.data_ptr(), None,
+                         ws.t["ain"].data_ptr(), ws.scratch.data_ptr())
+        run = _Run(plan, ws, bufs)
+        exec_params = [p for _, p in self._exec_named_parameters()]
+        exec_slices = [(o, n, shape) for _, o, n, shape in self._layout]
+        if need_grad:
+            final = _ExecutorFn.apply(features, run, self._flat, exec_slices, *exec_params)
+        else:
+            with torch.no_grad():
+                final = _ExecutorFn.forward(_NullCtx(), features, run, self._flat, exec_slices)
+            run.close()
+
+        # classifier + loss (nmn.py:241-269); masking done on the device instead of CPU-tensor indexing
+        answer_logits = self.classifier(final)
+        answer_logprobs = F.log_softmax(answer_logits, dim=-1)
+        best_logprobs, answer_predictions = torch.max(answer_logprobs, dim=1)
+        invalid = (valid_host == 0).to(features.device, non_blocking=True)
+        answer_predictions = answer_predictions.masked_fill(invalid, self._unknown_answer)
+        if answers is not None:
+            loss = F.cross_entropy(answer_logits, answers, reduction="none")
+        else:
+            loss = -best_logprobs
+        loss = loss.masked_fill(invalid, 3.33)  # constant, carries no gradient (in-place write in the reference)
+        if answers is not None:
+            self._answer_accuracy((answer_predictions == answers).sum().item(), B)
+            self._average_invalid_programs(int((valid_host == 0).sum()))
+
+        output_dict = {"predictions": answer_predictions, "loss": loss}
+        if self.training:
+            output_dict["metrics"] = self.get_metrics(reset=True)
+        return output_dict
+
+    def get_metrics(self, reset: bool = True) -> Dict[str, float]:
+        """``{"answer_accuracy", "average_invalid"}`` (nmn.py:277-296)."""
+        return {
+            "answer_accuracy": self._answer_accuracy.get_metric(reset=reset),
+            "average_invalid": self._average_invalid_programs.get_metric(reset=reset),
+        }
+
+
+class _NullCtx:
+    pass

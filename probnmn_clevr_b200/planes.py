@@ -42,3 +42,11 @@ def map_to_slots(m: torch.Tensor) -> torch.Tensor:
 
 def map_from_slots(s: torch.Tensor) -> torch.Tensor:
     return s.view(16, 16)[:14, :14]
+
+
+def to_half_planes(x: torch.Tensor, S: int) -> torch.Tensor:
+    """(C,14,14) -> fp16 (C/8, P, 8) shadow layout."""
+    C = x.shape[0]
+    buf = torch.zeros(C // 8, S, S, 8, dtype=torch.float16, device=x.device)
+    buf[:, :14, :14, :] = x.view(C // 8, 8, 14, 14).permute(0, 2, 3, 1).to(torch.float16)
+    return buf.view(C // 8, S * S, 8)

@@ -13,30 +13,8 @@ from typing import List, Optional, Tuple
 import numpy as np
 import torch
 
+from .nmn import module_class_of
 from .vocabulary import SPECIAL_TOKENS, Vocabulary
-
-
-# ------------------------------------------------------------------------------------------------
-# token -> module class, exactly the substring rules of probnmn/models/nmn.py:90-111
-# ------------------------------------------------------------------------------------------------
-def module_class_of(token: str) -> Optional[str]:
-    if token in ("@@PADDING@@", "@@UNKNOWN@@", "@start@", "@end@", "unique"):
-        return None
-    if token == "scene":
-        return "scene"
-    if token == "intersect":
-        return "and"
-    if token == "union":
-        return "or"
-    if "equal" in token or token in ("less_than", "greater_than"):
-        return "comparison"
-    if "query" in token or token in ("exist", "count"):
-        return "query"
-    if "relate" in token:
-        return "relate"
-    if "same" in token:
-        return "same"
-    return "attention"
 
 
 def module_param_shapes(cls: str, dim: int = 128) -> List[Tuple[str, Tuple[int, ...]]]:

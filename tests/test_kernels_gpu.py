@@ -11,7 +11,8 @@ import torch
 import torch.nn.functional as F
 
 from probnmn_clevr_b200 import _lib as L
-from probnmn_clevr_b200.planes import GUARD_FLOATS, fmt_for_dilation, from_planes, map_from_slots, round_tf32, to_planes
+from probnmn_clevr_b200.planes import (GUARD_FLOATS, fmt_for_dilation, from_planes, map_from_slots, round_tf32,
+                                       to_half_planes, to_planes)
 
 pytestmark = pytest.mark.gpu
 
@@ -192,46 +193,64 @@ def test_conv_stem_1024(impl):
         assert err < 1e-3
 
 
-def _run_wgrad(impl, dzs, xs, dil, ksize, cin_total, cin0):
+def _half_arena(hplanes_list):
+    total = 2 * GUARD_FLOATS * 2 + sum(p.numel() for p in hplanes_list)
+    arena = torch.zeros(total, device="cuda", dtype=torch.float16)
+    offs, o = [], GUARD_FLOATS * 2
+    for p in hplanes_list:
+        arena[o:o + p.numel()] = p.reshape(-1)
+        offs.append(o)
+        o += p.numel()
+    return arena, offs
+
+
+def _run_wgrad(impl, dzs, xs, dil, ksize, cin_total, cin0, scale=1.0):
+    """dzs / xs: fp16-representable tensors; the kernel consumes their fp16 half-plane copies"""
     lib = L.lib()
     fin = fmt_for_dilation(dil)
     S, P = fin
     n = len(dzs)
-    arena_dz, offs_dz = _arena([to_planes(d, S) for d in dzs])
-    arena_x, offs_x = _arena([to_planes(x, S) for x in xs])
+    arena_dz, offs_dz = _half_arena([to_half_planes(d * scale, S) for d in dzs])
+    arena_x, offs_x = _half_arena([to_half_planes(x, S) for x in xs])
     insts = (L.WgradInst * n)()
     for i in range(n):
-        insts[i].dz = arena_dz.data_ptr() + 4 * offs_dz[i]
-        insts[i].x = arena_x.data_ptr() + 4 * offs_x[i]
+        insts[i].dz = arena_dz.data_ptr() + 2 * offs_dz[i]
+        insts[i].x = arena_x.data_ptr() + 2 * offs_x[i]
     dw = torch.zeros(128, cin_total, ksize, ksize, device="cuda")
+    sc = torch.tensor([scale, 1.0 / scale, 0, 0], device="cuda")
     rows = 3 if ksize == 3 else 1
     tasks = (L.WgradTask * rows)()
     for r in range(rows):
-        tasks[r] = L.WgradTask(0, n, r, 3 if ksize == 3 else 1, dil, S, P, cin_total, cin0, ksize, dw.data_ptr(), 0)
+        tasks[r] = L.WgradTask(0, n, r, 3 if ksize == 3 else 1, dil, S, P, cin_total, cin0, ksize, dw.data_ptr(),
+                               sc.data_ptr())
     L.check(lib.pnmn_debug_launch_wgrad(tasks, rows, insts, n, impl, _stream()))
     torch.cuda.synchronize()
     return dw
+
+
+def _mkh(shape, gen, scale=1.0):
+    return (torch.randn(shape, generator=gen, device="cuda") * scale).half().float()
 
 
 @pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
 @pytest.mark.parametrize("dil,n_inst", [(1, 3), (2, 1), (4, 2), (8, 2)])
 def test_wgrad3x3(impl, dil, n_inst):
     g = torch.Generator(device="cuda").manual_seed(21 + dil)
-    dzs = [_mk((128, 14, 14), g) for _ in range(n_inst)]
-    xs = [_mk((128, 14, 14), g) for _ in range(n_inst)]
-    dw = _run_wgrad(impl, dzs, xs, dil, 3, 128, 0)
+    dzs = [_mkh((128, 14, 14), g) for _ in range(n_inst)]
+    xs = [_mkh((128, 14, 14), g) for _ in range(n_inst)]
+    dw = _run_wgrad(impl, dzs, xs, dil, 3, 128, 0, scale=4.0)
     ref = sum(torch.nn.grad.conv2d_weight(x[None], (128, 128, 3, 3), d[None], padding=dil, dilation=dil)
               for x, d in zip(xs, dzs))
     err = _relerr(dw, ref)
     print(f"wgrad impl={impl} dil={dil}: rel err {err:.3e}")
-    assert err < 2e-5  # exact tf32 products, fp32 accumulation
+    assert err < 2e-5  # exact fp16 products, fp32 accumulation
 
 
 @pytest.mark.parametrize("impl", [1, 0], ids=["simt", "tcgen05"])
 def test_wgrad_projection_half(impl):
     g = torch.Generator(device="cuda").manual_seed(31)
-    dzs = [_mk((128, 14, 14), g) for _ in range(2)]
-    xs = [_mk((128, 14, 14), g) for _ in range(2)]
+    dzs = [_mkh((128, 14, 14), g) for _ in range(2)]
+    xs = [_mkh((128, 14, 14), g) for _ in range(2)]
     dw = _run_wgrad(impl, dzs, xs, 1, 1, 256, 128)
     ref = sum(torch.einsum("ohw,ihw->oi", d, x) for x, d in zip(xs, dzs))
     err = _relerr(dw[:, 128:, 0, 0], ref)
