@@ -107,6 +107,12 @@ int pnmn_nmn_forward(pnmn_plan* p, const pnmn_buffers* bufs, const float* featur
  * stem and module parameters are ACCUMULATED into bufs->grads (autograd semantics). */
 int pnmn_nmn_backward(pnmn_plan* p, const pnmn_buffers* bufs, const float* grad_final_out, void* stream);
 
+/* Optional per-launch device timing (CUDA events on the launching stream), used by bench.py for the
+ * roofline of the dominant kernel.  ms / launches have 8 slots: {elementwise, conv<2 samples x 2 tiles>,
+ * conv<1 x 3>, wgrad, bias_grad, weight pack, feature layout, other}.  Reading synchronises and clears. */
+int pnmn_profile_enable(int on);
+int pnmn_profile_read(double* ms, int64_t* launches);
+
 /* ---- bring-up entry points used by tests/ (kernel-level parity against torch) ---------------- */
 int pnmn_debug_launch_conv(const void* tasks_host, int n_tasks, const void* cfgs_host, int n_cfgs,
                            int variant, int impl_simt, void* stream);

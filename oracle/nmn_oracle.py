@@ -50,9 +50,46 @@ def token_class(token: str) -> str:
     return "attention"
 
 
+# Operand rounding mode.  "fp32" is the reference's arithmetic.  "tf32" rounds the two operands of every
+# 128-output-channel convolution (activations and weights) to tf32 (cvt.rna, 10-bit mantissa) with a
+# straight-through gradient, fp32 accumulation: the arithmetic of a tf32 tensor-core implementation (and of
+# the reference itself on an Ampere-or-later GPU, where torch.backends.cudnn.allow_tf32 defaults to True).
+# Gradients of this network are ill-conditioned w.r.t. 1e-3 forward perturbations (saturated sigmoids), so
+# gradient parity of the CUDA path is asserted against the "tf32" oracle; outputs against the fp32 one.
+_ROUNDING = "fp32"
+
+
+class operand_rounding:
+    def __init__(self, mode):
+        assert mode in ("fp32", "tf32")
+        self.mode = mode
+
+    def __enter__(self):
+        global _ROUNDING
+        self.prev, _ROUNDING = _ROUNDING, self.mode
+
+    def __exit__(self, *a):
+        global _ROUNDING
+        _ROUNDING = self.prev
+
+
+def _round_tf32(t):
+    bits = t.detach().contiguous().view(torch.int32)
+    return ((bits + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+def _r(t):
+    if _ROUNDING == "fp32":
+        return t
+    return t + (_round_tf32(t) - t.detach())
+
+
 def _conv(sd, name, x, dilation=1, k3=True):
     pad = dilation if k3 else 0
-    return F.conv2d(x, sd[name + ".weight"], sd[name + ".bias"], padding=pad, dilation=dilation)
+    w = sd[name + ".weight"]
+    if w.shape[0] == 1:  # 1-channel heads: fp32 everywhere
+        return F.conv2d(x, w, sd[name + ".bias"], padding=pad, dilation=dilation)
+    return F.conv2d(_r(x), _r(w), sd[name + ".bias"], padding=pad, dilation=dilation)
 
 
 def attention_module(sd, tok, feats, attn):
@@ -81,9 +118,8 @@ def relate_module(sd, tok, feats, attn):
 def same_module(sd, tok, feats, attn):
     """nmn_modules.py:200-208; argmax = first maximum in row-major order, row = idx // W (torch 1.4)."""
     h, w = attn.shape[2], attn.shape[3]
-    idx = int(torch.argmax(attn[0, 0].reshape(-1)))  # torch.argmax returns the first maximal index
     flat = attn[0, 0].reshape(-1)
-    idx = int((flat == flat.max()).nonzero()[0])       # make "first maximum" explicit
+    idx = int((flat == flat.max()).nonzero()[0])  # first maximum in row-major order
     row, col = idx // w, idx % w
     vec = feats[:, :, row:row + 1, col:col + 1]
     x = torch.cat([feats * vec, attn], dim=1)
@@ -144,8 +180,8 @@ def classifier(sd, x):
 
 def stem(sd, features):
     """nmn.py:67-72,183"""
-    x = F.relu(F.conv2d(features, sd["stem.0.weight"], sd["stem.0.bias"], padding=1))
-    return F.relu(F.conv2d(x, sd["stem.2.weight"], sd["stem.2.bias"], padding=1))
+    x = F.relu(F.conv2d(_r(features), _r(sd["stem.0.weight"]), sd["stem.0.bias"], padding=1))
+    return F.relu(F.conv2d(_r(x), _r(sd["stem.2.weight"]), sd["stem.2.bias"], padding=1))
 
 
 def nmn_forward(sd: Dict[str, torch.Tensor], vocabulary, features: torch.Tensor, programs: torch.Tensor,

@@ -84,7 +84,8 @@ EXPORTS = [
     "pnmn_version", "pnmn_last_error", "pnmn_model_create", "pnmn_model_destroy", "pnmn_model_packed_floats",
     "pnmn_plan_create", "pnmn_plan_destroy", "pnmn_plan_valid", "pnmn_plan_sizes", "pnmn_plan_stats",
     "pnmn_nmn_forward", "pnmn_nmn_backward", "pnmn_debug_launch_conv", "pnmn_debug_launch_wgrad",
-    "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt",
+    "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt", "pnmn_profile_enable",
+    "pnmn_profile_read",
 ]
 
 
@@ -130,6 +131,8 @@ def lib() -> ctypes.CDLL:
     L.pnmn_debug_pack.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.pnmn_debug_nchw_to_planes.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]
     L.pnmn_debug_launch_elt.argtypes = [c_void_p, c_int, c_void_p]
+    L.pnmn_profile_enable.argtypes = [c_int]
+    L.pnmn_profile_read.argtypes = [POINTER(ctypes.c_double), POINTER(c_int64)]
     _lib = L
     return L
 

@@ -840,6 +840,20 @@ void fill_bases(uint64_t* base, const pnmn_buffers* b, const void* final_out, co
   base[AR_SCRATCH] = reinterpret_cast<uint64_t>(b->scratch);
 }
 
+// ---- optional per-launch timing (bench.py roofline): CUDA events on the launching stream ----------
+struct ProfRec { int kind; cudaEvent_t a, b; };
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;
+enum ProfKind { PK_ELT = 0, PK_CONV0, PK_CONV1, PK_WGRAD, PK_BIAS, PK_PACK, PK_LAYOUT, PK_OTHER, PK_COUNT };
+struct ProfScope {
+  cudaStream_t st; bool on; ProfRec r;
+  ProfScope(int kind, cudaStream_t s) : st(s), on(g_prof_on) {
+    if (!on) return;
+    r.kind = kind; cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, st);
+  }
+  ~ProfScope() { if (on) { cudaEventRecord(r.b, st); g_prof.push_back(r); } }
+};
+
 void resolve_conv(ConvTask& t, const uint64_t* base) {
   for (int i = 0; i < 2; ++i)
     for (int s = 0; s < NSMAX; ++s) resolve(t.in[i][s], base);
@@ -872,6 +886,7 @@ int run_launches(const pnmn_plan& p, const std::vector<LaunchItem>& ls, const ui
   const EltTask* elt = reinterpret_cast<const EltTask*>(blob + (bwd ? p.off_belt : p.off_felt));
   const int simt = conv_impl_simt();
   for (const LaunchItem& l : ls) {
+    ProfScope prof(l.kind, st);  // LaunchKind values coincide with ProfKind 0..4
     switch (l.kind) {
       case LK_ELT: CUDA_OK(launch_elt(elt + l.off, l.count, st)); break;
       case LK_CONV0: CUDA_OK(launch_conv(conv + l.off, l.count, cfgs, 0, simt, st)); break;
@@ -917,10 +932,12 @@ extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const f
       CUDA_OK(cudaMalloc(&d_tasks, m.pack.size() * sizeof(PackTask)));
       CUDA_OK(cudaMemcpy(d_tasks, m.pack.data(), m.pack.size() * sizeof(PackTask), cudaMemcpyHostToDevice));
     }
+    ProfScope prof(PK_PACK, st);
     CUDA_OK(launch_pack(d_tasks, static_cast<int>(m.pack.size()), m.total_tiles, bufs->params, bufs->packed, st));
   }
   fill_ones_map_kernel<<<1, 256, 0, st>>>(bufs->maps);
   // features -> planes for every valid sample
+  ProfScope prof_layout(PK_LAYOUT, st);
   CUDA_OK(launch_nchw_to_planes(features, bufs->ain, p.B, m.in_ch,
                                 reinterpret_cast<const int64_t*>(static_cast<const uint8_t*>(bufs->blob) + p.off_xin), st));
   return run_launches(p, p.flaunch, static_cast<const uint8_t*>(bufs->blob), false, st);
@@ -950,6 +967,24 @@ extern "C" int pnmn_nmn_backward(pnmn_plan* pp, const pnmn_buffers* bufs, const 
   CUDA_OK(cudaMemsetAsync(bufs->dmaps, 0, static_cast<size_t>(p.nmaps) * 1024, st));
   CUDA_OK(launch_loss_scale(grad_final_out, static_cast<size_t>(p.B) * 128 * 196, bufs->scratch, st));
   return run_launches(p, p.blaunch, static_cast<const uint8_t*>(bufs->blob), true, st);
+}
+
+extern "C" int pnmn_profile_enable(int on) {
+  g_prof_on = on != 0;
+  return 0;
+}
+// ms[k], launches[k] for k in {elt, conv<2,2>, conv<1,3>, wgrad, bias_grad, pack, layout, other}; clears the log
+extern "C" int pnmn_profile_read(double* ms, int64_t* launches) {
+  for (int k = 0; k < PK_COUNT; ++k) { ms[k] = 0; launches[k] = 0; }
+  CUDA_OK(cudaDeviceSynchronize());
+  for (ProfRec& r : g_prof) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    ms[r.kind] += t; launches[r.kind] += 1;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  return 0;
 }
 
 // ---- bring-up entry points -----------------------------------------------------------------------
