@@ -1,0 +1,290 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path named by BASELINE.json: the Neural Module Network executor, forward + backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload (BASELINE.json configs[1]): module_training.yml at batch 256 per GPU, synthetic 14x14x1024 features
+and ground-truth-style CLEVR programs (seeded grammar, <= 40 tokens), reference-shaped random-init weights.
+One step = NeuralModuleNetwork.forward(features, programs, answers) + loss.mean().backward() through the
+public nn.Module API (program compilation on the host included); N > 1 adds the gradient all-reduce (NCCL).
+
+Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM, `e2e` with pinned host
+inputs copied in and the loss read back every step.  `roofline` is the tcgen05 conv kernel (the dominant
+kernel) timed with CUDA events around every launch; `cpu_baseline` is the CPU oracle (a port of the
+reference's PyTorch path) on a bounded sample.  `--impl reference` times that CPU path alone.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "questions/sec (NMN executor fwd+bwd, batch 256 per GPU)"
+UNIT = "questions/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--length", type=int, default=40)
+    ap.add_argument("--cpu-sample", type=int, default=16, help="rows of the workload the CPU baseline runs")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args):
+    return {
+        "workload": "module_training.yml batch=256/GPU: NMN stem + module executor + classifier, fwd+bwd "
+                    "(BASELINE.json configs[1])",
+        "batch_per_gpu": args.batch, "program_length": args.length, "features": [1024, 14, 14],
+        "programs": "seeded CLEVR template grammar (probnmn_clevr_b200/synthetic.py), ground-truth style",
+        "weights": "reference shapes, He-normal, seed 0",
+        "step": "forward + loss.mean().backward(); no optimizer (executor-only config)",
+        "l2": "inputs larger than L2 (205 MB of features per step, two alternating batches)",
+        "parallelism": f"dp{args.gpus}",
+    }
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU path (oracle port of the reference): cpu_baseline and --impl reference
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_step(sd, vocab, feats, programs, answers):
+    from oracle import nmn_oracle
+    for p in sd.values():
+        p.grad = None
+    out = nmn_oracle.nmn_forward(sd, vocab, feats, programs, answers)
+    out["loss"].mean().backward()
+    return float(out["loss"].mean())
+
+
+def cpu_inputs(args, rows, seed=0):
+    from probnmn_clevr_b200.synthetic import ProgramSampler, make_answers, make_features, make_nmn_state_dict
+    from probnmn_clevr_b200.vocabulary import Vocabulary
+    vocab = Vocabulary.clevr()
+    sd = {k: v.requires_grad_(True) for k, v in make_nmn_state_dict(vocab, 0).items()}
+    programs = ProgramSampler(vocab, seed=seed).sample(args.batch, args.length)[:rows]
+    return vocab, sd, make_features(rows, seed), programs, make_answers(rows, seed)
+
+
+def run_reference(args):
+    """The reference's CPU PyTorch path (oracle port; /root/reference does not exist on the GPU box)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    rows = args.cpu_sample
+    vocab, sd, feats, programs, answers = cpu_inputs(args, rows)
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_step(sd, vocab, feats, programs, answers)
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_reference_step(sd, vocab, feats, programs, answers)
+    dt = time.perf_counter() - t0
+    value = rows * steps / dt
+    sample = f"{rows} rows of the batch-{args.batch} workload per step, fwd+bwd, {steps} steps"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 7:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[0]) for s in self.samples)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# ours
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch.distributed as dist
+    from probnmn_clevr_b200 import _lib as L
+    from probnmn_clevr_b200.nmn import NeuralModuleNetwork
+    from probnmn_clevr_b200.synthetic import ProgramSampler, make_answers, make_features, make_nmn_state_dict
+    from probnmn_clevr_b200.vocabulary import Vocabulary
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cudnn.allow_tf32 = False  # classifier stays fp32, as in the reference
+    torch.backends.cuda.matmul.allow_tf32 = False
+
+    vocab = Vocabulary.clevr()
+    model = NeuralModuleNetwork(vocab)
+    model.load_state_dict(make_nmn_state_dict(vocab, 0))
+    model = model.to(dev).train()
+
+    # two alternating batches per rank; host copies pinned for the end-to-end leg
+    host = []
+    for i in range(2):
+        seed = 100 * rank + i
+        host.append((make_features(args.batch, seed).pin_memory(),
+                     ProgramSampler(vocab, seed=seed).sample(args.batch, args.length).pin_memory(),
+                     make_answers(args.batch, seed).pin_memory()))
+    resident = [tuple(t.to(dev) for t in h) for h in host]
+
+    def step(feats, programs, answers):
+        model.zero_grad(set_to_none=True)
+        out = model(feats, programs, answers)
+        loss = out["loss"].mean()
+        loss.backward()
+        if world > 1:
+            model.allreduce_gradients()
+        return loss
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            fn(i)
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+
+    def resident_step(i):
+        step(*resident[i % 2])
+
+    def e2e_step(i):
+        f, p, a = host[i % 2]
+        loss = step(f.to(dev, non_blocking=True), p.to(dev, non_blocking=True), a.to(dev, non_blocking=True))
+        return loss.item()
+
+    for i in range(max(args.warmup, 3)):
+        resident_step(i)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(resident_step, args.steps)
+    sampler.stop_flag = True
+    stats = model.last_plan_stats
+    for i in range(2):
+        e2e_step(i)
+    ms_e2e = timed(e2e_step, args.steps)
+
+    value = world * args.batch * args.steps / (ms * 1e-3)
+    e2e_value = world * args.batch * args.steps / (ms_e2e * 1e-3)
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+
+    # per-kernel device time of a few profiled steps (CUDA events around every launch, same stream)
+    lib = L.lib()
+    prof_steps = min(args.steps, 5)
+    lib.pnmn_profile_enable(1)
+    for i in range(prof_steps):
+        resident_step(i)
+    pms, pln = (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)()
+    lib.pnmn_profile_read(pms, pln)
+    lib.pnmn_profile_enable(0)
+    kinds = ["elementwise", "conv_tc<2,2>", "conv_tc<1,3>", "wgrad_tc", "bias_grad", "pack_weights", "nchw_to_planes", "other"]
+    kernel_ms = {k: pms[i] / prof_steps for i, k in enumerate(kinds)}
+    conv_flops = stats[8] + stats[10]  # forward + dgrad FLOPs executed by conv_tc<2,2> per step
+    conv_ms = kernel_ms["conv_tc<2,2>"]
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = peaks.get("bf16_tflops_sustained", 1590.0)
+    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1590 (of fallback)"
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": workload_config(args),
+        "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int((stats[3] + stats[4] + 5) * args.steps),
+        "roofline": {
+            "bound": "tensor", "kernel": "conv_tc_kernel<2,2> (tcgen05 kind::tf32 shift-GEMM conv: forward + dgrad)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src,
+            "note": "operands are tf32 (half the bf16 tensor rate); peak is the measured bf16 cuBLAS figure",
+            "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms, "launches_per_step": pln[1] / prof_steps,
+            "traffic": None,
+        },
+        "kernel_ms_per_step": kernel_ms,
+        "plan": {"valid_programs": stats[0], "conv3x3_instances": stats[1], "module_tokens": stats[2],
+                 "forward_launches": stats[3], "backward_launches": stats[4], "wgrad_flops": stats[12]},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        torch.set_num_threads(os.cpu_count())
+        rows = args.cpu_sample
+        cvocab, sd, feats, programs, answers = cpu_inputs(args, rows)
+        cpu_reference_step(sd, cvocab, feats, programs, answers)
+        best = 1e30
+        for _ in range(2):
+            t0 = time.perf_counter()
+            cpu_reference_step(sd, cvocab, feats, programs, answers)
+            best = min(best, time.perf_counter() - t0)
+        line["cpu_baseline"] = {"value": rows / best, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                                "sample": f"{rows} rows of the same batch, fwd+bwd, best of 2 after 1 warm-up"}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

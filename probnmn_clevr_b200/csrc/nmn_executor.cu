@@ -261,7 +261,7 @@ struct pnmn_plan {
   // blob layout (bytes)
   int64_t off_cfg = 0, off_xin = 0, off_fconv = 0, off_felt = 0, off_bconv = 0, off_belt = 0, off_inst = 0, off_wt = 0,
           off_bt = 0, blob_bytes = 0;
-  int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int64_t stats[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<uint8_t> host_blob;
 };
 
@@ -788,6 +788,24 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   p.stats[5] = flops + n_conv3 * 2ll * 196 * 128 * 128 * 9;
   p.stats[6] = static_cast<int64_t>(p.fconv.size());
   p.stats[7] = static_cast<int64_t>(p.wtasks.size());
+  // algorithmic FLOPs (dense convention 2*196*N*K, padding taps counted) per kernel family
+  auto conv_flops = [&](const std::vector<ConvTask>& tasks, const std::vector<LaunchItem>& ls, int kind) {
+    int64_t f = 0;
+    for (const LaunchItem& l : ls)
+      if (l.kind == kind)
+        for (int i = 0; i < l.count; ++i) {
+          const ConvTask& t = tasks[l.off + i];
+          const ConvCfg& c = p.cfgs[t.cfg];
+          f += static_cast<int64_t>(t.n_samp) * 2 * 196 * 128 * (16ll * c.n_kb * c.ntaps);
+        }
+    return f;
+  };
+  p.stats[8] = conv_flops(p.fconv, p.flaunch, LK_CONV0);
+  p.stats[9] = conv_flops(p.fconv, p.flaunch, LK_CONV1);
+  p.stats[10] = conv_flops(p.bconv, p.blaunch, LK_CONV0);
+  p.stats[11] = conv_flops(p.bconv, p.blaunch, LK_CONV1);
+  for (const WgradTask& t : p.wtasks) p.stats[12] += static_cast<int64_t>(t.n_inst) * 2 * 196 * 128 * 128 * t.ntaps_x;
+  p.stats[13] = static_cast<int64_t>(p.felt.size() + p.belt.size());
   return plan;
 }
 

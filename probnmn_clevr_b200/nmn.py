@@ -152,8 +152,8 @@ _POOL = _WorkspacePool()
 class _Run:
     """One forward's plan + workspace; released after backward (or when dropped)."""
 
-    def __init__(self, plan, ws, bufs):
-        self.plan, self.ws, self.bufs = plan, ws, bufs
+    def __init__(self, plan, ws, bufs, gflat_box=None):
+        self.plan, self.ws, self.bufs, self.gflat_box = plan, ws, bufs, gflat_box
 
     def close(self):
         if self.plan is not None:
@@ -193,6 +193,8 @@ class _ExecutorFn(torch.autograd.Function):
         L.check(L.lib().pnmn_nmn_backward(run.plan, ctypes.byref(run.bufs), ctypes.c_void_p(grad_final.data_ptr()),
                                           stream), "pnmn_nmn_backward")
         grads = tuple(gflat[o:o + n].view(shape) for (o, n, shape) in ctx.exec_slices)
+        if run.gflat_box is not None:
+            run.gflat_box["gflat"] = gflat
         run.close()
         return (None, None, None, None) + grads
 
@@ -256,6 +258,7 @@ class NeuralModuleNetwork(nn.Module):
         self._model_handle = None
         self._packed: Optional[torch.Tensor] = None
         self.last_plan_stats: Optional[List[int]] = None
+        self._gflat_box: Dict[str, torch.Tensor] = {}
 
     @classmethod
     def from_config(cls, config):
@@ -350,7 +353,7 @@ class NeuralModuleNetwork(nn.Module):
         lib.pnmn_plan_valid(plan, ctypes.cast(valid_host.data_ptr(), ctypes.POINTER(ctypes.c_uint8)))
         sizes = (ctypes.c_int64 * L.SZ_COUNT)()
         lib.pnmn_plan_sizes(plan, sizes)
-        stats = (ctypes.c_int64 * 8)()
+        stats = (ctypes.c_int64 * 16)()
         lib.pnmn_plan_stats(plan, stats)
         self.last_plan_stats = list(stats)
 
@@ -363,7 +366,7 @@ class NeuralModuleNetwork(nn.Module):
                          ws.t["maps"].data_ptr(), ws.t["dmaps"].data_ptr(), ws.t["idx"].data_ptr(),
                          ws.t["blob"].data_ptr(), self._packed.data_ptr(), self._flat.data_ptr(), None,
                          ws.t["ain"].data_ptr(), ws.scratch.data_ptr())
-        run = _Run(plan, ws, bufs)
+        run = _Run(plan, ws, bufs, self._gflat_box)
         exec_params = [p for _, p in self._exec_named_parameters()]
         exec_slices = [(o, n, shape) for _, o, n, shape in self._layout]
         if need_grad:
@@ -392,6 +395,29 @@ class NeuralModuleNetwork(nn.Module):
         if self.training:
             output_dict["metrics"] = self.get_metrics(reset=True)
         return output_dict
+
+    def allreduce_gradients(self, group=None) -> None:
+        """Data-parallel gradient averaging over NCCL (one process per GPU): ONE all-reduce for the stem + module
+        gradients, which the executor's backward leaves in a single flat buffer, plus one per classifier tensor.
+        (The reference has no distributed path: it wraps the model in ``nn.DataParallel``,
+        trainers/_trainer.py:98-100, which mis-executes the NMN)"""
+        import torch.distributed as dist
+
+        avg = dist.ReduceOp.AVG
+        exec_params = [p for _, p in self._exec_named_parameters()]
+        gflat = self._gflat_box.get("gflat")
+        handles = []
+        lo = gflat.data_ptr() if gflat is not None else 0
+        hi = lo + (gflat.numel() * 4 if gflat is not None else 0)
+        aliased = gflat is not None and all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in exec_params)
+        if aliased:
+            handles.append(dist.all_reduce(gflat, op=avg, group=group, async_op=True))
+        else:
+            handles += [dist.all_reduce(p.grad, op=avg, group=group, async_op=True) for p in exec_params if p.grad is not None]
+        handles += [dist.all_reduce(p.grad, op=avg, group=group, async_op=True)
+                    for n, p in self.named_parameters() if n.startswith("classifier.") and p.grad is not None]
+        for h in handles:
+            h.wait()
 
     def get_metrics(self, reset: bool = True) -> Dict[str, float]:
         """``{"answer_accuracy", "average_invalid"}`` (nmn.py:277-296)."""

@@ -45,7 +45,7 @@ def _plan_valid(model, programs, need_grad=1):
     lib.pnmn_plan_valid(plan, ctypes.cast(valid.data_ptr(), ctypes.POINTER(ctypes.c_uint8)))
     sizes = (ctypes.c_int64 * L.SZ_COUNT)()
     lib.pnmn_plan_sizes(plan, sizes)
-    stats = (ctypes.c_int64 * 8)()
+    stats = (ctypes.c_int64 * 16)()
     lib.pnmn_plan_stats(plan, stats)
     lib.pnmn_plan_destroy(plan)
     return valid.numpy(), list(sizes), list(stats)
