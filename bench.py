@@ -53,6 +53,7 @@ def workload_config(args):
         "weights": "reference shapes, He-normal, seed 0",
         "step": "forward + loss.mean().backward(); no optimizer (executor-only config)",
         "l2": "inputs larger than L2 (205 MB of features per step, two alternating batches)",
+        "programs": "host-resident int64 (consumed by the host-side program compiler); features/answers in HBM",
         "parallelism": f"dp{args.gpus}",
     }
 
@@ -172,7 +173,9 @@ def run_ours(args):
         host.append((make_features(args.batch, seed).pin_memory(),
                      ProgramSampler(vocab, seed=seed).sample(args.batch, args.length).pin_memory(),
                      make_answers(args.batch, seed).pin_memory()))
-    resident = [tuple(t.to(dev) for t in h) for h in host]
+    # `value` leg: features / answers resident in HBM; the programs stay in (pinned) host memory because that is
+    # where the executor consumes them (its program compiler runs on the host)
+    resident = [(h[0].to(dev), h[1], h[2].to(dev)) for h in host]
 
     def step(feats, programs, answers):
         model.zero_grad(set_to_none=True)
@@ -205,15 +208,20 @@ def run_ours(args):
 
     def e2e_step(i):
         f, p, a = host[i % 2]
-        loss = step(f.to(dev, non_blocking=True), p.to(dev, non_blocking=True), a.to(dev, non_blocking=True))
+        loss = step(f.to(dev, non_blocking=True), p, a.to(dev, non_blocking=True))
         return loss.item()
 
     for i in range(max(args.warmup, 3)):
         resident_step(i)
+    host_ms = (ctypes.c_double * 4)()
+    L.lib().pnmn_debug_host_times(host_ms)
     sampler = ClockSampler(local)
     sampler.start()
     ms = timed(resident_step, args.steps)
     sampler.stop_flag = True
+    L.lib().pnmn_debug_host_times(host_ms)
+    host_ms_per_step = {"plan_create": host_ms[0] / args.steps, "forward_call": host_ms[1] / args.steps,
+                        "backward_call": host_ms[2] / args.steps}
     stats = model.last_plan_stats
     for i in range(2):
         e2e_step(i)
@@ -260,7 +268,7 @@ def run_ours(args):
             "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms, "launches_per_step": pln[1] / prof_steps,
             "traffic": None,
         },
-        "kernel_ms_per_step": kernel_ms,
+        "kernel_ms_per_step": kernel_ms, "host_ms_per_step": host_ms_per_step,
         "plan": {"valid_programs": stats[0], "conv3x3_instances": stats[1], "module_tokens": stats[2],
                  "forward_launches": stats[3], "backward_launches": stats[4], "wgrad_flops": stats[12]},
     }

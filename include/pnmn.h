@@ -53,7 +53,7 @@ enum pnmn_token_kind {
 pnmn_model* pnmn_model_create(int vocab_size, const int32_t* token_kind, const int64_t* token_param_off,
                               const int64_t* stem_param_off, int in_channels);
 void pnmn_model_destroy(pnmn_model* m);
-/* floats of scratch needed for the tf32-packed forward + dgrad weight tiles */
+/* floats (4-byte units) of scratch needed for the fp16-packed forward + dgrad weight tiles */
 int64_t pnmn_model_packed_floats(const pnmn_model* m);
 
 /* Program compiler: replaces the per-sample python interpreter with its B device->host syncs
@@ -121,10 +121,16 @@ int pnmn_debug_launch_conv(const void* tasks_host, int n_tasks, const void* cfgs
 int pnmn_debug_launch_wgrad(const void* tasks_host, int n_tasks, const void* insts_host, int n_insts,
                             int impl_simt, void* stream);
 int pnmn_debug_pack(const void* pack_tasks_host, int n_tasks, int total_tiles, const float* params,
-                    float* packed, void* stream);
+                    void* packed, void* stream);
 int pnmn_debug_nchw_to_planes(const float* src, float* dst, int batch, int channels,
                               int64_t dst_sample_stride, void* stream);
 int pnmn_debug_launch_elt(const void* tasks_host, int n_tasks, void* stream);
+/* per-task timestamps of the persistent executor (8 int64 per task: fetched, ready, body done, published,
+ * SM id, type|n_samp<<8|n_mt<<16, MMA k-steps, flags); forward tasks first, then backward; NULL disables */
+int pnmn_debug_set_trace(void* device_buffer, int64_t capacity_tasks);
+/* accumulated host-side milliseconds spent in {pnmn_plan_create, pnmn_nmn_forward, pnmn_nmn_backward} and the
+ * number of plans created since the last call (reading clears) */
+int pnmn_debug_host_times(double* ms);
 
 #ifdef __cplusplus
 }

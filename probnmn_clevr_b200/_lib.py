@@ -46,7 +46,7 @@ class ConvTask(Structure):
     _fields_ = [
         ("in_", (c_void_p * NSMAX) * 2), ("out", c_void_p * NSMAX), ("aux", c_void_p * NSMAX),
         ("map_out", c_void_p * NSMAX), ("w", c_void_p), ("bias", c_void_p), ("w3", c_void_p), ("b3", c_void_p),
-        ("cfg", c_int), ("n_samp", c_int), ("pad_", c_int64),
+        ("cfg", c_int), ("n_samp", c_int), ("mt0", c_int), ("n_mt", c_int),
     ]
 
 
@@ -74,7 +74,7 @@ class EltTask(Structure):
     _fields_ = [
         ("op", c_int), ("flags", c_int), ("a", c_void_p), ("b", c_void_p), ("c", c_void_p), ("g", c_void_p),
         ("o", c_void_p), ("o2", c_void_p), ("w", c_void_p), ("dw", c_void_p), ("dw2", c_void_p), ("idx", c_void_p),
-        ("scale", c_void_p), ("pad_", c_int64 * 4),
+        ("scale", c_void_p), ("part", c_int), ("n_parts", c_int), ("pad_", c_int64 * 3),
     ]
 
 
@@ -85,7 +85,7 @@ EXPORTS = [
     "pnmn_plan_create", "pnmn_plan_destroy", "pnmn_plan_valid", "pnmn_plan_sizes", "pnmn_plan_stats",
     "pnmn_nmn_forward", "pnmn_nmn_backward", "pnmn_debug_launch_conv", "pnmn_debug_launch_wgrad",
     "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt", "pnmn_profile_enable",
-    "pnmn_profile_read",
+    "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times",
 ]
 
 
@@ -131,6 +131,8 @@ def lib() -> ctypes.CDLL:
     L.pnmn_debug_pack.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]
     L.pnmn_debug_nchw_to_planes.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p]
     L.pnmn_debug_launch_elt.argtypes = [c_void_p, c_int, c_void_p]
+    L.pnmn_debug_set_trace.argtypes = [c_void_p, c_int64]
+    L.pnmn_debug_host_times.argtypes = [POINTER(ctypes.c_double)]
     L.pnmn_profile_enable.argtypes = [c_int]
     L.pnmn_profile_read.argtypes = [POINTER(ctypes.c_double), POINTER(c_int64)]
     _lib = L

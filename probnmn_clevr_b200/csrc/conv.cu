@@ -1,58 +1,32 @@
-// Shift-GEMM convolution for the NMN module executor (forward and dgrad share this kernel).
+// CUDA-core twin of the executor's convolution task (bring-up / debugging only).
 //
 //   out[slot, n] = epilogue( sum_{kb, tap, k} in[(kb,k)-th channel][slot + shift(tap)] * W[kb][tap][k][n] )
 //
-// One CTA runs one ConvTask: up to NS samples that use the SAME weights (so the weight stream
-// from L2 is shared), NMT 128-row M tiles per sample, N = 128 output channels, accumulators in
-// TMEM (NS*NMT*128 columns).  Operands are fp32 containers holding tf32-rounded values and the
-// MMA is tcgen05.mma.kind::tf32 (10-bit mantissa; bf16 operands miss the 1e-3 parity bar,
-// SURVEY.md §7 hard part 1).
-//
-// Data movement: warp 0 streams activation k-blocks (4 planes = 16 channels of every staged
-// sample, ONE contiguous cp.async.bulk per sample) and warp 1 streams 8 KB weight tiles into
-// mbarrier rings; warp 2 issues the MMAs: a 3x3 tap is nothing but a different START ADDRESS in
-// the (unswizzled, K-major) A descriptor, so each activation byte is loaded once per k-block
-// and reused by all 9 taps; warps 4-7 drain TMEM and run the fused epilogue (bias, ReLU, ReLU
-// backward mask, accumulate, fused 1x1-conv + sigmoid attention head).
+// Same ConvTask / ConvCfg semantics, same fp16 operands (half planes, packed fp16 weight tiles) and
+// the same fused epilogue as the tcgen05 path in exec.cu, but plain fp32 FMAs on CUDA cores.  It is
+// selected only by PNMN_EXEC=levels (one launch per level, used by tests to separate tensor-core
+// descriptor problems from scheduling / layout problems); the product path is the persistent
+// tcgen05 executor (exec.cu).
 //
 // Reference semantics: nn.Conv2d(128,128,3,padding=d,dilation=d) + F.relu and the 1x1 + sigmoid
 // heads of probnmn/modules/nmn_modules.py:82-87,119-123,160-168,239-244; stem nmn.py:67-72.
 #include <cuda_fp16.h>
 
 #include "executor.h"
+#include "layout.h"
 #include "tcgen05.cuh"
 
 namespace pnmn {
 
-constexpr int kConvThreads = 256;
-constexpr int kNumWStages = 8;
-constexpr int kWTileBytes = 16 * 128 * 4;  // 16 k x 128 n fp32
-constexpr int kMaxAStages = 4;
-constexpr int kSmemHeader = 1024;
-constexpr int kSmemGuard = 4096;  // trailing bytes garbage rows of the last M tile may read
-constexpr int kSmemTotal = 227 * 1024;
-constexpr int kABudget = kSmemTotal - kSmemHeader - kNumWStages * kWTileBytes - kSmemGuard;
-
-struct ConvSmemHeader {
-  uint64_t full_a[kMaxAStages];
-  uint64_t empty_a[kMaxAStages];
-  uint64_t full_w[kNumWStages];
-  uint64_t empty_w[kNumWStages];
-  uint64_t tmem_full;
-  uint32_t tmem_base;
-};
-static_assert(sizeof(ConvSmemHeader) <= kSmemHeader, "header too large");
-
 __device__ __forceinline__ int tap_shift(const ConvCfg& c, int tap) {
   return c.ntaps == 9 ? ((tap / 3 - 1) * c.S_in + (tap % 3 - 1)) * c.dil : 0;
 }
-
-// Fused epilogue for one output row (pixel slot) and 4 consecutive output channels.
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
   const __half2 h = __floats2half2_rn(fminf(fmaxf(a, -65504.f), 65504.f), fminf(fmaxf(b, -65504.f), 65504.f));
   return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+// Fused epilogue for one output row (pixel slot) and 4 consecutive output channels.
 __device__ __forceinline__ void epilogue4(const ConvTask& t, const ConvCfg& c, int s, int kc, int so,
                                           int sx, float4& o, float& dot) {
   const int n0 = kc * 4;
@@ -79,176 +53,15 @@ __device__ __forceinline__ void epilogue4(const ConvTask& t, const ConvCfg& c, i
     dot = fmaf(o.x, w.x, dot); dot = fmaf(o.y, w.y, dot);
     dot = fmaf(o.z, w.z, dot); dot = fmaf(o.w, w.w, dot);
   }
-  if (c.flags & F_STORE) {
-    o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
-    *dst = o;
-  }
+  o.x = to_tf32(o.x); o.y = to_tf32(o.y); o.z = to_tf32(o.z); o.w = to_tf32(o.w);
+  if (c.flags & F_STORE) *dst = o;
 }
 
-template <int NS, int NMT>
-__global__ void __launch_bounds__(kConvThreads, 1)
-conv_tc_kernel(const ConvTask* __restrict__ tasks, const ConvCfg* __restrict__ cfgs) {
-  extern __shared__ __align__(1024) uint8_t smem[];
-  ConvSmemHeader* hdr = reinterpret_cast<ConvSmemHeader*>(smem);
-  uint8_t* w_ring = smem + kSmemHeader;
-  uint8_t* a_ring = w_ring + kNumWStages * kWTileBytes;
-
-  const ConvTask t = tasks[blockIdx.x];
-  const ConvCfg c = cfgs[t.cfg];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  const uint32_t plane_bytes = static_cast<uint32_t>(c.P_in) * 16u;
-  const uint32_t samp_bytes = static_cast<uint32_t>(c.lead) * 16u + 4u * plane_bytes;
-  const uint32_t stage_bytes = NS * samp_bytes;
-  int nsa = kABudget / static_cast<int>(stage_bytes);
-  nsa = nsa > kMaxAStages ? kMaxAStages : nsa;
-
-  // Zero the lead gaps once (bulk copies never touch them).
-  for (int st = 0; st < nsa; ++st)
-    for (int s = 0; s < NS; ++s) {
-      float4* g = reinterpret_cast<float4*>(a_ring + st * stage_bytes + s * samp_bytes);
-      for (int i = threadIdx.x; i < c.lead; i += kConvThreads) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < kMaxAStages; ++i) {
-      mbar_init(smem_u32(&hdr->full_a[i]), 1);
-      mbar_init(smem_u32(&hdr->empty_a[i]), 1);
-    }
-    for (int i = 0; i < kNumWStages; ++i) {
-      mbar_init(smem_u32(&hdr->full_w[i]), 1);
-      mbar_init(smem_u32(&hdr->empty_w[i]), 1);
-    }
-    mbar_init(smem_u32(&hdr->tmem_full), 1);
-    fence_mbar_init();
-  }
-  if (warp == 2) tmem_alloc<512>(smem_u32(&hdr->tmem_base));
-  fence_proxy_async();
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = hdr->tmem_base;
-
-  if (warp == 0) {
-    // ---------------- activation producer ----------------
-    if (lane == 0) {
-      for (int kb = 0; kb < c.n_kb; ++kb) {
-        const int sa = kb % nsa;
-        const uint32_t ph = (kb / nsa) & 1;
-        mbar_wait(smem_u32(&hdr->empty_a[sa]), ph ^ 1);
-        const uint32_t bar = smem_u32(&hdr->full_a[sa]);
-        mbar_arrive_expect_tx(bar, t.n_samp * 4u * plane_bytes);
-        const int which = kb / c.kb_per_in, kbl = kb % c.kb_per_in;
-        for (int s = 0; s < t.n_samp; ++s) {
-          const float* src = t.in[which][s] + static_cast<size_t>(kbl) * 4 * c.P_in * 4;
-          bulk_g2s(smem_u32(a_ring + sa * stage_bytes + s * samp_bytes) + c.lead * 16u, src,
-                   4u * plane_bytes, bar);
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ---------------- weight producer ----------------
-    if (lane == 0) {
-      const int n_it = c.n_kb * c.ntaps;
-      for (int it = 0; it < n_it; ++it) {
-        const int sw = it % kNumWStages;
-        const uint32_t ph = (it / kNumWStages) & 1;
-        mbar_wait(smem_u32(&hdr->empty_w[sw]), ph ^ 1);
-        const uint32_t bar = smem_u32(&hdr->full_w[sw]);
-        mbar_arrive_expect_tx(bar, kWTileBytes);
-        bulk_g2s(smem_u32(w_ring + sw * kWTileBytes), t.w + static_cast<size_t>(it) * (kWTileBytes / 4),
-                 kWTileBytes, bar);
-      }
-    }
-  } else if (warp == 2) {
-    // ---------------- MMA issuer ----------------
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_tf32(128, 128, 0, 0);
-      int it = 0;
-      for (int kb = 0; kb < c.n_kb; ++kb) {
-        const int sa = kb % nsa;
-        mbar_wait(smem_u32(&hdr->full_a[sa]), (kb / nsa) & 1);
-        for (int tap = 0; tap < c.ntaps; ++tap, ++it) {
-          const int sw = it % kNumWStages;
-          mbar_wait(smem_u32(&hdr->full_w[sw]), (it / kNumWStages) & 1);
-          tc_fence_after();
-          const int shift = tap_shift(c, tap);
-          const uint32_t wb = smem_u32(w_ring + sw * kWTileBytes);
-          for (int s = 0; s < t.n_samp; ++s) {
-#pragma unroll
-            for (int mt = 0; mt < NMT; ++mt) {
-              const uint32_t ab = smem_u32(a_ring + sa * stage_bytes + s * samp_bytes) +
-                                  static_cast<uint32_t>(c.lead + mt * 128 + shift) * 16u;
-#pragma unroll
-              for (int k8 = 0; k8 < 2; ++k8) {
-                const uint64_t ad = make_smem_desc(ab + k8 * 2u * plane_bytes, plane_bytes, 128u);
-                const uint64_t bd = make_smem_desc(wb + k8 * 2u * 2048u, 2048u, 128u);
-                umma_tf32(tmem_base + (s * NMT + mt) * 128, ad, bd, idesc, (kb | tap | k8) != 0);
-              }
-            }
-          }
-          umma_commit(smem_u32(&hdr->empty_w[sw]));
-        }
-        umma_commit(smem_u32(&hdr->empty_a[sa]));
-      }
-      umma_commit(smem_u32(&hdr->tmem_full));
-    }
-  } else if (warp >= 4) {
-    // ---------------- epilogue ----------------
-    const int q = warp & 3;
-    mbar_wait(smem_u32(&hdr->tmem_full), 0);
-    tc_fence_after();
-    for (int s = 0; s < t.n_samp; ++s) {
-      for (int mt = 0; mt < NMT; ++mt) {
-        const int r = mt * 128 + q * 32 + lane;
-        const int y = r / c.S_in, x = r - y * c.S_in;
-        const bool valid = (y < kHW) && (x < kHW);
-        const int so = y * c.S_out + x, sx = y * c.S_aux + x;
-        float dot = 0.f;
-#pragma unroll 1
-        for (int chunk = 0; chunk < 4; ++chunk) {
-          uint32_t v[32];
-          tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (s * NMT + mt) * 128 + chunk * 32, v);
-          tmem_ld_wait();
-          if (valid) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float4 o0 = make_float4(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1]),
-                                      __uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3]));
-              float4 o1 = make_float4(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5]),
-                                      __uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7]));
-              const int kc = chunk * 8 + 2 * j;
-              epilogue4(t, c, s, kc, so, sx, o0, dot);
-              epilogue4(t, c, s, kc + 1, so, sx, o1, dot);
-              if (c.flags & F_HALF) {
-                uint4 h = make_uint4(pack_half2(o0.x, o0.y), pack_half2(o0.z, o0.w), pack_half2(o1.x, o1.y),
-                                     pack_half2(o1.z, o1.w));
-                uint8_t* hb = reinterpret_cast<uint8_t*>(t.out[s]) + shadow_bytes(c.P_out);
-                *reinterpret_cast<uint4*>(hb + (static_cast<size_t>(kc >> 1) * c.P_out + so) * 16) = h;
-              }
-            }
-          }
-        }
-        if ((c.flags & F_DOTSIG) && valid)
-          t.map_out[s][y * 16 + x] = 1.f / (1.f + expf(-(dot + __ldg(t.b3))));
-      }
-    }
-  }
-
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
-}
-
-// ------------------------------------------------------------------------------------------------
-// Bring-up / debugging twin: identical task semantics on CUDA cores in plain fp32 FMA.  It is
-// selected only by PNMN_CONV_IMPL=simt (tests use it to separate tensor-core descriptor problems
-// from scheduling / layout problems); the product path is the tcgen05 kernel above.
-// ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-conv_simt_kernel(const ConvTask* __restrict__ tasks, const ConvCfg* __restrict__ cfgs, int nmt) {
+conv_simt_kernel(const ConvTask* __restrict__ tasks, const ConvCfg* __restrict__ cfgs) {
   const ConvTask t = tasks[blockIdx.x];
   const ConvCfg c = cfgs[t.cfg];
+  const int nmt = c.P_in == 484 ? 3 : 2;
   const int rows = nmt * 128;
   // one thread per (sample, row, kc-out); 4 output channels each
   const int total = t.n_samp * rows * kKC;
@@ -260,22 +73,23 @@ conv_simt_kernel(const ConvTask* __restrict__ tasks, const ConvCfg* __restrict__
     const int r = (idx / kKC) % rows;
     const int s = idx / (kKC * rows);
     const int y = r / c.S_in, x = r - y * c.S_in;
-    if (y >= kHW || x >= kHW) continue;
+    if (y >= kHW || x >= kHW || r < t.mt0 * 128 || r >= (t.mt0 + t.n_mt) * 128) continue;
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int kb = 0; kb < c.n_kb; ++kb) {
       const int which = kb / c.kb_per_in, kbl = kb % c.kb_per_in;
-      const float* in = t.in[which][s];
+      const __half* in = static_cast<const __half*>(t.in[which][s]);
       for (int tap = 0; tap < c.ntaps; ++tap) {
         const int rr = r + tap_shift(c, tap);
-        const float* wt = t.w + (static_cast<size_t>(kb) * c.ntaps + tap) * (kWTileBytes / 4);
-        for (int kc = 0; kc < 4; ++kc) {
-          const int plane = kbl * 4 + kc;
+        const __half* wt = static_cast<const __half*>(t.w) + (static_cast<size_t>(kb) * c.ntaps + tap) * 2048;
+        for (int kc = 0; kc < 2; ++kc) {
+          const int plane = kbl * 2 + kc;
           if (plane == 0 && rr < 0) continue;  // staged lead gap == zeros
-          const float4 a = *reinterpret_cast<const float4*>(in + (static_cast<ptrdiff_t>(plane) * c.P_in + rr) * 4);
-          const float av[4] = {a.x, a.y, a.z, a.w};
-          for (int e = 0; e < 4; ++e)
+          const __half* a = in + (static_cast<ptrdiff_t>(plane) * c.P_in + rr) * 8;
+          for (int e = 0; e < 8; ++e) {
+            const float av = __half2float(a[e]);
             for (int j = 0; j < 4; ++j)
-              acc[j] = fmaf(av[e], wt[(kc * 128 + kc_out * 4 + j) * 4 + e], acc[j]);
+              acc[j] = fmaf(av, __half2float(wt[(kc * 128 + kc_out * 4 + j) * 8 + e]), acc[j]);
+          }
         }
       }
     }
@@ -295,31 +109,15 @@ conv_simt_kernel(const ConvTask* __restrict__ tasks, const ConvCfg* __restrict__
     for (int i = threadIdx.x; i < t.n_samp * rows; i += blockDim.x) {
       const int s = i / rows, r = i % rows;
       const int y = r / c.S_in, x = r - y * c.S_in;
-      if (y < kHW && x < kHW) t.map_out[s][y * 16 + x] = 1.f / (1.f + expf(-(dots[s * 512 + r] + __ldg(t.b3))));
+      if (y < kHW && x < kHW && r >= t.mt0 * 128 && r < (t.mt0 + t.n_mt) * 128)
+        t.map_out[s][y * 16 + x] = 1.f / (1.f + expf(-(dots[s * 512 + r] + __ldg(t.b3))));
     }
   }
 }
 
-// variant 0: NS=2, NMT=2 (P16 / P18 inputs)    variant 1: NS=1, NMT=3 (P22 input)
-cudaError_t launch_conv(const ConvTask* d_tasks, int n_tasks, const ConvCfg* d_cfgs, int variant,
-                        int impl_simt, cudaStream_t stream) {
+cudaError_t launch_conv_simt(const ConvTask* d_tasks, int n_tasks, const ConvCfg* d_cfgs, cudaStream_t stream) {
   if (n_tasks <= 0) return cudaSuccess;
-  if (impl_simt) {
-    conv_simt_kernel<<<n_tasks, 256, 0, stream>>>(d_tasks, d_cfgs, variant == 0 ? 2 : 3);
-    return cudaGetLastError();
-  }
-  static bool attr_done = false;
-  if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(conv_tc_kernel<2, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(conv_tc_kernel<1, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemTotal);
-    if (e != cudaSuccess) return e;
-    attr_done = true;
-  }
-  if (variant == 0)
-    conv_tc_kernel<2, 2><<<n_tasks, kConvThreads, kSmemTotal, stream>>>(d_tasks, d_cfgs);
-  else
-    conv_tc_kernel<1, 3><<<n_tasks, kConvThreads, kSmemTotal, stream>>>(d_tasks, d_cfgs);
+  conv_simt_kernel<<<n_tasks, 256, 0, stream>>>(d_tasks, d_cfgs);
   return cudaGetLastError();
 }
 

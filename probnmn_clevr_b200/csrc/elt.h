@@ -40,7 +40,8 @@ struct EltTask {
   float* dw2;
   int* idx;
   const float* scale;  // {loss scale, 1/loss scale} of this backward pass (backward ops only)
-  int64_t pad_[4];
+  int part, n_parts;   // plane-parallel ops are split over n_parts CTAs (planes [32*part/n, 32*(part+1)/n)); 0 = 1
+  int64_t pad_[3];
 };
 static_assert(sizeof(EltTask) == 128, "EltTask must stay 128 bytes");
 

@@ -1,0 +1,427 @@
+// Persistent program executor: ONE launch walks every sample's compiled program.
+//
+// The host-side program compiler (nmn_executor.cu) turns a batch of programs into a task list:
+// tensor-core convolution tasks (shift-GEMM, see conv.cu for the formulation) and CUDA-core tasks
+// (attend, same, min/max, the backward pieces; elt_body.cuh).  Every task names the tasks that
+// produce its inputs.  148 resident CTAs (one per SM) pull tasks from a global counter in list
+// order, spin on the `done` flags of their predecessors, run the task and publish their own flag.
+// Because predecessors always sit earlier in the list and tasks are fetched in order, a waiting
+// CTA can only wait for a task that is already running: no deadlock, no host round trips, no
+// per-level launch latency, and chains of different samples overlap freely across the SMs.
+//
+// Inside a CTA a convolution task is warp-specialised exactly like conv.cu: warp 0 streams
+// activation k-blocks and warp 1 streams weight tiles with cp.async.bulk into mbarrier rings,
+// warp 2 issues tcgen05.mma (kind::f16 on fp16 operands, fp32 accumulators in TMEM), warp 3 is the scheduler, warps
+// 4-11 (two per TMEM lane quarter, each taking half of the 128 columns) run the fused epilogue.
+// TMEM, barriers and ring phases persist across tasks.
+#include <cuda_fp16.h>
+
+#include "elt_body.cuh"
+#include "executor.h"
+#include "exec.h"
+#include "tcgen05.cuh"
+
+namespace pnmn {
+
+constexpr int kExThreads = 384;
+constexpr int kExWStages = 8;
+constexpr int kExWTile = 16 * 128 * 2;     // 4 KB: 16 k x 128 n fp16
+constexpr int kExWStage = 3 * kExWTile;    // one tap ROW (3 taps) per ring stage: one barrier round trip per row
+constexpr int kExAStages = 4;
+constexpr int kExAStage = 24 * 1024;       // max over plane formats of NS*(lead + 2*P)*16 (fp16 half planes)
+constexpr int kExHeader = 8 * 1024;
+constexpr int kExGuard = 3 * 1024;
+constexpr int kExSmem = kExHeader + kExWStages * kExWStage + kExAStages * kExAStage + kExGuard;
+static_assert(kExSmem <= 227 * 1024, "executor smem");
+
+struct ExHeader {
+  uint64_t full_a[kExAStages], empty_a[kExAStages];
+  uint64_t full_w[kExWStages], empty_w[kExWStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+  int task_idx;
+  TaskMeta meta;
+  alignas(16) uint8_t task[128];
+  alignas(16) float bias[128];
+  alignas(16) float w3[128];
+  float dotp[2][512];
+  EltSmem elt;
+};
+static_assert(sizeof(ExHeader) <= kExHeader, "executor header");
+
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ int ex_tap_shift(const ConvCfg& c, int tap) {
+  return c.ntaps == 9 ? ((tap / 3 - 1) * c.S_in + (tap % 3 - 1)) * c.dil : 0;
+}
+
+__device__ __forceinline__ long long gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ int smid() {
+  int v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+  return v;
+}
+
+// trace (optional, debugging / profiling): 16 int64 per task (globaltimer, ns):
+//   [0] fetched  [1] dependencies satisfied  [2] producer done  [3] published
+//   [4] SM id    [5] type | n_samp<<8 | n_mt<<16   [6] MMAs per (sample, M tile)   [7] cfg flags / elt op
+//   [8] roles start (after barrier B)  [9] first operands landed  [10] last MMA issued
+//   [11] accumulators complete  [12] epilogue stores issued  [13] epilogue fenced
+__global__ void __launch_bounds__(kExThreads, 1)
+exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ metas, int n_tasks,
+            const ConvCfg* __restrict__ cfgs, int* __restrict__ counter, int* __restrict__ done,
+            long long* __restrict__ trace) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  ExHeader* hdr = reinterpret_cast<ExHeader*>(smem);
+  uint8_t* w_ring = smem + kExHeader;
+  uint8_t* a_ring = w_ring + kExWStages * kExWStage;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < kExAStages; ++i) {
+      mbar_init(smem_u32(&hdr->full_a[i]), 1);
+      mbar_init(smem_u32(&hdr->empty_a[i]), 1);
+    }
+    for (int i = 0; i < kExWStages; ++i) {
+      mbar_init(smem_u32(&hdr->full_w[i]), 1);
+      mbar_init(smem_u32(&hdr->empty_w[i]), 1);
+    }
+    mbar_init(smem_u32(&hdr->tmem_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<512>(smem_u32(&hdr->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+
+  // ring positions persist across tasks (each role thread keeps its own copy)
+  uint32_t na = 0, nw = 0, n_conv = 0;
+
+  for (;;) {
+    // ---------------- scheduler: fetch the next task, wait for its producers ----------------
+    if (warp == 3) {
+      int idx = 0;
+      if (lane == 0) idx = atomicAdd(counter, 1);
+      idx = __shfl_sync(0xffffffffu, idx, 0);
+      if (idx < n_tasks) {
+        if (trace && lane == 0) trace[idx * 16 + 0] = gtime();
+        reinterpret_cast<uint32_t*>(hdr->task)[lane] = reinterpret_cast<const uint32_t*>(tasks + static_cast<size_t>(idx) * 128)[lane];
+        if (lane < static_cast<int>(sizeof(TaskMeta) / 4))
+          reinterpret_cast<uint32_t*>(&hdr->meta)[lane] = reinterpret_cast<const uint32_t*>(metas + idx)[lane];
+        __syncwarp();
+        if (lane < kMaxDeps) {
+          const int d = hdr->meta.deps[lane];
+          if (d >= 0) {
+            while (ld_acquire(done + d) == 0) __nanosleep(64);
+          }
+        }
+        __syncwarp();
+        if (trace && lane == 0) { trace[idx * 16 + 1] = gtime(); trace[idx * 16 + 4] = smid(); }
+      }
+      if (lane == 0) hdr->task_idx = idx;
+    }
+    __syncthreads();  // (A) task record + dependencies are in place
+    const int idx = hdr->task_idx;
+    if (idx >= n_tasks) break;
+
+    if (hdr->meta.type == TASK_CONV) {
+      // Everything the roles need is copied into registers up front: the PTX wrappers carry "memory"
+      // clobbers, so anything left in shared / local memory would be re-read around every MMA.
+      // They are also passed through a lane-0 shuffle: that is how the compiler learns they are warp-uniform,
+      // which lets the MMA issuer build its descriptors in uniform registers (no R2UR / elect loops per MMA).
+#define UNI(x) __shfl_sync(0xffffffffu, (x), 0)
+      const ConvTask* tp = reinterpret_cast<const ConvTask*>(hdr->task);
+      const int cfg_id = UNI(tp->cfg), n_samp = UNI(tp->n_samp), mt0 = UNI(tp->mt0), n_mt = UNI(tp->n_mt);
+      const ConvCfg* cp = cfgs + cfg_id;
+      const int n_kb = UNI(cp->n_kb), kb_per_in = UNI(cp->kb_per_in), ntaps = UNI(cp->ntaps), dil = UNI(cp->dil);
+      const int S_in = UNI(cp->S_in), P_in = UNI(cp->P_in), S_out = UNI(cp->S_out), P_out = UNI(cp->P_out);
+      const int S_aux = UNI(cp->S_aux), P_aux = UNI(cp->P_aux);
+      const int flags = UNI(cp->flags), lead = UNI(cp->lead);
+#undef UNI
+      const int nmt = P_in == 484 ? 3 : 2;  // M tiles per sample (P22 planes span 3)
+      const uint32_t plane_bytes = static_cast<uint32_t>(P_in) * 16u;
+      const uint32_t samp_bytes = static_cast<uint32_t>(lead) * 16u + 2u * plane_bytes;  // 2 half planes = 16 ch
+      const int tps = ntaps == 9 ? 3 : 1;     // taps per weight stage
+      const int rows_w = ntaps / tps;         // weight stages per k-block
+      const int n_ws = n_kb * rows_w;         // weight stages of this task
+      // zero the lead gaps of this plane format; stage bias / 1x1 head weights
+      for (int st = 0; st < kExAStages; ++st)
+        for (int s = 0; s < n_samp; ++s) {
+          float4* g = reinterpret_cast<float4*>(a_ring + st * kExAStage + s * samp_bytes);
+          for (int i = tid; i < lead; i += kExThreads) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      if (tid < 128) {
+        hdr->bias[tid] = (flags & F_BIAS) ? __ldg(tp->bias + tid) : 0.f;
+        hdr->w3[tid] = (flags & F_DOTSIG) ? __ldg(tp->w3 + tid) : 0.f;
+      }
+      fence_proxy_async();
+      __syncthreads();  // (B)
+
+      if (warp == 0) {
+        // ---------------- activation producer ----------------
+        if (lane == 0) {
+          const uint8_t* in00 = static_cast<const uint8_t*>(tp->in[0][0]);
+          const uint8_t* in01 = static_cast<const uint8_t*>(tp->in[0][1]);
+          const uint8_t* in10 = static_cast<const uint8_t*>(tp->in[1][0]);
+          const uint8_t* in11 = static_cast<const uint8_t*>(tp->in[1][1]);
+          const uint32_t a_base = smem_u32(a_ring) + lead * 16u;
+          const uint32_t kb_bytes = 2u * plane_bytes;
+          fence_proxy_async_all();
+          for (int kb = 0; kb < n_kb; ++kb, ++na) {
+            const int sa = na % kExAStages;
+            mbar_wait(smem_u32(&hdr->empty_a[sa]), ((na / kExAStages) & 1) ^ 1);
+            const uint32_t bar = smem_u32(&hdr->full_a[sa]);
+            mbar_arrive_expect_tx(bar, n_samp * kb_bytes);
+            const bool second = kb >= kb_per_in;
+            const size_t off = static_cast<size_t>(second ? kb - kb_per_in : kb) * kb_bytes;
+            bulk_g2s(a_base + sa * kExAStage, (second ? in10 : in00) + off, kb_bytes, bar);
+            if (n_samp > 1) bulk_g2s(a_base + sa * kExAStage + samp_bytes, (second ? in11 : in01) + off, kb_bytes, bar);
+          }
+        }
+      } else if (warp == 1) {
+        // ---------------- weight producer ----------------
+        if (lane == 0) {
+          const uint8_t* wsrc = static_cast<const uint8_t*>(tp->w);
+          const uint32_t bytes = static_cast<uint32_t>(tps) * kExWTile;
+          const uint32_t w_base = smem_u32(w_ring);
+          fence_proxy_async_all();
+          for (int it = 0; it < n_ws; ++it, ++nw) {
+            const int sw = nw % kExWStages;
+            mbar_wait(smem_u32(&hdr->empty_w[sw]), ((nw / kExWStages) & 1) ^ 1);
+            const uint32_t bar = smem_u32(&hdr->full_w[sw]);
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_g2s(w_base + sw * kExWStage, wsrc + static_cast<size_t>(it) * bytes, bytes, bar);
+          }
+        }
+      } else if (warp == 2) {
+        // ---------------- MMA issuer ----------------
+        // The whole warp runs the loop (uniform control flow and operands); one elected lane issues.
+        {
+          tc_fence_after();
+          if (trace && lane == 0) trace[idx * 16 + 8] = gtime();
+          const uint32_t idesc = make_idesc_f16(128, 128, 0, 0);
+          const uint64_t d_hi = make_smem_desc(0, 0, 128u) & 0xFFFFFFFF00000000ull;
+          // K-major, no swizzle: LBO = distance between the two 8-channel halves of a 16-deep k-block
+          const uint32_t a_lo0 = (smem_u32(a_ring) >> 4) + static_cast<uint32_t>(lead) + (static_cast<uint32_t>(P_in) << 16);
+          const uint32_t b_lo0 = (smem_u32(w_ring) >> 4) + ((2048u >> 4) << 16);
+          const uint32_t samp16 = samp_bytes >> 4;
+          const int row_shift = ntaps == 9 ? S_in * dil : 0;  // slots between tap rows
+          const int col_shift = ntaps == 9 ? dil : 0;
+          const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
+          // accumulators of this task: up to 4 (sample, M tile) pairs
+          uint32_t aoff[4], doff[4];
+          int n_acc = 0;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) { aoff[k] = 0; doff[k] = 0; }
+#pragma unroll
+          for (int s = 0; s < 2; ++s)
+#pragma unroll
+            for (int m = 0; m < 3; ++m)
+              if (s < n_samp && m >= mt0 && m < mt0 + n_mt) {
+                const uint32_t av = s * samp16 + m * 128, dv = tm + (s * nmt + m) * 128;
+                if (n_acc == 0) { aoff[0] = av; doff[0] = dv; }
+                else if (n_acc == 1) { aoff[1] = av; doff[1] = dv; }
+                else if (n_acc == 2) { aoff[2] = av; doff[2] = dv; }
+                else { aoff[3] = av; doff[3] = dv; }
+                ++n_acc;
+              }
+          uint32_t ua = __shfl_sync(0xffffffffu, na, 0), uw = __shfl_sync(0xffffffffu, nw, 0);
+          long long wait_a = 0, wait_w = 0;
+          for (int kb = 0; kb < n_kb; ++kb, ++ua) {
+            const int sa = ua % kExAStages;
+            long long c0 = trace ? clock64() : 0;
+            mbar_wait(smem_u32(&hdr->full_a[sa]), (ua / kExAStages) & 1);
+            if (trace) wait_a += clock64() - c0;
+            const uint32_t a_lo_kb = a_lo0 + sa * (kExAStage >> 4);
+            for (int ty = 0; ty < rows_w; ++ty, ++uw) {
+              const int sw = uw % kExWStages;
+              c0 = trace ? clock64() : 0;
+              mbar_wait(smem_u32(&hdr->full_w[sw]), (uw / kExWStages) & 1);
+              if (trace) wait_w += clock64() - c0;
+              tc_fence_after();
+              if (trace && lane == 0 && kb == 0 && ty == 0) trace[idx * 16 + 9] = gtime();
+              const uint32_t b_lo_row = b_lo0 + sw * (kExWStage >> 4);
+              const uint32_t a_lo_row = a_lo_kb + static_cast<uint32_t>((ty - (rows_w >> 1)) * row_shift - col_shift);
+              if (elect_one()) {
+#pragma unroll
+                for (int tx = 0; tx < 3; ++tx) {
+                  if (tx < tps) {
+                    const uint32_t a_lo_tap = a_lo_row + static_cast<uint32_t>(tx * col_shift);
+                    const uint64_t bd = d_hi | (b_lo_row + tx * (kExWTile >> 4));
+                    const uint32_t acc = (kb | ty | tx) == 0 ? 0u : 1u;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                      if (k < n_acc) umma_f16(doff[k], d_hi | (a_lo_tap + aoff[k]), bd, idesc, acc);
+                  }
+                }
+                umma_commit(smem_u32(&hdr->empty_w[sw]));
+                if (ty == rows_w - 1) umma_commit(smem_u32(&hdr->empty_a[sa]));
+              }
+              __syncwarp();
+            }
+          }
+          if (elect_one()) umma_commit(smem_u32(&hdr->tmem_full));
+          __syncwarp();
+          if (trace && lane == 0) { trace[idx * 16 + 10] = gtime(); trace[idx * 16 + 14] = wait_a; trace[idx * 16 + 15] = wait_w; }
+        }
+      } else if (warp >= 4) {
+        // ---------------- epilogue: 8 warps = 4 lane quarters x 2 column halves ----------------
+        const int ew = warp - 4, q = ew & 3, half = ew >> 2;
+        float* out_s[2] = {tp->out[0], tp->out[1]};
+        const float* aux_s[2] = {tp->aux[0], tp->aux[1]};
+        float* map_s[2] = {tp->map_out[0], tp->map_out[1]};
+        const float b3 = (flags & F_DOTSIG) ? __ldg(tp->b3) : 0.f;
+        mbar_wait(smem_u32(&hdr->tmem_full), n_conv & 1);
+        tc_fence_after();
+        if (trace && tid == 128) trace[idx * 16 + 11] = gtime();
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (s >= n_samp) break;
+          float* const outp = out_s[s];
+          const float* const auxp = (flags & F_MASK) ? aux_s[s] : outp;  // F_MASK and F_ACCUM never combine
+          uint8_t* const hb = reinterpret_cast<uint8_t*>(outp) + shadow_bytes(P_out);
+          for (int mt = mt0; mt < mt0 + n_mt; ++mt) {
+            const int r = mt * 128 + q * 32 + lane;
+            const int y = r / S_in, x = r - y * S_in;
+            const bool valid = (y < kHW) && (x < kHW);
+            const int so = y * S_out + x;
+            const int sx = (flags & F_MASK) ? y * S_aux + x : so;
+            const int Px = (flags & F_MASK) ? P_aux : P_out;
+            float dot = 0.f;
+#pragma unroll 1
+            for (int cc = 0; cc < 2; ++cc) {
+              const int chunk = half * 2 + cc;
+              uint32_t v[32];
+              tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (s * nmt + mt) * 128 + chunk * 32, v);
+              float4 ax[8];
+              if (valid && (flags & (F_MASK | F_ACCUM))) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  ax[j] = *reinterpret_cast<const float4*>(auxp + (static_cast<size_t>(chunk * 8 + j) * Px + sx) * 4);
+              }
+              tmem_ld_wait();
+              if (valid) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const int n0 = (chunk * 8 + j) * 4;
+                  const float4 bz = *reinterpret_cast<const float4*>(&hdr->bias[n0]);
+                  float4 o = make_float4(__uint_as_float(v[4 * j]) + bz.x, __uint_as_float(v[4 * j + 1]) + bz.y,
+                                         __uint_as_float(v[4 * j + 2]) + bz.z, __uint_as_float(v[4 * j + 3]) + bz.w);
+                  if (flags & F_RELU) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+                  if (flags & F_MASK) {
+                    o.x = ax[j].x > 0.f ? o.x : 0.f; o.y = ax[j].y > 0.f ? o.y : 0.f;
+                    o.z = ax[j].z > 0.f ? o.z : 0.f; o.w = ax[j].w > 0.f ? o.w : 0.f;
+                  }
+                  if (flags & F_ACCUM) { o.x += ax[j].x; o.y += ax[j].y; o.z += ax[j].z; o.w += ax[j].w; }
+                  if (flags & F_DOTSIG) {
+                    const float4 wz = *reinterpret_cast<const float4*>(&hdr->w3[n0]);
+                    dot = fmaf(o.x, wz.x, dot); dot = fmaf(o.y, wz.y, dot); dot = fmaf(o.z, wz.z, dot); dot = fmaf(o.w, wz.w, dot);
+                  }
+                  v[4 * j] = __float_as_uint(to_tf32(o.x)); v[4 * j + 1] = __float_as_uint(to_tf32(o.y));
+                  v[4 * j + 2] = __float_as_uint(to_tf32(o.z)); v[4 * j + 3] = __float_as_uint(to_tf32(o.w));
+                }
+                if (flags & F_STORE) {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j)
+                    *reinterpret_cast<uint4*>(outp + (static_cast<size_t>(chunk * 8 + j) * P_out + so) * 4) =
+                        make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                if (flags & F_HALF) {
+#pragma unroll
+                  for (int j = 0; j < 4; ++j) {
+                    const uint4 h = make_uint4(
+                        elt_pack_half2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                        elt_pack_half2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                        elt_pack_half2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                        elt_pack_half2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                    *reinterpret_cast<uint4*>(hb + (static_cast<size_t>(chunk * 4 + j) * P_out + so) * 16) = h;
+                  }
+                }
+              }
+            }
+            if (flags & F_DOTSIG) hdr->dotp[half][(s * nmt + mt) * 128 + q * 32 + lane] = dot;
+          }
+        }
+        if (flags & F_DOTSIG) {
+          asm volatile("bar.sync 2, 256;" ::: "memory");
+          if (half == 0) {
+#pragma unroll
+            for (int s = 0; s < 2; ++s) {
+              if (s >= n_samp) break;
+              for (int mt = mt0; mt < mt0 + n_mt; ++mt) {
+                const int r = mt * 128 + q * 32 + lane;
+                const int y = r / S_in, x = r - y * S_in;
+                if (y < kHW && x < kHW) {
+                  const int k = (s * nmt + mt) * 128 + q * 32 + lane;
+                  map_s[s][y * 16 + x] = 1.f / (1.f + expf(-(hdr->dotp[0][k] + hdr->dotp[1][k] + b3)));
+                }
+              }
+            }
+          }
+        }
+        if (trace && tid == 128) trace[idx * 16 + 12] = gtime();
+        __threadfence();
+        tc_fence_before();
+        if (trace && tid == 128) trace[idx * 16 + 13] = gtime();
+      }
+      if (trace && tid == 0) {
+        trace[idx * 16 + 5] = TASK_CONV | (n_samp << 8) | (n_mt << 16);
+        trace[idx * 16 + 6] = n_kb * ntaps;  // one K=16 MMA per (k-block, tap, sample, M tile)
+        trace[idx * 16 + 7] = flags;
+      }
+      ++n_conv;
+      // producers / issuer keep their ring counters in sync with the work every conv task does
+      if (!(warp == 0 && lane == 0)) na += n_kb;
+      if (!(warp == 1 && lane == 0)) nw += n_ws;
+    } else {
+      if (warp >= 4) {
+        const EltTask& t = *reinterpret_cast<const EltTask*>(hdr->task);
+        elt_task_body(t, tid - 128, hdr->elt);
+        __threadfence();
+        if (trace && tid == 128) { trace[idx * 16 + 5] = TASK_ELT; trace[idx * 16 + 6] = 0; trace[idx * 16 + 7] = t.op; }
+      }
+    }
+    if (trace && tid == 0) trace[idx * 16 + 2] = gtime();
+    __syncthreads();  // (C) every store of this task is fenced
+    if (tid == 0) {
+      st_release(done + idx, 1);
+      if (trace) trace[idx * 16 + 3] = gtime();
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<512>(tmem_base);
+}
+
+cudaError_t launch_exec(const uint8_t* d_tasks, const TaskMeta* d_meta, int n_tasks, const ConvCfg* d_cfgs,
+                        int* d_counter, int* d_done, long long* d_trace, cudaStream_t stream) {
+  if (n_tasks <= 0) return cudaSuccess;
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = n_tasks < sms ? n_tasks : sms;
+  exec_kernel<<<grid, kExThreads, kExSmem, stream>>>(d_tasks, d_meta, n_tasks, d_cfgs, d_counter, d_done, d_trace);
+  return cudaGetLastError();
+}
+
+}  // namespace pnmn

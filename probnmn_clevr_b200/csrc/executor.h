@@ -66,17 +66,18 @@ struct ConvCfg {
 };
 
 struct ConvTask {
-  const float* in[2][NSMAX];  // [input][sample] -> plane 0 of that input
+  const void* in[2][NSMAX];   // [input][sample] -> fp16 half plane 0 of that input (the shadow copy)
   float* out[NSMAX];
   const float* aux[NSMAX];    // ReLU-mask source
   float* map_out[NSMAX];      // P16 attention map (F_DOTSIG)
-  const float* w;             // packed weight tiles: [kb][tap][kc(4)][n(128)][4]
+  const void* w;              // packed fp16 weight tiles: [kb][tap][kc(2)][n(128)][8]
   const float* bias;          // [128]
   const float* w3;            // [128]
   const float* b3;            // [1]
   int cfg;
   int n_samp;
-  int64_t pad_;
+  int mt0;    // first 128-row M tile this CTA computes
+  int n_mt;   // number of M tiles (the scheduler splits a sample over CTAs when a level has few tasks)
 };
 static_assert(sizeof(ConvTask) == 128, "ConvTask must stay 128 bytes");
 

@@ -7,14 +7,15 @@
 
 namespace pnmn {
 
-// Packed weight tile (the tcgen05 B operand, K-major, no swizzle):
-//   dst[((kb*ntaps + tap)*4 + kc)*128*4 + n*4 + e] = tf32( src[(k_off + kb*16 + kc*4 + e)*k_stride
-//                                                           + (n_off + n)*n_stride + tap'*tap_stride] )
+// Packed weight tile (the tcgen05 B operand, K-major, no swizzle), fp16, 16 k x 128 n = 4 KB:
+//   dst[((kb*ntaps + tap)*2 + kc)*128*8 + n*8 + e] = half( src[(k_off + kb*16 + kc*8 + e)*k_stride
+//                                                            + (n_off + n)*n_stride + tap'*tap_stride] )
 // with tap' = flip ? ntaps-1-tap : tap.  Forward conv: k = cin, n = cout; dgrad: k = cout, n = cin and
-// the taps are mirrored (a correlation with the transposed, flipped kernel).
+// the taps are mirrored (a correlation with the transposed, flipped kernel).  fp16 keeps the same 10-bit
+// mantissa as tf32 (weights below 6.1e-5 in magnitude lose relative precision, which is immaterial).
 __global__ void __launch_bounds__(256) pack_weights_kernel(const PackTask* __restrict__ tasks,
                                                            const float* __restrict__ params,
-                                                           float* __restrict__ packed, int n_tasks) {
+                                                           __half* __restrict__ packed, int n_tasks) {
   // blockIdx.x enumerates tiles of all tasks; tasks carry their first global tile index (sorted)
   int task = 0;
   int tile = blockIdx.x;
@@ -31,19 +32,20 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const PackTask* __res
   const int kb = tile / t.ntaps, tap = tile % t.ntaps;
   const int tp = t.flip ? t.ntaps - 1 - tap : tap;
   const float* src = params + t.src_off;
-  float* dst = packed + t.dst_off + static_cast<size_t>(tile) * 2048;
+  __half* dst = packed + t.dst_off + static_cast<size_t>(tile) * 2048;
   for (int i = threadIdx.x; i < 2048; i += 256) {
-    const int e = i & 3, n = (i >> 2) & 127, kc = i >> 9;
-    const int k = t.k_off + kb * 16 + kc * 4 + e;
-    dst[i] = to_tf32(src[static_cast<size_t>(k) * t.k_stride + static_cast<size_t>(t.n_off + n) * t.n_stride +
-                         static_cast<size_t>(tp) * t.tap_stride]);
+    const int e = i & 7, n = (i >> 3) & 127, kc = i >> 10;
+    const int k = t.k_off + kb * 16 + kc * 8 + e;
+    const float v = src[static_cast<size_t>(k) * t.k_stride + static_cast<size_t>(t.n_off + n) * t.n_stride +
+                        static_cast<size_t>(tp) * t.tap_stride];
+    dst[i] = __float2half_rn(fminf(fmaxf(v, -65504.f), 65504.f));
   }
 }
 
 cudaError_t launch_pack(const PackTask* d_tasks, int n_tasks, int total_tiles, const float* params,
-                        float* packed, cudaStream_t stream) {
+                        void* packed, cudaStream_t stream) {
   if (total_tiles <= 0) return cudaSuccess;
-  pack_weights_kernel<<<total_tiles, 256, 0, stream>>>(d_tasks, params, packed, n_tasks);
+  pack_weights_kernel<<<total_tiles, 256, 0, stream>>>(d_tasks, params, static_cast<__half*>(packed), n_tasks);
   return cudaGetLastError();
 }
 

@@ -9,7 +9,7 @@ namespace pnmn {
 
 struct PackTask {
   int64_t src_off;   // offset (floats) of the reference-layout weight inside the flat parameter buffer
-  int64_t dst_off;   // offset (floats) inside the packed-weight buffer
+  int64_t dst_off;   // offset (halves) inside the packed-weight buffer
   int first_tile;    // global index of this task's first 16x128 tile
   int n_kb, ntaps, flip;
   int k_off, n_off;
@@ -26,11 +26,10 @@ struct BiasGradTaskH {  // mirrors BiasGradTask in wgrad.cu
 };
 
 cudaError_t launch_pack(const PackTask* d_tasks, int n_tasks, int total_tiles, const float* params,
-                        float* packed, cudaStream_t stream);
+                        void* packed, cudaStream_t stream);
 cudaError_t launch_nchw_to_planes(const float* src, float* dst, int B, int C, const int64_t* dst_off,
                                   cudaStream_t stream);
-cudaError_t launch_conv(const ConvTask* d_tasks, int n_tasks, const ConvCfg* d_cfgs, int variant,
-                        int impl_simt, cudaStream_t stream);
+cudaError_t launch_conv_simt(const ConvTask* d_tasks, int n_tasks, const ConvCfg* d_cfgs, cudaStream_t stream);
 cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, cudaStream_t stream);
 cudaError_t launch_bias_grad(const void* d_tasks, int n_tasks, int split, cudaStream_t stream);
 cudaError_t launch_elt(const EltTask* d_tasks, int n_tasks, cudaStream_t stream);

@@ -9,6 +9,7 @@
 // three launches.  The backward chain is derived from the same symbolic execution; weight
 // gradients are batched per weight tensor over all its instances in the batch.
 #include <algorithm>
+#include <chrono>
 #include <array>
 #include <cstdio>
 #include <cstring>
@@ -17,6 +18,7 @@
 #include <vector>
 
 #include "../../include/pnmn.h"
+#include "exec.h"
 #include "layout.h"
 
 using namespace pnmn;
@@ -56,12 +58,14 @@ constexpr int64_t kUnit16 = 48ll * 256 * 16;
 constexpr int64_t kUnit18 = 48ll * 324 * 16;
 constexpr int64_t kUnit22 = 48ll * 484 * 16;
 constexpr int kInstChunk = 16;     // instances per wgrad CTA
+constexpr int kNumSMs = 148;
+constexpr int kEltParts = 4;
 constexpr int kBiasSplit = 8;
 
 struct ConvW {
   int64_t w_off = -1, b_off = -1;  // floats into the flat parameter buffer
   int cin = 128, ksize = 3;
-  int64_t pk_fwd = -1, pk_bwd = -1;  // floats into the packed buffer
+  int64_t pk_fwd = -1, pk_bwd = -1;  // halves into the packed (fp16) weight-tile buffer
 };
 struct ModuleDesc {
   int kind = PNMN_TOK_SKIP;
@@ -144,7 +148,7 @@ extern "C" pnmn_model* pnmn_model_create(int vocab_size, const int32_t* token_ki
   return m;
 }
 extern "C" void pnmn_model_destroy(pnmn_model* m) { delete m; }
-extern "C" int64_t pnmn_model_packed_floats(const pnmn_model* m) { return m->packed_floats; }
+extern "C" int64_t pnmn_model_packed_floats(const pnmn_model* m) { return (m->packed_floats + 1) / 2; }  // fp16 tiles
 
 // =================================================================================================
 // Plan
@@ -181,22 +185,41 @@ struct ConvProto {
   int sample;
 };
 
+struct TaskRec { uint8_t b[128]; };
+
 struct Sched {
   std::vector<int> step, last;
   std::vector<std::array<std::vector<int>, 3>> buckets;  // indices into elts / protos
   std::vector<EltTask> elts;
+  std::vector<int> elt_sample;
   std::vector<ConvProto> protos;
-  explicit Sched(int B) : step(B, 0), last(B, -1) {}
+  bool unified;  // persistent executor: one stage per sample per step (dependencies are explicit)
+  bool dep_overflow = false;
+  Sched(int B, bool uni) : step(B, 0), last(B, -1), unified(uni) {
+    elts.reserve(static_cast<size_t>(B) * 64);
+    elt_sample.reserve(static_cast<size_t>(B) * 64);
+    protos.reserve(static_cast<size_t>(B) * 48);
+    buckets.reserve(128);
+  }
   int place(int s, int kind) {
-    if (kind <= last[s]) step[s]++;
+    if (unified ? last[s] >= 0 : kind <= last[s]) step[s]++;
     last[s] = kind;
     if (static_cast<int>(buckets.size()) <= step[s]) buckets.resize(step[s] + 1);
     return step[s];
   }
   void add_elt(int s, const EltTask& t) {
     const int st = place(s, LK_ELT);
-    buckets[st][LK_ELT].push_back(static_cast<int>(elts.size()));
-    elts.push_back(t);
+    // plane-parallel ops are split over 4 CTAs: shorter critical path, more memory parallelism
+    const bool splittable = t.op == OP_ATTEND || t.op == OP_ATTEND_BWD || t.op == OP_RELU_MASK || t.op == OP_SCATTER ||
+                            t.op == OP_GATHER || t.op == OP_DOTSIG_BWD;
+    const int n_parts = splittable ? kEltParts : 1;
+    for (int part = 0; part < n_parts; ++part) {
+      EltTask e = t;
+      e.part = part; e.n_parts = n_parts;
+      buckets[st][LK_ELT].push_back(static_cast<int>(elts.size()));
+      elts.push_back(e);
+      elt_sample.push_back(s);
+    }
   }
   void add_conv(int s, const ConvTask& t, int variant) {
     const int kind = variant == 0 ? LK_CONV0 : LK_CONV1;
@@ -204,7 +227,47 @@ struct Sched {
     buckets[st][kind].push_back(static_cast<int>(protos.size()));
     protos.push_back(ConvProto{t, s});
   }
-  // Flatten into launch order; conv tasks of one step that share (cfg, weights) are paired.
+  // Conv tasks of one step: pair samples that share (cfg, weights) on wide levels, split M tiles on narrow
+  // ones.  Calls emit(task, samples[], n_samples) for every CTA-level task.
+  template <class Emit>
+  void group_convs(std::vector<int>& v, int kind, Emit emit) {
+    if (v.empty()) return;
+    std::stable_sort(v.begin(), v.end(), [&](int x, int y) {
+      const ConvTask& a = protos[x].t; const ConvTask& c = protos[y].t;
+      if (a.cfg != c.cfg) return a.cfg < c.cfg;
+      return reinterpret_cast<uint64_t>(a.w) < reinterpret_cast<uint64_t>(c.w);
+    });
+    // Task granularity adapts to the level's width (one CTA per SM, 148 SMs): wide levels pair two
+    // samples per CTA (shared weight stream), narrow levels split a sample's M tiles over several CTAs.
+    const int U = static_cast<int>(v.size());
+    const int nmt = kind == LK_CONV0 ? 2 : 3;
+    const int cap = (kind == LK_CONV0 && U > kNumSMs) ? NSMAX : 1;
+    const int split = (U * nmt <= kNumSMs + kNumSMs / 2) ? nmt : 1;
+    size_t i = 0;
+    while (i < v.size()) {
+      ConvTask t = protos[v[i]].t;
+      int samples[NSMAX] = {protos[v[i]].sample, -1};
+      t.n_samp = 1;
+      size_t j = i + 1;
+      while (j < v.size() && t.n_samp < cap && protos[v[j]].t.cfg == t.cfg && protos[v[j]].t.w == t.w) {
+        const ConvTask& o = protos[v[j]].t;
+        const int k = t.n_samp++;
+        samples[k] = protos[v[j]].sample;
+        t.in[0][k] = o.in[0][0]; t.in[1][k] = o.in[1][0];
+        t.out[k] = o.out[0]; t.aux[k] = o.aux[0]; t.map_out[k] = o.map_out[0];
+        ++j;
+      }
+      if (split > 1) {
+        for (int m = 0; m < nmt; ++m) { t.mt0 = m; t.n_mt = 1; emit(t, samples, t.n_samp); }
+      } else {
+        t.mt0 = 0; t.n_mt = nmt;
+        emit(t, samples, t.n_samp);
+      }
+      i = j;
+    }
+  }
+
+  // Level-synchronous order (one launch per kind per step).
   void flatten(std::vector<EltTask>& out_elt, std::vector<ConvTask>& out_conv, std::vector<LaunchItem>& launches) {
     for (auto& b : buckets) {
       if (!b[LK_ELT].empty()) {
@@ -212,32 +275,54 @@ struct Sched {
         for (int i : b[LK_ELT]) out_elt.push_back(elts[i]);
       }
       for (int kind = LK_CONV0; kind <= LK_CONV1; ++kind) {
-        auto& v = b[kind];
-        if (v.empty()) continue;
-        std::stable_sort(v.begin(), v.end(), [&](int x, int y) {
-          const ConvTask& a = protos[x].t; const ConvTask& c = protos[y].t;
-          if (a.cfg != c.cfg) return a.cfg < c.cfg;
-          return reinterpret_cast<uint64_t>(a.w) < reinterpret_cast<uint64_t>(c.w);
-        });
+        if (b[kind].empty()) continue;
         const int64_t off = static_cast<int64_t>(out_conv.size());
-        const int cap = kind == LK_CONV0 ? NSMAX : 1;
-        size_t i = 0;
-        while (i < v.size()) {
-          ConvTask t = protos[v[i]].t;
-          t.n_samp = 1;
-          size_t j = i + 1;
-          while (j < v.size() && t.n_samp < cap && protos[v[j]].t.cfg == t.cfg && protos[v[j]].t.w == t.w) {
-            const ConvTask& o = protos[v[j]].t;
-            const int k = t.n_samp++;
-            t.in[0][k] = o.in[0][0]; t.in[1][k] = o.in[1][0];
-            t.out[k] = o.out[0]; t.aux[k] = o.aux[0]; t.map_out[k] = o.map_out[0];
-            ++j;
-          }
-          out_conv.push_back(t);
-          i = j;
-        }
+        group_convs(b[kind], kind, [&](const ConvTask& t, const int*, int) { out_conv.push_back(t); });
         launches.push_back({kind, off, static_cast<int>(out_conv.size() - off)});
       }
+    }
+  }
+
+  // Persistent-executor order: one list, every task names the tasks of its samples' previous stage.
+  void flatten_persistent(std::vector<TaskRec>& out, std::vector<TaskMeta>& meta) {
+    struct Latest { int n = 0; int ids[4] = {0, 0, 0, 0}; int stamp = -1; };
+    std::vector<Latest> latest(step.size()), next(step.size());
+    size_t total = elts.size();
+    for (auto& b : buckets) total += b[LK_CONV0].size() * 2 + b[LK_CONV1].size() * 3;
+    out.reserve(total);
+    meta.reserve(total);
+    int cur = 0;
+    auto push = [&](const void* rec, int type, const int* samples, int ns) {
+      out.emplace_back();
+      std::memcpy(out.back().b, rec, 128);
+      meta.emplace_back();
+      TaskMeta& m = meta.back();
+      m.type = type; m.n_deps = 0;
+      for (int k = 0; k < kMaxDeps; ++k) m.deps[k] = -1;
+      const int id = static_cast<int>(out.size()) - 1;
+      for (int k = 0; k < ns; ++k) {
+        const Latest& l = latest[samples[k]];
+        for (int j = 0; j < l.n; ++j) {
+          if (m.n_deps < kMaxDeps) m.deps[m.n_deps++] = l.ids[j];
+          else dep_overflow = true;
+        }
+        Latest& nx = next[samples[k]];
+        if (nx.stamp != cur) { nx.stamp = cur; nx.n = 0; }
+        if (nx.n < 4) nx.ids[nx.n++] = id;
+        else dep_overflow = true;
+      }
+    };
+    for (auto& b : buckets) {
+      for (int kind = LK_CONV0; kind <= LK_CONV1; ++kind)
+        group_convs(b[kind], kind, [&](const ConvTask& t, const int* samples, int ns) { push(&t, TASK_CONV, samples, ns); });
+      for (int i : b[LK_ELT]) push(&elts[i], TASK_ELT, &elt_sample[i], 1);
+      // a sample has exactly one stage per step: its `latest` set becomes this step's task ids
+      for (int kind = 0; kind < 3; ++kind)
+        for (int i : b[kind]) {
+          const int smp = kind == LK_ELT ? elt_sample[i] : protos[i].sample;
+          if (next[smp].stamp == cur) { latest[smp] = next[smp]; next[smp].stamp = -1; }
+        }
+      ++cur;
     }
   }
 };
@@ -258,6 +343,10 @@ struct pnmn_plan {
   std::vector<WgradTask> wtasks;
   std::vector<BiasGradTaskH> btasks;
   std::vector<int> xin_unit;  // per sample, -1 if the stem is skipped (invalid program)
+  bool persistent = true;     // one persistent executor launch per pass (exec.cu) vs one launch per level
+  std::vector<TaskRec> ftask, btask;
+  std::vector<TaskMeta> fmeta, bmeta;
+  int64_t off_ftask = 0, off_fmeta = 0, off_fsync = 0, off_btask = 0, off_bmeta = 0, off_bsync = 0;
   // blob layout (bytes)
   int64_t off_cfg = 0, off_xin = 0, off_fconv = 0, off_felt = 0, off_bconv = 0, off_belt = 0, off_inst = 0, off_wt = 0,
           off_bt = 0, blob_bytes = 0;
@@ -301,7 +390,7 @@ struct Builder {
   float* dmapp(int i) const { return sym<float>(AR_DMAPS, static_cast<int64_t>(i) * 1024); }
   const float* param(int64_t off) const { return sym<const float>(AR_PARAMS, off * 4); }
   float* grad(int64_t off) const { return sym<float>(AR_GRADS, off * 4); }
-  const float* packed(int64_t off) const { return sym<const float>(AR_PACKED, off * 4); }
+  const void* packed(int64_t off) const { return sym<const void>(AR_PACKED, off * 2); }
 
   int cfg_id(const ConvCfg& c) {
     for (size_t i = 0; i < p.cfgs.size(); ++i)
@@ -328,20 +417,37 @@ struct Builder {
 
 static const int kRelateDil[5] = {1, 2, 4, 8, 1};
 
+double g_host_ms[4] = {0, 0, 0, 0};  // plan_create, forward (host part), backward (host part), calls
+struct HostTimer {
+  int slot; std::chrono::steady_clock::time_point t0;
+  explicit HostTimer(int s) : slot(s), t0(std::chrono::steady_clock::now()) {}
+  ~HostTimer() { g_host_ms[slot] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+};
+long long* g_trace = nullptr;   // optional device buffer for per-task timestamps (pnmn_debug_set_trace)
+int64_t g_trace_cap = 0;        // capacity in tasks
+
+bool exec_persistent() {
+  const char* e = std::getenv("PNMN_EXEC");
+  return !(e && std::string(e) == "levels");
+}
+
 }  // namespace
 
 extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* programs, int B, int L, int need_grad) {
+  HostTimer timer(0);
+  g_host_ms[3] += 1;
   auto* plan = new pnmn_plan();
   pnmn_plan& p = *plan;
   p.m = m; p.B = B; p.L = L; p.need_grad = need_grad != 0;
   p.valid.assign(B, 0);
   p.xin_unit.assign(B, -1);
   Builder bd(p);
-  Sched fs(B), bs(B);
+  p.persistent = exec_persistent();
+  Sched fs(B, p.persistent), bs(B, p.persistent);
   int n_ain = 0;  // valid samples so far (index into the stem-input arena)
 
-  const int HF = p.need_grad ? F_HALF : 0;      // conv outputs also feed weight gradients
-  const int EHF = p.need_grad ? EF_HALF : 0;
+  const int HF = F_HALF;    // every conv / attend output is the fp16 operand of the next conv (and of wgrad)
+  const int EHF = EF_HALF;
   p.nmaps = 1;  // map 0 = the constant all-ones attention of `scene` (nmn.py:216)
   const int ones_val = bd.new_val(VK_ONES, 1, 0, false);
   bool ones_emitted = false;
@@ -414,13 +520,14 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
       const ConvW& c1 = m->convs[m->stem1];
       ConvTask t{};
       t.cfg = bd.make_cfg(m->in_ch / 16, m->in_ch / 16, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE | HF);
-      t.in[0][0] = bd.ainp(xin); t.out[0] = bd.p16(y1s_unit[n]);
+      t.in[0][0] = reinterpret_cast<const void*>(reinterpret_cast<uint64_t>(bd.ainp(xin)) + static_cast<uint64_t>(m->in_ch / 4) * 256 * 16);
+      t.out[0] = bd.p16(y1s_unit[n]);
       t.w = bd.packed(c1.pk_fwd); t.bias = bd.param(c1.b_off);
       fs.add_conv(n, t, 0);
       const ConvW& c2 = m->convs[m->stem2];
       ConvTask u{};
       u.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE | HF);
-      u.in[0][0] = bd.p16(y1s_unit[n]); u.out[0] = bd.p16(feat_unit[n]);
+      u.in[0][0] = Builder::shadow(bd.p16(y1s_unit[n]), kP16); u.out[0] = bd.p16(feat_unit[n]);
       u.w = bd.packed(c2.pk_fwd); u.bias = bd.param(c2.b_off);
       fs.add_conv(n, u, 0);
     }
@@ -460,7 +567,8 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           vo.unit = r.y_unit[2];
           ConvTask t{};
           t.cfg = bd.make_cfg(16, 8, 1, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE | HF);
-          t.in[0][0] = bd.p16(bd.vals[r.in0].unit); t.in[1][0] = bd.p16(bd.vals[r.in1].unit);
+          t.in[0][0] = Builder::shadow(bd.p16(bd.vals[r.in0].unit), kP16);
+          t.in[1][0] = Builder::shadow(bd.p16(bd.vals[r.in1].unit), kP16);
           t.out[0] = bd.p16(r.y_unit[0]); t.w = bd.packed(pj.pk_fwd); t.bias = bd.param(pj.b_off);
           fs.add_conv(n, t, 0);
           flops += 2ll * 196 * 128 * 256;
@@ -468,7 +576,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             const ConvW& cw = m->convs[md.convs[i]];
             ConvTask u{};
             u.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE | HF);
-            u.in[0][0] = bd.p16(r.y_unit[i - 1]); u.out[0] = bd.p16(r.y_unit[i]);
+            u.in[0][0] = Builder::shadow(bd.p16(r.y_unit[i - 1]), kP16); u.out[0] = bd.p16(r.y_unit[i]);
             u.w = bd.packed(cw.pk_fwd); u.bias = bd.param(cw.b_off);
             fs.add_conv(n, u, 0);
             n_conv3++;
@@ -496,7 +604,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             r.y_unit[i] = bd.alloc_fmt(fout);
             ConvTask t{};
             t.cfg = bd.make_cfg(8, 8, 9, d, fin, fout, fout, F_BIAS | F_RELU | F_STORE | HF | ((last && head) ? F_DOTSIG : 0));
-            t.in[0][0] = x; t.out[0] = bd.pfmt(fout, r.y_unit[i]);
+            t.in[0][0] = Builder::shadow(x, fin); t.out[0] = bd.pfmt(fout, r.y_unit[i]);
             t.w = bd.packed(cw.pk_fwd); t.bias = bd.param(cw.b_off);
             if (last && head) {
               vo.unit = static_cast<int>(p.nmaps++);
@@ -604,7 +712,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             const int du = bd.alloc16();
             ConvTask t{};
             t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_STORE | F_MASK | F_HALF);
-            t.in[0][0] = dz; t.out[0] = bd.p16(du); t.aux[0] = bd.p16(r.y_unit[i - 1]);
+            t.in[0][0] = Builder::shadow(dz, kP16); t.out[0] = bd.p16(du); t.aux[0] = bd.p16(r.y_unit[i - 1]);
             t.w = bd.packed(cw.pk_bwd);
             bs.add_conv(n, t, 0);
             dz = bd.p16(du);
@@ -619,7 +727,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             const bool fm = fused_mask(v);
             ConvTask t{};
             t.cfg = bd.make_cfg(8, 8, 1, 1, kP16, kP16, kP16, F_STORE | (fm ? (F_MASK | F_HALF) : 0) | (v.gwritten ? F_ACCUM : 0));
-            t.in[0][0] = dz; t.out[0] = gbuf(v); t.aux[0] = fm ? bd.p16(v.unit) : nullptr;
+            t.in[0][0] = Builder::shadow(dz, kP16); t.out[0] = gbuf(v); t.aux[0] = fm ? bd.p16(v.unit) : nullptr;
             t.w = bd.packed(pj.pk_bwd + static_cast<int64_t>(h) * 8 * 2048);
             v.gwritten = true;
             bs.add_conv(n, t, 0);
@@ -649,7 +757,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             const float* xin_i = i == 0 ? (r.x0_is_feat ? featp : bd.p16(r.x0_unit)) : bd.pfmt(f, r.y_unit[i - 1]);
             add_inst(md.convs[i], dz, xin_i, f, d);
             ConvTask t{};
-            t.in[0][0] = dz; t.w = bd.packed(cw.pk_bwd);
+            t.in[0][0] = Builder::shadow(dz, f); t.w = bd.packed(cw.pk_bwd);
             if (i > 0) {
               const PlaneFmt fprev = fmt_for_dilation(dil_of(i - 1));
               const int du = bd.alloc_fmt(fprev);
@@ -687,7 +795,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
       const ConvW& c2 = m->convs[m->stem2];
       ConvTask t{};
       t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_STORE | F_MASK | F_HALF);
-      t.in[0][0] = dfeatp; t.out[0] = bd.p16(dz1); t.aux[0] = bd.p16(y1s_unit[n]);
+      t.in[0][0] = Builder::shadow(dfeatp, kP16); t.out[0] = bd.p16(dz1); t.aux[0] = bd.p16(y1s_unit[n]);
       t.w = bd.packed(c2.pk_bwd);
       bs.add_conv(n, t, 0);
       add_inst(m->stem2, dfeatp, bd.p16(y1s_unit[n]), kP16, 1);
@@ -698,9 +806,12 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   }
 
   // ---------------- flatten ----------------
-  fs.flatten(p.felt, p.fconv, p.flaunch);
+  const auto t_emit = std::chrono::steady_clock::now();
+  if (p.persistent) fs.flatten_persistent(p.ftask, p.fmeta);
+  else fs.flatten(p.felt, p.fconv, p.flaunch);
   if (p.need_grad) {
-    bs.flatten(p.belt, p.bconv, p.blaunch);
+    if (p.persistent) bs.flatten_persistent(p.btask, p.bmeta);
+    else bs.flatten(p.belt, p.bconv, p.blaunch);
     // wgrad / bias-grad tasks per weight tensor
     const int64_t inst_base = 0;
     (void)inst_base;
@@ -762,6 +873,17 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
     p.blaunch.push_back({LK_BIAS, 0, static_cast<int>(p.btasks.size())});
   }
 
+  const auto t_flat = std::chrono::steady_clock::now();
+  if (std::getenv("PNMN_PLAN_TIMING")) {
+    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    std::fprintf(stderr, "plan: emit %.2f ms, flatten+wgrad %.2f ms, tasks fwd %zu bwd %zu\n", ms(timer.t0, t_emit),
+                 ms(t_emit, t_flat), p.ftask.size(), p.btask.size());
+  }
+  if (fs.dep_overflow || bs.dep_overflow) {
+    g_err = "internal error: a task has more predecessors than kMaxDeps";
+    delete plan;
+    return nullptr;
+  }
   // ---------------- blob layout ----------------
   auto align = [](int64_t x) { return (x + 255) / 256 * 256; };
   int64_t o = 0;
@@ -769,11 +891,17 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   p.off_xin = o; o = align(o + static_cast<int64_t>(B) * 8);
   p.off_fconv = o; o = align(o + static_cast<int64_t>(p.fconv.size() * sizeof(ConvTask)));
   p.off_felt = o; o = align(o + static_cast<int64_t>(p.felt.size() * sizeof(EltTask)));
+  p.off_ftask = o; o = align(o + static_cast<int64_t>(p.ftask.size() * sizeof(TaskRec)));
+  p.off_fmeta = o; o = align(o + static_cast<int64_t>(p.fmeta.size() * sizeof(TaskMeta)));
   p.off_bconv = o; o = align(o + static_cast<int64_t>(p.bconv.size() * sizeof(ConvTask)));
   p.off_belt = o; o = align(o + static_cast<int64_t>(p.belt.size() * sizeof(EltTask)));
   p.off_inst = o; o = align(o + static_cast<int64_t>(p.insts.size() * sizeof(WgradInst)));
   p.off_wt = o; o = align(o + static_cast<int64_t>(p.wtasks.size() * sizeof(WgradTask)));
   p.off_bt = o; o = align(o + static_cast<int64_t>(p.btasks.size() * sizeof(BiasGradTaskH)));
+  p.off_btask = o; o = align(o + static_cast<int64_t>(p.btask.size() * sizeof(TaskRec)));
+  p.off_bmeta = o; o = align(o + static_cast<int64_t>(p.bmeta.size() * sizeof(TaskMeta)));
+  p.off_fsync = o; o = align(o + 4 * static_cast<int64_t>(p.ftask.size() + 1));
+  p.off_bsync = o; o = align(o + 4 * static_cast<int64_t>(p.btask.size() + 1));
   p.blob_bytes = std::max<int64_t>(o, 256);
   // instance pointers inside wgrad/bias tasks were relative to the instance table
   for (auto& t : p.wtasks)
@@ -804,6 +932,24 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   p.stats[9] = conv_flops(p.fconv, p.flaunch, LK_CONV1);
   p.stats[10] = conv_flops(p.bconv, p.blaunch, LK_CONV0);
   p.stats[11] = conv_flops(p.bconv, p.blaunch, LK_CONV1);
+  if (p.persistent) {
+    auto task_flops = [&](const std::vector<TaskRec>& ts, const std::vector<TaskMeta>& ms) {
+      int64_t f = 0;
+      for (size_t i = 0; i < ts.size(); ++i)
+        if (ms[i].type == TASK_CONV) {
+          const ConvTask& t = *reinterpret_cast<const ConvTask*>(ts[i].b);
+          const ConvCfg& c = p.cfgs[t.cfg];
+          const int nmt = c.P_in == 484 ? 3 : 2;
+          f += static_cast<int64_t>(t.n_samp) * 2 * 196 * 128 * (16ll * c.n_kb * c.ntaps) * t.n_mt / nmt;
+        }
+      return f;
+    };
+    p.stats[8] = task_flops(p.ftask, p.fmeta);
+    p.stats[10] = task_flops(p.btask, p.bmeta);
+    p.stats[3] = 1; p.stats[4] = 3;
+    p.stats[6] = static_cast<int64_t>(p.ftask.size());
+    p.stats[14] = static_cast<int64_t>(p.btask.size());
+  }
   for (const WgradTask& t : p.wtasks) p.stats[12] += static_cast<int64_t>(t.n_inst) * 2 * 196 * 128 * 128 * t.ntaps_x;
   p.stats[13] = static_cast<int64_t>(p.felt.size() + p.belt.size());
   return plan;
@@ -884,15 +1030,6 @@ void resolve_elt(EltTask& t, const uint64_t* base) {
   resolve(t.idx, base); resolve(t.scale, base);
 }
 
-int conv_impl_simt() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = std::getenv("PNMN_CONV_IMPL");
-    v = (e && std::string(e) == "simt") ? 1 : 0;
-  }
-  return v;
-}
-
 __global__ void fill_ones_map_kernel(float* map) {
   const int i = threadIdx.x;
   if (i < 256) map[i] = ((i >> 4) < kHW && (i & 15) < kHW) ? 1.f : 0.f;
@@ -902,14 +1039,13 @@ int run_launches(const pnmn_plan& p, const std::vector<LaunchItem>& ls, const ui
   const ConvCfg* cfgs = reinterpret_cast<const ConvCfg*>(blob + p.off_cfg);
   const ConvTask* conv = reinterpret_cast<const ConvTask*>(blob + (bwd ? p.off_bconv : p.off_fconv));
   const EltTask* elt = reinterpret_cast<const EltTask*>(blob + (bwd ? p.off_belt : p.off_felt));
-  const int simt = conv_impl_simt();
   for (const LaunchItem& l : ls) {
     ProfScope prof(l.kind, st);  // LaunchKind values coincide with ProfKind 0..4
     switch (l.kind) {
       case LK_ELT: CUDA_OK(launch_elt(elt + l.off, l.count, st)); break;
-      case LK_CONV0: CUDA_OK(launch_conv(conv + l.off, l.count, cfgs, 0, simt, st)); break;
-      case LK_CONV1: CUDA_OK(launch_conv(conv + l.off, l.count, cfgs, 1, simt, st)); break;
-      case LK_WGRAD: CUDA_OK(launch_wgrad(reinterpret_cast<const WgradTask*>(blob + p.off_wt), l.count, simt, st)); break;
+      case LK_CONV0:
+      case LK_CONV1: CUDA_OK(launch_conv_simt(conv + l.off, l.count, cfgs, st)); break;
+      case LK_WGRAD: CUDA_OK(launch_wgrad(reinterpret_cast<const WgradTask*>(blob + p.off_wt), l.count, p.persistent ? 0 : 1, st)); break;
       case LK_BIAS: CUDA_OK(launch_bias_grad(blob + p.off_bt, l.count, kBiasSplit, st)); break;
       default: break;
     }
@@ -921,6 +1057,7 @@ int run_launches(const pnmn_plan& p, const std::vector<LaunchItem>& ls, const ui
 
 extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const float* features, float* final_out,
                                 void* stream) {
+  HostTimer timer(1);
   pnmn_plan& p = *pp;
   const pnmn_model& m = *p.m;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -928,13 +1065,20 @@ extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const f
   fill_bases(base, bufs, final_out, nullptr);
   // resolve + upload the forward part of the blob (cfgs, conv tasks, elt tasks, pack tasks)
   const int64_t fwd_bytes = p.off_bconv;
-  p.host_blob.assign(static_cast<size_t>(p.blob_bytes), 0);
+  if (p.host_blob.size() < static_cast<size_t>(p.blob_bytes)) p.host_blob.resize(static_cast<size_t>(p.blob_bytes));
   std::memcpy(p.host_blob.data() + p.off_cfg, p.cfgs.data(), p.cfgs.size() * sizeof(ConvCfg));
   {
     ConvTask* d = reinterpret_cast<ConvTask*>(p.host_blob.data() + p.off_fconv);
     for (size_t i = 0; i < p.fconv.size(); ++i) { d[i] = p.fconv[i]; resolve_conv(d[i], base); }
     EltTask* e = reinterpret_cast<EltTask*>(p.host_blob.data() + p.off_felt);
     for (size_t i = 0; i < p.felt.size(); ++i) { e[i] = p.felt[i]; resolve_elt(e[i], base); }
+    TaskRec* ft = reinterpret_cast<TaskRec*>(p.host_blob.data() + p.off_ftask);
+    for (size_t i = 0; i < p.ftask.size(); ++i) {
+      ft[i] = p.ftask[i];
+      if (p.fmeta[i].type == TASK_CONV) resolve_conv(*reinterpret_cast<ConvTask*>(ft[i].b), base);
+      else resolve_elt(*reinterpret_cast<EltTask*>(ft[i].b), base);
+    }
+    if (!p.fmeta.empty()) std::memcpy(p.host_blob.data() + p.off_fmeta, p.fmeta.data(), p.fmeta.size() * sizeof(TaskMeta));
     int64_t* x = reinterpret_cast<int64_t*>(p.host_blob.data() + p.off_xin);
     const int64_t ain_unit = static_cast<int64_t>(m.in_ch / 4) * 256 * 16 * 3 / 2;
     for (int n = 0; n < p.B; ++n) x[n] = p.xin_unit[n] < 0 ? -1 : (kGuard + p.xin_unit[n] * ain_unit) / 4;
@@ -955,13 +1099,26 @@ extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const f
   }
   fill_ones_map_kernel<<<1, 256, 0, st>>>(bufs->maps);
   // features -> planes for every valid sample
-  ProfScope prof_layout(PK_LAYOUT, st);
-  CUDA_OK(launch_nchw_to_planes(features, bufs->ain, p.B, m.in_ch,
-                                reinterpret_cast<const int64_t*>(static_cast<const uint8_t*>(bufs->blob) + p.off_xin), st));
+  {
+    ProfScope prof_layout(PK_LAYOUT, st);
+    CUDA_OK(launch_nchw_to_planes(features, bufs->ain, p.B, m.in_ch,
+                                  reinterpret_cast<const int64_t*>(static_cast<const uint8_t*>(bufs->blob) + p.off_xin), st));
+  }
+  if (p.persistent) {
+    uint8_t* blob = static_cast<uint8_t*>(bufs->blob);
+    CUDA_OK(cudaMemsetAsync(blob + p.off_fsync, 0, 4 * (p.ftask.size() + 1), st));
+    ProfScope prof(PK_CONV0, st);
+    CUDA_OK(launch_exec(blob + p.off_ftask, reinterpret_cast<const TaskMeta*>(blob + p.off_fmeta),
+                        static_cast<int>(p.ftask.size()), reinterpret_cast<const ConvCfg*>(blob + p.off_cfg),
+                        reinterpret_cast<int*>(blob + p.off_fsync), reinterpret_cast<int*>(blob + p.off_fsync) + 1,
+                        (g_trace && static_cast<int64_t>(p.ftask.size()) <= g_trace_cap) ? g_trace : nullptr, st));
+    return 0;
+  }
   return run_launches(p, p.flaunch, static_cast<const uint8_t*>(bufs->blob), false, st);
 }
 
 extern "C" int pnmn_nmn_backward(pnmn_plan* pp, const pnmn_buffers* bufs, const float* grad_final_out, void* stream) {
+  HostTimer timer(2);
   pnmn_plan& p = *pp;
   if (!p.need_grad) return fail("plan was created with need_grad = 0");
   if (!bufs->grads) return fail("grads buffer is NULL");
@@ -973,6 +1130,13 @@ extern "C" int pnmn_nmn_backward(pnmn_plan* pp, const pnmn_buffers* bufs, const 
     for (size_t i = 0; i < p.bconv.size(); ++i) { d[i] = p.bconv[i]; resolve_conv(d[i], base); }
     EltTask* e = reinterpret_cast<EltTask*>(p.host_blob.data() + p.off_belt);
     for (size_t i = 0; i < p.belt.size(); ++i) { e[i] = p.belt[i]; resolve_elt(e[i], base); }
+    TaskRec* bt2 = reinterpret_cast<TaskRec*>(p.host_blob.data() + p.off_btask);
+    for (size_t i = 0; i < p.btask.size(); ++i) {
+      bt2[i] = p.btask[i];
+      if (p.bmeta[i].type == TASK_CONV) resolve_conv(*reinterpret_cast<ConvTask*>(bt2[i].b), base);
+      else resolve_elt(*reinterpret_cast<EltTask*>(bt2[i].b), base);
+    }
+    if (!p.bmeta.empty()) std::memcpy(p.host_blob.data() + p.off_bmeta, p.bmeta.data(), p.bmeta.size() * sizeof(TaskMeta));
     WgradInst* wi = reinterpret_cast<WgradInst*>(p.host_blob.data() + p.off_inst);
     for (size_t i = 0; i < p.insts.size(); ++i) { wi[i] = p.insts[i]; resolve(wi[i].dz, base); resolve(wi[i].x, base); }
     WgradTask* wt = reinterpret_cast<WgradTask*>(p.host_blob.data() + p.off_wt);
@@ -984,7 +1148,32 @@ extern "C" int pnmn_nmn_backward(pnmn_plan* pp, const pnmn_buffers* bufs, const 
                           static_cast<size_t>(p.blob_bytes - p.off_bconv), cudaMemcpyHostToDevice, st));
   CUDA_OK(cudaMemsetAsync(bufs->dmaps, 0, static_cast<size_t>(p.nmaps) * 1024, st));
   CUDA_OK(launch_loss_scale(grad_final_out, static_cast<size_t>(p.B) * 128 * 196, bufs->scratch, st));
+  if (p.persistent) {
+    uint8_t* blob = static_cast<uint8_t*>(bufs->blob);
+    CUDA_OK(cudaMemsetAsync(blob + p.off_bsync, 0, 4 * (p.btask.size() + 1), st));
+    {
+      ProfScope prof(PK_CONV0, st);
+      CUDA_OK(launch_exec(blob + p.off_btask, reinterpret_cast<const TaskMeta*>(blob + p.off_bmeta),
+                          static_cast<int>(p.btask.size()), reinterpret_cast<const ConvCfg*>(blob + p.off_cfg),
+                          reinterpret_cast<int*>(blob + p.off_bsync), reinterpret_cast<int*>(blob + p.off_bsync) + 1,
+                          (g_trace && static_cast<int64_t>(p.ftask.size() + p.btask.size()) <= g_trace_cap)
+                              ? g_trace + 16 * p.ftask.size() : nullptr, st));
+    }
+  }
   return run_launches(p, p.blaunch, static_cast<const uint8_t*>(bufs->blob), true, st);
+}
+
+// per-task timestamps of the persistent executor: 8 int64 per task, forward tasks first, then backward
+extern "C" int pnmn_debug_set_trace(void* device_buffer, int64_t capacity_tasks) {
+  g_trace = static_cast<long long*>(device_buffer);
+  g_trace_cap = capacity_tasks;
+  return 0;
+}
+
+// accumulated host-side milliseconds: {plan_create, forward, backward, #plans}; reading clears
+extern "C" int pnmn_debug_host_times(double* ms) {
+  for (int i = 0; i < 4; ++i) { ms[i] = g_host_ms[i]; g_host_ms[i] = 0; }
+  return 0;
 }
 
 extern "C" int pnmn_profile_enable(int on) {
@@ -1017,11 +1206,26 @@ int upload(const void* host, size_t n, T** dev) {
 
 extern "C" int pnmn_debug_launch_conv(const void* tasks_host, int n_tasks, const void* cfgs_host, int n_cfgs,
                                       int variant, int impl_simt, void* stream) {
+  (void)variant;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
   ConvTask* dt = nullptr; ConvCfg* dc = nullptr;
   if (upload(tasks_host, n_tasks, &dt)) return 1;
   if (upload(cfgs_host, n_cfgs, &dc)) return 1;
-  CUDA_OK(launch_conv(dt, n_tasks, dc, variant, impl_simt, static_cast<cudaStream_t>(stream)));
-  CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
+  if (impl_simt) {
+    CUDA_OK(launch_conv_simt(dt, n_tasks, dc, st));
+  } else {
+    // run the tasks through the persistent executor kernel without dependencies
+    std::vector<TaskMeta> metas(n_tasks);
+    for (auto& mm : metas) { mm.type = TASK_CONV; mm.n_deps = 0; for (int k = 0; k < kMaxDeps; ++k) mm.deps[k] = -1; }
+    TaskMeta* dm = nullptr; int* sync = nullptr;
+    if (upload(metas.data(), metas.size(), &dm)) return 1;
+    CUDA_OK(cudaMalloc(&sync, 4 * (n_tasks + 1)));
+    CUDA_OK(cudaMemsetAsync(sync, 0, 4 * (n_tasks + 1), st));
+    CUDA_OK(launch_exec(reinterpret_cast<const uint8_t*>(dt), dm, n_tasks, dc, sync, sync + 1, nullptr, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    cudaFree(dm); cudaFree(sync);
+  }
+  CUDA_OK(cudaStreamSynchronize(st));
   cudaFree(dt); cudaFree(dc);
   return 0;
 }
@@ -1040,7 +1244,7 @@ extern "C" int pnmn_debug_launch_wgrad(const void* tasks_host, int n_tasks, cons
   return 0;
 }
 extern "C" int pnmn_debug_pack(const void* pack_tasks_host, int n_tasks, int total_tiles, const float* params,
-                               float* packed, void* stream) {
+                               void* packed, void* stream) {
   PackTask* dt = nullptr;
   if (upload(pack_tasks_host, n_tasks, &dt)) return 1;
   CUDA_OK(launch_pack(dt, n_tasks, total_tiles, params, packed, static_cast<cudaStream_t>(stream)));

@@ -96,22 +96,29 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
   } else if (warp == 2) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_f16(128, 128, 1, 1);
+      // MN-major, no swizzle: LBO = next 8-slot K group (128 B), SBO = next half plane.  Descriptor updates
+      // are one 32-bit add on the start-address field (16-byte units = slots).
+      const uint32_t a_hi = static_cast<uint32_t>(make_smem_desc(0, 0, kWgChunk * 16u) >> 32);
+      const uint32_t b_hi = static_cast<uint32_t>(make_smem_desc(0, 0, static_cast<uint32_t>(xs) * 16u) >> 32);
+      const uint32_t lbo = (128u >> 4) << 16;
+      const uint32_t ring_lo = smem_u32(ring) >> 4;
       for (int it = 0; it < total; ++it) {
         const int st = it % kWgStages;
         mbar_wait(smem_u32(&hdr->full[st]), (it / kWgStages) & 1);
         tc_fence_after();
-        const uint32_t sdz = smem_u32(ring + st * kWgStageBytes);
-        const uint32_t sx = sdz + dz_bytes;
+        const uint32_t a_lo0 = ring_lo + st * (kWgStageBytes >> 4) + lbo;
+        const uint32_t b_lo0 = a_lo0 + (dz_bytes >> 4);
         const int c0 = (it % n_chunks) * kWgChunk;
         int nk = (n_valid - c0 + 15) / 16;  // 16-slot MMA steps that can still see a non-zero dZ
         nk = nk > kWgChunk / 16 ? kWgChunk / 16 : nk;
         for (int tx = 0; tx < t.ntaps_x; ++tx) {
-          for (int k16 = 0; k16 < nk; ++k16) {
-            // MN-major, no swizzle: LBO = next 8-slot K group (128 B), SBO = next half plane
-            const uint64_t ad = make_smem_desc(sdz + k16 * 256u, 128u, kWgChunk * 16u);
-            const uint64_t bd = make_smem_desc(sx + (k16 * 16u + static_cast<uint32_t>(halo * tx)) * 16u, 128u,
-                                               static_cast<uint32_t>(xs) * 16u);
-            umma_f16(tmem_base + tx * 128, ad, bd, idesc, (it | k16) != 0);
+          const uint32_t b_lo = b_lo0 + static_cast<uint32_t>(halo * tx);
+          const uint32_t d = tmem_base + tx * 128;
+#pragma unroll
+          for (int k16 = 0; k16 < kWgChunk / 16; ++k16) {
+            if (k16 < nk)
+              umma_f16(d, (static_cast<uint64_t>(a_hi) << 32) | (a_lo0 + k16 * 16),
+                       (static_cast<uint64_t>(b_hi) << 32) | (b_lo + k16 * 16), idesc, (it | k16) != 0);
           }
         }
         umma_commit(smem_u32(&hdr->empty[st]));

@@ -343,7 +343,10 @@ class NeuralModuleNetwork(nn.Module):
         self._ensure_flat()
         features = features.contiguous().float()
         B, Lp = programs.shape
-        programs_host = programs.detach().to("cpu", torch.int64).contiguous()  # the single D2H of the forward
+        # The program compiler runs on the host: programs that are already host tensors cost no synchronisation
+        # (the reference accepts them too, it calls ``programs[n].cpu()``, nmn.py:203); device tensors cost the
+        # forward's single D2H copy.
+        programs_host = programs.detach().to("cpu", torch.int64).contiguous()
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for _, p in self._exec_named_parameters())
         plan = lib.pnmn_plan_create(self._model_handle, ctypes.cast(programs_host.data_ptr(), ctypes.POINTER(ctypes.c_int64)),
                                     B, Lp, 1 if need_grad else 0)
