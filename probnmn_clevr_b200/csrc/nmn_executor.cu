@@ -60,7 +60,7 @@ constexpr int64_t kUnit22 = 48ll * 484 * 16;
 constexpr int kInstChunk = 16;     // instances per wgrad CTA
 constexpr int kNumSMs = 148;
 constexpr int kEltParts = 4;
-constexpr int kBiasSplit = 8;
+constexpr int kBiasSplit = 32;
 
 struct ConvW {
   int64_t w_off = -1, b_off = -1;  // floats into the flat parameter buffer

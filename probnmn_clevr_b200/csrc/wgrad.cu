@@ -188,15 +188,40 @@ struct BiasGradTask {
   const float* scale;
 };
 __global__ void __launch_bounds__(128) bias_grad_kernel(const BiasGradTask* __restrict__ tasks) {
+  // thread = (half plane hp = tid/8, slot lane = tid%8): 16-byte loads, 8 adjacent threads read 128 contiguous bytes
   const BiasGradTask t = tasks[blockIdx.x];
-  const int n = threadIdx.x;  // output channel
+  const int hp = threadIdx.x >> 3, sl = threadIdx.x & 7;
   const int i0 = blockIdx.y, di = gridDim.y;
-  float acc = 0.f;
+  if (i0 >= t.n_inst) return;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int i = i0; i < t.n_inst; i += di) {
-    const __half* dz = static_cast<const __half*>(t.inst[i].dz) + static_cast<size_t>(n / 8) * t.P * 8 + (n % 8);
-    for (int p = 0; p < t.P; ++p) acc += __half2float(dz[p * 8]);
+    const uint4* dz = reinterpret_cast<const uint4*>(t.inst[i].dz) + static_cast<size_t>(hp) * t.P;
+    for (int p = sl; p < t.P; p += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = (p + 8 * u < t.P) ? dz[p + 8 * u] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const __half2* h = reinterpret_cast<const __half2*>(&v[u]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __half22float2(h[e]);
+          acc[2 * e] += f.x; acc[2 * e + 1] += f.y;
+        }
+      }
+    }
   }
-  if (t.n_inst > i0) atomicAdd(t.db + n, acc * (t.scale ? t.scale[1] : 1.f));
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 1);
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 2);
+    acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 4);
+  }
+  if (sl == 0) {
+    const float unscale = t.scale ? t.scale[1] : 1.f;
+#pragma unroll
+    for (int e = 0; e < 8; ++e) atomicAdd(t.db + hp * 8 + e, acc[e] * unscale);
+  }
 }
 
 cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, cudaStream_t stream) {
