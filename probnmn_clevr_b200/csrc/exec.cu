@@ -15,6 +15,7 @@
 // 4-11 (two per TMEM lane quarter, each taking half of the 128 columns) run the fused epilogue.
 // TMEM, barriers and ring phases persist across tasks.
 #include <cuda_fp16.h>
+#include <type_traits>
 
 #include "elt_body.cuh"
 #include "executor.h"
@@ -240,38 +241,62 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
               }
           uint32_t ua = __shfl_sync(0xffffffffu, na, 0), uw = __shfl_sync(0xffffffffu, nw, 0);
           long long wait_a = 0, wait_w = 0;
-          for (int kb = 0; kb < n_kb; ++kb, ++ua) {
-            const int sa = ua % kExAStages;
-            long long c0 = trace ? clock64() : 0;
-            mbar_wait(smem_u32(&hdr->full_a[sa]), (ua / kExAStages) & 1);
-            if (trace) wait_a += clock64() - c0;
-            const uint32_t a_lo_kb = a_lo0 + sa * (kExAStage >> 4);
-            for (int ty = 0; ty < rows_w; ++ty, ++uw) {
-              const int sw = uw % kExWStages;
-              c0 = trace ? clock64() : 0;
-              mbar_wait(smem_u32(&hdr->full_w[sw]), (uw / kExWStages) & 1);
-              if (trace) wait_w += clock64() - c0;
-              tc_fence_after();
-              if (trace && lane == 0 && kb == 0 && ty == 0) trace[idx * 16 + 9] = gtime();
-              const uint32_t b_lo_row = b_lo0 + sw * (kExWStage >> 4);
-              const uint32_t a_lo_row = a_lo_kb + static_cast<uint32_t>((ty - (rows_w >> 1)) * row_shift - col_shift);
-              if (elect_one()) {
+          const bool tr = trace != nullptr;
+          const uint32_t bar_fa = smem_u32(&hdr->full_a[0]), bar_ea = smem_u32(&hdr->empty_a[0]);
+          const uint32_t bar_fw = smem_u32(&hdr->full_w[0]), bar_ew = smem_u32(&hdr->empty_w[0]);
+          const uint32_t d_hi32 = static_cast<uint32_t>(d_hi >> 32);
+          const int ty0 = rows_w >> 1;
+          // The loop nest is instantiated per (taps per stage, accumulators): inside a stage every descriptor is
+          // one add away from a value computed BEFORE the barrier wait, so the single issuing lane spends a few
+          // instructions per MMA instead of re-deriving the addresses (the MMA pipe retires one 128x128x16 MMA
+          // per 64 cycles; the previous generic loop needed ~130 cycles of issue work per MMA).
+          auto run = [&](auto tps_c, auto nacc_c) {
+            constexpr int TPS = decltype(tps_c)::value;
+            constexpr int NACC = decltype(nacc_c)::value;
+            for (int kb = 0; kb < n_kb; ++kb, ++ua) {
+              const int sa = ua % kExAStages;
+              long long c0 = tr ? clock64() : 0;
+              mbar_wait(bar_fa + sa * 8, (ua / kExAStages) & 1);
+              if (tr) wait_a += clock64() - c0;
+              const uint32_t a_lo_kb = a_lo0 + sa * (kExAStage >> 4);
+              for (int ty = 0; ty < rows_w; ++ty, ++uw) {
+                const int sw = uw % kExWStages;
+                const uint32_t b_lo_row = b_lo0 + sw * (kExWStage >> 4);
+                const uint32_t a_lo_row = a_lo_kb + static_cast<uint32_t>((ty - ty0) * row_shift - col_shift);
+                uint32_t al[TPS][NACC], bl[TPS];
 #pragma unroll
-                for (int tx = 0; tx < 3; ++tx) {
-                  if (tx < tps) {
-                    const uint32_t a_lo_tap = a_lo_row + static_cast<uint32_t>(tx * col_shift);
-                    const uint64_t bd = d_hi | (b_lo_row + tx * (kExWTile >> 4));
-                    const uint32_t acc = (kb | ty | tx) == 0 ? 0u : 1u;
+                for (int tx = 0; tx < TPS; ++tx) {
+                  bl[tx] = b_lo_row + tx * (kExWTile >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                      if (k < n_acc) umma_f16(doff[k], d_hi | (a_lo_tap + aoff[k]), bd, idesc, acc);
-                  }
+                  for (int k = 0; k < NACC; ++k) al[tx][k] = a_lo_row + static_cast<uint32_t>(tx * col_shift) + aoff[k];
                 }
-                umma_commit(smem_u32(&hdr->empty_w[sw]));
-                if (ty == rows_w - 1) umma_commit(smem_u32(&hdr->empty_a[sa]));
+                const uint32_t acc0 = (kb | ty) == 0 ? 0u : 1u;
+                c0 = tr ? clock64() : 0;
+                mbar_wait(bar_fw + sw * 8, (uw / kExWStages) & 1);
+                if (tr) wait_w += clock64() - c0;
+                tc_fence_after();
+                if (tr && lane == 0 && kb == 0 && ty == 0) trace[idx * 16 + 9] = gtime();
+                if (elect_one()) {
+#pragma unroll
+                  for (int tx = 0; tx < TPS; ++tx)
+#pragma unroll
+                    for (int k = 0; k < NACC; ++k)
+                      umma_f16_2x32(doff[k], al[tx][k], d_hi32, bl[tx], d_hi32, idesc, tx == 0 ? acc0 : 1u);
+                  umma_commit(bar_ew + sw * 8);
+                  if (ty == rows_w - 1) umma_commit(bar_ea + sa * 8);
+                }
+                __syncwarp();
               }
-              __syncwarp();
             }
+          };
+          using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
+          using I3 = std::integral_constant<int, 3>; using I4 = std::integral_constant<int, 4>;
+          if (tps == 3) {
+            if (n_acc == 1) run(I3{}, I1{}); else if (n_acc == 2) run(I3{}, I2{});
+            else if (n_acc == 3) run(I3{}, I3{}); else run(I3{}, I4{});
+          } else {
+            if (n_acc == 1) run(I1{}, I1{}); else if (n_acc == 2) run(I1{}, I2{});
+            else if (n_acc == 3) run(I1{}, I3{}); else run(I1{}, I4{});
           }
           if (elect_one()) umma_commit(smem_u32(&hdr->tmem_full));
           __syncwarp();

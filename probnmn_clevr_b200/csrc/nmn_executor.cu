@@ -12,6 +12,8 @@
 #include <chrono>
 #include <array>
 #include <cstdio>
+#include <cstdlib>
+#include <cstddef>
 #include <cstring>
 #include <map>
 #include <string>
@@ -242,7 +244,8 @@ struct Sched {
     const int U = static_cast<int>(v.size());
     const int nmt = kind == LK_CONV0 ? 2 : 3;
     const int cap = (kind == LK_CONV0 && U > kNumSMs) ? NSMAX : 1;
-    const int split = (U * nmt <= kNumSMs + kNumSMs / 2) ? nmt : 1;
+    static const bool no_split = std::getenv("PNMN_NOSPLIT") != nullptr;  // diagnostics
+    const int split = (!no_split && U * nmt <= kNumSMs + kNumSMs / 2) ? nmt : 1;
     size_t i = 0;
     while (i < v.size()) {
       ConvTask t = protos[v[i]].t;
@@ -300,9 +303,10 @@ struct Sched {
       m.type = type; m.n_deps = 0;
       for (int k = 0; k < kMaxDeps; ++k) m.deps[k] = -1;
       const int id = static_cast<int>(out.size()) - 1;
+      static const bool no_deps = std::getenv("PNMN_NODEPS") != nullptr;  // diagnostics: throughput without dependencies (results are garbage)
       for (int k = 0; k < ns; ++k) {
         const Latest& l = latest[samples[k]];
-        for (int j = 0; j < l.n; ++j) {
+        for (int j = 0; j < (no_deps ? 0 : l.n); ++j) {
           if (m.n_deps < kMaxDeps) m.deps[m.n_deps++] = l.ids[j];
           else dep_overflow = true;
         }
@@ -351,7 +355,8 @@ struct pnmn_plan {
   int64_t off_cfg = 0, off_xin = 0, off_fconv = 0, off_felt = 0, off_bconv = 0, off_belt = 0, off_inst = 0, off_wt = 0,
           off_bt = 0, blob_bytes = 0;
   int64_t stats[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-  std::vector<uint8_t> host_blob;
+  std::vector<uint8_t> host_blob;   // level-by-level path only (resolved on the host)
+  struct PinnedBlob* pin = nullptr;  // persistent path: unresolved records, resolved on the device after upload
 };
 
 namespace {
@@ -414,6 +419,86 @@ struct Builder {
     return static_cast<int>(vals.size()) - 1;
   }
 };
+
+// ---- pinned staging buffers for the task tables --------------------------------------------------
+// A plan's records are written ONCE (with symbolic pointers) into page-locked memory by pnmn_plan_create,
+// uploaded with one truly asynchronous copy and resolved to device addresses by resolve_kernel; the host
+// never walks the records again.  Buffers are recycled; the event says when the last upload has been read.
+}  // namespace
+struct PinnedBlob {
+  uint8_t* p = nullptr;
+  size_t cap = 0;
+  bool pinned = false, pending = false;
+  cudaEvent_t ev = nullptr;
+};
+namespace {
+std::vector<PinnedBlob*> g_pin_free;
+int g_pin_total = 0;
+PinnedBlob* pin_acquire(size_t bytes) {
+  PinnedBlob* best = nullptr;
+  // prefer a buffer whose last upload has already been consumed by the GPU (the host may run ahead of the device)
+  for (int pass = 0; pass < 2 && !best; ++pass) {
+    if (pass == 1 && g_pin_total < 8) break;  // everything is in flight: grow the pool instead of stalling
+    for (size_t i = 0; i < g_pin_free.size(); ++i) {
+      PinnedBlob* c = g_pin_free[i];
+      if (c->cap < bytes) continue;
+      if (pass == 0 && c->pending && cudaEventQuery(c->ev) != cudaSuccess) continue;
+      best = c; g_pin_free.erase(g_pin_free.begin() + i); break;
+    }
+  }
+  cudaGetLastError();  // cudaEventQuery's cudaErrorNotReady is not an error
+  if (!best) {
+    best = new PinnedBlob();
+    best->cap = bytes + bytes / 2 + 4096;
+    void* q = nullptr;
+    if (cudaHostAlloc(&q, best->cap, cudaHostAllocDefault) == cudaSuccess) {
+      best->p = static_cast<uint8_t*>(q); best->pinned = true;
+      cudaEventCreateWithFlags(&best->ev, cudaEventDisableTiming);
+      ++g_pin_total;
+    } else {
+      cudaGetLastError();  // no device (CPU-only validity checks): plain memory, never uploaded
+      best->p = static_cast<uint8_t*>(std::malloc(best->cap));
+    }
+  }
+  if (best->pending) { cudaEventSynchronize(best->ev); best->pending = false; }
+  return best;
+}
+void pin_release(PinnedBlob* b) { if (b) g_pin_free.push_back(b); }
+
+struct BaseTable { uint64_t b[AR_COUNT]; };
+// one thread per 8-byte word of a record array; `mask` marks the words that hold (symbolic) pointers.
+// type_off >= 0: per-record int at blob[type_off + rec*type_stride] selects mask (0) or mask_alt (!= 0).
+__global__ void resolve_kernel(uint8_t* blob, int64_t off, int n_rec, int words, uint32_t mask, uint32_t mask_alt,
+                               int64_t type_off, int type_stride, BaseTable bases) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t rec = i / words;
+  const int w = static_cast<int>(i % words);
+  if (rec >= n_rec) return;
+  uint32_t m = mask;
+  if (type_off >= 0 && *reinterpret_cast<const int*>(blob + type_off + rec * type_stride) != 0) m = mask_alt;
+  if (!((m >> w) & 1u)) return;
+  uint64_t* p = reinterpret_cast<uint64_t*>(blob + off) + rec * words + w;
+  const uint64_t v = *p;
+  if (v >> 56) *p = bases.b[v >> 56] + (v & ((1ull << 56) - 1));
+}
+constexpr uint32_t kMaskConv = 0x3FFFu;        // ConvTask: 14 pointers in words 0..13
+constexpr uint32_t kMaskElt = 0xFFEu;          // EltTask: 11 pointers in words 1..11
+constexpr uint32_t kMaskInst = 0x3u;           // WgradInst: dz, x
+constexpr uint32_t kMaskWgrad = 0xC1u;         // WgradTask: inst (word 0), dw (6), scale (7)
+constexpr uint32_t kMaskBias = 0xDu;           // BiasGradTaskH: inst (0), db (2), scale (3)
+static_assert(sizeof(WgradTask) == 64 && sizeof(BiasGradTaskH) == 32 && sizeof(WgradInst) == 16, "record sizes");
+static_assert(offsetof(ConvTask, cfg) == 112 && offsetof(EltTask, a) == 8 && offsetof(EltTask, scale) == 88, "pointer words");
+static_assert(offsetof(WgradTask, dw) == 48 && offsetof(BiasGradTaskH, db) == 16, "pointer words");
+
+cudaError_t launch_resolve(uint8_t* blob, int64_t off, size_t n_rec, int rec_bytes, uint32_t mask, uint32_t mask_alt,
+                           int64_t type_off, int type_stride, const BaseTable& bt, cudaStream_t st) {
+  if (n_rec == 0) return cudaSuccess;
+  const int words = rec_bytes / 8;
+  const int64_t total = static_cast<int64_t>(n_rec) * words;
+  resolve_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(blob, off, static_cast<int>(n_rec), words, mask,
+                                                                              mask_alt, type_off, type_stride, bt);
+  return cudaGetLastError();
+}
 
 static const int kRelateDil[5] = {1, 2, 4, 8, 1};
 
@@ -909,6 +994,24 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   for (auto& t : p.btasks)
     t.inst = reinterpret_cast<const WgradInst*>(reinterpret_cast<uint64_t>(t.inst) + static_cast<uint64_t>(p.off_inst));
 
+  if (p.persistent) {
+    p.pin = pin_acquire(static_cast<size_t>(p.blob_bytes));
+    uint8_t* hb = p.pin->p;
+    auto put = [&](int64_t off, const void* src, size_t bytes) { if (bytes) std::memcpy(hb + off, src, bytes); };
+    put(p.off_cfg, p.cfgs.data(), p.cfgs.size() * sizeof(ConvCfg));
+    put(p.off_ftask, p.ftask.data(), p.ftask.size() * sizeof(TaskRec));
+    put(p.off_fmeta, p.fmeta.data(), p.fmeta.size() * sizeof(TaskMeta));
+    put(p.off_btask, p.btask.data(), p.btask.size() * sizeof(TaskRec));
+    put(p.off_bmeta, p.bmeta.data(), p.bmeta.size() * sizeof(TaskMeta));
+    put(p.off_inst, p.insts.data(), p.insts.size() * sizeof(WgradInst));
+    put(p.off_wt, p.wtasks.data(), p.wtasks.size() * sizeof(WgradTask));
+    put(p.off_bt, p.btasks.data(), p.btasks.size() * sizeof(BiasGradTaskH));
+    int64_t* x = reinterpret_cast<int64_t*>(hb + p.off_xin);
+    const int64_t ain_unit = static_cast<int64_t>(m->in_ch / 4) * 256 * 16 * 3 / 2;
+    for (int n = 0; n < B; ++n) x[n] = p.xin_unit[n] < 0 ? -1 : (kGuard + p.xin_unit[n] * ain_unit) / 4;
+    // the dependency flags + task counters live at the tail of the blob: they are uploaded as zeros
+    std::memset(hb + p.off_fsync, 0, static_cast<size_t>(p.blob_bytes - p.off_fsync));
+  }
   p.stats[1] = n_conv3;
   p.stats[2] = n_tokens;
   p.stats[3] = static_cast<int64_t>(p.flaunch.size());
@@ -955,7 +1058,10 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   return plan;
 }
 
-extern "C" void pnmn_plan_destroy(pnmn_plan* p) { delete p; }
+extern "C" void pnmn_plan_destroy(pnmn_plan* p) {
+  if (p) pin_release(p->pin);
+  delete p;
+}
 
 extern "C" int pnmn_plan_valid(const pnmn_plan* p, uint8_t* valid) {
   std::memcpy(valid, p->valid.data(), p->valid.size());
@@ -1063,6 +1169,17 @@ extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const f
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint64_t base[AR_COUNT];
   fill_bases(base, bufs, final_out, nullptr);
+  if (p.persistent) {
+    // one asynchronous upload of the whole (unresolved) blob, forward + backward records and zeroed flags
+    if (!p.pin || !p.pin->pinned) return fail("plan has no page-locked task table (created without a CUDA device?)");
+    CUDA_OK(cudaMemcpyAsync(bufs->blob, p.pin->p, static_cast<size_t>(p.blob_bytes), cudaMemcpyHostToDevice, st));
+    CUDA_OK(cudaEventRecord(p.pin->ev, st));
+    p.pin->pending = true;
+    BaseTable bt;
+    std::memcpy(bt.b, base, sizeof(bt.b));
+    CUDA_OK(launch_resolve(static_cast<uint8_t*>(bufs->blob), p.off_ftask, p.ftask.size(), 128, kMaskConv, kMaskElt,
+                           p.off_fmeta, sizeof(TaskMeta), bt, st));
+  } else {
   // resolve + upload the forward part of the blob (cfgs, conv tasks, elt tasks, pack tasks)
   const int64_t fwd_bytes = p.off_bconv;
   if (p.host_blob.size() < static_cast<size_t>(p.blob_bytes)) p.host_blob.resize(static_cast<size_t>(p.blob_bytes));
@@ -1084,6 +1201,7 @@ extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const f
     for (int n = 0; n < p.B; ++n) x[n] = p.xin_unit[n] < 0 ? -1 : (kGuard + p.xin_unit[n] * ain_unit) / 4;
   }
   CUDA_OK(cudaMemcpyAsync(bufs->blob, p.host_blob.data(), static_cast<size_t>(fwd_bytes), cudaMemcpyHostToDevice, st));
+  }
   // pack weights (tf32, MMA tile order): the packed buffer's head holds the pack-task table
   {
     // pack tasks are static per model; upload them behind the packed floats is not possible (caller
@@ -1106,7 +1224,6 @@ extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const f
   }
   if (p.persistent) {
     uint8_t* blob = static_cast<uint8_t*>(bufs->blob);
-    CUDA_OK(cudaMemsetAsync(blob + p.off_fsync, 0, 4 * (p.ftask.size() + 1), st));
     ProfScope prof(PK_CONV0, st);
     CUDA_OK(launch_exec(blob + p.off_ftask, reinterpret_cast<const TaskMeta*>(blob + p.off_fmeta),
                         static_cast<int>(p.ftask.size()), reinterpret_cast<const ConvCfg*>(blob + p.off_cfg),
@@ -1125,6 +1242,15 @@ extern "C" int pnmn_nmn_backward(pnmn_plan* pp, const pnmn_buffers* bufs, const 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   uint64_t base[AR_COUNT];
   fill_bases(base, bufs, nullptr, grad_final_out);
+  if (p.persistent) {
+    BaseTable bt;
+    std::memcpy(bt.b, base, sizeof(bt.b));
+    uint8_t* blob = static_cast<uint8_t*>(bufs->blob);
+    CUDA_OK(launch_resolve(blob, p.off_btask, p.btask.size(), 128, kMaskConv, kMaskElt, p.off_bmeta, sizeof(TaskMeta), bt, st));
+    CUDA_OK(launch_resolve(blob, p.off_inst, p.insts.size(), sizeof(WgradInst), kMaskInst, kMaskInst, -1, 0, bt, st));
+    CUDA_OK(launch_resolve(blob, p.off_wt, p.wtasks.size(), sizeof(WgradTask), kMaskWgrad, kMaskWgrad, -1, 0, bt, st));
+    CUDA_OK(launch_resolve(blob, p.off_bt, p.btasks.size(), sizeof(BiasGradTaskH), kMaskBias, kMaskBias, -1, 0, bt, st));
+  } else {
   {
     ConvTask* d = reinterpret_cast<ConvTask*>(p.host_blob.data() + p.off_bconv);
     for (size_t i = 0; i < p.bconv.size(); ++i) { d[i] = p.bconv[i]; resolve_conv(d[i], base); }
@@ -1146,11 +1272,11 @@ extern "C" int pnmn_nmn_backward(pnmn_plan* pp, const pnmn_buffers* bufs, const 
   }
   CUDA_OK(cudaMemcpyAsync(static_cast<uint8_t*>(bufs->blob) + p.off_bconv, p.host_blob.data() + p.off_bconv,
                           static_cast<size_t>(p.blob_bytes - p.off_bconv), cudaMemcpyHostToDevice, st));
+  }
   CUDA_OK(cudaMemsetAsync(bufs->dmaps, 0, static_cast<size_t>(p.nmaps) * 1024, st));
   CUDA_OK(launch_loss_scale(grad_final_out, static_cast<size_t>(p.B) * 128 * 196, bufs->scratch, st));
   if (p.persistent) {
     uint8_t* blob = static_cast<uint8_t*>(bufs->blob);
-    CUDA_OK(cudaMemsetAsync(blob + p.off_bsync, 0, 4 * (p.btask.size() + 1), st));
     {
       ProfScope prof(PK_CONV0, st);
       CUDA_OK(launch_exec(blob + p.off_btask, reinterpret_cast<const TaskMeta*>(blob + p.off_bmeta),

@@ -15,6 +15,7 @@ Same constructor, ``from_config``, ``forward(features, programs, answers=None)``
 There is no CPU or eager fallback: without the CUDA library / a CUDA device ``forward`` raises.
 """
 import ctypes
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
@@ -259,6 +260,8 @@ class NeuralModuleNetwork(nn.Module):
         self._packed: Optional[torch.Tensor] = None
         self.last_plan_stats: Optional[List[int]] = None
         self._gflat_box: Dict[str, torch.Tensor] = {}
+        # classifier GEMMs (library calls): "1" = TF32 tensor cores, default = IEEE fp32 like the reference
+        self.classifier_tf32 = os.environ.get("PNMN_CLASSIFIER_TF32", "0") == "1"
 
     @classmethod
     def from_config(cls, config):
@@ -380,7 +383,12 @@ class NeuralModuleNetwork(nn.Module):
             run.close()
 
         # classifier + loss (nmn.py:241-269); masking done on the device instead of CPU-tensor indexing
-        answer_logits = self.classifier(final)
+        if self.classifier_tf32:
+            prev = torch.backends.cuda.matmul.allow_tf32
+            final = _MatmulPrecision.apply(final, True, prev)
+            answer_logits = _MatmulPrecision.apply(self.classifier(final), prev, True)
+        else:
+            answer_logits = self.classifier(final)
         answer_logprobs = F.log_softmax(answer_logits, dim=-1)
         best_logprobs, answer_predictions = torch.max(answer_logprobs, dim=1)
         invalid = (valid_host == 0).to(features.device, non_blocking=True)
@@ -432,3 +440,25 @@ class NeuralModuleNetwork(nn.Module):
 
 class _NullCtx:
     pass
+
+
+class _MatmulPrecision(torch.autograd.Function):
+    """Identity that switches cuBLAS/cuDNN fp32 math between IEEE and TF32 tensor cores.  Two of them bracket
+    the classifier (plain library GEMMs: 1x1 conv, Linear 50176->1024, Linear 1024->28, nmn.py:75-83); autograd
+    replays them in reverse order, so the classifier's backward GEMMs run under the same setting."""
+
+    @staticmethod
+    def forward(ctx, x, on_forward, on_backward):
+        ctx.on_backward = on_backward
+        _MatmulPrecision.set(on_forward)
+        return x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        _MatmulPrecision.set(ctx.on_backward)
+        return g, None, None
+
+    @staticmethod
+    def set(tf32: bool):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
