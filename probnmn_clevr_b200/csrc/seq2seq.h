@@ -1,0 +1,210 @@
+// Internal types of the LSTM seq2seq (ProgramGenerator) path.  Nothing here is part of the C ABI
+// (include/pnmn.h); the entry points live in seq2seq_api.cu.
+//
+// Reference: probnmn/modules/seq2seq_base.py:101-276 on top of AllenNLP 0.9.0 SimpleSeq2Seq
+// (2-layer nn.LSTM encoder, dot-product attention, LSTMCell decoder, Linear projection).
+//
+// "Operand format": every matrix that feeds a tensor-core GEMM (hidden states, attended vectors,
+// gate gradients, weights) is stored as TWO fp16 matrices hi + lo (x ~= hi + lo, 22 mantissa bits)
+// in the unswizzled tcgen05 core-matrix order
+//        buf[row tile][k / 8][row % tile][k % 8]          (tile = 128 rows for activations,
+//                                                           64 rows for packed weights)
+// so that a 64-deep K chunk of one tile is ONE contiguous bulk copy and is at once a K-major
+// operand (8 rows x 16 B core matrices, LBO = tile*16 B, SBO = 128 B) and — read along the rows —
+// an MN-major operand for the weight-gradient GEMMs (LBO = 128 B, SBO = tile*16 B).
+// A GEMM is three MMAs per k-step: hi*hi + lo*hi + hi*lo with fp32 accumulation in TMEM, i.e. fp32-class
+// products on the fp16 tensor pipe: greedy argmax tokens must match the reference's fp32 path bit for bit
+// (BASELINE.json north_star), which a single 11-bit operand cannot deliver.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <cstdint>
+
+namespace pnmn {
+
+constexpr int kSH = 256;        // hidden size == embedding size (configs/*.yml: INPUT_SIZE = HIDDEN_SIZE = 256)
+constexpr int kSG = 4 * kSH;    // gate width
+constexpr int kSMaxV = 128;     // target vocabulary bound of the row kernels (programs: 44, questions: ~93)
+constexpr int kSMaxT = 64;      // source length bound (questions <= 45 tokens + @end@)
+
+// halves offset of element (r, k) of an activation operand with K features (128-row tiles)
+__host__ __device__ inline size_t op_off(int r, int k, int K) {
+  return (static_cast<size_t>(r >> 7) * (K >> 3) + (k >> 3)) * 1024 + static_cast<size_t>(r & 127) * 8 + (k & 7);
+}
+// halves offset of element (n, k) of a packed weight with K features (64-row tiles)
+__host__ __device__ inline size_t wp_off(int n, int k, int K) {
+  return (static_cast<size_t>(n >> 6) * (K >> 3) + (k >> 3)) * 512 + static_cast<size_t>(n & 63) * 8 + (k & 7);
+}
+
+__device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
+  x = fminf(fmaxf(x, -65504.f), 65504.f);
+  hi = __float2half_rn(x);
+  lo = __float2half_rn(x - __half2float(hi));
+}
+
+// ---- tensor-core step GEMM ------------------------------------------------------------------------
+//   acc[b][n] = sum_k A[b][k] * W[n][k]        b: batch rows (128 per CTA), n: 64 per CTA
+// A is the concatenation of up to two operand buffers along K; W is a packed weight.
+enum GemmEpilogue : int { EPI_LSTM = 0, EPI_DGRAD = 1 };
+
+struct GemmArgs {
+  const __half* a[2];     // operand buffers (hi; lo at + a_lo[i])
+  int64_t a_lo[2];        // halves
+  int a_K[2];             // features of each buffer (tile stride = a_K*128 halves)
+  int chunks_per_src;     // 64-wide K chunks taken from a[0] before a[1]
+  int K;                  // total K (multiple of 64)
+  const __half* w;        // packed weight [N/64][K/8][64][8] (hi; lo at + w_lo)
+  int64_t w_lo;
+  int B;                  // real rows (rows >= B are never written)
+  int t;                  // time step (mask = t < len[b]); len == nullptr: every row is valid
+  const int* len;
+  // ---- EPI_LSTM: n = gate*16 + u inside the CTA's tile nt <-> hidden unit j = nt*16 + u
+  const float* table;     // [V][1024] additive term (input projection + biases), row tok[b*tok_stride]
+  const int* tok;         // nullptr: row 0
+  int tok_stride;
+  const float* h_prev;    // fp32 [Bp][256]
+  const float* c_prev;
+  float* h_out;           // fp32 [Bp][256]
+  float* c_out;
+  __half* h_op;           // operand copy of h_out (K = 256); lo at + h_op_lo
+  int64_t h_op_lo;
+  float* gates;           // [Bp][1024] activated gates i,f,g,o (saved for backward) or nullptr
+  float* out_f;           // masked output (0 beyond the length): element (b, j) at out_f[b*out_stride + j], or nullptr
+  int64_t out_stride;
+  __half* out_op;         // operand copy of the masked output (K = 256) or nullptr
+  int64_t out_op_lo;
+  // ---- EPI_DGRAD: column n of the output belongs to out[n / 256][b][n % 256]
+  float* out[2];
+  int keep_masked[2];     // masked rows: 1 = leave out[i] untouched (carried state), 0 = write zeros
+  const float* scale;     // {loss scale, 1 / loss scale}: results are multiplied by scale[1]
+};
+
+cudaError_t launch_step_gemm(const GemmArgs& g, int epilogue, int n_tiles, int m_tiles, bool simt, cudaStream_t st);
+
+// ---- weight-gradient GEMM (contraction over batch rows and time) ------------------------------------
+//   dW[g][k] += scale[1] * sum_{t, b} dG[t][b][g] * X[t][b][k]
+struct WgradSeqArgs {
+  const __half* dg;       // [T][operand Bp x 1024] (hi; lo at + dg_lo), step stride dg_step (halves)
+  int64_t dg_lo, dg_step;
+  const __half* x;        // [T][operand Bp x 256]
+  int64_t x_lo, x_step;
+  int T, m_tiles;         // time steps, 128-row tiles per step
+  float* dw;              // fp32 [1024][ld] (+ column offset already applied)
+  int ld;
+  const float* scale;
+};
+cudaError_t launch_wgrad_seq(const WgradSeqArgs& a, bool simt, cudaStream_t st);
+
+// ---- CUDA-core kernels (seq2seq_rows.cu) -----------------------------------------------------------
+struct PackJob {
+  int N, K;               // packed matrix shape (rows n, features k)
+  int mode;               // 0: forward (rows gate-interleaved per 16 hidden units), 1: transposed for dgrad
+  int split;              // forward: k < split from src0 else src1; transposed: n < split from src0 else src1
+  int64_t src0, src1;     // float offsets into the flat parameter buffer
+  int ld0, ld1;           // row strides of the sources
+  int64_t dst;            // halves offset into the packed buffer (hi; lo at + N*K)
+};
+cudaError_t launch_pack_seq(const PackJob* d_jobs, int n_jobs, const float* params, __half* packed, cudaStream_t st);
+
+// C[m][n] (+)= alpha * sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ bias0[n] + bias1[n])       (plain fp32 FMAs)
+struct SimtGemm {
+  const float* A; const float* B; float* C;
+  int M, N, K;
+  int64_t sam, sak, sbk, sbn, ldc;
+  const float* bias0; const float* bias1;
+  float alpha;
+  int accumulate;
+};
+cudaError_t launch_simt_gemm(const SimtGemm& g, cudaStream_t st);
+
+struct SeqDims {
+  int B, Bp, Tq, Ts, Tp, S, Vs, Vt;
+  int teacher;   // targets given
+  int sampling;  // 1 = categorical sampling, 0 = greedy
+};
+
+// token preparation (AllenNLP add_sentence_boundary_token_ids + seq2seq_base.py:128-141)
+cudaError_t launch_prepare_tokens(const int64_t* source, const int64_t* target, SeqDims d, int* src, int* src_len,
+                                  int* tgt, cudaStream_t st);
+
+struct DecRowArgs {
+  SeqDims d;
+  int t;                  // step whose attention is computed (== S: only the logits of step S-1)
+  const float* h_dec;     // fp32 [S+1][Bp][256]; slot 0 = initial decoder state, slot t+1 = h_t
+  const float* enc;       // fp32 [B][Ts][256]
+  const int* src_len;
+  const int* tgt;         // [B][Tp+2] or nullptr
+  const float* out_w; const float* out_b;   // [Vt][256], [Vt]
+  float* logits;          // [S][B][Vt]
+  float* lse;             // [S][B]
+  int* pred;              // [S][B] raw predictions
+  float* logp;            // [S][B] log-probability of the prediction
+  int* inp;               // [S][B] decoder input token of each step
+  float* attn_p;          // [S][B][Ts]
+  __half* att_op;         // [S][operand Bp x 256] (hi; lo at + att_lo), step stride att_step
+  int64_t att_lo, att_step;
+  unsigned long long seed;
+};
+cudaError_t launch_dec_row(const DecRowArgs& a, cudaStream_t st);
+
+struct FinalizeArgs {
+  SeqDims d;
+  const int* pred; const float* logp; const float* logits; const float* lse; const int* tgt;
+  int64_t* raw_out; int64_t* pred_out; float* loss; float* logits_out;
+  float* coef;            // [S][B] d(loss_b)/d(-logprob or nll at step t), before the incoming gradient
+  int* label;             // [S][B] class whose one-hot enters dlogits
+};
+cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st);
+
+struct DecBwdRowArgs {
+  SeqDims d;
+  int t;                  // step whose logits/cell backward runs (-1: only the attention backward of step 0)
+  int do_attn;            // also run the attention backward of step t+1
+  const float* grad_loss; // [B]
+  const float* coef; const int* label;
+  const float* logits; const float* lse;
+  const float* out_w;
+  const float* h_dec;     // [S+1][Bp][256]
+  const float* c_dec;     // [S+1][Bp][256]
+  const float* gates;     // [S][Bp][1024]
+  const float* enc; const int* src_len;
+  const float* attn_p;
+  float* dlogits;         // [S][B][Vt]
+  float* dh; float* dc;   // carried gradients [Bp][256]
+  const float* datt;      // [Bp][256] (written by the dgrad GEMM of step t+1)
+  float* denc;            // [B][Ts][256]
+  __half* dg_op;          // [S][operand Bp x 1024]
+  int64_t dg_lo, dg_step;
+  const float* scale;
+};
+cudaError_t launch_dec_bwd_row(const DecBwdRowArgs& a, cudaStream_t st);
+
+struct EncCellBwdArgs {
+  int B, Bp, t, Ts;
+  const int* src_len;
+  const float* gates;     // [Bp][1024] of this step
+  const float* c_prev;    // [Bp][256]
+  const float* c_cur;
+  const float* dext;      // extra gradient on h_t: element (b, j) at dext[b*dext_stride + j] (nullptr: none)
+  int64_t dext_stride;
+  float* dh; float* dc;   // carried
+  __half* dg_op; int64_t dg_lo;   // operand of this step
+  const float* scale;
+};
+cudaError_t launch_enc_cell_bwd(const EncCellBwdArgs& a, cudaStream_t st);
+
+// dP[v][g] (+)= scale[1] * sum_{(t,b): tok == v} dG[t][b][g];  tok == nullptr: everything goes to row 0
+struct TableGradArgs {
+  const __half* dg; int64_t dg_lo, dg_step;
+  const int* tok; int64_t tok_step; int tok_stride;   // token of (t, b) = tok[t*tok_step + b*tok_stride]
+  int T, B, V;
+  float* dP;              // [V][1024]
+  const float* scale;
+};
+cudaError_t launch_table_grad(const TableGradArgs& a, cudaStream_t st);
+// out[g] += sum_v dP[v][g] for two destinations (bias_ih, bias_hh)
+cudaError_t launch_bias_from_table(const float* dP, int V, float* db0, float* db1, cudaStream_t st);
+// scale[0] = 2^k with max|g| * 2^k in [2^9, 2^10), scale[1] = 1 / scale[0]
+cudaError_t launch_seq_loss_scale(const float* grad_loss, int B, float* scale, cudaStream_t st);
+
+}  // namespace pnmn

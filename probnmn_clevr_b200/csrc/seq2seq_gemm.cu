@@ -1,0 +1,406 @@
+// Tensor-core GEMMs of the LSTM seq2seq path (ProgramGenerator): one time step of an LSTM layer / the
+// decoder cell with the gate non-linearities fused into the epilogue, the matching data-gradient GEMM,
+// and the weight-gradient GEMM that contracts over batch rows and time.
+//
+// Reference arithmetic: nn.LSTM / nn.LSTMCell inside AllenNLP's SimpleSeq2Seq as used by
+// probnmn/modules/seq2seq_base.py:77-92,201 (gate order i, f, g, o; c' = f*c + i*g; h' = o*tanh(c')).
+//
+// All three kernels use tcgen05.mma kind::f16 on split fp16 operands (hi*hi + lo*hi + hi*lo, fp32
+// accumulators in TMEM; see seq2seq.h), fed by 1-D bulk async copies into an mbarrier ring, and read
+// the accumulators back with tcgen05.ld for the fused epilogue.  Warp roles: 0 = copy producer,
+// 1 = MMA issuer, 2 = TMEM allocation, 4..7 = epilogue (one TMEM lane quarter each).
+// Each kernel has a CUDA-core twin with the same epilogue (PNMN_PG_SIMT=1, bring-up only).
+#include "seq2seq.h"
+#include "tcgen05.cuh"
+
+namespace pnmn {
+
+constexpr int kGThreads = 256;
+constexpr int kGStages = 4;
+constexpr int kGABytes = 128 * 64 * 2;   // one 64-deep K chunk of a 128-row activation tile (hi or lo)
+constexpr int kGWBytes = 64 * 64 * 2;    // the same of a 64-row weight tile
+constexpr int kGStage = 2 * kGABytes + 2 * kGWBytes;
+constexpr int kGHeader = 1024;
+constexpr int kGSmem = kGHeader + kGStages * kGStage;
+static_assert(kGSmem <= 227 * 1024, "step GEMM smem");
+
+struct GemmHeader {
+  uint64_t full[kGStages], empty[kGStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+__device__ __forceinline__ uint4 pack8(const __half* h) {
+  uint4 r;
+  r.x = static_cast<uint32_t>(__half_as_ushort(h[0])) | (static_cast<uint32_t>(__half_as_ushort(h[1])) << 16);
+  r.y = static_cast<uint32_t>(__half_as_ushort(h[2])) | (static_cast<uint32_t>(__half_as_ushort(h[3])) << 16);
+  r.z = static_cast<uint32_t>(__half_as_ushort(h[4])) | (static_cast<uint32_t>(__half_as_ushort(h[5])) << 16);
+  r.w = static_cast<uint32_t>(__half_as_ushort(h[6])) | (static_cast<uint32_t>(__half_as_ushort(h[7])) << 16);
+  return r;
+}
+
+// write 16 consecutive features [j0, j0+16) of row b into an operand buffer with K = 256
+__device__ __forceinline__ void store_op16(__half* op, int64_t lo_off, int b, int j0, const float* x) {
+  __half hi[16], lo[16];
+#pragma unroll
+  for (int u = 0; u < 16; ++u) split_f16(x[u], hi[u], lo[u]);
+#pragma unroll
+  for (int gidx = 0; gidx < 2; ++gidx) {
+    const size_t off = op_off(b, j0 + 8 * gidx, kSH);
+    *reinterpret_cast<uint4*>(op + off) = pack8(hi + 8 * gidx);
+    *reinterpret_cast<uint4*>(op + lo_off + off) = pack8(lo + 8 * gidx);
+  }
+}
+
+// ---- epilogues (shared by the tensor-core kernel and its CUDA-core twin) ----------------------------
+// acc[n], n = gate*16 + u  <->  pre-activation of gate `gate` of hidden unit j = nt*16 + u of row b
+__device__ __forceinline__ void epi_lstm(const GemmArgs& g, int b, int nt, const float* acc) {
+  if (b >= g.B) return;
+  const int j0 = nt * 16;
+  const float* tab = g.table + static_cast<size_t>(g.tok ? g.tok[static_cast<size_t>(b) * g.tok_stride] : 0) * kSG;
+  const bool valid = !g.len || g.t < g.len[b];
+  float hn[16], cn[16], ov[16], gi[16], gf[16], gg[16], go[16];
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    const float4 ti = *reinterpret_cast<const float4*>(tab + j0 + 4 * q4);
+    const float4 tf = *reinterpret_cast<const float4*>(tab + kSH + j0 + 4 * q4);
+    const float4 tg = *reinterpret_cast<const float4*>(tab + 2 * kSH + j0 + 4 * q4);
+    const float4 to = *reinterpret_cast<const float4*>(tab + 3 * kSH + j0 + 4 * q4);
+    const float4 cp = *reinterpret_cast<const float4*>(g.c_prev + static_cast<size_t>(b) * kSH + j0 + 4 * q4);
+    const float4 hp = *reinterpret_cast<const float4*>(g.h_prev + static_cast<size_t>(b) * kSH + j0 + 4 * q4);
+    const float tis[4] = {ti.x, ti.y, ti.z, ti.w}, tfs[4] = {tf.x, tf.y, tf.z, tf.w};
+    const float tgs[4] = {tg.x, tg.y, tg.z, tg.w}, tos[4] = {to.x, to.y, to.z, to.w};
+    const float cps[4] = {cp.x, cp.y, cp.z, cp.w}, hps[4] = {hp.x, hp.y, hp.z, hp.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int u = 4 * q4 + e;
+      const float i_ = sigmoidf_(acc[u] + tis[e]);
+      const float f_ = sigmoidf_(acc[16 + u] + tfs[e]);
+      const float g_ = tanhf(acc[32 + u] + tgs[e]);
+      const float o_ = sigmoidf_(acc[48 + u] + tos[e]);
+      const float c2 = f_ * cps[e] + i_ * g_;
+      const float h2 = o_ * tanhf(c2);
+      gi[u] = i_; gf[u] = f_; gg[u] = g_; go[u] = o_;
+      hn[u] = valid ? h2 : hps[e];
+      cn[u] = valid ? c2 : cps[e];
+      ov[u] = valid ? h2 : 0.f;
+    }
+  }
+  float* hd = g.h_out + static_cast<size_t>(b) * kSH + j0;
+  float* cd = g.c_out + static_cast<size_t>(b) * kSH + j0;
+#pragma unroll
+  for (int q4 = 0; q4 < 4; ++q4) {
+    *reinterpret_cast<float4*>(hd + 4 * q4) = make_float4(hn[4 * q4], hn[4 * q4 + 1], hn[4 * q4 + 2], hn[4 * q4 + 3]);
+    *reinterpret_cast<float4*>(cd + 4 * q4) = make_float4(cn[4 * q4], cn[4 * q4 + 1], cn[4 * q4 + 2], cn[4 * q4 + 3]);
+  }
+  store_op16(g.h_op, g.h_op_lo, b, j0, hn);
+  if (g.gates) {
+    float* gd = g.gates + static_cast<size_t>(b) * kSG + j0;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4) {
+      *reinterpret_cast<float4*>(gd + 4 * q4) = make_float4(gi[4 * q4], gi[4 * q4 + 1], gi[4 * q4 + 2], gi[4 * q4 + 3]);
+      *reinterpret_cast<float4*>(gd + kSH + 4 * q4) = make_float4(gf[4 * q4], gf[4 * q4 + 1], gf[4 * q4 + 2], gf[4 * q4 + 3]);
+      *reinterpret_cast<float4*>(gd + 2 * kSH + 4 * q4) = make_float4(gg[4 * q4], gg[4 * q4 + 1], gg[4 * q4 + 2], gg[4 * q4 + 3]);
+      *reinterpret_cast<float4*>(gd + 3 * kSH + 4 * q4) = make_float4(go[4 * q4], go[4 * q4 + 1], go[4 * q4 + 2], go[4 * q4 + 3]);
+    }
+  }
+  if (g.out_f) {
+    float* od = g.out_f + static_cast<size_t>(b) * g.out_stride + j0;
+#pragma unroll
+    for (int q4 = 0; q4 < 4; ++q4)
+      *reinterpret_cast<float4*>(od + 4 * q4) = make_float4(ov[4 * q4], ov[4 * q4 + 1], ov[4 * q4 + 2], ov[4 * q4 + 3]);
+  }
+  if (g.out_op) store_op16(g.out_op, g.out_op_lo, b, j0, ov);
+}
+
+// acc[c], c in [0, 64): column n = nt*64 + c of [dA1 | dA2]
+__device__ __forceinline__ void epi_dgrad(const GemmArgs& g, int b, int nt, const float* acc) {
+  if (b >= g.B) return;
+  const int n0 = nt * 64, which = n0 >> 8, col0 = n0 & 255;
+  const bool masked = g.len && g.t >= g.len[b];
+  if (masked && g.keep_masked[which]) return;
+  const float s = masked ? 0.f : g.scale[1];
+  float* od = g.out[which] + static_cast<size_t>(b) * kSH + col0;
+#pragma unroll
+  for (int q4 = 0; q4 < 16; ++q4)
+    *reinterpret_cast<float4*>(od + 4 * q4) =
+        make_float4(acc[4 * q4] * s, acc[4 * q4 + 1] * s, acc[4 * q4 + 2] * s, acc[4 * q4 + 3] * s);
+}
+
+// ---- tensor-core kernel ------------------------------------------------------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmArgs g) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  GemmHeader* hdr = reinterpret_cast<GemmHeader*>(smem);
+  uint8_t* ring = smem + kGHeader;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nt = blockIdx.x, mt = blockIdx.y;
+  const int n_chunks = g.K / 64;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kGStages; ++i) {
+      mbar_init(smem_u32(&hdr->full[i]), 1);
+      mbar_init(smem_u32(&hdr->empty[i]), 1);
+    }
+    mbar_init(smem_u32(&hdr->tmem_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<64>(smem_u32(&hdr->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kc = 0; kc < n_chunks; ++kc) {
+        const int st = kc % kGStages;
+        mbar_wait(smem_u32(&hdr->empty[st]), ((kc / kGStages) & 1) ^ 1);
+        const uint32_t bar = smem_u32(&hdr->full[st]);
+        mbar_arrive_expect_tx(bar, kGStage);
+        const int si = kc / g.chunks_per_src, cj = kc % g.chunks_per_src;
+        const __half* a = g.a[si] + (static_cast<size_t>(mt) * (g.a_K[si] >> 3) + cj * 8) * 1024;
+        const __half* w = g.w + (static_cast<size_t>(nt) * (g.K >> 3) + kc * 8) * 512;
+        const uint32_t dst = smem_u32(ring + st * kGStage);
+        bulk_g2s(dst, a, kGABytes, bar);
+        bulk_g2s(dst + kGABytes, a + g.a_lo[si], kGABytes, bar);
+        bulk_g2s(dst + 2 * kGABytes, w, kGWBytes, bar);
+        bulk_g2s(dst + 2 * kGABytes + kGWBytes, w + g.w_lo, kGWBytes, bar);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, 64, 0, 0);
+      // K-major, no swizzle: LBO = distance between the two 8-deep halves of a k16 step (one plane), SBO = 128 B
+      const uint64_t a_hi = make_smem_desc(0, 128 * 16, 128) & 0xFFFFFFFFFFFFC000ull;
+      const uint64_t w_hi = make_smem_desc(0, 64 * 16, 128) & 0xFFFFFFFFFFFFC000ull;
+      for (int kc = 0; kc < n_chunks; ++kc) {
+        const int st = kc % kGStages;
+        mbar_wait(smem_u32(&hdr->full[st]), (kc / kGStages) & 1);
+        tc_fence_after();
+        const uint32_t base = smem_u32(ring + st * kGStage);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint64_t ah = a_hi | (((base + i * 2 * 2048) >> 4) & 0x3FFF);
+          const uint64_t al = a_hi | (((base + kGABytes + i * 2 * 2048) >> 4) & 0x3FFF);
+          const uint64_t wh = w_hi | (((base + 2 * kGABytes + i * 2 * 1024) >> 4) & 0x3FFF);
+          const uint64_t wl = w_hi | (((base + 2 * kGABytes + kGWBytes + i * 2 * 1024) >> 4) & 0x3FFF);
+          umma_f16(tmem_base, ah, wh, idesc, (kc | i) != 0);
+          umma_f16(tmem_base, al, wh, idesc, 1);
+          umma_f16(tmem_base, ah, wl, idesc, 1);
+        }
+        umma_commit(smem_u32(&hdr->empty[st]));
+      }
+      umma_commit(smem_u32(&hdr->tmem_full));
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int b = mt * 128 + q * 32 + lane;
+    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    tc_fence_after();
+    uint32_t v0[32], v1[32];
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), v0);
+    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 32, v1);
+    tmem_ld_wait();
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) { acc[i] = __uint_as_float(v0[i]); acc[32 + i] = __uint_as_float(v1[i]); }
+    if (EPI == EPI_LSTM) epi_lstm(g, b, nt, acc);
+    else epi_dgrad(g, b, nt, acc);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<64>(tmem_base);
+}
+
+// ---- CUDA-core twin (bring-up): thread = batch row, 64 fp32 accumulators ------------------------------
+template <int EPI>
+__global__ void __launch_bounds__(128) step_gemm_simt_kernel(const GemmArgs g) {
+  const int nt = blockIdx.x, mt = blockIdx.y;
+  const int b = mt * 128 + threadIdx.x;
+  float acc[64];
+#pragma unroll
+  for (int n = 0; n < 64; ++n) acc[n] = 0.f;
+  for (int k = 0; k < g.K; ++k) {
+    const int kc = k / 64, si = kc / g.chunks_per_src;
+    const int kk = k - si * g.chunks_per_src * 64;
+    const size_t ao = op_off(b, kk, g.a_K[si]);
+    const float av = __half2float(g.a[si][ao]) + __half2float(g.a[si][g.a_lo[si] + ao]);
+#pragma unroll 8
+    for (int n = 0; n < 64; ++n) {
+      const size_t wo = wp_off(nt * 64 + n, k, g.K);
+      acc[n] = fmaf(av, __half2float(g.w[wo]) + __half2float(g.w[g.w_lo + wo]), acc[n]);
+    }
+  }
+  if (EPI == EPI_LSTM) epi_lstm(g, b, nt, acc);
+  else epi_dgrad(g, b, nt, acc);
+}
+
+cudaError_t launch_step_gemm(const GemmArgs& g, int epilogue, int n_tiles, int m_tiles, bool simt, cudaStream_t st) {
+  const dim3 grid(n_tiles, m_tiles);
+  if (simt) {
+    if (epilogue == EPI_LSTM) step_gemm_simt_kernel<EPI_LSTM><<<grid, 128, 0, st>>>(g);
+    else step_gemm_simt_kernel<EPI_DGRAD><<<grid, 128, 0, st>>>(g);
+    return cudaGetLastError();
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(step_gemm_tc_kernel<EPI_LSTM>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(step_gemm_tc_kernel<EPI_DGRAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, kGSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  if (epilogue == EPI_LSTM) step_gemm_tc_kernel<EPI_LSTM><<<grid, kGThreads, kGSmem, st>>>(g);
+  else step_gemm_tc_kernel<EPI_DGRAD><<<grid, kGThreads, kGSmem, st>>>(g);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// weight gradient: dW[g][k] += scale[1] * sum_{t,b} dG[t][b][g] * X[t][b][k]
+// GEMM view: M = 128 gate rows (blockIdx.x), N = 128 features (blockIdx.y), K = batch rows x time; both
+// operands are read MN-major straight from the operand buffers (64 batch rows per ring stage); the time
+// range is split over blockIdx.z and the partial sums are combined with fp32 atomics.
+// =====================================================================================================
+constexpr int kWSStages = 3;
+constexpr int kWSRows = 64;
+constexpr int kWSPlane = kWSRows * 16;             // 1 KB: 8 channels of 64 batch rows
+constexpr int kWSOperand = 16 * kWSPlane;          // 128 channels (hi or lo)
+constexpr int kWSStage = 4 * kWSOperand;           // dG hi, dG lo, X hi, X lo
+constexpr int kWSSmem = kGHeader + kWSStages * kWSStage;
+static_assert(kWSSmem <= 227 * 1024, "wgrad_seq smem");
+
+struct WSHeader {
+  uint64_t full[kWSStages], empty[kWSStages];
+  uint64_t tmem_full;
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(kGThreads, 1) wgrad_seq_tc_kernel(const WgradSeqArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  WSHeader* hdr = reinterpret_cast<WSHeader*>(smem);
+  uint8_t* ring = smem + kGHeader;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int gt = blockIdx.x, nt = blockIdx.y;
+  const int t0 = static_cast<int>((static_cast<long long>(a.T) * blockIdx.z) / gridDim.z);
+  const int t1 = static_cast<int>((static_cast<long long>(a.T) * (blockIdx.z + 1)) / gridDim.z);
+  const int per_t = a.m_tiles * 2;                 // 64-row chunks per time step
+  const int total = (t1 - t0) * per_t;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < kWSStages; ++i) {
+      mbar_init(smem_u32(&hdr->full[i]), 1);
+      mbar_init(smem_u32(&hdr->empty[i]), 1);
+    }
+    mbar_init(smem_u32(&hdr->tmem_full), 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc<128>(smem_u32(&hdr->tmem_base));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = hdr->tmem_base;
+
+  if (warp == 0) {
+    for (int it = 0; it < total; ++it) {
+      const int st = it % kWSStages;
+      const uint32_t bar = smem_u32(&hdr->full[st]);
+      if (lane == 0) {
+        mbar_wait(smem_u32(&hdr->empty[st]), ((it / kWSStages) & 1) ^ 1);
+        mbar_arrive_expect_tx(bar, kWSStage);
+      }
+      __syncwarp();
+      if (lane < 16) {
+        const int t = t0 + it / per_t, c = it % per_t, mt = c >> 1, r0 = (c & 1) * kWSRows;
+        const __half* dg = a.dg + static_cast<size_t>(t) * a.dg_step +
+                           (static_cast<size_t>(mt) * (kSG >> 3) + gt * 16 + lane) * 1024 + r0 * 8;
+        const __half* x = a.x + static_cast<size_t>(t) * a.x_step +
+                          (static_cast<size_t>(mt) * (kSH >> 3) + nt * 16 + lane) * 1024 + r0 * 8;
+        const uint32_t dst = smem_u32(ring + st * kWSStage) + lane * kWSPlane;
+        bulk_g2s(dst, dg, kWSPlane, bar);
+        bulk_g2s(dst + kWSOperand, dg + a.dg_lo, kWSPlane, bar);
+        bulk_g2s(dst + 2 * kWSOperand, x, kWSPlane, bar);
+        bulk_g2s(dst + 3 * kWSOperand, x + a.x_lo, kWSPlane, bar);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_f16(128, 128, 1, 1);
+      // MN-major, no swizzle: LBO = next 8-row K group (128 B), SBO = next 8-channel plane
+      const uint64_t d_hi = make_smem_desc(0, 128, kWSPlane) & 0xFFFFFFFFFFFFC000ull;
+      for (int it = 0; it < total; ++it) {
+        const int st = it % kWSStages;
+        mbar_wait(smem_u32(&hdr->full[st]), (it / kWSStages) & 1);
+        tc_fence_after();
+        const uint32_t base = smem_u32(ring + st * kWSStage);
+#pragma unroll
+        for (int k16 = 0; k16 < kWSRows / 16; ++k16) {
+          const uint64_t gh = d_hi | (((base + k16 * 256) >> 4) & 0x3FFF);
+          const uint64_t gl = d_hi | (((base + kWSOperand + k16 * 256) >> 4) & 0x3FFF);
+          const uint64_t xh = d_hi | (((base + 2 * kWSOperand + k16 * 256) >> 4) & 0x3FFF);
+          const uint64_t xl = d_hi | (((base + 3 * kWSOperand + k16 * 256) >> 4) & 0x3FFF);
+          umma_f16(tmem_base, gh, xh, idesc, (it | k16) != 0);
+          umma_f16(tmem_base, gl, xh, idesc, 1);
+          umma_f16(tmem_base, gh, xl, idesc, 1);
+        }
+        umma_commit(smem_u32(&hdr->empty[st]));
+      }
+      umma_commit(smem_u32(&hdr->tmem_full));
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int grow = gt * 128 + q * 32 + lane;
+    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    tc_fence_after();
+    const float unscale = a.scale[1];
+    for (int chunk = 0; chunk < 4; ++chunk) {
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + chunk * 32, v);
+      tmem_ld_wait();
+      if (total > 0) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          atomicAdd(a.dw + static_cast<size_t>(grow) * a.ld + nt * 128 + chunk * 32 + j, __uint_as_float(v[j]) * unscale);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc<128>(tmem_base);
+}
+
+__global__ void __launch_bounds__(256) wgrad_seq_simt_kernel(const WgradSeqArgs a) {
+  const int k = blockIdx.x * 16 + (threadIdx.x & 15);
+  const int grow = blockIdx.y * 16 + (threadIdx.x >> 4);
+  float acc = 0.f;
+  for (int t = 0; t < a.T; ++t) {
+    const __half* dg = a.dg + static_cast<size_t>(t) * a.dg_step;
+    const __half* x = a.x + static_cast<size_t>(t) * a.x_step;
+    for (int b = 0; b < a.m_tiles * 128; ++b) {
+      const size_t go = op_off(b, grow, kSG), xo = op_off(b, k, kSH);
+      acc = fmaf(__half2float(dg[go]) + __half2float(dg[a.dg_lo + go]), __half2float(x[xo]) + __half2float(x[a.x_lo + xo]), acc);
+    }
+  }
+  atomicAdd(a.dw + static_cast<size_t>(grow) * a.ld + k, acc * a.scale[1]);
+}
+
+cudaError_t launch_wgrad_seq(const WgradSeqArgs& a, bool simt, cudaStream_t st) {
+  if (a.T <= 0) return cudaSuccess;
+  if (simt) {
+    wgrad_seq_simt_kernel<<<dim3(kSH / 16, kSG / 16), 256, 0, st>>>(a);
+    return cudaGetLastError();
+  }
+  static bool attr_done = false;
+  if (!attr_done) {
+    cudaError_t e = cudaFuncSetAttribute(wgrad_seq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSSmem);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  const int split = a.T < 9 ? a.T : 9;   // 8 x 2 x 9 = 144 CTAs on 148 SMs
+  wgrad_seq_tc_kernel<<<dim3(kSG / 128, kSH / 128, split), kGThreads, kWSSmem, st>>>(a);
+  return cudaGetLastError();
+}
+
+}  // namespace pnmn
