@@ -115,7 +115,43 @@ int pnmn_nmn_backward(pnmn_plan* p, const pnmn_buffers* bufs, const float* grad_
 int pnmn_profile_enable(int on);
 int pnmn_profile_read(double* ms, int64_t* launches);
 
+/* ---- LSTM seq2seq: ProgramGenerator (probnmn/models/program_generator.py:27-59 on top of
+ * probnmn/modules/seq2seq_base.py:49-341 and AllenNLP 0.9.0 SimpleSeq2Seq) ---------------------------
+ * All parameters live in one flat fp32 buffer; the offsets (in floats) name the reference's state-dict
+ * entries.  hidden == input size == 256, a 2-layer encoder, vocabularies of at most 128 entries. */
+typedef struct pnmn_pg_desc {
+  int32_t vocab_src, vocab_tgt, hidden, num_layers;
+  int64_t src_embed;                                          /* _source_embedder.token_embedder_tokens.weight (Vs,H) */
+  int64_t enc_w_ih[2], enc_w_hh[2], enc_b_ih[2], enc_b_hh[2]; /* _encoder._module.{weight,bias}_{ih,hh}_l{0,1}        */
+  int64_t tgt_embed;                                          /* _target_embedder.weight (Vt,H)                       */
+  int64_t dec_w_ih, dec_w_hh, dec_b_ih, dec_b_hh;             /* _decoder_cell.*; weight_ih (4H,2H) = [attended|embed] */
+  int64_t out_w, out_b;                                       /* _output_projection_layer.{weight (Vt,H), bias}       */
+} pnmn_pg_desc;
+
+/* bytes of device scratch for one forward (+ backward when need_grad); must be ZERO-FILLED whenever it is
+ * (re)allocated or any of (batch, tq, tp, steps, need_grad) changes; -1 on bad arguments */
+int64_t pnmn_pg_workspace_bytes(const pnmn_pg_desc* m, int batch, int tq, int tp, int steps, int need_grad);
+
+/* Seq2SeqBase.forward (seq2seq_base.py:101-155) + _forward_loop (:157-276): boundary tokens, 2-layer LSTM encoder,
+ * attention decoder, greedy (sampling = 0, torch.max) or categorical (sampling = 1, pad/unk/start never drawn) token
+ * choice, _trim_predictions (:278-293) and the per-row loss: teacher-forced sequence cross entropy when `target`
+ * is given (:247-254, :333-341; steps must be tp + 1), else the negated length-normalised log-probability of the
+ * chosen tokens (:235-244; steps = max_decoding_steps).  source: device int64 [batch][tq] zero-padded question
+ * tokens WITHOUT boundaries; target: device int64 [batch][tp] or NULL.  Outputs (device): raw_predictions and
+ * predictions int64 [batch][steps] (before / after trimming), loss fp32 [batch], logits fp32
+ * [batch][steps][vocab_tgt] (optional, may be NULL).  seed: Philox key of this call's sampling stream. */
+int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const int64_t* source, const int64_t* target, int batch,
+                    int tq, int tp, int steps, int sampling, uint64_t seed, int need_grad, void* workspace,
+                    int64_t* raw_predictions, int64_t* predictions, float* loss, float* logits, void* stream);
+/* autograd of the above: grad_loss is d(objective)/d(loss) [batch]; parameter gradients are ACCUMULATED into grads
+ * (same offsets as params).  Must follow a pnmn_pg_forward with need_grad = 1 on the same workspace and sizes. */
+int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, float* grads, const float* grad_loss, int batch, int tq,
+                     int tp, int steps, int teacher, void* workspace, void* stream);
+
 /* ---- bring-up entry points used by tests/ (kernel-level parity against torch) ---------------- */
+/* byte offsets of {encoder outputs, layer-0 h, layer-1 (+decoder) h, layer-1 c, decoder c, source table, target table,
+ * attention probabilities, logits} inside a pnmn_pg workspace, then {state slot bytes, Ts, padded batch} */
+int pnmn_pg_debug_layout(const pnmn_pg_desc* m, int batch, int tq, int tp, int steps, int need_grad, int64_t* out /* [12] */);
 int pnmn_debug_launch_conv(const void* tasks_host, int n_tasks, const void* cfgs_host, int n_cfgs,
                            int variant, int impl_simt, void* stream);
 int pnmn_debug_launch_wgrad(const void* tasks_host, int n_tasks, const void* insts_host, int n_insts,

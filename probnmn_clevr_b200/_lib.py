@@ -80,12 +80,25 @@ class EltTask(Structure):
 
 assert ctypes.sizeof(ConvTask) == 128 and ctypes.sizeof(EltTask) == 128
 
+
+class PgDesc(Structure):
+    """pnmn_pg_desc (include/pnmn.h): sizes + float offsets of the seq2seq parameters inside the flat buffer."""
+    _fields_ = [
+        ("vocab_src", c_int32), ("vocab_tgt", c_int32), ("hidden", c_int32), ("num_layers", c_int32),
+        ("src_embed", c_int64),
+        ("enc_w_ih", c_int64 * 2), ("enc_w_hh", c_int64 * 2), ("enc_b_ih", c_int64 * 2), ("enc_b_hh", c_int64 * 2),
+        ("tgt_embed", c_int64),
+        ("dec_w_ih", c_int64), ("dec_w_hh", c_int64), ("dec_b_ih", c_int64), ("dec_b_hh", c_int64),
+        ("out_w", c_int64), ("out_b", c_int64),
+    ]
+
 EXPORTS = [
     "pnmn_version", "pnmn_last_error", "pnmn_model_create", "pnmn_model_destroy", "pnmn_model_packed_floats",
     "pnmn_plan_create", "pnmn_plan_destroy", "pnmn_plan_valid", "pnmn_plan_sizes", "pnmn_plan_stats",
     "pnmn_nmn_forward", "pnmn_nmn_backward", "pnmn_debug_launch_conv", "pnmn_debug_launch_wgrad",
     "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt", "pnmn_profile_enable",
     "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times",
+    "pnmn_pg_workspace_bytes", "pnmn_pg_forward", "pnmn_pg_backward", "pnmn_pg_debug_layout",
 ]
 
 
@@ -133,6 +146,13 @@ def lib() -> ctypes.CDLL:
     L.pnmn_debug_launch_elt.argtypes = [c_void_p, c_int, c_void_p]
     L.pnmn_debug_set_trace.argtypes = [c_void_p, c_int64]
     L.pnmn_debug_host_times.argtypes = [POINTER(ctypes.c_double)]
+    L.pnmn_pg_workspace_bytes.restype = c_int64
+    L.pnmn_pg_workspace_bytes.argtypes = [POINTER(PgDesc), c_int, c_int, c_int, c_int, c_int]
+    L.pnmn_pg_forward.argtypes = [POINTER(PgDesc), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                  ctypes.c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.pnmn_pg_backward.argtypes = [POINTER(PgDesc), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
+                                   c_void_p, c_void_p]
+    L.pnmn_pg_debug_layout.argtypes = [POINTER(PgDesc), c_int, c_int, c_int, c_int, c_int, POINTER(c_int64)]
     L.pnmn_profile_enable.argtypes = [c_int]
     L.pnmn_profile_read.argtypes = [POINTER(ctypes.c_double), POINTER(c_int64)]
     _lib = L

@@ -117,6 +117,8 @@ int add_conv_w(pnmn_model* m, int64_t w, int64_t b, int cin, int ksize, bool nee
 
 }  // namespace
 
+namespace pnmn { void set_last_error(const std::string& s) { g_err = s; } }
+
 extern "C" int pnmn_version(void) { return PNMN_VERSION; }
 extern "C" const char* pnmn_last_error(void) { return g_err.c_str(); }
 

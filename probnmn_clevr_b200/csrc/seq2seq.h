@@ -104,7 +104,8 @@ struct PackJob {
   int ld0, ld1;           // row strides of the sources
   int64_t dst;            // halves offset into the packed buffer (hi; lo at + N*K)
 };
-cudaError_t launch_pack_seq(const PackJob* d_jobs, int n_jobs, const float* params, __half* packed, cudaStream_t st);
+struct PackJobs { PackJob j[8]; };   // passed by value as a kernel argument
+cudaError_t launch_pack_seq(const PackJobs& jobs, int n_jobs, const float* params, __half* packed, cudaStream_t st);
 
 // C[m][n] (+)= alpha * sum_k A[m*sam + k*sak] * B[k*sbk + n*sbn] (+ bias0[n] + bias1[n])       (plain fp32 FMAs)
 struct SimtGemm {

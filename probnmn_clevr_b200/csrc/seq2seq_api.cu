@@ -1,0 +1,396 @@
+// C ABI of the LSTM seq2seq path (include/pnmn.h: pnmn_pg_*): workspace layout and the launch sequences of
+// ProgramGenerator.forward / backward.
+//
+// Replaces Seq2SeqBase.forward + _forward_loop + _trim_predictions + _get_loss
+// (probnmn/modules/seq2seq_base.py:101-341) together with AllenNLP's _encode / _init_decoder_state /
+// _prepare_output_projections underneath it, and the autograd pass through them.  Every launch goes to the
+// caller's stream; nothing synchronises with the host (the reference syncs once per decoding step and once per
+// row, seq2seq_base.py:188,286).
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/pnmn.h"
+#include "seq2seq.h"
+
+using namespace pnmn;
+
+extern "C" const char* pnmn_last_error(void);
+namespace pnmn { void set_last_error(const std::string& s); }
+
+namespace {
+
+int fail(const std::string& s) {
+  pnmn::set_last_error(s);
+  return 1;
+}
+#define CUDA_OK(x)                                                                        \
+  do {                                                                                    \
+    cudaError_t e_ = (x);                                                                 \
+    if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); \
+  } while (0)
+
+bool use_simt() {
+  static const bool v = std::getenv("PNMN_PG_SIMT") != nullptr;
+  return v;
+}
+
+// byte offsets into the caller's workspace (all 256-byte aligned)
+struct Layout {
+  SeqDims d;
+  int64_t slotf, slotop, slotg, slotdg;   // per-step sizes: fp32 state (floats), operand K=256 (halves, hi+lo),
+                                          // gates (floats), gate-gradient operand (halves, hi+lo)
+  int64_t src, src_len, tgt, inp, pred, label, logp, lse, coef, logits, attn_p, dlogits;
+  int64_t P0, Pd, P1, dP0, dPd, dP1;
+  int64_t pk_hh0, pk_1, pk_d, pkT_0, pkT_1, pkT_d;   // packed weights (halves offsets inside `packed`)
+  int64_t packed;
+  int64_t zeros;
+  int64_t h0f, c0f, h0op, out0op, g0;      // encoder layer 0
+  int64_t h1f, c1f, h1op, g1, enc;         // encoder layer 1 (+ decoder slots appended to h1f / h1op)
+  int64_t cdf, attop, gd;                  // decoder
+  int64_t dh, dc, datt, denc, dout0, dgd, dg1, dg0, scale;
+  int64_t total;
+};
+
+Layout make_layout(const pnmn_pg_desc* m, int B, int Tq, int Tp, int S, bool need_grad) {
+  Layout L;
+  std::memset(&L, 0, sizeof(L));
+  SeqDims& d = L.d;
+  d.B = B; d.Bp = (B + 127) / 128 * 128; d.Tq = Tq; d.Ts = Tq + 1; d.Tp = Tp; d.S = S;
+  d.Vs = m->vocab_src; d.Vt = m->vocab_tgt;
+  L.slotf = static_cast<int64_t>(d.Bp) * kSH;
+  L.slotop = 2 * L.slotf;
+  L.slotg = static_cast<int64_t>(d.Bp) * kSG;
+  L.slotdg = 2 * L.slotg;
+  int64_t o = 0;
+  auto take = [&](int64_t bytes) { const int64_t r = o; o += (bytes + 255) / 256 * 256; return r; };
+  const int64_t SB = static_cast<int64_t>(S) * B;
+  L.src = take(4ll * B * d.Ts); L.src_len = take(4ll * B); L.tgt = take(4ll * B * (Tp + 2));
+  L.inp = take(4 * SB); L.pred = take(4 * SB); L.label = take(4 * SB);
+  L.logp = take(4 * SB); L.lse = take(4 * SB); L.coef = take(4 * SB);
+  L.logits = take(4 * SB * d.Vt); L.attn_p = take(4 * SB * d.Ts);
+  L.P0 = take(4ll * d.Vs * kSG); L.Pd = take(4ll * d.Vt * kSG); L.P1 = take(4ll * kSG);
+  // packed weights: forward tiles, then the transposed tiles of the data-gradient GEMMs
+  int64_t ph = 0;
+  auto takeh = [&](int64_t n, int64_t k) { const int64_t r = ph; ph += 2 * n * k; return r; };
+  L.pk_hh0 = takeh(kSG, kSH); L.pk_1 = takeh(kSG, 2 * kSH); L.pk_d = takeh(kSG, 2 * kSH);
+  L.pkT_0 = takeh(kSH, kSG); L.pkT_1 = takeh(2 * kSH, kSG); L.pkT_d = takeh(2 * kSH, kSG);
+  L.packed = take(2 * ph);
+  L.zeros = take(4 * L.slotf);
+  L.h0f = take(4 * L.slotf * (d.Ts + 1)); L.c0f = take(4 * L.slotf * (d.Ts + 1));
+  L.h0op = take(2 * L.slotop * (d.Ts + 1)); L.out0op = take(2 * L.slotop * d.Ts);
+  // layer 1 state slots 0..Ts, directly followed by the decoder's slots 1..S (decoder slot 0 IS layer-1 slot Ts)
+  L.h1f = take(4 * L.slotf * (d.Ts + 1 + S)); L.c1f = take(4 * L.slotf * (d.Ts + 1));
+  L.h1op = take(2 * L.slotop * (d.Ts + 1 + S));
+  L.enc = take(4ll * B * d.Ts * kSH);
+  L.cdf = take(4 * L.slotf * (S + 1)); L.attop = take(2 * L.slotop * S);
+  L.scale = take(256);
+  if (need_grad) {
+    L.g0 = take(4 * L.slotg * d.Ts); L.g1 = take(4 * L.slotg * d.Ts); L.gd = take(4 * L.slotg * S);
+    L.dlogits = take(4ll * S * d.Bp * d.Vt);
+    L.dP0 = take(4ll * d.Vs * kSG); L.dPd = take(4ll * d.Vt * kSG); L.dP1 = take(4ll * kSG);
+    L.dh = take(4 * L.slotf); L.dc = take(4 * L.slotf); L.datt = take(4 * L.slotf);
+    L.denc = take(4ll * B * d.Ts * kSH); L.dout0 = take(4 * L.slotf * d.Ts);
+    L.dgd = take(2 * L.slotdg * S); L.dg1 = take(2 * L.slotdg * d.Ts); L.dg0 = take(2 * L.slotdg * d.Ts);
+  }
+  L.total = o;
+  return L;
+}
+
+int check_dims(const pnmn_pg_desc* m, int B, int Tq, int Tp, int S, bool teacher) {
+  if (!m) return fail("pnmn_pg: NULL model description");
+  if (m->hidden != kSH) return fail("pnmn_pg: the B200 seq2seq kernels are built for input_size = hidden_size = 256");
+  if (m->num_layers != 2) return fail("pnmn_pg: the encoder must have 2 layers");
+  if (m->vocab_tgt < 4 || m->vocab_tgt > kSMaxV) return fail("pnmn_pg: target vocabulary must have 4..128 entries");
+  if (m->vocab_src < 4 || m->vocab_src > kSMaxV) return fail("pnmn_pg: source vocabulary must have 4..128 entries");
+  if (B < 1) return fail("pnmn_pg: empty batch");
+  if (Tq < 0 || Tq + 1 > kSMaxT) return fail("pnmn_pg: source sequences longer than 63 tokens are not supported");
+  if (S < 1) return fail("pnmn_pg: at least one decoding step");
+  if (teacher && S != Tp + 1) return fail("pnmn_pg: with targets the number of decoding steps must be target_length + 1");
+  return 0;
+}
+
+template <class T>
+T* at(void* ws, int64_t off) { return reinterpret_cast<T*>(static_cast<uint8_t*>(ws) + off); }
+
+}  // namespace
+
+extern "C" int64_t pnmn_pg_workspace_bytes(const pnmn_pg_desc* m, int batch, int tq, int tp, int steps, int need_grad) {
+  if (check_dims(m, batch, tq, tp, steps, false)) return -1;
+  return make_layout(m, batch, tq, tp, steps, need_grad != 0).total;
+}
+
+// byte offsets of a few workspace buffers, for the parity tests: {enc (fp32 [B][Ts][256]), h0f, h1f, c1f, cdf, P0, Pd,
+// attn_p, logits, slot bytes of the fp32 state arrays, Ts, Bp}
+extern "C" int pnmn_pg_debug_layout(const pnmn_pg_desc* m, int batch, int tq, int tp, int steps, int need_grad, int64_t* out) {
+  if (check_dims(m, batch, tq, tp, steps, false)) return 1;
+  const Layout L = make_layout(m, batch, tq, tp, steps, need_grad != 0);
+  const int64_t v[12] = {L.enc, L.h0f, L.h1f, L.c1f, L.cdf, L.P0, L.Pd, L.attn_p, L.logits, 4 * L.slotf, L.d.Ts, L.d.Bp};
+  for (int i = 0; i < 12; ++i) out[i] = v[i];
+  return 0;
+}
+
+extern "C" int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const int64_t* source, const int64_t* target,
+                               int batch, int tq, int tp, int steps, int sampling, uint64_t seed, int need_grad,
+                               void* ws, int64_t* raw_predictions, int64_t* predictions, float* loss, float* logits_out,
+                               void* stream) {
+  const bool teacher = target != nullptr;
+  if (check_dims(m, batch, tq, tp, steps, teacher)) return 1;
+  if (!params || !source || !ws || !raw_predictions || !predictions || !loss) return fail("pnmn_pg_forward: NULL buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Layout L = make_layout(m, batch, tq, tp, steps, need_grad != 0);
+  SeqDims& d = L.d;
+  d.teacher = teacher ? 1 : 0;
+  d.sampling = sampling ? 1 : 0;
+  const bool simt = use_simt();
+  const int MT = d.Bp / 128;
+  __half* packed = at<__half>(ws, L.packed);
+
+  CUDA_OK(launch_prepare_tokens(source, target, d, at<int>(ws, L.src), at<int>(ws, L.src_len), at<int>(ws, L.tgt), st));
+
+  // ---- weights -> split fp16 tiles ------------------------------------------------------------------------
+  {
+    PackJobs J;
+    std::memset(&J, 0, sizeof(J));
+    auto job = [](int N, int K, int mode, int split, int64_t s0, int ld0, int64_t s1, int ld1, int64_t dst) {
+      PackJob j; j.N = N; j.K = K; j.mode = mode; j.split = split; j.src0 = s0; j.src1 = s1; j.ld0 = ld0; j.ld1 = ld1; j.dst = dst;
+      return j;
+    };
+    J.j[0] = job(kSG, kSH, 0, kSH, m->enc_w_hh[0], kSH, m->enc_w_hh[0], kSH, L.pk_hh0);
+    J.j[1] = job(kSG, 2 * kSH, 0, kSH, m->enc_w_ih[1], kSH, m->enc_w_hh[1], kSH, L.pk_1);
+    J.j[2] = job(kSG, 2 * kSH, 0, kSH, m->dec_w_ih, 2 * kSH, m->dec_w_hh, kSH, L.pk_d);   // cat(attended, embedding): attended first
+    J.j[3] = job(kSH, kSG, 1, kSH, m->enc_w_hh[0], kSH, m->enc_w_hh[0], kSH, L.pkT_0);
+    J.j[4] = job(2 * kSH, kSG, 1, kSH, m->enc_w_ih[1], kSH, m->enc_w_hh[1], kSH, L.pkT_1);
+    J.j[5] = job(2 * kSH, kSG, 1, kSH, m->dec_w_ih, 2 * kSH, m->dec_w_hh, kSH, L.pkT_d);
+    CUDA_OK(launch_pack_seq(J, need_grad ? 6 : 3, params, packed, st));
+  }
+  // ---- input-projection tables: P[v] = Emb[v] . W_ih^T + b_ih + b_hh ----------------------------------------
+  {
+    SimtGemm g;
+    std::memset(&g, 0, sizeof(g));
+    g.alpha = 1.f; g.N = kSG; g.ldc = kSG; g.sak = 1; g.sbk = 1;
+    g.A = params + m->src_embed; g.sam = kSH; g.M = d.Vs; g.K = kSH;
+    g.B = params + m->enc_w_ih[0]; g.sbn = kSH;
+    g.bias0 = params + m->enc_b_ih[0]; g.bias1 = params + m->enc_b_hh[0]; g.C = at<float>(ws, L.P0);
+    CUDA_OK(launch_simt_gemm(g, st));
+    g.A = params + m->tgt_embed; g.M = d.Vt;
+    g.B = params + m->dec_w_ih + kSH; g.sbn = 2 * kSH;
+    g.bias0 = params + m->dec_b_ih; g.bias1 = params + m->dec_b_hh; g.C = at<float>(ws, L.Pd);
+    CUDA_OK(launch_simt_gemm(g, st));
+    g.M = 1; g.K = 0; g.bias0 = params + m->enc_b_ih[1]; g.bias1 = params + m->enc_b_hh[1]; g.C = at<float>(ws, L.P1);
+    CUDA_OK(launch_simt_gemm(g, st));
+  }
+
+  GemmArgs g;
+  std::memset(&g, 0, sizeof(g));
+  g.B = d.B; g.chunks_per_src = 4; g.a_K[0] = g.a_K[1] = kSH; g.a_lo[0] = g.a_lo[1] = L.slotf; g.h_op_lo = L.slotf;
+  g.out_op_lo = L.slotf;
+  g.len = at<int>(ws, L.src_len);
+  // ---- encoder layer 0 ------------------------------------------------------------------------------------
+  for (int t = 0; t < d.Ts; ++t) {
+    g.t = t; g.K = kSH;
+    g.a[0] = at<__half>(ws, L.h0op) + t * L.slotop; g.a[1] = nullptr;
+    g.w = packed + L.pk_hh0; g.w_lo = static_cast<int64_t>(kSG) * kSH;
+    g.table = at<float>(ws, L.P0); g.tok = at<int>(ws, L.src) + t; g.tok_stride = d.Ts;
+    g.h_prev = at<float>(ws, L.h0f) + t * L.slotf; g.c_prev = at<float>(ws, L.c0f) + t * L.slotf;
+    g.h_out = at<float>(ws, L.h0f) + (t + 1) * L.slotf; g.c_out = at<float>(ws, L.c0f) + (t + 1) * L.slotf;
+    g.h_op = at<__half>(ws, L.h0op) + (t + 1) * L.slotop;
+    g.gates = need_grad ? at<float>(ws, L.g0) + t * L.slotg : nullptr;
+    g.out_f = nullptr; g.out_op = at<__half>(ws, L.out0op) + t * L.slotop;
+    CUDA_OK(launch_step_gemm(g, EPI_LSTM, kSG / 64, MT, simt, st));
+  }
+  // ---- encoder layer 1 ------------------------------------------------------------------------------------
+  for (int t = 0; t < d.Ts; ++t) {
+    g.t = t; g.K = 2 * kSH;
+    g.a[0] = at<__half>(ws, L.out0op) + t * L.slotop; g.a[1] = at<__half>(ws, L.h1op) + t * L.slotop;
+    g.w = packed + L.pk_1; g.w_lo = static_cast<int64_t>(kSG) * 2 * kSH;
+    g.table = at<float>(ws, L.P1); g.tok = nullptr; g.tok_stride = 0;
+    g.h_prev = at<float>(ws, L.h1f) + t * L.slotf; g.c_prev = at<float>(ws, L.c1f) + t * L.slotf;
+    g.h_out = at<float>(ws, L.h1f) + (t + 1) * L.slotf; g.c_out = at<float>(ws, L.c1f) + (t + 1) * L.slotf;
+    g.h_op = at<__half>(ws, L.h1op) + (t + 1) * L.slotop;
+    g.gates = need_grad ? at<float>(ws, L.g1) + t * L.slotg : nullptr;
+    g.out_f = at<float>(ws, L.enc) + static_cast<int64_t>(t) * kSH; g.out_stride = static_cast<int64_t>(d.Ts) * kSH;
+    g.out_op = nullptr;
+    CUDA_OK(launch_step_gemm(g, EPI_LSTM, kSG / 64, MT, simt, st));
+  }
+  // ---- decoder: h_0 = encoder output at the last valid position = frozen final layer-1 state, c_0 = 0 -------
+  DecRowArgs r;
+  std::memset(&r, 0, sizeof(r));
+  r.d = d;
+  r.h_dec = at<float>(ws, L.h1f) + d.Ts * L.slotf;
+  r.enc = at<float>(ws, L.enc); r.src_len = at<int>(ws, L.src_len); r.tgt = teacher ? at<int>(ws, L.tgt) : nullptr;
+  r.out_w = params + m->out_w; r.out_b = params + m->out_b;
+  r.logits = at<float>(ws, L.logits); r.lse = at<float>(ws, L.lse); r.pred = at<int>(ws, L.pred);
+  r.logp = at<float>(ws, L.logp); r.inp = at<int>(ws, L.inp); r.attn_p = at<float>(ws, L.attn_p);
+  r.att_op = at<__half>(ws, L.attop); r.att_lo = L.slotf; r.att_step = L.slotop;
+  r.seed = seed;
+  g.len = nullptr; g.out_f = nullptr; g.out_op = nullptr;
+  for (int t = 0; t <= d.S; ++t) {
+    r.t = t;
+    CUDA_OK(launch_dec_row(r, st));
+    if (t == d.S) break;
+    g.t = t; g.K = 2 * kSH;
+    g.a[0] = at<__half>(ws, L.attop) + t * L.slotop; g.a[1] = at<__half>(ws, L.h1op) + (d.Ts + t) * L.slotop;
+    g.w = packed + L.pk_d; g.w_lo = static_cast<int64_t>(kSG) * 2 * kSH;
+    g.table = at<float>(ws, L.Pd); g.tok = at<int>(ws, L.inp) + static_cast<int64_t>(t) * d.B; g.tok_stride = 1;
+    g.h_prev = at<float>(ws, L.h1f) + (d.Ts + t) * L.slotf; g.c_prev = at<float>(ws, L.cdf) + t * L.slotf;
+    g.h_out = at<float>(ws, L.h1f) + (d.Ts + t + 1) * L.slotf; g.c_out = at<float>(ws, L.cdf) + (t + 1) * L.slotf;
+    g.h_op = at<__half>(ws, L.h1op) + (d.Ts + t + 1) * L.slotop;
+    g.gates = need_grad ? at<float>(ws, L.gd) + t * L.slotg : nullptr;
+    CUDA_OK(launch_step_gemm(g, EPI_LSTM, kSG / 64, MT, simt, st));
+  }
+  FinalizeArgs f;
+  std::memset(&f, 0, sizeof(f));
+  f.d = d;
+  f.pred = at<int>(ws, L.pred); f.logp = at<float>(ws, L.logp); f.logits = at<float>(ws, L.logits); f.lse = at<float>(ws, L.lse);
+  f.tgt = teacher ? at<int>(ws, L.tgt) : nullptr;
+  f.raw_out = raw_predictions; f.pred_out = predictions; f.loss = loss; f.logits_out = logits_out;
+  f.coef = at<float>(ws, L.coef); f.label = at<int>(ws, L.label);
+  CUDA_OK(launch_finalize(f, st));
+  return 0;
+}
+
+extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, float* grads, const float* grad_loss, int batch,
+                                int tq, int tp, int steps, int teacher, void* ws, void* stream) {
+  if (check_dims(m, batch, tq, tp, steps, teacher != 0)) return 1;
+  if (!params || !grads || !grad_loss || !ws) return fail("pnmn_pg_backward: NULL buffer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  Layout L = make_layout(m, batch, tq, tp, steps, true);
+  SeqDims& d = L.d;
+  d.teacher = teacher ? 1 : 0;
+  const bool simt = use_simt();
+  const int MT = d.Bp / 128;
+  const __half* packed = at<__half>(ws, L.packed);
+  float* scale = at<float>(ws, L.scale);
+
+  CUDA_OK(launch_seq_loss_scale(grad_loss, d.B, scale, st));
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dh), 0, 4 * L.slotf, st));
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dc), 0, 4 * L.slotf, st));
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.denc), 0, 4ll * d.B * d.Ts * kSH, st));
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dP0), 0, 4ll * d.Vs * kSG, st));
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dPd), 0, 4ll * d.Vt * kSG, st));
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dP1), 0, 4ll * kSG, st));
+
+  GemmArgs g;
+  std::memset(&g, 0, sizeof(g));
+  g.B = d.B; g.K = kSG; g.chunks_per_src = kSG / 64; g.a_K[0] = kSG; g.a_lo[0] = L.slotg; g.scale = scale;
+
+  // ---- decoder ------------------------------------------------------------------------------------------------
+  DecBwdRowArgs r;
+  std::memset(&r, 0, sizeof(r));
+  r.d = d;
+  r.grad_loss = grad_loss; r.coef = at<float>(ws, L.coef); r.label = at<int>(ws, L.label);
+  r.logits = at<float>(ws, L.logits); r.lse = at<float>(ws, L.lse); r.out_w = params + m->out_w;
+  r.h_dec = at<float>(ws, L.h1f) + d.Ts * L.slotf; r.c_dec = at<float>(ws, L.cdf); r.gates = at<float>(ws, L.gd);
+  r.enc = at<float>(ws, L.enc); r.src_len = at<int>(ws, L.src_len); r.attn_p = at<float>(ws, L.attn_p);
+  r.dlogits = at<float>(ws, L.dlogits); r.dh = at<float>(ws, L.dh); r.dc = at<float>(ws, L.dc);
+  r.datt = at<float>(ws, L.datt); r.denc = at<float>(ws, L.denc);
+  r.dg_op = at<__half>(ws, L.dgd); r.dg_lo = L.slotg; r.dg_step = L.slotdg; r.scale = scale;
+  g.len = nullptr;
+  g.w = packed + L.pkT_d; g.w_lo = static_cast<int64_t>(2 * kSH) * kSG;
+  g.out[0] = at<float>(ws, L.datt); g.out[1] = at<float>(ws, L.dh);
+  for (int t = d.S - 1; t >= 0; --t) {
+    r.t = t; r.do_attn = t < d.S - 1 ? 1 : 0;
+    CUDA_OK(launch_dec_bwd_row(r, st));
+    g.t = t; g.a[0] = at<__half>(ws, L.dgd) + t * L.slotdg;
+    CUDA_OK(launch_step_gemm(g, EPI_DGRAD, 2 * kSH / 64, MT, simt, st));
+  }
+  r.t = -1; r.do_attn = 1;
+  CUDA_OK(launch_dec_bwd_row(r, st));   // attention of step 0 -> d(initial decoder state), d(encoder outputs)
+
+  // ---- encoder layer 1: dh carries d(final state); dc restarts (the decoder's c_0 is a constant) ------------------
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dc), 0, 4 * L.slotf, st));
+  EncCellBwdArgs e;
+  std::memset(&e, 0, sizeof(e));
+  e.B = d.B; e.Bp = d.Bp; e.Ts = d.Ts; e.src_len = at<int>(ws, L.src_len);
+  e.dh = at<float>(ws, L.dh); e.dc = at<float>(ws, L.dc); e.dg_lo = L.slotg; e.scale = scale;
+  g.len = at<int>(ws, L.src_len);
+  g.w = packed + L.pkT_1; g.w_lo = static_cast<int64_t>(2 * kSH) * kSG;
+  g.out[1] = at<float>(ws, L.dh); g.keep_masked[0] = 0; g.keep_masked[1] = 1;
+  for (int t = d.Ts - 1; t >= 0; --t) {
+    e.t = t; e.gates = at<float>(ws, L.g1) + t * L.slotg;
+    e.c_prev = at<float>(ws, L.c1f) + t * L.slotf; e.c_cur = at<float>(ws, L.c1f) + (t + 1) * L.slotf;
+    e.dext = at<float>(ws, L.denc) + static_cast<int64_t>(t) * kSH; e.dext_stride = static_cast<int64_t>(d.Ts) * kSH;
+    e.dg_op = at<__half>(ws, L.dg1) + t * L.slotdg;
+    CUDA_OK(launch_enc_cell_bwd(e, st));
+    g.t = t; g.a[0] = at<__half>(ws, L.dg1) + t * L.slotdg;
+    g.out[0] = at<float>(ws, L.dout0) + t * L.slotf;
+    CUDA_OK(launch_step_gemm(g, EPI_DGRAD, 2 * kSH / 64, MT, simt, st));
+  }
+  // ---- encoder layer 0 ---------------------------------------------------------------------------------------------
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dh), 0, 4 * L.slotf, st));
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dc), 0, 4 * L.slotf, st));
+  g.w = packed + L.pkT_0; g.w_lo = static_cast<int64_t>(kSH) * kSG;
+  g.out[0] = at<float>(ws, L.dh); g.out[1] = nullptr; g.keep_masked[0] = 1;
+  for (int t = d.Ts - 1; t >= 0; --t) {
+    e.t = t; e.gates = at<float>(ws, L.g0) + t * L.slotg;
+    e.c_prev = at<float>(ws, L.c0f) + t * L.slotf; e.c_cur = at<float>(ws, L.c0f) + (t + 1) * L.slotf;
+    e.dext = at<float>(ws, L.dout0) + t * L.slotf; e.dext_stride = kSH;
+    e.dg_op = at<__half>(ws, L.dg0) + t * L.slotdg;
+    CUDA_OK(launch_enc_cell_bwd(e, st));
+    g.t = t; g.a[0] = at<__half>(ws, L.dg0) + t * L.slotdg;
+    CUDA_OK(launch_step_gemm(g, EPI_DGRAD, kSH / 64, MT, simt, st));
+  }
+
+  // ---- weight gradients: contraction over batch rows x time on the tensor cores ---------------------------------------
+  WgradSeqArgs w;
+  std::memset(&w, 0, sizeof(w));
+  w.dg_lo = L.slotg; w.dg_step = L.slotdg; w.x_lo = L.slotf; w.x_step = L.slotop; w.m_tiles = MT; w.scale = scale;
+  w.dg = at<__half>(ws, L.dg0); w.T = d.Ts;
+  w.x = at<__half>(ws, L.h0op); w.dw = grads + m->enc_w_hh[0]; w.ld = kSH;
+  CUDA_OK(launch_wgrad_seq(w, simt, st));
+  w.dg = at<__half>(ws, L.dg1);
+  w.x = at<__half>(ws, L.out0op); w.dw = grads + m->enc_w_ih[1];
+  CUDA_OK(launch_wgrad_seq(w, simt, st));
+  w.x = at<__half>(ws, L.h1op); w.dw = grads + m->enc_w_hh[1];
+  CUDA_OK(launch_wgrad_seq(w, simt, st));
+  w.dg = at<__half>(ws, L.dgd); w.T = d.S;
+  w.x = at<__half>(ws, L.attop); w.dw = grads + m->dec_w_ih; w.ld = 2 * kSH;
+  CUDA_OK(launch_wgrad_seq(w, simt, st));
+  w.x = at<__half>(ws, L.h1op) + d.Ts * L.slotop; w.dw = grads + m->dec_w_hh; w.ld = kSH;
+  CUDA_OK(launch_wgrad_seq(w, simt, st));
+
+  // ---- tables -> biases, embeddings, input-projection weights ------------------------------------------------------------
+  TableGradArgs tg;
+  std::memset(&tg, 0, sizeof(tg));
+  tg.dg_lo = L.slotg; tg.dg_step = L.slotdg; tg.B = d.B; tg.scale = scale;
+  tg.dg = at<__half>(ws, L.dg0); tg.T = d.Ts; tg.V = d.Vs; tg.tok = at<int>(ws, L.src); tg.tok_step = 1; tg.tok_stride = d.Ts;
+  tg.dP = at<float>(ws, L.dP0);
+  CUDA_OK(launch_table_grad(tg, st));
+  tg.dg = at<__half>(ws, L.dg1); tg.V = 1; tg.tok = nullptr; tg.dP = at<float>(ws, L.dP1);
+  CUDA_OK(launch_table_grad(tg, st));
+  tg.dg = at<__half>(ws, L.dgd); tg.T = d.S; tg.V = d.Vt; tg.tok = at<int>(ws, L.inp); tg.tok_step = d.B; tg.tok_stride = 1;
+  tg.dP = at<float>(ws, L.dPd);
+  CUDA_OK(launch_table_grad(tg, st));
+  CUDA_OK(launch_bias_from_table(at<float>(ws, L.dP0), d.Vs, grads + m->enc_b_ih[0], grads + m->enc_b_hh[0], st));
+  CUDA_OK(launch_bias_from_table(at<float>(ws, L.dP1), 1, grads + m->enc_b_ih[1], grads + m->enc_b_hh[1], st));
+  CUDA_OK(launch_bias_from_table(at<float>(ws, L.dPd), d.Vt, grads + m->dec_b_ih, grads + m->dec_b_hh, st));
+  {
+    SimtGemm s;
+    std::memset(&s, 0, sizeof(s));
+    s.alpha = 1.f; s.accumulate = 1;
+    // dEmb_src[v][e] += sum_g dP0[v][g] * W_ih0[g][e]
+    s.A = at<float>(ws, L.dP0); s.sam = kSG; s.sak = 1; s.M = d.Vs; s.K = kSG;
+    s.B = params + m->enc_w_ih[0]; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = grads + m->src_embed; s.ldc = kSH;
+    CUDA_OK(launch_simt_gemm(s, st));
+    // dW_ih0[g][e] += sum_v dP0[v][g] * Emb_src[v][e]
+    s.A = at<float>(ws, L.dP0); s.sam = 1; s.sak = kSG; s.M = kSG; s.K = d.Vs;
+    s.B = params + m->src_embed; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = grads + m->enc_w_ih[0]; s.ldc = kSH;
+    CUDA_OK(launch_simt_gemm(s, st));
+    // dEmb_tgt[v][e] += sum_g dPd[v][g] * W_dec_ih[g][256 + e]
+    s.A = at<float>(ws, L.dPd); s.sam = kSG; s.sak = 1; s.M = d.Vt; s.K = kSG;
+    s.B = params + m->dec_w_ih + kSH; s.sbk = 2 * kSH; s.sbn = 1; s.N = kSH; s.C = grads + m->tgt_embed; s.ldc = kSH;
+    CUDA_OK(launch_simt_gemm(s, st));
+    // dW_dec_ih[g][256 + e] += sum_v dPd[v][g] * Emb_tgt[v][e]
+    s.A = at<float>(ws, L.dPd); s.sam = 1; s.sak = kSG; s.M = kSG; s.K = d.Vt;
+    s.B = params + m->tgt_embed; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = grads + m->dec_w_ih + kSH; s.ldc = 2 * kSH;
+    CUDA_OK(launch_simt_gemm(s, st));
+    // output projection: dW_o[v][j] += sum_{t,b} dlogits[t][b][v] * h_t[b][j];  db_o[v] += sum dlogits
+    s.A = at<float>(ws, L.dlogits); s.sam = 1; s.sak = d.Vt; s.M = d.Vt; s.K = d.S * d.Bp;
+    s.B = at<float>(ws, L.h1f) + (d.Ts + 1) * L.slotf; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = grads + m->out_w; s.ldc = kSH;
+    CUDA_OK(launch_simt_gemm(s, st));
+    s.B = scale + 2; s.sbk = 0; s.sbn = 0; s.N = 1; s.C = grads + m->out_b; s.ldc = 1;
+    CUDA_OK(launch_simt_gemm(s, st));
+  }
+  return 0;
+}

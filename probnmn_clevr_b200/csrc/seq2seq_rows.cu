@@ -1,0 +1,619 @@
+// CUDA-core kernels of the LSTM seq2seq path: everything that is row-local (one batch row per CTA) or
+// tiny — token boundaries, the decoder's output projection / softmax / token choice / dot-product attention,
+// their backward, the LSTM cell backward, table (embedding-projection) gradients, weight packing and a
+// small strided fp32 GEMM for the |V| x 1024 tables.
+//
+// Reference: probnmn/modules/seq2seq_base.py:101-341 (in-repo logic) and AllenNLP 0.9.0
+// SimpleSeq2Seq._prepare_output_projections / nn.util.masked_softmax / add_sentence_boundary_token_ids
+// (restated in oracle/seq2seq_oracle.py).
+#include "seq2seq.h"
+
+namespace pnmn {
+
+namespace {
+
+constexpr int kPad = 0, kStart = 2, kEnd = 3;  // identical in every padded namespace (seq2seq_base.py:61-65)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ uint4 pack8h(const __half* h) {
+  uint4 r;
+  r.x = static_cast<uint32_t>(__half_as_ushort(h[0])) | (static_cast<uint32_t>(__half_as_ushort(h[1])) << 16);
+  r.y = static_cast<uint32_t>(__half_as_ushort(h[2])) | (static_cast<uint32_t>(__half_as_ushort(h[3])) << 16);
+  r.z = static_cast<uint32_t>(__half_as_ushort(h[4])) | (static_cast<uint32_t>(__half_as_ushort(h[5])) << 16);
+  r.w = static_cast<uint32_t>(__half_as_ushort(h[6])) | (static_cast<uint32_t>(__half_as_ushort(h[7])) << 16);
+  return r;
+}
+// 8 consecutive features [k0, k0+8) of row b -> operand buffer (hi; lo at + lo_off)
+__device__ __forceinline__ void store_op8(__half* op, int64_t lo_off, int b, int k0, int K, const float* x, float mul) {
+  __half hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) split_f16(x[e] * mul, hi[e], lo[e]);
+  const size_t off = op_off(b, k0, K);
+  *reinterpret_cast<uint4*>(op + off) = pack8h(hi);
+  *reinterpret_cast<uint4*>(op + lo_off + off) = pack8h(lo);
+}
+
+// Philox4x32-10 (counter-based; one draw per (row, step), reproducible and independent of launch geometry)
+__device__ __forceinline__ void philox_round(uint32_t (&c)[4], uint32_t k0, uint32_t k1) {
+  const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+  const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+  const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+  c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+}
+__device__ __forceinline__ float philox_uniform(unsigned long long seed, uint32_t row, uint32_t step) {
+  uint32_t c[4] = {row, step, 0x9E3779B9u, 0u};
+  uint32_t k0 = static_cast<uint32_t>(seed), k1 = static_cast<uint32_t>(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    philox_round(c, k0, k1);
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+  return static_cast<float>(c[0] >> 8) * (1.0f / 16777216.0f);  // [0, 1)
+}
+
+}  // namespace
+
+// =====================================================================================================
+// tokens: AllenNLP add_sentence_boundary_token_ids, then the source drops its leading @start@
+// (seq2seq_base.py:128-141).  src: [B][Tq+1] = w_1..w_n @end@ 0..;  tgt: [B][Tp+2] = @start@ p_1..p_m @end@ 0..
+// =====================================================================================================
+// out-of-vocabulary ids map to @@UNKNOWN@@ (the reference's embedding lookup would raise instead)
+__device__ __forceinline__ int clamp_tok(int64_t v, int V) { return (v < 0 || v >= V) ? 1 : static_cast<int>(v); }
+
+__global__ void prepare_tokens_kernel(const int64_t* __restrict__ source, const int64_t* __restrict__ target, SeqDims d,
+                                      int* __restrict__ src, int* __restrict__ src_len, int* __restrict__ tgt) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  int n = 0;
+  for (int s = 0; s < d.Tq; ++s) n += source[static_cast<size_t>(b) * d.Tq + s] != kPad;
+  for (int s = 0; s < d.Ts; ++s)
+    src[static_cast<size_t>(b) * d.Ts + s] = s < d.Tq ? clamp_tok(source[static_cast<size_t>(b) * d.Tq + s], d.Vs) : kPad;
+  src[static_cast<size_t>(b) * d.Ts + n] = kEnd;
+  int len = 0;
+  for (int s = 0; s < d.Ts; ++s) len += src[static_cast<size_t>(b) * d.Ts + s] != kPad;
+  src_len[b] = len;
+  if (target) {
+    const int W = d.Tp + 2;
+    int m = 0;
+    for (int s = 0; s < d.Tp; ++s) m += target[static_cast<size_t>(b) * d.Tp + s] != kPad;
+    tgt[static_cast<size_t>(b) * W] = kStart;
+    for (int s = 0; s < d.Tp; ++s) tgt[static_cast<size_t>(b) * W + 1 + s] = clamp_tok(target[static_cast<size_t>(b) * d.Tp + s], d.Vt);
+    tgt[static_cast<size_t>(b) * W + d.Tp + 1] = kPad;
+    tgt[static_cast<size_t>(b) * W + m + 1] = kEnd;
+  }
+}
+cudaError_t launch_prepare_tokens(const int64_t* source, const int64_t* target, SeqDims d, int* src, int* src_len, int* tgt,
+                                  cudaStream_t st) {
+  prepare_tokens_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(source, target, d, src, src_len, tgt);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// decoder, row-local part of one step (one CTA per batch row, 256 threads = one per hidden unit):
+//   (a) t > 0: output projection of step t-1, softmax / log-softmax, greedy max or categorical sampling
+//       (seq2seq_base.py:201-220), (b) t < S: choose the input token of step t (:188-198), dot-product
+//       attention over the encoder outputs with AllenNLP's masked_softmax, attended vector -> operand copy.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) dec_row_kernel(const DecRowArgs a) {
+  __shared__ float sh[kSH], satt[kSH], slg[kSMaxV], ssc[kSMaxT], sp[kSMaxT];
+  __shared__ int s_pred;
+  const SeqDims& d = a.d;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t = a.t;
+  sh[tid] = a.h_dec[(static_cast<size_t>(t) * d.Bp + b) * kSH + tid];
+  __syncthreads();
+
+  if (t > 0) {
+    const int tp = t - 1;
+    for (int v = warp; v < d.Vt; v += 8) {
+      const float4 w0 = *reinterpret_cast<const float4*>(a.out_w + static_cast<size_t>(v) * kSH + lane * 8);
+      const float4 w1 = *reinterpret_cast<const float4*>(a.out_w + static_cast<size_t>(v) * kSH + lane * 8 + 4);
+      const float* h = sh + lane * 8;
+      float acc = w0.x * h[0];
+      acc = fmaf(w0.y, h[1], acc); acc = fmaf(w0.z, h[2], acc); acc = fmaf(w0.w, h[3], acc);
+      acc = fmaf(w1.x, h[4], acc); acc = fmaf(w1.y, h[5], acc); acc = fmaf(w1.z, h[6], acc); acc = fmaf(w1.w, h[7], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) slg[v] = acc + a.out_b[v];
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float m = -INFINITY;
+      for (int v = lane; v < d.Vt; v += 32) m = fmaxf(m, slg[v]);
+      m = warp_max(m);
+      float e[kSMaxV / 32], sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < kSMaxV / 32; ++i) {
+        const int v = lane + 32 * i;
+        e[i] = v < d.Vt ? expf(slg[v] - m) : 0.f;
+        sum += e[i];
+      }
+      sum = warp_sum(sum);
+      int pred;
+      if (!d.sampling) {
+        // torch.max(class_probabilities, 1): largest probability, lowest index on ties (seq2seq_base.py:209)
+        float bv = -1.f; int bi = 0x7fffffff;
+#pragma unroll
+        for (int i = 0; i < kSMaxV / 32; ++i) {
+          const int v = lane + 32 * i;
+          const float p = e[i] / sum;
+          if (v < d.Vt && p > bv) { bv = p; bi = v; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+          if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+        }
+        pred = bi;
+      } else {
+        // never sample @@PADDING@@ / @@UNKNOWN@@ / @start@ (indices 0..2), then torch.multinomial (:212-215)
+        // probabilities go through shared memory (reuse satt) for the sequential inverse-CDF walk
+#pragma unroll
+        for (int i = 0; i < kSMaxV / 32; ++i) {
+          const int v = lane + 32 * i;
+          if (v < d.Vt) satt[v] = v <= kStart ? 0.f : e[i] / sum;
+        }
+        __syncwarp();
+        pred = 0;
+        if (lane == 0) {
+          float total = 0.f;
+          for (int v = 0; v < d.Vt; ++v) total += satt[v];
+          const float u = philox_uniform(a.seed, static_cast<uint32_t>(b), static_cast<uint32_t>(tp)) * total;
+          float cum = 0.f;
+          int last = kEnd;
+          pred = -1;
+          for (int v = 0; v < d.Vt; ++v) {
+            if (satt[v] > 0.f) {
+              last = v;
+              cum += satt[v];
+              if (cum > u) { pred = v; break; }
+            }
+          }
+          if (pred < 0) pred = last;
+        }
+        pred = __shfl_sync(0xffffffffu, pred, 0);
+      }
+      const float lse = m + logf(sum);
+      for (int v = lane; v < d.Vt; v += 32) a.logits[(static_cast<size_t>(tp) * d.B + b) * d.Vt + v] = slg[v];
+      if (lane == 0) {
+        a.lse[static_cast<size_t>(tp) * d.B + b] = lse;
+        a.pred[static_cast<size_t>(tp) * d.B + b] = pred;
+        a.logp[static_cast<size_t>(tp) * d.B + b] = slg[pred] - lse;
+        s_pred = pred;
+      }
+    }
+    __syncthreads();
+  }
+  if (t >= d.S) return;
+
+  // ---- input token of step t: gold token under teacher forcing, else the previous prediction ----------
+  if (tid == 0) {
+    const int tok = d.teacher ? a.tgt[static_cast<size_t>(b) * (d.Tp + 2) + t] : (t == 0 ? kStart : s_pred);
+    a.inp[static_cast<size_t>(t) * d.B + b] = tok;
+  }
+  // ---- dot-product attention ---------------------------------------------------------------------------
+  const float* enc = a.enc + static_cast<size_t>(b) * d.Ts * kSH;
+  const int len = a.src_len[b];
+  for (int s = warp; s < d.Ts; s += 8) {
+    const float4 e0 = *reinterpret_cast<const float4*>(enc + static_cast<size_t>(s) * kSH + lane * 8);
+    const float4 e1 = *reinterpret_cast<const float4*>(enc + static_cast<size_t>(s) * kSH + lane * 8 + 4);
+    const float* h = sh + lane * 8;
+    float acc = e0.x * h[0];
+    acc = fmaf(e0.y, h[1], acc); acc = fmaf(e0.z, h[2], acc); acc = fmaf(e0.w, h[3], acc);
+    acc = fmaf(e1.x, h[4], acc); acc = fmaf(e1.y, h[5], acc); acc = fmaf(e1.z, h[6], acc); acc = fmaf(e1.w, h[7], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) ssc[s] = acc;
+  }
+  __syncthreads();
+  if (warp == 0) {
+    // masked_softmax (allennlp 0.9.0): p = softmax(scores * mask) * mask; p /= (sum(p) + 1e-13)
+    float z[kSMaxT / 32], m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < kSMaxT / 32; ++i) {
+      const int s = lane + 32 * i;
+      z[i] = s < d.Ts ? (s < len ? ssc[s] : 0.f) : -INFINITY;
+      m = fmaxf(m, z[i]);
+    }
+    m = warp_max(m);
+    float u[kSMaxT / 32], Z = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSMaxT / 32; ++i) {
+      const int s = lane + 32 * i;
+      u[i] = s < d.Ts ? expf(z[i] - m) : 0.f;
+      Z += u[i];
+    }
+    Z = warp_sum(Z);
+    float r[kSMaxT / 32], R = 0.f;
+#pragma unroll
+    for (int i = 0; i < kSMaxT / 32; ++i) {
+      const int s = lane + 32 * i;
+      r[i] = s < len ? u[i] / Z : 0.f;
+      R += r[i];
+    }
+    R = warp_sum(R) + 1e-13f;
+#pragma unroll
+    for (int i = 0; i < kSMaxT / 32; ++i) {
+      const int s = lane + 32 * i;
+      if (s < d.Ts) {
+        const float p = r[i] / R;
+        sp[s] = p;
+        a.attn_p[(static_cast<size_t>(t) * d.B + b) * d.Ts + s] = p;
+      }
+    }
+  }
+  __syncthreads();
+  {
+    float acc = 0.f;
+    for (int s = 0; s < len; ++s) acc = fmaf(sp[s], enc[static_cast<size_t>(s) * kSH + tid], acc);
+    satt[tid] = acc;
+  }
+  __syncthreads();
+  if (tid < kSH / 8) store_op8(a.att_op + static_cast<size_t>(t) * a.att_step, a.att_lo, b, tid * 8, kSH, satt + tid * 8, 1.f);
+}
+cudaError_t launch_dec_row(const DecRowArgs& a, cudaStream_t st) {
+  dec_row_kernel<<<a.d.B, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// trimming (seq2seq_base.py:278-293), per-row losses (:235-254, :333-341) and the dlogits coefficients
+// =====================================================================================================
+__global__ void finalize_kernel(const FinalizeArgs a) {
+  const SeqDims& d = a.d;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  int first_end = -1;
+  for (int t = 0; t < d.S; ++t)
+    if (a.pred[static_cast<size_t>(t) * d.B + b] == kEnd) { first_end = t; break; }
+  float lp_sum = 0.f, cnt = 0.f;
+  for (int t = 0; t < d.S; ++t) {
+    const int raw = a.pred[static_cast<size_t>(t) * d.B + b];
+    int keep;
+    if (first_end < 0) keep = raw;                     // no @end@: row unchanged
+    else if (first_end == 0) keep = kPad;              // @end@ first: the whole row becomes padding
+    else keep = t <= first_end ? raw : kPad;
+    a.raw_out[static_cast<size_t>(b) * d.S + t] = raw;
+    a.pred_out[static_cast<size_t>(b) * d.S + t] = keep;
+    const float pm = keep != kPad ? 1.f : 0.f;
+    lp_sum += a.logp[static_cast<size_t>(t) * d.B + b] * pm;
+    cnt += pm;
+  }
+  if (!d.teacher) {
+    a.loss[b] = -(lp_sum / (cnt + 1e-12f));
+    for (int t = 0; t < d.S; ++t) {
+      const int raw = a.pred[static_cast<size_t>(t) * d.B + b];
+      const bool kept = first_end < 0 ? raw != kPad : (first_end > 0 && t <= first_end && raw != kPad);
+      a.coef[static_cast<size_t>(t) * d.B + b] = kept ? 1.f / (cnt + 1e-12f) : 0.f;
+      a.label[static_cast<size_t>(t) * d.B + b] = raw;
+    }
+  } else {
+    // sequence_cross_entropy_with_logits(average=None): sum(nll * mask) / (sum(mask) + 1e-13) per row
+    const int W = d.Tp + 2;
+    float n = 0.f, tot = 0.f;
+    for (int t = 0; t < d.S; ++t) n += a.tgt[static_cast<size_t>(b) * W + t + 1] != kPad ? 1.f : 0.f;
+    for (int t = 0; t < d.S; ++t) {
+      const int lab = a.tgt[static_cast<size_t>(b) * W + t + 1];
+      const float m = lab != kPad ? 1.f : 0.f;
+      const float nll = a.lse[static_cast<size_t>(t) * d.B + b] - a.logits[(static_cast<size_t>(t) * d.B + b) * d.Vt + lab];
+      tot += nll * m;
+      a.coef[static_cast<size_t>(t) * d.B + b] = m / (n + 1e-13f);
+      a.label[static_cast<size_t>(t) * d.B + b] = lab;
+    }
+    a.loss[b] = tot / (n + 1e-13f);
+  }
+  if (a.logits_out)
+    for (int t = 0; t < d.S; ++t)
+      for (int v = 0; v < d.Vt; ++v)
+        a.logits_out[(static_cast<size_t>(b) * d.S + t) * d.Vt + v] = a.logits[(static_cast<size_t>(t) * d.B + b) * d.Vt + v];
+}
+cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
+  finalize_kernel<<<(a.d.B + 63) / 64, 64, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// decoder backward, row-local part (one CTA per row, thread = hidden unit)
+// =====================================================================================================
+__device__ __forceinline__ void cell_bwd(float dh, float dc_in, float i_, float f_, float g_, float o_, float c_cur,
+                                         float c_prev, float (&da)[4], float& dc_prev) {
+  const float tc = tanhf(c_cur);
+  const float do_ = dh * tc;
+  const float dc = dc_in + dh * o_ * (1.f - tc * tc);
+  da[0] = dc * g_ * i_ * (1.f - i_);
+  da[1] = dc * c_prev * f_ * (1.f - f_);
+  da[2] = dc * i_ * (1.f - g_ * g_);
+  da[3] = do_ * o_ * (1.f - o_);
+  dc_prev = dc * f_;
+}
+
+__global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a) {
+  __shared__ float s_datt[kSH], s_dp[kSMaxT], s_ds[kSMaxT], s_p[kSMaxT], s_dl[kSMaxV];
+  __shared__ __align__(16) float s_dg[kSG];
+  const SeqDims& d = a.d;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t = a.t;
+  float dh = a.dh[static_cast<size_t>(b) * kSH + tid];
+
+  if (a.do_attn) {
+    // attention of step ta = t+1 used h_t (slot ta): scores_s = enc_s . h, p = masked_softmax, att = sum p_s enc_s
+    const int ta = t + 1;
+    const float* enc = a.enc + static_cast<size_t>(b) * d.Ts * kSH;
+    float* denc = a.denc + static_cast<size_t>(b) * d.Ts * kSH;
+    const int len = a.src_len[b];
+    const float datt = a.datt[static_cast<size_t>(b) * kSH + tid];
+    const float hq = a.h_dec[(static_cast<size_t>(ta) * d.Bp + b) * kSH + tid];
+    s_datt[tid] = datt;
+    if (tid < d.Ts) s_p[tid] = a.attn_p[(static_cast<size_t>(ta) * d.B + b) * d.Ts + tid];
+    __syncthreads();
+    for (int s = warp; s < len; s += 8) {
+      const float4 e0 = *reinterpret_cast<const float4*>(enc + static_cast<size_t>(s) * kSH + lane * 8);
+      const float4 e1 = *reinterpret_cast<const float4*>(enc + static_cast<size_t>(s) * kSH + lane * 8 + 4);
+      const float* g = s_datt + lane * 8;
+      float acc = e0.x * g[0];
+      acc = fmaf(e0.y, g[1], acc); acc = fmaf(e0.z, g[2], acc); acc = fmaf(e0.w, g[3], acc);
+      acc = fmaf(e1.x, g[4], acc); acc = fmaf(e1.y, g[5], acc); acc = fmaf(e1.z, g[6], acc); acc = fmaf(e1.w, g[7], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) s_dp[s] = acc;
+    }
+    __syncthreads();
+    if (warp == 0) {
+      float G = 0.f;
+      for (int s = lane; s < len; s += 32) G += s_p[s] * s_dp[s];
+      G = warp_sum(G);
+      for (int s = lane; s < d.Ts; s += 32) s_ds[s] = s < len ? s_p[s] * (s_dp[s] - G) : 0.f;
+    }
+    __syncthreads();
+    float acc = 0.f;
+    for (int s = 0; s < len; ++s) {
+      const float e = enc[static_cast<size_t>(s) * kSH + tid];
+      acc = fmaf(s_ds[s], e, acc);
+      denc[static_cast<size_t>(s) * kSH + tid] += s_p[s] * datt + s_ds[s] * hq;
+    }
+    dh += acc;
+  }
+  if (t < 0) {
+    a.dh[static_cast<size_t>(b) * kSH + tid] = dh;
+    return;
+  }
+
+  // ---- output projection + (log-)softmax backward of step t ---------------------------------------------
+  const float cf = a.grad_loss[b] * a.coef[static_cast<size_t>(t) * d.B + b];
+  if (tid < d.Vt) {
+    const float lg = a.logits[(static_cast<size_t>(t) * d.B + b) * d.Vt + tid];
+    const float p = expf(lg - a.lse[static_cast<size_t>(t) * d.B + b]);
+    const float dl = cf * (p - (tid == a.label[static_cast<size_t>(t) * d.B + b] ? 1.f : 0.f));
+    s_dl[tid] = dl;
+    a.dlogits[(static_cast<size_t>(t) * d.Bp + b) * d.Vt + tid] = dl;
+  }
+  __syncthreads();
+  if (cf != 0.f) {
+    float acc = 0.f;
+    for (int v = 0; v < d.Vt; ++v) acc = fmaf(a.out_w[static_cast<size_t>(v) * kSH + tid], s_dl[v], acc);
+    dh += acc;
+  }
+  // ---- LSTM cell backward ---------------------------------------------------------------------------------
+  const float* gt = a.gates + (static_cast<size_t>(t) * d.Bp + b) * kSG;
+  float da[4], dc_prev;
+  cell_bwd(dh, a.dc[static_cast<size_t>(b) * kSH + tid], gt[tid], gt[kSH + tid], gt[2 * kSH + tid], gt[3 * kSH + tid],
+           a.c_dec[(static_cast<size_t>(t + 1) * d.Bp + b) * kSH + tid], a.c_dec[(static_cast<size_t>(t) * d.Bp + b) * kSH + tid], da,
+           dc_prev);
+  a.dc[static_cast<size_t>(b) * kSH + tid] = dc_prev;
+  s_dg[tid] = da[0]; s_dg[kSH + tid] = da[1]; s_dg[2 * kSH + tid] = da[2]; s_dg[3 * kSH + tid] = da[3];
+  __syncthreads();
+  if (tid < kSG / 8) store_op8(a.dg_op + static_cast<size_t>(t) * a.dg_step, a.dg_lo, b, tid * 8, kSG, s_dg + tid * 8, a.scale[0]);
+}
+cudaError_t launch_dec_bwd_row(const DecBwdRowArgs& a, cudaStream_t st) {
+  dec_bwd_row_kernel<<<a.d.B, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// encoder: LSTM cell backward of one (layer, step); rows beyond their length carry dh / dc through unchanged
+__global__ void __launch_bounds__(256) enc_cell_bwd_kernel(const EncCellBwdArgs a) {
+  __shared__ __align__(16) float s_dg[kSG];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const bool valid = a.t < a.src_len[b];
+  float da[4] = {0.f, 0.f, 0.f, 0.f};
+  if (valid) {
+    float dh = a.dh[static_cast<size_t>(b) * kSH + tid];
+    if (a.dext) dh += a.dext[static_cast<size_t>(b) * a.dext_stride + tid];
+    const float* gt = a.gates + static_cast<size_t>(b) * kSG;
+    float dc_prev;
+    cell_bwd(dh, a.dc[static_cast<size_t>(b) * kSH + tid], gt[tid], gt[kSH + tid], gt[2 * kSH + tid], gt[3 * kSH + tid],
+             a.c_cur[static_cast<size_t>(b) * kSH + tid], a.c_prev[static_cast<size_t>(b) * kSH + tid], da, dc_prev);
+    a.dc[static_cast<size_t>(b) * kSH + tid] = dc_prev;
+  }
+  s_dg[tid] = da[0]; s_dg[kSH + tid] = da[1]; s_dg[2 * kSH + tid] = da[2]; s_dg[3 * kSH + tid] = da[3];
+  __syncthreads();
+  if (tid < kSG / 8) store_op8(a.dg_op, a.dg_lo, b, tid * 8, kSG, s_dg + tid * 8, a.scale[0]);
+}
+cudaError_t launch_enc_cell_bwd(const EncCellBwdArgs& a, cudaStream_t st) {
+  enc_cell_bwd_kernel<<<a.B, 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// table gradient: dP[v][g] += scale[1] * sum over (t, b) with token v of dG[t][b][g]
+// CTA = 32 gate columns x a slice of the time range; thread = (batch row, 8-column group): 16-byte loads that
+// are contiguous across a warp's 32 rows; per-token partial sums in shared memory.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) table_grad_kernel(const TableGradArgs a) {
+  __shared__ float acc[kSMaxV * 32];
+  const int tid = threadIdx.x;
+  for (int i = tid; i < a.V * 32; i += 256) acc[i] = 0.f;
+  __syncthreads();
+  const int g0 = blockIdx.x * 32;
+  const int t0 = static_cast<int>((static_cast<long long>(a.T) * blockIdx.y) / gridDim.y);
+  const int t1 = static_cast<int>((static_cast<long long>(a.T) * (blockIdx.y + 1)) / gridDim.y);
+  const int grp = tid >> 6, r = tid & 63;   // 4 column groups x 64 rows per pass
+  for (int t = t0; t < t1; ++t) {
+    const __half* dg = a.dg + static_cast<size_t>(t) * a.dg_step;
+    for (int b = r; b < a.B; b += 64) {
+      const int v = a.tok ? a.tok[static_cast<size_t>(t) * a.tok_step + static_cast<size_t>(b) * a.tok_stride] : 0;
+      const size_t off = op_off(b, g0 + grp * 8, kSG);
+      const uint4 hi = *reinterpret_cast<const uint4*>(dg + off);
+      const uint4 lo = *reinterpret_cast<const uint4*>(dg + a.dg_lo + off);
+      const __half2* h2 = reinterpret_cast<const __half2*>(&hi);
+      const __half2* l2 = reinterpret_cast<const __half2*>(&lo);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 hf = __half22float2(h2[e]), lf = __half22float2(l2[e]);
+        const float x0 = hf.x + lf.x, x1 = hf.y + lf.y;
+        if (x0 != 0.f) atomicAdd(&acc[v * 32 + grp * 8 + 2 * e], x0);
+        if (x1 != 0.f) atomicAdd(&acc[v * 32 + grp * 8 + 2 * e + 1], x1);
+      }
+    }
+  }
+  __syncthreads();
+  const float unscale = a.scale[1];
+  for (int i = tid; i < a.V * 32; i += 256) {
+    const float x = acc[i];
+    if (x != 0.f) atomicAdd(a.dP + static_cast<size_t>(i >> 5) * kSG + g0 + (i & 31), x * unscale);
+  }
+}
+cudaError_t launch_table_grad(const TableGradArgs& a, cudaStream_t st) {
+  if (a.T <= 0) return cudaSuccess;
+  const int split = a.T < 8 ? a.T : 8;
+  table_grad_kernel<<<dim3(kSG / 32, split), 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+__global__ void bias_from_table_kernel(const float* __restrict__ dP, int V, float* __restrict__ db0, float* __restrict__ db1) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= kSG) return;
+  float s = 0.f;
+  for (int v = 0; v < V; ++v) s += dP[static_cast<size_t>(v) * kSG + g];
+  db0[g] += s;
+  db1[g] += s;
+}
+cudaError_t launch_bias_from_table(const float* dP, int V, float* db0, float* db1, cudaStream_t st) {
+  bias_from_table_kernel<<<kSG / 256, 256, 0, st>>>(dP, V, db0, db1);
+  return cudaGetLastError();
+}
+
+__global__ void seq_loss_scale_kernel(const float* __restrict__ g, int B, float* __restrict__ scale) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (int i = threadIdx.x; i < B; i += blockDim.x) m = fmaxf(m, fabsf(g[i]));
+  m = warp_max(m);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < static_cast<int>(blockDim.x >> 5); ++i) m = fmaxf(m, red[i]);
+    float s = 1.f;
+    if (m > 0.f && isfinite(m)) {
+      int e;
+      frexpf(m, &e);            // m = f * 2^e, f in [0.5, 1)
+      int k = 10 - e;           // m * 2^k in [2^9, 2^10)
+      k = k > 60 ? 60 : (k < -60 ? -60 : k);
+      s = ldexpf(1.f, k);
+    }
+    scale[0] = s;
+    scale[1] = 1.f / s;
+    scale[2] = 1.f;
+  }
+}
+cudaError_t launch_seq_loss_scale(const float* grad_loss, int B, float* scale, cudaStream_t st) {
+  seq_loss_scale_kernel<<<1, 256, 0, st>>>(grad_loss, B, scale);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// weight packing: fp32 parameters -> split fp16 tiles [n/64][k/8][64][8] (hi, then lo)
+// =====================================================================================================
+__global__ void __launch_bounds__(256) pack_seq_kernel(const PackJobs jobs, const float* __restrict__ params,
+                                                       __half* __restrict__ packed) {
+  const PackJob& j = jobs.j[blockIdx.y];
+  const int groups = j.N * (j.K >> 3);
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= groups) return;
+  // idx enumerates (n tile, k group, row) in storage order so that the 16-byte stores coalesce
+  const int r = idx & 63, kg = (idx >> 6) % (j.K >> 3), nt = (idx >> 6) / (j.K >> 3);
+  const int n = nt * 64 + r;
+  __half hi[8], lo[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = kg * 8 + e;
+    float v;
+    if (j.mode == 0) {
+      const int gr = (r >> 4) * kSH + nt * 16 + (r & 15);
+      v = k < j.split ? params[j.src0 + static_cast<int64_t>(gr) * j.ld0 + k]
+                      : params[j.src1 + static_cast<int64_t>(gr) * j.ld1 + (k - j.split)];
+    } else {
+      v = n < j.split ? params[j.src0 + static_cast<int64_t>(k) * j.ld0 + n]
+                      : params[j.src1 + static_cast<int64_t>(k) * j.ld1 + (n - j.split)];
+    }
+    split_f16(v, hi[e], lo[e]);
+  }
+  const size_t off = j.dst + wp_off(n, kg * 8, j.K);
+  *reinterpret_cast<uint4*>(packed + off) = pack8h(hi);
+  *reinterpret_cast<uint4*>(packed + off + static_cast<size_t>(j.N) * j.K) = pack8h(lo);
+}
+cudaError_t launch_pack_seq(const PackJobs& jobs, int n_jobs, const float* params, __half* packed, cudaStream_t st) {
+  // the largest job is 1024 x 512: 65536 groups of 8
+  pack_seq_kernel<<<dim3(256, n_jobs), 256, 0, st>>>(jobs, params, packed);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// small strided fp32 GEMM (tables, embedding / projection gradients): 32x32 tile per CTA, split-K over
+// blockIdx.z with atomics when gridDim.z > 1 (C must then be an accumulation target)
+// =====================================================================================================
+__global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemm g) {
+  __shared__ float sa[32][33], sb[32][33];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int m0 = blockIdx.y * 32, n0 = blockIdx.x * 32;
+  const int kz = gridDim.z;
+  const int k_lo = static_cast<int>((static_cast<long long>(g.K) * blockIdx.z) / kz);
+  const int k_hi = static_cast<int>((static_cast<long long>(g.K) * (blockIdx.z + 1)) / kz);
+  float acc[2][2] = {{0.f, 0.f}, {0.f, 0.f}};
+  for (int k0 = k_lo; k0 < k_hi; k0 += 32) {
+    for (int i = threadIdx.x; i < 1024; i += 256) {
+      const int r = i >> 5, c = i & 31;  // r: m (or n) inside the tile, c: k
+      const int k = k0 + c;
+      sa[r][c] = (m0 + r < g.M && k < k_hi) ? g.A[static_cast<int64_t>(m0 + r) * g.sam + static_cast<int64_t>(k) * g.sak] : 0.f;
+      sb[r][c] = (n0 + r < g.N && k < k_hi) ? g.B[static_cast<int64_t>(k) * g.sbk + static_cast<int64_t>(n0 + r) * g.sbn] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int c = 0; c < 32; ++c) {
+      const float a0 = sa[ty][c], a1 = sa[ty + 16][c], b0 = sb[tx][c], b1 = sb[tx + 16][c];
+      acc[0][0] = fmaf(a0, b0, acc[0][0]); acc[0][1] = fmaf(a0, b1, acc[0][1]);
+      acc[1][0] = fmaf(a1, b0, acc[1][0]); acc[1][1] = fmaf(a1, b1, acc[1][1]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int jn = 0; jn < 2; ++jn) {
+      const int m = m0 + ty + 16 * i, n = n0 + tx + 16 * jn;
+      if (m >= g.M || n >= g.N) continue;
+      float v = acc[i][jn] * g.alpha;
+      if (blockIdx.z == 0) {
+        if (g.bias0) v += g.bias0[n];
+        if (g.bias1) v += g.bias1[n];
+      }
+      float* c = g.C + static_cast<int64_t>(m) * g.ldc + n;
+      if (kz > 1) atomicAdd(c, v);
+      else if (g.accumulate) *c += v;
+      else *c = v;
+    }
+}
+cudaError_t launch_simt_gemm(const SimtGemm& g, cudaStream_t st) {
+  int kz = 1;
+  if (g.K >= 2048 && g.accumulate) kz = 16;
+  simt_gemm_kernel<<<dim3((g.N + 31) / 32, (g.M + 31) / 32, kz), 256, 0, st>>>(g);
+  return cudaGetLastError();
+}
+
+}  // namespace pnmn

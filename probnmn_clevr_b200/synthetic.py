@@ -171,3 +171,30 @@ def make_questions(batch: int, vocab_size: int, seed: int = 0, max_length: int =
         n = int(rng.integers(min_length, max_length + 1))
         out[b, :n] = rng.integers(len(SPECIAL_TOKENS), vocab_size, size=n)
     return torch.from_numpy(out)
+
+
+def make_seq2seq_state_dict(vocab_src: int = 93, vocab_tgt: int = 44, hidden: int = 256, seed: int = 0,
+                            gain: float = 1.0) -> "OrderedDict[str, torch.Tensor]":
+    """Reference-shaped ``ProgramGenerator`` / ``QuestionReconstructor`` parameters (AllenNLP ``SimpleSeq2Seq`` key
+    names) with PyTorch's default initialisations; ``gain`` > 1 scales the output projection
+    so that token decisions have realistic margins."""
+    g = torch.Generator().manual_seed(7000 + seed)
+    k = 1.0 / hidden ** 0.5
+    u = lambda *shape: (torch.rand(*shape, generator=g) * 2 - 1) * k
+    sd = OrderedDict()
+    emb = torch.randn(vocab_src, hidden, generator=g) * (2.0 / (vocab_src + hidden)) ** 0.5
+    emb[0] = 0  # padding_index
+    sd["_source_embedder.token_embedder_tokens.weight"] = emb
+    for layer in range(2):
+        sd[f"_encoder._module.weight_ih_l{layer}"] = u(4 * hidden, hidden)
+        sd[f"_encoder._module.weight_hh_l{layer}"] = u(4 * hidden, hidden)
+        sd[f"_encoder._module.bias_ih_l{layer}"] = u(4 * hidden)
+        sd[f"_encoder._module.bias_hh_l{layer}"] = u(4 * hidden)
+    sd["_target_embedder.weight"] = torch.randn(vocab_tgt, hidden, generator=g) * (2.0 / (vocab_tgt + hidden)) ** 0.5
+    sd["_decoder_cell.weight_ih"] = u(4 * hidden, 2 * hidden)
+    sd["_decoder_cell.weight_hh"] = u(4 * hidden, hidden)
+    sd["_decoder_cell.bias_ih"] = u(4 * hidden)
+    sd["_decoder_cell.bias_hh"] = u(4 * hidden)
+    sd["_output_projection_layer.weight"] = u(vocab_tgt, hidden) * gain
+    sd["_output_projection_layer.bias"] = u(vocab_tgt) * gain
+    return sd

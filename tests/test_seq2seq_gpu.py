@@ -1,0 +1,189 @@
+"""GPU parity of the CUDA ProgramGenerator (pnmn_pg_forward / pnmn_pg_backward through the nn.Module drop-in) against
+the CPU oracle ``oracle/seq2seq_oracle.py`` on the same seeded inputs.
+
+The oracle's AllenNLP-resident arithmetic is PARITY UNPINNED (allennlp==0.9.0 is absent; see the oracle's header);
+its LSTM / LSTMCell restatement is cross-checked against torch.nn.LSTM (packed) and nn.LSTMCell in
+tests/test_seq2seq_oracle.py.  Tolerances: logits / losses / encoder outputs 1e-3 relative (BASELINE.json north_star;
+the split-fp16 GEMMs land around 1e-6), greedy tokens bit-exact, gradients 1e-3 relative in the global L2 sense.
+"""
+import ctypes
+import os
+
+import pytest
+import torch
+
+from oracle import seq2seq_oracle as O
+from probnmn_clevr_b200 import _lib as L
+from probnmn_clevr_b200.seq2seq import ProgramGenerator, QuestionReconstructor
+from probnmn_clevr_b200.synthetic import ProgramSampler, make_questions, make_seq2seq_state_dict
+from probnmn_clevr_b200.vocabulary import Vocabulary
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12))
+
+
+@pytest.fixture(scope="module")
+def vocab():
+    return Vocabulary.clevr()
+
+
+def build(vocab, seed=0, gain=1.0, cls=ProgramGenerator):
+    vs = vocab.get_vocab_size("questions" if cls is ProgramGenerator else "programs")
+    vt = vocab.get_vocab_size("programs" if cls is ProgramGenerator else "questions")
+    sd = make_seq2seq_state_dict(vs, vt, seed=seed, gain=gain)
+    m = cls(vocab)
+    m.load_state_dict(sd)
+    m = m.cuda()
+    m.return_logits = True
+    return m, sd
+
+
+def inputs(vocab, B, seed, tq=40, tp=26):
+    q = make_questions(B, vocab.get_vocab_size("questions"), seed=seed, max_length=tq)
+    p = ProgramSampler(vocab, seed=seed).sample(B, tp)
+    return q, p
+
+
+def workspace_view(model, ws_key_args, ws):
+    d = (ctypes.c_int64 * 12)()
+    L.check(L.lib().pnmn_pg_debug_layout(ctypes.byref(model._desc), *ws_key_args, d))
+    return list(d)
+
+
+@pytest.mark.parametrize("B", [5, 130])
+def test_encoder_outputs_and_teacher_forced_logits(vocab, B):
+    """Teacher forcing: every step's logits depend only on gold inputs, so the whole (B, steps, V) tensor is compared."""
+    model, sd = build(vocab, 0)
+    model.eval()
+    q, p = inputs(vocab, B, 1)
+    with torch.no_grad():
+        out = model(q.cuda(), p.cuda(), decoding_strategy="greedy")
+        ref = O.seq2seq_forward(sd, q, p, decoding_strategy="greedy")
+    assert out["logits"].shape == ref["logits"].shape
+    err = rel(out["logits"].cpu(), ref["logits"])
+    print(f"B={B}: teacher-forced logits rel err {err:.2e}; loss rel err {rel(out['loss'].cpu(), ref['loss']):.2e}")
+    assert err < 1e-3
+    assert rel(out["loss"].cpu(), ref["loss"]) < 1e-3
+    agree = (out["raw_predictions"].cpu() == ref["raw_predictions"]).float().mean().item()
+    print(f"   greedy per-step argmax agreement {agree:.4f}")
+    assert torch.equal(out["predictions"].cpu(), ref["predictions"])
+
+
+def test_free_running_greedy_tokens_bit_exact(vocab):
+    """No targets: 26 autoregressive steps; tokens must match the fp32 reference path exactly (north_star)."""
+    model, sd = build(vocab, 3, gain=4.0)
+    model.eval()
+    q, _ = inputs(vocab, 64, 5)
+    with torch.no_grad():
+        out = model(q.cuda(), decoding_strategy="greedy")
+        ref = O.seq2seq_forward(sd, q, None, decoding_strategy="greedy", max_decoding_steps=26)
+    assert torch.equal(out["raw_predictions"].cpu(), ref["raw_predictions"])
+    assert torch.equal(out["predictions"].cpu(), ref["predictions"])
+    assert rel(out["loss"].cpu(), ref["loss"]) < 1e-3
+    assert rel(out["logits"].cpu(), ref["logits"]) < 1e-3
+    toks = model.decode({"predictions": out["predictions"]})["predicted_tokens"]
+    assert len(toks) == 64 and all(isinstance(t, list) for t in toks)
+
+
+def test_sampling_statistics_and_replay(vocab):
+    """Sampled tokens never include pad/unk/start; replaying them through the oracle reproduces log-probs and loss."""
+    model, sd = build(vocab, 4)
+    model.train()
+    q, _ = inputs(vocab, 96, 6)
+    out = model(q.cuda(), decoding_strategy="sampling")
+    raw = out["raw_predictions"].cpu()
+    assert int((raw <= 2).sum()) == 0
+    ref = O.seq2seq_forward(sd, q, None, decoding_strategy="sampling", max_decoding_steps=26, forced_choices=raw)
+    assert torch.equal(out["predictions"].cpu(), ref["predictions"])
+    assert rel(out["loss"].detach().cpu(), ref["loss"]) < 1e-3
+    # two calls draw different samples; the empirical first-token distribution follows the softmax
+    out2 = model(q.cuda(), decoding_strategy="sampling")
+    assert not torch.equal(out2["raw_predictions"].cpu(), raw)
+    big_q = q[:1].repeat(4096, 1)
+    with torch.no_grad():
+        s = model(big_q.cuda(), decoding_strategy="sampling")
+    p = torch.softmax(s["logits"][0, 0].cpu(), -1)
+    p[:3] = 0
+    p = p / p.sum()
+    freq = torch.bincount(s["raw_predictions"][:, 0].cpu(), minlength=p.numel()).float() / 4096
+    assert float((freq - p).abs().max()) < 0.03
+
+
+def grads_of(model):
+    return {n: p.grad.detach().cpu().clone() for n, p in model.named_parameters()}
+
+
+@pytest.mark.parametrize("mode", ["teacher", "sampled"])
+def test_backward_matches_oracle_autograd(vocab, mode):
+    B = 37
+    model, sd = build(vocab, 2)
+    model.train()
+    q, p = inputs(vocab, B, 8)
+    w = torch.linspace(0.5, 1.5, B)  # non-uniform upstream gradient
+    if mode == "teacher":
+        out = model(q.cuda(), p.cuda(), decoding_strategy="sampling")
+    else:
+        out = model(q.cuda(), decoding_strategy="sampling")
+    (out["loss"] * w.cuda()).sum().backward()
+    got = grads_of(model)
+    sdr = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    if mode == "teacher":
+        ref = O.seq2seq_forward(sdr, q, p, decoding_strategy="greedy")
+    else:
+        ref = O.seq2seq_forward(sdr, q, None, max_decoding_steps=26, forced_choices=out["raw_predictions"].cpu())
+    assert rel(out["loss"].detach().cpu(), ref["loss"].detach()) < 1e-3
+    (ref["loss"] * w).sum().backward()
+    num = den = 0.0
+    for k, v in sdr.items():
+        g = v.grad if v.grad is not None else torch.zeros_like(v)
+        e = float((got[k] - g).norm() / (g.norm() + 1e-12))
+        print(f"   {mode} {k:48s} |g| {float(g.norm()):.3e} rel err {e:.2e}")
+        num += float((got[k] - g).norm() ** 2)
+        den += float(g.norm() ** 2)
+        assert e < 2e-3, k
+    assert (num / den) ** 0.5 < 1e-3
+
+
+def test_question_reconstructor_same_kernels(vocab):
+    """Programs -> questions (V_tgt = 93, 45 steps): next-1 row of SURVEY.md §8f, same kernels."""
+    model, sd = build(vocab, 5, cls=QuestionReconstructor)
+    model.eval()
+    q, p = inputs(vocab, 20, 9)
+    with torch.no_grad():
+        out = model(p.cuda(), q.cuda(), decoding_strategy="greedy")
+        ref = O.seq2seq_forward(sd, p, q, decoding_strategy="greedy")
+    assert rel(out["logits"].cpu(), ref["logits"]) < 1e-3
+    assert rel(out["loss"].cpu(), ref["loss"]) < 1e-3
+    assert set(model.get_metrics()) == {"BLEU", "perplexity", "sequence_accuracy", "word_error_rate"}
+
+
+def test_edge_cases(vocab):
+    """Batch of one, shortest / longest questions, an all-padding question, a row whose first token is @end@."""
+    model, sd = build(vocab, 6)
+    model.eval()
+    q = torch.zeros(3, 45, dtype=torch.int64)
+    q[0, :45] = torch.arange(45) % 80 + 4
+    q[1, 0] = 7
+    # q[2] is all padding: source becomes a lone @end@
+    with torch.no_grad():
+        out = model(q.cuda(), decoding_strategy="greedy")
+        ref = O.seq2seq_forward(sd, q, None, decoding_strategy="greedy", max_decoding_steps=26)
+        assert torch.equal(out["predictions"].cpu(), ref["predictions"])
+        assert rel(out["loss"].cpu(), ref["loss"]) < 1e-3
+        one = model(q[:1].cuda(), decoding_strategy="greedy")
+    assert torch.equal(one["predictions"].cpu(), ref["predictions"][:1])
+    # trimming: force @end@ as the very first prediction through the output bias
+    sd2 = {k: v.clone() for k, v in sd.items()}
+    sd2["_output_projection_layer.bias"][3] = 50.0
+    model.load_state_dict(sd2)
+    with torch.no_grad():
+        out = model(q.cuda(), decoding_strategy="greedy")
+    assert int(out["predictions"].abs().sum()) == 0 and int(out["raw_predictions"][:, 0].min()) == 3
+
+
+@pytest.mark.skipif(os.environ.get("PNMN_PG_SIMT") is not None, reason="already the CUDA-core twin")
+def test_reports_native_library_loaded():
+    assert os.path.exists(L.LIB_PATH)
