@@ -41,6 +41,7 @@ def parse():
     ap.add_argument("--length", type=int, default=40)
     ap.add_argument("--cpu-sample", type=int, default=16, help="rows of the workload the CPU baseline runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary ProgramGenerator / joint-step legs")
     return ap.parse_args()
 
 
@@ -109,22 +110,49 @@ def run_reference(args):
 # clocks
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler(threading.Thread):
+    """SM clock / power / throttle reasons sampled DURING the timed region through NVML (nvidia_ml_py; a few hundred
+    samples per second), falling back to one nvidia-smi query per 100 ms."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.samples, self.stop_flag = index, [], False
+        self.index, self.samples, self.stop_flag, self.source = index, [], False, "nvidia-smi"
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml, self.source = pynvml, "nvml"
+        except Exception:
+            self.nvml = None
 
     def run(self):
         while not self.stop_flag:
             try:
+                if self.nvml is not None:
+                    n = self.nvml
+                    mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+                    try:
+                        mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                    except Exception:
+                        mask = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    watts = n.nvmlDeviceGetPowerUsage(self.handle) / 1e3
+                    self.samples.append((mhz, self.max_mhz, watts, mask))
+                    time.sleep(0.004)
+                    continue
                 out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
                                       "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
                 f = [x.strip() for x in out.strip().split(",")]
                 if len(f) >= 7:
-                    self.samples.append(f)
+                    mask = sum(bit for (name, bit), v in zip(self.BITS.items(), f[3:7]) if v.lower().startswith("active"))
+                    self.samples.append((float(f[0]), float(f[1]), float(f[2]), mask))
             except Exception:
                 pass
             time.sleep(0.1)
@@ -132,11 +160,10 @@ class ClockSampler(threading.Thread):
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[0]) for s in self.samples)
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(s[3 + i].lower().startswith("active") for s in self.samples)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][1]), "reasons": reasons,
-                "samples": len(sm), "power_w_max": max(float(s[2]) for s in self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [name for name, bit in self.BITS.items() if any(s[3] & bit for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons,
+                "samples": len(sm), "power_w_max": max(s[2] for s in self.samples), "source": self.source}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -245,6 +272,7 @@ def run_ours(args):
     conv_flops = stats[8] + stats[10]  # forward + dgrad FLOPs executed by conv_tc<2,2> per step
     conv_ms = kernel_ms["conv_tc<2,2>"]
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    extras = {} if args.no_extras else extra_legs(args, model, vocab, dev, resident, timed)
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -256,22 +284,26 @@ def run_ours(args):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "tf32", "data": "synthetic", "config": workload_config(args),
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(args),
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int((stats[3] + stats[4] + 5) * args.steps),
         "roofline": {
-            "bound": "tensor", "kernel": "conv_tc_kernel<2,2> (tcgen05 kind::tf32 shift-GEMM conv: forward + dgrad)",
+            "bound": "tensor", "kernel": "exec_kernel (persistent tcgen05 kind::f16 shift-GEMM executor: forward + dgrad launches)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src,
-            "note": "operands are tf32 (half the bf16 tensor rate); peak is the measured bf16 cuBLAS figure",
+            "note": "fp16 operands, fp32 accumulation in TMEM; peak is the bf16 cuBLAS figure; the kernel's time includes "
+                    "its CUDA-core tasks and dependency waits",
             "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms, "launches_per_step": pln[1] / prof_steps,
-            "traffic": None,
+            "traffic": traffic_per_launch(),
         },
         "kernel_ms_per_step": kernel_ms, "host_ms_per_step": host_ms_per_step,
         "plan": {"valid_programs": stats[0], "conv3x3_instances": stats[1], "module_tokens": stats[2],
                  "forward_launches": stats[3], "backward_launches": stats[4], "wgrad_flops": stats[12]},
+        "classifier_math": {"split": "split bf16 x2 (one cuBLAS tensor-core GEMM over the 3x contraction, fp32 accumulate)",
+                            "tf32": "tf32 (cuBLAS/cuDNN)", "ieee": "ieee fp32 (cuBLAS/cuDNN)"}[model.classifier_math],
     }
+    line.update(extras)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count())
         rows = args.cpu_sample
@@ -288,6 +320,64 @@ def run_ours(args):
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum of exec_kernel per launch, from the committed ncu --set full capture
+    of the same workload (profiles/<round>_traffic.json, written by scripts/summarize_profiles.py); None if absent."""
+    try:
+        files = sorted(f for f in os.listdir(os.path.join(ROOT, "profiles")) if f.endswith("_traffic.json"))
+        return json.load(open(os.path.join(ROOT, "profiles", files[-1])))["exec_kernel_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def extra_legs(args, nmn, vocab, dev, resident, timed):
+    """Secondary numbers (not the headline): BASELINE.json configs[2] (ProgramGenerator, question_coding mix) and
+    configs[3] (joint step: ProgramGenerator sampling + NMN + REINFORCE-weighted objective) at the same batch."""
+    from probnmn_clevr_b200.seq2seq import ProgramGenerator
+    from probnmn_clevr_b200.synthetic import ProgramSampler, make_questions, make_seq2seq_state_dict
+    B = args.batch
+    pg = ProgramGenerator(vocab)
+    pg.load_state_dict(make_seq2seq_state_dict(vocab.get_vocab_size("questions"), vocab.get_vocab_size("programs"), seed=0))
+    pg = pg.to(dev).train()
+    questions = make_questions(B, vocab.get_vocab_size("questions"), seed=0, max_length=40).to(dev)
+    gt_programs = ProgramSampler(vocab, seed=0).sample(B, 26).to(dev)
+    half = B // 2
+
+    def pg_step(i):
+        # question_coding "ours" mix (question_coding_trainer.py:120-152): supervised half teacher-forced, rest sampled
+        pg.zero_grad(set_to_none=True)
+        sup = pg(questions[:half], gt_programs[:half], decoding_strategy="sampling")
+        uns = pg(questions[half:], decoding_strategy="sampling")
+        (sup["loss"].mean() + uns["loss"].mean()).backward()
+
+    def joint_step(i):
+        # modules/elbo.py:230-275 restricted to the hot path: sample programs, answer with the NMN, REINFORCE the
+        # generator with the (detached) answer log-likelihood.  A random-init generator samples mostly invalid
+        # programs, so the NMN runs the batch's ground-truth-style programs (what a trained generator emits).
+        feats, programs, answers = resident[i % 2]
+        pg.zero_grad(set_to_none=True)
+        nmn.zero_grad(set_to_none=True)
+        gen = pg(questions, decoding_strategy="sampling")
+        out = nmn(feats, programs, answers)
+        reward = (-out["loss"]).detach()
+        objective = out["loss"].mean() + (gen["loss"] * (reward - reward.mean())).mean()
+        objective.backward()
+
+    res = {}
+    for name, fn in (("pg", pg_step), ("joint", joint_step)):
+        for i in range(3):
+            fn(i)
+        steps = max(3, min(args.steps, 10))
+        ms = timed(fn, steps)
+        world = int(os.environ.get("WORLD_SIZE", "1"))
+        res[name] = {"value": world * B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps}
+    res["pg"]["workload"] = ("question_coding_ours.yml mix at batch %d: %d rows teacher-forced + %d rows sampled (26 steps), "
+                             "questions <= 40 tokens, fwd+bwd (BASELINE.json configs[2])" % (B, half, B - half))
+    res["joint"]["workload"] = ("joint step at batch %d: ProgramGenerator sampling fwd+bwd + NMN fwd+bwd on GT-style programs + "
+                                "REINFORCE-weighted objective (BASELINE.json configs[3] restricted to the hot path)" % B)
+    return res
 
 
 if __name__ == "__main__":

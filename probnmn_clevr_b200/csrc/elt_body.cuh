@@ -128,7 +128,7 @@ __device__ __forceinline__ void elt_task_body(const EltTask& t, const int tid, E
           acc0 += g0.x * f0.x + g0.y * f0.y + g0.z * f0.z + g0.w * f0.w;
           acc1 += g1.x * f1.x + g1.y * f1.y + g1.z * f1.z + g1.w * f1.w;
         }
-        if (n_parts > 1) atomicAdd(t.o + s, acc0 + acc1);
+        if (n_parts > 1) red_add_f32(t.o + s, acc0 + acc1);
         else t.o[s] += acc0 + acc1;
       }
     } break;
@@ -184,7 +184,7 @@ __device__ __forceinline__ void elt_task_body(const EltTask& t, const int tid, E
       const float sum_g = elt_block_sum(gp, sm.red, tid);
       const float sum_ga = elt_block_sum(tid < 196 ? gp * t.b[s] : 0.f, sm.red, tid);
       const float unscale = t.scale[1];
-      if (tid == 0) { atomicAdd(t.dw2, sum_g * unscale); atomicAdd(t.dw + 128, sum_ga * unscale); }
+      if (tid == 0) { red_add_f32(t.dw2, sum_g * unscale); red_add_f32(t.dw + 128, sum_ga * unscale); }
       ELT_SYNC();
       {
         // thread = (plane kc, part): 4 channels, pixels part, part+8, ...
@@ -210,8 +210,8 @@ __device__ __forceinline__ void elt_task_body(const EltTask& t, const int tid, E
         }
         ELT_SYNC();  // all dfeat writes of slot `is` are done before the extra term is added
         if (part == 0) {
-          atomicAdd(t.dw + kc * 4 + 0, q.x * v.x * unscale); atomicAdd(t.dw + kc * 4 + 1, q.y * v.y * unscale);
-          atomicAdd(t.dw + kc * 4 + 2, q.z * v.z * unscale); atomicAdd(t.dw + kc * 4 + 3, q.w * v.w * unscale);
+          red_add_f32(t.dw + kc * 4 + 0, q.x * v.x * unscale); red_add_f32(t.dw + kc * 4 + 1, q.y * v.y * unscale);
+          red_add_f32(t.dw + kc * 4 + 2, q.z * v.z * unscale); red_add_f32(t.dw + kc * 4 + 3, q.w * v.w * unscale);
           float* dp = t.o2 + (kc * 256 + is) * 4;
           float4 d = ld4(dp);
           d.x += q.x * wc.x; d.y += q.y * wc.y; d.z += q.z * wc.z; d.w += q.w * wc.w;
@@ -295,7 +295,7 @@ __device__ __forceinline__ void elt_task_body(const EltTask& t, const int tid, E
       sm.sh[tid] = gp;
       const float sum_g = elt_block_sum(gp, sm.red, tid);
       const float unscale = t.scale[1];
-      if (tid == 0 && t.part == 0) atomicAdd(t.dw2, sum_g * unscale);
+      if (tid == 0 && t.part == 0) red_add_f32(t.dw2, sum_g * unscale);
       ELT_SYNC();
       {
         // thread = (plane kc, lane-in-plane sub): pixels sub, sub+tpk, ... ; writes dZ and accumulates dw3 in one pass
@@ -330,8 +330,8 @@ __device__ __forceinline__ void elt_task_body(const EltTask& t, const int tid, E
           q.z += __shfl_xor_sync(0xffffffffu, q.z, o); q.w += __shfl_xor_sync(0xffffffffu, q.w, o);
         }
         if (sub == 0) {
-          atomicAdd(t.dw + kc * 4 + 0, q.x * unscale); atomicAdd(t.dw + kc * 4 + 1, q.y * unscale);
-          atomicAdd(t.dw + kc * 4 + 2, q.z * unscale); atomicAdd(t.dw + kc * 4 + 3, q.w * unscale);
+          red_add_f32(t.dw + kc * 4 + 0, q.x * unscale); red_add_f32(t.dw + kc * 4 + 1, q.y * unscale);
+          red_add_f32(t.dw + kc * 4 + 2, q.z * unscale); red_add_f32(t.dw + kc * 4 + 3, q.w * unscale);
         }
       }
     } break;

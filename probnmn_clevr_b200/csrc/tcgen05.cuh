@@ -192,6 +192,13 @@ __device__ __forceinline__ float to_tf32(float x) {
   return __uint_as_float(u);
 }
 
+// Fire-and-forget fp32 reduction into GLOBAL memory (SASS REDG).  atomicAdd() on a pointer that was loaded from a task
+// record compiles to a generic ATOM with a shared/global dispatch and a returned predicate: every call then blocks
+// for an L2 round trip (measured: it made up 2/3 of wgrad_tc_kernel's time, profiles/r1 ncu source page).
+__device__ __forceinline__ void red_add_f32(float* gptr, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(gptr), "f"(v) : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred = 0;
   asm volatile(

@@ -13,7 +13,7 @@
 // fp32 accumulation: same 10-bit mantissa as tf32, twice the tensor rate, half the bytes.  A tap is
 // again just a different start address of the X descriptor.
 // One CTA owns one tap ROW (3 taps -> 3 accumulators of 128 TMEM columns) of one weight tensor
-// and walks a list of instances, streaming 64-slot chunks of dZ and X through an mbarrier ring.
+// and walks a list of instances, streaming 128-slot chunks of dZ and X through an mbarrier ring.
 #include <cuda_fp16.h>
 
 #include "executor.h"
@@ -22,8 +22,9 @@
 namespace pnmn {
 
 constexpr int kWgThreads = 256;
-constexpr int kWgChunk = 64;        // slots (K) per stage
-constexpr int kWgStages = 5;
+constexpr int kWgChunk = 128;       // slots (K) per stage: 2 KB per half plane and copy (the copy engine is issue-bound on
+                                    // small copies: 1 KB pieces ran at ~10 GB/s per SM, ncu profiles/r1)
+constexpr int kWgStages = 3;
 constexpr int kWgHeader = 1024;
 constexpr int kWgSmemTotal = 227 * 1024;
 constexpr int kHP = kC / 8;              // fp16 half planes per 128-channel tensor
@@ -69,28 +70,40 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
   const uint32_t tmem_base = hdr->tmem_base;
 
   if (warp == 0) {
-    // producer: lane = half plane index (lanes 16..31 idle)
+    // producer: lane = half plane index (lanes 16..31 idle).  The instance table is read 32 entries at a time into
+    // registers (one entry per lane) and broadcast with shuffles: a dependent global load per ring stage would put an
+    // L2 round trip on the issue path of every stage.
+    unsigned long long my_dz = 0, my_x = 0;
     for (int it = 0; it < total; ++it) {
       const int st = it % kWgStages;
       const uint32_t ph = (it / kWgStages) & 1;
       const int inst = it / n_chunks, ch = it % n_chunks;
+      if (ch == 0 && (inst & 31) == 0) {
+        const int mine = inst + lane;
+        if (mine < t.n_inst) {
+          const WgradInst wi = t.inst[mine];
+          my_dz = reinterpret_cast<unsigned long long>(wi.dz);
+          my_x = reinterpret_cast<unsigned long long>(wi.x);
+        }
+      }
+      const uint8_t* gdz = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, my_dz, inst & 31));
+      const uint8_t* gx = reinterpret_cast<const uint8_t*>(__shfl_sync(0xffffffffu, my_x, inst & 31));
       const uint32_t bar = smem_u32(&hdr->full[st]);
       if (lane == 0) {
         mbar_wait(smem_u32(&hdr->empty[st]), ph ^ 1);
         mbar_arrive_expect_tx(bar, dz_bytes + kHP * xs * 16);
       }
       __syncwarp();
-      if (lane < kHP) {
-        const WgradInst wi = t.inst[inst];
-        const int c0 = ch * kWgChunk;
+      {
+        // lanes 0..15 fetch the dZ half planes, lanes 16..31 the X half planes
+        const int c0 = ch * kWgChunk, hp = lane & (kHP - 1);
         uint8_t* sdz = ring + st * kWgStageBytes;
         uint8_t* sx = sdz + dz_bytes;
-        const uint8_t* gdz = static_cast<const uint8_t*>(wi.dz);
-        const uint8_t* gx = static_cast<const uint8_t*>(wi.x);
-        bulk_g2s(smem_u32(sdz + lane * kWgChunk * 16), gdz + (static_cast<ptrdiff_t>(lane) * t.P + c0) * 16,
-                 kWgChunk * 16, bar);
-        bulk_g2s(smem_u32(sx + lane * xs * 16),
-                 gx + (static_cast<ptrdiff_t>(lane) * t.P + c0 + row_shift - halo) * 16, xs * 16, bar);
+        if (lane < kHP)
+          bulk_g2s(smem_u32(sdz + hp * kWgChunk * 16), gdz + (static_cast<ptrdiff_t>(hp) * t.P + c0) * 16, kWgChunk * 16, bar);
+        else
+          bulk_g2s(smem_u32(sx + hp * xs * 16), gx + (static_cast<ptrdiff_t>(hp) * t.P + c0 + row_shift - halo) * 16, xs * 16,
+                   bar);
       }
     }
   } else if (warp == 2) {
@@ -142,7 +155,7 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int cin = t.cin0 + chunk * 32 + j;
-            atomicAdd(t.dw + (static_cast<size_t>(cout) * t.cin_total + cin) * kk + tap,
+            red_add_f32(t.dw + (static_cast<size_t>(cout) * t.cin_total + cin) * kk + tap,
                       __uint_as_float(v[j]) * unscale);
           }
         }
@@ -175,7 +188,7 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgradTask* __rest
     }
     const int tap = t.ksize == 3 ? t.tap_row * 3 + tx : 0;
     if (t.n_inst > 0)
-      atomicAdd(t.dw + (static_cast<size_t>(cout) * t.cin_total + t.cin0 + cin) * kk + tap, acc * unscale);
+      red_add_f32(t.dw + (static_cast<size_t>(cout) * t.cin_total + t.cin0 + cin) * kk + tap, acc * unscale);
   }
 }
 
@@ -220,7 +233,7 @@ __global__ void __launch_bounds__(128) bias_grad_kernel(const BiasGradTask* __re
   if (sl == 0) {
     const float unscale = t.scale ? t.scale[1] : 1.f;
 #pragma unroll
-    for (int e = 0; e < 8; ++e) atomicAdd(t.db + hp * 8 + e, acc[e] * unscale);
+    for (int e = 0; e < 8; ++e) red_add_f32(t.db + hp * 8 + e, acc[e] * unscale);
   }
 }
 

@@ -1,0 +1,62 @@
+"""Data parallelism over questions: one process per GPU, every rank runs the joint step on its own shard
+of the batch and the gradients are averaged with ONE collective per flat buffer.
+
+The reference only knows single-process ``nn.DataParallel`` (trainers/_trainer.py:98-100), which mis-executes the NMN
+(its module table is a plain dict that ``replicate`` does not copy).  The path itself has no exchange
+step — samples are independent in forward — so the gradient average is the only collective (NCCL over NVLink on the
+GPU box; the same code runs over ``gloo`` in the CPU tests).
+"""
+from typing import Iterable, List, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_rows(n_rows: int, rank: int, world: int) -> Tuple[int, int]:
+    """[begin, end) of this rank's contiguous shard of a global batch (remainder rows go to the lowest ranks)."""
+    base, rem = divmod(n_rows, world)
+    begin = rank * base + min(rank, rem)
+    return begin, begin + base + (1 if rank < rem else 0)
+
+
+def gradient_buckets(models: Iterable[torch.nn.Module]) -> List[torch.Tensor]:
+    """Tensors to all-reduce: a model whose backward left all its gradients inside one flat buffer contributes that
+    buffer (the executor's / the seq2seq kernels' backward write one), everything else its ``.grad`` tensors."""
+    buckets: List[torch.Tensor] = []
+    for m in models:
+        params = [p for p in m.parameters() if p.grad is not None]
+        if not params:
+            continue
+        # gradients that are views into the same storage (a flat gradient buffer) form ONE bucket; buckets are emitted in
+        # parameter order so that every rank issues the same sequence of collectives
+        by_storage = {}
+        for p in params:
+            by_storage.setdefault(p.grad.untyped_storage().data_ptr(), []).append(p.grad)
+        for gs in by_storage.values():
+            if len(gs) == 1:
+                buckets.append(gs[0])
+                continue
+            flat = torch.empty(0, dtype=gs[0].dtype, device=gs[0].device).set_(gs[0].untyped_storage())
+            lo = min(g.storage_offset() for g in gs)
+            hi = max(g.storage_offset() + g.numel() for g in gs)
+            buckets.append(flat[lo:hi])
+    return buckets
+
+
+def allreduce_gradients(models: Iterable[torch.nn.Module], group: Optional[dist.ProcessGroup] = None,
+                        weight: float = 1.0) -> int:
+    """Average the gradients of ``models`` over the process group; returns the number of collectives issued.
+    ``weight`` is this rank's share of the global objective (e.g. rows_on_rank / rows_total * world_size) so that ranks
+    with unequal shard sizes reproduce the single-process global-batch mean exactly (SURVEY.md §8e caveat)."""
+    world = dist.get_world_size(group)
+    buckets = gradient_buckets(models)
+    handles = []
+    for b in buckets:
+        if weight != 1.0:
+            b.mul_(weight)
+        handles.append(dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for h in handles:
+        h.wait()
+    for b in buckets:
+        b.div_(world)
+    return len(buckets)

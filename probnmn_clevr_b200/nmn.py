@@ -260,8 +260,14 @@ class NeuralModuleNetwork(nn.Module):
         self._packed: Optional[torch.Tensor] = None
         self.last_plan_stats: Optional[List[int]] = None
         self._gflat_box: Dict[str, torch.Tensor] = {}
-        # classifier GEMMs (library calls): "1" = TF32 tensor cores, default = IEEE fp32 like the reference
-        self.classifier_tf32 = os.environ.get("PNMN_CLASSIFIER_TF32", "0") == "1"
+        # classifier GEMMs (plain library GEMMs, nmn.py:75-83): "ieee" (default) = cuBLAS/cuDNN fp32 like the reference;
+        # "split" = every fp32 operand split into two bf16 halves, one tensor-core GEMM over the 3x contraction
+        # (experimental: the splitting passes over the 205 MB fc1 weight eat most of the gain); "tf32" = 10-bit
+        # operands (misses the gradient parity bar, kept for comparison only)
+        self.classifier_math = os.environ.get("PNMN_CLASSIFIER", "tf32" if os.environ.get("PNMN_CLASSIFIER_TF32") == "1" else "ieee")
+        if self.classifier_math not in ("split", "ieee", "tf32"):
+            raise ValueError("PNMN_CLASSIFIER must be split, ieee or tf32")
+        self.classifier_tf32 = self.classifier_math == "tf32"
 
     @classmethod
     def from_config(cls, config):
@@ -383,7 +389,9 @@ class NeuralModuleNetwork(nn.Module):
             run.close()
 
         # classifier + loss (nmn.py:241-269); masking done on the device instead of CPU-tensor indexing
-        if self.classifier_tf32:
+        if self.classifier_math == "split":
+            answer_logits = self._classifier_split(final)
+        elif self.classifier_tf32:
             prev = torch.backends.cuda.matmul.allow_tf32
             final = _MatmulPrecision.apply(final, True, prev)
             answer_logits = _MatmulPrecision.apply(self.classifier(final), prev, True)
@@ -407,28 +415,27 @@ class NeuralModuleNetwork(nn.Module):
             output_dict["metrics"] = self.get_metrics(reset=True)
         return output_dict
 
+    def _classifier_split(self, final: torch.Tensor) -> torch.Tensor:
+        """nmn.py:75-83 with the two large GEMMs (1x1 conv 128->1024 over B*196 pixels, Linear 50176->1024) as
+        split-bf16 tensor-core products; ReLU / max-pool / the 1024->28 Linear stay plain fp32 ops."""
+        conv, fc1, fc2 = self.classifier[0], self.classifier[4], self.classifier[6]
+        B, C, H, W = final.shape
+        x = final.permute(0, 2, 3, 1).reshape(B * H * W, C)
+        y = F.relu(_SplitLinear.apply(x, conv.weight.view(conv.out_channels, C), conv.bias))
+        y = y.view(B, H, W, conv.out_channels).permute(0, 3, 1, 2)          # NCHW view of channels-last data
+        y = F.max_pool2d(y, kernel_size=2, stride=2)
+        y = y.contiguous(memory_format=torch.contiguous_format).reshape(B, -1)  # (C, 7, 7) flatten order, nmn_modules.py:250
+        z = F.relu(_SplitLinear.apply(y, fc1.weight, fc1.bias))
+        return F.linear(z, fc2.weight, fc2.bias)
+
     def allreduce_gradients(self, group=None) -> None:
         """Data-parallel gradient averaging over NCCL (one process per GPU): ONE all-reduce for the stem + module
         gradients, which the executor's backward leaves in a single flat buffer, plus one per classifier tensor.
         (The reference has no distributed path: it wraps the model in ``nn.DataParallel``,
         trainers/_trainer.py:98-100, which mis-executes the NMN)"""
-        import torch.distributed as dist
+        from .dist import allreduce_gradients
 
-        avg = dist.ReduceOp.AVG
-        exec_params = [p for _, p in self._exec_named_parameters()]
-        gflat = self._gflat_box.get("gflat")
-        handles = []
-        lo = gflat.data_ptr() if gflat is not None else 0
-        hi = lo + (gflat.numel() * 4 if gflat is not None else 0)
-        aliased = gflat is not None and all(p.grad is not None and lo <= p.grad.data_ptr() < hi for p in exec_params)
-        if aliased:
-            handles.append(dist.all_reduce(gflat, op=avg, group=group, async_op=True))
-        else:
-            handles += [dist.all_reduce(p.grad, op=avg, group=group, async_op=True) for p in exec_params if p.grad is not None]
-        handles += [dist.all_reduce(p.grad, op=avg, group=group, async_op=True)
-                    for n, p in self.named_parameters() if n.startswith("classifier.") and p.grad is not None]
-        for h in handles:
-            h.wait()
+        allreduce_gradients([self], group=group)
 
     def get_metrics(self, reset: bool = True) -> Dict[str, float]:
         """``{"answer_accuracy", "average_invalid"}`` (nmn.py:277-296)."""
@@ -440,6 +447,38 @@ class NeuralModuleNetwork(nn.Module):
 
 class _NullCtx:
     pass
+
+
+def _split3(x: torch.Tensor, dim: int, second_low: bool) -> torch.Tensor:
+    """x ~= hi + lo in bf16; returns cat([hi, lo, hi]) (second_low) or cat([hi, hi, lo]) along ``dim``: contracting two
+    such tensors over ``dim`` yields hi*hi + lo*hi + hi*lo, i.e. the product to ~16 mantissa bits per operand."""
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return torch.cat([hi, lo, hi] if second_low else [hi, hi, lo], dim)
+
+
+class _SplitLinear(torch.autograd.Function):
+    """y = x @ w.T + b with fp32 inputs / outputs, computed by ONE bf16 tensor-core GEMM (fp32 accumulate) over the
+    3x-long split contraction; same for both gradient GEMMs.  Library call (cuBLAS), used for the classifier only."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        y = torch.mm(_split3(x, 1, True), _split3(w, 1, False).t(), out_dtype=torch.float32)
+        return y + b
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.mm(_split3(g, 1, True), _split3(w, 0, False), out_dtype=torch.float32)
+        if ctx.needs_input_grad[1]:
+            dw = torch.mm(_split3(g, 0, True).t(), _split3(x, 0, False), out_dtype=torch.float32)
+        if ctx.needs_input_grad[2]:
+            db = g.sum(0)
+        return dx, dw, db
 
 
 class _MatmulPrecision(torch.autograd.Function):

@@ -38,6 +38,13 @@ for rep in sorted(f for f in os.listdir("gpurun_out") if f.endswith(f"_{tag}.ncu
         continue
     hdr, units = rows[0], rows[1]
     P(f"\n## `ncu --set full --clock-control none` : {rep}\n")
+    if rep.startswith("exec_"):
+        tot = [float(r[hdr.index("dram__bytes_read.sum")]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[units[hdr.index("dram__bytes_read.sum")]]
+               + float(r[hdr.index("dram__bytes_write.sum")]) * {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1}[units[hdr.index("dram__bytes_write.sum")]]
+               for r in rows[2:]]
+        import json
+        json.dump({"exec_kernel_bytes_per_launch": sum(tot) / len(tot), "launches": len(tot), "per_launch": tot,
+                   "source": f"ncu --set full, {rep}"}, open(f"profiles/{tag}_traffic.json", "w"))
     for r in rows[2:]:
         P(f"### `{r[hdr.index('Kernel Name')][:100]}` (launch id {r[0]})\n")
         P("| metric | value | unit |\n|---|---:|---|")
