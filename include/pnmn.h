@@ -109,6 +109,11 @@ int pnmn_nmn_forward(pnmn_plan* p, const pnmn_buffers* bufs, const float* featur
  * stem and module parameters are ACCUMULATED into bufs->grads (autograd semantics). */
 int pnmn_nmn_backward(pnmn_plan* p, const pnmn_buffers* bufs, const float* grad_final_out, void* stream);
 
+/* Classifier helper (probnmn/models/nmn.py:75-83 are plain library GEMMs): splits an fp32 matrix [rows][cols] (device) into
+ * bf16 hi / lo parts and writes the three chunks of the split contraction, side by side (stack_rows = 0: [rows][3*cols])
+ * or stacked (stack_rows = 1: [3*rows][cols]); chunk order (hi, lo, hi) if second_low else (hi, hi, lo). */
+int pnmn_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int stack_rows, int second_low, void* stream);
+
 /* Optional per-launch device timing (CUDA events on the launching stream), used by bench.py for the
  * roofline of the dominant kernel.  ms / launches have 8 slots: {elementwise, conv<2 samples x 2 tiles>,
  * conv<1 x 3>, wgrad, bias_grad, weight pack, feature layout, other}.  Reading synchronises and clears. */

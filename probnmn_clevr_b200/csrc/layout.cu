@@ -2,6 +2,7 @@
 #include <cuda_fp16.h>
 
 #include "executor.h"
+#include <cuda_bf16.h>
 #include "layout.h"
 #include "tcgen05.cuh"
 
@@ -80,6 +81,41 @@ cudaError_t launch_nchw_to_planes(const float* src, float* dst, int B, int C, co
                                   cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
   nchw_to_planes_kernel<<<dim3(C / 4, B), 256, 0, stream>>>(src, dst, C, dst_off);
+  return cudaGetLastError();
+}
+
+
+// x ~= hi + lo in bf16 (16 mantissa bits); writes the three chunks of the split contraction in one pass:
+//   stack_rows == 0: dst [rows][3*cols] = [hi | a | b]      stack_rows == 1: dst [3*rows][cols] = [hi ; a ; b]
+//   (a, b) = (lo, hi) when second_low else (hi, lo).  Contracting a second_low tensor with a !second_low tensor over the
+//   tripled dimension yields hi*hi + lo*hi + hi*lo.  Used by the classifier's library GEMMs (nmn.py, _SplitLinear).
+__global__ void split3_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int64_t cols,
+                                   int stack_rows, int second_low) {
+  const int64_t n4 = rows * cols / 4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = __float2bfloat16_rn(x[e]);
+      lo[e] = __float2bfloat16_rn(x[e] - __bfloat162float(hi[e]));
+    }
+    const int64_t r = (i * 4) / cols, c = (i * 4) % cols;
+    const int64_t chunk = stack_rows ? rows * cols : cols;
+    const int64_t base = stack_rows ? r * cols + c : r * 3 * cols + c;
+    const uint2 H = *reinterpret_cast<const uint2*>(hi), Lw = *reinterpret_cast<const uint2*>(lo);
+    *reinterpret_cast<uint2*>(dst + base) = H;
+    *reinterpret_cast<uint2*>(dst + base + chunk) = second_low ? Lw : H;
+    *reinterpret_cast<uint2*>(dst + base + 2 * chunk) = second_low ? H : Lw;
+  }
+}
+cudaError_t launch_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int stack_rows, int second_low,
+                               cudaStream_t st) {
+  if (rows * cols == 0) return cudaSuccess;
+  const int64_t n4 = rows * cols / 4;
+  const int blocks = static_cast<int>(n4 / 256 + 1 < 148 * 16 ? n4 / 256 + 1 : 148 * 16);
+  split3_bf16_kernel<<<blocks, 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), rows, cols, stack_rows, second_low);
   return cudaGetLastError();
 }
 

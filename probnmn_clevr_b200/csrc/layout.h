@@ -33,6 +33,8 @@ cudaError_t launch_conv_simt(const ConvTask* d_tasks, int n_tasks, const ConvCfg
 cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, cudaStream_t stream);
 cudaError_t launch_bias_grad(const void* d_tasks, int n_tasks, int split, cudaStream_t stream);
 cudaError_t launch_elt(const EltTask* d_tasks, int n_tasks, cudaStream_t stream);
+cudaError_t launch_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int stack_rows, int second_low,
+                               cudaStream_t stream);
 cudaError_t launch_loss_scale(const float* grad, size_t n, float* scale, cudaStream_t stream);
 
 }  // namespace pnmn

@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <cstddef>
 #include <cstring>
+#include <malloc.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -126,6 +127,15 @@ extern "C" pnmn_model* pnmn_model_create(int vocab_size, const int32_t* token_ki
                                          const int64_t* token_param_off, const int64_t* stem_param_off,
                                          int in_channels) {
   if (in_channels % 128 != 0) { g_err = "in_channels must be a multiple of 128"; return nullptr; }
+  // The program compiler builds several MB of task tables per forward.  glibc serves such blocks with mmap and returns
+  // them on free, so every plan would page-fault its tables in again (~half of pnmn_plan_create's time); keep them on
+  // the heap instead.
+  static const bool heap_tuned = [] {
+    mallopt(M_MMAP_THRESHOLD, 1 << 30);
+    mallopt(M_TRIM_THRESHOLD, 1 << 30);
+    return true;
+  }();
+  (void)heap_tuned;
   auto* m = new pnmn_model();
   m->V = vocab_size;
   m->in_ch = in_channels;
@@ -961,11 +971,8 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   }
 
   const auto t_flat = std::chrono::steady_clock::now();
-  if (std::getenv("PNMN_PLAN_TIMING")) {
-    auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
-    std::fprintf(stderr, "plan: emit %.2f ms, flatten+wgrad %.2f ms, tasks fwd %zu bwd %zu\n", ms(timer.t0, t_emit),
-                 ms(t_emit, t_flat), p.ftask.size(), p.btask.size());
-  }
+  static const bool plan_timing = std::getenv("PNMN_PLAN_TIMING") != nullptr;
+  auto ms_between = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
   if (fs.dep_overflow || bs.dep_overflow) {
     g_err = "internal error: a task has more predecessors than kMaxDeps";
     delete plan;
@@ -1014,6 +1021,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
     // the dependency flags + task counters live at the tail of the blob: they are uploaded as zeros
     std::memset(hb + p.off_fsync, 0, static_cast<size_t>(p.blob_bytes - p.off_fsync));
   }
+  const auto t_blob = std::chrono::steady_clock::now();
   p.stats[1] = n_conv3;
   p.stats[2] = n_tokens;
   p.stats[3] = static_cast<int64_t>(p.flaunch.size());
@@ -1057,6 +1065,10 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   }
   for (const WgradTask& t : p.wtasks) p.stats[12] += static_cast<int64_t>(t.n_inst) * 2 * 196 * 128 * 128 * t.ntaps_x;
   p.stats[13] = static_cast<int64_t>(p.felt.size() + p.belt.size());
+  if (plan_timing)
+    std::fprintf(stderr, "plan: emit %.2f ms, flatten+wgrad %.2f ms, blob %.2f ms, stats %.2f ms, tasks fwd %zu bwd %zu\n",
+                 ms_between(timer.t0, t_emit), ms_between(t_emit, t_flat), ms_between(t_flat, t_blob),
+                 ms_between(t_blob, std::chrono::steady_clock::now()), p.ftask.size(), p.btask.size());
   return plan;
 }
 
@@ -1319,6 +1331,14 @@ extern "C" int pnmn_profile_read(double* ms, int64_t* launches) {
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
   g_prof.clear();
+  return 0;
+}
+
+// bf16 hi/lo split of an fp32 matrix for the classifier's split-precision library GEMMs (see layout.cu)
+extern "C" int pnmn_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int stack_rows, int second_low,
+                                void* stream) {
+  if (!src || !dst || rows < 0 || cols < 0 || cols % 4 != 0) return fail("pnmn_split3_bf16: bad arguments (cols must be a multiple of 4)");
+  CUDA_OK(launch_split3_bf16(src, dst, rows, cols, stack_rows, second_low, static_cast<cudaStream_t>(stream)));
   return 0;
 }
 
