@@ -233,9 +233,27 @@ def run_ours(args):
     def resident_step(i):
         step(*resident[i % 2])
 
+    # end-to-end leg: every step's features / answers start in PINNED HOST memory; the copy of step i+1 is issued on a side
+    # stream before step i computes (probnmn_clevr_b200/feed.py), so all K copies sit inside the timed region but overlap
+    # with compute; the loss is read back (device -> host) every step
+    from probnmn_clevr_b200.feed import DevicePrefetcher
+    feed = DevicePrefetcher(dev)
+    e2e_total = {"n": 0}
+
     def e2e_step(i):
-        f, p, a = host[i % 2]
-        loss = step(f.to(dev, non_blocking=True), p, a.to(dev, non_blocking=True))
+        if feed.pending() == 0:
+            feed.submit(i, (host[i % 2][0], host[i % 2][2]))
+        f, a = feed.get(i)
+        model.zero_grad(set_to_none=True)
+        out = model(f, host[i % 2][1], a)
+        # the next batch's copy is queued AFTER this forward's task-table upload (same H2D engine, FIFO): it then overlaps
+        # with the executor instead of delaying it
+        if i + 1 < e2e_total["n"]:
+            feed.submit(i + 1, (host[(i + 1) % 2][0], host[(i + 1) % 2][2]))
+        loss = out["loss"].mean()
+        loss.backward()
+        if world > 1:
+            model.allreduce_gradients()
         return loss.item()
 
     for i in range(max(args.warmup, 3)):
@@ -250,8 +268,10 @@ def run_ours(args):
     host_ms_per_step = {"plan_create": host_ms[0] / args.steps, "forward_call": host_ms[1] / args.steps,
                         "backward_call": host_ms[2] / args.steps}
     stats = model.last_plan_stats
+    e2e_total["n"] = 2
     for i in range(2):
         e2e_step(i)
+    e2e_total["n"] = args.steps
     ms_e2e = timed(e2e_step, args.steps)
 
     value = world * args.batch * args.steps / (ms * 1e-3)
@@ -287,7 +307,9 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(args),
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps,
+                "pipeline": "pinned host buffers; the copy of step i+1 runs on a side stream during step i (feed.DevicePrefetcher); "
+                            "loss.item() every step"},
         "gpu_launches": int((stats[3] + stats[4] + 5) * args.steps),
         "roofline": {
             "bound": "tensor", "kernel": "exec_kernel (persistent tcgen05 kind::f16 shift-GEMM executor: forward + dgrad launches)",

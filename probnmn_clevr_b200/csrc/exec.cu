@@ -9,11 +9,16 @@
 // CTA can only wait for a task that is already running: no deadlock, no host round trips, no
 // per-level launch latency, and chains of different samples overlap freely across the SMs.
 //
-// Inside a CTA a convolution task is warp-specialised exactly like conv.cu: warp 0 streams
-// activation k-blocks and warp 1 streams weight tiles with cp.async.bulk into mbarrier rings,
-// warp 2 issues tcgen05.mma (kind::f16 on fp16 operands, fp32 accumulators in TMEM), warp 3 is the scheduler, warps
-// 4-11 (two per TMEM lane quarter, each taking half of the 128 columns) run the fused epilogue.
-// TMEM, barriers and ring phases persist across tasks.
+// Inside a CTA a convolution task is warp-specialised: warp 0 streams activation k-blocks and warp 1
+// streams weight tiles with cp.async.bulk into mbarrier rings, warp 2 issues tcgen05.mma (kind::f16 on
+// fp16 operands, fp32 accumulators in TMEM), warp 3 is the scheduler, warps 4-7 (one per TMEM lane
+// quarter) run the fused epilogue.  TMEM, barriers and ring phases persist across tasks.
+//
+// TWO CTAs are resident per SM (256 threads, <= 128 registers, 107 KB of shared memory and 256 TMEM
+// columns each): a task is a strictly serial chain (wait for predecessors -> first operands -> MMAs ->
+// epilogue -> publish; profiles/r1: a 72-MMA task spends 2.4 us of its 20 us in the tensor pipe), so
+// the second CTA's mainloop fills the tensor pipe while the first one is in its epilogue or waiting.
+// A task therefore owns at most two accumulators (one sample x two M tiles, or two samples x one).
 #include <cuda_fp16.h>
 #include <type_traits>
 
@@ -24,16 +29,18 @@
 
 namespace pnmn {
 
-constexpr int kExThreads = 384;
-constexpr int kExWStages = 8;
+constexpr int kExThreads = 256;
+constexpr int kExCtasPerSM = 2;
+constexpr int kExMaxAcc = 2;               // accumulators (128 TMEM columns each) per task
+constexpr int kExWStages = 4;
 constexpr int kExWTile = 16 * 128 * 2;     // 4 KB: 16 k x 128 n fp16
 constexpr int kExWStage = 3 * kExWTile;    // one tap ROW (3 taps) per ring stage: one barrier round trip per row
-constexpr int kExAStages = 4;
+constexpr int kExAStages = 2;
 constexpr int kExAStage = 24 * 1024;       // max over plane formats of NS*(lead + 2*P)*16 (fp16 half planes)
 constexpr int kExHeader = 8 * 1024;
 constexpr int kExGuard = 3 * 1024;
 constexpr int kExSmem = kExHeader + kExWStages * kExWStage + kExAStages * kExAStage + kExGuard;
-static_assert(kExSmem <= 227 * 1024, "executor smem");
+static_assert(kExCtasPerSM * (kExSmem + 1024) <= 228 * 1024, "executor smem: two CTAs per SM");
 
 struct ExHeader {
   uint64_t full_a[kExAStages], empty_a[kExAStages];
@@ -45,7 +52,6 @@ struct ExHeader {
   alignas(16) uint8_t task[128];
   alignas(16) float bias[128];
   alignas(16) float w3[128];
-  float dotp[2][512];
   EltSmem elt;
 };
 static_assert(sizeof(ExHeader) <= kExHeader, "executor header");
@@ -80,7 +86,7 @@ __device__ __forceinline__ int smid() {
 //   [4] SM id    [5] type | n_samp<<8 | n_mt<<16   [6] MMAs per (sample, M tile)   [7] cfg flags / elt op
 //   [8] roles start (after barrier B)  [9] first operands landed  [10] last MMA issued
 //   [11] accumulators complete  [12] epilogue stores issued  [13] epilogue fenced
-__global__ void __launch_bounds__(kExThreads, 1)
+__global__ void __launch_bounds__(kExThreads, kExCtasPerSM)
 exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ metas, int n_tasks,
             const ConvCfg* __restrict__ cfgs, int* __restrict__ counter, int* __restrict__ done,
             long long* __restrict__ trace) {
@@ -102,7 +108,7 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
     mbar_init(smem_u32(&hdr->tmem_full), 1);
     fence_mbar_init();
   }
-  if (warp == 2) tmem_alloc<512>(smem_u32(&hdr->tmem_base));
+  if (warp == 2) tmem_alloc<kExMaxAcc * 128>(smem_u32(&hdr->tmem_base));
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -152,7 +158,6 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
       const int S_aux = UNI(cp->S_aux), P_aux = UNI(cp->P_aux);
       const int flags = UNI(cp->flags), lead = UNI(cp->lead);
 #undef UNI
-      const int nmt = P_in == 484 ? 3 : 2;  // M tiles per sample (P22 planes span 3)
       const uint32_t plane_bytes = static_cast<uint32_t>(P_in) * 16u;
       const uint32_t samp_bytes = static_cast<uint32_t>(lead) * 16u + 2u * plane_bytes;  // 2 half planes = 16 ch
       const int tps = ntaps == 9 ? 3 : 1;     // taps per weight stage
@@ -222,21 +227,19 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
           const int row_shift = ntaps == 9 ? S_in * dil : 0;  // slots between tap rows
           const int col_shift = ntaps == 9 ? dil : 0;
           const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
-          // accumulators of this task: up to 4 (sample, M tile) pairs
-          uint32_t aoff[4], doff[4];
+          // accumulators of this task: up to kExMaxAcc (sample, M tile) pairs, TMEM slot = running index
+          uint32_t aoff[kExMaxAcc], doff[kExMaxAcc];
           int n_acc = 0;
 #pragma unroll
-          for (int k = 0; k < 4; ++k) { aoff[k] = 0; doff[k] = 0; }
+          for (int k = 0; k < kExMaxAcc; ++k) { aoff[k] = 0; doff[k] = 0; }
 #pragma unroll
           for (int s = 0; s < 2; ++s)
 #pragma unroll
             for (int m = 0; m < 3; ++m)
-              if (s < n_samp && m >= mt0 && m < mt0 + n_mt) {
-                const uint32_t av = s * samp16 + m * 128, dv = tm + (s * nmt + m) * 128;
+              if (s < n_samp && m >= mt0 && m < mt0 + n_mt && n_acc < kExMaxAcc) {
+                const uint32_t av = s * samp16 + m * 128, dv = tm + n_acc * 128;
                 if (n_acc == 0) { aoff[0] = av; doff[0] = dv; }
-                else if (n_acc == 1) { aoff[1] = av; doff[1] = dv; }
-                else if (n_acc == 2) { aoff[2] = av; doff[2] = dv; }
-                else { aoff[3] = av; doff[3] = dv; }
+                else { aoff[1] = av; doff[1] = dv; }
                 ++n_acc;
               }
           uint32_t ua = __shfl_sync(0xffffffffu, na, 0), uw = __shfl_sync(0xffffffffu, nw, 0);
@@ -290,21 +293,19 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
             }
           };
           using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
-          using I3 = std::integral_constant<int, 3>; using I4 = std::integral_constant<int, 4>;
+          using I3 = std::integral_constant<int, 3>;
           if (tps == 3) {
-            if (n_acc == 1) run(I3{}, I1{}); else if (n_acc == 2) run(I3{}, I2{});
-            else if (n_acc == 3) run(I3{}, I3{}); else run(I3{}, I4{});
+            if (n_acc == 1) run(I3{}, I1{}); else run(I3{}, I2{});
           } else {
-            if (n_acc == 1) run(I1{}, I1{}); else if (n_acc == 2) run(I1{}, I2{});
-            else if (n_acc == 3) run(I1{}, I3{}); else run(I1{}, I4{});
+            if (n_acc == 1) run(I1{}, I1{}); else run(I1{}, I2{});
           }
           if (elect_one()) umma_commit(smem_u32(&hdr->tmem_full));
           __syncwarp();
           if (trace && lane == 0) { trace[idx * 16 + 10] = gtime(); trace[idx * 16 + 14] = wait_a; trace[idx * 16 + 15] = wait_w; }
         }
       } else if (warp >= 4) {
-        // ---------------- epilogue: 8 warps = 4 lane quarters x 2 column halves ----------------
-        const int ew = warp - 4, q = ew & 3, half = ew >> 2;
+        // ---------------- epilogue: 4 warps = the 4 TMEM lane quarters; a thread owns one pixel row x 128 channels ----
+        const int q = warp - 4;
         float* out_s[2] = {tp->out[0], tp->out[1]};
         const float* aux_s[2] = {tp->aux[0], tp->aux[1]};
         float* map_s[2] = {tp->map_out[0], tp->map_out[1]};
@@ -312,13 +313,14 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
         mbar_wait(smem_u32(&hdr->tmem_full), n_conv & 1);
         tc_fence_after();
         if (trace && tid == 128) trace[idx * 16 + 11] = gtime();
+        int acc_slot = 0;
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
           if (s >= n_samp) break;
           float* const outp = out_s[s];
           const float* const auxp = (flags & F_MASK) ? aux_s[s] : outp;  // F_MASK and F_ACCUM never combine
           uint8_t* const hb = reinterpret_cast<uint8_t*>(outp) + shadow_bytes(P_out);
-          for (int mt = mt0; mt < mt0 + n_mt; ++mt) {
+          for (int mt = mt0; mt < mt0 + n_mt && acc_slot < kExMaxAcc; ++mt, ++acc_slot) {
             const int r = mt * 128 + q * 32 + lane;
             const int y = r / S_in, x = r - y * S_in;
             const bool valid = (y < kHW) && (x < kHW);
@@ -327,10 +329,9 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
             const int Px = (flags & F_MASK) ? P_aux : P_out;
             float dot = 0.f;
 #pragma unroll 1
-            for (int cc = 0; cc < 2; ++cc) {
-              const int chunk = half * 2 + cc;
+            for (int chunk = 0; chunk < 4; ++chunk) {
               uint32_t v[32];
-              tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + (s * nmt + mt) * 128 + chunk * 32, v);
+              tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_slot * 128 + chunk * 32, v);
               float4 ax[8];
               if (valid && (flags & (F_MASK | F_ACCUM))) {
 #pragma unroll
@@ -377,24 +378,8 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
                 }
               }
             }
-            if (flags & F_DOTSIG) hdr->dotp[half][(s * nmt + mt) * 128 + q * 32 + lane] = dot;
-          }
-        }
-        if (flags & F_DOTSIG) {
-          asm volatile("bar.sync 2, 256;" ::: "memory");
-          if (half == 0) {
-#pragma unroll
-            for (int s = 0; s < 2; ++s) {
-              if (s >= n_samp) break;
-              for (int mt = mt0; mt < mt0 + n_mt; ++mt) {
-                const int r = mt * 128 + q * 32 + lane;
-                const int y = r / S_in, x = r - y * S_in;
-                if (y < kHW && x < kHW) {
-                  const int k = (s * nmt + mt) * 128 + q * 32 + lane;
-                  map_s[s][y * 16 + x] = 1.f / (1.f + expf(-(hdr->dotp[0][k] + hdr->dotp[1][k] + b3)));
-                }
-              }
-            }
+            // the thread holds the whole 128-channel dot product of its pixel: 1x1 head + sigmoid (nmn_modules.py:86,167)
+            if ((flags & F_DOTSIG) && valid) map_s[s][y * 16 + x] = 1.f / (1.f + expf(-(dot + b3)));
           }
         }
         if (trace && tid == 128) trace[idx * 16 + 12] = gtime();
@@ -412,12 +397,11 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
       if (!(warp == 0 && lane == 0)) na += n_kb;
       if (!(warp == 1 && lane == 0)) nw += n_ws;
     } else {
-      if (warp >= 4) {
-        const EltTask& t = *reinterpret_cast<const EltTask*>(hdr->task);
-        elt_task_body(t, tid - 128, hdr->elt);
-        __threadfence();
-        if (trace && tid == 128) { trace[idx * 16 + 5] = TASK_ELT; trace[idx * 16 + 6] = 0; trace[idx * 16 + 7] = t.op; }
-      }
+      // CUDA-core task: all 256 threads of the CTA (the tensor-core roles have nothing to do meanwhile)
+      const EltTask& t = *reinterpret_cast<const EltTask*>(hdr->task);
+      elt_task_body(t, tid, hdr->elt);
+      __threadfence();
+      if (trace && tid == 128) { trace[idx * 16 + 5] = TASK_ELT; trace[idx * 16 + 6] = 0; trace[idx * 16 + 7] = t.op; }
     }
     if (trace && tid == 0) trace[idx * 16 + 2] = gtime();
     __syncthreads();  // (C) every store of this task is fenced
@@ -429,7 +413,7 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc<512>(tmem_base);
+  if (warp == 2) tmem_dealloc<kExMaxAcc * 128>(tmem_base);
 }
 
 cudaError_t launch_exec(const uint8_t* d_tasks, const TaskMeta* d_meta, int n_tasks, const ConvCfg* d_cfgs,
@@ -444,7 +428,7 @@ cudaError_t launch_exec(const uint8_t* d_tasks, const TaskMeta* d_meta, int n_ta
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = n_tasks < sms ? n_tasks : sms;
+  const int grid = n_tasks < kExCtasPerSM * sms ? n_tasks : kExCtasPerSM * sms;
   exec_kernel<<<grid, kExThreads, kExSmem, stream>>>(d_tasks, d_meta, n_tasks, d_cfgs, d_counter, d_done, d_trace);
   return cudaGetLastError();
 }

@@ -255,7 +255,8 @@ struct Sched {
     // samples per CTA (shared weight stream), narrow levels split a sample's M tiles over several CTAs.
     const int U = static_cast<int>(v.size());
     const int nmt = kind == LK_CONV0 ? 2 : 3;
-    const int cap = (kind == LK_CONV0 && U > kNumSMs) ? NSMAX : 1;
+    static const bool pair_always = std::getenv("PNMN_PAIR_ALWAYS") != nullptr;  // diagnostics
+    const int cap = (kind == LK_CONV0 && (U > kNumSMs || pair_always)) ? NSMAX : 1;
     static const bool no_split = std::getenv("PNMN_NOSPLIT") != nullptr;  // diagnostics
     const int split = (!no_split && U * nmt <= kNumSMs + kNumSMs / 2) ? nmt : 1;
     size_t i = 0;
@@ -272,11 +273,11 @@ struct Sched {
         t.out[k] = o.out[0]; t.aux[k] = o.aux[0]; t.map_out[k] = o.map_out[0];
         ++j;
       }
-      if (split > 1) {
+      // a task owns at most TWO accumulators (two executor CTAs share an SM's 512 TMEM columns, exec.cu)
+      if (split > 1 || t.n_samp > 1) {
         for (int m = 0; m < nmt; ++m) { t.mt0 = m; t.n_mt = 1; emit(t, samples, t.n_samp); }
       } else {
-        t.mt0 = 0; t.n_mt = nmt;
-        emit(t, samples, t.n_samp);
+        for (int m = 0; m < nmt; m += 2) { t.mt0 = m; t.n_mt = std::min(2, nmt - m); emit(t, samples, t.n_samp); }
       }
       i = j;
     }
@@ -1362,7 +1363,20 @@ extern "C" int pnmn_debug_launch_conv(const void* tasks_host, int n_tasks, const
   if (impl_simt) {
     CUDA_OK(launch_conv_simt(dt, n_tasks, dc, st));
   } else {
-    // run the tasks through the persistent executor kernel without dependencies
+    // run the tasks through the persistent executor kernel without dependencies; the kernel handles at most two
+    // accumulators per task, so wider test tasks are cut into per-M-tile pieces first
+    {
+      std::vector<ConvTask> host(static_cast<const ConvTask*>(tasks_host), static_cast<const ConvTask*>(tasks_host) + n_tasks);
+      std::vector<ConvTask> cut;
+      for (const ConvTask& t : host) {
+        if (t.n_samp * t.n_mt <= 2) { cut.push_back(t); continue; }
+        for (int m = t.mt0; m < t.mt0 + t.n_mt; ++m) { ConvTask u = t; u.mt0 = m; u.n_mt = 1; cut.push_back(u); }
+      }
+      cudaFree(dt);
+      dt = nullptr;
+      n_tasks = static_cast<int>(cut.size());
+      if (upload(cut.data(), cut.size(), &dt)) return 1;
+    }
     std::vector<TaskMeta> metas(n_tasks);
     for (auto& mm : metas) { mm.type = TASK_CONV; mm.n_deps = 0; for (int k = 0; k < kMaxDeps; ++k) mm.deps[k] = -1; }
     TaskMeta* dm = nullptr; int* sync = nullptr;
