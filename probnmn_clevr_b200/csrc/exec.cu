@@ -339,7 +339,22 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
                   ax[j] = *reinterpret_cast<const float4*>(auxp + (static_cast<size_t>(chunk * 8 + j) * Px + sx) * 4);
               }
               tmem_ld_wait();
-              if (valid) {
+              if (valid && (flags & F_ATTBWD)) {
+                // g = this conv's output (gradient w.r.t. feat * map): dmap += <g, feat>, dfeat (+)= g * map
+                const float* feat = aux_s[s];
+                const float mval = map_s[s][y * 16 + x];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  const size_t off = (static_cast<size_t>(chunk * 8 + j) * 256 + (y * 16 + x)) * 4;
+                  const float4 f = *reinterpret_cast<const float4*>(feat + off);
+                  const float gx = __uint_as_float(v[4 * j]), gy = __uint_as_float(v[4 * j + 1]);
+                  const float gz = __uint_as_float(v[4 * j + 2]), gw = __uint_as_float(v[4 * j + 3]);
+                  dot = fmaf(gx, f.x, dot); dot = fmaf(gy, f.y, dot); dot = fmaf(gz, f.z, dot); dot = fmaf(gw, f.w, dot);
+                  float4 o = make_float4(gx * mval, gy * mval, gz * mval, gw * mval);
+                  if (flags & F_ACCUM) { o.x += ax[j].x; o.y += ax[j].y; o.z += ax[j].z; o.w += ax[j].w; }
+                  *reinterpret_cast<float4*>(outp + off) = o;
+                }
+              } else if (valid) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                   const int n0 = (chunk * 8 + j) * 4;
@@ -379,7 +394,30 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
               }
             }
             // the thread holds the whole 128-channel dot product of its pixel: 1x1 head + sigmoid (nmn_modules.py:86,167)
-            if ((flags & F_DOTSIG) && valid) map_s[s][y * 16 + x] = 1.f / (1.f + expf(-(dot + b3)));
+            if ((flags & F_ATTBWD) && valid) {
+              float* dmap = reinterpret_cast<float*>(const_cast<void*>(tp->in[1][s]));
+              dmap[y * 16 + x] += dot;   // one writer per pixel: a sample's backward chain is serial
+            }
+            if ((flags & F_DOTSIG) && valid) {
+              const float m = 1.f / (1.f + expf(-(dot + b3)));
+              map_s[s][y * 16 + x] = m;
+              if (flags & F_ATTEND) {
+                // the next module's first conv reads feat * map: write its fp16 operand planes right here
+                const float* feat = aux_s[s];
+                uint8_t* x0h = reinterpret_cast<uint8_t*>(const_cast<void*>(tp->in[1][s]));
+                const int s16 = y * 16 + x;
+#pragma unroll 4
+                for (int hp = 0; hp < 16; ++hp) {
+                  const float4 f0 = *reinterpret_cast<const float4*>(feat + (static_cast<size_t>(2 * hp) * 256 + s16) * 4);
+                  const float4 f1 = *reinterpret_cast<const float4*>(feat + (static_cast<size_t>(2 * hp + 1) * 256 + s16) * 4);
+                  const uint4 h = make_uint4(elt_pack_half2(to_tf32(f0.x * m), to_tf32(f0.y * m)),
+                                             elt_pack_half2(to_tf32(f0.z * m), to_tf32(f0.w * m)),
+                                             elt_pack_half2(to_tf32(f1.x * m), to_tf32(f1.y * m)),
+                                             elt_pack_half2(to_tf32(f1.z * m), to_tf32(f1.w * m)));
+                  *reinterpret_cast<uint4*>(x0h + (static_cast<size_t>(hp) * 256 + s16) * 16) = h;
+                }
+              }
+            }
           }
         }
         if (trace && tid == 128) trace[idx * 16 + 12] = gtime();

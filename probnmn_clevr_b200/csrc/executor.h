@@ -48,6 +48,11 @@ enum ConvFlags : int {
   F_MASK = 16,    // y = aux[n] > 0 ? y : 0                            (ReLU backward)
   F_ACCUM = 32,   // y += out[] (existing contents)
   F_HALF = 64,    // also write the fp16 shadow copy behind out[]
+  // persistent executor only (exec.cu) -- the elementwise op that would follow is folded into the epilogue:
+  F_ATTEND = 128, // with F_DOTSIG: also write the NEXT module's attended input  x0 = feat * map  (fp16 shadow only);
+                  // aux[s] = feat (P16 fp32 planes), in[1][s] = shadow of x0          (nmn_modules.py:83,120,161)
+  F_ATTBWD = 256, // backward of that product on the data gradient g this conv computes:  dmap[p] += sum_c g[c][p]*feat[c][p],
+                  // out[s] (= dfeat) (+)= g*map;  aux[s] = feat, map_out[s] = map (read), in[1][s] = dmap (P16 fp32 map)
 };
 
 // byte offset of the fp16 shadow behind a 128-channel fp32 plane buffer of P slots per plane

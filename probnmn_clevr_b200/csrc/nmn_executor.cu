@@ -180,6 +180,8 @@ struct Val {
   bool gwritten = false;
   bool live = false;
   bool cons_minmax = false;
+  int dotsig_proto = -1;   // forward conv proto (index into Sched::protos) whose fused 1x1 head produced this map
+  bool attend_fused = false;
 };
 struct OpRec {
   int kind = 0, tok = 0;
@@ -189,6 +191,7 @@ struct OpRec {
   int nconv = 0;
   int y_unit[5] = {-1, -1, -1, -1, -1};  // conv outputs (arena of the NEXT conv's input format)
   int idx_slot = -1;
+  bool attend_fused = false;  // feat * map is produced by the previous module's head conv (F_ATTEND), no elementwise task
 };
 
 enum LaunchKind { LK_ELT = 0, LK_CONV0 = 1, LK_CONV1 = 2, LK_WGRAD = 3, LK_BIAS = 4 };
@@ -235,11 +238,12 @@ struct Sched {
       elt_sample.push_back(s);
     }
   }
-  void add_conv(int s, const ConvTask& t, int variant) {
+  int add_conv(int s, const ConvTask& t, int variant) {
     const int kind = variant == 0 ? LK_CONV0 : LK_CONV1;
     const int st = place(s, kind);
     buckets[st][kind].push_back(static_cast<int>(protos.size()));
     protos.push_back(ConvProto{t, s});
+    return static_cast<int>(protos.size()) - 1;
   }
   // Conv tasks of one step: pair samples that share (cfg, weights) on wide levels, split M tiles on narrow
   // ones.  Calls emit(task, samples[], n_samples) for every CTA-level task.
@@ -426,6 +430,12 @@ struct Builder {
     return cfg_id(c);
   }
 
+  int cfg_with_flags(int id, int extra) {
+    ConvCfg c = p.cfgs[id];
+    c.flags |= extra;
+    return cfg_id(c);
+  }
+
   int new_val(int kind, int ch, int unit, bool relu_out) {
     Val v; v.kind = kind; v.ch = ch; v.unit = unit; v.relu_out = relu_out;
     vals.push_back(v);
@@ -544,6 +554,9 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   Sched fs(B, p.persistent), bs(B, p.persistent);
   int n_ain = 0;  // valid samples so far (index into the stem-input arena)
 
+  // fold feat * map (and its backward) into the neighbouring conv epilogues; only the persistent executor implements it
+  static const bool no_fuse = std::getenv("PNMN_NOFUSE") != nullptr;
+  const bool fuse_attend = p.persistent && !no_fuse;
   const int HF = F_HALF;    // every conv / attend output is the fp16 operand of the next conv (and of wgrad)
   const int EHF = EF_HALF;
   p.nmaps = 1;  // map 0 = the constant all-ones attention of `scene` (nmn.py:216)
@@ -685,6 +698,16 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           const float* x = featp;
           if (a.kind == VK_ONES) {
             r.x0_is_feat = true;  // feats * ones == feats: feed the stem output straight in
+          } else if (fuse_attend && a.kind == VK_MAP && a.dotsig_proto >= 0 && !a.attend_fused) {
+            // the map comes out of a conv epilogue (fused 1x1 head): let that epilogue write feat * map as well
+            r.x0_unit = bd.alloc16();
+            r.attend_fused = true;
+            bd.vals[r.in0].attend_fused = true;
+            ConvProto& pr = fs.protos[a.dotsig_proto];
+            pr.t.aux[0] = featp;
+            pr.t.in[1][0] = Builder::shadow(bd.p16(r.x0_unit), kP16);
+            pr.t.cfg = bd.cfg_with_flags(pr.t.cfg, F_ATTEND);
+            x = bd.p16(r.x0_unit);
           } else {
             r.x0_unit = bd.alloc16();
             EltTask e{}; e.op = OP_ATTEND; e.flags = EHF; e.a = featp; e.b = bd.mapp(a.unit); e.o = bd.p16(r.x0_unit);
@@ -710,7 +733,8 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
               t.w3 = bd.param(md.head_w); t.b3 = bd.param(md.head_b);
               flops += 2ll * 196 * 128;
             }
-            fs.add_conv(n, t, fin.P == kP22.P ? 1 : 0);
+            const int proto = fs.add_conv(n, t, fin.P == kP22.P ? 1 : 0);
+            if (last && head) bd.vals[r.out].dotsig_proto = proto;
             x = t.out[0];
             n_conv3++;
           }
@@ -867,6 +891,16 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
               Val& fv = bd.vals[feat_val];
               t.cfg = bd.make_cfg(8, 8, 9, d, f, kP16, kP16, F_STORE | (fv.gwritten ? F_ACCUM : 0));
               t.out[0] = const_cast<float*>(dfeatp);
+              fv.gwritten = true;
+              bs.add_conv(n, t, 0);
+            } else if (fuse_attend) {
+              // dX0 never touches memory: the epilogue turns it into dmap += <dX0, feat> and dfeat (+)= dX0 * map
+              Val& fv = bd.vals[feat_val];
+              t.cfg = bd.make_cfg(8, 8, 9, d, f, kP16, kP16, F_ATTBWD | (fv.gwritten ? F_ACCUM : 0));
+              t.out[0] = const_cast<float*>(dfeatp);
+              t.aux[0] = featp;
+              t.map_out[0] = bd.mapp(a.unit);
+              t.in[1][0] = bd.dmapp(a.unit);
               fv.gwritten = true;
               bs.add_conv(n, t, 0);
             } else {
