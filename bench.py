@@ -262,7 +262,9 @@ def run_ours(args):
     L.lib().pnmn_debug_host_times(host_ms)
     sampler = ClockSampler(local)
     sampler.start()
+    L.lib().pnmn_launch_count(1)
     ms = timed(resident_step, args.steps)
+    own_launches = int(L.lib().pnmn_launch_count(1))
     sampler.stop_flag = True
     L.lib().pnmn_debug_host_times(host_ms)
     host_ms_per_step = {"plan_create": host_ms[0] / args.steps, "forward_call": host_ms[1] / args.steps,
@@ -310,7 +312,7 @@ def run_ours(args):
                 "ms_per_step": ms_e2e / args.steps,
                 "pipeline": "pinned host buffers; the copy of step i+1 runs on a side stream during step i (feed.DevicePrefetcher); "
                             "loss.item() every step"},
-        "gpu_launches": int((stats[3] + stats[4] + 5) * args.steps),
+        "gpu_launches": own_launches,
         "roofline": {
             "bound": "tensor", "kernel": "exec_kernel (persistent tcgen05 kind::f16 shift-GEMM executor: forward + dgrad launches)",
             "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src,

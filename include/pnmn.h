@@ -114,6 +114,9 @@ int pnmn_nmn_backward(pnmn_plan* p, const pnmn_buffers* bufs, const float* grad_
  * or stacked (stack_rows = 1: [3*rows][cols]); chunk order (hi, lo, hi) if second_low else (hi, hi, lo). */
 int pnmn_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int stack_rows, int second_low, void* stream);
 
+/* kernels launched by the library so far (reset != 0 clears the counter); bench.py reports it as "gpu_launches" */
+long long pnmn_launch_count(int reset);
+
 /* Optional per-launch device timing (CUDA events on the launching stream), used by bench.py for the
  * roofline of the dominant kernel.  ms / launches have 8 slots: {elementwise, conv<2 samples x 2 tiles>,
  * conv<1 x 3>, wgrad, bias_grad, weight pack, feature layout, other}.  Reading synchronises and clears. */

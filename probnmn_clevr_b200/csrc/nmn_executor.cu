@@ -118,7 +118,16 @@ int add_conv_w(pnmn_model* m, int64_t w, int64_t b, int cin, int ksize, bool nee
 
 }  // namespace
 
-namespace pnmn { void set_last_error(const std::string& s) { g_err = s; } }
+namespace pnmn {
+void set_last_error(const std::string& s) { g_err = s; }
+static long long g_launch_count = 0;   // kernels launched by the library (bench.py "gpu_launches")
+void count_launches(int n) { g_launch_count += n; }
+}
+extern "C" long long pnmn_launch_count(int reset) {
+  const long long v = pnmn::g_launch_count;
+  if (reset) pnmn::g_launch_count = 0;
+  return v;
+}
 
 extern "C" int pnmn_version(void) { return PNMN_VERSION; }
 extern "C" const char* pnmn_last_error(void) { return g_err.c_str(); }
@@ -304,15 +313,21 @@ struct Sched {
   }
 
   // Persistent-executor order: one list, every task names the tasks of its samples' previous stage.
-  void flatten_persistent(std::vector<TaskRec>& out, std::vector<TaskMeta>& meta) {
+  // Persistent-executor order: one list, every task names the tasks of its samples' previous stage.
+  // PNMN_EST_ORDER=1 additionally sorts the list by each task's ESTIMATED start time (critical-path times from a per-task
+  // cost model) instead of keeping it step-aligned.  Measured on the bench workload: no gain (2.68 vs 2.70 ms; the span
+  // is set by the longest chain, not by lock-step between chains) for 0.7 ms more host time, hence off by default.
+  void flatten_persistent(std::vector<TaskRec>& out, std::vector<TaskMeta>& meta, const std::vector<ConvCfg>& cfgs) {
     struct Latest { int n = 0; int ids[4] = {0, 0, 0, 0}; int stamp = -1; };
     std::vector<Latest> latest(step.size()), next(step.size());
+    std::vector<float> chain_t(step.size(), 0.f), next_t(step.size(), 0.f), est;
     size_t total = elts.size();
     for (auto& b : buckets) total += b[LK_CONV0].size() * 2 + b[LK_CONV1].size() * 3;
     out.reserve(total);
     meta.reserve(total);
+    est.reserve(total);
     int cur = 0;
-    auto push = [&](const void* rec, int type, const int* samples, int ns) {
+    auto push = [&](const void* rec, int type, const int* samples, int ns, float dur) {
       out.emplace_back();
       std::memcpy(out.back().b, rec, 128);
       meta.emplace_back();
@@ -321,6 +336,9 @@ struct Sched {
       for (int k = 0; k < kMaxDeps; ++k) m.deps[k] = -1;
       const int id = static_cast<int>(out.size()) - 1;
       static const bool no_deps = std::getenv("PNMN_NODEPS") != nullptr;  // diagnostics: throughput without dependencies (results are garbage)
+      float start = 0.f;
+      for (int k = 0; k < ns; ++k) start = std::max(start, chain_t[samples[k]]);
+      est.push_back(start);
       for (int k = 0; k < ns; ++k) {
         const Latest& l = latest[samples[k]];
         for (int j = 0; j < (no_deps ? 0 : l.n); ++j) {
@@ -328,23 +346,49 @@ struct Sched {
           else dep_overflow = true;
         }
         Latest& nx = next[samples[k]];
-        if (nx.stamp != cur) { nx.stamp = cur; nx.n = 0; }
+        if (nx.stamp != cur) { nx.stamp = cur; nx.n = 0; next_t[samples[k]] = 0.f; }
         if (nx.n < 4) nx.ids[nx.n++] = id;
         else dep_overflow = true;
+        next_t[samples[k]] = std::max(next_t[samples[k]], start + dur);
       }
+    };
+    // measured body times (profiles/r1 trace): ~8 us fixed + 0.14 us per MMA and accumulator (0.095 for the long stem conv)
+    auto conv_us = [&](const ConvTask& t) {
+      const ConvCfg& c = cfgs[t.cfg];
+      const float mm = static_cast<float>(c.n_kb * c.ntaps);
+      return 8.f + (mm <= 100.f ? 0.14f : 0.095f) * mm * static_cast<float>(t.n_samp * t.n_mt);
+    };
+    auto elt_us = [](const EltTask& e) {
+      return e.op == OP_SAME ? 12.f : (e.op == OP_SAME_BWD ? 22.f : ((e.op == OP_MINMAX || e.op == OP_MINMAX_BWD) ? 4.f : 9.f));
     };
     for (auto& b : buckets) {
       for (int kind = LK_CONV0; kind <= LK_CONV1; ++kind)
-        group_convs(b[kind], kind, [&](const ConvTask& t, const int* samples, int ns) { push(&t, TASK_CONV, samples, ns); });
-      for (int i : b[LK_ELT]) push(&elts[i], TASK_ELT, &elt_sample[i], 1);
+        group_convs(b[kind], kind, [&](const ConvTask& t, const int* samples, int ns) { push(&t, TASK_CONV, samples, ns, conv_us(t)); });
+      for (int i : b[LK_ELT]) push(&elts[i], TASK_ELT, &elt_sample[i], 1, elt_us(elts[i]));
       // a sample has exactly one stage per step: its `latest` set becomes this step's task ids
       for (int kind = 0; kind < 3; ++kind)
         for (int i : b[kind]) {
           const int smp = kind == LK_ELT ? elt_sample[i] : protos[i].sample;
-          if (next[smp].stamp == cur) { latest[smp] = next[smp]; next[smp].stamp = -1; }
+          if (next[smp].stamp == cur) { latest[smp] = next[smp]; next[smp].stamp = -1; chain_t[smp] = next_t[smp]; }
         }
       ++cur;
     }
+    static const bool est_order = std::getenv("PNMN_EST_ORDER") != nullptr;
+    if (!est_order || out.empty()) return;
+    const int n = static_cast<int>(out.size());
+    std::vector<int> order(n), newpos(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return est[a] < est[c]; });
+    for (int i = 0; i < n; ++i) newpos[order[i]] = i;
+    std::vector<TaskRec> out2(n);
+    std::vector<TaskMeta> meta2(n);
+    for (int i = 0; i < n; ++i) {
+      out2[i] = out[order[i]];
+      meta2[i] = meta[order[i]];
+      for (int k = 0; k < meta2[i].n_deps; ++k) meta2[i].deps[k] = newpos[meta2[i].deps[k]];
+    }
+    out.swap(out2);
+    meta.swap(meta2);
   }
 };
 
@@ -557,6 +601,9 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   // fold feat * map (and its backward) into the neighbouring conv epilogues; only the persistent executor implements it
   static const bool no_fuse = std::getenv("PNMN_NOFUSE") != nullptr;
   const bool fuse_attend = p.persistent && !no_fuse;
+  // (Tried and dropped, profiles/r1_notes: storing conv outputs that only feed other convs as fp16 planes alone, with
+  // fp16 ReLU masks in the backward, cuts the executor's DRAM traffic by a third but not its time: the epilogue is
+  // latency-bound, not store-bound, and the extra mask path cost registers.)
   const int HF = F_HALF;    // every conv / attend output is the fp16 operand of the next conv (and of wgrad)
   const int EHF = EF_HALF;
   p.nmaps = 1;  // map 0 = the constant all-ones attention of `scene` (nmn.py:216)
@@ -834,7 +881,8 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             const int du = bd.alloc16();
             ConvTask t{};
             t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_STORE | F_MASK | F_HALF);
-            t.in[0][0] = Builder::shadow(dz, kP16); t.out[0] = bd.p16(du); t.aux[0] = bd.p16(r.y_unit[i - 1]);
+            t.in[0][0] = Builder::shadow(dz, kP16); t.out[0] = bd.p16(du);
+            t.aux[0] = bd.p16(r.y_unit[i - 1]);
             t.w = bd.packed(cw.pk_bwd);
             bs.add_conv(n, t, 0);
             dz = bd.p16(du);
@@ -884,7 +932,8 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
               const PlaneFmt fprev = fmt_for_dilation(dil_of(i - 1));
               const int du = bd.alloc_fmt(fprev);
               t.cfg = bd.make_cfg(8, 8, 9, d, f, fprev, f, F_STORE | F_MASK | F_HALF);
-              t.out[0] = bd.pfmt(fprev, du); t.aux[0] = xin_i;
+              t.out[0] = bd.pfmt(fprev, du);
+              t.aux[0] = xin_i;
               bs.add_conv(n, t, f.P == kP22.P ? 1 : 0);
               dz = t.out[0];
             } else if (r.x0_is_feat) {
@@ -927,7 +976,8 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
       const ConvW& c2 = m->convs[m->stem2];
       ConvTask t{};
       t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_STORE | F_MASK | F_HALF);
-      t.in[0][0] = Builder::shadow(dfeatp, kP16); t.out[0] = bd.p16(dz1); t.aux[0] = bd.p16(y1s_unit[n]);
+      t.in[0][0] = Builder::shadow(dfeatp, kP16); t.out[0] = bd.p16(dz1);
+      t.aux[0] = bd.p16(y1s_unit[n]);
       t.w = bd.packed(c2.pk_bwd);
       bs.add_conv(n, t, 0);
       add_inst(m->stem2, dfeatp, bd.p16(y1s_unit[n]), kP16, 1);
@@ -939,10 +989,10 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
 
   // ---------------- flatten ----------------
   const auto t_emit = std::chrono::steady_clock::now();
-  if (p.persistent) fs.flatten_persistent(p.ftask, p.fmeta);
+  if (p.persistent) fs.flatten_persistent(p.ftask, p.fmeta, p.cfgs);
   else fs.flatten(p.felt, p.fconv, p.flaunch);
   if (p.need_grad) {
-    if (p.persistent) bs.flatten_persistent(p.btask, p.bmeta);
+    if (p.persistent) bs.flatten_persistent(p.btask, p.bmeta, p.cfgs);
     else bs.flatten(p.belt, p.bconv, p.blaunch);
     // wgrad / bias-grad tasks per weight tensor
     const int64_t inst_base = 0;
@@ -1273,6 +1323,7 @@ extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const f
   }
   if (p.persistent) {
     uint8_t* blob = static_cast<uint8_t*>(bufs->blob);
+    pnmn::count_launches(5);   // resolve, pack_weights, fill_ones_map, nchw_to_planes, exec_kernel
     ProfScope prof(PK_CONV0, st);
     CUDA_OK(launch_exec(blob + p.off_ftask, reinterpret_cast<const TaskMeta*>(blob + p.off_fmeta),
                         static_cast<int>(p.ftask.size()), reinterpret_cast<const ConvCfg*>(blob + p.off_cfg),
@@ -1326,6 +1377,7 @@ extern "C" int pnmn_nmn_backward(pnmn_plan* pp, const pnmn_buffers* bufs, const 
   CUDA_OK(launch_loss_scale(grad_final_out, static_cast<size_t>(p.B) * 128 * 196, bufs->scratch, st));
   if (p.persistent) {
     uint8_t* blob = static_cast<uint8_t*>(bufs->blob);
+    pnmn::count_launches(9);   // 4 x resolve, amax + loss scale, exec_kernel, wgrad_tc, bias_grad
     {
       ProfScope prof(PK_CONV0, st);
       CUDA_OK(launch_exec(blob + p.off_btask, reinterpret_cast<const TaskMeta*>(blob + p.off_bmeta),
@@ -1374,6 +1426,7 @@ extern "C" int pnmn_split3_bf16(const float* src, void* dst, int64_t rows, int64
                                 void* stream) {
   if (!src || !dst || rows < 0 || cols < 0 || cols % 4 != 0) return fail("pnmn_split3_bf16: bad arguments (cols must be a multiple of 4)");
   CUDA_OK(launch_split3_bf16(src, dst, rows, cols, stack_rows, second_low, static_cast<cudaStream_t>(stream)));
+  pnmn::count_launches(1);
   return 0;
 }
 

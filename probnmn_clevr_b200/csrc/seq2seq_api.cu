@@ -16,7 +16,7 @@
 using namespace pnmn;
 
 extern "C" const char* pnmn_last_error(void);
-namespace pnmn { void set_last_error(const std::string& s); }
+namespace pnmn { void set_last_error(const std::string& s); void count_launches(int n); }
 
 namespace {
 
@@ -247,6 +247,7 @@ extern "C" int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const
   f.raw_out = raw_predictions; f.pred_out = predictions; f.loss = loss; f.logits_out = logits_out;
   f.coef = at<float>(ws, L.coef); f.label = at<int>(ws, L.label);
   CUDA_OK(launch_finalize(f, st));
+  pnmn::count_launches(6 + 2 * d.Ts + 2 * d.S + 1);   // prepare, pack, 3 tables, encoder steps, decoder row + step kernels, finalize
   return 0;
 }
 
@@ -392,5 +393,6 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
     s.B = scale + 2; s.sbk = 0; s.sbn = 0; s.N = 1; s.C = grads + m->out_b; s.ldc = 1;
     CUDA_OK(launch_simt_gemm(s, st));
   }
+  pnmn::count_launches(1 + 2 * d.S + 1 + 4 * d.Ts + 5 + 3 + 3 + 6);   // scale, decoder, encoder, wgrads, tables, biases, small GEMMs
   return 0;
 }
