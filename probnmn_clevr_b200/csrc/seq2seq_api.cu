@@ -267,6 +267,8 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
   CUDA_OK(launch_seq_loss_scale(grad_loss, d.B, scale, st));
   CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dh), 0, 4 * L.slotf, st));
   CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dc), 0, 4 * L.slotf, st));
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.datt), 0, 4 * L.slotf, st));
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dout0), 0, 4 * L.slotf * d.Ts, st));
   CUDA_OK(cudaMemsetAsync(at<float>(ws, L.denc), 0, 4ll * d.B * d.Ts * kSH, st));
   CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dP0), 0, 4ll * d.Vs * kSG, st));
   CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dPd), 0, 4ll * d.Vt * kSG, st));

@@ -115,18 +115,17 @@ __device__ __forceinline__ void epi_lstm(const GemmArgs& g, int b, int nt, const
   if (g.out_op) store_op16(g.out_op, g.out_op_lo, b, j0, ov);
 }
 
-// acc[c], c in [0, 64): column n = nt*64 + c of [dA1 | dA2]
+// acc[c], c in [0, 64): column n = nt*64 + c of [dA1 | dA2].  The K range is split over blockIdx.z, so the partial
+// sums are ADDED (fire-and-forget reductions) into buffers whose consumers left them zeroed; masked rows (beyond the
+// sequence length) contribute nothing: carried state stays, per-step outputs stay zero.
 __device__ __forceinline__ void epi_dgrad(const GemmArgs& g, int b, int nt, const float* acc) {
   if (b >= g.B) return;
+  if (g.len && g.t >= g.len[b]) return;
   const int n0 = nt * 64, which = n0 >> 8, col0 = n0 & 255;
-  const bool masked = g.len && g.t >= g.len[b];
-  if (masked && g.keep_masked[which]) return;
-  const float s = masked ? 0.f : g.scale[1];
+  const float s = g.scale[1];
   float* od = g.out[which] + static_cast<size_t>(b) * kSH + col0;
 #pragma unroll
-  for (int q4 = 0; q4 < 16; ++q4)
-    *reinterpret_cast<float4*>(od + 4 * q4) =
-        make_float4(acc[4 * q4] * s, acc[4 * q4 + 1] * s, acc[4 * q4 + 2] * s, acc[4 * q4 + 3] * s);
+  for (int c = 0; c < 64; ++c) red_add_f32(od + c, acc[c] * s);
 }
 
 // ---- tensor-core kernel ------------------------------------------------------------------------------
@@ -137,7 +136,9 @@ __global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmAr
   uint8_t* ring = smem + kGHeader;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nt = blockIdx.x, mt = blockIdx.y;
-  const int n_chunks = g.K / 64;
+  // K chunks [kc_lo, kc_hi) of this CTA (EPI_DGRAD splits K over blockIdx.z; EPI_LSTM runs with gridDim.z == 1)
+  const int kc_lo = (g.K / 64) * blockIdx.z / gridDim.z, kc_hi = (g.K / 64) * (blockIdx.z + 1) / gridDim.z;
+  const int n_chunks = kc_hi - kc_lo;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGStages; ++i) {
@@ -155,9 +156,10 @@ __global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmAr
 
   if (warp == 0) {
     if (lane == 0) {
-      for (int kc = 0; kc < n_chunks; ++kc) {
-        const int st = kc % kGStages;
-        mbar_wait(smem_u32(&hdr->empty[st]), ((kc / kGStages) & 1) ^ 1);
+      for (int it = 0; it < n_chunks; ++it) {
+        const int kc = kc_lo + it;
+        const int st = it % kGStages;
+        mbar_wait(smem_u32(&hdr->empty[st]), ((it / kGStages) & 1) ^ 1);
         const uint32_t bar = smem_u32(&hdr->full[st]);
         mbar_arrive_expect_tx(bar, kGStage);
         const int si = kc / g.chunks_per_src, cj = kc % g.chunks_per_src;
@@ -176,7 +178,7 @@ __global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmAr
       // K-major, no swizzle: LBO = distance between the two 8-deep halves of a k16 step (one plane), SBO = 128 B
       const uint64_t a_hi = make_smem_desc(0, 128 * 16, 128) & 0xFFFFFFFFFFFFC000ull;
       const uint64_t w_hi = make_smem_desc(0, 64 * 16, 128) & 0xFFFFFFFFFFFFC000ull;
-      for (int kc = 0; kc < n_chunks; ++kc) {
+      for (int kc = 0; kc < n_chunks; ++kc) {   // kc counts this CTA's chunks
         const int st = kc % kGStages;
         mbar_wait(smem_u32(&hdr->full[st]), (kc / kGStages) & 1);
         tc_fence_after();
@@ -239,7 +241,8 @@ __global__ void __launch_bounds__(128) step_gemm_simt_kernel(const GemmArgs g) {
 }
 
 cudaError_t launch_step_gemm(const GemmArgs& g, int epilogue, int n_tiles, int m_tiles, bool simt, cudaStream_t st) {
-  const dim3 grid(n_tiles, m_tiles);
+  // the data-gradient GEMMs have K = 1024 and few output tiles: split K four ways (partial sums are reduced with atomics)
+  const dim3 grid(n_tiles, m_tiles, (epilogue == EPI_DGRAD && !simt) ? 4 : 1);
   if (simt) {
     if (epilogue == EPI_LSTM) step_gemm_simt_kernel<EPI_LSTM><<<grid, 128, 0, st>>>(g);
     else step_gemm_simt_kernel<EPI_DGRAD><<<grid, 128, 0, st>>>(g);

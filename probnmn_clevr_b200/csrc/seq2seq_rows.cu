@@ -343,6 +343,8 @@ __global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a)
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int t = a.t;
   float dh = a.dh[static_cast<size_t>(b) * kSH + tid];
+  // dh / datt are accumulation targets of the next data-gradient GEMM (split-K partial sums): leave them zeroed
+  if (t >= 0) a.dh[static_cast<size_t>(b) * kSH + tid] = 0.f;
 
   if (a.do_attn) {
     // attention of step ta = t+1 used h_t (slot ta): scores_s = enc_s . h, p = masked_softmax, att = sum p_s enc_s
@@ -351,6 +353,7 @@ __global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a)
     float* denc = a.denc + static_cast<size_t>(b) * d.Ts * kSH;
     const int len = a.src_len[b];
     const float datt = a.datt[static_cast<size_t>(b) * kSH + tid];
+    const_cast<float*>(a.datt)[static_cast<size_t>(b) * kSH + tid] = 0.f;
     const float hq = a.h_dec[(static_cast<size_t>(ta) * d.Bp + b) * kSH + tid];
     s_datt[tid] = datt;
     if (tid < d.Ts) s_p[tid] = a.attn_p[(static_cast<size_t>(ta) * d.B + b) * d.Ts + tid];
@@ -425,6 +428,7 @@ __global__ void __launch_bounds__(256) enc_cell_bwd_kernel(const EncCellBwdArgs 
   float da[4] = {0.f, 0.f, 0.f, 0.f};
   if (valid) {
     float dh = a.dh[static_cast<size_t>(b) * kSH + tid];
+    a.dh[static_cast<size_t>(b) * kSH + tid] = 0.f;   // the data-gradient GEMM of this step accumulates the new value
     if (a.dext) dh += a.dext[static_cast<size_t>(b) * a.dext_stride + tid];
     const float* gt = a.gates + static_cast<size_t>(b) * kSG;
     float dc_prev;
@@ -610,8 +614,9 @@ __global__ void __launch_bounds__(256) simt_gemm_kernel(const SimtGemm g) {
     }
 }
 cudaError_t launch_simt_gemm(const SimtGemm& g, cudaStream_t st) {
+  // few output tiles and a long contraction: split K over blockIdx.z (atomics), needs an accumulation target
   int kz = 1;
-  if (g.K >= 2048 && g.accumulate) kz = 16;
+  if (g.accumulate && g.K >= 512) kz = g.K >= 2048 ? 16 : g.K / 128;
   simt_gemm_kernel<<<dim3((g.N + 31) / 32, (g.M + 31) / 32, kz), 256, 0, st>>>(g);
   return cudaGetLastError();
 }
