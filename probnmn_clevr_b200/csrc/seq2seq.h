@@ -36,6 +36,28 @@ __host__ __device__ inline size_t wp_off(int n, int k, int K) {
   return (static_cast<size_t>(n >> 6) * (K >> 3) + (k >> 3)) * 512 + static_cast<size_t>(n & 63) * 8 + (k & 7);
 }
 
+// Programmatic dependent launch: the ~110 dependent per-step kernels of a pass are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization; each one lets its successor start at once
+// (pdl_launch_dependents) and blocks (pdl_wait) only where it first touches data of its predecessor, so the launch
+// gap, barrier / TMEM set-up and the weight prefetch of step t+1 overlap with step t.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+#ifdef __CUDACC__
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl,
+                              Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+#endif
+bool seq_use_pdl();   // PNMN_PG_NOPDL=1 disables it (diagnostics)
+
 __device__ __forceinline__ void split_f16(float x, __half& hi, __half& lo) {
   x = fminf(fmaxf(x, -65504.f), 65504.f);
   hi = __float2half_rn(x);

@@ -10,10 +10,17 @@
 // the accumulators back with tcgen05.ld for the fused epilogue.  Warp roles: 0 = copy producer,
 // 1 = MMA issuer, 2 = TMEM allocation, 4..7 = epilogue (one TMEM lane quarter each).
 // Each kernel has a CUDA-core twin with the same epilogue (PNMN_PG_SIMT=1, bring-up only).
+#include <cstdlib>
+
 #include "seq2seq.h"
 #include "tcgen05.cuh"
 
 namespace pnmn {
+
+bool seq_use_pdl() {
+  static const bool v = std::getenv("PNMN_PG_NOPDL") == nullptr;
+  return v;
+}
 
 constexpr int kGThreads = 256;
 constexpr int kGStages = 4;
@@ -139,6 +146,7 @@ __global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmAr
   // K chunks [kc_lo, kc_hi) of this CTA (EPI_DGRAD splits K over blockIdx.z; EPI_LSTM runs with gridDim.z == 1)
   const int kc_lo = (g.K / 64) * blockIdx.z / gridDim.z, kc_hi = (g.K / 64) * (blockIdx.z + 1) / gridDim.z;
   const int n_chunks = kc_hi - kc_lo;
+  pdl_launch_dependents();
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGStages; ++i) {
@@ -156,20 +164,34 @@ __global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmAr
 
   if (warp == 0) {
     if (lane == 0) {
+      // the packed weights were written long before the previous step: prefetch them for the first ring pass, THEN wait
+      // for the previous kernel (whose epilogue produces this step's activation operand)
+      const int pre = n_chunks < kGStages ? n_chunks : kGStages;
+      for (int it = 0; it < pre; ++it) {
+        const uint32_t bar = smem_u32(&hdr->full[it]);
+        mbar_arrive_expect_tx(bar, kGStage);
+        const __half* w = g.w + (static_cast<size_t>(nt) * (g.K >> 3) + (kc_lo + it) * 8) * 512;
+        const uint32_t dst = smem_u32(ring + it * kGStage);
+        bulk_g2s(dst + 2 * kGABytes, w, kGWBytes, bar);
+        bulk_g2s(dst + 2 * kGABytes + kGWBytes, w + g.w_lo, kGWBytes, bar);
+      }
+      pdl_wait();
       for (int it = 0; it < n_chunks; ++it) {
         const int kc = kc_lo + it;
         const int st = it % kGStages;
-        mbar_wait(smem_u32(&hdr->empty[st]), ((it / kGStages) & 1) ^ 1);
         const uint32_t bar = smem_u32(&hdr->full[st]);
-        mbar_arrive_expect_tx(bar, kGStage);
+        const uint32_t dst = smem_u32(ring + st * kGStage);
+        if (it >= pre) {
+          mbar_wait(smem_u32(&hdr->empty[st]), ((it / kGStages) & 1) ^ 1);
+          mbar_arrive_expect_tx(bar, kGStage);
+          const __half* w = g.w + (static_cast<size_t>(nt) * (g.K >> 3) + kc * 8) * 512;
+          bulk_g2s(dst + 2 * kGABytes, w, kGWBytes, bar);
+          bulk_g2s(dst + 2 * kGABytes + kGWBytes, w + g.w_lo, kGWBytes, bar);
+        }
         const int si = kc / g.chunks_per_src, cj = kc % g.chunks_per_src;
         const __half* a = g.a[si] + (static_cast<size_t>(mt) * (g.a_K[si] >> 3) + cj * 8) * 1024;
-        const __half* w = g.w + (static_cast<size_t>(nt) * (g.K >> 3) + kc * 8) * 512;
-        const uint32_t dst = smem_u32(ring + st * kGStage);
         bulk_g2s(dst, a, kGABytes, bar);
         bulk_g2s(dst + kGABytes, a + g.a_lo[si], kGABytes, bar);
-        bulk_g2s(dst + 2 * kGABytes, w, kGWBytes, bar);
-        bulk_g2s(dst + 2 * kGABytes + kGWBytes, w + g.w_lo, kGWBytes, bar);
       }
     }
   } else if (warp == 1) {
@@ -200,6 +222,7 @@ __global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmAr
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int b = mt * 128 + q * 32 + lane;
+    pdl_wait();   // the epilogue reads state written by the previous step's kernel
     mbar_wait(smem_u32(&hdr->tmem_full), 0);
     tc_fence_after();
     uint32_t v0[32], v1[32];
@@ -256,9 +279,9 @@ cudaError_t launch_step_gemm(const GemmArgs& g, int epilogue, int n_tiles, int m
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  if (epilogue == EPI_LSTM) step_gemm_tc_kernel<EPI_LSTM><<<grid, kGThreads, kGSmem, st>>>(g);
-  else step_gemm_tc_kernel<EPI_DGRAD><<<grid, kGThreads, kGSmem, st>>>(g);
-  return cudaGetLastError();
+  const bool pdl = seq_use_pdl();
+  if (epilogue == EPI_LSTM) return launch_pdl(step_gemm_tc_kernel<EPI_LSTM>, grid, dim3(kGThreads), kGSmem, st, pdl, g);
+  return launch_pdl(step_gemm_tc_kernel<EPI_DGRAD>, grid, dim3(kGThreads), kGSmem, st, pdl, g);
 }
 
 // =====================================================================================================

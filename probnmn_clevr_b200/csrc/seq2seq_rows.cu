@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(256) dec_row_kernel(const DecRowArgs a) {
   const SeqDims& d = a.d;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int t = a.t;
+  pdl_launch_dependents();
+  pdl_wait();
   sh[tid] = a.h_dec[(static_cast<size_t>(t) * d.Bp + b) * kSH + tid];
   __syncthreads();
 
@@ -261,8 +263,7 @@ __global__ void __launch_bounds__(256) dec_row_kernel(const DecRowArgs a) {
   if (tid < kSH / 8) store_op8(a.att_op + static_cast<size_t>(t) * a.att_step, a.att_lo, b, tid * 8, kSH, satt + tid * 8, 1.f);
 }
 cudaError_t launch_dec_row(const DecRowArgs& a, cudaStream_t st) {
-  dec_row_kernel<<<a.d.B, 256, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(dec_row_kernel, dim3(a.d.B), dim3(256), 0, st, seq_use_pdl(), a);
 }
 
 // =====================================================================================================
@@ -342,6 +343,8 @@ __global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a)
   const SeqDims& d = a.d;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int t = a.t;
+  pdl_launch_dependents();
+  pdl_wait();
   float dh = a.dh[static_cast<size_t>(b) * kSH + tid];
   // dh / datt are accumulation targets of the next data-gradient GEMM (split-K partial sums): leave them zeroed
   if (t >= 0) a.dh[static_cast<size_t>(b) * kSH + tid] = 0.f;
@@ -416,14 +419,15 @@ __global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a)
   if (tid < kSG / 8) store_op8(a.dg_op + static_cast<size_t>(t) * a.dg_step, a.dg_lo, b, tid * 8, kSG, s_dg + tid * 8, a.scale[0]);
 }
 cudaError_t launch_dec_bwd_row(const DecBwdRowArgs& a, cudaStream_t st) {
-  dec_bwd_row_kernel<<<a.d.B, 256, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(dec_bwd_row_kernel, dim3(a.d.B), dim3(256), 0, st, seq_use_pdl(), a);
 }
 
 // encoder: LSTM cell backward of one (layer, step); rows beyond their length carry dh / dc through unchanged
 __global__ void __launch_bounds__(256) enc_cell_bwd_kernel(const EncCellBwdArgs a) {
   __shared__ __align__(16) float s_dg[kSG];
   const int b = blockIdx.x, tid = threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
   const bool valid = a.t < a.src_len[b];
   float da[4] = {0.f, 0.f, 0.f, 0.f};
   if (valid) {
@@ -441,8 +445,7 @@ __global__ void __launch_bounds__(256) enc_cell_bwd_kernel(const EncCellBwdArgs 
   if (tid < kSG / 8) store_op8(a.dg_op, a.dg_lo, b, tid * 8, kSG, s_dg + tid * 8, a.scale[0]);
 }
 cudaError_t launch_enc_cell_bwd(const EncCellBwdArgs& a, cudaStream_t st) {
-  enc_cell_bwd_kernel<<<a.B, 256, 0, st>>>(a);
-  return cudaGetLastError();
+  return launch_pdl(enc_cell_bwd_kernel, dim3(a.B), dim3(256), 0, st, seq_use_pdl(), a);
 }
 
 // =====================================================================================================
