@@ -39,8 +39,23 @@ __device__ __forceinline__ void st_half4(float* base, int kc, int s, float4 v) {
   *reinterpret_cast<uint2*>(hb + (static_cast<size_t>(kc >> 1) * 256 + s) * 16 + (kc & 1) * 8) =
       make_uint2(elt_pack_half2(v.x, v.y), elt_pack_half2(v.z, v.w));
 }
-__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
-__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+// Explicit global-space 16-byte accesses.  Every pointer of a task record is loaded from memory, so the compiler can only
+// emit GENERIC loads / stores (LD.E / ST.E) for plain dereferences; the .global forms keep the LSU on its fast path.
+__device__ __forceinline__ uint4 ldg128(const void* p) {
+  uint4 v;
+  asm volatile("ld.global.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void stg128(void* p, uint4 v) {
+  asm volatile("st.global.v4.b32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 ld4(const float* p) {
+  const uint4 v = ldg128(p);
+  return make_float4(__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w));
+}
+__device__ __forceinline__ void st4(float* p, float4 v) {
+  stg128(p, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+}
 
 __device__ __forceinline__ float elt_block_sum(float v, float* red, int tid) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

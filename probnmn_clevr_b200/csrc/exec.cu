@@ -20,6 +20,7 @@
 // the second CTA's mainloop fills the tensor pipe while the first one is in its epilogue or waiting.
 // A task therefore owns at most two accumulators (one sample x two M tiles, or two samples x one).
 #include <cuda_fp16.h>
+#include <cstdlib>
 #include <type_traits>
 
 #include "elt_body.cuh"
@@ -52,6 +53,7 @@ struct ExHeader {
   alignas(16) uint8_t task[128];
   alignas(16) float bias[128];
   alignas(16) float w3[128];
+  float dotp[kExMaxAcc][2][128];  // partial 64-channel dot products of the two column halves of an accumulator
   EltSmem elt;
 };
 static_assert(sizeof(ExHeader) <= kExHeader, "executor header");
@@ -61,10 +63,40 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+// two fp32 -> packed fp16x2 (a in the low half), round to nearest, saturating to +-65504: one F2FP instruction
+__device__ __forceinline__ uint32_t pack_half2_sat(float a, float b) {
+  uint32_t u;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a));
+  return u;
+}
+
+// fp32 -> tf32 (round to nearest, ties away: cvt.rna.tf32.f32), result as an fp32 bit pattern with 13 zero low bits.
+// Two integer instructions instead of the four ptxas emits for the cvt (no special case is needed: inf stays inf, the
+// largest finite values round to inf as they should).
+__device__ __forceinline__ uint32_t round_tf32(float x) { return (__float_as_uint(x) + 0x1000u) & 0xffffe000u; }
+// same with ReLU folded into the conversion
+__device__ __forceinline__ uint32_t pack_half2_relu_sat(float a, float b) {
+  uint32_t u;
+  asm("cvt.rn.relu.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(u) : "f"(b), "f"(a));
+  return u;
+}
+// h where the fp16 pair m is > 0, else 0 (ReLU backward on packed halves)
+__device__ __forceinline__ uint32_t mask_half2_gt0(uint32_t h, uint32_t m) {
+  const __half2 hv = *reinterpret_cast<const __half2*>(&h);
+  const __half2 mv = *reinterpret_cast<const __half2*>(&m);
+  const __half2 r = __hmul2(hv, __hgt2(mv, __float2half2_rn(0.f)));
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
 
 __device__ __forceinline__ int ex_tap_shift(const ConvCfg& c, int tap) {
   return c.ntaps == 9 ? ((tap / 3 - 1) * c.S_in + (tap % 3 - 1)) * c.dil : 0;
@@ -86,10 +118,11 @@ __device__ __forceinline__ int smid() {
 //   [4] SM id    [5] type | n_samp<<8 | n_mt<<16   [6] MMAs per (sample, M tile)   [7] cfg flags / elt op
 //   [8] roles start (after barrier B)  [9] first operands landed  [10] last MMA issued
 //   [11] accumulators complete  [12] epilogue stores issued  [13] epilogue fenced
+template <bool kTrace>
 __global__ void __launch_bounds__(kExThreads, kExCtasPerSM)
 exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ metas, int n_tasks,
             const ConvCfg* __restrict__ cfgs, int* __restrict__ counter, int* __restrict__ done,
-            long long* __restrict__ trace) {
+            long long* __restrict__ trace, int dbg) {
   extern __shared__ __align__(1024) uint8_t smem[];
   ExHeader* hdr = reinterpret_cast<ExHeader*>(smem);
   uint8_t* w_ring = smem + kExHeader;
@@ -124,7 +157,7 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
       if (lane == 0) idx = atomicAdd(counter, 1);
       idx = __shfl_sync(0xffffffffu, idx, 0);
       if (idx < n_tasks) {
-        if (trace && lane == 0) trace[idx * 16 + 0] = gtime();
+        if (kTrace && lane == 0) trace[idx * kTraceW + 0] = gtime();
         reinterpret_cast<uint32_t*>(hdr->task)[lane] = reinterpret_cast<const uint32_t*>(tasks + static_cast<size_t>(idx) * 128)[lane];
         if (lane < static_cast<int>(sizeof(TaskMeta) / 4))
           reinterpret_cast<uint32_t*>(&hdr->meta)[lane] = reinterpret_cast<const uint32_t*>(metas + idx)[lane];
@@ -132,11 +165,14 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
         if (lane < kMaxDeps) {
           const int d = hdr->meta.deps[lane];
           if (d >= 0) {
-            while (ld_acquire(done + d) == 0) __nanosleep(64);
+            // relaxed polls (an acquire load invalidates the SM's whole L1 on EVERY poll, which hurts the other CTA of
+            // this SM), then ONE acquire fence once every producer has published
+            while (ld_relaxed(done + d) == 0) __nanosleep(32);
           }
         }
         __syncwarp();
-        if (trace && lane == 0) { trace[idx * 16 + 1] = gtime(); trace[idx * 16 + 4] = smid(); }
+        asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (kTrace && lane == 0) { trace[idx * kTraceW + 1] = gtime(); trace[idx * kTraceW + 4] = smid(); }
       }
       if (lane == 0) hdr->task_idx = idx;
     }
@@ -217,7 +253,7 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
         // The whole warp runs the loop (uniform control flow and operands); one elected lane issues.
         {
           tc_fence_after();
-          if (trace && lane == 0) trace[idx * 16 + 8] = gtime();
+          if (kTrace && lane == 0) trace[idx * kTraceW + 8] = gtime();
           const uint32_t idesc = make_idesc_f16(128, 128, 0, 0);
           const uint64_t d_hi = make_smem_desc(0, 0, 128u) & 0xFFFFFFFF00000000ull;
           // K-major, no swizzle: LBO = distance between the two 8-channel halves of a 16-deep k-block
@@ -244,7 +280,7 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
               }
           uint32_t ua = __shfl_sync(0xffffffffu, na, 0), uw = __shfl_sync(0xffffffffu, nw, 0);
           long long wait_a = 0, wait_w = 0;
-          const bool tr = trace != nullptr;
+          constexpr bool tr = kTrace;
           const uint32_t bar_fa = smem_u32(&hdr->full_a[0]), bar_ea = smem_u32(&hdr->empty_a[0]);
           const uint32_t bar_fw = smem_u32(&hdr->full_w[0]), bar_ew = smem_u32(&hdr->empty_w[0]);
           const uint32_t d_hi32 = static_cast<uint32_t>(d_hi >> 32);
@@ -278,7 +314,7 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
                 mbar_wait(bar_fw + sw * 8, (uw / kExWStages) & 1);
                 if (tr) wait_w += clock64() - c0;
                 tc_fence_after();
-                if (tr && lane == 0 && kb == 0 && ty == 0) trace[idx * 16 + 9] = gtime();
+                if (tr && lane == 0 && kb == 0 && ty == 0) trace[idx * kTraceW + 9] = gtime();
                 if (elect_one()) {
 #pragma unroll
                   for (int tx = 0; tx < TPS; ++tx)
@@ -301,63 +337,127 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
           }
           if (elect_one()) umma_commit(smem_u32(&hdr->tmem_full));
           __syncwarp();
-          if (trace && lane == 0) { trace[idx * 16 + 10] = gtime(); trace[idx * 16 + 14] = wait_a; trace[idx * 16 + 15] = wait_w; }
+          if (kTrace && lane == 0) { trace[idx * kTraceW + 10] = gtime(); trace[idx * kTraceW + 14] = wait_a; trace[idx * kTraceW + 15] = wait_w; }
         }
-      } else if (warp >= 4) {
-        // ---------------- epilogue: 4 warps = the 4 TMEM lane quarters; a thread owns one pixel row x 128 channels ----
-        const int q = warp - 4;
-        float* out_s[2] = {tp->out[0], tp->out[1]};
-        const float* aux_s[2] = {tp->aux[0], tp->aux[1]};
-        float* map_s[2] = {tp->map_out[0], tp->map_out[1]};
+      }
+      __syncwarp();
+      {
+        // ---------------- epilogue: ALL 8 warps (the role warps join once their loops are done) ----------------
+        // A warp may only read the TMEM lane quarter (warp % 4); warps 4-7 take accumulator columns 0..63 of their
+        // quarter, warps 0-3 columns 64..127, so a thread owns one pixel row x 64 channels.  (Measured, profiles/r1:
+        // with 4 epilogue warps a 32-column chunk took 0.7 us even with every store removed -- one warp per scheduler
+        // running a dependent ALU chain -- and a warp can only issue ~8 B/clk of 16-byte stores.)
+        const int q = warp & 3;
+        const int half = warp < 4 ? 1 : 0;
+        const int prow = q * 32 + lane;  // pixel row of this thread inside the 128-row tile
         const float b3 = (flags & F_DOTSIG) ? __ldg(tp->b3) : 0.f;
         mbar_wait(smem_u32(&hdr->tmem_full), n_conv & 1);
         tc_fence_after();
-        if (trace && tid == 128) trace[idx * 16 + 11] = gtime();
+        if (kTrace && tid == 128) { trace[idx * kTraceW + 11] = gtime(); trace[idx * kTraceW + 20] = clock64(); }
         int acc_slot = 0;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (s >= n_samp) break;
-          float* const outp = out_s[s];
-          const float* const auxp = (flags & F_MASK) ? aux_s[s] : outp;  // F_MASK and F_ACCUM never combine
+        // (deliberately NOT unrolled over the samples: the kernel's code footprint decides how well it runs)
+#pragma unroll 1
+        for (int s = 0; s < n_samp; ++s) {
+          float* const outp = tp->out[s];
+          const float* const aux_ss = tp->aux[s];
+          float* const map_ss = tp->map_out[s];
+          void* const in1_ss = const_cast<void*>(tp->in[1][s]);
+          const float* const auxp = (flags & F_MASK) ? aux_ss : outp;  // F_MASK and F_ACCUM never combine
           uint8_t* const hb = reinterpret_cast<uint8_t*>(outp) + shadow_bytes(P_out);
           for (int mt = mt0; mt < mt0 + n_mt && acc_slot < kExMaxAcc; ++mt, ++acc_slot) {
-            const int r = mt * 128 + q * 32 + lane;
+            const int r = mt * 128 + prow;
             const int y = r / S_in, x = r - y * S_in;
             const bool valid = (y < kHW) && (x < kHW);
             const int so = y * S_out + x;
             const int sx = (flags & F_MASK) ? y * S_aux + x : so;
             const int Px = (flags & F_MASK) ? P_aux : P_out;
             float dot = 0.f;
+            // lean tasks: the output only feeds other convs (and wgrad / a ReLU mask): fp16 planes alone
+            const bool lean = (flags & F_HALF) && !(flags & (F_STORE | F_DOTSIG | F_ATTBWD | F_ACCUM | F_MASK));
+            // 16 accumulator columns per pass (4 fp32 planes / 2 fp16 half planes): everything a pass keeps live fits in
+            // registers -- a spilled value costs an L2 round trip here, because the other CTA's acquire / release
+            // traffic keeps invalidating the SM's L1
 #pragma unroll 1
-            for (int chunk = 0; chunk < 4; ++chunk) {
-              uint32_t v[32];
-              tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_slot * 128 + chunk * 32, v);
-              float4 ax[8];
+            for (int chunk = 4 * half; chunk < 4 * half + 4; ++chunk) {
+              uint32_t v[16];
+              tmem_ld16(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc_slot * 128 + chunk * 16, v);
+              if (lean) {
+                uint4 mh[2];
+                if (valid && (flags & F_MASK16)) {
+                  const uint8_t* mb = reinterpret_cast<const uint8_t*>(aux_ss) + (static_cast<size_t>(chunk * 2) * P_aux + (y * S_aux + x)) * 16;
+                  mh[0] = ldg128(mb);
+                  mh[1] = ldg128(mb + static_cast<size_t>(P_aux) * 16);
+                }
+                tmem_ld_wait();
+                if (kTrace && tid == 128 && acc_slot == 0 && chunk == 0) trace[idx * kTraceW + 16] = clock64();
+                if (valid) {
+                  if (flags & F_BIAS) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                      const float4 bz = *reinterpret_cast<const float4*>(&hdr->bias[chunk * 16 + j * 4]);
+                      v[4 * j] = __float_as_uint(__uint_as_float(v[4 * j]) + bz.x);
+                      v[4 * j + 1] = __float_as_uint(__uint_as_float(v[4 * j + 1]) + bz.y);
+                      v[4 * j + 2] = __float_as_uint(__uint_as_float(v[4 * j + 2]) + bz.z);
+                      v[4 * j + 3] = __float_as_uint(__uint_as_float(v[4 * j + 3]) + bz.w);
+                    }
+                  }
+                  uint8_t* ob = hb + (static_cast<size_t>(chunk * 2) * P_out + so) * 16;
+#pragma unroll
+                  for (int j = 0; j < 2; ++j) {
+                    uint4 h;
+                    if (flags & F_RELU) {
+                      h = make_uint4(pack_half2_relu_sat(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                     pack_half2_relu_sat(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                     pack_half2_relu_sat(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                     pack_half2_relu_sat(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                    } else {
+                      h = make_uint4(pack_half2_sat(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                                     pack_half2_sat(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                                     pack_half2_sat(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                                     pack_half2_sat(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                    }
+                    if (flags & F_MASK16) {
+                      h.x = mask_half2_gt0(h.x, mh[j].x); h.y = mask_half2_gt0(h.y, mh[j].y);
+                      h.z = mask_half2_gt0(h.z, mh[j].z); h.w = mask_half2_gt0(h.w, mh[j].w);
+                    }
+                    if (!(dbg & 2)) stg128(ob + static_cast<size_t>(j) * P_out * 16, h);
+                  }
+                }
+                if (kTrace && tid == 128 && acc_slot == 0 && chunk == 0) trace[idx * kTraceW + 17] = clock64();
+                continue;
+              }
+              float4 ax[4];
               if (valid && (flags & (F_MASK | F_ACCUM))) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
-                  ax[j] = *reinterpret_cast<const float4*>(auxp + (static_cast<size_t>(chunk * 8 + j) * Px + sx) * 4);
+                for (int j = 0; j < 4; ++j)
+                  ax[j] = ld4(auxp + (static_cast<size_t>(chunk * 4 + j) * Px + sx) * 4);
+              }
+              float4 fx[4];
+              if (valid && (flags & F_ATTBWD)) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  fx[j] = ld4(aux_ss + (static_cast<size_t>(chunk * 4 + j) * 256 + (y * 16 + x)) * 4);
               }
               tmem_ld_wait();
+              if (kTrace && tid == 128 && acc_slot == 0 && chunk == 0) trace[idx * kTraceW + 16] = clock64();
               if (valid && (flags & F_ATTBWD)) {
                 // g = this conv's output (gradient w.r.t. feat * map): dmap += <g, feat>, dfeat (+)= g * map
-                const float* feat = aux_s[s];
-                const float mval = map_s[s][y * 16 + x];
+                const float mval = map_ss[y * 16 + x];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const size_t off = (static_cast<size_t>(chunk * 8 + j) * 256 + (y * 16 + x)) * 4;
-                  const float4 f = *reinterpret_cast<const float4*>(feat + off);
+                for (int j = 0; j < 4; ++j) {
+                  const size_t off = (static_cast<size_t>(chunk * 4 + j) * 256 + (y * 16 + x)) * 4;
+                  const float4 f = fx[j];
                   const float gx = __uint_as_float(v[4 * j]), gy = __uint_as_float(v[4 * j + 1]);
                   const float gz = __uint_as_float(v[4 * j + 2]), gw = __uint_as_float(v[4 * j + 3]);
                   dot = fmaf(gx, f.x, dot); dot = fmaf(gy, f.y, dot); dot = fmaf(gz, f.z, dot); dot = fmaf(gw, f.w, dot);
                   float4 o = make_float4(gx * mval, gy * mval, gz * mval, gw * mval);
                   if (flags & F_ACCUM) { o.x += ax[j].x; o.y += ax[j].y; o.z += ax[j].z; o.w += ax[j].w; }
-                  *reinterpret_cast<float4*>(outp + off) = o;
+                  st4(outp + off, o);
                 }
               } else if (valid) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const int n0 = (chunk * 8 + j) * 4;
+                for (int j = 0; j < 4; ++j) {
+                  const int n0 = (chunk * 4 + j) * 4;
                   const float4 bz = *reinterpret_cast<const float4*>(&hdr->bias[n0]);
                   float4 o = make_float4(__uint_as_float(v[4 * j]) + bz.x, __uint_as_float(v[4 * j + 1]) + bz.y,
                                          __uint_as_float(v[4 * j + 2]) + bz.z, __uint_as_float(v[4 * j + 3]) + bz.w);
@@ -371,64 +471,77 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
                     const float4 wz = *reinterpret_cast<const float4*>(&hdr->w3[n0]);
                     dot = fmaf(o.x, wz.x, dot); dot = fmaf(o.y, wz.y, dot); dot = fmaf(o.z, wz.z, dot); dot = fmaf(o.w, wz.w, dot);
                   }
-                  v[4 * j] = __float_as_uint(to_tf32(o.x)); v[4 * j + 1] = __float_as_uint(to_tf32(o.y));
-                  v[4 * j + 2] = __float_as_uint(to_tf32(o.z)); v[4 * j + 3] = __float_as_uint(to_tf32(o.w));
+                  v[4 * j] = round_tf32(o.x); v[4 * j + 1] = round_tf32(o.y);
+                  v[4 * j + 2] = round_tf32(o.z); v[4 * j + 3] = round_tf32(o.w);
                 }
-                if (flags & F_STORE) {
+                if ((flags & F_STORE) && !(dbg & 1)) {
 #pragma unroll
-                  for (int j = 0; j < 8; ++j)
-                    *reinterpret_cast<uint4*>(outp + (static_cast<size_t>(chunk * 8 + j) * P_out + so) * 4) =
-                        make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                  for (int j = 0; j < 4; ++j)
+                    stg128(outp + (static_cast<size_t>(chunk * 4 + j) * P_out + so) * 4,
+                           make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
                 }
-                if (flags & F_HALF) {
+                if ((flags & F_HALF) && !(dbg & 2)) {
 #pragma unroll
-                  for (int j = 0; j < 4; ++j) {
+                  for (int j = 0; j < 2; ++j) {
                     const uint4 h = make_uint4(
-                        elt_pack_half2(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
-                        elt_pack_half2(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
-                        elt_pack_half2(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
-                        elt_pack_half2(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
-                    *reinterpret_cast<uint4*>(hb + (static_cast<size_t>(chunk * 4 + j) * P_out + so) * 16) = h;
+                        pack_half2_sat(__uint_as_float(v[8 * j]), __uint_as_float(v[8 * j + 1])),
+                        pack_half2_sat(__uint_as_float(v[8 * j + 2]), __uint_as_float(v[8 * j + 3])),
+                        pack_half2_sat(__uint_as_float(v[8 * j + 4]), __uint_as_float(v[8 * j + 5])),
+                        pack_half2_sat(__uint_as_float(v[8 * j + 6]), __uint_as_float(v[8 * j + 7])));
+                    stg128(hb + (static_cast<size_t>(chunk * 2 + j) * P_out + so) * 16, h);
+                  }
+                }
+              }
+              if (kTrace && tid == 128 && acc_slot == 0 && chunk == 0) trace[idx * kTraceW + 17] = clock64();
+            }
+            if (kTrace && tid == 128 && acc_slot == 0) trace[idx * kTraceW + 18] = clock64();
+            if (flags & (F_ATTBWD | F_DOTSIG)) {
+              // the two column halves of a pixel row live in two warps: combine their 64-channel partial dot products
+              hdr->dotp[acc_slot][half][prow] = dot;
+              __syncthreads();
+              dot = hdr->dotp[acc_slot][0][prow] + hdr->dotp[acc_slot][1][prow];
+            }
+            if ((flags & F_ATTBWD) && valid && half == 0) {
+              float* dmap = reinterpret_cast<float*>(in1_ss);
+              dmap[y * 16 + x] += dot;   // one writer per pixel: a sample's backward chain is serial
+            }
+            // the whole 128-channel dot product of the pixel: 1x1 head + sigmoid (nmn_modules.py:86,167)
+            if ((flags & F_DOTSIG) && valid) {
+              const float m = 1.f / (1.f + expf(-(dot + b3)));
+              if (half == 0) map_ss[y * 16 + x] = m;
+              if ((flags & F_ATTEND) && !(dbg & 4)) {
+                // the next module's first conv reads feat * map: write its fp16 operand planes right here
+                // (this thread: 8 of the 16 half planes; all 16 feature loads are issued before the first use)
+                const float* __restrict__ feat = aux_ss;
+                uint8_t* __restrict__ x0h = reinterpret_cast<uint8_t*>(in1_ss);
+                const int s16 = y * 16 + x;
+#pragma unroll 1
+                for (int b4 = 0; b4 < 2; ++b4) {
+                  float4 f[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    f[i] = ld4(feat + (static_cast<size_t>(16 * half + 8 * b4 + i) * 256 + s16) * 4);
+#pragma unroll
+                  for (int i = 0; i < 4; ++i) {
+                    const float4 f0 = f[2 * i], f1 = f[2 * i + 1];
+                    const uint4 h = make_uint4(pack_half2_sat(f0.x * m, f0.y * m), pack_half2_sat(f0.z * m, f0.w * m),
+                                               pack_half2_sat(f1.x * m, f1.y * m), pack_half2_sat(f1.z * m, f1.w * m));
+                    stg128(x0h + (static_cast<size_t>(8 * half + 4 * b4 + i) * 256 + s16) * 16, h);
                   }
                 }
               }
             }
-            // the thread holds the whole 128-channel dot product of its pixel: 1x1 head + sigmoid (nmn_modules.py:86,167)
-            if ((flags & F_ATTBWD) && valid) {
-              float* dmap = reinterpret_cast<float*>(const_cast<void*>(tp->in[1][s]));
-              dmap[y * 16 + x] += dot;   // one writer per pixel: a sample's backward chain is serial
-            }
-            if ((flags & F_DOTSIG) && valid) {
-              const float m = 1.f / (1.f + expf(-(dot + b3)));
-              map_s[s][y * 16 + x] = m;
-              if (flags & F_ATTEND) {
-                // the next module's first conv reads feat * map: write its fp16 operand planes right here
-                const float* feat = aux_s[s];
-                uint8_t* x0h = reinterpret_cast<uint8_t*>(const_cast<void*>(tp->in[1][s]));
-                const int s16 = y * 16 + x;
-#pragma unroll 4
-                for (int hp = 0; hp < 16; ++hp) {
-                  const float4 f0 = *reinterpret_cast<const float4*>(feat + (static_cast<size_t>(2 * hp) * 256 + s16) * 4);
-                  const float4 f1 = *reinterpret_cast<const float4*>(feat + (static_cast<size_t>(2 * hp + 1) * 256 + s16) * 4);
-                  const uint4 h = make_uint4(elt_pack_half2(to_tf32(f0.x * m), to_tf32(f0.y * m)),
-                                             elt_pack_half2(to_tf32(f0.z * m), to_tf32(f0.w * m)),
-                                             elt_pack_half2(to_tf32(f1.x * m), to_tf32(f1.y * m)),
-                                             elt_pack_half2(to_tf32(f1.z * m), to_tf32(f1.w * m)));
-                  *reinterpret_cast<uint4*>(x0h + (static_cast<size_t>(hp) * 256 + s16) * 16) = h;
-                }
-              }
-            }
+            if (kTrace && tid == 128 && acc_slot == 0) trace[idx * kTraceW + 19] = clock64();
           }
         }
-        if (trace && tid == 128) trace[idx * 16 + 12] = gtime();
-        __threadfence();
+        if (kTrace && tid == 128) trace[idx * kTraceW + 12] = gtime();
         tc_fence_before();
-        if (trace && tid == 128) trace[idx * 16 + 13] = gtime();
+        if (kTrace && tid == 128) trace[idx * kTraceW + 13] = gtime();
       }
-      if (trace && tid == 0) {
-        trace[idx * 16 + 5] = TASK_CONV | (n_samp << 8) | (n_mt << 16);
-        trace[idx * 16 + 6] = n_kb * ntaps;  // one K=16 MMA per (k-block, tap, sample, M tile)
-        trace[idx * 16 + 7] = flags;
+      if (kTrace && tid == 0) {
+        trace[idx * kTraceW + 5] = TASK_CONV | (n_samp << 8) | (n_mt << 16);
+        trace[idx * kTraceW + 6] = n_kb * ntaps;  // one K=16 MMA per (k-block, tap, sample, M tile)
+        trace[idx * kTraceW + 7] = flags;
       }
       ++n_conv;
       // producers / issuer keep their ring counters in sync with the work every conv task does
@@ -437,15 +550,17 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
     } else {
       // CUDA-core task: all 256 threads of the CTA (the tensor-core roles have nothing to do meanwhile)
       const EltTask& t = *reinterpret_cast<const EltTask*>(hdr->task);
+#ifndef PNMN_NO_ELT  // (timing experiment: how much of the conv path's time is instruction-cache pressure from this code?)
       elt_task_body(t, tid, hdr->elt);
-      __threadfence();
-      if (trace && tid == 128) { trace[idx * 16 + 5] = TASK_ELT; trace[idx * 16 + 6] = 0; trace[idx * 16 + 7] = t.op; }
+#endif
+      if (kTrace && tid == 128) { trace[idx * kTraceW + 5] = TASK_ELT; trace[idx * kTraceW + 6] = 0; trace[idx * kTraceW + 7] = t.op; }
     }
-    if (trace && tid == 0) trace[idx * 16 + 2] = gtime();
-    __syncthreads();  // (C) every store of this task is fenced
+    if (kTrace && tid == 0) trace[idx * kTraceW + 2] = gtime();
+    __syncthreads();  // (C) every store of this task has been issued; the release below is cumulative over them (bar.sync
+                      // orders the CTA's writes before thread 0's st.release.gpu -- the cutlass::Semaphore::release pattern)
     if (tid == 0) {
       st_release(done + idx, 1);
-      if (trace) trace[idx * 16 + 3] = gtime();
+      if (trace) trace[idx * kTraceW + 3] = gtime();
     }
   }
 
@@ -459,7 +574,9 @@ cudaError_t launch_exec(const uint8_t* d_tasks, const TaskMeta* d_meta, int n_ta
   if (n_tasks <= 0) return cudaSuccess;
   static bool attr_done = false;
   if (!attr_done) {
-    cudaError_t e = cudaFuncSetAttribute(exec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExSmem);
+    cudaError_t e = cudaFuncSetAttribute(exec_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExSmem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(exec_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExSmem);
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
@@ -467,7 +584,9 @@ cudaError_t launch_exec(const uint8_t* d_tasks, const TaskMeta* d_meta, int n_ta
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = n_tasks < kExCtasPerSM * sms ? n_tasks : kExCtasPerSM * sms;
-  exec_kernel<<<grid, kExThreads, kExSmem, stream>>>(d_tasks, d_meta, n_tasks, d_cfgs, d_counter, d_done, d_trace);
+  static const int dbg = std::getenv("PNMN_EXEC_DBG") ? std::atoi(std::getenv("PNMN_EXEC_DBG")) : 0;  // timing experiments only
+  if (d_trace) exec_kernel<true><<<grid, kExThreads, kExSmem, stream>>>(d_tasks, d_meta, n_tasks, d_cfgs, d_counter, d_done, d_trace, dbg);
+  else exec_kernel<false><<<grid, kExThreads, kExSmem, stream>>>(d_tasks, d_meta, n_tasks, d_cfgs, d_counter, d_done, d_trace, dbg);
   return cudaGetLastError();
 }
 

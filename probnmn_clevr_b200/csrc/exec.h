@@ -8,6 +8,8 @@ namespace pnmn {
 
 constexpr int kMaxDeps = 10;  // two paired samples x up to four parts (split elementwise op / M tiles) of the previous stage
 
+constexpr int kTraceW = 32;  // int64 entries per task in the optional trace buffer (exec.cu)
+
 enum TaskType : int { TASK_CONV = 0, TASK_ELT = 1 };
 
 struct TaskMeta {

@@ -53,6 +53,8 @@ enum ConvFlags : int {
                   // aux[s] = feat (P16 fp32 planes), in[1][s] = shadow of x0          (nmn_modules.py:83,120,161)
   F_ATTBWD = 256, // backward of that product on the data gradient g this conv computes:  dmap[p] += sum_c g[c][p]*feat[c][p],
                   // out[s] (= dfeat) (+)= g*map;  aux[s] = feat, map_out[s] = map (read), in[1][s] = dmap (P16 fp32 map)
+  F_MASK16 = 512, // like F_MASK, but aux[s] points to the fp16 half planes of the forward activation (persistent executor:
+                  // activations that only feed other convs are stored as fp16 planes alone, no F_STORE)
 };
 
 // byte offset of the fp16 shadow behind a 128-channel fp32 plane buffer of P slots per plane

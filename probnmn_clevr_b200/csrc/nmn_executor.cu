@@ -605,6 +605,16 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   // fp16 ReLU masks in the backward, cuts the executor's DRAM traffic by a third but not its time: the epilogue is
   // latency-bound, not store-bound, and the extra mask path cost registers.)
   const int HF = F_HALF;    // every conv / attend output is the fp16 operand of the next conv (and of wgrad)
+  // Persistent executor: activations / gradients that only feed other convs (next conv, wgrad, a ReLU mask) are stored as
+  // fp16 planes alone -- the epilogue is instruction-bound (profiles/r1_summary.md), and the fp16-only path needs a
+  // fifth of the instructions and a third of the bytes of the fp32 + tf32-rounding + fp16 one.
+  static const bool no_lean = std::getenv("PNMN_NOLEAN") != nullptr;
+  const bool lean = p.persistent && !no_lean;
+  const int ST_INT = lean ? 0 : F_STORE;                       // store flag of such an internal tensor
+  const int MASK_INT = lean ? F_MASK16 : F_MASK;               // ReLU mask read from such an internal forward activation
+  auto mask_src = [&](const float* act, PlaneFmt f) -> const float* {
+    return lean ? static_cast<const float*>(Builder::shadow(act, f)) : act;
+  };
   const int EHF = EF_HALF;
   p.nmaps = 1;  // map 0 = the constant all-ones attention of `scene` (nmn.py:216)
   const int ones_val = bd.new_val(VK_ONES, 1, 0, false);
@@ -677,7 +687,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
     {
       const ConvW& c1 = m->convs[m->stem1];
       ConvTask t{};
-      t.cfg = bd.make_cfg(m->in_ch / 16, m->in_ch / 16, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE | HF);
+      t.cfg = bd.make_cfg(m->in_ch / 16, m->in_ch / 16, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | ST_INT | HF);
       t.in[0][0] = reinterpret_cast<const void*>(reinterpret_cast<uint64_t>(bd.ainp(xin)) + static_cast<uint64_t>(m->in_ch / 4) * 256 * 16);
       t.out[0] = bd.p16(y1s_unit[n]);
       t.w = bd.packed(c1.pk_fwd); t.bias = bd.param(c1.b_off);
@@ -724,7 +734,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           r.y_unit[0] = bd.alloc16(); r.y_unit[1] = bd.alloc16(); r.y_unit[2] = bd.alloc16();
           vo.unit = r.y_unit[2];
           ConvTask t{};
-          t.cfg = bd.make_cfg(16, 8, 1, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE | HF);
+          t.cfg = bd.make_cfg(16, 8, 1, 1, kP16, kP16, kP16, F_BIAS | F_RELU | ST_INT | HF);
           t.in[0][0] = Builder::shadow(bd.p16(bd.vals[r.in0].unit), kP16);
           t.in[1][0] = Builder::shadow(bd.p16(bd.vals[r.in1].unit), kP16);
           t.out[0] = bd.p16(r.y_unit[0]); t.w = bd.packed(pj.pk_fwd); t.bias = bd.param(pj.b_off);
@@ -733,7 +743,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           for (int i = 1; i < 3; ++i) {
             const ConvW& cw = m->convs[md.convs[i]];
             ConvTask u{};
-            u.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE | HF);
+            u.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | (i == 2 ? F_STORE : ST_INT) | HF);
             u.in[0][0] = Builder::shadow(bd.p16(r.y_unit[i - 1]), kP16); u.out[0] = bd.p16(r.y_unit[i]);
             u.w = bd.packed(cw.pk_fwd); u.bias = bd.param(cw.b_off);
             fs.add_conv(n, u, 0);
@@ -771,7 +781,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             const bool last = i + 1 == r.nconv;
             r.y_unit[i] = bd.alloc_fmt(fout);
             ConvTask t{};
-            t.cfg = bd.make_cfg(8, 8, 9, d, fin, fout, fout, F_BIAS | F_RELU | F_STORE | HF | ((last && head) ? F_DOTSIG : 0));
+            t.cfg = bd.make_cfg(8, 8, 9, d, fin, fout, fout, F_BIAS | F_RELU | (last ? F_STORE : ST_INT) | HF | ((last && head) ? F_DOTSIG : 0));
             t.in[0][0] = Builder::shadow(x, fin); t.out[0] = bd.pfmt(fout, r.y_unit[i]);
             t.w = bd.packed(cw.pk_fwd); t.bias = bd.param(cw.b_off);
             if (last && head) {
@@ -880,9 +890,9 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             add_inst(md.convs[i], dz, bd.p16(r.y_unit[i - 1]), kP16, 1);
             const int du = bd.alloc16();
             ConvTask t{};
-            t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_STORE | F_MASK | F_HALF);
+            t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, ST_INT | MASK_INT | F_HALF);
             t.in[0][0] = Builder::shadow(dz, kP16); t.out[0] = bd.p16(du);
-            t.aux[0] = bd.p16(r.y_unit[i - 1]);
+            t.aux[0] = mask_src(bd.p16(r.y_unit[i - 1]), kP16);
             t.w = bd.packed(cw.pk_bwd);
             bs.add_conv(n, t, 0);
             dz = bd.p16(du);
@@ -931,9 +941,9 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             if (i > 0) {
               const PlaneFmt fprev = fmt_for_dilation(dil_of(i - 1));
               const int du = bd.alloc_fmt(fprev);
-              t.cfg = bd.make_cfg(8, 8, 9, d, f, fprev, f, F_STORE | F_MASK | F_HALF);
+              t.cfg = bd.make_cfg(8, 8, 9, d, f, fprev, f, ST_INT | MASK_INT | F_HALF);
               t.out[0] = bd.pfmt(fprev, du);
-              t.aux[0] = xin_i;
+              t.aux[0] = mask_src(xin_i, f);
               bs.add_conv(n, t, f.P == kP22.P ? 1 : 0);
               dz = t.out[0];
             } else if (r.x0_is_feat) {
@@ -975,9 +985,9 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
       const int dz1 = bd.alloc16();
       const ConvW& c2 = m->convs[m->stem2];
       ConvTask t{};
-      t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_STORE | F_MASK | F_HALF);
+      t.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, ST_INT | MASK_INT | F_HALF);
       t.in[0][0] = Builder::shadow(dfeatp, kP16); t.out[0] = bd.p16(dz1);
-      t.aux[0] = bd.p16(y1s_unit[n]);
+      t.aux[0] = mask_src(bd.p16(y1s_unit[n]), kP16);
       t.w = bd.packed(c2.pk_bwd);
       bs.add_conv(n, t, 0);
       add_inst(m->stem2, dfeatp, bd.p16(y1s_unit[n]), kP16, 1);
@@ -1384,7 +1394,7 @@ extern "C" int pnmn_nmn_backward(pnmn_plan* pp, const pnmn_buffers* bufs, const 
                           static_cast<int>(p.btask.size()), reinterpret_cast<const ConvCfg*>(blob + p.off_cfg),
                           reinterpret_cast<int*>(blob + p.off_bsync), reinterpret_cast<int*>(blob + p.off_bsync) + 1,
                           (g_trace && static_cast<int64_t>(p.ftask.size() + p.btask.size()) <= g_trace_cap)
-                              ? g_trace + 16 * p.ftask.size() : nullptr, st));
+                              ? g_trace + kTraceW * p.ftask.size() : nullptr, st));
     }
   }
   return run_launches(p, p.blaunch, static_cast<const uint8_t*>(bufs->blob), true, st);
