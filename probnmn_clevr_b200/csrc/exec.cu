@@ -33,19 +33,23 @@ namespace pnmn {
 constexpr int kExThreads = 256;
 constexpr int kExCtasPerSM = 2;
 constexpr int kExMaxAcc = 2;               // accumulators (128 TMEM columns each) per task
-constexpr int kExWStages = 4;
 constexpr int kExWTile = 16 * 128 * 2;     // 4 KB: 16 k x 128 n fp16
-constexpr int kExWStage = 3 * kExWTile;    // one tap ROW (3 taps) per ring stage: one barrier round trip per row
-constexpr int kExAStages = 2;
-constexpr int kExAStage = 24 * 1024;       // max over plane formats of NS*(lead + 2*P)*16 (fp16 half planes)
-constexpr int kExHeader = 8 * 1024;
-constexpr int kExGuard = 3 * 1024;
-constexpr int kExSmem = kExHeader + kExWStages * kExWStage + kExAStages * kExAStage + kExGuard;
+// Weight ring: a stage holds SIX taps (24 KB) of the linear (k-block, tap) weight stream of a 3x3 conv -- two k-blocks are
+// three stages -- or one tap of a 1x1 conv.  The issuing thread pays ~175 cycles per barrier wait + commit and ~48 per
+// MMA (scripts/microbench/mma_stage.cu), so with 3-tap stages a one-accumulator task spent 320 cycles of issue work per
+// 192 cycles of tensor work; six taps bring the two level.  The ring is THREE stages deep when the activation ring leaves
+// room (one sample, P16 / P18 planes), else two.
+constexpr int kExWTapsPerStage = 6;
+constexpr int kExWStage = kExWTapsPerStage * kExWTile;
+constexpr int kExWStagesMax = 3;
+constexpr int kExAStagesMax = 4;          // activation ring: 2-4 stages of one k-block, see the ring split in exec_kernel
+constexpr int kExHeader = 5 * 1024;
+constexpr int kExSmem = 107 * 1024;        // header | weight ring | activation ring | guard for the positive tap shifts
 static_assert(kExCtasPerSM * (kExSmem + 1024) <= 228 * 1024, "executor smem: two CTAs per SM");
 
 struct ExHeader {
-  uint64_t full_a[kExAStages], empty_a[kExAStages];
-  uint64_t full_w[kExWStages], empty_w[kExWStages];
+  uint64_t full_a[kExAStagesMax], empty_a[kExAStagesMax];
+  uint64_t full_w[kExWStagesMax], empty_w[kExWStagesMax];
   uint64_t tmem_full;
   uint32_t tmem_base;
   int task_idx;
@@ -126,15 +130,14 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
   extern __shared__ __align__(1024) uint8_t smem[];
   ExHeader* hdr = reinterpret_cast<ExHeader*>(smem);
   uint8_t* w_ring = smem + kExHeader;
-  uint8_t* a_ring = w_ring + kExWStages * kExWStage;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
   if (tid == 0) {
-    for (int i = 0; i < kExAStages; ++i) {
+    for (int i = 0; i < kExAStagesMax; ++i) {
       mbar_init(smem_u32(&hdr->full_a[i]), 1);
       mbar_init(smem_u32(&hdr->empty_a[i]), 1);
     }
-    for (int i = 0; i < kExWStages; ++i) {
+    for (int i = 0; i < kExWStagesMax; ++i) {
       mbar_init(smem_u32(&hdr->full_w[i]), 1);
       mbar_init(smem_u32(&hdr->empty_w[i]), 1);
     }
@@ -147,8 +150,11 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
 
-  // ring positions persist across tasks (each role thread keeps its own copy)
-  uint32_t na = 0, nw = 0, n_conv = 0;
+  // Barrier phases persist across tasks.  Every task starts at ring stage 0 (all stages are free once the previous
+  // task's accumulators completed), with a task-dependent number of stages, so each role thread tracks the phase parity
+  // of every barrier it waits on as one bit per stage: "full" bits (the MMA issuer) start at 0, "empty" bits (the
+  // producers) at 1 (= passes on a fresh barrier); a bit flips each time its stage is used.
+  uint32_t pf_a = 0, pf_w = 0, pe_a = 0xfu, pe_w = 0x7u, n_conv = 0;
 
   for (;;) {
     // ---------------- scheduler: fetch the next task, wait for its producers ----------------
@@ -196,13 +202,24 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
 #undef UNI
       const uint32_t plane_bytes = static_cast<uint32_t>(P_in) * 16u;
       const uint32_t samp_bytes = static_cast<uint32_t>(lead) * 16u + 2u * plane_bytes;  // 2 half planes = 16 ch
-      const int tps = ntaps == 9 ? 3 : 1;     // taps per weight stage
-      const int rows_w = ntaps / tps;         // weight stages per k-block
-      const int n_ws = n_kb * rows_w;         // weight stages of this task
+      const int tps = ntaps == 9 ? kExWTapsPerStage : 1;  // taps per weight stage
+      const int n_ws = n_kb * ntaps / tps;                 // weight stages of this task (n_kb is even)
+      const uint32_t a_stage = (static_cast<uint32_t>(n_samp) * samp_bytes + 127u) & ~127u;
+      // ring split of this task: both streams are latency-bound (a stage can only be refilled once its MMAs completed), so
+      // the shared memory left after the header and the guard for the largest positive tap shift goes to as many stages
+      // as fit -- (weight, activation) stages = (3,3) for one P16 sample, (2,4) for one P18 sample, (2,3) for two P16
+      // samples, else (2,2)
+      const uint32_t guard = ntaps == 9 ? ((static_cast<uint32_t>((S_in + 1) * dil) * 16u + 255u) & ~127u) : 128u;
+      const uint32_t ring_avail = static_cast<uint32_t>(kExSmem - kExHeader) - guard;
+      int n_wst = 2, n_ast = 2;
+      if (3u * a_stage + 3u * kExWStage <= ring_avail) { n_wst = 3; n_ast = 3; }
+      else if (4u * a_stage + 2u * kExWStage <= ring_avail) n_ast = 4;
+      else if (3u * a_stage + 2u * kExWStage <= ring_avail) n_ast = 3;
+      uint8_t* a_ring = w_ring + n_wst * kExWStage;
       // zero the lead gaps of this plane format; stage bias / 1x1 head weights
-      for (int st = 0; st < kExAStages; ++st)
+      for (int st = 0; st < n_ast; ++st)
         for (int s = 0; s < n_samp; ++s) {
-          float4* g = reinterpret_cast<float4*>(a_ring + st * kExAStage + s * samp_bytes);
+          float4* g = reinterpret_cast<float4*>(a_ring + st * a_stage + s * samp_bytes);
           for (int i = tid; i < lead; i += kExThreads) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
       if (tid < 128) {
@@ -222,30 +239,40 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
           const uint32_t a_base = smem_u32(a_ring) + lead * 16u;
           const uint32_t kb_bytes = 2u * plane_bytes;
           fence_proxy_async_all();
-          for (int kb = 0; kb < n_kb; ++kb, ++na) {
-            const int sa = na % kExAStages;
-            mbar_wait(smem_u32(&hdr->empty_a[sa]), ((na / kExAStages) & 1) ^ 1);
+          int sa = 0;
+          for (int kb = 0; kb < n_kb; ++kb) {
+            mbar_wait(smem_u32(&hdr->empty_a[sa]), (pe_a >> sa) & 1u);
+            pe_a ^= 1u << sa;
             const uint32_t bar = smem_u32(&hdr->full_a[sa]);
             mbar_arrive_expect_tx(bar, n_samp * kb_bytes);
             const bool second = kb >= kb_per_in;
             const size_t off = static_cast<size_t>(second ? kb - kb_per_in : kb) * kb_bytes;
-            bulk_g2s(a_base + sa * kExAStage, (second ? in10 : in00) + off, kb_bytes, bar);
-            if (n_samp > 1) bulk_g2s(a_base + sa * kExAStage + samp_bytes, (second ? in11 : in01) + off, kb_bytes, bar);
+            bulk_g2s(a_base + sa * a_stage, (second ? in10 : in00) + off, kb_bytes, bar);
+            if (n_samp > 1) bulk_g2s(a_base + sa * a_stage + samp_bytes, (second ? in11 : in01) + off, kb_bytes, bar);
+            sa = sa + 1 == n_ast ? 0 : sa + 1;
           }
         }
-      } else if (warp == 1) {
-        // ---------------- weight producer ----------------
+      } else if (warp == 1 || warp == 3) {
+        // ---------------- weight producers ----------------
+        // TWO issuing threads (warp 1 and the otherwise idle scheduler warp 3) take alternate stages: one thread can only
+        // start a bulk copy every ~500 cycles whatever its size (scripts/microbench/bulk_stream.cu).  Both walk the whole
+        // stage sequence so that their phase bits follow every use of every stage.
         if (lane == 0) {
           const uint8_t* wsrc = static_cast<const uint8_t*>(tp->w);
           const uint32_t bytes = static_cast<uint32_t>(tps) * kExWTile;
           const uint32_t w_base = smem_u32(w_ring);
+          const int mine = warp == 3 ? 1 : 0;
           fence_proxy_async_all();
-          for (int it = 0; it < n_ws; ++it, ++nw) {
-            const int sw = nw % kExWStages;
-            mbar_wait(smem_u32(&hdr->empty_w[sw]), ((nw / kExWStages) & 1) ^ 1);
-            const uint32_t bar = smem_u32(&hdr->full_w[sw]);
-            mbar_arrive_expect_tx(bar, bytes);
-            bulk_g2s(w_base + sw * kExWStage, wsrc + static_cast<size_t>(it) * bytes, bytes, bar);
+          int sw = 0;
+          for (int it = 0; it < n_ws; ++it) {
+            if ((it & 1) == mine) {
+              mbar_wait(smem_u32(&hdr->empty_w[sw]), (pe_w >> sw) & 1u);
+              const uint32_t bar = smem_u32(&hdr->full_w[sw]);
+              mbar_arrive_expect_tx(bar, bytes);
+              bulk_g2s(w_base + sw * kExWStage, wsrc + static_cast<size_t>(it) * bytes, bytes, bar);
+            }
+            pe_w ^= 1u << sw;
+            sw = sw + 1 == n_wst ? 0 : sw + 1;
           }
         }
       } else if (warp == 2) {
@@ -259,7 +286,7 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
           // K-major, no swizzle: LBO = distance between the two 8-channel halves of a 16-deep k-block
           const uint32_t a_lo0 = (smem_u32(a_ring) >> 4) + static_cast<uint32_t>(lead) + (static_cast<uint32_t>(P_in) << 16);
           const uint32_t b_lo0 = (smem_u32(w_ring) >> 4) + ((2048u >> 4) << 16);
-          const uint32_t samp16 = samp_bytes >> 4;
+          const uint32_t samp16 = samp_bytes >> 4, a_stage16 = a_stage >> 4;
           const int row_shift = ntaps == 9 ? S_in * dil : 0;  // slots between tap rows
           const int col_shift = ntaps == 9 ? dil : 0;
           const uint32_t tm = __shfl_sync(0xffffffffu, tmem_base, 0);
@@ -278,65 +305,92 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
                 else { aoff[1] = av; doff[1] = dv; }
                 ++n_acc;
               }
-          uint32_t ua = __shfl_sync(0xffffffffu, na, 0), uw = __shfl_sync(0xffffffffu, nw, 0);
+          uint32_t fa = __shfl_sync(0xffffffffu, pf_a, 0), fw = __shfl_sync(0xffffffffu, pf_w, 0);
           long long wait_a = 0, wait_w = 0;
           constexpr bool tr = kTrace;
           const uint32_t bar_fa = smem_u32(&hdr->full_a[0]), bar_ea = smem_u32(&hdr->empty_a[0]);
           const uint32_t bar_fw = smem_u32(&hdr->full_w[0]), bar_ew = smem_u32(&hdr->empty_w[0]);
           const uint32_t d_hi32 = static_cast<uint32_t>(d_hi >> 32);
-          const int ty0 = rows_w >> 1;
-          // The loop nest is instantiated per (taps per stage, accumulators): inside a stage every descriptor is
-          // one add away from a value computed BEFORE the barrier wait, so the single issuing lane spends a few
-          // instructions per MMA instead of re-deriving the addresses (the MMA pipe retires one 128x128x16 MMA
-          // per 64 cycles; the previous generic loop needed ~130 cycles of issue work per MMA).
-          auto run = [&](auto tps_c, auto nacc_c) {
-            constexpr int TPS = decltype(tps_c)::value;
+          int sw = 0, sa = 0;
+          auto wait_full_a = [&](int sa) {
+            const long long c0 = tr ? clock64() : 0;
+            mbar_wait(bar_fa + sa * 8, (fa >> sa) & 1u);
+            fa ^= 1u << sa;
+            if (tr) wait_a += clock64() - c0;
+          };
+          auto wait_full_w = [&]() {
+            const long long c0 = tr ? clock64() : 0;
+            mbar_wait(bar_fw + sw * 8, (fw >> sw) & 1u);
+            fw ^= 1u << sw;
+            if (tr) wait_w += clock64() - c0;
+          };
+          // 3x3 conv: two k-blocks (18 taps) = three weight stages A, B, C per trip, everything unrolled so that every
+          // descriptor is one add away from a loop-invariant value:
+          //   A: taps 0-5 of k-block 0 | B: taps 6-8 of k-block 0, taps 0-2 of k-block 1 | C: taps 3-8 of k-block 1
+          auto run9 = [&](auto nacc_c) {
             constexpr int NACC = decltype(nacc_c)::value;
-            for (int kb = 0; kb < n_kb; ++kb, ++ua) {
-              const int sa = ua % kExAStages;
-              long long c0 = tr ? clock64() : 0;
-              mbar_wait(bar_fa + sa * 8, (ua / kExAStages) & 1);
-              if (tr) wait_a += clock64() - c0;
-              const uint32_t a_lo_kb = a_lo0 + sa * (kExAStage >> 4);
-              for (int ty = 0; ty < rows_w; ++ty, ++uw) {
-                const int sw = uw % kExWStages;
-                const uint32_t b_lo_row = b_lo0 + sw * (kExWStage >> 4);
-                const uint32_t a_lo_row = a_lo_kb + static_cast<uint32_t>((ty - ty0) * row_shift - col_shift);
-                uint32_t al[TPS][NACC], bl[TPS];
+            int sh[9];
 #pragma unroll
-                for (int tx = 0; tx < TPS; ++tx) {
-                  bl[tx] = b_lo_row + tx * (kExWTile >> 4);
+            for (int t = 0; t < 9; ++t) sh[t] = (t / 3 - 1) * row_shift + (t % 3 - 1) * col_shift;
+            for (int kb = 0; kb < n_kb; kb += 2) {
+              const int sa0 = sa, sa1 = sa + 1 == n_ast ? 0 : sa + 1;  // activation stages of k-blocks kb, kb + 1
+              sa = sa1 + 1 == n_ast ? 0 : sa1 + 1;
+              const uint32_t a_lo_kb[2] = {a_lo0 + sa0 * a_stage16, a_lo0 + sa1 * a_stage16};
+              const uint32_t bar_ea_kb[2] = {bar_ea + sa0 * 8, bar_ea + sa1 * 8};
 #pragma unroll
-                  for (int k = 0; k < NACC; ++k) al[tx][k] = a_lo_row + static_cast<uint32_t>(tx * col_shift) + aoff[k];
-                }
-                const uint32_t acc0 = (kb | ty) == 0 ? 0u : 1u;
-                c0 = tr ? clock64() : 0;
-                mbar_wait(bar_fw + sw * 8, (uw / kExWStages) & 1);
-                if (tr) wait_w += clock64() - c0;
+              for (int st = 0; st < 3; ++st) {
+                if (st < 2) wait_full_a(st == 0 ? sa0 : sa1);
+                wait_full_w();
                 tc_fence_after();
-                if (tr && lane == 0 && kb == 0 && ty == 0) trace[idx * kTraceW + 9] = gtime();
+                if (tr && lane == 0 && kb == 0 && st == 0) trace[idx * kTraceW + 9] = gtime();
+                const uint32_t b_lo_st = b_lo0 + sw * (kExWStage >> 4);
                 if (elect_one()) {
 #pragma unroll
-                  for (int tx = 0; tx < TPS; ++tx)
+                  for (int j = 0; j < 6; ++j) {
+                    const int t18 = st * 6 + j, kbi = t18 / 9, tap = t18 % 9;
+                    const uint32_t a_lo = a_lo_kb[kbi] + static_cast<uint32_t>(sh[tap]);
 #pragma unroll
                     for (int k = 0; k < NACC; ++k)
-                      umma_f16_2x32(doff[k], al[tx][k], d_hi32, bl[tx], d_hi32, idesc, tx == 0 ? acc0 : 1u);
+                      umma_f16_2x32(doff[k], a_lo + aoff[k], d_hi32, b_lo_st + j * (kExWTile >> 4), d_hi32, idesc,
+                                    t18 == 0 ? (kb == 0 ? 0u : 1u) : 1u);
+                    if (tap == 8) umma_commit(bar_ea_kb[kbi]);
+                  }
                   umma_commit(bar_ew + sw * 8);
-                  if (ty == rows_w - 1) umma_commit(bar_ea + sa * 8);
                 }
                 __syncwarp();
+                sw = sw + 1 == n_wst ? 0 : sw + 1;
               }
             }
           };
+          // 1x1 conv: one tap per k-block and per weight stage
+          auto run1 = [&](auto nacc_c) {
+            constexpr int NACC = decltype(nacc_c)::value;
+            for (int kb = 0; kb < n_kb; ++kb) {
+              wait_full_a(sa);
+              wait_full_w();
+              tc_fence_after();
+              if (tr && lane == 0 && kb == 0) trace[idx * kTraceW + 9] = gtime();
+              const uint32_t a_lo = a_lo0 + sa * a_stage16, b_lo = b_lo0 + sw * (kExWStage >> 4);
+              if (elect_one()) {
+#pragma unroll
+                for (int k = 0; k < NACC; ++k) umma_f16_2x32(doff[k], a_lo + aoff[k], d_hi32, b_lo, d_hi32, idesc, kb == 0 ? 0u : 1u);
+                umma_commit(bar_ew + sw * 8);
+                umma_commit(bar_ea + sa * 8);
+              }
+              __syncwarp();
+              sw = sw + 1 == n_wst ? 0 : sw + 1;
+              sa = sa + 1 == n_ast ? 0 : sa + 1;
+            }
+          };
           using I1 = std::integral_constant<int, 1>; using I2 = std::integral_constant<int, 2>;
-          using I3 = std::integral_constant<int, 3>;
-          if (tps == 3) {
-            if (n_acc == 1) run(I3{}, I1{}); else run(I3{}, I2{});
+          if (ntaps == 9) {
+            if (n_acc == 1) run9(I1{}); else run9(I2{});
           } else {
-            if (n_acc == 1) run(I1{}, I1{}); else run(I1{}, I2{});
+            if (n_acc == 1) run1(I1{}); else run1(I2{});
           }
           if (elect_one()) umma_commit(smem_u32(&hdr->tmem_full));
           __syncwarp();
+          pf_a = fa; pf_w = fw;
           if (kTrace && lane == 0) { trace[idx * kTraceW + 10] = gtime(); trace[idx * kTraceW + 14] = wait_a; trace[idx * kTraceW + 15] = wait_w; }
         }
       }
@@ -544,9 +598,6 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
         trace[idx * kTraceW + 7] = flags;
       }
       ++n_conv;
-      // producers / issuer keep their ring counters in sync with the work every conv task does
-      if (!(warp == 0 && lane == 0)) na += n_kb;
-      if (!(warp == 1 && lane == 0)) nw += n_ws;
     } else {
       // CUDA-core task: all 256 threads of the CTA (the tensor-core roles have nothing to do meanwhile)
       const EltTask& t = *reinterpret_cast<const EltTask*>(hdr->task);

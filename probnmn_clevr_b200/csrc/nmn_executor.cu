@@ -269,9 +269,11 @@ struct Sched {
     const int U = static_cast<int>(v.size());
     const int nmt = kind == LK_CONV0 ? 2 : 3;
     static const bool pair_always = std::getenv("PNMN_PAIR_ALWAYS") != nullptr;  // diagnostics
-    const int cap = (kind == LK_CONV0 && (U > kNumSMs || pair_always)) ? NSMAX : 1;
+    static const int pair_min = std::getenv("PNMN_PAIR_MIN") ? std::atoi(std::getenv("PNMN_PAIR_MIN")) : kNumSMs;
+    static const int split_max = std::getenv("PNMN_SPLIT_MAX") ? std::atoi(std::getenv("PNMN_SPLIT_MAX")) : kNumSMs + kNumSMs / 2;
+    const int cap = (kind == LK_CONV0 && (U > pair_min || pair_always)) ? NSMAX : 1;
     static const bool no_split = std::getenv("PNMN_NOSPLIT") != nullptr;  // diagnostics
-    const int split = (!no_split && U * nmt <= kNumSMs + kNumSMs / 2) ? nmt : 1;
+    const int split = (!no_split && U * nmt <= split_max) ? nmt : 1;
     size_t i = 0;
     while (i < v.size()) {
       ConvTask t = protos[v[i]].t;

@@ -2,9 +2,9 @@
 # one development iteration on the GPU: NMN parity tests, executor trace, short bench
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_nmn_gpu.py tests/test_kernels_gpu.py -x -q 2>&1 | tail -5
-timeout 600 python scripts/trace_exec.py 2>&1 | grep -E "conv n_samp|==|sum|epilogue" | grep -E "==|sum|mmas/tile=  72|mmas/tile= 576|epilogue" | cut -c1-330 | tee gpurun_out/trace.txt
-timeout 600 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err || tail -5 gpurun_out/bench_quick.err
+timeout 300 python -m pytest tests/test_nmn_gpu.py tests/test_kernels_gpu.py -x -q 2>&1 | tail -5
+timeout 200 python scripts/trace_exec.py 2>&1 | grep -E "conv n_samp|==|sum|epilogue" | grep -E "==|sum|mmas/tile=  72|mmas/tile= 576|epilogue" | cut -c1-330 | tee gpurun_out/trace.txt
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err || tail -5 gpurun_out/bench_quick.err
 python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench_quick.json'))

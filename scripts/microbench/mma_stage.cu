@@ -12,13 +12,14 @@ __global__ void __launch_bounds__(128, 1) bench(long long* out, int n_stage, con
   __shared__ uint64_t bars[8], done_bar, cbar[4];
   __shared__ uint32_t tmem_ptr;
   __shared__ volatile int stop;
+  __shared__ int flag;
   const int warp = threadIdx.x >> 5;
   for (int i = threadIdx.x; i < 200 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 8; ++i) mbar_init(smem_u32(&bars[i]), 1);
     for (int i = 0; i < 4; ++i) mbar_init(smem_u32(&cbar[i]), 1);
     mbar_init(smem_u32(&done_bar), 1);
-    stop = 0;
+    stop = 0; flag = 1;
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc<512>(smem_u32(&tmem_ptr));
@@ -34,7 +35,8 @@ __global__ void __launch_bounds__(128, 1) bench(long long* out, int n_stage, con
     mbar_arrive(smem_u32(&done_bar));
     const long long t0 = clock64();
     for (int st = 0; st < n_stage; ++st) {
-      if (V >= 3) mbar_wait(smem_u32(&done_bar), 0);
+      if (V == 3 || V == 4) mbar_wait(smem_u32(&done_bar), 0);
+      if (V >= 5) { while (*reinterpret_cast<volatile int*>(&flag) < 1) {} }
       if (V >= 2) tc_fence_after();
 #pragma unroll
       for (int i = 0; i < G; ++i)
@@ -47,6 +49,9 @@ __global__ void __launch_bounds__(128, 1) bench(long long* out, int n_stage, con
     const long long t2 = clock64();
     stop = 1;
     if (blockIdx.x == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+  } else if (V == 6 && threadIdx.x == 96) {
+    // a watcher thread hammering mbarrier waits on a completed phase while the issuer polls a plain shared flag
+    while (!stop) mbar_wait(smem_u32(&done_bar), 0);
   } else if (V == 4 && threadIdx.x == 64) {
     // stream 12 KB bulk copies into the upper smem region as fast as one barrier round trip allows
     uint32_t ph = 0;
@@ -83,5 +88,8 @@ int main() {
   run<2, 3>("V2 + fence::after_thread_sync", d, g); run<2, 12>("V2 + fence::after_thread_sync", d, g);
   run<3, 3>("V3 + mbarrier wait (completed phase)", d, g); run<3, 12>("V3 + mbarrier wait (completed phase)", d, g);
   run<4, 3>("V4 = V1 + concurrent cp.async.bulk stream", d, g); run<4, 12>("V4 = V1 + concurrent cp.async.bulk stream", d, g);
+  run<5, 3>("V5 = V2 + poll a volatile shared flag", d, g); run<5, 1>("V5 = V2 + poll a volatile shared flag", d, g);
+  run<6, 3>("V6 = V5 + a watcher warp doing mbarrier waits", d, g); run<6, 1>("V6 = V5 + a watcher warp doing mbarrier waits", d, g);
+  run<3, 1>("V3 + mbarrier wait (completed phase)", d, g); run<3, 6>("V3 + mbarrier wait (completed phase)", d, g);
   return 0;
 }
