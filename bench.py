@@ -219,10 +219,12 @@ def run_ours(args):
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
+        t_host = time.perf_counter()
         for i in range(steps):
             fn(i)
         if finish is not None:
             finish()
+        timed.host_issue_ms = (time.perf_counter() - t_host) * 1e3  # host time to ISSUE the steps (no device sync inside)
         b.record()
         if world > 1:
             dist.barrier()
@@ -282,11 +284,13 @@ def run_ours(args):
     sampler.start()
     L.lib().pnmn_launch_count(1)
     ms = timed(resident_step, args.steps)
+    host_issue_ms = timed.host_issue_ms
     own_launches = int(L.lib().pnmn_launch_count(1))
     sampler.stop_flag = True
     L.lib().pnmn_debug_host_times(host_ms)
     host_ms_per_step = {"plan_create": host_ms[0] / args.steps, "forward_call": host_ms[1] / args.steps,
-                        "backward_call": host_ms[2] / args.steps}
+                        "backward_call": host_ms[2] / args.steps,
+                        "issue_total": host_issue_ms / args.steps}  # wall time the host needs to issue one step
     stats = model.last_plan_stats
     e2e_total["n"] = 2
     for i in range(2):

@@ -114,6 +114,13 @@ int pnmn_nmn_backward(pnmn_plan* p, const pnmn_buffers* bufs, const float* grad_
  * or stacked (stack_rows = 1: [3*rows][cols]); chunk order (hi, lo, hi) if second_low else (hi, hi, lo). */
 int pnmn_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int stack_rows, int second_low, void* stream);
 
+/* Classifier helper: ReLU -> MaxPool2d(2,2) -> flatten (probnmn/models/nmn.py:77-79, nmn_modules.py:250-251) on the
+ * channels-last output y [B][14*14][C] of the 1x1 convolution (device, fp32, bias included): pooled [B][C*7*7] in the
+ * reference's (C, 7, 7) flatten order, code [B][C*7*7] bytes (argmax position | 4 if active) for the backward pass, which
+ * writes gy [B][14*14][C] from g [B][C*7*7].  C must be a multiple of 64. */
+int pnmn_relu_pool_fwd(const float* y, float* pooled, void* code, int64_t B, int64_t C, void* stream);
+int pnmn_relu_pool_bwd(const float* g, const void* code, float* gy, int64_t B, int64_t C, void* stream);
+
 /* kernels launched by the library so far (reset != 0 clears the counter); bench.py reports it as "gpu_launches" */
 long long pnmn_launch_count(int reset);
 

@@ -119,4 +119,59 @@ cudaError_t launch_split3_bf16(const float* src, void* dst, int64_t rows, int64_
   return cudaGetLastError();
 }
 
+// ---- classifier: ReLU + 2x2 max-pool + (C,7,7) flatten of the channels-last 1x1-conv output (nmn.py:77-79, nmn_modules.py:250)
+// y: [B][196][C] fp32 (bias already added), pooled: [B][C*49] fp32, code: [B][C*49] bytes = argmax position in the
+// window (bits 0-1: dy*2 + dx, first maximum in scan order like ATen's max_pool2d) | 4 if the pooled value is > 0.
+// One block per (sample, 64 channels): every global access is a contiguous 256-byte (reads) or 12.5 KB (writes) run.
+constexpr int kPoolCB = 64;
+__global__ void __launch_bounds__(256) relu_pool_fwd_kernel(const float* __restrict__ y, float* __restrict__ pooled,
+                                                            uint8_t* __restrict__ code, int C) {
+  __shared__ float tile[kPoolCB * 49];
+  __shared__ uint8_t ctile[kPoolCB * 49];
+  const int b = blockIdx.y, c0 = blockIdx.x * kPoolCB;
+  const int cw = threadIdx.x % kPoolCB, wq = threadIdx.x / kPoolCB;
+  const float* yb = y + (static_cast<size_t>(b) * 196) * C + c0 + cw;
+  for (int w = wq; w < 49; w += 4) {
+    const int py = w / 7, px = w - py * 7;
+    const float* p00 = yb + static_cast<size_t>((2 * py) * 14 + 2 * px) * C;
+    const float v0 = p00[0], v1 = p00[C], v2 = p00[static_cast<size_t>(14) * C], v3 = p00[static_cast<size_t>(15) * C];
+    float m = v0; int a = 0;
+    if (v1 > m) { m = v1; a = 1; }
+    if (v2 > m) { m = v2; a = 2; }
+    if (v3 > m) { m = v3; a = 3; }
+    tile[cw * 49 + w] = fmaxf(m, 0.f);
+    ctile[cw * 49 + w] = static_cast<uint8_t>(a | (m > 0.f ? 4 : 0));
+  }
+  __syncthreads();
+  const size_t o = static_cast<size_t>(b) * C * 49 + static_cast<size_t>(c0) * 49;
+  for (int i = threadIdx.x; i < kPoolCB * 49; i += 256) { pooled[o + i] = tile[i]; code[o + i] = ctile[i]; }
+}
+__global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const float* __restrict__ g, const uint8_t* __restrict__ code,
+                                                            float* __restrict__ gy, int C) {
+  __shared__ float tile[kPoolCB * 49];
+  __shared__ uint8_t ctile[kPoolCB * 49];
+  const int b = blockIdx.y, c0 = blockIdx.x * kPoolCB;
+  const size_t o = static_cast<size_t>(b) * C * 49 + static_cast<size_t>(c0) * 49;
+  for (int i = threadIdx.x; i < kPoolCB * 49; i += 256) { tile[i] = g[o + i]; ctile[i] = code[o + i]; }
+  __syncthreads();
+  const int cw = threadIdx.x % kPoolCB, pq = threadIdx.x / kPoolCB;
+  float* gb = gy + (static_cast<size_t>(b) * 196) * C + c0 + cw;
+  for (int p = pq; p < 196; p += 4) {
+    const int yy = p / 14, xx = p - yy * 14;
+    const int w = (yy >> 1) * 7 + (xx >> 1), pos = (yy & 1) * 2 + (xx & 1);
+    const int cd = ctile[cw * 49 + w];
+    gb[static_cast<size_t>(p) * C] = (cd == (pos | 4)) ? tile[cw * 49 + w] : 0.f;
+  }
+}
+cudaError_t launch_relu_pool_fwd(const float* y, float* pooled, uint8_t* code, int B, int C, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  relu_pool_fwd_kernel<<<dim3(C / kPoolCB, B), 256, 0, st>>>(y, pooled, code, C);
+  return cudaGetLastError();
+}
+cudaError_t launch_relu_pool_bwd(const float* g, const uint8_t* code, float* gy, int B, int C, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  relu_pool_bwd_kernel<<<dim3(C / kPoolCB, B), 256, 0, st>>>(g, code, gy, C);
+  return cudaGetLastError();
+}
+
 }  // namespace pnmn

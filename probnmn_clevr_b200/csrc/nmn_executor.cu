@@ -1442,6 +1442,20 @@ extern "C" int pnmn_split3_bf16(const float* src, void* dst, int64_t rows, int64
   return 0;
 }
 
+// ReLU + 2x2 max-pool + flatten between the classifier's two GEMMs (nmn.py:77-79) and its backward (see layout.cu)
+extern "C" int pnmn_relu_pool_fwd(const float* y, float* pooled, void* code, int64_t B, int64_t C, void* stream) {
+  if (!y || !pooled || !code || B < 0 || C <= 0 || C % 64 != 0) return fail("pnmn_relu_pool_fwd: bad arguments (C must be a multiple of 64)");
+  CUDA_OK(launch_relu_pool_fwd(y, pooled, static_cast<uint8_t*>(code), static_cast<int>(B), static_cast<int>(C), static_cast<cudaStream_t>(stream)));
+  pnmn::count_launches(1);
+  return 0;
+}
+extern "C" int pnmn_relu_pool_bwd(const float* g, const void* code, float* gy, int64_t B, int64_t C, void* stream) {
+  if (!g || !gy || !code || B < 0 || C <= 0 || C % 64 != 0) return fail("pnmn_relu_pool_bwd: bad arguments (C must be a multiple of 64)");
+  CUDA_OK(launch_relu_pool_bwd(g, static_cast<const uint8_t*>(code), gy, static_cast<int>(B), static_cast<int>(C), static_cast<cudaStream_t>(stream)));
+  pnmn::count_launches(1);
+  return 0;
+}
+
 // ---- bring-up entry points -----------------------------------------------------------------------
 namespace {
 template <class T>

@@ -465,10 +465,13 @@ class NeuralModuleNetwork(nn.Module):
         conv, fc1, fc2 = self.classifier[0], self.classifier[4], self.classifier[6]
         B, C, H, W = final.shape
         x = final.permute(0, 2, 3, 1).reshape(B * H * W, C)
-        y = F.relu(_SplitLinear.apply(x, conv.weight.view(conv.out_channels, C), conv.bias))
-        y = y.view(B, H, W, conv.out_channels).permute(0, 3, 1, 2)          # NCHW view of channels-last data
-        y = F.max_pool2d(y, kernel_size=2, stride=2)
-        y = y.contiguous(memory_format=torch.contiguous_format).reshape(B, -1)  # (C, 7, 7) flatten order, nmn_modules.py:250
+        y = _SplitLinear.apply(x, conv.weight.view(conv.out_channels, C), conv.bias)   # channels-last, pre-activation
+        if H == 14 and W == 14 and conv.out_channels % 64 == 0:
+            y = _ReluPoolFlatten.apply(y, B)  # ReLU + MaxPool2d(2,2) + (C,7,7) flatten in one pass (nmn.py:77-79)
+        else:
+            y = F.relu(y).view(B, H, W, conv.out_channels).permute(0, 3, 1, 2)  # NCHW view of channels-last data
+            y = F.max_pool2d(y, kernel_size=2, stride=2)
+            y = y.contiguous(memory_format=torch.contiguous_format).reshape(B, -1)  # (C, 7, 7) order, nmn_modules.py:250
         z = F.relu(_SplitLinear.apply(y, fc1.weight, fc1.bias))
         logits = F.linear(z, fc2.weight, fc2.bias)
         for hook in self.classifier._forward_hooks.values():  # tests / tools observe the classifier through hooks
@@ -530,6 +533,36 @@ class _SplitLinear(torch.autograd.Function):
         if ctx.needs_input_grad[2]:
             db = g.sum(0)
         return dx, dw, db
+
+
+class _ReluPoolFlatten(torch.autograd.Function):
+    """ReLU -> MaxPool2d(2, 2) -> flatten of the channels-last 1x1-conv output [B*196, C] (nmn.py:77-79; flatten order
+    (C, 7, 7), nmn_modules.py:250-251) as ONE pass over the 205 MB tensor; the backward routes each pooled gradient to the
+    first maximum of its window (ATen's tie rule) if that maximum was positive (``pnmn_relu_pool_fwd`` / ``_bwd``)."""
+
+    @staticmethod
+    def forward(ctx, y, B):
+        y = y.contiguous()
+        C = y.shape[1]
+        pooled = torch.empty((B, C * 49), dtype=torch.float32, device=y.device)
+        code = torch.empty((B, C * 49), dtype=torch.uint8, device=y.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)
+        L.check(L.lib().pnmn_relu_pool_fwd(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(pooled.data_ptr()),
+                                           ctypes.c_void_p(code.data_ptr()), B, C, stream), "pnmn_relu_pool_fwd")
+        ctx.save_for_backward(code)
+        ctx.shape = (B, C)
+        return pooled
+
+    @staticmethod
+    def backward(ctx, g):
+        (code,) = ctx.saved_tensors
+        B, C = ctx.shape
+        g = g.contiguous()
+        gy = torch.empty((B * 196, C), dtype=torch.float32, device=g.device)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
+        L.check(L.lib().pnmn_relu_pool_bwd(ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(code.data_ptr()),
+                                           ctypes.c_void_p(gy.data_ptr()), B, C, stream), "pnmn_relu_pool_bwd")
+        return gy, None
 
 
 class _MatmulPrecision(torch.autograd.Function):

@@ -9,5 +9,5 @@ python - <<'PY'
 import json
 d=json.load(open('gpurun_out/bench_quick.json'))
 print('value', round(d['value']), 'ms/step', round(d['ms_per_step'],2), 'e2e', round(d['e2e']['value']), 'roofline frac', round(d['roofline']['frac'],4))
-print({k: round(v,2) for k,v in d['kernel_ms_per_step'].items()}, d.get('host_ms_per_step'))
+print({k: round(v,2) for k,v in d["kernel_ms_per_step"].items()}, {k: round(v,2) for k,v in d["host_ms_per_step"].items()})
 PY

@@ -260,3 +260,23 @@ def test_wgrad_projection_half(impl):
     print(f"wgrad proj impl={impl}: rel err {err:.3e}")
     assert err < 2e-5
     assert dw[:, :128].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("B,C", [(3, 64), (5, 1024)])
+def test_relu_pool_flatten(B, C):
+    """ReLU -> MaxPool2d(2,2) -> flatten between the classifier's GEMMs (nmn.py:77-79, nmn_modules.py:250-251):
+    the fused pass equals the PyTorch ops bit for bit, forward and backward (ties and all-negative windows included)."""
+    from probnmn_clevr_b200.nmn import _ReluPoolFlatten
+    g = torch.Generator(device="cuda").manual_seed(5)
+    y = torch.randn((B * 196, C), generator=g, device="cuda")
+    y[::7] = y[::7].round()          # exact ties inside windows
+    y[3::11] = -y[3::11].abs()       # windows without a positive value
+    y1 = y.clone().requires_grad_(True)
+    out = _ReluPoolFlatten.apply(y1, B)
+    y2 = y.clone().requires_grad_(True)
+    ref = F.max_pool2d(F.relu(y2).view(B, 14, 14, C).permute(0, 3, 1, 2), 2, 2).contiguous().reshape(B, -1)
+    assert torch.equal(out, ref)
+    go = torch.randn(out.shape, generator=g, device="cuda")
+    out.backward(go)
+    ref.backward(go)
+    assert torch.equal(y1.grad, y2.grad)
