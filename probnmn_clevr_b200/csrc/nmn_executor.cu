@@ -507,7 +507,9 @@ PinnedBlob* pin_acquire(size_t bytes) {
   PinnedBlob* best = nullptr;
   // prefer a buffer whose last upload has already been consumed by the GPU (the host may run ahead of the device)
   for (int pass = 0; pass < 2 && !best; ++pass) {
-    if (pass == 1 && g_pin_total < 8) break;  // everything is in flight: grow the pool instead of stalling
+    // everything is in flight: grow the pool up to three buffers (the host then runs at most two steps ahead of the
+    // device; cudaHostAlloc costs milliseconds and synchronises, so the pool must not keep growing), else wait for the oldest
+    if (pass == 1 && g_pin_total < 3) break;
     for (size_t i = 0; i < g_pin_free.size(); ++i) {
       PinnedBlob* c = g_pin_free[i];
       if (c->cap < bytes) continue;

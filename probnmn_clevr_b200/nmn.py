@@ -102,10 +102,83 @@ class _Average:
         return out
 
 
-class _Accuracy(_Average):
+class _Accuracy:
+    """BooleanAccuracy (nmn.py:120-121).  Per-batch correct counts may arrive as DEVICE scalars: they are only read
+    (one device -> host sync) when somebody asks for the value, so that ``forward`` never waits for the device."""
+
+    def __init__(self):
+        self.total, self.count, self.pending = 0.0, 0, []
+
     def __call__(self, correct, total):
-        self.total += float(correct)
+        if torch.is_tensor(correct):
+            self.pending.append(correct)
+        else:
+            self.total += float(correct)
         self.count += int(total)
+
+    def snapshot(self, reset=False):
+        state = (self.total, self.count, list(self.pending))
+        if reset:
+            self.total, self.count, self.pending = 0.0, 0, []
+        return state
+
+    @staticmethod
+    def value(state):
+        total, count, pending = state
+        total += sum(float(t.item()) for t in pending)
+        return total / count if count else 0.0
+
+    def get_metric(self, reset=False):
+        return self.value(self.snapshot(reset))
+
+
+class _LazyMetrics(dict):
+    """The ``"metrics"`` entry of the training-mode output (nmn.py:273-274): a real ``dict`` (the reference's trainer
+    tests ``isinstance(..., dict)``, trainers/_trainer.py:197) whose values are computed -- and the device synchronised --
+    the first time one of them is read.  Keys, length and membership never synchronise."""
+
+    def __init__(self, thunks):
+        super().__init__({k: None for k in thunks})
+        self._thunks = dict(thunks)
+
+    def _force(self):
+        if self._thunks is not None:
+            thunks, self._thunks = self._thunks, None
+            for k, f in thunks.items():
+                super().__setitem__(k, f())
+        return self
+
+    def __getitem__(self, k):
+        self._force()
+        return super().__getitem__(k)
+
+    def get(self, k, default=None):
+        self._force()
+        return super().get(k, default)
+
+    def __iter__(self):  # (also keeps dict(...) / {**...} off the C fast path that would copy the placeholders)
+        return iter(list(super().keys()))
+
+    def items(self):
+        self._force()
+        return super().items()
+
+    def values(self):
+        self._force()
+        return super().values()
+
+    def copy(self):
+        return dict(self._force())
+
+    def __eq__(self, other):
+        self._force()
+        return super().__eq__(other)
+
+    __hash__ = None
+
+    def __repr__(self):
+        self._force()
+        return super().__repr__()
 
 
 # ------------------------------------------------------------------------------------------------
@@ -451,12 +524,18 @@ class NeuralModuleNetwork(nn.Module):
             loss = -best_logprobs
         loss = loss.masked_fill(invalid, 3.33)  # constant, carries no gradient (in-place write in the reference)
         if answers is not None:
-            self._answer_accuracy((answer_predictions == answers).sum().item(), B)
+            # the correct count stays on the device until a metric is read: no synchronisation inside forward
+            self._answer_accuracy((answer_predictions == answers).sum(), B)
             self._average_invalid_programs(int((valid_host == 0).sum()))
 
         output_dict = {"predictions": answer_predictions, "loss": loss}
         if self.training:
-            output_dict["metrics"] = self.get_metrics(reset=True)
+            # same values as the reference's ``self.get_metrics(reset=True)`` (nmn.py:274): the accumulators are
+            # snapshotted and reset NOW, the numbers are produced when the dict is first read
+            acc_state = self._answer_accuracy.snapshot(reset=True)
+            invalid_now = self._average_invalid_programs.get_metric(reset=True)
+            output_dict["metrics"] = _LazyMetrics({"answer_accuracy": lambda: _Accuracy.value(acc_state),
+                                                   "average_invalid": lambda: invalid_now})
         return output_dict
 
     def _classifier_split(self, final: torch.Tensor) -> torch.Tensor:

@@ -82,3 +82,32 @@ def test_program_compiler_edge_cases(model):
         valid, sizes, stats = _plan_valid(model, big, ng)
         assert valid.all()
         assert stats[1] > 0 and sizes[L.SZ_ARENA16] > 0
+
+
+def test_lazy_metrics_is_a_dict_that_reads_late():
+    """The training-mode "metrics" entry (nmn.py:273-274) must stay a dict for the reference's trainer
+    (trainers/_trainer.py:197) but must not synchronise the device until a value is read."""
+    import json
+
+    import torch
+
+    from probnmn_clevr_b200.nmn import _Accuracy, _LazyMetrics
+
+    calls = []
+    acc = _Accuracy()
+    acc(torch.tensor(3), 4)
+    acc(1, 4)
+    state = acc.snapshot(reset=True)
+    assert acc.get_metric() == 0.0  # reset happened at snapshot time
+
+    def read():
+        calls.append(1)
+        return _Accuracy.value(state)
+
+    m = _LazyMetrics({"answer_accuracy": read, "average_invalid": lambda: 0.25})
+    assert isinstance(m, dict) and len(m) == 2 and "answer_accuracy" in m and list(m) == ["answer_accuracy", "average_invalid"]
+    assert calls == []  # nothing evaluated so far
+    assert m["answer_accuracy"] == 0.5 and calls == [1]
+    assert dict(m) == {"answer_accuracy": 0.5, "average_invalid": 0.25} == {**m}
+    assert json.loads(json.dumps(m)) == {"answer_accuracy": 0.5, "average_invalid": 0.25}
+    assert calls == [1]  # evaluated once
