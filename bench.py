@@ -34,8 +34,8 @@ UNIT = "questions/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=40)
+    ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--length", type=int, default=40)
@@ -234,8 +234,20 @@ def run_ours(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms)
 
+    lookahead = os.environ.get("PNMN_NO_PRECOMPILE") is None  # diagnostics: compile every plan inline
+
     def resident_step(i):
-        step(*resident[i % 2])
+        # software pipeline of the host side: the program compiler works on the NEXT batch (helper thread) while this
+        # thread issues the current step -- the same look-ahead an input pipeline gives the feature copy
+        f, p, a = resident[i % 2]
+        model.zero_grad(set_to_none=True)
+        if lookahead:
+            model.precompile(resident[(i + 1) % 2][1])
+        out = model(f, p, a)
+        loss = out["loss"].mean()
+        loss.backward()
+        if world > 1:
+            model.allreduce_gradients()
 
     # end-to-end leg: every step's features / answers start in PINNED HOST memory; the copy of step i+1 is issued on a side
     # stream before step i computes (probnmn_clevr_b200/feed.py), so all K copies sit inside the timed region but overlap
@@ -252,11 +264,25 @@ def run_ours(args):
         loss_events[i].synchronize()
         loss_values.append(float(loss_host[i]))
 
+    e2e_variant = os.environ.get("PNMN_E2E_VARIANT", "")  # diagnostics only: "nocopy" / "noread" drop one part of the leg
+
     def e2e_step(i):
+        if e2e_variant == "nocopy":
+            model.zero_grad(set_to_none=True)
+            out = model(resident[i % 2][0], host[i % 2][1], resident[i % 2][2])
+            loss = out["loss"].mean()
+            loss.backward()
+            loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+            loss_events[i].record()
+            if i > 0:
+                read_loss(i - 1)
+            return
         if feed.pending() == 0:
             feed.submit(i, (host[i % 2][0], host[i % 2][2]))
         f, a = feed.get(i)
         model.zero_grad(set_to_none=True)
+        if lookahead and i + 1 < e2e_total["n"]:
+            model.precompile(host[(i + 1) % 2][1])
         out = model(f, host[i % 2][1], a)
         # the next batch's copy is queued AFTER this forward's task-table upload (same H2D engine, FIFO): it then overlaps
         # with the executor instead of delaying it
@@ -270,13 +296,17 @@ def run_ours(args):
         # loop) so that the host can prepare step i+1 while step i still runs; the last one is read by e2e_finish()
         loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         loss_events[i].record()
-        if i > 0:
+        if i > 0 and e2e_variant != "noread":
             read_loss(i - 1)
 
     def e2e_finish():
+        if e2e_variant == "noread":
+            for j in range(e2e_total["n"]):
+                read_loss(j)
+            return
         read_loss(e2e_total["n"] - 1)
 
-    for i in range(max(args.warmup, 3)):
+    for i in range(max(args.warmup, 8)):  # (at least 8: the pinned staging pool of the plan uploads settles during warm-up)
         resident_step(i)
     host_ms = (ctypes.c_double * 4)()
     L.lib().pnmn_debug_host_times(host_ms)
@@ -300,6 +330,16 @@ def run_ours(args):
     loss_values.clear()
     ms_e2e = timed(e2e_step, args.steps, e2e_finish)
     assert len(loss_values) == args.steps and all(v == v for v in loss_values), "every step's loss must have been read back"
+
+    # the end-to-end leg moves 205.5 MB of fp32 features per step: what the host -> device link alone sustains for that copy
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(3):
+        resident[0][0].copy_(host[0][0], non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_ms = ev0.elapsed_time(ev1) / 3
 
     value = world * args.batch * args.steps / (ms * 1e-3)
     e2e_value = world * args.batch * args.steps / (ms_e2e * 1e-3)
@@ -335,6 +375,7 @@ def run_ours(args):
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps,
+                "h2d_copy_alone_ms": h2d_ms,  # bare pinned -> device copy of one step's features: the floor of this leg
                 "pipeline": "pinned host buffers; the copy of step i+1 runs on a side stream during step i (feed.DevicePrefetcher); "
                             "every step's loss is copied to pinned host memory and read one step later (all K reads inside the timed region)"},
         "gpu_launches": own_launches,

@@ -18,6 +18,8 @@
 #include <malloc.h>
 #include <map>
 #include <string>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "../../include/pnmn.h"
@@ -259,11 +261,20 @@ struct Sched {
   template <class Emit>
   void group_convs(std::vector<int>& v, int kind, Emit emit) {
     if (v.empty()) return;
-    std::stable_sort(v.begin(), v.end(), [&](int x, int y) {
-      const ConvTask& a = protos[x].t; const ConvTask& c = protos[y].t;
-      if (a.cfg != c.cfg) return a.cfg < c.cfg;
-      return reinterpret_cast<uint64_t>(a.w) < reinterpret_cast<uint64_t>(c.w);
-    });
+    // stable order by (cfg, weights): sort packed 64-bit keys (cfg | weight offset / 16 | position) instead of chasing
+    // the 136-byte prototypes in a comparator -- this sort was a quarter of pnmn_plan_create
+    {
+      std::vector<uint64_t> keys(v.size());
+      for (size_t i = 0; i < v.size(); ++i) {
+        const ConvTask& a = protos[v[i]].t;
+        const uint64_t w16 = (reinterpret_cast<uint64_t>(a.w) & ((1ull << 36) - 1)) >> 4;  // symbolic pointer: offset in the packed-weight arena
+        keys[i] = static_cast<uint64_t>(a.cfg) << 56 | (w16 & 0xFFFFFFFull) << 28 | static_cast<uint64_t>(i);
+      }
+      std::sort(keys.begin(), keys.end());
+      std::vector<int> sorted(v.size());
+      for (size_t i = 0; i < v.size(); ++i) sorted[i] = v[keys[i] & 0xFFFFFFFull];
+      v.swap(sorted);
+    }
     // Task granularity adapts to the level's width (one CTA per SM, 148 SMs): wide levels pair two
     // samples per CTA (shared weight stream), narrow levels split a sample's M tiles over several CTAs.
     const int U = static_cast<int>(v.size());
@@ -320,6 +331,7 @@ struct Sched {
   // cost model) instead of keeping it step-aligned.  Measured on the bench workload: no gain (2.68 vs 2.70 ms; the span
   // is set by the longest chain, not by lock-step between chains) for 0.7 ms more host time, hence off by default.
   void flatten_persistent(std::vector<TaskRec>& out, std::vector<TaskMeta>& meta, const std::vector<ConvCfg>& cfgs) {
+    static const bool est_order = std::getenv("PNMN_EST_ORDER") != nullptr;
     struct Latest { int n = 0; int ids[4] = {0, 0, 0, 0}; int stamp = -1; };
     std::vector<Latest> latest(step.size()), next(step.size());
     std::vector<float> chain_t(step.size(), 0.f), next_t(step.size(), 0.f), est;
@@ -330,8 +342,7 @@ struct Sched {
     est.reserve(total);
     int cur = 0;
     auto push = [&](const void* rec, int type, const int* samples, int ns, float dur) {
-      out.emplace_back();
-      std::memcpy(out.back().b, rec, 128);
+      out.push_back(*static_cast<const TaskRec*>(rec));
       meta.emplace_back();
       TaskMeta& m = meta.back();
       m.type = type; m.n_deps = 0;
@@ -339,8 +350,10 @@ struct Sched {
       const int id = static_cast<int>(out.size()) - 1;
       static const bool no_deps = std::getenv("PNMN_NODEPS") != nullptr;  // diagnostics: throughput without dependencies (results are garbage)
       float start = 0.f;
-      for (int k = 0; k < ns; ++k) start = std::max(start, chain_t[samples[k]]);
-      est.push_back(start);
+      if (est_order) {
+        for (int k = 0; k < ns; ++k) start = std::max(start, chain_t[samples[k]]);
+        est.push_back(start);
+      }
       for (int k = 0; k < ns; ++k) {
         const Latest& l = latest[samples[k]];
         for (int j = 0; j < (no_deps ? 0 : l.n); ++j) {
@@ -365,8 +378,8 @@ struct Sched {
     };
     for (auto& b : buckets) {
       for (int kind = LK_CONV0; kind <= LK_CONV1; ++kind)
-        group_convs(b[kind], kind, [&](const ConvTask& t, const int* samples, int ns) { push(&t, TASK_CONV, samples, ns, conv_us(t)); });
-      for (int i : b[LK_ELT]) push(&elts[i], TASK_ELT, &elt_sample[i], 1, elt_us(elts[i]));
+        group_convs(b[kind], kind, [&](const ConvTask& t, const int* samples, int ns) { push(&t, TASK_CONV, samples, ns, est_order ? conv_us(t) : 0.f); });
+      for (int i : b[LK_ELT]) push(&elts[i], TASK_ELT, &elt_sample[i], 1, est_order ? elt_us(elts[i]) : 0.f);
       // a sample has exactly one stage per step: its `latest` set becomes this step's task ids
       for (int kind = 0; kind < 3; ++kind)
         for (int i : b[kind]) {
@@ -375,7 +388,6 @@ struct Sched {
         }
       ++cur;
     }
-    static const bool est_order = std::getenv("PNMN_EST_ORDER") != nullptr;
     if (!est_order || out.empty()) return;
     const int n = static_cast<int>(out.size());
     std::vector<int> order(n), newpos(n);
@@ -460,10 +472,19 @@ struct Builder {
   float* grad(int64_t off) const { return sym<float>(AR_GRADS, off * 4); }
   const void* packed(int64_t off) const { return sym<const void>(AR_PACKED, off * 2); }
 
+  // configurations are looked up ~13k times per plan: compare one packed 64-bit key instead of the 48-byte records
+  std::vector<uint64_t> cfg_keys;
+  static uint64_t cfg_key(const ConvCfg& c) {
+    return static_cast<uint64_t>(c.n_kb) | static_cast<uint64_t>(c.kb_per_in) << 8 | static_cast<uint64_t>(c.ntaps) << 16 |
+           static_cast<uint64_t>(c.dil) << 20 | static_cast<uint64_t>(c.S_in) << 24 | static_cast<uint64_t>(c.S_out) << 32 |
+           static_cast<uint64_t>(c.S_aux) << 40 | static_cast<uint64_t>(c.flags) << 48;
+  }
   int cfg_id(const ConvCfg& c) {
-    for (size_t i = 0; i < p.cfgs.size(); ++i)
-      if (std::memcmp(&p.cfgs[i], &c, sizeof(ConvCfg)) == 0) return static_cast<int>(i);
+    const uint64_t key = cfg_key(c);
+    for (size_t i = 0; i < cfg_keys.size(); ++i)
+      if (cfg_keys[i] == key) return static_cast<int>(i);
     p.cfgs.push_back(c);
+    cfg_keys.push_back(key);
     return static_cast<int>(p.cfgs.size()) - 1;
   }
   int make_cfg(int n_kb, int kb_per_in, int ntaps, int dil, PlaneFmt in, PlaneFmt out, PlaneFmt aux, int flags) {
@@ -503,13 +524,15 @@ struct PinnedBlob {
 namespace {
 std::vector<PinnedBlob*> g_pin_free;
 int g_pin_total = 0;
+std::mutex g_pin_mutex;  // plans may be compiled on a helper thread (NeuralModuleNetwork.precompile) and destroyed on another
 PinnedBlob* pin_acquire(size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_pin_mutex);
   PinnedBlob* best = nullptr;
   // prefer a buffer whose last upload has already been consumed by the GPU (the host may run ahead of the device)
   for (int pass = 0; pass < 2 && !best; ++pass) {
-    // everything is in flight: grow the pool up to three buffers (the host then runs at most two steps ahead of the
+    // everything is in flight: grow the pool up to five buffers (look-ahead compile + the host running two steps ahead of the
     // device; cudaHostAlloc costs milliseconds and synchronises, so the pool must not keep growing), else wait for the oldest
-    if (pass == 1 && g_pin_total < 3) break;
+    if (pass == 1 && g_pin_total < 5) break;
     for (size_t i = 0; i < g_pin_free.size(); ++i) {
       PinnedBlob* c = g_pin_free[i];
       if (c->cap < bytes) continue;
@@ -534,7 +557,11 @@ PinnedBlob* pin_acquire(size_t bytes) {
   if (best->pending) { cudaEventSynchronize(best->ev); best->pending = false; }
   return best;
 }
-void pin_release(PinnedBlob* b) { if (b) g_pin_free.push_back(b); }
+void pin_release(PinnedBlob* b) {
+  if (!b) return;
+  std::lock_guard<std::mutex> lock(g_pin_mutex);
+  g_pin_free.push_back(b);
+}
 
 struct BaseTable { uint64_t b[AR_COUNT]; };
 // one thread per 8-byte word of a record array; `mask` marks the words that hold (symbolic) pointers.
@@ -573,11 +600,16 @@ cudaError_t launch_resolve(uint8_t* blob, int64_t off, size_t n_rec, int rec_byt
 
 static const int kRelateDil[5] = {1, 2, 4, 8, 1};
 
+std::mutex g_host_ms_mutex;
 double g_host_ms[4] = {0, 0, 0, 0};  // plan_create, forward (host part), backward (host part), calls
 struct HostTimer {
   int slot; std::chrono::steady_clock::time_point t0;
   explicit HostTimer(int s) : slot(s), t0(std::chrono::steady_clock::now()) {}
-  ~HostTimer() { g_host_ms[slot] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); }
+  ~HostTimer() {
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    std::lock_guard<std::mutex> lock(g_host_ms_mutex);
+    g_host_ms[slot] += ms;
+  }
 };
 long long* g_trace = nullptr;   // optional device buffer for per-task timestamps (pnmn_debug_set_trace)
 int64_t g_trace_cap = 0;        // capacity in tasks
@@ -591,7 +623,7 @@ bool exec_persistent() {
 
 extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* programs, int B, int L, int need_grad) {
   HostTimer timer(0);
-  g_host_ms[3] += 1;
+  { std::lock_guard<std::mutex> lock(g_host_ms_mutex); g_host_ms[3] += 1; }
   auto* plan = new pnmn_plan();
   pnmn_plan& p = *plan;
   p.m = m; p.B = B; p.L = L; p.need_grad = need_grad != 0;
@@ -1003,11 +1035,18 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
 
   // ---------------- flatten ----------------
   const auto t_emit = std::chrono::steady_clock::now();
-  if (p.persistent) fs.flatten_persistent(p.ftask, p.fmeta, p.cfgs);
-  else fs.flatten(p.felt, p.fconv, p.flaunch);
+  // the forward list, the backward list and the weight-gradient tasks are independent: the backward list (the longest)
+  // is flattened on a helper thread while this thread does the other two
+  std::thread bwd_flatten;
+  if (p.persistent) {
+    if (p.need_grad) bwd_flatten = std::thread([&] { bs.flatten_persistent(p.btask, p.bmeta, p.cfgs); });
+    fs.flatten_persistent(p.ftask, p.fmeta, p.cfgs);
+  } else {
+    fs.flatten(p.felt, p.fconv, p.flaunch);
+  }
+  struct Joiner { std::thread& t; ~Joiner() { if (t.joinable()) t.join(); } } joiner{bwd_flatten};
   if (p.need_grad) {
-    if (p.persistent) bs.flatten_persistent(p.btask, p.bmeta, p.cfgs);
-    else bs.flatten(p.belt, p.bconv, p.blaunch);
+    if (!p.persistent) bs.flatten(p.belt, p.bconv, p.blaunch);
     // wgrad / bias-grad tasks per weight tensor
     const int64_t inst_base = 0;
     (void)inst_base;
@@ -1069,6 +1108,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
     p.blaunch.push_back({LK_BIAS, 0, static_cast<int>(p.btasks.size())});
   }
 
+  if (bwd_flatten.joinable()) bwd_flatten.join();
   const auto t_flat = std::chrono::steady_clock::now();
   static const bool plan_timing = std::getenv("PNMN_PLAN_TIMING") != nullptr;
   auto ms_between = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };

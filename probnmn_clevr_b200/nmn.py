@@ -172,7 +172,12 @@ class _LazyMetrics(dict):
 
     def __eq__(self, other):
         self._force()
+        if isinstance(other, _LazyMetrics):
+            other._force()
         return super().__eq__(other)
+
+    def __ne__(self, other):
+        return not self.__eq__(other)
 
     __hash__ = None
 
@@ -343,6 +348,7 @@ class NeuralModuleNetwork(nn.Module):
         self._packed: Optional[torch.Tensor] = None
         self.last_plan_stats: Optional[List[int]] = None
         self._gflat_box: Dict[str, torch.Tensor] = {}
+        self._precompiled: list = []  # pending (programs, need_grad, future of a plan) entries, see precompile()
         # classifier GEMMs (plain library GEMMs, nmn.py:75-83): "split" (default) = every fp32 operand split into two bf16
         # halves (pnmn_split3_bf16, one pass), one cuBLAS tensor-core GEMM over the 3x contraction with fp32 accumulation
         # (~16 mantissa bits per operand); "ieee" = cuBLAS/cuDNN fp32 SIMT like the reference; "tf32" = 10-bit operands
@@ -476,10 +482,9 @@ class NeuralModuleNetwork(nn.Module):
         # forward's single D2H copy.
         programs_host = programs.detach().to("cpu", torch.int64).contiguous()
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._exec_params)
-        plan = lib.pnmn_plan_create(self._model_handle, ctypes.cast(programs_host.data_ptr(), ctypes.POINTER(ctypes.c_int64)),
-                                    B, Lp, 1 if need_grad else 0)
-        if not plan:
-            raise RuntimeError("pnmn_plan_create failed: " + lib.pnmn_last_error().decode())
+        plan = self._take_precompiled(programs_host, need_grad)
+        if plan is None:
+            plan = self._compile(programs_host, need_grad, None)
         valid_host = torch.empty(B, dtype=torch.uint8)
         lib.pnmn_plan_valid(plan, ctypes.cast(valid_host.data_ptr(), ctypes.POINTER(ctypes.c_uint8)))
         sizes = (ctypes.c_int64 * L.SZ_COUNT)()
@@ -538,6 +543,55 @@ class NeuralModuleNetwork(nn.Module):
                                                    "average_invalid": lambda: invalid_now})
         return output_dict
 
+    # ---- program compiler -------------------------------------------------------------------------------------------
+    def _compile(self, programs_host: torch.Tensor, need_grad: bool, device):
+        lib = L.lib()
+        B, Lp = programs_host.shape
+        ptr = ctypes.cast(programs_host.data_ptr(), ctypes.POINTER(ctypes.c_int64))
+        if device is not None:  # helper thread: the pinned staging buffers and their events belong to this device
+            with torch.cuda.device(device):
+                plan = lib.pnmn_plan_create(self._model_handle, ptr, B, Lp, 1 if need_grad else 0)
+        else:
+            plan = lib.pnmn_plan_create(self._model_handle, ptr, B, Lp, 1 if need_grad else 0)
+        if not plan:
+            raise RuntimeError("pnmn_plan_create failed: " + lib.pnmn_last_error().decode())
+        return plan
+
+    def precompile(self, programs: torch.Tensor, need_grad: Optional[bool] = None) -> None:
+        """Optional look-ahead for input pipelines: start compiling ``programs`` (host tensor, (B, L) token ids) into an
+        executor plan on a helper thread.  A later ``forward`` whose programs have the same contents picks the plan up
+        instead of compiling inline (2-4 ms of host time per 256 programs).  At most two plans wait at a time (the oldest
+        is dropped), so a pipeline can submit batch i+1 before it runs batch i.  The reference has no counterpart -- its
+        interpreter walks the programs inside forward (nmn.py:191-238) -- and results are identical with or without it."""
+        self._ensure_flat()
+        if programs.device.type != "cpu":
+            raise ValueError("precompile needs the programs in host memory (that is where the compiler runs)")
+        host = programs.detach().to(torch.int64).contiguous().clone()
+        if need_grad is None:
+            need_grad = self.training and any(p.requires_grad for p in self._exec_params)
+        device = self._flat.device if self._flat is not None and self._flat.is_cuda else None
+        while len(self._precompiled) >= 2:
+            self._destroy_pending(self._precompiled.pop(0))
+        self._precompiled.append((host, bool(need_grad), _compile_pool().submit(self._compile, host, bool(need_grad), device)))
+
+    def _take_precompiled(self, programs_host: torch.Tensor, need_grad: bool):
+        for k, (host, ng, fut) in enumerate(self._precompiled):
+            if ng == need_grad and host.shape == programs_host.shape and torch.equal(host, programs_host):
+                del self._precompiled[k]
+                return fut.result()
+        return None
+
+    @staticmethod
+    def _destroy_pending(entry) -> None:
+        try:
+            L.lib().pnmn_plan_destroy(entry[2].result())
+        except Exception:
+            pass
+
+    def _drop_precompiled(self) -> None:
+        while self._precompiled:
+            self._destroy_pending(self._precompiled.pop())
+
     def _classifier_split(self, final: torch.Tensor) -> torch.Tensor:
         """nmn.py:75-83 with the two large GEMMs (1x1 conv 128->1024 over B*196 pixels, Linear 50176->1024) as
         split-bf16 tensor-core products; ReLU / max-pool / the 1024->28 Linear stay plain fp32 ops."""
@@ -576,6 +630,18 @@ class NeuralModuleNetwork(nn.Module):
 
 class _NullCtx:
     pass
+
+
+_COMPILE_POOL = None
+
+
+def _compile_pool():
+    """One helper thread for NeuralModuleNetwork.precompile (ctypes releases the GIL around the C++ compiler)."""
+    global _COMPILE_POOL
+    if _COMPILE_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _COMPILE_POOL = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pnmn-plan")
+    return _COMPILE_POOL
 
 
 def _split3(x: torch.Tensor, dim: int, second_low: bool) -> torch.Tensor:

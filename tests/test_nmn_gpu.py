@@ -190,3 +190,34 @@ def test_attention_maps_and_bigger_batch_against_oracle(model):
     print(f"oracle batch: logits rel err {e:.2e}, final rel err {ef:.2e}")
     assert e < 1e-3 and ef < 1e-3
     np.testing.assert_allclose(out["loss"].detach().cpu().numpy(), ref["loss"].numpy(), rtol=1e-3, atol=1e-3)
+
+
+def test_precompile_lookahead_changes_nothing(model):
+    """NeuralModuleNetwork.precompile (plan compiled ahead of time on a helper thread) is purely a host-side pipeline:
+    the step that picks the plan up returns the same bits as an inline compile, a plan compiled for other programs is
+    discarded, and the training-mode metrics are the lazily evaluated dict."""
+    vocab = model.vocabulary
+    sampler = ProgramSampler(vocab, seed=23)
+    programs = torch.cat([sampler.sample(12, 26), sampler.garbage(4, 26)])
+    other = sampler.sample(16, 26)
+    feats, answers = make_features(16, 5).cuda(), make_answers(16, 5).cuda()
+    model.train()
+
+    def step(pre):
+        model.zero_grad()
+        if pre is not None:
+            model.precompile(pre)
+        out = model(feats, programs, answers)
+        out["loss"].mean().backward()
+        g = torch.cat([p.grad.flatten() for p in model.parameters() if p.grad is not None])
+        return out, g.clone()
+
+    ref, gref = step(None)
+    hit, ghit = step(programs)           # plan picked up
+    miss, gmiss = step(other)            # stale plan discarded, inline compile
+    for out, g in ((hit, ghit), (miss, gmiss)):
+        assert torch.equal(out["predictions"], ref["predictions"]) and torch.equal(out["loss"], ref["loss"])
+        assert out["metrics"] == ref["metrics"] and isinstance(out["metrics"], dict)
+    # gradients: the weight-gradient kernels accumulate with atomics (order varies run to run), so equality is to rounding
+    for g in (ghit, gmiss):
+        assert float((g - gref).abs().max()) <= 1e-5 * float(gref.abs().max())
