@@ -176,7 +176,7 @@ int pnmn_debug_pack(const void* pack_tasks_host, int n_tasks, int total_tiles, c
 int pnmn_debug_nchw_to_planes(const float* src, float* dst, int batch, int channels,
                               int64_t dst_sample_stride, void* stream);
 int pnmn_debug_launch_elt(const void* tasks_host, int n_tasks, void* stream);
-/* per-task timestamps of the persistent executor (8 int64 per task: fetched, ready, body done, published,
+/* per-task timestamps of the persistent executor (32 int64 per task, layout in csrc/exec.cu: fetched, ready, body done, published,
  * SM id, type|n_samp<<8|n_mt<<16, MMA k-steps, flags); forward tasks first, then backward; NULL disables */
 int pnmn_debug_set_trace(void* device_buffer, int64_t capacity_tasks);
 /* accumulated host-side milliseconds spent in {pnmn_plan_create, pnmn_nmn_forward, pnmn_nmn_backward} and the
