@@ -179,6 +179,10 @@ int pnmn_debug_launch_elt(const void* tasks_host, int n_tasks, void* stream);
 /* per-task timestamps of the persistent executor (32 int64 per task, layout in csrc/exec.cu: fetched, ready, body done, published,
  * SM id, type|n_samp<<8|n_mt<<16, MMA k-steps, flags); forward tasks first, then backward; NULL disables */
 int pnmn_debug_set_trace(void* device_buffer, int64_t capacity_tasks);
+/* task metadata of the persistent executor lists (pass 0 forward / 1 backward): 16 int32 per task
+ * {type, n_deps, deps[10], conv: n_samp, n_mt, MMAs per accumulator, flags | elementwise: op, part, 0, 0};
+ * returns the number of tasks (host only, no device work) */
+int64_t pnmn_debug_plan_meta(const pnmn_plan* p, int pass, int32_t* out, int64_t cap_tasks);
 /* accumulated host-side milliseconds spent in {pnmn_plan_create, pnmn_nmn_forward, pnmn_nmn_backward} and the
  * number of plans created since the last call (reading clears) */
 int pnmn_debug_host_times(double* ms);

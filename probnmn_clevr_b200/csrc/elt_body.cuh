@@ -351,7 +351,7 @@ __device__ __forceinline__ void elt_task_body(const EltTask& t, const int tid, E
       }
     } break;
 
-    case OP_RELU_MASK: {  // o = a (dY) masked by b (Y) > 0
+    case OP_RELU_MASK: {  // o = a (dY) [+ c, the second d(feat) accumulator of a two-strand backward] masked by b (Y) > 0
       for (int i0 = tid; i0 < items; i0 += 4 * 256) {
         float4 g[4], y[4];
         int off[4];
@@ -362,6 +362,10 @@ __device__ __forceinline__ void elt_task_body(const EltTask& t, const int tid, E
             off[u] = ((kc_lo + i / 196) * 256 + valid_slot16(i % 196)) * 4;
             g[u] = ld4(t.a + off[u]);
             y[u] = ld4(t.b + off[u]);
+            if (t.c) {
+              const float4 g2 = ld4(t.c + off[u]);
+              g[u].x += g2.x; g[u].y += g2.y; g[u].z += g2.z; g[u].w += g2.w;
+            }
           }
         }
 #pragma unroll

@@ -193,6 +193,7 @@ struct Val {
   bool cons_minmax = false;
   int dotsig_proto = -1;   // forward conv proto (index into Sched::protos) whose fused 1x1 head produced this map
   bool attend_fused = false;
+  int strand = -1;         // forward strand (Sched) that produces this value; -1 = the constant all-ones map
 };
 struct OpRec {
   int kind = 0, tok = 0;
@@ -203,6 +204,8 @@ struct OpRec {
   int y_unit[5] = {-1, -1, -1, -1, -1};  // conv outputs (arena of the NEXT conv's input format)
   int idx_slot = -1;
   bool attend_fused = false;  // feat * map is produced by the previous module's head conv (F_ATTEND), no elementwise task
+  int strand = -1;            // forward strand of this op's stages
+  int secondary = -1;         // binary ops: forward strand of the other input when it differs (joined here), else -1
 };
 
 enum LaunchKind { LK_ELT = 0, LK_CONV0 = 1, LK_CONV1 = 2, LK_WGRAD = 3, LK_BIAS = 4 };
@@ -215,19 +218,49 @@ struct ConvProto {
 
 struct TaskRec { uint8_t b[128]; };
 
+// Stages are placed on STRANDS.  A strand is a serial chain of stages (every stage waits for all tasks of the strand's
+// previous stage).  A sample starts with one strand (the stem); with the persistent executor the independent sub-chains of
+// a program -- everything between a `scene` token and the binary module that consumes it (nmn.py:216-222: `scene` parks the
+// running output in `saved` and restarts from the all-ones attention) -- get their own strand: fork() starts a strand
+// behind the current stage of its parent, join() makes the next stage of a strand wait for another strand as well.  The
+// two branches of a comparison / union / intersection then run concurrently instead of back to back, which shortens the
+// longest dependency chain of the batch -- the quantity that bounds the executor's span (scripts/sim_sched.py).
 struct Sched {
-  std::vector<int> step, last;
+  std::vector<int> step, last;                // per strand
+  std::vector<int> fork_parent, fork_step;    // per strand: parent (-1 = root) and the step of its first stage
+  struct Join { int step, primary, secondary; };
+  std::vector<Join> joins;
   std::vector<std::array<std::vector<int>, 3>> buckets;  // indices into elts / protos
   std::vector<EltTask> elts;
-  std::vector<int> elt_sample;
-  std::vector<ConvProto> protos;
-  bool unified;  // persistent executor: one stage per sample per step (dependencies are explicit)
+  std::vector<int> elt_sample;                // strand of every elementwise task
+  std::vector<ConvProto> protos;              // ConvProto::sample = strand
+  bool unified;  // persistent executor: one stage per strand per step (dependencies are explicit)
   bool dep_overflow = false;
-  Sched(int B, bool uni) : step(B, 0), last(B, -1), unified(uni) {
+  Sched(int B, bool uni) : unified(uni) {
+    step.reserve(static_cast<size_t>(B) * 3); last.reserve(static_cast<size_t>(B) * 3);
+    fork_parent.reserve(static_cast<size_t>(B) * 3); fork_step.reserve(static_cast<size_t>(B) * 3);
     elts.reserve(static_cast<size_t>(B) * 64);
     elt_sample.reserve(static_cast<size_t>(B) * 64);
     protos.reserve(static_cast<size_t>(B) * 48);
     buckets.reserve(128);
+  }
+  int new_strand() {
+    step.push_back(0); last.push_back(-1); fork_parent.push_back(-1); fork_step.push_back(0);
+    return static_cast<int>(step.size()) - 1;
+  }
+  int next_step(int s) const { return last[s] >= 0 ? step[s] + 1 : step[s]; }
+  // a strand whose first stage waits for the parent's CURRENT stage (later stages of the parent do not matter to it)
+  int fork(int parent) {
+    const int start = next_step(parent);
+    const int s = new_strand();
+    step[s] = start; fork_parent[s] = parent; fork_step[s] = start;
+    return s;
+  }
+  // the next stage placed on `primary` also waits for the current stage of `secondary`
+  void join(int primary, int secondary) {
+    const int st = std::max(next_step(primary), next_step(secondary));
+    step[primary] = last[primary] >= 0 ? st - 1 : st;
+    joins.push_back(Join{st, primary, secondary});
   }
   int place(int s, int kind) {
     if (unified ? last[s] >= 0 : kind <= last[s]) step[s]++;
@@ -325,80 +358,132 @@ struct Sched {
     }
   }
 
-  // Persistent-executor order: one list, every task names the tasks of its samples' previous stage.
-  // Persistent-executor order: one list, every task names the tasks of its samples' previous stage.
-  // PNMN_EST_ORDER=1 additionally sorts the list by each task's ESTIMATED start time (critical-path times from a per-task
-  // cost model) instead of keeping it step-aligned.  Measured on the bench workload: no gain (2.68 vs 2.70 ms; the span
-  // is set by the longest chain, not by lock-step between chains) for 0.7 ms more host time, hence off by default.
+  // Persistent-executor order: one list, every task names the tasks of its strands' previous stage (plus the stages that
+  // joins and forks bring in).  The list is then sorted by each task's REMAINING CHAIN TIME, longest first (the classic
+  // critical-path list-scheduling priority; a producer's remaining time exceeds its consumers', so producers stay in
+  // front and the executor's in-order fetch stays deadlock-free).  With the step-aligned order the long chains' stages
+  // sat behind whole levels of short-chain work; replaying the recorded trace (scripts/sim_sched.py) puts the forward
+  // pass of the bench workload at 767 us step-aligned vs 704 us in this order (critical path 695 us), the backward at
+  // 839 vs 754 us.  PNMN_LIST_ORDER=level keeps the step-aligned list.  Durations come from a cost model fitted to the
+  // trace (profiles/r1b_summary.md).
   void flatten_persistent(std::vector<TaskRec>& out, std::vector<TaskMeta>& meta, const std::vector<ConvCfg>& cfgs) {
-    static const bool est_order = std::getenv("PNMN_EST_ORDER") != nullptr;
-    struct Latest { int n = 0; int ids[4] = {0, 0, 0, 0}; int stamp = -1; };
+    static const bool cp_order = [] { const char* e = std::getenv("PNMN_LIST_ORDER"); return !(e && std::string(e) == "level"); }();
+    struct Latest { int n = 0; int ids[8] = {0, 0, 0, 0, 0, 0, 0, 0}; int stamp = -1; };
     std::vector<Latest> latest(step.size()), next(step.size());
-    std::vector<float> chain_t(step.size(), 0.f), next_t(step.size(), 0.f), est;
+    // forks / joins by the step at which they take effect
+    std::vector<std::vector<int>> forks_at(buckets.size()), joins_at(buckets.size());
+    for (size_t s = 0; s < step.size(); ++s)
+      if (fork_parent[s] >= 0 && fork_step[s] < static_cast<int>(buckets.size())) forks_at[fork_step[s]].push_back(static_cast<int>(s));
+    for (size_t j = 0; j < joins.size(); ++j)
+      if (joins[j].step < static_cast<int>(buckets.size())) joins_at[joins[j].step].push_back(static_cast<int>(j));
+    std::vector<float> dur;
     size_t total = elts.size();
     for (auto& b : buckets) total += b[LK_CONV0].size() * 2 + b[LK_CONV1].size() * 3;
     out.reserve(total);
     meta.reserve(total);
-    est.reserve(total);
+    dur.reserve(total);
     int cur = 0;
-    auto push = [&](const void* rec, int type, const int* samples, int ns, float dur) {
+    static const bool no_deps = std::getenv("PNMN_NODEPS") != nullptr;  // diagnostics: throughput without dependencies (results are garbage)
+    auto push = [&](const void* rec, int type, const int* strands, int ns, float d) {
       out.push_back(*static_cast<const TaskRec*>(rec));
       meta.emplace_back();
+      dur.push_back(d);
       TaskMeta& m = meta.back();
       m.type = type; m.n_deps = 0;
       for (int k = 0; k < kMaxDeps; ++k) m.deps[k] = -1;
       const int id = static_cast<int>(out.size()) - 1;
-      static const bool no_deps = std::getenv("PNMN_NODEPS") != nullptr;  // diagnostics: throughput without dependencies (results are garbage)
-      float start = 0.f;
-      if (est_order) {
-        for (int k = 0; k < ns; ++k) start = std::max(start, chain_t[samples[k]]);
-        est.push_back(start);
-      }
       for (int k = 0; k < ns; ++k) {
-        const Latest& l = latest[samples[k]];
+        const Latest& l = latest[strands[k]];
         for (int j = 0; j < (no_deps ? 0 : l.n); ++j) {
+          bool dup = false;  // two strands forked from the same stage share their producers
+          for (int q = 0; q < m.n_deps; ++q) dup = dup || m.deps[q] == l.ids[j];
+          if (dup) continue;
           if (m.n_deps < kMaxDeps) m.deps[m.n_deps++] = l.ids[j];
           else dep_overflow = true;
         }
-        Latest& nx = next[samples[k]];
-        if (nx.stamp != cur) { nx.stamp = cur; nx.n = 0; next_t[samples[k]] = 0.f; }
-        if (nx.n < 4) nx.ids[nx.n++] = id;
+        Latest& nx = next[strands[k]];
+        if (nx.stamp != cur) { nx.stamp = cur; nx.n = 0; }
+        if (nx.n < 8) nx.ids[nx.n++] = id;
         else dep_overflow = true;
-        next_t[samples[k]] = std::max(next_t[samples[k]], start + dur);
       }
     };
-    // measured body times (profiles/r1 trace): ~8 us fixed + 0.14 us per MMA and accumulator (0.095 for the long stem conv)
+    // body + publish times in us, fitted to the per-task trace of the bench workload (one-accumulator 3x3 conv: 12 us)
     auto conv_us = [&](const ConvTask& t) {
       const ConvCfg& c = cfgs[t.cfg];
       const float mm = static_cast<float>(c.n_kb * c.ntaps);
-      return 8.f + (mm <= 100.f ? 0.14f : 0.095f) * mm * static_cast<float>(t.n_samp * t.n_mt);
+      const float nacc = static_cast<float>(t.n_samp * t.n_mt);
+      float extra = 0.f;
+      if (c.flags & F_ATTBWD) extra += 2.8f;
+      if (c.flags & F_MASK16) extra += 1.6f;
+      if (c.flags & (F_MASK | F_ACCUM)) extra += 2.3f;
+      if (c.flags & F_ATTEND) extra += 3.3f;
+      return 7.f + nacc * (1.f + (mm <= 100.f ? 0.055f : 0.09f) * mm + extra) + 2.7f * static_cast<float>(t.n_samp - 1);
     };
     auto elt_us = [](const EltTask& e) {
-      return e.op == OP_SAME ? 12.f : (e.op == OP_SAME_BWD ? 22.f : ((e.op == OP_MINMAX || e.op == OP_MINMAX_BWD) ? 4.f : 9.f));
+      switch (e.op) {
+        case OP_SAME: return 14.f;
+        case OP_SAME_BWD: return 21.f;
+        case OP_MINMAX: return 2.5f;
+        case OP_MINMAX_BWD: return 3.7f;
+        case OP_DOTSIG_BWD: return 6.f;
+        case OP_ATTEND: return 7.f;
+        default: return 8.5f;
+      }
     };
     for (auto& b : buckets) {
+      // a forked strand starts from its parent's latest stage (strand ids grow from parent to child); a join adds the other
+      // strand's latest stage to the producers of this step's stage
+      for (int s : forks_at[cur]) { latest[s] = latest[fork_parent[s]]; latest[s].stamp = -1; }
+      for (int j : joins_at[cur]) {
+        Latest& l = latest[joins[j].primary];
+        const Latest& o = latest[joins[j].secondary];
+        for (int k = 0; k < o.n; ++k) {
+          bool dup = false;
+          for (int q = 0; q < l.n; ++q) dup = dup || l.ids[q] == o.ids[k];
+          if (dup) continue;
+          if (l.n < 8) l.ids[l.n++] = o.ids[k];
+          else dep_overflow = true;
+        }
+      }
       for (int kind = LK_CONV0; kind <= LK_CONV1; ++kind)
-        group_convs(b[kind], kind, [&](const ConvTask& t, const int* samples, int ns) { push(&t, TASK_CONV, samples, ns, est_order ? conv_us(t) : 0.f); });
-      for (int i : b[LK_ELT]) push(&elts[i], TASK_ELT, &elt_sample[i], 1, est_order ? elt_us(elts[i]) : 0.f);
-      // a sample has exactly one stage per step: its `latest` set becomes this step's task ids
+        group_convs(b[kind], kind, [&](const ConvTask& t, const int* strands, int ns) { push(&t, TASK_CONV, strands, ns, conv_us(t)); });
+      for (int i : b[LK_ELT]) push(&elts[i], TASK_ELT, &elt_sample[i], 1, elt_us(elts[i]));
+      // a strand has exactly one stage per step: its `latest` set becomes this step's task ids
       for (int kind = 0; kind < 3; ++kind)
         for (int i : b[kind]) {
           const int smp = kind == LK_ELT ? elt_sample[i] : protos[i].sample;
-          if (next[smp].stamp == cur) { latest[smp] = next[smp]; next[smp].stamp = -1; chain_t[smp] = next_t[smp]; }
+          if (next[smp].stamp == cur) { latest[smp] = next[smp]; next[smp].stamp = -1; }
         }
       ++cur;
     }
-    if (!est_order || out.empty()) return;
+    if (!cp_order || out.empty() || dep_overflow) return;
     const int n = static_cast<int>(out.size());
-    std::vector<int> order(n), newpos(n);
-    for (int i = 0; i < n; ++i) order[i] = i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return est[a] < est[c]; });
-    for (int i = 0; i < n; ++i) newpos[order[i]] = i;
+    // remaining chain time of every task (its own duration + the longest chain of consumers behind it)
+    std::vector<float> rem(dur);
+    for (int i = n - 1; i >= 0; --i)
+      for (int k = 0; k < meta[i].n_deps; ++k) {
+        const int j = meta[i].deps[k];
+        rem[j] = std::max(rem[j], dur[j] + 1.f + rem[i]);
+      }
+    // sort keys: remaining time (descending) in the high word, list position in the low word (stable, and cheap to sort)
+    std::vector<uint64_t> keys(n);
+    for (int i = 0; i < n; ++i) {
+      const uint32_t r = static_cast<uint32_t>(std::min(rem[i], 4.0e6f) * 1000.f);  // ns resolution, << 2^32
+      keys[i] = static_cast<uint64_t>(0xFFFFFFFFu - r) << 32 | static_cast<uint32_t>(i);
+    }
+    std::sort(keys.begin(), keys.end());
+    std::vector<int> newpos(n);
+    for (int i = 0; i < n; ++i) newpos[static_cast<uint32_t>(keys[i])] = i;
+    // quantisation of the key can tie a producer with its consumer only if durations were < 1 ns: check, fall back if so
+    for (int i = 0; i < n; ++i)
+      for (int k = 0; k < meta[i].n_deps; ++k)
+        if (newpos[meta[i].deps[k]] >= newpos[i]) return;
     std::vector<TaskRec> out2(n);
     std::vector<TaskMeta> meta2(n);
     for (int i = 0; i < n; ++i) {
-      out2[i] = out[order[i]];
-      meta2[i] = meta[order[i]];
+      const int o = static_cast<int>(static_cast<uint32_t>(keys[i]));
+      out2[i] = out[o];
+      meta2[i] = meta[o];
       for (int k = 0; k < meta2[i].n_deps; ++k) meta2[i].deps[k] = newpos[meta2[i].deps[k]];
     }
     out.swap(out2);
@@ -621,7 +706,8 @@ bool exec_persistent() {
 
 }  // namespace
 
-extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* programs, int B, int L, int need_grad) {
+static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs, int B, int L, int need_grad,
+                                   bool allow_strands, bool* overflow) {
   HostTimer timer(0);
   { std::lock_guard<std::mutex> lock(g_host_ms_mutex); g_host_ms[3] += 1; }
   auto* plan = new pnmn_plan();
@@ -637,6 +723,9 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   // fold feat * map (and its backward) into the neighbouring conv epilogues; only the persistent executor implements it
   static const bool no_fuse = std::getenv("PNMN_NOFUSE") != nullptr;
   const bool fuse_attend = p.persistent && !no_fuse;
+  // independent sub-chains of a program on their own strands (Sched); PNMN_NOSTRANDS=1 restores one chain per sample
+  static const bool no_strands = std::getenv("PNMN_NOSTRANDS") != nullptr;
+  const bool strands_on = p.persistent && allow_strands && !no_strands;
   // (Tried and dropped, profiles/r1_notes: storing conv outputs that only feed other convs as fp16 planes alone, with
   // fp16 ReLU masks in the backward, cuts the executor's DRAM traffic by a third but not its time: the epilogue is
   // latency-bound, not store-bound, and the extra mask path cost registers.)
@@ -665,6 +754,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
     const int feat_val = bd.new_val(VK_FEAT, 128, -1, true);
     std::vector<OpRec> ops;
     int out = feat_val, saved = -1;
+    int n_scene = 0, n_binary = 0;
     bool ok = true;
     for (int i = L - 1; i >= 0 && ok; --i) {
       const int64_t tok = programs[static_cast<size_t>(n) * L + i];
@@ -672,20 +762,20 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
       const ModuleDesc& md = m->mods[tok];
       switch (md.kind) {
         case PNMN_TOK_SKIP: break;
-        case PNMN_TOK_SCENE: saved = out; out = ones_val; break;
+        case PNMN_TOK_SCENE: saved = out; out = ones_val; ++n_scene; break;
         case PNMN_TOK_AND:
         case PNMN_TOK_OR: {
           if (saved < 0) { ok = false; break; }
           OpRec r; r.kind = md.kind; r.tok = static_cast<int>(tok); r.in0 = out; r.in1 = saved;
           const int ch = std::max(bd.vals[out].ch, bd.vals[saved].ch);
           r.out = bd.new_val(ch == 1 ? VK_MAP : VK_BUF, ch, -1, false);
-          ops.push_back(r); out = r.out;
+          ops.push_back(r); out = r.out; ++n_binary;
         } break;
         case PNMN_TOK_COMPARE: {
           if (saved < 0 || bd.vals[out].ch != 128 || bd.vals[saved].ch != 128) { ok = false; break; }
           OpRec r; r.kind = md.kind; r.tok = static_cast<int>(tok); r.in0 = out; r.in1 = saved; r.nconv = 3;
           r.out = bd.new_val(VK_BUF, 128, -1, true);
-          ops.push_back(r); out = r.out;
+          ops.push_back(r); out = r.out; ++n_binary;
         } break;
         case PNMN_TOK_QUERY:
         case PNMN_TOK_RELATE:
@@ -701,13 +791,19 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
       }
     }
     if (ok && bd.vals[out].ch != 128) ok = false;  // nmn.py:231-232
+    const int st_f = fs.new_strand();  // the sample's stem strand
     if (!ok) {
       bd.vals.resize(val_mark);
       EltTask g{}; g.op = OP_GATHER; g.a = nullptr;
       g.o = sym<float>(AR_FINAL, static_cast<int64_t>(n) * 128 * 196 * 4);
-      fs.add_elt(n, g);
+      fs.add_elt(st_f, g);
       continue;
     }
+    // Independent sub-chains on their own strands (see Sched).  Restricted to the well-formed shape -- at most two `scene`
+    // tokens and one binary module, so every value has at most one consumer: the backward pass then has at most two
+    // concurrent strands, each value's gradient has a single writer, and only d(feat) needs a second accumulator.
+    const bool par = strands_on && n_scene <= 2 && n_binary <= 1;
+    bd.vals[feat_val].strand = st_f;
     p.valid[n] = 1;
     p.stats[0]++;
 
@@ -727,13 +823,13 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
       t.in[0][0] = reinterpret_cast<const void*>(reinterpret_cast<uint64_t>(bd.ainp(xin)) + static_cast<uint64_t>(m->in_ch / 4) * 256 * 16);
       t.out[0] = bd.p16(y1s_unit[n]);
       t.w = bd.packed(c1.pk_fwd); t.bias = bd.param(c1.b_off);
-      fs.add_conv(n, t, 0);
+      fs.add_conv(st_f, t, 0);
       const ConvW& c2 = m->convs[m->stem2];
       ConvTask u{};
       u.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | F_STORE | HF);
       u.in[0][0] = Builder::shadow(bd.p16(y1s_unit[n]), kP16); u.out[0] = bd.p16(feat_unit[n]);
       u.w = bd.packed(c2.pk_fwd); u.bias = bd.param(c2.b_off);
-      fs.add_conv(n, u, 0);
+      fs.add_conv(st_f, u, 0);
     }
     const float* featp = bd.p16(feat_unit[n]);
 
@@ -741,6 +837,18 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
     for (OpRec& r : ops) {
       const ModuleDesc& md = m->mods[r.tok];
       n_tokens++;
+      // strand of this op's stages
+      int sf = st_f;
+      if (par) {
+        const int pa = bd.vals[r.in0].strand, pb = r.in1 >= 0 ? bd.vals[r.in1].strand : -1;
+        const bool binary = r.kind == PNMN_TOK_AND || r.kind == PNMN_TOK_OR || r.kind == PNMN_TOK_COMPARE;
+        if (pa >= 0 && pa != st_f) sf = pa;                 // continue the running output's chain
+        else if (binary && pb >= 0 && pb != st_f) sf = pb;  // the running output is the stem / all-ones: continue `saved`'s chain
+        else sf = fs.fork(st_f);                            // first module after `scene`: a new chain behind the stem
+        if (binary && pb >= 0 && pb != st_f && pb != sf) { r.secondary = pb; fs.join(sf, pb); }
+      }
+      r.strand = sf;
+      bd.vals[r.out].strand = sf;
       switch (r.kind) {
         case PNMN_TOK_AND:
         case PNMN_TOK_OR: {
@@ -752,7 +860,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           e.b = b.ch == 1 ? bd.mapp(b.unit) : bd.p16(b.unit);
           if (vo.ch == 1) { vo.unit = static_cast<int>(p.nmaps++); e.o = bd.mapp(vo.unit); }
           else { vo.unit = bd.alloc16(); e.o = bd.p16(vo.unit); }
-          fs.add_elt(n, e);
+          fs.add_elt(sf, e);
         } break;
         case PNMN_TOK_SAME: {
           Val& vo = bd.vals[r.out];
@@ -762,7 +870,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           e.a = featp; e.b = bd.mapp(bd.vals[r.in0].unit);
           e.w = bd.param(md.head_w); e.c = bd.param(md.head_b);
           e.o = bd.mapp(vo.unit); e.idx = sym<int>(AR_IDX, static_cast<int64_t>(r.idx_slot) * 4);
-          fs.add_elt(n, e);
+          fs.add_elt(sf, e);
         } break;
         case PNMN_TOK_COMPARE: {
           Val& vo = bd.vals[r.out];
@@ -774,7 +882,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           t.in[0][0] = Builder::shadow(bd.p16(bd.vals[r.in0].unit), kP16);
           t.in[1][0] = Builder::shadow(bd.p16(bd.vals[r.in1].unit), kP16);
           t.out[0] = bd.p16(r.y_unit[0]); t.w = bd.packed(pj.pk_fwd); t.bias = bd.param(pj.b_off);
-          fs.add_conv(n, t, 0);
+          fs.add_conv(sf, t, 0);
           flops += 2ll * 196 * 128 * 256;
           for (int i = 1; i < 3; ++i) {
             const ConvW& cw = m->convs[md.convs[i]];
@@ -782,7 +890,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             u.cfg = bd.make_cfg(8, 8, 9, 1, kP16, kP16, kP16, F_BIAS | F_RELU | (i == 2 ? F_STORE : ST_INT) | HF);
             u.in[0][0] = Builder::shadow(bd.p16(r.y_unit[i - 1]), kP16); u.out[0] = bd.p16(r.y_unit[i]);
             u.w = bd.packed(cw.pk_fwd); u.bias = bd.param(cw.b_off);
-            fs.add_conv(n, u, 0);
+            fs.add_conv(sf, u, 0);
             n_conv3++;
           }
         } break;
@@ -804,7 +912,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           } else {
             r.x0_unit = bd.alloc16();
             EltTask e{}; e.op = OP_ATTEND; e.flags = EHF; e.a = featp; e.b = bd.mapp(a.unit); e.o = bd.p16(r.x0_unit);
-            fs.add_elt(n, e);
+            fs.add_elt(sf, e);
             x = bd.p16(r.x0_unit);
           }
           const bool head = r.kind != PNMN_TOK_QUERY;
@@ -826,7 +934,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
               t.w3 = bd.param(md.head_w); t.b3 = bd.param(md.head_b);
               flops += 2ll * 196 * 128;
             }
-            const int proto = fs.add_conv(n, t, fin.P == kP22.P ? 1 : 0);
+            const int proto = fs.add_conv(sf, t, fin.P == kP22.P ? 1 : 0);
             if (last && head) bd.vals[r.out].dotsig_proto = proto;
             x = t.out[0];
             n_conv3++;
@@ -838,7 +946,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
     {
       EltTask g{}; g.op = OP_GATHER; g.a = bd.p16(bd.vals[out].unit);
       g.o = sym<float>(AR_FINAL, static_cast<int64_t>(n) * 128 * 196 * 4);
-      fs.add_elt(n, g);
+      fs.add_elt(bd.vals[out].strand >= 0 ? bd.vals[out].strand : st_f, g);
     }
     if (!p.need_grad) continue;
 
@@ -869,6 +977,26 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
     };
 
     // ---------------- backward stages ----------------
+    // Backward strands mirror the forward ones: the root strand carries the output's chain; at the backward of a binary
+    // module the chain of its other input forks off.  The forked chain accumulates its share of d(feat) in a buffer of
+    // its own (two concurrent read-modify-write streams into one buffer would race); the stem's backward adds the two.
+    const int rb = bs.new_strand();
+    const int root_f = (par && bd.vals[out].strand >= 0) ? bd.vals[out].strand : st_f;
+    int sec_f = -1, sec_b = -1;          // forward / backward strand of the forked chain
+    int dfeat2_unit = -1;
+    bool dfeat2_written = false;
+    auto bstrand = [&](const OpRec& r) { return (par && r.strand == sec_f && sec_b >= 0) ? sec_b : rb; };
+    (void)root_f;
+    // (pointer, written flag) of the d(feat) accumulator a backward strand uses
+    auto dfeat_of = [&](int sb, bool*& written) -> float* {
+      if (sb == sec_b && sec_b >= 0) {
+        if (dfeat2_unit < 0) dfeat2_unit = bd.alloc16();
+        written = &dfeat2_written;
+        return bd.p16(dfeat2_unit);
+      }
+      written = &bd.vals[feat_val].gwritten;
+      return const_cast<float*>(dfeatp);
+    };
     {  // d(final module output) arrives as NCHW from the classifier
       Val& v = bd.vals[out];
       EltTask e{}; e.op = OP_SCATTER; e.scale = bd.scalep();
@@ -876,17 +1004,18 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
       e.b = fused_mask(v) ? bd.p16(v.unit) : nullptr;
       e.o = gbuf(v); e.flags = v.gwritten ? EF_ACCUM : 0;
       v.gwritten = true;
-      bs.add_elt(n, e);
+      bs.add_elt(rb, e);
     }
     for (int k = static_cast<int>(ops.size()) - 1; k >= 0; --k) {
       OpRec& r = ops[k];
       Val& vo = bd.vals[r.out];
       if (!vo.live) continue;
       const ModuleDesc& md = m->mods[r.tok];
+      const int sb = bstrand(r);
       // 128-channel outputs whose gradient was accumulated unmasked need the ReLU mask now
       if (vo.kind == VK_BUF && vo.relu_out && !fused_mask(vo)) {
         EltTask e{}; e.op = OP_RELU_MASK; e.a = bd.p16(vo.gunit); e.b = bd.p16(vo.unit); e.o = bd.p16(vo.gunit);
-        bs.add_elt(n, e);
+        bs.add_elt(sb, e);
       }
       switch (r.kind) {
         case PNMN_TOK_AND:
@@ -905,7 +1034,8 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             if (b.ch == 1) e.o2 = bd.dmapp(b.unit);
             else { e.o2 = gbuf(b); if (b.gwritten) e.flags |= EF_ACCUM2; b.gwritten = true; }
           }
-          bs.add_elt(n, e);
+          bs.add_elt(sb, e);
+          if (par && r.secondary >= 0 && sec_b < 0) { sec_f = r.secondary; sec_b = bs.fork(sb); }
         } break;
         case PNMN_TOK_SAME: {
           const Val& a = bd.vals[r.in0];
@@ -913,10 +1043,12 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
           EltTask e{}; e.op = OP_SAME_BWD; e.scale = bd.scalep();
           e.a = featp; e.b = bd.mapp(a.unit); e.c = bd.mapp(vo.unit); e.g = bd.dmapp(vo.unit);
           e.o = a.kind == VK_ONES ? nullptr : bd.dmapp(a.unit);
-          e.o2 = const_cast<float*>(dfeatp); e.flags = fv.gwritten ? EF_ACCUM : 0; fv.gwritten = true;
+          bool* dfw = nullptr;
+          e.o2 = dfeat_of(sb, dfw); e.flags = *dfw ? EF_ACCUM : 0; *dfw = true;
+          (void)fv;
           e.w = bd.param(md.head_w); e.dw = bd.grad(md.head_w); e.dw2 = bd.grad(md.head_b);
           e.idx = sym<int>(AR_IDX, static_cast<int64_t>(r.idx_slot) * 4);
-          bs.add_elt(n, e);
+          bs.add_elt(sb, e);
         } break;
         case PNMN_TOK_COMPARE: {
           // dZ of conv2 is the (masked) gradient of the output value
@@ -930,7 +1062,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             t.in[0][0] = Builder::shadow(dz, kP16); t.out[0] = bd.p16(du);
             t.aux[0] = mask_src(bd.p16(r.y_unit[i - 1]), kP16);
             t.w = bd.packed(cw.pk_bwd);
-            bs.add_conv(n, t, 0);
+            bs.add_conv(sb, t, 0);
             dz = bd.p16(du);
           }
           const ConvW& pj = m->convs[md.convs[0]];
@@ -946,8 +1078,9 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             t.in[0][0] = Builder::shadow(dz, kP16); t.out[0] = gbuf(v); t.aux[0] = fm ? bd.p16(v.unit) : nullptr;
             t.w = bd.packed(pj.pk_bwd + static_cast<int64_t>(h) * 8 * 2048);
             v.gwritten = true;
-            bs.add_conv(n, t, 0);
+            bs.add_conv(sb, t, 0);   // (the two projection halves are consecutive stages of this strand)
           }
+          if (par && r.secondary >= 0 && sec_b < 0) { sec_f = r.secondary; sec_b = bs.fork(sb); }
         } break;
         default: {  // ATTENTION / QUERY / RELATE
           const Val& a = bd.vals[r.in0];
@@ -961,7 +1094,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
             e.g = bd.dmapp(vo.unit); e.c = bd.mapp(vo.unit); e.a = bd.p16(r.y_unit[nc - 1]);
             e.w = bd.param(md.head_w); e.dw = bd.grad(md.head_w); e.dw2 = bd.grad(md.head_b);
             e.o = bd.p16(du);
-            bs.add_elt(n, e);
+            bs.add_elt(sb, e);
             dz = bd.p16(du);
           } else {
             dz = bd.p16(vo.gunit);
@@ -980,44 +1113,52 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
               t.cfg = bd.make_cfg(8, 8, 9, d, f, fprev, f, ST_INT | MASK_INT | F_HALF);
               t.out[0] = bd.pfmt(fprev, du);
               t.aux[0] = mask_src(xin_i, f);
-              bs.add_conv(n, t, f.P == kP22.P ? 1 : 0);
+              bs.add_conv(sb, t, f.P == kP22.P ? 1 : 0);
               dz = t.out[0];
             } else if (r.x0_is_feat) {
-              Val& fv = bd.vals[feat_val];
-              t.cfg = bd.make_cfg(8, 8, 9, d, f, kP16, kP16, F_STORE | (fv.gwritten ? F_ACCUM : 0));
-              t.out[0] = const_cast<float*>(dfeatp);
-              fv.gwritten = true;
-              bs.add_conv(n, t, 0);
+              bool* dfw = nullptr;
+              float* dfp = dfeat_of(sb, dfw);
+              t.cfg = bd.make_cfg(8, 8, 9, d, f, kP16, kP16, F_STORE | (*dfw ? F_ACCUM : 0));
+              t.out[0] = dfp;
+              *dfw = true;
+              bs.add_conv(sb, t, 0);
             } else if (fuse_attend) {
               // dX0 never touches memory: the epilogue turns it into dmap += <dX0, feat> and dfeat (+)= dX0 * map
-              Val& fv = bd.vals[feat_val];
-              t.cfg = bd.make_cfg(8, 8, 9, d, f, kP16, kP16, F_ATTBWD | (fv.gwritten ? F_ACCUM : 0));
-              t.out[0] = const_cast<float*>(dfeatp);
+              bool* dfw = nullptr;
+              float* dfp = dfeat_of(sb, dfw);
+              t.cfg = bd.make_cfg(8, 8, 9, d, f, kP16, kP16, F_ATTBWD | (*dfw ? F_ACCUM : 0));
+              t.out[0] = dfp;
               t.aux[0] = featp;
               t.map_out[0] = bd.mapp(a.unit);
               t.in[1][0] = bd.dmapp(a.unit);
-              fv.gwritten = true;
-              bs.add_conv(n, t, 0);
+              *dfw = true;
+              bs.add_conv(sb, t, 0);
             } else {
               const int du = bd.alloc16();
               t.cfg = bd.make_cfg(8, 8, 9, d, f, kP16, kP16, F_STORE);
               t.out[0] = bd.p16(du);
-              bs.add_conv(n, t, 0);
-              Val& fv = bd.vals[feat_val];
+              bs.add_conv(sb, t, 0);
+              bool* dfw = nullptr;
+              float* dfp = dfeat_of(sb, dfw);
               EltTask e{}; e.op = OP_ATTEND_BWD;
               e.a = bd.p16(du); e.b = featp; e.c = bd.mapp(a.unit);
-              e.o = bd.dmapp(a.unit); e.o2 = const_cast<float*>(dfeatp);
-              e.flags = fv.gwritten ? EF_ACCUM : 0; fv.gwritten = true;
-              bs.add_elt(n, e);
+              e.o = bd.dmapp(a.unit); e.o2 = dfp;
+              e.flags = *dfw ? EF_ACCUM : 0; *dfw = true;
+              bs.add_elt(sb, e);
             }
           }
         } break;
       }
     }
     // ---------------- stem backward ----------------
-    if (bd.vals[feat_val].gwritten) {
-      EltTask e{}; e.op = OP_RELU_MASK; e.a = dfeatp; e.b = featp; e.o = const_cast<float*>(dfeatp);
-      bs.add_elt(n, e);
+    if (bd.vals[feat_val].gwritten || dfeat2_written) {
+      // d(feat) = the root strand's accumulator (+ the forked chain's), masked by the stem's ReLU
+      const bool main_w = bd.vals[feat_val].gwritten;
+      EltTask e{}; e.op = OP_RELU_MASK; e.b = featp; e.o = const_cast<float*>(dfeatp);
+      e.a = main_w ? dfeatp : bd.p16(dfeat2_unit);
+      e.c = (main_w && dfeat2_written) ? bd.p16(dfeat2_unit) : nullptr;
+      if (sec_b >= 0) bs.join(rb, sec_b);
+      bs.add_elt(rb, e);
       const int dz1 = bd.alloc16();
       const ConvW& c2 = m->convs[m->stem2];
       ConvTask t{};
@@ -1025,7 +1166,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
       t.in[0][0] = Builder::shadow(dfeatp, kP16); t.out[0] = bd.p16(dz1);
       t.aux[0] = mask_src(bd.p16(y1s_unit[n]), kP16);
       t.w = bd.packed(c2.pk_bwd);
-      bs.add_conv(n, t, 0);
+      bs.add_conv(rb, t, 0);
       add_inst(m->stem2, dfeatp, bd.p16(y1s_unit[n]), kP16, 1);
       bd.conv_insts[m->stem1].push_back(WgradInst{
           Builder::shadow(bd.p16(dz1), kP16),
@@ -1114,6 +1255,7 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
   auto ms_between = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
   if (fs.dep_overflow || bs.dep_overflow) {
     g_err = "internal error: a task has more predecessors than kMaxDeps";
+    *overflow = true;
     delete plan;
     return nullptr;
   }
@@ -1209,6 +1351,14 @@ extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* progr
                  ms_between(timer.t0, t_emit), ms_between(t_emit, t_flat), ms_between(t_flat, t_blob),
                  ms_between(t_blob, std::chrono::steady_clock::now()), p.ftask.size(), p.btask.size());
   return plan;
+}
+
+extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* programs, int B, int L, int need_grad) {
+  bool overflow = false;
+  pnmn_plan* p = plan_create_impl(m, programs, B, L, need_grad, true, &overflow);
+  // joins of concurrent strands can exceed a task's dependency slots on exotic batches: compile those with one chain per sample
+  if (!p && overflow) p = plan_create_impl(m, programs, B, L, need_grad, false, &overflow);
+  return p;
 }
 
 extern "C" void pnmn_plan_destroy(pnmn_plan* p) {
@@ -1449,6 +1599,28 @@ extern "C" int pnmn_debug_set_trace(void* device_buffer, int64_t capacity_tasks)
   g_trace = static_cast<long long*>(device_buffer);
   g_trace_cap = capacity_tasks;
   return 0;
+}
+
+// task metadata of the persistent executor's lists (offline schedule analysis, scripts/sim_sched.py):
+// pass 0 = forward, 1 = backward; out receives 16 int32 per task {type, n_deps, deps[10], then for a conv task
+// n_samp, n_mt, MMAs per accumulator, cfg flags / for an elementwise task op, part, 0, 0}; returns the task count
+extern "C" int64_t pnmn_debug_plan_meta(const pnmn_plan* p, int pass, int32_t* out, int64_t cap_tasks) {
+  const std::vector<TaskMeta>& m = pass == 0 ? p->fmeta : p->bmeta;
+  const std::vector<TaskRec>& r = pass == 0 ? p->ftask : p->btask;
+  const int64_t n = static_cast<int64_t>(m.size());
+  for (int64_t i = 0; out && i < std::min(n, cap_tasks); ++i) {
+    int32_t* o = out + i * 16;
+    std::memcpy(o, &m[i], sizeof(TaskMeta));
+    if (m[i].type == TASK_CONV) {
+      const ConvTask& t = *reinterpret_cast<const ConvTask*>(r[i].b);
+      const ConvCfg& c = p->cfgs[t.cfg];
+      o[12] = t.n_samp; o[13] = t.n_mt; o[14] = c.n_kb * c.ntaps; o[15] = c.flags;
+    } else {
+      const EltTask& t = *reinterpret_cast<const EltTask*>(r[i].b);
+      o[12] = t.op; o[13] = t.part; o[14] = 0; o[15] = 0;
+    }
+  }
+  return n;
 }
 
 // accumulated host-side milliseconds: {plan_create, forward, backward, #plans}; reading clears
