@@ -204,6 +204,9 @@ def run_ours(args):
     # where the executor consumes them (its program compiler runs on the host)
     resident = [(h[0].to(dev), h[1], h[2].to(dev)) for h in host]
 
+    if world > 1 and os.environ.get("PNMN_NO_GRAD_OVERLAP") is None:
+        model.enable_gradient_overlap()  # classifier gradients are all-reduced underneath the executor's backward
+
     def step(feats, programs, answers):
         model.zero_grad(set_to_none=True)
         out = model(feats, programs, answers)
@@ -241,9 +244,9 @@ def run_ours(args):
         # thread issues the current step -- the same look-ahead an input pipeline gives the feature copy
         f, p, a = resident[i % 2]
         model.zero_grad(set_to_none=True)
-        if lookahead:
-            model.precompile(resident[(i + 1) % 2][1])
         out = model(f, p, a)
+        if lookahead:
+            model.precompile(resident[(i + 2) % 2][1])  # two steps ahead: two plans in flight on two helper threads
         loss = out["loss"].mean()
         loss.backward()
         if world > 1:
@@ -281,9 +284,9 @@ def run_ours(args):
             feed.submit(i, (host[i % 2][0], host[i % 2][2]))
         f, a = feed.get(i)
         model.zero_grad(set_to_none=True)
-        if lookahead and i + 1 < e2e_total["n"]:
-            model.precompile(host[(i + 1) % 2][1])
         out = model(f, host[i % 2][1], a)
+        if lookahead and i + 2 < e2e_total["n"]:
+            model.precompile(host[(i + 2) % 2][1])  # two steps ahead (the input pipeline knows its next two batches)
         # the next batch's copy is queued AFTER this forward's task-table upload (same H2D engine, FIFO): it then overlaps
         # with the executor instead of delaying it
         if i + 1 < e2e_total["n"]:

@@ -157,7 +157,7 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
   uint32_t pf_a = 0, pf_w = 0, pe_a = 0xfu, pe_w = 0x7u, n_conv = 0;
 
   for (;;) {
-    // ---------------- scheduler: fetch the next task, wait for its producers ----------------
+    // ---------------- scheduler: fetch the next task ----------------
     if (warp == 3) {
       int idx = 0;
       if (lane == 0) idx = atomicAdd(counter, 1);
@@ -167,24 +167,29 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
         reinterpret_cast<uint32_t*>(hdr->task)[lane] = reinterpret_cast<const uint32_t*>(tasks + static_cast<size_t>(idx) * 128)[lane];
         if (lane < static_cast<int>(sizeof(TaskMeta) / 4))
           reinterpret_cast<uint32_t*>(&hdr->meta)[lane] = reinterpret_cast<const uint32_t*>(metas + idx)[lane];
-        __syncwarp();
-        if (lane < kMaxDeps) {
-          const int d = hdr->meta.deps[lane];
-          if (d >= 0) {
-            // relaxed polls (an acquire load invalidates the SM's whole L1 on EVERY poll, which hurts the other CTA of
-            // this SM), then ONE acquire fence once every producer has published
-            while (ld_relaxed(done + d) == 0) __nanosleep(32);
-          }
-        }
-        __syncwarp();
-        asm volatile("fence.acq_rel.gpu;" ::: "memory");
-        if (kTrace && lane == 0) { trace[idx * kTraceW + 1] = gtime(); trace[idx * kTraceW + 4] = smid(); }
       }
       if (lane == 0) hdr->task_idx = idx;
     }
-    __syncthreads();  // (A) task record + dependencies are in place
+    __syncthreads();  // (A) the task record is in place; its producers may still be running
     const int idx = hdr->task_idx;
     if (idx >= n_tasks) break;
+    // Wait for the producers (warp 0, the warp that streams the activations).  Everything of a task that does NOT read
+    // a producer's output -- configuration, bias / head weights, the zero lead gaps and above all the first stages of the
+    // WEIGHT stream -- is done by the other warps meanwhile, so a task on the critical path (which always arrives here
+    // before its producer has published) starts its MMAs as soon as its activations can be fetched.
+    auto wait_deps = [&]() {
+      if (lane < kMaxDeps) {
+        const int d = hdr->meta.deps[lane];
+        if (d >= 0) {
+          // relaxed polls (an acquire load invalidates the SM's whole L1 on EVERY poll, which hurts the other CTA of
+          // this SM), then ONE acquire fence once every producer has published
+          while (ld_relaxed(done + d) == 0) __nanosleep(32);
+        }
+      }
+      __syncwarp();
+      asm volatile("fence.acq_rel.gpu;" ::: "memory");
+      if (kTrace && lane == 0) { trace[idx * kTraceW + 1] = gtime(); trace[idx * kTraceW + 4] = smid(); }
+    };
 
     if (hdr->meta.type == TASK_CONV) {
       // Everything the roles need is copied into registers up front: the PTX wrappers carry "memory"
@@ -216,65 +221,74 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
       else if (4u * a_stage + 2u * kExWStage <= ring_avail) n_ast = 4;
       else if (3u * a_stage + 2u * kExWStage <= ring_avail) n_ast = 3;
       uint8_t* a_ring = w_ring + n_wst * kExWStage;
-      // zero the lead gaps of this plane format; stage bias / 1x1 head weights
-      for (int st = 0; st < n_ast; ++st)
-        for (int s = 0; s < n_samp; ++s) {
-          float4* g = reinterpret_cast<float4*>(a_ring + st * a_stage + s * samp_bytes);
-          for (int i = tid; i < lead; i += kExThreads) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      // ---------------- activation producer (warp 0, lane 0): k-blocks [a_kb, upto) ----------------
+      int a_kb = 0, a_sa = 0;
+      auto produce_a = [&](int upto) {
+        const uint8_t* in00 = static_cast<const uint8_t*>(tp->in[0][0]);
+        const uint8_t* in01 = static_cast<const uint8_t*>(tp->in[0][1]);
+        const uint8_t* in10 = static_cast<const uint8_t*>(tp->in[1][0]);
+        const uint8_t* in11 = static_cast<const uint8_t*>(tp->in[1][1]);
+        const uint32_t a_base = smem_u32(a_ring) + lead * 16u;
+        const uint32_t kb_bytes = 2u * plane_bytes;
+        fence_proxy_async_all();
+        for (; a_kb < upto; ++a_kb) {
+          mbar_wait(smem_u32(&hdr->empty_a[a_sa]), (pe_a >> a_sa) & 1u);
+          pe_a ^= 1u << a_sa;
+          const uint32_t bar = smem_u32(&hdr->full_a[a_sa]);
+          mbar_arrive_expect_tx(bar, n_samp * kb_bytes);
+          const bool second = a_kb >= kb_per_in;
+          const size_t off = static_cast<size_t>(second ? a_kb - kb_per_in : a_kb) * kb_bytes;
+          bulk_g2s(a_base + a_sa * a_stage, (second ? in10 : in00) + off, kb_bytes, bar);
+          if (n_samp > 1) bulk_g2s(a_base + a_sa * a_stage + samp_bytes, (second ? in11 : in01) + off, kb_bytes, bar);
+          a_sa = a_sa + 1 == n_ast ? 0 : a_sa + 1;
         }
-      if (tid < 128) {
-        hdr->bias[tid] = (flags & F_BIAS) ? __ldg(tp->bias + tid) : 0.f;
-        hdr->w3[tid] = (flags & F_DOTSIG) ? __ldg(tp->w3 + tid) : 0.f;
+      };
+      // ---------------- weight producers (lane 0 of warps 1 and 3): stages [w_it, upto) ----------------
+      // TWO issuing threads take alternate stages: one thread can only start a bulk copy every ~500 cycles whatever its
+      // size (scripts/microbench/bulk_stream.cu).  Both walk the whole stage sequence so that their phase bits follow
+      // every use of every stage.
+      int w_it = 0, w_sw = 0;
+      auto produce_w = [&](int upto) {
+        const uint8_t* wsrc = static_cast<const uint8_t*>(tp->w);
+        const uint32_t bytes = static_cast<uint32_t>(tps) * kExWTile;
+        const uint32_t w_base = smem_u32(w_ring);
+        const int mine = warp == 3 ? 1 : 0;
+        fence_proxy_async_all();
+        for (; w_it < upto; ++w_it) {
+          if ((w_it & 1) == mine) {
+            mbar_wait(smem_u32(&hdr->empty_w[w_sw]), (pe_w >> w_sw) & 1u);
+            const uint32_t bar = smem_u32(&hdr->full_w[w_sw]);
+            mbar_arrive_expect_tx(bar, bytes);
+            bulk_g2s(w_base + w_sw * kExWStage, wsrc + static_cast<size_t>(w_it) * bytes, bytes, bar);
+          }
+          pe_w ^= 1u << w_sw;
+          w_sw = w_sw + 1 == n_wst ? 0 : w_sw + 1;
+        }
+      };
+      // ---- before the producers of this task have published: the first ring-full of weights, the zero lead gaps of
+      // this plane format, bias / 1x1 head weights; warp 0 polls the dependency flags and then starts the activations
+      if (warp == 0) {
+        wait_deps();
+        if (lane == 0) produce_a(n_ast < n_kb ? n_ast : n_kb);
+      } else if (warp == 1 || warp == 3) {
+        if (lane == 0) produce_w(n_wst < n_ws ? n_wst : n_ws);
+      } else if (warp >= 4) {
+        const int t = tid - 128;
+        for (int st = 0; st < n_ast; ++st)
+          for (int s = 0; s < n_samp; ++s) {
+            float4* g = reinterpret_cast<float4*>(a_ring + st * a_stage + s * samp_bytes);
+            for (int i = t; i < lead; i += 128) g[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        hdr->bias[t] = (flags & F_BIAS) ? __ldg(tp->bias + t) : 0.f;
+        hdr->w3[t] = (flags & F_DOTSIG) ? __ldg(tp->w3 + t) : 0.f;
       }
       fence_proxy_async();
-      __syncthreads();  // (B)
+      __syncthreads();  // (B) producers have published (warp 0's acquire fence is cumulative over this barrier)
 
       if (warp == 0) {
-        // ---------------- activation producer ----------------
-        if (lane == 0) {
-          const uint8_t* in00 = static_cast<const uint8_t*>(tp->in[0][0]);
-          const uint8_t* in01 = static_cast<const uint8_t*>(tp->in[0][1]);
-          const uint8_t* in10 = static_cast<const uint8_t*>(tp->in[1][0]);
-          const uint8_t* in11 = static_cast<const uint8_t*>(tp->in[1][1]);
-          const uint32_t a_base = smem_u32(a_ring) + lead * 16u;
-          const uint32_t kb_bytes = 2u * plane_bytes;
-          fence_proxy_async_all();
-          int sa = 0;
-          for (int kb = 0; kb < n_kb; ++kb) {
-            mbar_wait(smem_u32(&hdr->empty_a[sa]), (pe_a >> sa) & 1u);
-            pe_a ^= 1u << sa;
-            const uint32_t bar = smem_u32(&hdr->full_a[sa]);
-            mbar_arrive_expect_tx(bar, n_samp * kb_bytes);
-            const bool second = kb >= kb_per_in;
-            const size_t off = static_cast<size_t>(second ? kb - kb_per_in : kb) * kb_bytes;
-            bulk_g2s(a_base + sa * a_stage, (second ? in10 : in00) + off, kb_bytes, bar);
-            if (n_samp > 1) bulk_g2s(a_base + sa * a_stage + samp_bytes, (second ? in11 : in01) + off, kb_bytes, bar);
-            sa = sa + 1 == n_ast ? 0 : sa + 1;
-          }
-        }
+        if (lane == 0) produce_a(n_kb);
       } else if (warp == 1 || warp == 3) {
-        // ---------------- weight producers ----------------
-        // TWO issuing threads (warp 1 and the otherwise idle scheduler warp 3) take alternate stages: one thread can only
-        // start a bulk copy every ~500 cycles whatever its size (scripts/microbench/bulk_stream.cu).  Both walk the whole
-        // stage sequence so that their phase bits follow every use of every stage.
-        if (lane == 0) {
-          const uint8_t* wsrc = static_cast<const uint8_t*>(tp->w);
-          const uint32_t bytes = static_cast<uint32_t>(tps) * kExWTile;
-          const uint32_t w_base = smem_u32(w_ring);
-          const int mine = warp == 3 ? 1 : 0;
-          fence_proxy_async_all();
-          int sw = 0;
-          for (int it = 0; it < n_ws; ++it) {
-            if ((it & 1) == mine) {
-              mbar_wait(smem_u32(&hdr->empty_w[sw]), (pe_w >> sw) & 1u);
-              const uint32_t bar = smem_u32(&hdr->full_w[sw]);
-              mbar_arrive_expect_tx(bar, bytes);
-              bulk_g2s(w_base + sw * kExWStage, wsrc + static_cast<size_t>(it) * bytes, bytes, bar);
-            }
-            pe_w ^= 1u << sw;
-            sw = sw + 1 == n_wst ? 0 : sw + 1;
-          }
-        }
+        if (lane == 0) produce_w(n_ws);
       } else if (warp == 2) {
         // ---------------- MMA issuer ----------------
         // The whole warp runs the loop (uniform control flow and operands); one elected lane issues.
@@ -600,6 +614,8 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
       ++n_conv;
     } else {
       // CUDA-core task: all 256 threads of the CTA (the tensor-core roles have nothing to do meanwhile)
+      if (warp == 0) wait_deps();
+      __syncthreads();  // (B)
       const EltTask& t = *reinterpret_cast<const EltTask*>(hdr->task);
 #ifndef PNMN_NO_ELT  // (timing experiment: how much of the conv path's time is instruction-cache pressure from this code?)
       elt_task_body(t, tid, hdr->elt);

@@ -457,6 +457,15 @@ struct Sched {
       ++cur;
     }
     if (!cp_order || out.empty() || dep_overflow) return;
+    static const bool timing = std::getenv("PNMN_PLAN_TIMING") != nullptr;
+    const auto t_sort0 = std::chrono::steady_clock::now();
+    struct SortTimer {
+      bool on; std::chrono::steady_clock::time_point t0; size_t n;
+      ~SortTimer() {
+        if (on) std::fprintf(stderr, "plan:   critical-path order of %zu tasks: %.2f ms\n", n,
+                             std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+      }
+    } sort_timer{timing, t_sort0, out.size()};
     const int n = static_cast<int>(out.size());
     // remaining chain time of every task (its own duration + the longest chain of consumers behind it)
     std::vector<float> rem(dur);
@@ -465,26 +474,28 @@ struct Sched {
         const int j = meta[i].deps[k];
         rem[j] = std::max(rem[j], dur[j] + 1.f + rem[i]);
       }
-    // sort keys: remaining time (descending) in the high word, list position in the low word (stable, and cheap to sort)
-    std::vector<uint64_t> keys(n);
+    // Stable counting sort by remaining time, longest first, quantised to 1/8 us.  The list is topologically ordered and
+    // the sort is stable, so a producer (whose remaining time is at least its consumer's) stays in front on ties.
+    float rmax = 0.f;
+    for (int i = 0; i < n; ++i) rmax = std::max(rmax, rem[i]);
+    const int n_bins = std::min(1 << 16, static_cast<int>(rmax * 8.f) + 2);
+    std::vector<int> bin(n), start(n_bins + 1, 0), newpos(n);
     for (int i = 0; i < n; ++i) {
-      const uint32_t r = static_cast<uint32_t>(std::min(rem[i], 4.0e6f) * 1000.f);  // ns resolution, << 2^32
-      keys[i] = static_cast<uint64_t>(0xFFFFFFFFu - r) << 32 | static_cast<uint32_t>(i);
+      bin[i] = n_bins - 1 - std::min(n_bins - 1, static_cast<int>(rem[i] * 8.f));
+      ++start[bin[i] + 1];
     }
-    std::sort(keys.begin(), keys.end());
-    std::vector<int> newpos(n);
-    for (int i = 0; i < n; ++i) newpos[static_cast<uint32_t>(keys[i])] = i;
-    // quantisation of the key can tie a producer with its consumer only if durations were < 1 ns: check, fall back if so
+    for (int k = 0; k < n_bins; ++k) start[k + 1] += start[k];
+    for (int i = 0; i < n; ++i) newpos[i] = start[bin[i]]++;
     for (int i = 0; i < n; ++i)
       for (int k = 0; k < meta[i].n_deps; ++k)
-        if (newpos[meta[i].deps[k]] >= newpos[i]) return;
+        if (newpos[meta[i].deps[k]] >= newpos[i]) return;  // cannot happen (see above); keep the step-aligned list if it does
     std::vector<TaskRec> out2(n);
     std::vector<TaskMeta> meta2(n);
     for (int i = 0; i < n; ++i) {
-      const int o = static_cast<int>(static_cast<uint32_t>(keys[i]));
-      out2[i] = out[o];
-      meta2[i] = meta[o];
-      for (int k = 0; k < meta2[i].n_deps; ++k) meta2[i].deps[k] = newpos[meta2[i].deps[k]];
+      const int d = newpos[i];
+      out2[d] = out[i];
+      meta2[d] = meta[i];
+      for (int k = 0; k < meta2[d].n_deps; ++k) meta2[d].deps[k] = newpos[meta2[d].deps[k]];
     }
     out.swap(out2);
     meta.swap(meta2);

@@ -43,6 +43,59 @@ def gradient_buckets(models: Iterable[torch.nn.Module]) -> List[torch.Tensor]:
     return buckets
 
 
+class GradientOverlap:
+    """Starts the all-reduce of a parameter's gradient the moment autograd has accumulated it, instead of after the whole
+    backward pass.  In the NMN step the classifier's gradients come first (classifier.4.weight alone is 205 MB of the
+    257 MB the step reduces) and the module executor's backward + weight-gradient kernels (~1.5 ms) follow: the large
+    collective then travels over NVLink underneath them.  ``finish`` waits for the early collectives and reduces whatever
+    is left (the flat buffers the CUDA backward writes, which autograd never sees).  Every rank runs the same autograd
+    graph, so the hooks fire -- and the collectives are issued -- in the same order everywhere."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
+                 min_numel: int = 1, weight: float = 1.0):
+        self.group = group
+        self.weight = weight
+        self._pending: List[Tuple[torch.Tensor, "dist.Work"]] = []
+        self._hooks = []
+        for p in params:
+            if p.requires_grad and p.numel() >= min_numel:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        g = p.grad
+        if g is None or not dist.is_initialized():
+            return
+        if self.weight != 1.0:
+            g.mul_(self.weight)
+        self._pending.append((g, dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True)))
+
+    def finish(self, models: Iterable[torch.nn.Module]) -> int:
+        """Average every gradient of ``models``: wait for the collectives the hooks started, all-reduce the rest.
+        Returns the number of collectives this step used."""
+        world = dist.get_world_size(self.group)
+        early = {g.data_ptr() for g, _ in self._pending}
+        rest = [b for b in gradient_buckets(models) if b.data_ptr() not in early]
+        handles = []
+        for b in rest:
+            if self.weight != 1.0:
+                b.mul_(self.weight)
+            handles.append(dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for g, h in self._pending:
+            h.wait()
+            g.div_(world)
+        for b, h in zip(rest, handles):
+            h.wait()
+            b.div_(world)
+        n = len(self._pending) + len(rest)
+        self._pending = []
+        return n
+
+    def remove(self) -> None:
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 def allreduce_gradients(models: Iterable[torch.nn.Module], group: Optional[dist.ProcessGroup] = None,
                         weight: float = 1.0) -> int:
     """Average the gradients of ``models`` over the process group; returns the number of collectives issued.

@@ -348,6 +348,7 @@ class NeuralModuleNetwork(nn.Module):
         self._packed: Optional[torch.Tensor] = None
         self.last_plan_stats: Optional[List[int]] = None
         self._gflat_box: Dict[str, torch.Tensor] = {}
+        self._grad_overlap = None
         self._precompiled: list = []  # pending (programs, need_grad, future of a plan) entries, see precompile()
         # classifier GEMMs (plain library GEMMs, nmn.py:75-83): "split" (default) = every fp32 operand split into two bf16
         # halves (pnmn_split3_bf16, one pass), one cuBLAS tensor-core GEMM over the 3x contraction with fp32 accumulation
@@ -560,8 +561,8 @@ class NeuralModuleNetwork(nn.Module):
     def precompile(self, programs: torch.Tensor, need_grad: Optional[bool] = None) -> None:
         """Optional look-ahead for input pipelines: start compiling ``programs`` (host tensor, (B, L) token ids) into an
         executor plan on a helper thread.  A later ``forward`` whose programs have the same contents picks the plan up
-        instead of compiling inline (2-4 ms of host time per 256 programs).  At most two plans wait at a time (the oldest
-        is dropped), so a pipeline can submit batch i+1 before it runs batch i.  The reference has no counterpart -- its
+        instead of compiling inline (2-4 ms of host time per 256 programs).  At most three plans wait at a time (the oldest
+        is dropped), so a pipeline can submit batches i+1 and i+2 before it runs batch i.  The reference has no counterpart -- its
         interpreter walks the programs inside forward (nmn.py:191-238) -- and results are identical with or without it."""
         self._ensure_flat()
         if programs.device.type != "cpu":
@@ -570,7 +571,7 @@ class NeuralModuleNetwork(nn.Module):
         if need_grad is None:
             need_grad = self.training and any(p.requires_grad for p in self._exec_params)
         device = self._flat.device if self._flat is not None and self._flat.is_cuda else None
-        while len(self._precompiled) >= 2:
+        while len(self._precompiled) >= 3:
             self._destroy_pending(self._precompiled.pop(0))
         self._precompiled.append((host, bool(need_grad), _compile_pool().submit(self._compile, host, bool(need_grad), device)))
 
@@ -618,7 +619,20 @@ class NeuralModuleNetwork(nn.Module):
         trainers/_trainer.py:98-100, which mis-executes the NMN)"""
         from .dist import allreduce_gradients
 
-        allreduce_gradients([self], group=group)
+        if self._grad_overlap is not None:
+            self._grad_overlap.finish([self])
+        else:
+            allreduce_gradients([self], group=group)
+
+    def enable_gradient_overlap(self, group=None) -> None:
+        """Start the all-reduce of each classifier gradient as soon as autograd has produced it (they are 206 of the
+        257 MB a step reduces and come first in the backward pass), underneath the module executor's backward;
+        ``allreduce_gradients`` then only waits for them and reduces the executor's flat gradient buffer."""
+        from .dist import GradientOverlap
+
+        if self._grad_overlap is not None:
+            self._grad_overlap.remove()
+        self._grad_overlap = GradientOverlap(self.classifier.parameters(), group=group)
 
     def get_metrics(self, reset: bool = True) -> Dict[str, float]:
         """``{"answer_accuracy", "average_invalid"}`` (nmn.py:277-296)."""
@@ -636,11 +650,12 @@ _COMPILE_POOL = None
 
 
 def _compile_pool():
-    """One helper thread for NeuralModuleNetwork.precompile (ctypes releases the GIL around the C++ compiler)."""
+    """Two helper threads for NeuralModuleNetwork.precompile (ctypes releases the GIL around the C++ compiler): a pipeline
+    that knows its batches two steps ahead keeps two plans in flight, so a compile has two step times to finish."""
     global _COMPILE_POOL
     if _COMPILE_POOL is None:
         from concurrent.futures import ThreadPoolExecutor
-        _COMPILE_POOL = ThreadPoolExecutor(max_workers=1, thread_name_prefix="pnmn-plan")
+        _COMPILE_POOL = ThreadPoolExecutor(max_workers=2, thread_name_prefix="pnmn-plan")
     return _COMPILE_POOL
 
 

@@ -7,7 +7,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from probnmn_clevr_b200.dist import allreduce_gradients, gradient_buckets, shard_rows
+from probnmn_clevr_b200.dist import GradientOverlap, allreduce_gradients, gradient_buckets, shard_rows
 
 
 def test_shard_rows_cover_the_batch():
@@ -65,6 +65,31 @@ def _worker(rank, world, path, rows):
         allreduce_gradients([w], weight=(e - b) / rows * world)
         assert torch.allclose(w.weight.grad, ref.weight.grad, atol=1e-6)
         assert torch.allclose(w.bias.grad, ref.bias.grad, atol=1e-6)
+
+        # overlapped variant: hooked parameters start their all-reduce inside backward, finish() reduces the rest (here:
+        # the flat-buffer model) -- same averages as the plain path
+        torch.manual_seed(2 + rank)
+        net = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 1))
+        torch.manual_seed(5)
+        with torch.no_grad():
+            for p in net.parameters():
+                p.copy_(torch.randn_like(p))
+        twin = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 1))
+        twin.load_state_dict(net.state_dict())
+        xs = torch.randn(6, 4)
+        overlap = GradientOverlap(net.parameters())
+        for _ in range(2):  # two steps: the pending list is cleared by finish()
+            net.zero_grad(set_to_none=True); twin.zero_grad(set_to_none=True)
+            net(xs).pow(2).mean().backward()
+            twin(xs).pow(2).mean().backward()
+            model.fake_backward(rank + 1)
+            used = overlap.finish([net, model])
+            assert used == 4 + 2, used      # 4 hooked tensors + the flat bucket + the plain tensor
+            allreduce_gradients([twin])
+            for p, q in zip(net.parameters(), twin.parameters()):
+                assert torch.allclose(p.grad, q.grad, atol=1e-7)
+            assert torch.allclose(model.a.grad, torch.full((5, 3), want))
+        overlap.remove()
     finally:
         dist.destroy_process_group()
 
