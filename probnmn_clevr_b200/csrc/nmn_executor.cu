@@ -228,6 +228,8 @@ struct TaskRec { uint8_t b[128]; };
 struct Sched {
   std::vector<int> step, last;                // per strand
   std::vector<int> fork_parent, fork_step;    // per strand: parent (-1 = root) and the step of its first stage
+  std::vector<int> strand_sample;             // per strand: the sample it belongs to
+  std::vector<uint8_t> critical;              // per strand: its sample has one of the longest chains (mark_critical)
   struct Join { int step, primary, secondary; };
   std::vector<Join> joins;
   std::vector<std::array<std::vector<int>, 3>> buckets;  // indices into elts / protos
@@ -244,15 +246,32 @@ struct Sched {
     protos.reserve(static_cast<size_t>(B) * 48);
     buckets.reserve(128);
   }
-  int new_strand() {
+  int new_strand(int sample) {
     step.push_back(0); last.push_back(-1); fork_parent.push_back(-1); fork_step.push_back(0);
+    strand_sample.push_back(sample);
     return static_cast<int>(step.size()) - 1;
+  }
+  // Samples whose chain is long enough to bound the pass: their convolutions are never paired with another sample and
+  // always split over the M tiles (two CTAs, ~11 us per stage instead of ~20 us for a paired task), everything else is
+  // grouped for throughput.  A sample is critical when its last stage lies beyond `frac` of the batch's deepest one.
+  void mark_critical(int n_samples, float frac) {
+    critical.assign(step.size(), 0);
+    if (!unified || frac >= 1.f) return;
+    std::vector<int> end(n_samples, 0);
+    int deepest = 0;
+    for (size_t s = 0; s < step.size(); ++s) {
+      const int e = last[s] >= 0 ? step[s] + 1 : 0;
+      end[strand_sample[s]] = std::max(end[strand_sample[s]], e);
+      deepest = std::max(deepest, e);
+    }
+    const int thr = std::max(8, static_cast<int>(frac * static_cast<float>(deepest)));
+    for (size_t s = 0; s < step.size(); ++s) critical[s] = end[strand_sample[s]] >= thr;
   }
   int next_step(int s) const { return last[s] >= 0 ? step[s] + 1 : step[s]; }
   // a strand whose first stage waits for the parent's CURRENT stage (later stages of the parent do not matter to it)
   int fork(int parent) {
     const int start = next_step(parent);
-    const int s = new_strand();
+    const int s = new_strand(strand_sample[parent]);
     step[s] = start; fork_parent[s] = parent; fork_step[s] = start;
     return s;
   }
@@ -318,13 +337,16 @@ struct Sched {
     const int cap = (kind == LK_CONV0 && (U > pair_min || pair_always)) ? NSMAX : 1;
     static const bool no_split = std::getenv("PNMN_NOSPLIT") != nullptr;  // diagnostics
     const int split = (!no_split && U * nmt <= split_max) ? nmt : 1;
+    const bool have_crit = !critical.empty();
     size_t i = 0;
     while (i < v.size()) {
       ConvTask t = protos[v[i]].t;
       int samples[NSMAX] = {protos[v[i]].sample, -1};
       t.n_samp = 1;
+      const bool crit = have_crit && critical[samples[0]];
       size_t j = i + 1;
-      while (j < v.size() && t.n_samp < cap && protos[v[j]].t.cfg == t.cfg && protos[v[j]].t.w == t.w) {
+      while (j < v.size() && !crit && t.n_samp < cap && protos[v[j]].t.cfg == t.cfg && protos[v[j]].t.w == t.w &&
+             !(have_crit && critical[protos[v[j]].sample])) {
         const ConvTask& o = protos[v[j]].t;
         const int k = t.n_samp++;
         samples[k] = protos[v[j]].sample;
@@ -333,7 +355,7 @@ struct Sched {
         ++j;
       }
       // a task owns at most TWO accumulators (two executor CTAs share an SM's 512 TMEM columns, exec.cu)
-      if (split > 1 || t.n_samp > 1) {
+      if (split > 1 || t.n_samp > 1 || crit) {
         for (int m = 0; m < nmt; ++m) { t.mt0 = m; t.n_mt = 1; emit(t, samples, t.n_samp); }
       } else {
         for (int m = 0; m < nmt; m += 2) { t.mt0 = m; t.n_mt = std::min(2, nmt - m); emit(t, samples, t.n_samp); }
@@ -626,9 +648,9 @@ PinnedBlob* pin_acquire(size_t bytes) {
   PinnedBlob* best = nullptr;
   // prefer a buffer whose last upload has already been consumed by the GPU (the host may run ahead of the device)
   for (int pass = 0; pass < 2 && !best; ++pass) {
-    // everything is in flight: grow the pool up to five buffers (look-ahead compile + the host running two steps ahead of the
+    // everything is in flight: grow the pool up to eight buffers (two look-ahead compiles + the host running two steps ahead of the
     // device; cudaHostAlloc costs milliseconds and synchronises, so the pool must not keep growing), else wait for the oldest
-    if (pass == 1 && g_pin_total < 5) break;
+    if (pass == 1 && g_pin_total < 8) break;
     for (size_t i = 0; i < g_pin_free.size(); ++i) {
       PinnedBlob* c = g_pin_free[i];
       if (c->cap < bytes) continue;
@@ -802,7 +824,7 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
       }
     }
     if (ok && bd.vals[out].ch != 128) ok = false;  // nmn.py:231-232
-    const int st_f = fs.new_strand();  // the sample's stem strand
+    const int st_f = fs.new_strand(n);  // the sample's stem strand
     if (!ok) {
       bd.vals.resize(val_mark);
       EltTask g{}; g.op = OP_GATHER; g.a = nullptr;
@@ -991,7 +1013,7 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
     // Backward strands mirror the forward ones: the root strand carries the output's chain; at the backward of a binary
     // module the chain of its other input forks off.  The forked chain accumulates its share of d(feat) in a buffer of
     // its own (two concurrent read-modify-write streams into one buffer would race); the stem's backward adds the two.
-    const int rb = bs.new_strand();
+    const int rb = bs.new_strand(n);
     const int root_f = (par && bd.vals[out].strand >= 0) ? bd.vals[out].strand : st_f;
     int sec_f = -1, sec_b = -1;          // forward / backward strand of the forked chain
     int dfeat2_unit = -1;
@@ -1190,6 +1212,14 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
   // the forward list, the backward list and the weight-gradient tasks are independent: the backward list (the longest)
   // is flattened on a helper thread while this thread does the other two
   std::thread bwd_flatten;
+  {
+    // thresholds from replaying the recorded trace over the bench workload (scripts/sim_sched.py) and confirmed on the GPU;
+    // the backward pass has ~1.8x the tasks of the forward pass, so splitting costs it more slot time
+    static const float crit_fwd = std::getenv("PNMN_CRIT") ? static_cast<float>(std::atof(std::getenv("PNMN_CRIT"))) : 0.7f;
+    static const float crit_bwd = std::getenv("PNMN_CRIT_BWD") ? static_cast<float>(std::atof(std::getenv("PNMN_CRIT_BWD"))) : 0.8f;
+    fs.mark_critical(B, crit_fwd);
+    if (p.need_grad) bs.mark_critical(B, crit_bwd);
+  }
   if (p.persistent) {
     if (p.need_grad) bwd_flatten = std::thread([&] { bs.flatten_persistent(p.btask, p.bmeta, p.cfgs); });
     fs.flatten_persistent(p.ftask, p.fmeta, p.cfgs);
