@@ -120,6 +120,11 @@ int pnmn_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, in
  * writes gy [B][14*14][C] from g [B][C*7*7].  C must be a multiple of 64. */
 int pnmn_relu_pool_fwd(const float* y, float* pooled, void* code, int64_t B, int64_t C, void* stream);
 int pnmn_relu_pool_bwd(const float* g, const void* code, float* gy, int64_t B, int64_t C, void* stream);
+/* same routing, output as the bf16 (hi, lo) pair g2[2][B*196][C] (hi = bf16(gy), lo = bf16(gy - hi)) that the
+ * split-precision classifier GEMMs consume; the fp32 gradient is never materialised */
+int pnmn_relu_pool_bwd_split(const float* g, const void* code, void* g2, int64_t B, int64_t C, void* stream);
+/* dst[2][n] bf16 = (hi, lo) split of src[n] fp32, n % 4 == 0 */
+int pnmn_split2_bf16(const float* src, void* dst, int64_t n, void* stream);
 
 /* kernels launched by the library so far (reset != 0 clears the counter); bench.py reports it as "gpu_launches" */
 long long pnmn_launch_count(int reset);

@@ -163,6 +163,67 @@ __global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const float* __restr
     gb[static_cast<size_t>(p) * C] = (cd == (pos | 4)) ? tile[cw * 49 + w] : 0.f;
   }
 }
+// Same routing, but the gradient leaves as the bf16 (hi, lo) pair the classifier's split-precision GEMMs consume:
+// g2[0][B*196][C] = bf16(gy), g2[1][B*196][C] = bf16(gy - hi).  The fp32 tensor (205 MB at batch 256) is never written and
+// the two split passes that used to read it back (dgrad and wgrad layouts, 0.5 GB each) disappear.
+__global__ void __launch_bounds__(256) relu_pool_bwd_split_kernel(const float* __restrict__ g, const uint8_t* __restrict__ code,
+                                                                  __nv_bfloat16* __restrict__ g2, int C, size_t plane) {
+  __shared__ float tile[kPoolCB * 49];
+  __shared__ uint8_t ctile[kPoolCB * 49];
+  const int b = blockIdx.y, c0 = blockIdx.x * kPoolCB;
+  const size_t o = static_cast<size_t>(b) * C * 49 + static_cast<size_t>(c0) * 49;
+  for (int i = threadIdx.x; i < kPoolCB * 49; i += 256) { tile[i] = g[o + i]; ctile[i] = code[o + i]; }
+  __syncthreads();
+  // thread = (channel pair cp = tid % 32, pixel phase pq = tid / 32): 4-byte bf16x2 stores, 128 contiguous bytes per warp
+  const int cp = threadIdx.x % (kPoolCB / 2), pq = threadIdx.x / (kPoolCB / 2);
+  __nv_bfloat16* gb = g2 + (static_cast<size_t>(b) * 196) * C + c0 + 2 * cp;
+  for (int p = pq; p < 196; p += 256 / (kPoolCB / 2)) {
+    const int yy = p / 14, xx = p - yy * 14;
+    const int w = (yy >> 1) * 7 + (xx >> 1), pos = (yy & 1) * 2 + (xx & 1);
+    float v[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int cd = ctile[(2 * cp + e) * 49 + w];
+      v[e] = (cd == (pos | 4)) ? tile[(2 * cp + e) * 49 + w] : 0.f;
+    }
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
+    const __nv_bfloat162 hi = __halves2bfloat162(h0, h1);
+    const __nv_bfloat162 lo = __halves2bfloat162(__float2bfloat16_rn(v[0] - __bfloat162float(h0)),
+                                                 __float2bfloat16_rn(v[1] - __bfloat162float(h1)));
+    *reinterpret_cast<__nv_bfloat162*>(gb + static_cast<size_t>(p) * C) = hi;
+    *reinterpret_cast<__nv_bfloat162*>(gb + plane + static_cast<size_t>(p) * C) = lo;
+  }
+}
+
+// x ~= hi + lo in bf16: dst[0][n] = hi, dst[1][n] = lo (one pass; the operands of the classifier's shared-split GEMMs)
+__global__ void split2_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
+  const int64_t n4 = n / 4;
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const float x[4] = {v.x, v.y, v.z, v.w};
+    __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      hi[e] = __float2bfloat16_rn(x[e]);
+      lo[e] = __float2bfloat16_rn(x[e] - __bfloat162float(hi[e]));
+    }
+    *reinterpret_cast<uint2*>(dst + i * 4) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(dst + n + i * 4) = *reinterpret_cast<const uint2*>(lo);
+  }
+}
+cudaError_t launch_split2_bf16(const float* src, void* dst, int64_t n, cudaStream_t st) {
+  if (n == 0) return cudaSuccess;
+  const int64_t n4 = n / 4;
+  const int blocks = static_cast<int>(n4 / 256 + 1 < 148 * 16 ? n4 / 256 + 1 : 148 * 16);
+  split2_bf16_kernel<<<blocks, 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), n);
+  return cudaGetLastError();
+}
+cudaError_t launch_relu_pool_bwd_split(const float* g, const uint8_t* code, void* g2, int B, int C, cudaStream_t st) {
+  if (B <= 0) return cudaSuccess;
+  relu_pool_bwd_split_kernel<<<dim3(C / kPoolCB, B), 256, 0, st>>>(g, code, static_cast<__nv_bfloat16*>(g2), C,
+                                                                   static_cast<size_t>(B) * 196 * C);
+  return cudaGetLastError();
+}
 cudaError_t launch_relu_pool_fwd(const float* y, float* pooled, uint8_t* code, int B, int C, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
   relu_pool_fwd_kernel<<<dim3(C / kPoolCB, B), 256, 0, st>>>(y, pooled, code, C);

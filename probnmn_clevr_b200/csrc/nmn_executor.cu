@@ -1711,6 +1711,21 @@ extern "C" int pnmn_relu_pool_bwd(const float* g, const void* code, float* gy, i
   return 0;
 }
 
+// the same backward with the gradient written as the bf16 (hi, lo) pair [2][B*196][C] of the split-precision GEMMs
+extern "C" int pnmn_relu_pool_bwd_split(const float* g, const void* code, void* g2, int64_t B, int64_t C, void* stream) {
+  if (!g || !g2 || !code || B < 0 || C <= 0 || C % 64 != 0) return fail("pnmn_relu_pool_bwd_split: bad arguments (C must be a multiple of 64)");
+  CUDA_OK(launch_relu_pool_bwd_split(g, static_cast<const uint8_t*>(code), g2, static_cast<int>(B), static_cast<int>(C), static_cast<cudaStream_t>(stream)));
+  pnmn::count_launches(1);
+  return 0;
+}
+// bf16 (hi, lo) pair [2][n] of an fp32 array (n a multiple of 4)
+extern "C" int pnmn_split2_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (!src || !dst || n < 0 || n % 4 != 0) return fail("pnmn_split2_bf16: bad arguments (n must be a multiple of 4)");
+  CUDA_OK(launch_split2_bf16(src, dst, n, static_cast<cudaStream_t>(stream)));
+  pnmn::count_launches(1);
+  return 0;
+}
+
 // ---- bring-up entry points -----------------------------------------------------------------------
 namespace {
 template <class T>

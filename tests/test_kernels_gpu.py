@@ -280,3 +280,64 @@ def test_relu_pool_flatten(B, C):
     out.backward(go)
     ref.backward(go)
     assert torch.equal(y1.grad, y2.grad)
+
+
+@pytest.mark.parametrize("B,C", [(3, 64), (5, 1024)])
+def test_relu_pool_bwd_split_and_split2(B, C):
+    """pnmn_relu_pool_bwd_split writes the routed gradient as the bf16 (hi, lo) pair of the split-precision GEMMs:
+    hi is bit-exactly bf16(gy) of the fp32 kernel, lo bit-exactly bf16(gy - hi); pnmn_split2_bf16 does the same for a
+    plain array."""
+    import ctypes
+    from probnmn_clevr_b200 import _lib as L
+    from probnmn_clevr_b200.nmn import _ReluPoolFlatten, _split2
+    g = torch.Generator(device="cuda").manual_seed(9)
+    y = torch.randn((B * 196, C), generator=g, device="cuda")
+    y[::5] = -y[::5].abs()
+    y1 = y.clone().requires_grad_(True)
+    out = _ReluPoolFlatten.apply(y1, B)
+    go = torch.randn(out.shape, generator=g, device="cuda")
+    out.backward(go)
+    gy = y1.grad
+    # the byte codes of the forward kernel
+    pooled = torch.empty_like(out); code = torch.empty(out.shape, dtype=torch.uint8, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check(L.lib().pnmn_relu_pool_fwd(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(pooled.data_ptr()),
+                                       ctypes.c_void_p(code.data_ptr()), B, C, st), "fwd")
+    g2 = torch.full((2, B * 196, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.check(L.lib().pnmn_relu_pool_bwd_split(ctypes.c_void_p(go.data_ptr()), ctypes.c_void_p(code.data_ptr()),
+                                             ctypes.c_void_p(g2.data_ptr()), B, C, st), "bwd_split")
+    hi = gy.bfloat16()
+    lo = (gy - hi.float()).bfloat16()
+    assert torch.equal(g2[0], hi) and torch.equal(g2[1], lo)
+    s2 = _split2(gy)
+    assert torch.equal(s2[0], hi) and torch.equal(s2[1], lo)
+    # bias gradient from the pooled gradient alone (what _ConvReluPool.backward does)
+    db = (go * (code >= 4)).view(B, C, 49).sum(dim=(0, 2))
+    assert torch.allclose(db, gy.sum(0), rtol=1e-4, atol=1e-4)
+
+
+def test_fused_classifier_nodes_match_the_plain_split_path():
+    """_ConvReluPool + _BigLinear (shared weight split, gradient never materialised in fp32) against the one-GEMM-per-op
+    _SplitLinear path: same logits and gradients up to fp32 summation order."""
+    from probnmn_clevr_b200.nmn import NeuralModuleNetwork
+    from probnmn_clevr_b200.synthetic import make_nmn_state_dict
+    from probnmn_clevr_b200.vocabulary import Vocabulary
+    vocab = Vocabulary.clevr()
+    m = NeuralModuleNetwork(vocab)
+    m.load_state_dict(make_nmn_state_dict(vocab, 0))
+    m = m.cuda()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    final = torch.randn((6, 128, 14, 14), generator=g, device="cuda").relu_()
+    res = {}
+    for fused in (True, False):
+        m._classifier_fused = fused
+        m.zero_grad(set_to_none=True)
+        f = final.clone().requires_grad_(True)
+        logits = m._classifier_split(f)
+        logits.square().sum().backward()
+        res[fused] = (logits.detach(), f.grad, [p.grad.clone() for p in m.classifier.parameters()])
+    rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-30))
+    assert rel(res[True][0], res[False][0]) < 2e-5
+    assert rel(res[True][1], res[False][1]) < 2e-5
+    for a, b in zip(res[True][2], res[False][2]):
+        assert rel(a, b) < 2e-5
