@@ -62,6 +62,10 @@ int64_t pnmn_model_packed_floats(const pnmn_model* m);
 pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* programs_host, int batch, int length,
                             int need_grad);
 void pnmn_plan_destroy(pnmn_plan* p);
+/* Optional: copy the plan's task tables into `device_blob` (PNMN_SZ_BLOB bytes, caller-owned) on `stream` ahead of time;
+ * a pnmn_nmn_forward whose pnmn_buffers.blob is the same pointer then skips its own upload (the caller orders the
+ * forward's stream after this one).  Lets an input pipeline keep every host -> device copy off the compute stream. */
+int pnmn_plan_upload(pnmn_plan* p, void* device_blob, void* stream);
 /* valid[b] = 1 if the reference would execute program b without raising (nmn.py:231-238) */
 int pnmn_plan_valid(const pnmn_plan* p, uint8_t* valid);
 

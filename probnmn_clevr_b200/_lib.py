@@ -94,7 +94,7 @@ class PgDesc(Structure):
 
 EXPORTS = [
     "pnmn_version", "pnmn_last_error", "pnmn_model_create", "pnmn_model_destroy", "pnmn_model_packed_floats",
-    "pnmn_plan_create", "pnmn_plan_destroy", "pnmn_plan_valid", "pnmn_plan_sizes", "pnmn_plan_stats",
+    "pnmn_plan_create", "pnmn_plan_destroy", "pnmn_plan_upload", "pnmn_plan_valid", "pnmn_plan_sizes", "pnmn_plan_stats",
     "pnmn_nmn_forward", "pnmn_nmn_backward", "pnmn_debug_launch_conv", "pnmn_debug_launch_wgrad",
     "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt", "pnmn_profile_enable",
     "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times", "pnmn_debug_plan_meta",
@@ -134,6 +134,7 @@ def lib() -> ctypes.CDLL:
     L.pnmn_plan_create.restype = c_void_p
     L.pnmn_plan_create.argtypes = [c_void_p, POINTER(c_int64), c_int, c_int, c_int]
     L.pnmn_plan_destroy.argtypes = [c_void_p]
+    L.pnmn_plan_upload.argtypes = [c_void_p, c_void_p, c_void_p]
     L.pnmn_plan_valid.argtypes = [c_void_p, POINTER(c_uint8)]
     L.pnmn_plan_sizes.argtypes = [c_void_p, POINTER(c_int64)]
     L.pnmn_plan_stats.argtypes = [c_void_p, POINTER(c_int64)]

@@ -349,6 +349,7 @@ class NeuralModuleNetwork(nn.Module):
         self.last_plan_stats: Optional[List[int]] = None
         self._gflat_box: Dict[str, torch.Tensor] = {}
         self._grad_overlap = None
+        self._upload_stream = None
         self._precompiled: list = []  # pending (programs, need_grad, future of a plan) entries, see precompile()
         # classifier GEMMs (plain library GEMMs, nmn.py:75-83): "split" (default) = every fp32 operand split into two bf16
         # halves (pnmn_split3_bf16, one pass), one cuBLAS tensor-core GEMM over the 3x contraction with fp32 accumulation
@@ -485,9 +486,12 @@ class NeuralModuleNetwork(nn.Module):
         # forward's single D2H copy.
         programs_host = programs.detach().to("cpu", torch.int64).contiguous()
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._exec_params)
-        plan = self._take_precompiled(programs_host, need_grad)
-        if plan is None:
+        pre = self._take_precompiled(programs_host, need_grad)
+        pre_blob = pre_event = None
+        if pre is None:
             plan = self._compile(programs_host, need_grad, None)
+        else:
+            plan, pre_blob, pre_event = pre
         valid_host = torch.empty(B, dtype=torch.uint8)
         lib.pnmn_plan_valid(plan, ctypes.cast(valid_host.data_ptr(), ctypes.POINTER(ctypes.c_uint8)))
         sizes = (ctypes.c_int64 * L.SZ_COUNT)()
@@ -501,11 +505,19 @@ class NeuralModuleNetwork(nn.Module):
         if self._packed is None or self._packed.device != features.device:
             self._packed = torch.empty(lib.pnmn_model_packed_floats(self._model_handle), dtype=torch.float32,
                                        device=features.device)
+        blob = ws.t["blob"]
+        if pre_blob is not None and pre_blob.device == features.device:
+            # the look-ahead compile already uploaded the task tables on its own stream (pnmn_plan_upload)
+            current = torch.cuda.current_stream(features.device)
+            current.wait_event(pre_event)
+            pre_blob.record_stream(current)
+            blob = pre_blob
         bufs = L.Buffers(ws.t["arena16"].data_ptr(), ws.t["arena18"].data_ptr(), ws.t["arena22"].data_ptr(),
                          ws.t["maps"].data_ptr(), ws.t["dmaps"].data_ptr(), ws.t["idx"].data_ptr(),
-                         ws.t["blob"].data_ptr(), self._packed.data_ptr(), self._flat.data_ptr(), None,
+                         blob.data_ptr(), self._packed.data_ptr(), self._flat.data_ptr(), None,
                          ws.t["ain"].data_ptr(), ws.scratch.data_ptr())
         run = _Run(plan, ws, bufs, self._gflat_box)
+        run.blob = blob  # (a pre-uploaded table buffer lives until the backward pass has run)
         if need_grad:
             final = _ExecutorFn.apply(features, self._anchor, run, self)
         else:
@@ -560,6 +572,28 @@ class NeuralModuleNetwork(nn.Module):
             raise RuntimeError("pnmn_plan_create failed: " + lib.pnmn_last_error().decode())
         return plan
 
+    def _compile_and_upload(self, programs_host: torch.Tensor, need_grad: bool, device):
+        """Helper-thread half of ``precompile``: compile, then copy the task tables to the device on the upload stream, so
+        that the forward pass itself issues no host -> device copy (one queued inside forward would wait for the compute
+        stream and then find the copy engine busy with the next batch's features)."""
+        plan = self._compile(programs_host, need_grad, device)
+        if device is None:
+            return plan, None, None
+        lib = L.lib()
+        try:
+            sizes = (ctypes.c_int64 * L.SZ_COUNT)()
+            lib.pnmn_plan_sizes(plan, sizes)
+            with torch.cuda.device(device), torch.cuda.stream(self._upload_stream):
+                blob = torch.empty(int(sizes[L.SZ_BLOB]), dtype=torch.uint8, device=device)
+                L.check(lib.pnmn_plan_upload(plan, ctypes.c_void_p(blob.data_ptr()),
+                                             ctypes.c_void_p(self._upload_stream.cuda_stream)), "pnmn_plan_upload")
+                event = torch.cuda.Event()
+                event.record(self._upload_stream)
+            return plan, blob, event
+        except Exception:
+            lib.pnmn_plan_destroy(plan)
+            raise
+
     def precompile(self, programs: torch.Tensor, need_grad: Optional[bool] = None) -> None:
         """Optional look-ahead for input pipelines: start compiling ``programs`` (host tensor, (B, L) token ids) into an
         executor plan on a helper thread.  A later ``forward`` whose programs have the same contents picks the plan up
@@ -573,9 +607,12 @@ class NeuralModuleNetwork(nn.Module):
         if need_grad is None:
             need_grad = self.training and any(p.requires_grad for p in self._exec_params)
         device = self._flat.device if self._flat is not None and self._flat.is_cuda else None
+        if device is not None and (self._upload_stream is None or self._upload_stream.device != device):
+            self._upload_stream = torch.cuda.Stream(device)
         while len(self._precompiled) >= 3:
             self._destroy_pending(self._precompiled.pop(0))
-        self._precompiled.append((host, bool(need_grad), _compile_pool().submit(self._compile, host, bool(need_grad), device)))
+        self._precompiled.append((host, bool(need_grad),
+                                  _compile_pool().submit(self._compile_and_upload, host, bool(need_grad), device)))
 
     def _take_precompiled(self, programs_host: torch.Tensor, need_grad: bool):
         for k, (host, ng, fut) in enumerate(self._precompiled):
@@ -587,7 +624,7 @@ class NeuralModuleNetwork(nn.Module):
     @staticmethod
     def _destroy_pending(entry) -> None:
         try:
-            L.lib().pnmn_plan_destroy(entry[2].result())
+            L.lib().pnmn_plan_destroy(entry[2].result()[0])
         except Exception:
             pass
 
