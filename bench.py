@@ -261,6 +261,10 @@ def run_ours(args):
         # while this thread issues the current step -- the same look-ahead an input pipeline gives the feature copy
         throttle()
         f, p, a = resident[i % 2]
+        if os.environ.get("PNMN_DEBUG_INPUTS"):
+            bad = ((a < 0) | (a >= 28))
+            if bool(bad.any()):
+                raise RuntimeError(f"rank {rank} resident step {i}: {int(bad.sum())} bad answers")
         model.zero_grad(set_to_none=True)
         out = model(f, p, a)
         if lookahead:
@@ -278,8 +282,9 @@ def run_ours(args):
     feed = DevicePrefetcher(dev)
     e2e_total = {"n": 0}
 
-    loss_host = torch.zeros(max(args.steps, 2), dtype=torch.float32).pin_memory()
-    loss_events = [torch.cuda.Event() for _ in range(max(args.steps, 2))]
+    n_slots = max(args.steps, args.warmup, 8)
+    loss_host = torch.zeros(n_slots, dtype=torch.float32).pin_memory()
+    loss_events = [torch.cuda.Event() for _ in range(n_slots)]
     loss_values = []
 
     def read_loss(i):
@@ -302,6 +307,12 @@ def run_ours(args):
         if feed.pending() == 0:
             feed.submit(i, (host[i % 2][0], host[i % 2][2]))
         f, a = feed.get(i)
+        if os.environ.get("PNMN_DEBUG_INPUTS"):  # diagnostics: the batch as the device sees it (synchronises)
+            bad = ((a < 0) | (a >= 28))
+            if bool(bad.any()):
+                idx = bad.nonzero().flatten()
+                raise RuntimeError(f"rank {rank} e2e step {i}: {int(bad.sum())} bad answers, rows {idx[:4].tolist()}..{idx[-4:].tolist()}, "
+                                   f"values {a[idx[:4]].tolist()}, host ok {bool(((host[i % 2][2] >= 0) & (host[i % 2][2] < 28)).all())}")
         model.zero_grad(set_to_none=True)
         out = model(f, host[i % 2][1], a)
         if lookahead and i + 2 < e2e_total["n"]:
@@ -346,8 +357,10 @@ def run_ours(args):
                         "issue_total": host_issue_ms / args.steps,  # wall time the host needs to issue one step
                         "run_ahead_wait": issued["wait_s"] * 1e3 / args.steps}  # waiting for step i-2 (run-ahead bound)
     stats = model.last_plan_stats
-    e2e_total["n"] = 2
-    for i in range(2):
+    # warm-up of the end-to-end leg (W steps like the resident leg: the prefetcher's device ring, the upload stream's
+    # allocator pool and the pinned staging buffers are first touched here)
+    e2e_total["n"] = max(args.warmup, 8)
+    for i in range(e2e_total["n"]):
         e2e_step(i)
     e2e_finish()
     e2e_total["n"] = args.steps

@@ -42,6 +42,11 @@ class DevicePrefetcher:
             bufs = [torch.empty(t.shape, dtype=t.dtype, device=self.device) for t in tensors]
             self._bufs[slot] = bufs
             self._free[slot] = None
+            # The new blocks come from the COMPUTE stream's allocator pool: the caching allocator hands out memory whose
+            # previous owner may still have work pending on that stream (e.g. a gradient freed by zero_grad whose in-place
+            # average has not run yet).  The copy stream must not write them before that work has drained.  Only on
+            # (re)allocation, i.e. never in steady state.
+            self.stream.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(self.stream):
             if self._free[slot] is not None:
                 self.stream.wait_event(self._free[slot])
