@@ -125,8 +125,11 @@ int pnmn_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, in
 int pnmn_relu_pool_fwd(const float* y, float* pooled, void* code, int64_t B, int64_t C, void* stream);
 int pnmn_relu_pool_bwd(const float* g, const void* code, float* gy, int64_t B, int64_t C, void* stream);
 /* same routing, output as the bf16 (hi, lo) pair g2[2][B*196][C] (hi = bf16(gy), lo = bf16(gy - hi)) that the
- * split-precision classifier GEMMs consume; the fp32 gradient is never materialised */
-int pnmn_relu_pool_bwd_split(const float* g, const void* code, void* g2, int64_t B, int64_t C, void* stream);
+ * split-precision classifier GEMMs consume; the fp32 gradient is never materialised (db: see below) */
+int pnmn_relu_pool_bwd_split(const float* g, const void* code, void* g2, float* db, int64_t B, int64_t C, void* stream);
+/* pnmn_relu_pool_fwd with the 1x1 conv's bias[C] added to y first (y = the bias-free GEMM output); in
+ * pnmn_relu_pool_bwd_split, db (optional, [C], zeroed by the caller) receives that bias's gradient */
+int pnmn_relu_pool_fwd_bias(const float* y, const float* bias, float* pooled, void* code, int64_t B, int64_t C, void* stream);
 /* dst[2][n] bf16 = (hi, lo) split of src[n] fp32, n % 4 == 0 */
 int pnmn_split2_bf16(const float* src, void* dst, int64_t n, void* stream);
 

@@ -98,7 +98,7 @@ EXPORTS = [
     "pnmn_nmn_forward", "pnmn_nmn_backward", "pnmn_debug_launch_conv", "pnmn_debug_launch_wgrad",
     "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt", "pnmn_profile_enable",
     "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times", "pnmn_debug_plan_meta",
-    "pnmn_split3_bf16", "pnmn_relu_pool_fwd", "pnmn_relu_pool_bwd", "pnmn_relu_pool_bwd_split", "pnmn_split2_bf16", "pnmn_launch_count", "pnmn_pg_workspace_bytes", "pnmn_pg_forward", "pnmn_pg_backward", "pnmn_pg_debug_layout",
+    "pnmn_split3_bf16", "pnmn_relu_pool_fwd", "pnmn_relu_pool_bwd", "pnmn_relu_pool_bwd_split", "pnmn_relu_pool_fwd_bias", "pnmn_split2_bf16", "pnmn_launch_count", "pnmn_pg_workspace_bytes", "pnmn_pg_forward", "pnmn_pg_backward", "pnmn_pg_debug_layout",
 ]
 
 
@@ -157,7 +157,8 @@ def lib() -> ctypes.CDLL:
     L.pnmn_split3_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]
     L.pnmn_relu_pool_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
     L.pnmn_relu_pool_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
-    L.pnmn_relu_pool_bwd_split.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
+    L.pnmn_relu_pool_bwd_split.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
+    L.pnmn_relu_pool_fwd_bias.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
     L.pnmn_split2_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     L.pnmn_launch_count.restype = ctypes.c_longlong
     L.pnmn_launch_count.argtypes = [c_int]

@@ -25,8 +25,22 @@ __global__ void __launch_bounds__(256) elt_kernel(const EltTask* __restrict__ ta
 // the same scaled values; every parameter gradient is multiplied by scale[1] = 1/scale on its way out).
 __global__ void __launch_bounds__(256) amax_kernel(const float* __restrict__ x, size_t n, unsigned int* amax_bits) {
   float m = 0.f;
-  for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n; i += static_cast<size_t>(gridDim.x) * blockDim.x)
-    m = fmaxf(m, fabsf(x[i]));
+  // 16-byte loads, four in flight per thread (x is a 16-byte aligned tensor; the tail is read element-wise)
+  const size_t n4 = n / 4, stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const float4* x4 = reinterpret_cast<const float4*>(x);
+  size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  for (; i + 3 * stride < n4; i += 4 * stride) {
+    const float4 a = x4[i], b = x4[i + stride], c = x4[i + 2 * stride], d = x4[i + 3 * stride];
+    m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))),
+                       fmaxf(fmaxf(fabsf(b.x), fabsf(b.y)), fmaxf(fabsf(b.z), fabsf(b.w)))));
+    m = fmaxf(m, fmaxf(fmaxf(fmaxf(fabsf(c.x), fabsf(c.y)), fmaxf(fabsf(c.z), fabsf(c.w))),
+                       fmaxf(fmaxf(fabsf(d.x), fabsf(d.y)), fmaxf(fabsf(d.z), fabsf(d.w)))));
+  }
+  for (; i < n4; i += stride) {
+    const float4 a = x4[i];
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(a.x), fabsf(a.y)), fmaxf(fabsf(a.z), fabsf(a.w))));
+  }
+  for (size_t j = n4 * 4 + blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; j < n; j += stride) m = fmaxf(m, fabsf(x[j]));
   for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
   if ((threadIdx.x & 31) == 0 && m > 0.f && m < INFINITY) atomicMax(amax_bits, __float_as_uint(m));
 }
@@ -45,7 +59,7 @@ __global__ void scale_kernel(float* scale /* [0]=scale [1]=1/scale, [2]=amax bit
 cudaError_t launch_loss_scale(const float* grad, size_t n, float* scale, cudaStream_t stream) {
   cudaError_t e = cudaMemsetAsync(scale, 0, 16, stream);
   if (e != cudaSuccess) return e;
-  amax_kernel<<<296, 256, 0, stream>>>(grad, n, reinterpret_cast<unsigned int*>(scale) + 2);
+  amax_kernel<<<148 * 4, 256, 0, stream>>>(grad, n, reinterpret_cast<unsigned int*>(scale) + 2);
   scale_kernel<<<1, 1, 0, stream>>>(scale);
   return cudaGetLastError();
 }

@@ -50,37 +50,42 @@ cudaError_t launch_pack(const PackTask* d_tasks, int n_tasks, int total_tiles, c
   return cudaGetLastError();
 }
 
-// NCHW fp32 features [B][C][14][14]  ->  planes [C/4][P16][4] (tf32-rounded, valid slots only).
-// dst_off[b] = float offset of sample b's first plane inside `dst`, or < 0 to skip the sample
-// (invalid program: its stem is never executed).
+// NCHW fp32 features [B][C][14][14]  ->  the fp16 half planes [C/8][P16][8] of a stem-input unit (valid slots only; the
+// padding slots are the arena's permanent zeros).  A unit is laid out like every activation -- C/4 fp32 planes followed
+// by their fp16 shadow -- but nothing ever reads the fp32 planes of the INPUT features (the stem's first conv and its
+// weight gradient take the shadow), so only the shadow is written: 103 MB instead of 371 MB per 256 samples.
+// dst_off[b] = float offset of sample b's unit inside `dst`, or < 0 to skip the sample (invalid program: its stem is
+// never executed).  One block per (sample, 8 channels): 16-byte stores, one per pixel slot.
 __global__ void __launch_bounds__(256) nchw_to_planes_kernel(const float* __restrict__ src, float* __restrict__ dst,
                                                              int C, const int64_t* __restrict__ dst_off) {
   const int b = blockIdx.y;
-  const int kc = blockIdx.x;  // plane
+  const int hp = blockIdx.x;  // half plane = 8 channels
   const int64_t off = dst_off[b];
   if (off < 0) return;
-  const float* s = src + (static_cast<size_t>(b) * C + kc * 4) * 196;
-  float* d = dst + off + static_cast<size_t>(kc) * 256 * 4;
-  __shared__ float tile[4 * 196];
-  for (int i = threadIdx.x; i < 4 * 196; i += 256) tile[i] = s[i];
+  const float* s = src + (static_cast<size_t>(b) * C + hp * 8) * 196;
+  __shared__ float tile[8 * 196];
+  for (int i = threadIdx.x; i < 8 * 196 / 4; i += 256)
+    reinterpret_cast<float4*>(tile)[i] = reinterpret_cast<const float4*>(s)[i];  // (8 * 196 floats, 16-byte aligned)
   __syncthreads();
   if (threadIdx.x < 196) {
     const int p = threadIdx.x, slot = (p / kHW) * 16 + (p % kHW);
-    float4 v = make_float4(to_tf32(tile[p]), to_tf32(tile[196 + p]), to_tf32(tile[392 + p]), to_tf32(tile[588 + p]));
-    *reinterpret_cast<float4*>(d + slot * 4) = v;
-    // fp16 shadow [C/8][256][8] behind the C/4 fp32 planes (operand of the stem conv1 weight gradient)
+    uint32_t h[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      // same value chain as every other activation: tf32 rounding first, then the (saturating) fp16 operand copy
+      const __half2 v = __floats2half2_rn(fminf(to_tf32(tile[(2 * e) * 196 + p]), 65504.f),
+                                          fminf(to_tf32(tile[(2 * e + 1) * 196 + p]), 65504.f));
+      h[e] = *reinterpret_cast<const uint32_t*>(&v);
+    }
     uint8_t* hb = reinterpret_cast<uint8_t*>(dst + off) + static_cast<size_t>(C / 4) * 256 * 16;
-    const __half2 h0 = __floats2half2_rn(fminf(v.x, 65504.f), fminf(v.y, 65504.f));
-    const __half2 h1 = __floats2half2_rn(fminf(v.z, 65504.f), fminf(v.w, 65504.f));
-    *reinterpret_cast<uint2*>(hb + (static_cast<size_t>(kc >> 1) * 256 + slot) * 16 + (kc & 1) * 8) =
-        make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    *reinterpret_cast<uint4*>(hb + (static_cast<size_t>(hp) * 256 + slot) * 16) = make_uint4(h[0], h[1], h[2], h[3]);
   }
 }
 
 cudaError_t launch_nchw_to_planes(const float* src, float* dst, int B, int C, const int64_t* dst_off,
                                   cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  nchw_to_planes_kernel<<<dim3(C / 4, B), 256, 0, stream>>>(src, dst, C, dst_off);
+  nchw_to_planes_kernel<<<dim3(C / 8, B), 256, 0, stream>>>(src, dst, C, dst_off);
   return cudaGetLastError();
 }
 
@@ -124,17 +129,20 @@ cudaError_t launch_split3_bf16(const float* src, void* dst, int64_t rows, int64_
 // window (bits 0-1: dy*2 + dx, first maximum in scan order like ATen's max_pool2d) | 4 if the pooled value is > 0.
 // One block per (sample, 64 channels): every global access is a contiguous 256-byte (reads) or 12.5 KB (writes) run.
 constexpr int kPoolCB = 64;
-__global__ void __launch_bounds__(256) relu_pool_fwd_kernel(const float* __restrict__ y, float* __restrict__ pooled,
-                                                            uint8_t* __restrict__ code, int C) {
+// `bias` (optional, [C]) is added to y first -- max(v_i) + b == max(v_i + b) exactly, so the conv bias costs nothing here,
+// where the library GEMM would first broadcast it into its 205 MB output.
+__global__ void __launch_bounds__(256) relu_pool_fwd_kernel(const float* __restrict__ y, const float* __restrict__ bias,
+                                                            float* __restrict__ pooled, uint8_t* __restrict__ code, int C) {
   __shared__ float tile[kPoolCB * 49];
   __shared__ uint8_t ctile[kPoolCB * 49];
   const int b = blockIdx.y, c0 = blockIdx.x * kPoolCB;
   const int cw = threadIdx.x % kPoolCB, wq = threadIdx.x / kPoolCB;
+  const float bb = bias ? bias[c0 + cw] : 0.f;
   const float* yb = y + (static_cast<size_t>(b) * 196) * C + c0 + cw;
   for (int w = wq; w < 49; w += 4) {
     const int py = w / 7, px = w - py * 7;
     const float* p00 = yb + static_cast<size_t>((2 * py) * 14 + 2 * px) * C;
-    const float v0 = p00[0], v1 = p00[C], v2 = p00[static_cast<size_t>(14) * C], v3 = p00[static_cast<size_t>(15) * C];
+    const float v0 = p00[0] + bb, v1 = p00[C] + bb, v2 = p00[static_cast<size_t>(14) * C] + bb, v3 = p00[static_cast<size_t>(15) * C] + bb;
     float m = v0; int a = 0;
     if (v1 > m) { m = v1; a = 1; }
     if (v2 > m) { m = v2; a = 2; }
@@ -166,14 +174,27 @@ __global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const float* __restr
 // Same routing, but the gradient leaves as the bf16 (hi, lo) pair the classifier's split-precision GEMMs consume:
 // g2[0][B*196][C] = bf16(gy), g2[1][B*196][C] = bf16(gy - hi).  The fp32 tensor (205 MB at batch 256) is never written and
 // the two split passes that used to read it back (dgrad and wgrad layouts, 0.5 GB each) disappear.
+// `db` (optional, [C], zeroed by the caller) receives the bias gradient: a window's gradient reaches exactly one pixel, and
+// only if its maximum was positive (code bit 2), so db[c] is a sum over the pooled gradient (one atomic per block and channel).
 __global__ void __launch_bounds__(256) relu_pool_bwd_split_kernel(const float* __restrict__ g, const uint8_t* __restrict__ code,
-                                                                  __nv_bfloat16* __restrict__ g2, int C, size_t plane) {
+                                                                  __nv_bfloat16* __restrict__ g2, float* __restrict__ db,
+                                                                  int C, size_t plane) {
   __shared__ float tile[kPoolCB * 49];
   __shared__ uint8_t ctile[kPoolCB * 49];
+  __shared__ float part[4][kPoolCB];
   const int b = blockIdx.y, c0 = blockIdx.x * kPoolCB;
   const size_t o = static_cast<size_t>(b) * C * 49 + static_cast<size_t>(c0) * 49;
   for (int i = threadIdx.x; i < kPoolCB * 49; i += 256) { tile[i] = g[o + i]; ctile[i] = code[o + i]; }
   __syncthreads();
+  if (db) {
+    const int ch = threadIdx.x % kPoolCB, q = threadIdx.x / kPoolCB;
+    float s = 0.f;
+    for (int w = q; w < 49; w += 4) s += (ctile[ch * 49 + w] & 4) ? tile[ch * 49 + w] : 0.f;
+    part[q][ch] = s;
+    __syncthreads();
+    if (threadIdx.x < kPoolCB)
+      atomicAdd(db + c0 + threadIdx.x, part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x]);
+  }
   // thread = (channel pair cp = tid % 32, pixel phase pq = tid / 32): 4-byte bf16x2 stores, 128 contiguous bytes per warp
   const int cp = threadIdx.x % (kPoolCB / 2), pq = threadIdx.x / (kPoolCB / 2);
   __nv_bfloat16* gb = g2 + (static_cast<size_t>(b) * 196) * C + c0 + 2 * cp;
@@ -218,15 +239,15 @@ cudaError_t launch_split2_bf16(const float* src, void* dst, int64_t n, cudaStrea
   split2_bf16_kernel<<<blocks, 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), n);
   return cudaGetLastError();
 }
-cudaError_t launch_relu_pool_bwd_split(const float* g, const uint8_t* code, void* g2, int B, int C, cudaStream_t st) {
+cudaError_t launch_relu_pool_bwd_split(const float* g, const uint8_t* code, void* g2, float* db, int B, int C, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  relu_pool_bwd_split_kernel<<<dim3(C / kPoolCB, B), 256, 0, st>>>(g, code, static_cast<__nv_bfloat16*>(g2), C,
+  relu_pool_bwd_split_kernel<<<dim3(C / kPoolCB, B), 256, 0, st>>>(g, code, static_cast<__nv_bfloat16*>(g2), db, C,
                                                                    static_cast<size_t>(B) * 196 * C);
   return cudaGetLastError();
 }
-cudaError_t launch_relu_pool_fwd(const float* y, float* pooled, uint8_t* code, int B, int C, cudaStream_t st) {
+cudaError_t launch_relu_pool_fwd(const float* y, const float* bias, float* pooled, uint8_t* code, int B, int C, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;
-  relu_pool_fwd_kernel<<<dim3(C / kPoolCB, B), 256, 0, st>>>(y, pooled, code, C);
+  relu_pool_fwd_kernel<<<dim3(C / kPoolCB, B), 256, 0, st>>>(y, bias, pooled, code, C);
   return cudaGetLastError();
 }
 cudaError_t launch_relu_pool_bwd(const float* g, const uint8_t* code, float* gy, int B, int C, cudaStream_t st) {

@@ -1504,8 +1504,43 @@ __global__ void fill_ones_map_kernel(float* map) {
   if (i < 256) map[i] = ((i >> 4) < kHW && (i & 15) < kHW) ? 1.f : 0.f;
 }
 
+// Side stream (one per device) for work that only has to finish by the end of the backward call: the bias-gradient kernel
+// (128-thread CTAs, no shared memory, HBM-bound) runs underneath wgrad_tc_kernel, which keeps one 256-thread CTA per SM busy
+// waiting on its operand ring (profiles/r1c: 12 % of the warp slots active).
+struct SideStream { cudaStream_t s = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+std::mutex g_side_mutex;
+std::map<int, SideStream> g_side;
+SideStream* side_stream() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(g_side_mutex);
+  SideStream& ss = g_side[dev];
+  if (!ss.s) {
+    if (cudaStreamCreateWithFlags(&ss.s, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ss.join, cudaEventDisableTiming) != cudaSuccess) {
+      cudaGetLastError();
+      ss = SideStream();
+      return nullptr;
+    }
+  }
+  return &ss;
+}
+
 int run_launches(const pnmn_plan& p, const std::vector<LaunchItem>& ls, const uint8_t* blob, bool bwd, cudaStream_t st) {
   const ConvCfg* cfgs = reinterpret_cast<const ConvCfg*>(blob + p.off_cfg);
+  static const bool no_side = std::getenv("PNMN_NO_SIDE_STREAM") != nullptr;
+  if (bwd && p.persistent && !g_prof_on && !no_side && ls.size() == 2 && ls[0].kind == LK_WGRAD && ls[1].kind == LK_BIAS) {
+    if (SideStream* ss = side_stream()) {
+      CUDA_OK(cudaEventRecord(ss->fork, st));
+      CUDA_OK(cudaStreamWaitEvent(ss->s, ss->fork, 0));
+      CUDA_OK(launch_bias_grad(blob + p.off_bt, ls[1].count, kBiasSplit, ss->s));
+      CUDA_OK(cudaEventRecord(ss->join, ss->s));
+      CUDA_OK(launch_wgrad(reinterpret_cast<const WgradTask*>(blob + p.off_wt), ls[0].count, 0, st));
+      CUDA_OK(cudaStreamWaitEvent(st, ss->join, 0));
+      return 0;
+    }
+  }
   const ConvTask* conv = reinterpret_cast<const ConvTask*>(blob + (bwd ? p.off_bconv : p.off_fconv));
   const EltTask* elt = reinterpret_cast<const EltTask*>(blob + (bwd ? p.off_belt : p.off_felt));
   for (const LaunchItem& l : ls) {
@@ -1721,7 +1756,14 @@ extern "C" int pnmn_split3_bf16(const float* src, void* dst, int64_t rows, int64
 // ReLU + 2x2 max-pool + flatten between the classifier's two GEMMs (nmn.py:77-79) and its backward (see layout.cu)
 extern "C" int pnmn_relu_pool_fwd(const float* y, float* pooled, void* code, int64_t B, int64_t C, void* stream) {
   if (!y || !pooled || !code || B < 0 || C <= 0 || C % 64 != 0) return fail("pnmn_relu_pool_fwd: bad arguments (C must be a multiple of 64)");
-  CUDA_OK(launch_relu_pool_fwd(y, pooled, static_cast<uint8_t*>(code), static_cast<int>(B), static_cast<int>(C), static_cast<cudaStream_t>(stream)));
+  CUDA_OK(launch_relu_pool_fwd(y, nullptr, pooled, static_cast<uint8_t*>(code), static_cast<int>(B), static_cast<int>(C), static_cast<cudaStream_t>(stream)));
+  pnmn::count_launches(1);
+  return 0;
+}
+// same with the 1x1 conv's bias added to y first (y is then the bias-free GEMM output)
+extern "C" int pnmn_relu_pool_fwd_bias(const float* y, const float* bias, float* pooled, void* code, int64_t B, int64_t C, void* stream) {
+  if (!y || !bias || !pooled || !code || B < 0 || C <= 0 || C % 64 != 0) return fail("pnmn_relu_pool_fwd_bias: bad arguments (C must be a multiple of 64)");
+  CUDA_OK(launch_relu_pool_fwd(y, bias, pooled, static_cast<uint8_t*>(code), static_cast<int>(B), static_cast<int>(C), static_cast<cudaStream_t>(stream)));
   pnmn::count_launches(1);
   return 0;
 }
@@ -1733,9 +1775,9 @@ extern "C" int pnmn_relu_pool_bwd(const float* g, const void* code, float* gy, i
 }
 
 // the same backward with the gradient written as the bf16 (hi, lo) pair [2][B*196][C] of the split-precision GEMMs
-extern "C" int pnmn_relu_pool_bwd_split(const float* g, const void* code, void* g2, int64_t B, int64_t C, void* stream) {
+extern "C" int pnmn_relu_pool_bwd_split(const float* g, const void* code, void* g2, float* db, int64_t B, int64_t C, void* stream) {
   if (!g || !g2 || !code || B < 0 || C <= 0 || C % 64 != 0) return fail("pnmn_relu_pool_bwd_split: bad arguments (C must be a multiple of 64)");
-  CUDA_OK(launch_relu_pool_bwd_split(g, static_cast<const uint8_t*>(code), g2, static_cast<int>(B), static_cast<int>(C), static_cast<cudaStream_t>(stream)));
+  CUDA_OK(launch_relu_pool_bwd_split(g, static_cast<const uint8_t*>(code), g2, db, static_cast<int>(B), static_cast<int>(C), static_cast<cudaStream_t>(stream)));
   pnmn::count_launches(1);
   return 0;
 }

@@ -770,13 +770,16 @@ class _ConvReluPool(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, w, b, B):
-        y = torch.addmm(b, _split3(x, 1, True), _split3(w, 1, False).t(), out_dtype=torch.float32)
+        # (the bias is added inside the pooling pass: addmm would first broadcast it into the 205 MB output)
+        y = torch.mm(_split3(x, 1, True), _split3(w, 1, False).t(), out_dtype=torch.float32)
         C = w.shape[0]
         pooled = torch.empty((B, C * 49), dtype=torch.float32, device=y.device)
         code = torch.empty((B, C * 49), dtype=torch.uint8, device=y.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)
-        L.check(L.lib().pnmn_relu_pool_fwd(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(pooled.data_ptr()),
-                                           ctypes.c_void_p(code.data_ptr()), B, C, stream), "pnmn_relu_pool_fwd")
+        bias = b.contiguous()
+        L.check(L.lib().pnmn_relu_pool_fwd_bias(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(bias.data_ptr()),
+                                                ctypes.c_void_p(pooled.data_ptr()), ctypes.c_void_p(code.data_ptr()), B, C,
+                                                stream), "pnmn_relu_pool_fwd_bias")
         ctx.save_for_backward(x, w, code)
         ctx.B = B
         return pooled
@@ -788,16 +791,16 @@ class _ConvReluPool(torch.autograd.Function):
         g = g.contiguous()
         g2 = torch.empty((2, M, C), dtype=torch.bfloat16, device=g.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
+        db = torch.zeros(C, dtype=torch.float32, device=g.device) if ctx.needs_input_grad[2] else None
         L.check(L.lib().pnmn_relu_pool_bwd_split(ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(code.data_ptr()),
-                                                 ctypes.c_void_p(g2.data_ptr()), B, C, stream), "pnmn_relu_pool_bwd_split")
-        dx = dw = db = None
+                                                 ctypes.c_void_p(g2.data_ptr()),
+                                                 ctypes.c_void_p(db.data_ptr() if db is not None else None), B, C, stream),
+                "pnmn_relu_pool_bwd_split")
+        dx = dw = None
         if ctx.needs_input_grad[0]:
             dx = _mm3(g2, _split2(w))                 # (M, C) x (C, Cin)
         if ctx.needs_input_grad[1]:
             dw = _mm3(g2, _split2(x), ta=True)        # (C, M) x (M, Cin)
-        if ctx.needs_input_grad[2]:
-            # a window's gradient reaches exactly one pixel, and only if its maximum was positive (code bit 2)
-            db = (g * (code >= 4)).view(B, C, 49).sum(dim=(0, 2))
         return dx, dw, db, None
 
 

@@ -21,11 +21,12 @@ for _ in range(2): step()
 torch.cuda.synchronize()
 cp.start(); step(); torch.cuda.synchronize(); cp.stop()
 PY
-timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,launch__grid_size --clock-control none --csv --log-file gpurun_out/launches_r1.csv python /tmp/one_step.py > gpurun_out/ncu_list.log 2>&1
+timeout 900 ncu --profile-from-start off --metrics gpu__time_duration.sum,launch__grid_size --clock-control none --csv --log-file gpurun_out/launches_${TAG:-r1}.csv python /tmp/one_step.py > gpurun_out/ncu_list.log 2>&1
 tail -3 gpurun_out/ncu_list.log
 python - <<'PY'
 import csv, collections
-rows=[r for r in csv.reader(open('gpurun_out/launches_r1.csv')) if len(r)>10]
+import os
+rows=[r for r in csv.reader(open('gpurun_out/launches_%s.csv' % os.environ.get('TAG','r1'))) if len(r)>10]
 hdr=rows[0]; ki=hdr.index('Kernel Name'); mi=hdr.index('Metric Name'); vi=hdr.index('Metric Value'); ii=hdr.index('ID')
 d=collections.OrderedDict()
 for r in rows[1:]:

@@ -304,16 +304,23 @@ def test_relu_pool_bwd_split_and_split2(B, C):
     L.check(L.lib().pnmn_relu_pool_fwd(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(pooled.data_ptr()),
                                        ctypes.c_void_p(code.data_ptr()), B, C, st), "fwd")
     g2 = torch.full((2, B * 196, C), float("nan"), dtype=torch.bfloat16, device="cuda")
+    db = torch.zeros(C, device="cuda")
     L.check(L.lib().pnmn_relu_pool_bwd_split(ctypes.c_void_p(go.data_ptr()), ctypes.c_void_p(code.data_ptr()),
-                                             ctypes.c_void_p(g2.data_ptr()), B, C, st), "bwd_split")
+                                             ctypes.c_void_p(g2.data_ptr()), ctypes.c_void_p(db.data_ptr()), B, C, st), "bwd_split")
     hi = gy.bfloat16()
     lo = (gy - hi.float()).bfloat16()
     assert torch.equal(g2[0], hi) and torch.equal(g2[1], lo)
     s2 = _split2(gy)
     assert torch.equal(s2[0], hi) and torch.equal(s2[1], lo)
-    # bias gradient from the pooled gradient alone (what _ConvReluPool.backward does)
-    db = (go * (code >= 4)).view(B, C, 49).sum(dim=(0, 2))
+    # bias gradient, summed inside the same pass from the pooled gradient alone
     assert torch.allclose(db, gy.sum(0), rtol=1e-4, atol=1e-4)
+    # forward with the bias folded in: identical to adding it first
+    bias = torch.randn(C, generator=g, device="cuda")
+    p2 = torch.empty_like(out); c2 = torch.empty_like(code)
+    L.check(L.lib().pnmn_relu_pool_fwd_bias(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(bias.data_ptr()), ctypes.c_void_p(p2.data_ptr()),
+                                            ctypes.c_void_p(c2.data_ptr()), B, C, st), "fwd_bias")
+    ref = F.max_pool2d(F.relu(y + bias).view(B, 14, 14, C).permute(0, 3, 1, 2), 2, 2).contiguous().reshape(B, -1)
+    assert torch.equal(p2, ref)
 
 
 def test_fused_classifier_nodes_match_the_plain_split_path():
@@ -343,3 +350,27 @@ def test_fused_classifier_nodes_match_the_plain_split_path():
     assert rel(res[True][1], res[False][1]) < 1e-4
     for a, b in zip(res[True][2], res[False][2]):
         assert rel(a, b) < 1e-4
+
+
+def test_nchw_to_planes_writes_the_fp16_shadow():
+    """Stem input staging: NCHW fp32 features -> fp16 half planes [C/8][256 slots][8] behind the (unwritten) fp32 planes of
+    the unit; padding slots stay zero (extract_features.py:102-131 gives NCHW fp32; executor.h describes the planes)."""
+    import ctypes
+    from probnmn_clevr_b200 import _lib as L
+    B, C = 3, 256
+    g = torch.Generator(device="cuda").manual_seed(13)
+    x = torch.randn((B, C, 14, 14), generator=g, device="cuda").relu_()
+    unit_floats = (C // 4) * 256 * 4 * 3 // 2
+    dst = torch.zeros(B * unit_floats, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    L.check(L.lib().pnmn_debug_nchw_to_planes(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(dst.data_ptr()), B, C,
+                                              unit_floats, st), "nchw_to_planes")
+    units = dst.view(B, unit_floats)
+    assert units[:, : (C // 4) * 256 * 4].abs().max().item() == 0.0          # fp32 planes: untouched
+    shadow = units[:, (C // 4) * 256 * 4:].contiguous().view(torch.float16).view(B, C // 8, 16, 16, 8)
+    # tf32 rounding (ties away from zero on the 13 dropped bits), then fp16
+    xi = x.view(torch.int32)
+    tf32 = ((xi + 0x1000) & ~0x1FFF).view(torch.float32)
+    want = tf32.half().view(B, C // 8, 8, 14, 14).permute(0, 1, 3, 4, 2)
+    assert torch.equal(shadow[:, :, :14, :14, :], want)
+    assert shadow[:, :, 14:].abs().max().item() == 0.0 and shadow[:, :, :, 14:].abs().max().item() == 0.0
