@@ -291,6 +291,7 @@ def run_ours(args):
         loss_events[i].synchronize()
         loss_values.append(float(loss_host[i]))
 
+    e2e_trace = [] if os.environ.get("PNMN_E2E_TRACE") else None  # diagnostics: per-step device / host timestamps
     e2e_variant = os.environ.get("PNMN_E2E_VARIANT", "")  # diagnostics only: "nocopy" / "noread" drop one part of the leg
 
     def e2e_step(i):
@@ -304,6 +305,10 @@ def run_ours(args):
             if i > 0:
                 read_loss(i - 1)
             return
+        if e2e_trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            e2e_trace.append((i, ev, time.perf_counter()))
         if feed.pending() == 0:
             feed.submit(i, (host[i % 2][0], host[i % 2][2]))
         f, a = feed.get(i)
@@ -369,6 +374,11 @@ def run_ours(args):
     loss_values.clear()
     ms_e2e = timed(lambda j: e2e_step(W + j), args.steps, e2e_finish)
     assert len(loss_values) == args.steps + 1 and all(v == v for v in loss_values), "every step's loss must have been read back"
+    if e2e_trace is not None and rank == 0:
+        torch.cuda.synchronize()
+        for (i0, a0, h0), (i1, a1, h1) in zip(e2e_trace, e2e_trace[1:]):
+            print(f"e2e step {i0}: device start->start {a0.elapsed_time(a1):6.2f} ms, host {1e3 * (h1 - h0):6.2f} ms", file=sys.stderr)
+        e2e_trace.clear()
 
     # the end-to-end leg moves 205.5 MB of fp32 features per step: what the host -> device link alone sustains for that copy
     torch.cuda.synchronize()

@@ -85,7 +85,9 @@ int pnmn_plan_sizes(const pnmn_plan* p, int64_t* sizes /* [PNMN_SZ_COUNT] */);
 /* statistics: [0] #valid programs, [1] #3x3 module conv instances, [2] #module tokens executed,
  * [3] forward launches, [4] backward launches, [5] algorithmic forward FLOPs of the module convs,
  * [6] forward conv CTAs, [7] wgrad CTAs, [8]/[9] forward FLOPs run by the conv kernel variants <2,2>/<1,3>
- * (stem included), [10]/[11] the same for backward (dgrad), [12] wgrad FLOPs, [13] elementwise CTAs */
+ * (stem included), [10]/[11] the same for backward (dgrad), [12] wgrad FLOPs, [13] elementwise CTAs,
+ * [14] backward executor tasks, [15] byte offset inside the blob of the per-sample stem-input table
+ * (int64 per sample, < 0 = invalid program: lets the caller build the validity mask on the device) */
 int pnmn_plan_stats(const pnmn_plan* p, int64_t* stats /* [16] */);
 
 typedef struct pnmn_buffers {

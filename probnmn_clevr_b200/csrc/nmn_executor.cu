@@ -1388,6 +1388,7 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
   }
   for (const WgradTask& t : p.wtasks) p.stats[12] += static_cast<int64_t>(t.n_inst) * 2 * 196 * 128 * 128 * t.ntaps_x;
   p.stats[13] = static_cast<int64_t>(p.felt.size() + p.belt.size());
+  p.stats[15] = p.off_xin;  // byte offset, inside the task-table blob, of the per-sample stem-input table (int64, < 0 = invalid program)
   if (plan_timing)
     std::fprintf(stderr, "plan: emit %.2f ms, flatten+wgrad %.2f ms, blob %.2f ms, stats %.2f ms, tasks fwd %zu bwd %zu\n",
                  ms_between(timer.t0, t_emit), ms_between(t_emit, t_flat), ms_between(t_flat, t_blob),

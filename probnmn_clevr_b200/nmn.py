@@ -15,6 +15,7 @@ Same constructor, ``from_config``, ``forward(features, programs, answers=None)``
 There is no CPU or eager fallback: without the CUDA library / a CUDA device ``forward`` raises.
 """
 import ctypes
+import threading
 import os
 from typing import Dict, List, Optional, Tuple
 
@@ -228,6 +229,35 @@ class _WorkspacePool:
 _POOL = _WorkspacePool()
 
 
+class _BlobPool:
+    """Device buffers for task tables uploaded ahead of time (``precompile``).  They are kept and recycled instead of being
+    allocated per plan: a buffer that is filled on the upload stream and read on the compute stream can only go back to
+    the caching allocator with deferred frees, and the ``cudaMalloc`` calls that replace it (every few steps) stall the
+    device.  A buffer is reused once the compute stream has passed the point where its last user released it."""
+
+    def __init__(self):
+        self.free: List[Tuple[torch.Tensor, Optional[torch.cuda.Event]]] = []
+        self.lock = threading.Lock()
+
+    def acquire(self, nbytes: int, device, stream) -> torch.Tensor:
+        with self.lock:
+            for k, (t, ev) in enumerate(self.free):
+                if t.device == device and t.numel() >= nbytes and (ev is None or ev.query()):
+                    del self.free[k]
+                    return t
+        with torch.cuda.stream(stream):
+            return torch.empty(int(nbytes * 1.5) + 4096, dtype=torch.uint8, device=device)
+
+    def release(self, t: torch.Tensor) -> None:
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(t.device))
+        with self.lock:
+            self.free.append((t, ev))
+
+
+_BLOBS = _BlobPool()
+
+
 class _Run:
     """One forward's plan + workspace; released after backward (or when dropped)."""
 
@@ -238,6 +268,9 @@ class _Run:
         if self.plan is not None:
             L.lib().pnmn_plan_destroy(self.plan)
             self.plan = None
+        if getattr(self, "pool_blob", None) is not None:
+            _BLOBS.release(self.pool_blob)
+            self.pool_blob = None
         if self.ws is not None:
             _POOL.release(self.ws)
             self.ws = None
@@ -510,14 +543,14 @@ class NeuralModuleNetwork(nn.Module):
             # the look-ahead compile already uploaded the task tables on its own stream (pnmn_plan_upload)
             current = torch.cuda.current_stream(features.device)
             current.wait_event(pre_event)
-            pre_blob.record_stream(current)
             blob = pre_blob
         bufs = L.Buffers(ws.t["arena16"].data_ptr(), ws.t["arena18"].data_ptr(), ws.t["arena22"].data_ptr(),
                          ws.t["maps"].data_ptr(), ws.t["dmaps"].data_ptr(), ws.t["idx"].data_ptr(),
                          blob.data_ptr(), self._packed.data_ptr(), self._flat.data_ptr(), None,
                          ws.t["ain"].data_ptr(), ws.scratch.data_ptr())
         run = _Run(plan, ws, bufs, self._gflat_box)
-        run.blob = blob  # (a pre-uploaded table buffer lives until the backward pass has run)
+        run.blob = blob
+        run.pool_blob = pre_blob  # goes back to the pool when the run is closed (after the backward pass)
         if need_grad:
             final = _ExecutorFn.apply(features, self._anchor, run, self)
         else:
@@ -536,7 +569,11 @@ class NeuralModuleNetwork(nn.Module):
             answer_logits = self.classifier(final)
         answer_logprobs = F.log_softmax(answer_logits, dim=-1)
         best_logprobs, answer_predictions = torch.max(answer_logprobs, dim=1)
-        invalid = (valid_host == 0).to(features.device, non_blocking=True)
+        # validity mask on the device: read from the plan's task tables (per-sample stem-input offset, < 0 = invalid) rather than
+        # uploaded -- a host -> device copy queued here would wait behind whatever the copy engine is doing (the next batch's
+        # 205 MB of features in a pipelined loop: 3.7 ms) and stall the whole stream
+        xin_off = int(stats[15])
+        invalid = run.blob[xin_off:xin_off + 8 * B].view(torch.int64) < 0
         answer_predictions = answer_predictions.masked_fill(invalid, self._unknown_answer)
         if answers is not None:
             loss = F.cross_entropy(answer_logits, answers, reduction="none")
@@ -577,14 +614,14 @@ class NeuralModuleNetwork(nn.Module):
         that the forward pass itself issues no host -> device copy (one queued inside forward would wait for the compute
         stream and then find the copy engine busy with the next batch's features)."""
         plan = self._compile(programs_host, need_grad, device)
-        if device is None:
+        if device is None or os.environ.get("PNMN_NO_EARLY_UPLOAD"):  # (switch: comparison runs)
             return plan, None, None
         lib = L.lib()
         try:
             sizes = (ctypes.c_int64 * L.SZ_COUNT)()
             lib.pnmn_plan_sizes(plan, sizes)
             with torch.cuda.device(device), torch.cuda.stream(self._upload_stream):
-                blob = torch.empty(int(sizes[L.SZ_BLOB]), dtype=torch.uint8, device=device)
+                blob = _BLOBS.acquire(int(sizes[L.SZ_BLOB]), device, self._upload_stream)
                 L.check(lib.pnmn_plan_upload(plan, ctypes.c_void_p(blob.data_ptr()),
                                              ctypes.c_void_p(self._upload_stream.cuda_stream)), "pnmn_plan_upload")
                 event = torch.cuda.Event()
@@ -624,7 +661,10 @@ class NeuralModuleNetwork(nn.Module):
     @staticmethod
     def _destroy_pending(entry) -> None:
         try:
-            L.lib().pnmn_plan_destroy(entry[2].result()[0])
+            plan, blob, _ = entry[2].result()
+            L.lib().pnmn_plan_destroy(plan)
+            if blob is not None:
+                _BLOBS.release(blob)
         except Exception:
             pass
 
