@@ -279,7 +279,15 @@ def run_ours(args):
     # stream before step i computes (probnmn_clevr_b200/feed.py), so all K copies sit inside the timed region but overlap
     # with compute; the loss is read back (device -> host) every step
     from probnmn_clevr_b200.feed import DevicePrefetcher
-    feed = DevicePrefetcher(dev)
+    prefetch_ahead = int(os.environ.get("PNMN_PREFETCH_AHEAD", "1"))  # batches copied ahead of the one being computed
+    feed = DevicePrefetcher(dev, depth=prefetch_ahead + 2)
+    feed_state = {"next": 0}
+
+    def feed_upto(last):
+        while feed_state["next"] <= last:
+            k = feed_state["next"]
+            feed.submit(k, (host[k % 2][0], host[k % 2][2]))
+            feed_state["next"] += 1
     e2e_total = {"n": 0, "first": 0}
 
     n_slots = args.steps + max(args.warmup, 8) + 8
@@ -309,8 +317,9 @@ def run_ours(args):
             ev = torch.cuda.Event(enable_timing=True)
             ev.record()
             e2e_trace.append((i, ev, time.perf_counter()))
-        if feed.pending() == 0:
-            feed.submit(i, (host[i % 2][0], host[i % 2][2]))
+        if feed_state["next"] <= i:  # (first step of a sequence: nothing was prefetched)
+            feed_state["next"] = i
+            feed_upto(i)
         f, a = feed.get(i)
         if os.environ.get("PNMN_DEBUG_INPUTS"):  # diagnostics: the batch as the device sees it (synchronises)
             bad = ((a < 0) | (a >= 28))
@@ -324,15 +333,15 @@ def run_ours(args):
             model.precompile(host[(i + 2) % 2][1])  # two steps ahead (the input pipeline knows its next two batches)
         # the next batch's copy is queued AFTER this forward's task-table upload (same H2D engine, FIFO): it then overlaps
         # with the executor instead of delaying it
-        if i + 1 < e2e_total["n"]:
-            feed.submit(i + 1, (host[(i + 1) % 2][0], host[(i + 1) % 2][2]))
+        feed_upto(min(i + prefetch_ahead, e2e_total["n"] - 1))
         loss = out["loss"].mean()
         loss.backward()
         if world > 1:
             model.allreduce_gradients()
         # every step's loss goes device -> pinned host; it is READ one step later (the usual logging lag of a training
         # loop) so that the host can prepare step i+1 while step i still runs; the last one is read by e2e_finish()
-        loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+        if e2e_variant != "nod2h":  # (diagnostics: "nod2h" keeps the per-step synchronisation but drops the 4-byte copy)
+            loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         loss_events[i].record()
         if i > e2e_total["first"] and e2e_variant != "noread":
             read_loss(i - 1)
@@ -407,6 +416,7 @@ def run_ours(args):
     kernel_ms = {k: pms[i] / prof_steps for i, k in enumerate(kinds)}
     # the same kernels while the next batch's 205 MB host -> device copy is in flight (end-to-end leg)
     e2e_total["n"], e2e_total["first"] = prof_steps, 0
+    feed_state["next"] = 0
     loss_values.clear()
     lib.pnmn_profile_enable(1)
     for i in range(prof_steps):
