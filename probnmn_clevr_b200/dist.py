@@ -57,9 +57,16 @@ class GradientOverlap:
         self.weight = weight
         self._pending: List[Tuple[torch.Tensor, "dist.Work"]] = []
         self._hooks = []
+        self._avg: Optional[bool] = None
         for p in params:
             if p.requires_grad and p.numel() >= min_numel:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
+
+    def _op(self):
+        """NCCL averages inside the collective (no per-tensor division kernel afterwards); gloo only sums."""
+        if self._avg is None:
+            self._avg = dist.get_backend(self.group) == "nccl"
+        return dist.ReduceOp.AVG if self._avg else dist.ReduceOp.SUM
 
     def _on_grad(self, p: torch.nn.Parameter) -> None:
         g = p.grad
@@ -67,26 +74,31 @@ class GradientOverlap:
             return
         if self.weight != 1.0:
             g.mul_(self.weight)
-        self._pending.append((g, dist.all_reduce(g, op=dist.ReduceOp.SUM, group=self.group, async_op=True)))
+        self._pending.append((g, dist.all_reduce(g, op=self._op(), group=self.group, async_op=True)))
 
-    def finish(self, models: Iterable[torch.nn.Module]) -> int:
+    def finish(self, models: Optional[Iterable[torch.nn.Module]] = None, buckets: Optional[List[torch.Tensor]] = None) -> int:
         """Average every gradient of ``models``: wait for the collectives the hooks started, all-reduce the rest.
-        Returns the number of collectives this step used."""
+        A caller that knows what is left (e.g. one flat gradient buffer) passes it as ``buckets`` and saves the walk over
+        every parameter.  Returns the number of collectives this step used."""
         world = dist.get_world_size(self.group)
-        early = {g.data_ptr() for g, _ in self._pending}
-        rest = [b for b in gradient_buckets(models) if b.data_ptr() not in early]
+        if buckets is None:
+            early = {g.data_ptr() for g, _ in self._pending}
+            buckets = [b for b in gradient_buckets(models) if b.data_ptr() not in early]
+        op = self._op()
         handles = []
-        for b in rest:
+        for b in buckets:
             if self.weight != 1.0:
                 b.mul_(self.weight)
-            handles.append(dist.all_reduce(b, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+            handles.append(dist.all_reduce(b, op=op, group=self.group, async_op=True))
         for g, h in self._pending:
             h.wait()
-            g.div_(world)
-        for b, h in zip(rest, handles):
+            if not self._avg:
+                g.div_(world)
+        for b, h in zip(buckets, handles):
             h.wait()
-            b.div_(world)
-        n = len(self._pending) + len(rest)
+            if not self._avg:
+                b.div_(world)
+        n = len(self._pending) + len(buckets)
         self._pending = []
         return n
 

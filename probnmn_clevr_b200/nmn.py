@@ -707,7 +707,15 @@ class NeuralModuleNetwork(nn.Module):
         from .dist import allreduce_gradients
 
         if self._grad_overlap is not None:
-            self._grad_overlap.finish([self])
+            # every classifier gradient is already travelling (hooks); what is left is the executor's flat gradient buffer
+            # when the parameters' .grad are its views (the normal case), else whatever the parameter walk finds
+            params = self._exec_params or []
+            flat_ok = (self._gflat is not None and self._gviews is not None and len(params) > 0
+                       and params[0].grad is self._gviews[0] and params[-1].grad is self._gviews[-1])
+            if flat_ok:
+                self._grad_overlap.finish(buckets=[self._gflat])
+            else:
+                self._grad_overlap.finish([self])
         else:
             allreduce_gradients([self], group=group)
 
