@@ -452,14 +452,13 @@ class NeuralModuleNetwork(nn.Module):
             self._gviews = [self._gflat[o:o + n].view(shape) for _, o, n, shape in self._layout]
         views = self._gviews
         self._gflat_box["gflat"] = self._gflat
-        n_none = sum(1 for p in params if p.grad is None)
-        if n_none == len(params):
+        if all(p.grad is v for p, v in zip(params, views) if p.requires_grad):
+            return self._gflat, None  # (the common case first: one pass over the 222 parameters)
+        if all(p.grad is None for p in params):
             self._gflat.zero_()
             for p, v in zip(params, views):
                 if p.requires_grad:
                     p.grad = v
-            return self._gflat, None
-        if n_none == 0 and all(p.grad is v for p, v in zip(params, views) if p.requires_grad):
             return self._gflat, None
         tmp = torch.zeros_like(self._flat)
 
@@ -473,6 +472,20 @@ class NeuralModuleNetwork(nn.Module):
                 else:
                     p.grad = p.grad + g
         return tmp, finish
+
+    def zero_grad(self, set_to_none: bool = True) -> None:
+        """``nn.Module.zero_grad``.  When the executor parameters' gradients are the views of the flat gradient buffer (the
+        state every backward pass leaves), they are cleared with ONE memset and stay attached -- zero tensors, which is what
+        the reference's ``optimizer.zero_grad()`` produces under its pinned torch 1.4 (``_trainer.py:193``) -- instead of
+        222 attribute writes here and 222 re-attachments in the next backward (~0.5 ms of host time per step)."""
+        params, views = self._exec_params, self._gviews
+        if (set_to_none and params and views is not None and self._gflat is not None
+                and all(p.grad is v for p, v in zip(params, views) if p.requires_grad)):
+            self._gflat.zero_()
+            for p in self.classifier.parameters():
+                p.grad = None
+            return
+        super().zero_grad(set_to_none=set_to_none)
 
     def _create_model_handle(self):
         offs = {name: o for name, o, _, _ in self._layout}
