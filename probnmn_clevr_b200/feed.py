@@ -10,6 +10,7 @@ block per step made the caching allocator wait for, or cudaMalloc around, blocks
 A slot is overwritten only after the compute stream has passed the point where its previous tenant was handed back,
 which with ``depth`` = 3 lies more than a full step in the past.
 """
+import os
 from typing import Dict, Hashable, List, Optional, Sequence, Tuple
 
 import torch
@@ -23,6 +24,7 @@ class DevicePrefetcher:
         self.device = torch.device(device)
         self.stream = torch.cuda.Stream(self.device)
         self.depth = depth
+        self.chunks = int(os.environ.get("PNMN_FEED_CHUNKS", "1"))  # large tensors are copied in this many slices
         self._bufs: List[Optional[List[torch.Tensor]]] = [None] * depth
         self._free: List[Optional[torch.cuda.Event]] = [None] * depth  # compute stream is done with the slot's tenant
         self._next = 0
@@ -51,7 +53,14 @@ class DevicePrefetcher:
             if self._free[slot] is not None:
                 self.stream.wait_event(self._free[slot])
             for b, t in zip(bufs, tensors):
-                b.copy_(t, non_blocking=True)
+                n = t.shape[0] if t.dim() > 0 else 1
+                if self.chunks > 1 and t.numel() * t.element_size() >= (32 << 20) and n >= self.chunks:
+                    # one DMA per slice: anything else that needs the copy engine waits for a slice, not for the whole batch
+                    step = (n + self.chunks - 1) // self.chunks
+                    for lo in range(0, n, step):
+                        b[lo:lo + step].copy_(t[lo:lo + step], non_blocking=True)
+                else:
+                    b.copy_(t, non_blocking=True)
             event = torch.cuda.Event()
             event.record(self.stream)
         self._slots[key] = (slot, event)
