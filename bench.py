@@ -13,11 +13,6 @@ inputs copied in and the loss read back every step.  `roofline` is the tcgen05 c
 kernel) timed with CUDA events around every launch; `cpu_baseline` is the CPU oracle (a port of the
 reference's PyTorch path) on a bounded sample.  `--impl reference` times that CPU path alone.
 """
-import os
-# More hardware work queues than the default 8: the step uses the compute stream, the feature-copy stream, the table-upload
-# stream, the library's side stream and NCCL's; streams that share a queue serialise, and a kernel queued behind the 3.7 ms
-# feature copy stalls the step (measured: a +5 ms stall every ~4 steps with 8 queues).  Must be set before CUDA initialises.
-os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 import argparse
 import ctypes
 import json
