@@ -147,6 +147,8 @@ def lib() -> ctypes.CDLL:
     L.pnmn_debug_launch_elt.argtypes = [c_void_p, c_int, c_void_p]
     L.pnmn_debug_set_trace.argtypes = [c_void_p, c_int64]
     L.pnmn_debug_host_times.argtypes = [POINTER(ctypes.c_double)]
+    L.pnmn_debug_plan_meta.restype = c_int64
+    L.pnmn_debug_plan_meta.argtypes = [c_void_p, c_int, c_void_p, c_int64]
     L.pnmn_pg_workspace_bytes.restype = c_int64
     L.pnmn_pg_workspace_bytes.argtypes = [POINTER(PgDesc), c_int, c_int, c_int, c_int, c_int]
     L.pnmn_pg_forward.argtypes = [POINTER(PgDesc), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
