@@ -300,6 +300,7 @@ def run_ours(args):
         loss_values.append(float(loss_host[i]))
 
     e2e_trace = [] if os.environ.get("PNMN_E2E_TRACE") else None  # diagnostics: per-step device / host timestamps
+    e2e_lag = int(os.environ.get("PNMN_E2E_LAG", "1"))  # a step's loss is read this many steps later
     e2e_variant = os.environ.get("PNMN_E2E_VARIANT", "")  # diagnostics only: "nocopy" / "noread" drop one part of the leg
 
     def e2e_step(i):
@@ -331,8 +332,8 @@ def run_ours(args):
         out = model(f, host[i % 2][1], a)
         if lookahead and i + 2 < e2e_total["n"]:
             model.precompile(host[(i + 2) % 2][1])  # two steps ahead (the input pipeline knows its next two batches)
-        # the next batch's copy is queued AFTER this forward's task-table upload (same H2D engine, FIFO): it then overlaps
-        # with the executor instead of delaying it
+        # (queued after the forward pass has been issued; measured alternatives -- first thing in the step, two batches ahead,
+        # loss read two steps later -- were no faster on average and more erratic: profiles/r1c_notes.md)
         feed_upto(min(i + prefetch_ahead, e2e_total["n"] - 1))
         loss = out["loss"].mean()
         loss.backward()
@@ -343,15 +344,16 @@ def run_ours(args):
         if e2e_variant != "nod2h":  # (diagnostics: "nod2h" keeps the per-step synchronisation but drops the 4-byte copy)
             loss_host[i:i + 1].copy_(loss.detach().reshape(1), non_blocking=True)
         loss_events[i].record()
-        if i > e2e_total["first"] and e2e_variant != "noread":
-            read_loss(i - 1)
+        if i - e2e_lag >= e2e_total["first"] and e2e_variant != "noread":
+            read_loss(i - e2e_lag)
 
     def e2e_finish():
         if e2e_variant == "noread":
             for j in range(e2e_total["first"], e2e_total["n"]):
                 read_loss(j)
             return
-        read_loss(e2e_total["n"] - 1)
+        for j in range(max(e2e_total["first"], e2e_total["n"] - e2e_lag), e2e_total["n"]):
+            read_loss(j)
 
     for i in range(max(args.warmup, 8)):  # (at least 8: the pinned staging pool of the plan uploads settles during warm-up)
         resident_step(i)
@@ -382,7 +384,7 @@ def run_ours(args):
         e2e_step(i)
     loss_values.clear()
     ms_e2e = timed(lambda j: e2e_step(W + j), args.steps, e2e_finish)
-    assert len(loss_values) == args.steps + 1 and all(v == v for v in loss_values), "every step's loss must have been read back"
+    assert len(loss_values) == args.steps + e2e_lag and all(v == v for v in loss_values), "every step's loss must have been read back"
     if e2e_trace is not None and rank == 0:
         torch.cuda.synchronize()
         for (i0, a0, h0), (i1, a1, h1) in zip(e2e_trace, e2e_trace[1:]):
