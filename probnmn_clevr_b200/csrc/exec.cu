@@ -3,16 +3,19 @@
 // The host-side program compiler (nmn_executor.cu) turns a batch of programs into a task list:
 // tensor-core convolution tasks (shift-GEMM, see conv.cu for the formulation) and CUDA-core tasks
 // (attend, same, min/max, the backward pieces; elt_body.cuh).  Every task names the tasks that
-// produce its inputs.  148 resident CTAs (one per SM) pull tasks from a global counter in list
+// produce its inputs.  296 resident CTAs (two per SM) pull tasks from a global counter in list
 // order, spin on the `done` flags of their predecessors, run the task and publish their own flag.
 // Because predecessors always sit earlier in the list and tasks are fetched in order, a waiting
 // CTA can only wait for a task that is already running: no deadlock, no host round trips, no
-// per-level launch latency, and chains of different samples overlap freely across the SMs.
+// per-level launch latency, and chains of different samples overlap freely across the SMs.  The list
+// order is the schedule: the compiler sorts it by remaining chain time (critical path first).
 //
-// Inside a CTA a convolution task is warp-specialised: warp 0 streams activation k-blocks and warp 1
-// streams weight tiles with cp.async.bulk into mbarrier rings, warp 2 issues tcgen05.mma (kind::f16 on
-// fp16 operands, fp32 accumulators in TMEM), warp 3 is the scheduler, warps 4-7 (one per TMEM lane
-// quarter) run the fused epilogue.  TMEM, barriers and ring phases persist across tasks.
+// Inside a CTA a convolution task is warp-specialised: warp 3 fetches the task record; warp 0 polls the
+// dependency flags and then streams activation k-blocks, warps 1 and 3 stream weight stages with cp.async.bulk
+// into mbarrier rings (the first ring-full of weights, the configuration and the bias staging do not depend on
+// the producers and are issued while warp 0 still polls), warp 2 issues tcgen05.mma (kind::f16 on fp16 operands,
+// fp32 accumulators in TMEM), and all 8 warps run the fused epilogue (warps 4-7 take accumulator columns 0..63
+// of their TMEM lane quarter, warps 0-3 columns 64..127).  TMEM, barriers and ring phases persist across tasks.
 //
 // TWO CTAs are resident per SM (256 threads, <= 128 registers, 107 KB of shared memory and 256 TMEM
 // columns each): a task is a strictly serial chain (wait for predecessors -> first operands -> MMAs ->

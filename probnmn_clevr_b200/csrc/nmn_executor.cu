@@ -1015,12 +1015,10 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
     // module the chain of its other input forks off.  The forked chain accumulates its share of d(feat) in a buffer of
     // its own (two concurrent read-modify-write streams into one buffer would race); the stem's backward adds the two.
     const int rb = bs.new_strand(n);
-    const int root_f = (par && bd.vals[out].strand >= 0) ? bd.vals[out].strand : st_f;
     int sec_f = -1, sec_b = -1;          // forward / backward strand of the forked chain
     int dfeat2_unit = -1;
     bool dfeat2_written = false;
     auto bstrand = [&](const OpRec& r) { return (par && r.strand == sec_f && sec_b >= 0) ? sec_b : rb; };
-    (void)root_f;
     // (pointer, written flag) of the d(feat) accumulator a backward strand uses
     auto dfeat_of = [&](int sb, bool*& written) -> float* {
       if (sb == sec_b && sec_b >= 0) {
