@@ -1220,8 +1220,19 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
     if (p.need_grad) bs.mark_critical(B, crit_bwd);
   }
   if (p.persistent) {
-    if (p.need_grad) bwd_flatten = std::thread([&] { bs.flatten_persistent(p.btask, p.bmeta, p.cfgs); });
-    fs.flatten_persistent(p.ftask, p.fmeta, p.cfgs);
+    static const bool plan_timing_f = std::getenv("PNMN_PLAN_TIMING") != nullptr;
+    if (p.need_grad) bwd_flatten = std::thread([&] {
+      const auto a = std::chrono::steady_clock::now();
+      bs.flatten_persistent(p.btask, p.bmeta, p.cfgs);
+      if (plan_timing_f) std::fprintf(stderr, "plan:   backward flatten (helper thread) %.2f ms\n",
+                                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count());
+    });
+    {
+      const auto a = std::chrono::steady_clock::now();
+      fs.flatten_persistent(p.ftask, p.fmeta, p.cfgs);
+      if (plan_timing_f) std::fprintf(stderr, "plan:   forward flatten %.2f ms\n",
+                                      std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - a).count());
+    }
   } else {
     fs.flatten(p.felt, p.fconv, p.flaunch);
   }
