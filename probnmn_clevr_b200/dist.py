@@ -53,13 +53,18 @@ class GradientOverlap:
 
     def __init__(self, params: Iterable[torch.nn.Parameter], group: Optional[dist.ProcessGroup] = None,
                  min_numel: int = 1, weight: float = 1.0):
+        """Gradients of at least ``min_numel`` elements start their own collective from the hook; smaller ones are only
+        collected there and travel TOGETHER in one flat buffer at ``finish`` (a collective costs the host 0.1-0.3 ms to
+        launch whatever its size, and the step is host-bound at eight processes per box)."""
         self.group = group
         self.weight = weight
+        self.min_numel = min_numel
         self._pending: List[Tuple[torch.Tensor, "dist.Work"]] = []
+        self._small: List[torch.Tensor] = []
         self._hooks = []
         self._avg: Optional[bool] = None
         for p in params:
-            if p.requires_grad and p.numel() >= min_numel:
+            if p.requires_grad:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
     def _op(self):
@@ -72,6 +77,9 @@ class GradientOverlap:
         g = p.grad
         if g is None or not dist.is_initialized():
             return
+        if g.numel() < self.min_numel:
+            self._small.append(g)
+            return
         if self.weight != 1.0:
             g.mul_(self.weight)
         self._pending.append((g, dist.all_reduce(g, op=self._op(), group=self.group, async_op=True)))
@@ -82,9 +90,16 @@ class GradientOverlap:
         every parameter.  Returns the number of collectives this step used."""
         world = dist.get_world_size(self.group)
         if buckets is None:
-            early = {g.data_ptr() for g, _ in self._pending}
+            early = {g.data_ptr() for g, _ in self._pending} | {g.data_ptr() for g in self._small}
             buckets = [b for b in gradient_buckets(models) if b.data_ptr() not in early]
+        else:
+            buckets = list(buckets)
         op = self._op()
+        # the small hooked gradients: one flat buffer, one collective, copied back afterwards
+        small, packed = self._small, None
+        if small:
+            packed = torch.cat([g.reshape(-1) for g in small])
+            buckets.append(packed)
         handles = []
         for b in buckets:
             if self.weight != 1.0:
@@ -98,8 +113,14 @@ class GradientOverlap:
             h.wait()
             if not self._avg:
                 b.div_(world)
+        if packed is not None:
+            off = 0
+            for g in small:
+                g.copy_(packed[off:off + g.numel()].view_as(g))
+                off += g.numel()
         n = len(self._pending) + len(buckets)
         self._pending = []
+        self._small = []
         return n
 
     def remove(self) -> None:

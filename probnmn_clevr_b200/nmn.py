@@ -740,7 +740,8 @@ class NeuralModuleNetwork(nn.Module):
 
         if self._grad_overlap is not None:
             self._grad_overlap.remove()
-        self._grad_overlap = GradientOverlap(self.classifier.parameters(), group=group)
+        # classifier.4.weight (51 M elements) gets its own early collective; the five small tensors share one at the end
+        self._grad_overlap = GradientOverlap(self.classifier.parameters(), group=group, min_numel=1 << 20)
 
     def get_metrics(self, reset: bool = True) -> Dict[str, float]:
         """``{"answer_accuracy", "average_invalid"}`` (nmn.py:277-296)."""

@@ -77,19 +77,22 @@ def _worker(rank, world, path, rows):
         twin = torch.nn.Sequential(torch.nn.Linear(4, 8), torch.nn.ReLU(), torch.nn.Linear(8, 1))
         twin.load_state_dict(net.state_dict())
         xs = torch.randn(6, 4)
-        overlap = GradientOverlap(net.parameters())
-        for _ in range(2):  # two steps: the pending list is cleared by finish()
-            net.zero_grad(set_to_none=True); twin.zero_grad(set_to_none=True)
-            net(xs).pow(2).mean().backward()
-            twin(xs).pow(2).mean().backward()
-            model.fake_backward(rank + 1)
-            used = overlap.finish([net, model])
-            assert used == 4 + 2, used      # 4 hooked tensors + the flat bucket + the plain tensor
-            allreduce_gradients([twin])
-            for p, q in zip(net.parameters(), twin.parameters()):
-                assert torch.allclose(p.grad, q.grad, atol=1e-7)
-            assert torch.allclose(model.a.grad, torch.full((5, 3), want))
-        overlap.remove()
+        for min_numel, n_coll in ((1, 4 + 2), (16, 1 + 1 + 2)):
+            # min_numel = 16: only the (8, 4) weight starts its own collective inside backward; the other three hooked
+            # tensors travel together in one flat buffer at finish()
+            overlap = GradientOverlap(net.parameters(), min_numel=min_numel)
+            for _ in range(2):  # two steps: the pending lists are cleared by finish()
+                net.zero_grad(set_to_none=True); twin.zero_grad(set_to_none=True)
+                net(xs).pow(2).mean().backward()
+                twin(xs).pow(2).mean().backward()
+                model.fake_backward(rank + 1)
+                used = overlap.finish([net, model])
+                assert used == n_coll, used      # hooked tensors (+ their flat buffer) + the flat bucket + the plain tensor
+                allreduce_gradients([twin])
+                for p, q in zip(net.parameters(), twin.parameters()):
+                    assert torch.allclose(p.grad, q.grad, atol=1e-7)
+                assert torch.allclose(model.a.grad, torch.full((5, 3), want))
+            overlap.remove()
     finally:
         dist.destroy_process_group()
 
