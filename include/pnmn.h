@@ -6,8 +6,13 @@
  * device pointers, sizes and a cudaStream_t — no torch types cross this boundary.  Every entry
  * point cites the reference code it replaces.  Conventions:
  *   - all functions returning int: 0 = ok, non-zero = error; pnmn_last_error() has the text
- *   - no device allocation happens inside the library: the caller owns every buffer (sizes are
- *     reported by pnmn_plan_sizes / pnmn_model_packed_floats)
+ *   - the product entry points allocate NO device memory: the caller owns every device buffer (sizes are reported by
+ *     pnmn_plan_sizes / pnmn_model_packed_floats / pnmn_pg_workspace_bytes).  What the library does own: a small pool of
+ *     page-locked HOST staging buffers for task tables (recycled, bounded) and, per device, one non-blocking side stream
+ *     with two events (bias gradients run underneath the weight-gradient kernel).  Only the pnmn_debug_* bring-up entry
+ *     points allocate (and free) device scratch of their own.
+ *   - every launch goes to the device that is current on the calling thread; the python layer makes the tensors'
+ *     device current around each call
  *   - no CPU fallback exists: without a CUDA device every compute entry point fails
  *   - thread safety: a plan/model is used by one thread at a time; different plans are independent
  */
@@ -197,6 +202,11 @@ int pnmn_debug_set_trace(void* device_buffer, int64_t capacity_tasks);
  * {type, n_deps, deps[10], conv: n_samp, n_mt, MMAs per accumulator, flags | elementwise: op, part, 0, 0};
  * returns the number of tasks (host only, no device work) */
 int64_t pnmn_debug_plan_meta(const pnmn_plan* p, int pass, int32_t* out, int64_t cap_tasks);
+/* attention maps (1-channel module outputs; probnmn/modules/nmn_modules.py:82-87,160-168,200-208 and the 1-channel results
+ * of And / Or, :25-27,43-45) of a plan, for parity tests: 4 int32 per record {sample, index of the module call inside the
+ * sample's program in execution order, token id, map unit}; after pnmn_nmn_forward map unit u is the top-left 14 x 14 block
+ * of the 16 x 16 fp32 grid at pnmn_buffers.maps + 256 * u.  Returns the number of records (host only). */
+int64_t pnmn_debug_plan_maps(const pnmn_plan* p, int32_t* out, int64_t cap_records);
 /* accumulated host-side milliseconds spent in {pnmn_plan_create, pnmn_nmn_forward, pnmn_nmn_backward} and the
  * number of plans created since the last call (reading clears) */
 int pnmn_debug_host_times(double* ms);

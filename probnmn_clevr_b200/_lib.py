@@ -97,7 +97,7 @@ EXPORTS = [
     "pnmn_plan_create", "pnmn_plan_destroy", "pnmn_plan_upload", "pnmn_plan_valid", "pnmn_plan_sizes", "pnmn_plan_stats",
     "pnmn_nmn_forward", "pnmn_nmn_backward", "pnmn_debug_launch_conv", "pnmn_debug_launch_wgrad",
     "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt", "pnmn_profile_enable",
-    "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times", "pnmn_debug_plan_meta",
+    "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times", "pnmn_debug_plan_meta", "pnmn_debug_plan_maps",
     "pnmn_split3_bf16", "pnmn_relu_pool_fwd", "pnmn_relu_pool_bwd", "pnmn_relu_pool_bwd_split", "pnmn_relu_pool_fwd_bias", "pnmn_split2_bf16", "pnmn_launch_count", "pnmn_pg_workspace_bytes", "pnmn_pg_forward", "pnmn_pg_backward", "pnmn_pg_debug_layout",
 ]
 
@@ -149,6 +149,8 @@ def lib() -> ctypes.CDLL:
     L.pnmn_debug_host_times.argtypes = [POINTER(ctypes.c_double)]
     L.pnmn_debug_plan_meta.restype = c_int64
     L.pnmn_debug_plan_meta.argtypes = [c_void_p, c_int, c_void_p, c_int64]
+    L.pnmn_debug_plan_maps.restype = c_int64
+    L.pnmn_debug_plan_maps.argtypes = [c_void_p, c_void_p, c_int64]
     L.pnmn_pg_workspace_bytes.restype = c_int64
     L.pnmn_pg_workspace_bytes.argtypes = [POINTER(PgDesc), c_int, c_int, c_int, c_int, c_int]
     L.pnmn_pg_forward.argtypes = [POINTER(PgDesc), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,

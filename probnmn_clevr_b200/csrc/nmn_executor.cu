@@ -540,14 +540,15 @@ struct pnmn_plan {
   std::vector<WgradTask> wtasks;
   std::vector<BiasGradTaskH> btasks;
   std::vector<int> xin_unit;  // per sample, -1 if the stem is skipped (invalid program)
+  std::vector<int32_t> map_trace;  // {sample, module call index, token, map unit} of every 1-channel module output
   bool persistent = true;     // one persistent executor launch per pass (exec.cu) vs one launch per level
   void* uploaded_to = nullptr;  // device buffer that already holds this plan's task tables (pnmn_plan_upload)
   std::vector<TaskRec> ftask, btask;
   std::vector<TaskMeta> fmeta, bmeta;
   int64_t off_ftask = 0, off_fmeta = 0, off_fsync = 0, off_btask = 0, off_bmeta = 0, off_bsync = 0;
   // blob layout (bytes)
-  int64_t off_cfg = 0, off_xin = 0, off_fconv = 0, off_felt = 0, off_bconv = 0, off_belt = 0, off_inst = 0, off_wt = 0,
-          off_bt = 0, blob_bytes = 0;
+  int64_t off_cfg = 0, off_xin = 0, off_pack = 0, off_fconv = 0, off_felt = 0, off_bconv = 0, off_belt = 0, off_inst = 0,
+          off_wt = 0, off_bt = 0, blob_bytes = 0;
   int64_t stats[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   std::vector<uint8_t> host_blob;   // level-by-level path only (resolved on the host)
   struct PinnedBlob* pin = nullptr;  // persistent path: unresolved records, resolved on the device after upload
@@ -868,9 +869,11 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
     const float* featp = bd.p16(feat_unit[n]);
 
     // ---------------- forward stages ----------------
+    int op_index = -1;
     for (OpRec& r : ops) {
       const ModuleDesc& md = m->mods[r.tok];
       n_tokens++;
+      ++op_index;
       // strand of this op's stages
       int sf = st_f;
       if (par) {
@@ -975,6 +978,10 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
           }
           if (!head) vo.unit = r.y_unit[r.nconv - 1];
         } break;
+      }
+      if (bd.vals[r.out].ch == 1) {
+        const int32_t rec[4] = {n, op_index, r.tok, bd.vals[r.out].unit};
+        p.map_trace.insert(p.map_trace.end(), rec, rec + 4);
       }
     }
     {
@@ -1315,6 +1322,8 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
   int64_t o = 0;
   p.off_cfg = o; o = align(o + static_cast<int64_t>(p.cfgs.size() * sizeof(ConvCfg)));
   p.off_xin = o; o = align(o + static_cast<int64_t>(B) * 8);
+  // the model's (static) weight-pack tasks travel with every plan: the library then owns no device memory at all
+  p.off_pack = o; o = align(o + static_cast<int64_t>(m->pack.size() * sizeof(PackTask)));
   p.off_fconv = o; o = align(o + static_cast<int64_t>(p.fconv.size() * sizeof(ConvTask)));
   p.off_felt = o; o = align(o + static_cast<int64_t>(p.felt.size() * sizeof(EltTask)));
   p.off_ftask = o; o = align(o + static_cast<int64_t>(p.ftask.size() * sizeof(TaskRec)));
@@ -1340,6 +1349,7 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
     uint8_t* hb = p.pin->p;
     auto put = [&](int64_t off, const void* src, size_t bytes) { if (bytes) std::memcpy(hb + off, src, bytes); };
     put(p.off_cfg, p.cfgs.data(), p.cfgs.size() * sizeof(ConvCfg));
+    put(p.off_pack, m->pack.data(), m->pack.size() * sizeof(PackTask));
     put(p.off_ftask, p.ftask.data(), p.ftask.size() * sizeof(TaskRec));
     put(p.off_fmeta, p.fmeta.data(), p.fmeta.size() * sizeof(TaskMeta));
     put(p.off_btask, p.btask.data(), p.btask.size() * sizeof(TaskRec));
@@ -1594,6 +1604,7 @@ extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const f
   const int64_t fwd_bytes = p.off_bconv;
   if (p.host_blob.size() < static_cast<size_t>(p.blob_bytes)) p.host_blob.resize(static_cast<size_t>(p.blob_bytes));
   std::memcpy(p.host_blob.data() + p.off_cfg, p.cfgs.data(), p.cfgs.size() * sizeof(ConvCfg));
+  std::memcpy(p.host_blob.data() + p.off_pack, m.pack.data(), m.pack.size() * sizeof(PackTask));
   {
     ConvTask* d = reinterpret_cast<ConvTask*>(p.host_blob.data() + p.off_fconv);
     for (size_t i = 0; i < p.fconv.size(); ++i) { d[i] = p.fconv[i]; resolve_conv(d[i], base); }
@@ -1612,18 +1623,11 @@ extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const f
   }
   CUDA_OK(cudaMemcpyAsync(bufs->blob, p.host_blob.data(), static_cast<size_t>(fwd_bytes), cudaMemcpyHostToDevice, st));
   }
-  // pack weights (tf32, MMA tile order): the packed buffer's head holds the pack-task table
+  // pack weights (fp16 MMA tile order); the pack-task table is part of the plan's blob (uploaded above)
   {
-    // pack tasks are static per model; upload them behind the packed floats is not possible (caller
-    // sized the buffer exactly), so they travel in a small persistent device allocation.
-    static std::map<const pnmn_model*, PackTask*> cache;
-    PackTask*& d_tasks = cache[&m];
-    if (!d_tasks) {
-      CUDA_OK(cudaMalloc(&d_tasks, m.pack.size() * sizeof(PackTask)));
-      CUDA_OK(cudaMemcpy(d_tasks, m.pack.data(), m.pack.size() * sizeof(PackTask), cudaMemcpyHostToDevice));
-    }
     ProfScope prof(PK_PACK, st);
-    CUDA_OK(launch_pack(d_tasks, static_cast<int>(m.pack.size()), m.total_tiles, bufs->params, bufs->packed, st));
+    CUDA_OK(launch_pack(reinterpret_cast<const PackTask*>(static_cast<const uint8_t*>(bufs->blob) + p.off_pack),
+                        static_cast<int>(m.pack.size()), m.total_tiles, bufs->params, bufs->packed, st));
   }
   fill_ones_map_kernel<<<1, 256, 0, st>>>(bufs->maps);
   // features -> planes for every valid sample
@@ -1727,6 +1731,15 @@ extern "C" int64_t pnmn_debug_plan_meta(const pnmn_plan* p, int pass, int32_t* o
       o[12] = t.op; o[13] = t.part; o[14] = 0; o[15] = 0;
     }
   }
+  return n;
+}
+
+// 1-channel module outputs (attention maps) of a plan: 4 int32 per record {sample, index of the module call inside the
+// sample's program (execution order, `scene` / skipped tokens not counted), token id, map unit}; map unit u lives at
+// pnmn_buffers.maps + 256 * u as a 16 x 16 grid whose top-left 14 x 14 block is the map.  Returns the record count.
+extern "C" int64_t pnmn_debug_plan_maps(const pnmn_plan* p, int32_t* out, int64_t cap_records) {
+  const int64_t n = static_cast<int64_t>(p->map_trace.size() / 4);
+  if (out) std::memcpy(out, p->map_trace.data(), static_cast<size_t>(std::min(n, cap_records)) * 4 * sizeof(int32_t));
   return n;
 }
 

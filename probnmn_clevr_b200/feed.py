@@ -18,7 +18,9 @@ import torch
 
 class DevicePrefetcher:
     """``submit(key, tensors)`` starts the asynchronous copies; ``get(key)`` makes the current stream wait for them.
-    The tensors returned by ``get`` stay valid until ``depth - 1`` further batches have been fetched."""
+    The tensors returned by ``get(i)`` belong to the caller until the NEXT ``get``: that call marks the slot as released
+    at the current point of the compute stream, so work enqueued on them BEFORE the next ``get`` is safe, work enqueued
+    after it races with a later ``submit`` that recycles the slot (``depth`` - 1 submits later)."""
 
     def __init__(self, device: torch.device, depth: int = 3):
         self.device = torch.device(device)

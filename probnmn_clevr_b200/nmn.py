@@ -308,9 +308,10 @@ class _ExecutorFn(torch.autograd.Function):
         grad_final = grad_final.contiguous()
         target, finish = model._attach_grads()
         run.bufs.grads = target.data_ptr()
-        stream = ctypes.c_void_p(torch.cuda.current_stream(grad_final.device).cuda_stream)
-        L.check(L.lib().pnmn_nmn_backward(run.plan, ctypes.byref(run.bufs), ctypes.c_void_p(grad_final.data_ptr()),
-                                          stream), "pnmn_nmn_backward")
+        with torch.cuda.device(grad_final.device):  # (the autograd thread's current device is not necessarily the tensors')
+            stream = ctypes.c_void_p(torch.cuda.current_stream(grad_final.device).cuda_stream)
+            L.check(L.lib().pnmn_nmn_backward(run.plan, ctypes.byref(run.bufs), ctypes.c_void_p(grad_final.data_ptr()),
+                                              stream), "pnmn_nmn_backward")
         if finish is not None:
             finish()
         run.close()
@@ -384,6 +385,9 @@ class NeuralModuleNetwork(nn.Module):
         self._grad_overlap = None
         self._upload_stream = None
         self._precompiled: list = []  # pending (programs, need_grad, future of a plan) entries, see precompile()
+        # parity tests: keep every 1-channel module output (attention map) of the last forward, see _read_attention_maps
+        self.capture_attention_maps = False
+        self.last_attention_maps = None
         # classifier GEMMs (plain library GEMMs, nmn.py:75-83): "split" (default) = every fp32 operand split into two bf16
         # halves (pnmn_split3_bf16, one pass), one cuBLAS tensor-core GEMM over the 3x contraction with fp32 accumulation
         # (~16 mantissa bits per operand); "ieee" = cuBLAS/cuDNN fp32 SIMT like the reference; "tf32" = 10-bit operands
@@ -523,6 +527,12 @@ class NeuralModuleNetwork(nn.Module):
         """
         if not features.is_cuda:
             raise RuntimeError("NeuralModuleNetwork (B200) needs CUDA tensors; there is no CPU fallback")
+        # the library launches on the calling thread's current device: make it the tensors' device (the reference's
+        # trainer only does ``model.to(f"cuda:{gpu_ids[0]}")``, trainers/_trainer.py:92-95, never set_device)
+        with torch.cuda.device(features.device):
+            return self._forward(features, programs, answers)
+
+    def _forward(self, features: torch.Tensor, programs: torch.Tensor, answers: Optional[torch.Tensor]):
         lib = L.lib()
         self._ensure_flat()
         features = features.contiguous().float()
@@ -569,6 +579,15 @@ class NeuralModuleNetwork(nn.Module):
         else:
             with torch.no_grad():
                 final = _ExecutorFn.forward(_NullCtx(), features, None, run, self)
+        # validity mask on the device: read from the plan's task tables (per-sample stem-input offset, < 0 = invalid) rather than
+        # uploaded -- a host -> device copy queued here would wait behind whatever the copy engine is doing (the next batch's
+        # 205 MB of features in a pipelined loop: 3.7 ms) and stall the whole stream.  Read BEFORE the run is closed: closing
+        # hands a pre-uploaded table buffer back to the pool, where a look-ahead compile may overwrite it.
+        xin_off = int(stats[15])
+        invalid = run.blob[xin_off:xin_off + 8 * B].view(torch.int64) < 0
+        if self.capture_attention_maps:
+            self.last_attention_maps = self._read_attention_maps(plan, ws)
+        if not need_grad:
             run.close()
 
         # classifier + loss (nmn.py:241-269); masking done on the device instead of CPU-tensor indexing
@@ -582,11 +601,6 @@ class NeuralModuleNetwork(nn.Module):
             answer_logits = self.classifier(final)
         answer_logprobs = F.log_softmax(answer_logits, dim=-1)
         best_logprobs, answer_predictions = torch.max(answer_logprobs, dim=1)
-        # validity mask on the device: read from the plan's task tables (per-sample stem-input offset, < 0 = invalid) rather than
-        # uploaded -- a host -> device copy queued here would wait behind whatever the copy engine is doing (the next batch's
-        # 205 MB of features in a pipelined loop: 3.7 ms) and stall the whole stream
-        xin_off = int(stats[15])
-        invalid = run.blob[xin_off:xin_off + 8 * B].view(torch.int64) < 0
         answer_predictions = answer_predictions.masked_fill(invalid, self._unknown_answer)
         if answers is not None:
             loss = F.cross_entropy(answer_logits, answers, reduction="none")
@@ -607,6 +621,22 @@ class NeuralModuleNetwork(nn.Module):
             output_dict["metrics"] = _LazyMetrics({"answer_accuracy": lambda: _Accuracy.value(acc_state),
                                                    "average_invalid": lambda: invalid_now})
         return output_dict
+
+    @staticmethod
+    def _read_attention_maps(plan, ws):
+        """[(sample, module call index, token id, (14, 14) tensor)] for every 1-channel module output of the forward pass
+        just launched (nmn_modules.py:82-87,160-168,200-208 and 1-channel And / Or results), read back from the map arena
+        through ``pnmn_debug_plan_maps``.  The module call index counts the modules the reference would call for that
+        sample in execution order (``scene`` and skipped tokens call none)."""
+        lib = L.lib()
+        n = int(lib.pnmn_debug_plan_maps(plan, None, 0))
+        rec = torch.zeros(max(n, 1), 4, dtype=torch.int32)
+        lib.pnmn_debug_plan_maps(plan, ctypes.c_void_p(rec.data_ptr()), n)
+        arena = ws.t["maps"]
+        grid = arena[: arena.numel() // 256 * 256].view(-1, 16, 16)
+        units = rec[:n, 3].to(torch.int64)
+        maps = grid[units.to(grid.device)][:, :14, :14].cpu() if n else torch.zeros(0, 14, 14)
+        return [(int(rec[i, 0]), int(rec[i, 1]), int(rec[i, 2]), maps[i]) for i in range(n)]
 
     # ---- program compiler -------------------------------------------------------------------------------------------
     def _compile(self, programs_host: torch.Tensor, need_grad: bool, device):

@@ -101,10 +101,11 @@ class _Seq2SeqFn(torch.autograd.Function):
         desc, B, Tq, Tp, S, teacher = run.args
         gflat = torch.zeros_like(flat)
         grad_loss = grad_loss.contiguous().float()
-        stream = ctypes.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream)
-        L.check(L.lib().pnmn_pg_backward(ctypes.byref(desc), ctypes.c_void_p(flat.data_ptr()), ctypes.c_void_p(gflat.data_ptr()),
-                                         ctypes.c_void_p(grad_loss.data_ptr()), B, Tq, Tp, S, teacher,
-                                         ctypes.c_void_p(run.ws.data_ptr()), stream), "pnmn_pg_backward")
+        with torch.cuda.device(flat.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(flat.device).cuda_stream)
+            L.check(L.lib().pnmn_pg_backward(ctypes.byref(desc), ctypes.c_void_p(flat.data_ptr()),
+                                             ctypes.c_void_p(gflat.data_ptr()), ctypes.c_void_p(grad_loss.data_ptr()), B, Tq, Tp,
+                                             S, teacher, ctypes.c_void_p(run.ws.data_ptr()), stream), "pnmn_pg_backward")
         run.close()
         grads = tuple(gflat[o:o + n].view(shape) for (o, n, shape) in ctx.slices)
         return (None, None, None, None) + grads
@@ -124,6 +125,8 @@ class Seq2SeqBase(nn.Module):
     dropout: float, optional (default = 0.0) -- only 0.0 is supported (all reference configs use 0.0)
     max_decoding_steps: int, optional (default = 30)
     """
+
+    _instances = 0
 
     def __init__(self, vocabulary, source_namespace: str, target_namespace: str, input_size: int = 256,
                  hidden_size: int = 256, num_layers: int = 2, dropout: float = 0.0, max_decoding_steps: int = 30):
@@ -165,6 +168,10 @@ class Seq2SeqBase(nn.Module):
         self._layout: Optional[List[Tuple[str, int, int, torch.Size]]] = None
         self._desc = None
         self._calls = 0
+        # per-instance salt of the sampling stream: construction order within the process (deterministic for a given script,
+        # unlike id(self)), so that two runs with the same torch.manual_seed draw the same samples
+        Seq2SeqBase._instances += 1
+        self._salt = Seq2SeqBase._instances
         self.return_logits = False   # tests: also return "logits" (B, steps, V) and "raw_predictions"
         self._metrics = {"loss_sum": 0.0, "loss_n": 0, "seq_correct": 0, "seq_n": 0, "recall_sum": 0.0, "recall_n": 0,
                          "bleu_match": Counter(), "bleu_total": Counter(), "bleu_pred_len": 0, "bleu_ref_len": 0}
@@ -219,6 +226,10 @@ class Seq2SeqBase(nn.Module):
             raise ValueError(f"decoding_strategy must be 'sampling' or 'greedy', got {decoding_strategy!r}")
         if not source_tokens.is_cuda:
             raise RuntimeError("Seq2SeqBase (B200) needs CUDA tensors; there is no CPU fallback")
+        with torch.cuda.device(source_tokens.device):  # the library launches on the thread's current device
+            return self._forward(source_tokens, target_tokens, decoding_strategy)
+
+    def _forward(self, source_tokens, target_tokens, decoding_strategy):
         lib = L.lib()
         self._ensure_flat()
         dev = source_tokens.device
@@ -244,7 +255,9 @@ class Seq2SeqBase(nn.Module):
         loss = torch.empty(B, dtype=torch.float32, device=dev)
         logits = torch.empty(B, S, self._vt, dtype=torch.float32, device=dev) if self.return_logits else None
         self._calls += 1
-        seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._calls * 0xD1B54A32D192ED03 + id(self) % 65521) % (1 << 64)
+        # Philox key of this call: (torch.manual_seed value, construction-order salt of the module, per-module call counter).
+        # The counter advances on EVERY forward (validation passes included), as the global generator does in the reference.
+        seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._calls * 0xD1B54A32D192ED03 + self._salt * 0x2545F4914F6CDD1D) % (1 << 64)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         L.check(lib.pnmn_pg_forward(
             ctypes.byref(self._desc), ctypes.c_void_p(self._flat.data_ptr()), ctypes.c_void_p(source.data_ptr()),

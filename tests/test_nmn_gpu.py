@@ -221,3 +221,152 @@ def test_precompile_lookahead_changes_nothing(model):
     # gradients: the weight-gradient kernels accumulate with atomics (order varies run to run), so equality is to rounding
     for g in (ghit, gmiss):
         assert float((g - gref).abs().max()) <= 1e-5 * float(gref.abs().max())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# attention maps (north_star: "within 1e-3 ... (answer logits, attention maps)")
+# ---------------------------------------------------------------------------------------------------------------------
+MAP_TOL = 1e-3   # max |a - b| over a map; maps are sigmoid outputs / min / max of such, i.e. values in [0, 1]
+
+
+def _captured_maps(model, programs, answers, feats, train):
+    model.capture_attention_maps = True
+    try:
+        out, box = _run(model, programs, answers, feats, train=train)
+        torch.cuda.synchronize()
+        return out, {(n, j): m for n, j, _tok, m in model.last_attention_maps}
+    finally:
+        model.capture_attention_maps = False
+        model.last_attention_maps = None
+
+
+@pytest.mark.parametrize("train", [True, False], ids=["train_plan", "eval_plan"])
+@pytest.mark.parametrize("name", ["semantic", "sampled"])
+def test_attention_maps_match_reference_golden(model, name, train):
+    """Every 1-channel module output (AttentionModule / RelateModule / SameModule outputs, 1-channel And / Or results:
+    nmn_modules.py:25-27,43-45,82-87,160-168,200-208) of the CUDA executor against the maps the VERBATIM reference produced
+    (forward hooks on its modules, oracle/make_golden.py), element-wise: max |a - b| <= 1e-3 on values in [0, 1]."""
+    g = np.load(GOLDEN)
+    programs = torch.from_numpy(g[f"{name}.programs"])
+    answers = torch.from_numpy(g[f"{name}.answers"])
+    feats = make_features(programs.shape[0], 0)
+    if train:
+        _, mine = _captured_maps(model, programs, answers, feats, True)
+    else:
+        with torch.no_grad():
+            _, mine = _captured_maps(model, programs, None, feats, False)
+    gold = g[f"{name}.attention_maps"]
+    assert len(gold) > 0 and len(mine) == len(gold), (len(mine), len(gold))
+    worst = 0.0
+    for row in gold:
+        key = (int(row[0]), int(row[1]))
+        assert key in mine, f"the executor produced no map for sample {key[0]}, module call {key[1]}"
+        worst = max(worst, float(np.abs(mine[key].numpy().reshape(-1) - row[2:]).max()))
+    print(f"[{name}/{'train' if train else 'eval'}] {len(gold)} attention maps, max |cuda - reference| = {worst:.2e}")
+    assert worst <= MAP_TOL
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# parity at the benchmarked configuration (bench.py: batch 256, programs <= 40 tokens, seeds 0 / 1 / 100)
+# ---------------------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("seed,length,rows", [(0, 40, 256), (1, 40, 256), (100, 40, 256), (0, 26, 128)],
+                         ids=["bench_seed0", "bench_seed1", "bench_rank1", "joint_128x26"])
+def test_bench_configuration_against_oracle(model, seed, length, rows):
+    """The batches bench.py times (pairing of samples, critical-sample splitting, strands and the dependency-slot
+    fallback only engage at this size): logits, module outputs, loss, validity and attention maps against the CPU oracle,
+    for the training plan (need_grad) and the evaluation plan (torch.no_grad)."""
+    vocab = model.vocabulary
+    programs = ProgramSampler(vocab, seed=seed).sample(256, length)[:rows]
+    feats, answers = make_features(rows, seed), make_answers(rows, seed)
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    torch.set_num_threads(os.cpu_count())
+    with torch.no_grad():
+        ref = nmn_oracle.nmn_forward(sd, vocab, feats, programs, answers, want=("traces",))
+    ref_maps = {(n, j): o[0, 0] for n, tr in enumerate(ref["traces"]) if int(ref["valid"][n]) == 1
+                for j, (_t, o) in enumerate(tr) if o.shape[1] == 1}
+    for train in (True, False):
+        if train:
+            out, mine = _captured_maps(model, programs, answers, feats, True)
+            box = None
+        else:
+            with torch.no_grad():
+                out, mine = _captured_maps(model, programs, answers, feats, False)
+        # _captured_maps ran _run, whose hook results are gone: run the classifier hook again on the same inputs
+        with torch.set_grad_enabled(train):
+            out2, box = _run(model, programs, answers, feats, train=train)
+        assert torch.equal(out["predictions"], out2["predictions"])
+        assert (out["predictions"].cpu() == 28).eq(ref["valid"] == 0).all()
+        e = _relmax(box["logits"].cpu().numpy(), ref["logits"].numpy())
+        ef = _relmax(box["final"].cpu().numpy(), ref["final"].numpy())
+        np.testing.assert_allclose(out["loss"].detach().cpu().numpy(), ref["loss"].numpy(), rtol=1e-3, atol=1e-3)
+        assert set(mine) == set(ref_maps)
+        em = max(float((mine[k] - ref_maps[k]).abs().max()) for k in ref_maps)
+        print(f"[seed {seed} L {length} B {rows} {'train' if train else 'eval'}] logits {e:.2e}  final {ef:.2e}  "
+              f"maps {em:.2e} ({len(ref_maps)} maps)  valid {int(ref['valid'].sum())}")
+        assert e < 1e-3 and ef < 1e-3 and em <= MAP_TOL
+        if train:
+            out2["loss"].mean().backward()   # releases the plan / workspace like a training step
+
+
+def test_precompile_under_no_grad_reads_its_own_validity_mask(model):
+    """Evaluation pipeline with look-ahead compiles: the validity mask of batch i must come from batch i's task
+    tables even when the helper thread is already uploading batch i+1's tables into a recycled buffer."""
+    vocab = model.vocabulary
+    sampler = ProgramSampler(vocab, seed=31)
+    batches = [torch.cat([sampler.sample(10, 26), sampler.garbage(6, 26)])[torch.randperm(16, generator=torch.Generator().manual_seed(k))]
+               for k in range(6)]
+    feats, answers = make_features(16, 9).cuda(), make_answers(16, 9).cuda()
+    model.eval()
+    sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    expect = [nmn_oracle.nmn_forward(sd, vocab, feats.cpu(), p, answers.cpu())["valid"] == 0 for p in batches]
+    with torch.no_grad():
+        for rounds in range(3):
+            model.precompile(batches[0], need_grad=False)
+            for i, p in enumerate(batches):
+                if i + 1 < len(batches):
+                    model.precompile(batches[i + 1], need_grad=False)
+                out = model(feats, p, answers)
+                assert torch.equal(out["predictions"].cpu() == 28, expect[i]), (rounds, i)
+                assert torch.equal(out["loss"].cpu() == 3.33, expect[i]), (rounds, i)
+    model.train()
+
+
+def test_backward_tighter_than_tf32_rounding_noise():
+    """He-initialised network (ReLU kinks and saturated heads included): the CUDA gradient must sit CLOSER to the
+    tf32-operand oracle than that oracle sits to the fp32 one -- i.e. whatever differs from the reference's fp32 gradient
+    is the operand precision north_star asks for (tensor cores), not an error of the backward pass.  Errors are relative
+    L2 norms, per tensor (tensors holding > 1 % of the largest tensor-gradient norm) and over the whole gradient."""
+    g = np.load(GOLDEN)
+    vocab = Vocabulary.clevr()
+    sd0 = make_nmn_state_dict(vocab, 0)
+    model = NeuralModuleNetwork(vocab)
+    model.load_state_dict(sd0)
+    model = model.cuda()
+    programs = torch.from_numpy(g["sampled.programs"])
+    answers = torch.from_numpy(g["sampled.answers"])
+    feats = make_features(programs.shape[0], 0)
+    out, box = _run(model, programs, answers, feats)
+    out["loss"].mean().backward()
+    torch.set_num_threads(os.cpu_count())
+
+    def oracle_grads(mode):
+        sd = {k: v.clone().requires_grad_(True) for k, v in sd0.items()}
+        with nmn_oracle.operand_rounding(mode):
+            ref = nmn_oracle.nmn_forward(sd, vocab, feats, programs, answers)
+            ref["loss"].mean().backward()
+        return {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in sd.items()}
+
+    g_tf32, g_fp32 = oracle_grads("tf32"), oracle_grads("fp32")
+    worst_c, l2_c = _grad_errors(model, g_tf32, verbose=False)
+
+    class _Holder:   # _grad_errors reads named_parameters() with .grad
+        def __init__(self, grads):
+            self.items = [(k, type("P", (), {"grad": v})()) for k, v in grads.items()]
+
+        def named_parameters(self):
+            return self.items
+    worst_o, l2_o = _grad_errors(_Holder(g_tf32), g_fp32, verbose=False)
+    print(f"He-init: cuda vs tf32 oracle: global {l2_c:.2e}, worst tensor {worst_c[0]:.2e} ({worst_c[1]}); "
+          f"tf32 oracle vs fp32 oracle: global {l2_o:.2e}, worst tensor {worst_o[0]:.2e} ({worst_o[1]})")
+    assert l2_c < l2_o, "the CUDA gradient is further from the tf32 oracle than tf32 rounding itself moves the gradient"
+    assert l2_c < 3e-2
