@@ -182,6 +182,44 @@ int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const int64_t* s
 int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, float* grads, const float* grad_loss, int batch, int tq,
                      int tp, int steps, int teacher, void* workspace, void* stream);
 
+/* ---- ProgramPrior (probnmn/models/program_prior.py:16-155): 2-layer LSTM language model over program tokens with tied
+ * input / output embeddings.  Offsets (in floats) name the reference's state-dict entries inside one flat fp32 buffer. */
+typedef struct pnmn_prior_desc {
+  int32_t vocab, hidden, num_layers, pad_;
+  int64_t embed;                              /* _embedder.token_embedder_programs.weight == _output_layer.weight (V,H) */
+  int64_t w_ih[2], w_hh[2], b_ih[2], b_hh[2]; /* _encoder._module.{weight,bias}_{ih,hh}_l{0,1}                          */
+  int64_t proj;                               /* _projection_layer.weight (input_size, hidden_size), no bias            */
+} pnmn_prior_desc;
+/* bytes of ZERO-FILLED device scratch for one forward; -1 on bad arguments */
+int64_t pnmn_prior_workspace_bytes(const pnmn_prior_desc* m, int batch, int length);
+/* ProgramPrior.forward (program_prior.py:80-155): programs: device int64 [batch][length] zero-padded WITHOUT boundary
+ * tokens.  Outputs (device): loss fp32 [batch] = teacher-forced sequence cross entropy of @start@ p_1..p_m @end@
+ * (sum over tokens / (count + 1e-13)), predictions int64 [batch][length + 1] = one categorical draw per position from
+ * the next-token distribution with pad / unk / start zeroed, times the mask (:119-139), logits fp32
+ * [batch][length + 1][vocab] (optional).  Forward only: in the joint-training step the prior is frozen and only feeds the
+ * REINFORCE reward (trainers/joint_training_trainer.py:107-112, modules/elbo.py:256). */
+int pnmn_prior_forward(const pnmn_prior_desc* m, const float* params, const int64_t* programs, int batch, int length,
+                       uint64_t seed, void* workspace, int64_t* predictions, float* loss, float* logits, void* stream);
+
+/* ---- optimiser side of the joint-training step ------------------------------------------------------------------------
+ * Element-wise gradient clamp to [-clamp, clamp] (trainers/joint_training_trainer.py:182-188; clamp <= 0 disables it)
+ * fused with one Adam step (torch.optim.Adam, amsgrad off, as built in trainers/_trainer.py:103-108 and stepped at :193)
+ * over n consecutive floats: params / grads / exp_avg / exp_avg_sq are 16-byte-aligned device arrays, `step` is the
+ * 1-based step count of these parameters.  write_clamped_grad != 0 also stores the clamped gradient (the reference clamps
+ * parameter.grad in place). */
+int pnmn_clamp_adam(float* params, float* grads, float* exp_avg, float* exp_avg_sq, int64_t n, int64_t step, double lr,
+                    double beta1, double beta2, double eps, double weight_decay, double clamp, int write_clamped_grad,
+                    void* stream);
+/* REINFORCE reward, moving-average baseline and ELBO scalars of modules/elbo.py in one launch, nothing leaves the device
+ * (the reference reads `centered_reward.mean().item()` every step, elbo.py:33).  Inputs: per-row losses (device fp32 [n];
+ * nmn_loss NULL = question coding, elbo.py:128-163).  mode 0 = "ours" (:256-275), 1 = "baseline" (:241-251).
+ * baseline: device fp32 [1], read then updated (b += decay * mean(reward - b)); centered: device fp32 [n] = reward - b
+ * (before the update); stats: device fp32 [5] = {reconstruction_likelihood, kl_divergence, elbo, reinforce_reward,
+ * mean nmn loss}. */
+int pnmn_elbo_glue(const float* pg_loss, const float* qr_loss, const float* prior_loss, const float* nmn_loss, int n,
+                   float beta, float gamma, float baseline_decay, int mode, float* baseline, float* centered, float* stats,
+                   void* stream);
+
 /* ---- bring-up entry points used by tests/ (kernel-level parity against torch) ---------------- */
 /* byte offsets of {encoder outputs, layer-0 h, layer-1 (+decoder) h, layer-1 c, decoder c, source table, target table,
  * attention probabilities, logits} inside a pnmn_pg workspace, then {state slot bytes, Ts, padded batch} */

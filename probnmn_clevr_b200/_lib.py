@@ -92,6 +92,16 @@ class PgDesc(Structure):
         ("out_w", c_int64), ("out_b", c_int64),
     ]
 
+class PriorDesc(Structure):
+    """pnmn_prior_desc (include/pnmn.h)."""
+    _fields_ = [
+        ("vocab", c_int32), ("hidden", c_int32), ("num_layers", c_int32), ("pad_", c_int32),
+        ("embed", c_int64),
+        ("w_ih", c_int64 * 2), ("w_hh", c_int64 * 2), ("b_ih", c_int64 * 2), ("b_hh", c_int64 * 2),
+        ("proj", c_int64),
+    ]
+
+
 EXPORTS = [
     "pnmn_version", "pnmn_last_error", "pnmn_model_create", "pnmn_model_destroy", "pnmn_model_packed_floats",
     "pnmn_plan_create", "pnmn_plan_destroy", "pnmn_plan_upload", "pnmn_plan_valid", "pnmn_plan_sizes", "pnmn_plan_stats",
@@ -99,6 +109,7 @@ EXPORTS = [
     "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt", "pnmn_profile_enable",
     "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times", "pnmn_debug_plan_meta", "pnmn_debug_plan_maps",
     "pnmn_split3_bf16", "pnmn_relu_pool_fwd", "pnmn_relu_pool_bwd", "pnmn_relu_pool_bwd_split", "pnmn_relu_pool_fwd_bias", "pnmn_split2_bf16", "pnmn_launch_count", "pnmn_pg_workspace_bytes", "pnmn_pg_forward", "pnmn_pg_backward", "pnmn_pg_debug_layout",
+    "pnmn_prior_workspace_bytes", "pnmn_prior_forward", "pnmn_clamp_adam", "pnmn_elbo_glue",
 ]
 
 
@@ -158,6 +169,15 @@ def lib() -> ctypes.CDLL:
     L.pnmn_pg_backward.argtypes = [POINTER(PgDesc), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p]
     L.pnmn_pg_debug_layout.argtypes = [POINTER(PgDesc), c_int, c_int, c_int, c_int, c_int, POINTER(c_int64)]
+    L.pnmn_prior_workspace_bytes.restype = c_int64
+    L.pnmn_prior_workspace_bytes.argtypes = [POINTER(PriorDesc), c_int, c_int]
+    L.pnmn_prior_forward.argtypes = [POINTER(PriorDesc), c_void_p, c_void_p, c_int, c_int, ctypes.c_uint64, c_void_p,
+                                     c_void_p, c_void_p, c_void_p, c_void_p]
+    c_double = ctypes.c_double
+    L.pnmn_clamp_adam.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_double, c_double, c_double,
+                                  c_double, c_double, c_double, c_int, c_void_p]
+    L.pnmn_elbo_glue.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_int,
+                                 c_void_p, c_void_p, c_void_p, c_void_p]
     L.pnmn_split3_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]
     L.pnmn_relu_pool_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
     L.pnmn_relu_pool_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]

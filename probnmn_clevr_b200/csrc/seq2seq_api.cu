@@ -64,8 +64,12 @@ Layout make_layout(const pnmn_pg_desc* m, int B, int Tq, int Tp, int S, bool nee
   L.slotdg = 2 * L.slotg;
   int64_t o = 0;
   auto take = [&](int64_t bytes) { const int64_t r = o; o += (bytes + 255) / 256 * 256; return r; };
-  const int64_t SB = static_cast<int64_t>(S) * B;
-  L.src = take(4ll * B * d.Ts); L.src_len = take(4ll * B); L.tgt = take(4ll * B * (Tp + 2));
+  // every size is a function of the PADDED batch (Bp) only: a caller whose batch size varies from call to call (the
+  // supervised / unsupervised split of the joint-training step) keeps one zero-filled workspace per padded size; the
+  // kernels index with the real B, the backward row kernels zero the gradient operands of the padding rows
+  const int64_t Bq = d.Bp;
+  const int64_t SB = static_cast<int64_t>(S) * Bq;
+  L.src = take(4ll * Bq * d.Ts); L.src_len = take(4ll * Bq); L.tgt = take(4ll * Bq * (Tp + 2));
   L.inp = take(4 * SB); L.pred = take(4 * SB); L.label = take(4 * SB);
   L.logp = take(4 * SB); L.lse = take(4 * SB); L.coef = take(4 * SB);
   L.logits = take(4 * SB * d.Vt); L.attn_p = take(4 * SB * d.Ts);
@@ -82,7 +86,7 @@ Layout make_layout(const pnmn_pg_desc* m, int B, int Tq, int Tp, int S, bool nee
   // layer 1 state slots 0..Ts, directly followed by the decoder's slots 1..S (decoder slot 0 IS layer-1 slot Ts)
   L.h1f = take(4 * L.slotf * (d.Ts + 1 + S)); L.c1f = take(4 * L.slotf * (d.Ts + 1));
   L.h1op = take(2 * L.slotop * (d.Ts + 1 + S));
-  L.enc = take(4ll * B * d.Ts * kSH);
+  L.enc = take(4ll * Bq * d.Ts * kSH);
   L.cdf = take(4 * L.slotf * (S + 1)); L.attop = take(2 * L.slotop * S);
   L.scale = take(256);
   if (need_grad) {
@@ -90,7 +94,7 @@ Layout make_layout(const pnmn_pg_desc* m, int B, int Tq, int Tp, int S, bool nee
     L.dlogits = take(4ll * S * d.Bp * d.Vt);
     L.dP0 = take(4ll * d.Vs * kSG); L.dPd = take(4ll * d.Vt * kSG); L.dP1 = take(4ll * kSG);
     L.dh = take(4 * L.slotf); L.dc = take(4 * L.slotf); L.datt = take(4 * L.slotf);
-    L.denc = take(4ll * B * d.Ts * kSH); L.dout0 = take(4 * L.slotf * d.Ts);
+    L.denc = take(4ll * Bq * d.Ts * kSH); L.dout0 = take(4 * L.slotf * d.Ts);
     L.dgd = take(2 * L.slotdg * S); L.dg1 = take(2 * L.slotdg * d.Ts); L.dg0 = take(2 * L.slotdg * d.Ts);
   }
   L.total = o;

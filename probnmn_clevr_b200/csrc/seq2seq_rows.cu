@@ -345,6 +345,21 @@ __global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a)
   const int t = a.t;
   pdl_launch_dependents();
   pdl_wait();
+  if (b >= d.B) {
+    // padding row of the 128-row tile: its gate-gradient operand and dlogits row are contracted over by the weight-gradient
+    // GEMMs, so they must be zero whatever an earlier, larger batch left there
+    if (t >= 0) {
+      if (tid < kSG / 8) {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        __half* op = a.dg_op + static_cast<size_t>(t) * a.dg_step;
+        const size_t off = op_off(b, tid * 8, kSG);
+        *reinterpret_cast<uint4*>(op + off) = z;
+        *reinterpret_cast<uint4*>(op + a.dg_lo + off) = z;
+      }
+      if (tid < d.Vt) a.dlogits[(static_cast<size_t>(t) * d.Bp + b) * d.Vt + tid] = 0.f;
+    }
+    return;
+  }
   float dh = a.dh[static_cast<size_t>(b) * kSH + tid];
   // dh / datt are accumulation targets of the next data-gradient GEMM (split-K partial sums): leave them zeroed
   if (t >= 0) a.dh[static_cast<size_t>(b) * kSH + tid] = 0.f;
@@ -419,7 +434,7 @@ __global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a)
   if (tid < kSG / 8) store_op8(a.dg_op + static_cast<size_t>(t) * a.dg_step, a.dg_lo, b, tid * 8, kSG, s_dg + tid * 8, a.scale[0]);
 }
 cudaError_t launch_dec_bwd_row(const DecBwdRowArgs& a, cudaStream_t st) {
-  return launch_pdl(dec_bwd_row_kernel, dim3(a.d.B), dim3(256), 0, st, seq_use_pdl(), a);
+  return launch_pdl(dec_bwd_row_kernel, dim3(a.d.Bp), dim3(256), 0, st, seq_use_pdl(), a);
 }
 
 // encoder: LSTM cell backward of one (layer, step); rows beyond their length carry dh / dc through unchanged
@@ -428,7 +443,7 @@ __global__ void __launch_bounds__(256) enc_cell_bwd_kernel(const EncCellBwdArgs 
   const int b = blockIdx.x, tid = threadIdx.x;
   pdl_launch_dependents();
   pdl_wait();
-  const bool valid = a.t < a.src_len[b];
+  const bool valid = b < a.B && a.t < a.src_len[b];   // (b >= B: padding row of the tile, zero gradient operand)
   float da[4] = {0.f, 0.f, 0.f, 0.f};
   if (valid) {
     float dh = a.dh[static_cast<size_t>(b) * kSH + tid];
@@ -445,7 +460,7 @@ __global__ void __launch_bounds__(256) enc_cell_bwd_kernel(const EncCellBwdArgs 
   if (tid < kSG / 8) store_op8(a.dg_op, a.dg_lo, b, tid * 8, kSG, s_dg + tid * 8, a.scale[0]);
 }
 cudaError_t launch_enc_cell_bwd(const EncCellBwdArgs& a, cudaStream_t st) {
-  return launch_pdl(enc_cell_bwd_kernel, dim3(a.B), dim3(256), 0, st, seq_use_pdl(), a);
+  return launch_pdl(enc_cell_bwd_kernel, dim3(a.Bp), dim3(256), 0, st, seq_use_pdl(), a);
 }
 
 // =====================================================================================================

@@ -1,0 +1,152 @@
+"""One iteration of the ``joint_training`` phase over the CUDA drop-ins.
+
+Mirrors the reference's ``_Trainer.step`` for this phase -- ``optimizer.zero_grad()`` (trainers/_trainer.py:193),
+``JointTrainingTrainer._do_iteration`` (trainers/joint_training_trainer.py:128-198: unsupervised rows through
+``JointTrainingElbo``, supervised rows teacher-forced through the program generator and the question reconstructor,
+``loss_objective.backward()``, element-wise gradient clamp) and ``optimizer.step()`` (:193) -- with the same objective,
+the same hyper-parameter names (ALPHA, BETA, GAMMA, DELTA, OBJECTIVE of the config) and the same returned dictionary.
+The trainer's data loading, logging, checkpointing and LR scheduling stay the reference's (out of scope).
+
+What is different is only HOW the work is issued:
+
+* the supervised / unsupervised split is taken on the host when ``batch["supervision"]`` is a host tensor (the reference
+  calls ``.nonzero()`` on the device: one synchronisation, joint_training_trainer.py:131-132);
+* independent passes run on separate CUDA streams: the teacher-forced passes over the supervised rows on one, the
+  question reconstructor + program prior over the sampled programs on another, while this thread compiles the sampled
+  programs for the module executor; autograd replays each pass on its own stream;
+* the gradient clamp is fused into the optimizer (``optim.FusedClampAdam``); with more than one process the gradients are
+  averaged over NCCL before it (clamp AFTER the reduction, as ``nn.DataParallel`` + ``clamp_`` does in the reference).
+"""
+from typing import Any, Dict, Optional
+
+import torch
+import torch.distributed as dist
+
+from .elbo import JointTrainingElbo
+from .optim import FusedClampAdam
+
+
+def split_batch(batch: Dict[str, torch.Tensor]) -> Dict[str, Dict[str, torch.Tensor]]:
+    """Host-side split of a reference-style batch (keys ``question``, ``answer``, ``program``, ``image``,
+    ``supervision``; probnmn/data/datasets.py:209-228) into the rows without program supervision (``"unsup"``: question,
+    image, answer) and the rows with it (``"sup"``: question, program) -- joint_training_trainer.py:131-138,160-161.
+    An input pipeline calls this BEFORE the host -> device copy: the features of supervised rows are never used by the
+    step, so half of the 205 MB batch does not have to travel."""
+    sup = batch["supervision"].to(torch.bool)
+    iu = (~sup).nonzero().flatten()
+    isup = sup.nonzero().flatten()
+    return {"unsup": {"question": batch["question"][iu], "image": batch["image"][iu], "answer": batch["answer"][iu]},
+            "sup": {"question": batch["question"][isup], "program": batch["program"][isup]}}
+
+
+class JointTrainingStep:
+    r"""
+    Parameters
+    ----------
+    program_generator, question_reconstructor, nmn: trained models (``probnmn_clevr_b200`` drop-ins), as in
+        ``JointTrainingTrainer.__init__`` (joint_training_trainer.py:81-105)
+    program_prior: frozen ``ProgramPrior`` (:107-112); put in ``eval()`` mode here
+    alpha, beta, gamma, delta, objective: ALPHA / BETA / GAMMA / DELTA / OBJECTIVE of the config
+        (configs/joint_training_ours.yml:6-16)
+    lr, weight_decay: OPTIM.LR_INITIAL / OPTIM.WEIGHT_DECAY (:18-25); clamp: the [-5, 5] gradient clamp (:187-188)
+    concurrent: issue independent passes on side streams (results do not depend on it)
+    group: process group for data-parallel gradient averaging (default group when ``torch.distributed`` is initialised)
+    """
+
+    def __init__(self, program_generator, question_reconstructor, nmn, program_prior, alpha: float = 100.0,
+                 beta: float = 0.1, gamma: float = 1.0, delta: float = 0.99, objective: str = "ours", lr: float = 1e-6,
+                 weight_decay: float = 0.0, clamp: Optional[float] = 5.0, concurrent: bool = True, group=None):
+        self.program_generator, self.question_reconstructor = program_generator, question_reconstructor
+        self.nmn, self.program_prior = nmn, program_prior
+        program_prior.eval()
+        self.alpha, self.gamma, self.objective = alpha, gamma, objective
+        self.elbo = JointTrainingElbo(program_generator, question_reconstructor, program_prior, nmn, beta=beta, gamma=gamma,
+                                      baseline_decay=delta, objective=objective, concurrent=concurrent)
+        trained = [program_generator, question_reconstructor, nmn]
+        # same parameter order as the reference's optimizer (trainers/_trainer.py:103-108: models in dict order)
+        params = [p for m in trained for p in m.parameters()]
+        self.optimizer = FusedClampAdam(params, lr=lr, weight_decay=weight_decay, clamp=clamp, modules=trained)
+        self.concurrent = concurrent
+        self.group = group
+        self._sup_stream: Optional[torch.cuda.Stream] = None
+        self.iteration = -1
+
+    @classmethod
+    def from_config(cls, config, program_generator, question_reconstructor, nmn, program_prior, **kw):
+        _C = config
+        return cls(program_generator, question_reconstructor, nmn, program_prior, alpha=_C.ALPHA, beta=_C.BETA,
+                   gamma=_C.GAMMA, delta=_C.DELTA, objective=_C.OBJECTIVE, lr=_C.OPTIM.LR_INITIAL,
+                   weight_decay=_C.OPTIM.WEIGHT_DECAY, **kw)
+
+    # ---- joint_training_trainer.py:128-198 ------------------------------------------------------------------------------
+    def do_iteration(self, batch: Dict[str, Any]) -> Dict[str, Any]:
+        if "unsup" in batch:
+            parts = batch
+        elif not batch["supervision"].is_cuda:
+            parts = split_batch(batch)
+        else:
+            sup = batch["supervision"]
+            isup, iu = sup.nonzero().flatten(), (1 - sup).nonzero().flatten()   # (device: synchronises, like the reference)
+            parts = {"unsup": {k: batch[k][iu] for k in ("question", "image", "answer")},
+                     "sup": {"question": batch["question"][isup], "program": batch["program"][isup]}}
+        un, su = parts["unsup"], parts["sup"]
+        dev = self.nmn.stem[0].weight.device
+        to = lambda t: t if t.device == dev else t.to(dev, non_blocking=True)
+        ours = self.objective == "ours"
+        main = torch.cuda.current_stream(dev)
+
+        sup_out = None
+        if ours:
+            q_sup, p_sup = to(su["question"]), to(su["program"])
+            if self.concurrent:
+                if self._sup_stream is None or self._sup_stream.device != dev:
+                    self._sup_stream = torch.cuda.Stream(dev)
+                side = self._sup_stream
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    sup_out = self._supervised(q_sup, p_sup)
+            # (sequential order otherwise: after the ELBO, as in the reference)
+
+        elbo_output_dict = self.elbo(to(un["question"]), to(un["image"]), to(un["answer"]))
+        nmn_loss = elbo_output_dict.pop("nmn_loss")
+        loss_objective = self.gamma * nmn_loss - elbo_output_dict["elbo"]
+
+        if ours:
+            if sup_out is None:
+                sup_out = self._supervised(q_sup, p_sup)
+            else:
+                main.wait_stream(self._sup_stream)
+                for t in sup_out:
+                    t.record_stream(main)
+            pg_sup, qr_sup = sup_out
+            loss_objective = loss_objective + self.alpha * (pg_sup + qr_sup)
+
+        loss_objective.backward()
+        # (clamp of every gradient to [-5, 5], :182-188: fused into self.optimizer.step())
+
+        out = {"loss": {"nmn": nmn_loss.detach()}, "elbo": {k: v.detach() for k, v in elbo_output_dict.items()}}
+        if ours:
+            out["loss"].update({"question_reconstruction_gt": qr_sup.detach(), "program_generation_gt": pg_sup.detach()})
+        out["objective"] = loss_objective.detach()
+        return out
+
+    def _supervised(self, questions, programs):
+        """alpha * (log q(z'|x') + log p(x'|z')) over the rows with ground-truth programs (:152-176)."""
+        pg = self.program_generator(questions, programs, decoding_strategy="sampling")
+        qr = self.question_reconstructor(programs, questions, decoding_strategy="sampling")
+        return pg["loss"].mean(), qr["loss"].mean()
+
+    def allreduce_gradients(self) -> None:
+        from .dist import allreduce_gradients
+        self.nmn.allreduce_gradients(group=self.group)
+        allreduce_gradients([self.program_generator, self.question_reconstructor], group=self.group)
+
+    def step(self, batch: Dict[str, Any]) -> Dict[str, Any]:
+        """``_Trainer.step`` (trainers/_trainer.py:172-196) without the dataloader / tensorboard parts."""
+        self.optimizer.zero_grad(set_to_none=True)
+        out = self.do_iteration(batch)
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            self.allreduce_gradients()
+        self.optimizer.step()
+        self.iteration += 1
+        return out

@@ -540,7 +540,14 @@ class NeuralModuleNetwork(nn.Module):
         # The program compiler runs on the host: programs that are already host tensors cost no synchronisation
         # (the reference accepts them too, it calls ``programs[n].cpu()``, nmn.py:203); device tensors cost the
         # forward's single D2H copy.
-        programs_host = programs.detach().to("cpu", torch.int64).contiguous()
+        handed = getattr(programs, "_pnmn_host", None)
+        if handed is not None and programs.is_cuda:
+            # produced by a Seq2SeqBase forward on this device: its pinned host copy is already on its way (seq2seq._handover);
+            # wait for THAT copy only instead of synchronising the compute stream (which may be busy with later work)
+            handed[1].synchronize()
+            programs_host = handed[0].clone()
+        else:
+            programs_host = programs.detach().to("cpu", torch.int64).contiguous()
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._exec_params)
         pre = self._take_precompiled(programs_host, need_grad)
         pre_blob = pre_event = None

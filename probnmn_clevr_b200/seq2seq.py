@@ -51,6 +51,7 @@ class _Workspaces:
         self.free: Dict[tuple, List[torch.Tensor]] = {}
         self.order: List[tuple] = []
         self.limit = limit
+        self.sizes: Dict[tuple, int] = {}
 
     def acquire(self, key, nbytes, device):
         lst = self.free.setdefault(key, [])
@@ -85,6 +86,64 @@ class _Run:
             self.close()
         except Exception:
             pass
+
+
+class _HostCopies:
+    """Pinned staging buffers + one copy stream per device for ``_handover``."""
+
+    def __init__(self):
+        self.streams: Dict[torch.device, torch.cuda.Stream] = {}
+        self.ring: Dict[torch.dtype, list] = {}   # dtype -> [items, next index]
+
+    def stream(self, device):
+        s = self.streams.get(device)
+        if s is None:
+            s = self.streams[device] = torch.cuda.Stream(device)
+        return s
+
+    def buffer(self, shape, dtype):
+        """Round-robin over 8 flat pinned buffers per dtype (grown on demand, viewed with the requested shape): a buffer is
+        overwritten only after 8 later hand-overs (two training steps), long after its reader -- which clones it -- is
+        done.  Keyed by dtype, not shape: the sub-batch sizes of the joint-training step change every step and page-locked
+        allocations cost milliseconds."""
+        numel = 1
+        for d in shape:
+            numel *= int(d)
+        ring = self.ring.setdefault(dtype, [[], 0])
+        items, nxt = ring
+        if len(items) < 8:
+            item = [torch.empty(max(numel, 1 << 15), dtype=dtype).pin_memory(), None, None]
+            items.append(item)
+        else:
+            item = items[nxt % 8]
+            ring[1] = nxt + 1
+            if item[1] is not None:
+                item[1].synchronize()
+            if item[0].numel() < numel:
+                item[0] = torch.empty(numel * 2, dtype=dtype).pin_memory()
+        item[2] = item[0][:numel].view(shape)
+        return item
+
+
+_HOST = _HostCopies()
+
+
+def _handover(tensor: torch.Tensor) -> None:
+    """Attach ``tensor._pnmn_host = (pinned copy, event)``: the copy runs on a side stream as soon as everything queued so
+    far on the current stream (the producing forward pass) is done, independent of what the caller queues next."""
+    dev = tensor.device
+    current = torch.cuda.current_stream(dev)
+    side = _HOST.stream(dev)
+    item = _HOST.buffer(tensor.shape, tensor.dtype)
+    ready = torch.cuda.Event()
+    ready.record(current)
+    side.wait_event(ready)
+    with torch.cuda.stream(side):
+        item[2].copy_(tensor, non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(side)
+    item[1] = done
+    tensor._pnmn_host = (item[2], done)
 
 
 class _Seq2SeqFn(torch.autograd.Function):
@@ -173,6 +232,10 @@ class Seq2SeqBase(nn.Module):
         Seq2SeqBase._instances += 1
         self._salt = Seq2SeqBase._instances
         self.return_logits = False   # tests: also return "logits" (B, steps, V) and "raw_predictions"
+        # start an asynchronous device -> pinned-host copy of "predictions" on a side stream right behind the forward pass:
+        # a NeuralModuleNetwork that is handed this tensor (modules/elbo.py:233-239, joint_training_evaluator.py:98-103)
+        # compiles the programs on the host and would otherwise synchronise the whole compute stream to read them
+        self.handover_predictions = True
         self._metrics = {"loss_sum": 0.0, "loss_n": 0, "seq_correct": 0, "seq_n": 0, "recall_sum": 0.0, "recall_n": 0,
                          "bleu_match": Counter(), "bleu_total": Counter(), "bleu_pred_len": 0, "bleu_ref_len": 0}
 
@@ -243,10 +306,16 @@ class Seq2SeqBase(nn.Module):
         else:
             target, Tp, S = None, 0, self._max_decoding_steps  # :177
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())
-        nbytes = lib.pnmn_pg_workspace_bytes(ctypes.byref(self._desc), B, Tq, Tp, S, 1 if need_grad else 0)
-        if nbytes < 0:
-            raise RuntimeError("pnmn_pg_workspace_bytes failed: " + lib.pnmn_last_error().decode())
-        key = (dev, B, Tq, Tp, S, need_grad, self._vs, self._vt)
+        # the workspace layout depends on the batch size only through its multiple of 128 (csrc/seq2seq_api.cu), so the
+        # varying sub-batch sizes of the joint-training step (supervised / unsupervised split) share zero-filled buffers
+        Bp = (B + 127) // 128 * 128
+        key = (dev, Bp, Tq, Tp, S, need_grad, self._vs, self._vt)
+        nbytes = _WS.sizes.get(key)
+        if nbytes is None:
+            nbytes = lib.pnmn_pg_workspace_bytes(ctypes.byref(self._desc), Bp, Tq, Tp, S, 1 if need_grad else 0)
+            if nbytes < 0:
+                raise RuntimeError("pnmn_pg_workspace_bytes failed: " + lib.pnmn_last_error().decode())
+            _WS.sizes[key] = nbytes
         ws = _WS.acquire(key, nbytes, dev)
         run = _Run(key, ws, (self._desc, B, Tq, Tp, S, 1 if teacher else 0))
 
@@ -273,6 +342,8 @@ class Seq2SeqBase(nn.Module):
         else:
             run.close()
 
+        if self.handover_predictions:
+            _handover(predictions)
         output_dict = {"predictions": predictions, "loss": loss}
         if self.return_logits:
             output_dict["logits"], output_dict["raw_predictions"] = logits, raw

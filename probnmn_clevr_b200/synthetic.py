@@ -198,3 +198,62 @@ def make_seq2seq_state_dict(vocab_src: int = 93, vocab_tgt: int = 44, hidden: in
     sd["_output_projection_layer.weight"] = u(vocab_tgt, hidden) * gain
     sd["_output_projection_layer.bias"] = u(vocab_tgt) * gain
     return sd
+
+
+# ------------------------------------------------------------------------------------------------
+# joint-training batches: questions that determine their programs, supervision flags, remaining weights
+# ------------------------------------------------------------------------------------------------
+def questions_for_programs(programs: torch.Tensor, vocab_size: int, seed: int = 0, max_length: int = 40) -> torch.Tensor:
+    """Synthetic questions ``(B, max_length)`` from which the program is recoverable, standing in for CLEVR's
+    question -> program mapping (no dataset in this environment): program token p at prefix position i becomes the
+    question word ``4 + 2 * (p - 4) + (i % 2)``, followed by 0..14 filler words from the top of the vocabulary (real
+    questions are longer than their programs' 'content').  Token ids stay below ``vocab_size``; 0 pads."""
+    rng = np.random.default_rng(5000 + seed)
+    prog = programs.numpy()
+    B = prog.shape[0]
+    content_top = 4 + 2 * 40
+    assert vocab_size > content_top + 1, "question vocabulary too small for the synthetic mapping"
+    out = np.zeros((B, max_length), dtype=np.int64)
+    for b in range(B):
+        toks = [int(p) for p in prog[b] if p != 0]
+        q = [4 + 2 * (p - 4) + (i % 2) for i, p in enumerate(toks)]
+        q += list(rng.integers(content_top, vocab_size, size=int(rng.integers(0, 15))))
+        q = q[:max_length]
+        out[b, : len(q)] = q
+    return torch.from_numpy(out)
+
+
+def make_joint_batch(vocabulary, batch: int, seed: int = 0, program_length: int = 26, question_length: int = 40,
+                     supervised_fraction: float = 0.5, with_images: bool = True) -> dict:
+    """A ``JointTrainingDataset`` batch (probnmn/data/datasets.py:209-228) of synthetic tensors on the host: ``question``
+    (B, 40), ``program`` (B, 26), ``answer`` (B,), ``image`` (B, 1024, 14, 14) fp32, ``supervision`` (B,) with
+    Bernoulli(0.5) flags (``SupervisionWeightedRandomSampler`` balances the two kinds, data/samplers.py:17-26)."""
+    programs = ProgramSampler(vocabulary, seed=seed).sample(batch, program_length)
+    rng = np.random.default_rng(6000 + seed)
+    return {
+        "question": questions_for_programs(programs, vocabulary.get_vocab_size("questions"), seed, question_length),
+        "program": programs,
+        "answer": make_answers(batch, seed),
+        "image": make_features(batch, seed) if with_images else None,
+        "supervision": torch.from_numpy((rng.random(batch) < supervised_fraction).astype(np.int64)),
+    }
+
+
+def make_prior_state_dict(vocab: int = 44, hidden: int = 256, seed: int = 0) -> "OrderedDict[str, torch.Tensor]":
+    """Reference-shaped ``ProgramPrior`` parameters (AllenNLP key names; the output layer is tied to the embedding,
+    program_prior.py:59-62) with PyTorch's default initialisations."""
+    g = torch.Generator().manual_seed(8000 + seed)
+    k = 1.0 / hidden ** 0.5
+    u = lambda *shape: (torch.rand(*shape, generator=g) * 2 - 1) * k
+    sd = OrderedDict()
+    emb = torch.randn(vocab, hidden, generator=g) * (2.0 / (vocab + hidden)) ** 0.5
+    emb[0] = 0
+    sd["_embedder.token_embedder_programs.weight"] = emb
+    for layer in range(2):
+        sd[f"_encoder._module.weight_ih_l{layer}"] = u(4 * hidden, hidden)
+        sd[f"_encoder._module.weight_hh_l{layer}"] = u(4 * hidden, hidden)
+        sd[f"_encoder._module.bias_ih_l{layer}"] = u(4 * hidden)
+        sd[f"_encoder._module.bias_hh_l{layer}"] = u(4 * hidden)
+    sd["_projection_layer.weight"] = u(hidden, hidden)
+    sd["_output_layer.weight"] = emb
+    return sd
