@@ -1,17 +1,24 @@
 #!/usr/bin/env python
-"""Benchmark of the hot path named by BASELINE.json: the Neural Module Network executor, forward + backward.
+"""Benchmark of the hot path named by BASELINE.json: one joint_training iteration (joint_training_ours.yml) at batch 256
+per GPU -- ProgramGenerator sampling -> QuestionReconstructor + NeuralModuleNetwork + ProgramPrior on the SAMPLED
+programs -> REINFORCE / ELBO objective + the supervised terms -> backward -> gradient clamp -> Adam.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload joint|executor]
 
-Workload (BASELINE.json configs[1]): module_training.yml at batch 256 per GPU, synthetic 14x14x1024 features
-and ground-truth-style CLEVR programs (seeded grammar, <= 40 tokens), reference-shaped random-init weights.
-One step = NeuralModuleNetwork.forward(features, programs, answers) + loss.mean().backward() through the
-public nn.Module API (program compilation on the host included); N > 1 adds the gradient all-reduce (NCCL).
+Workload "joint" (default; BASELINE.json configs[3], configs[4] at N = 8): synthetic JointTrainingDataset batches
+(questions <= 40 tokens that determine their programs, 14x14x1024 features, answers, Bernoulli(0.5) supervision flags),
+reference-shaped weights (He-normal module network, default-initialised reconstructor / prior, a program generator
+pre-trained on the synthetic question -> program mapping: the config starts from checkpoints, and a random-init generator
+samples programs the executor cannot run).  One step = probnmn_clevr_b200.joint.JointTrainingStep.step: what
+JointTrainingTrainer.step does per batch (trainers/_trainer.py:172-196, joint_training_trainer.py:128-198); N > 1 adds the
+NCCL gradient average before the clamp.
+Workload "executor" (BASELINE.json configs[1]): NeuralModuleNetwork forward + backward on ground-truth-style programs of
+up to 40 tokens; reported under "extra" in the default run.
 
-Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM, `e2e` with pinned host
-inputs copied in and the loss read back every step.  `roofline` is the tcgen05 conv kernel (the dominant
-kernel) timed with CUDA events around every launch; `cpu_baseline` is the CPU oracle (a port of the
-reference's PyTorch path) on a bounded sample.  `--impl reference` times that CPU path alone.
+Prints ONE JSON line (rank 0).  `value` is measured with inputs resident in HBM, `e2e` with pinned host inputs copied in
+and the objective read back every step.  `roofline` is the persistent tcgen05 executor kernel (the dominant kernel) timed
+with CUDA events around every launch; `cpu_baseline` is the CPU oracle port of the same step on a bounded sample.
+`--impl reference` times that CPU path alone.
 """
 import argparse
 import ctypes
@@ -27,8 +34,12 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "questions/sec (NMN executor fwd+bwd, batch 256 per GPU)"
+METRIC = "questions/sec (joint_training fwd+bwd, batch 256 per GPU)"
+METRIC_EXECUTOR = "questions/sec (NMN executor fwd+bwd, batch 256 per GPU)"
 UNIT = "questions/s"
+PG_ASSET = os.path.join(ROOT, "probnmn_clevr_b200", "assets", "pg_synthetic_fp16.npz")
+# configs/joint_training_ours.yml:6-25
+JOINT = dict(alpha=100.0, beta=0.1, gamma=1.0, delta=0.99, objective="ours", lr=1e-6, weight_decay=0.0, clamp=5.0)
 
 
 def parse():
@@ -37,15 +48,16 @@ def parse():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="joint", choices=["joint", "executor"])
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--length", type=int, default=40)
-    ap.add_argument("--cpu-sample", type=int, default=16, help="rows of the workload the CPU baseline runs")
+    ap.add_argument("--cpu-sample", type=int, default=32, help="rows of the workload the CPU baseline runs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-extras", action="store_true", help="skip the secondary ProgramGenerator / joint-step legs")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary legs (executor-only, ProgramGenerator)")
     return ap.parse_args()
 
 
-def workload_config(args):
+def executor_config(args):
     return {
         "workload": "module_training.yml batch=256/GPU: NMN stem + module executor + classifier, fwd+bwd "
                     "(BASELINE.json configs[1])",
@@ -98,9 +110,9 @@ def run_reference(args):
     value = rows * steps / dt
     sample = f"{rows} rows of the batch-{args.batch} workload per step, fwd+bwd, {steps} steps"
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "impl": "reference", "metric": METRIC_EXECUTOR, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
         "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": workload_config(args),
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": executor_config(args),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -169,13 +181,9 @@ class ClockSampler(threading.Thread):
 # ---------------------------------------------------------------------------------------------------------
 # ours
 # ---------------------------------------------------------------------------------------------------------
-def run_ours(args):
+def init_ours():
+    """process group / device of this rank (one process per GPU)"""
     import torch.distributed as dist
-    from probnmn_clevr_b200 import _lib as L
-    from probnmn_clevr_b200.nmn import NeuralModuleNetwork
-    from probnmn_clevr_b200.synthetic import ProgramSampler, make_answers, make_features, make_nmn_state_dict
-    from probnmn_clevr_b200.vocabulary import Vocabulary
-
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -187,6 +195,56 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
     torch.backends.cudnn.allow_tf32 = False  # classifier stays fp32, as in the reference
     torch.backends.cuda.matmul.allow_tf32 = False
+    return {"world": world, "rank": rank, "local": local, "dev": dev}
+
+
+def make_timed(ctx):
+    import torch.distributed as dist
+    world, dev = ctx["world"], ctx["dev"]
+
+    def timed(fn, steps, finish=None):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        t_host = time.perf_counter()
+        for i in range(steps):
+            fn(i)
+        if finish is not None:
+            finish()
+        timed.host_issue_ms = (time.perf_counter() - t_host) * 1e3  # host time to ISSUE the steps (no device sync inside)
+        b.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([a.elapsed_time(b)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms)
+    return timed
+
+
+def load_peaks():
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        peaks = {}
+    peak = peaks.get("bf16_tflops_sustained", 1590.0)
+    src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1590 (of fallback)"
+    return peak, src, peaks
+
+
+def run_executor(args, ctx, extra=False):
+    """BASELINE.json configs[1]: the module executor alone (stem + modules + classifier, forward + backward, no optimizer)
+    on ground-truth-style programs.  The default run reports it under "extra"."""
+    import torch.distributed as dist
+    from probnmn_clevr_b200 import _lib as L
+    from probnmn_clevr_b200.nmn import NeuralModuleNetwork
+    from probnmn_clevr_b200.synthetic import ProgramSampler, make_answers, make_features, make_nmn_state_dict
+    from probnmn_clevr_b200.vocabulary import Vocabulary
+
+    world, rank, local, dev = ctx["world"], ctx["rank"], ctx["local"], ctx["dev"]
 
     vocab = Vocabulary.clevr()
     model = NeuralModuleNetwork(vocab)
@@ -216,26 +274,7 @@ def run_ours(args):
             model.allreduce_gradients()
         return loss
 
-    def timed(fn, steps, finish=None):
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        t_host = time.perf_counter()
-        for i in range(steps):
-            fn(i)
-        if finish is not None:
-            finish()
-        timed.host_issue_ms = (time.perf_counter() - t_host) * 1e3  # host time to ISSUE the steps (no device sync inside)
-        b.record()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ms = torch.tensor([a.elapsed_time(b)], device=dev)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms)
+    timed = make_timed(ctx)
 
     lookahead = os.environ.get("PNMN_NO_PRECOMPILE") is None  # diagnostics: compile every plan inline
 
@@ -435,19 +474,12 @@ def run_ours(args):
     conv_flops = stats[8] + stats[10]  # forward + dgrad FLOPs executed by conv_tc<2,2> per step
     conv_ms = kernel_ms["conv_tc<2,2>"]
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
-    extras = {} if args.no_extras else extra_legs(args, model, vocab, dev, resident, timed)
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = peaks.get("bf16_tflops_sustained", 1590.0)
-    peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (of measured)" if peaks else "fallback 1590 (of fallback)"
+    peak, peak_src, _ = load_peaks()
 
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC_EXECUTOR, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 8), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": workload_config(args),
+        "vs_baseline": None, "dtype": "f16", "data": "synthetic", "config": executor_config(args),
         "clocks": sampler.summary(),
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                 "ms_per_step": ms_e2e / args.steps,
@@ -470,7 +502,11 @@ def run_ours(args):
         "classifier_math": {"split": "split bf16 x2 (one cuBLAS tensor-core GEMM over the 3x contraction, fp32 accumulate)",
                             "tf32": "tf32 (cuBLAS/cuDNN)", "ieee": "ieee fp32 (cuBLAS/cuDNN)"}[model.classifier_math],
     }
-    line.update(extras)
+    model._drop_precompiled()
+    if extra:
+        return line
+    if not args.no_extras:
+        line["pg"] = pg_leg(args, ctx, vocab, timed)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         torch.set_num_threads(os.cpu_count())
         rows = args.cpu_sample
@@ -483,10 +519,7 @@ def run_ours(args):
             best = min(best, time.perf_counter() - t0)
         line["cpu_baseline"] = {"value": rows / best, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                                 "sample": f"{rows} rows of the same batch, fwd+bwd, best of 2 after 1 warm-up"}
-    if rank == 0:
-        print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    return line
 
 
 def traffic_per_launch():
@@ -499,12 +532,11 @@ def traffic_per_launch():
         return None
 
 
-def extra_legs(args, nmn, vocab, dev, resident, timed):
-    """Secondary numbers (not the headline): BASELINE.json configs[2] (ProgramGenerator, question_coding mix) and
-    configs[3] (joint step: ProgramGenerator sampling + NMN + REINFORCE-weighted objective) at the same batch."""
+def pg_leg(args, ctx, vocab, timed):
+    """BASELINE.json configs[2]: ProgramGenerator alone on the question_coding "ours" mix."""
     from probnmn_clevr_b200.seq2seq import ProgramGenerator
     from probnmn_clevr_b200.synthetic import ProgramSampler, make_questions, make_seq2seq_state_dict
-    B = args.batch
+    B, dev = args.batch, ctx["dev"]
     pg = ProgramGenerator(vocab)
     pg.load_state_dict(make_seq2seq_state_dict(vocab.get_vocab_size("questions"), vocab.get_vocab_size("programs"), seed=0))
     pg = pg.to(dev).train()
@@ -519,37 +551,385 @@ def extra_legs(args, nmn, vocab, dev, resident, timed):
         uns = pg(questions[half:], decoding_strategy="sampling")
         (sup["loss"].mean() + uns["loss"].mean()).backward()
 
-    def joint_step(i):
-        # modules/elbo.py:230-275 restricted to the hot path: sample programs, answer with the NMN, REINFORCE the
-        # generator with the (detached) answer log-likelihood.  A random-init generator samples mostly invalid
-        # programs, so the NMN runs the batch's ground-truth-style programs (what a trained generator emits).
-        feats, programs, answers = resident[i % 2]
-        pg.zero_grad(set_to_none=True)
-        nmn.zero_grad(set_to_none=True)
-        gen = pg(questions, decoding_strategy="sampling")
-        out = nmn(feats, programs, answers)
-        reward = (-out["loss"]).detach()
-        objective = out["loss"].mean() + (gen["loss"] * (reward - reward.mean())).mean()
-        objective.backward()
+    for i in range(3):
+        pg_step(i)
+    steps = max(3, min(args.steps, 10))
+    ms = timed(pg_step, steps)
+    return {"value": ctx["world"] * B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "workload": ("question_coding_ours.yml mix at batch %d: %d rows teacher-forced + %d rows sampled (26 steps), "
+                         "questions <= 40 tokens, fwd+bwd (BASELINE.json configs[2])" % (B, half, B - half))}
 
+
+# ---------------------------------------------------------------------------------------------------------
+# the joint_training iteration (headline)
+# ---------------------------------------------------------------------------------------------------------
+def joint_config(args, world):
+    return {
+        "workload": "joint_training_ours.yml batch=256/GPU: ProgramGenerator sampling -> QuestionReconstructor + NeuralModuleNetwork "
+                    "+ ProgramPrior on the sampled programs, REINFORCE/ELBO + supervised terms, backward, clamp, Adam "
+                    "(BASELINE.json configs[3]; configs[4] at 8 GPUs)",
+        "batch_per_gpu": args.batch, "questions": "<= 40 tokens, synthetic, determine their programs",
+        "programs": "sampled by the ProgramGenerator (26 decoding steps); ground-truth programs (<= 26 tokens) on supervised rows",
+        "features": [1024, 14, 14], "supervision": "Bernoulli(0.5) per row (SupervisionWeightedRandomSampler balances the two kinds)",
+        "hyper": JOINT,
+        "weights": "module network He-normal seed 0; reconstructor / prior default init; program generator pre-trained on the "
+                   "synthetic question->program mapping (probnmn_clevr_b200/assets/pg_synthetic_fp16.npz, scripts/pretrain_pg.py)",
+        "l2": "inputs larger than L2 (~103 MB of features per step, two alternating batches)",
+        "parallelism": f"dp{world}",
+    }
+
+
+def load_pg_asset():
+    import numpy as np
+    if not os.path.exists(PG_ASSET):
+        raise SystemExit(f"{PG_ASSET} is missing (scripts/pretrain_pg.py writes it)")
+    z = np.load(PG_ASSET)
+    return {k: torch.from_numpy(z[k].astype("float32")) for k in z.files}
+
+
+def joint_state_dicts(vocab):
+    from probnmn_clevr_b200.synthetic import make_nmn_state_dict, make_prior_state_dict, make_seq2seq_state_dict
+    vq, vp = vocab.get_vocab_size("questions"), vocab.get_vocab_size("programs")
+    return {"program_generator": load_pg_asset(), "question_reconstructor": make_seq2seq_state_dict(vp, vq, seed=1),
+            "nmn": make_nmn_state_dict(vocab, 0), "program_prior": make_prior_state_dict(vp, seed=0)}
+
+
+def run_joint(args, ctx):
+    import numpy as np
+    import torch.distributed as dist
+    from probnmn_clevr_b200 import _lib as L
+    from probnmn_clevr_b200.feed import DevicePrefetcher
+    from probnmn_clevr_b200.joint import JointTrainingStep, split_batch
+    from probnmn_clevr_b200.nmn import NeuralModuleNetwork
+    from probnmn_clevr_b200.program_prior import ProgramPrior
+    from probnmn_clevr_b200.seq2seq import ProgramGenerator, QuestionReconstructor
+    from probnmn_clevr_b200.synthetic import make_joint_batch
+    from probnmn_clevr_b200.vocabulary import Vocabulary
+
+    world, rank, local, dev = ctx["world"], ctx["rank"], ctx["local"], ctx["dev"]
+    torch.manual_seed(0)
+    vocab = Vocabulary.clevr()
+    sds = joint_state_dicts(vocab)
+    models = {}
+    for name, cls in (("program_generator", ProgramGenerator), ("question_reconstructor", QuestionReconstructor),
+                      ("nmn", NeuralModuleNetwork), ("program_prior", ProgramPrior)):
+        m = cls(vocab)
+        m.load_state_dict(sds[name])
+        models[name] = m.to(dev).train()
+    if world > 1 and os.environ.get("PNMN_NO_GRAD_OVERLAP") is None:
+        models["nmn"].enable_gradient_overlap()
+    js = JointTrainingStep(models["program_generator"], models["question_reconstructor"], models["nmn"],
+                           models["program_prior"], concurrent=os.environ.get("PNMN_NO_STREAMS") is None, **JOINT)
+    nmn = models["nmn"]
+
+    # two alternating batches per rank, split on the host the way an input pipeline would (joint.split_batch), pinned
+    KEYS = (("unsup", "question"), ("unsup", "image"), ("unsup", "answer"), ("sup", "question"), ("sup", "program"))
+    host = []
+    for i in range(2):
+        parts = split_batch(make_joint_batch(vocab, args.batch, seed=100 * rank + i))
+        host.append([parts[a][b].contiguous().pin_memory() for a, b in KEYS])
+    as_parts = lambda ts: {"unsup": {"question": ts[0], "image": ts[1], "answer": ts[2]}, "sup": {"question": ts[3], "program": ts[4]}}
+    resident = [as_parts([t.to(dev) for t in h]) for h in host]
+    timed = make_timed(ctx)
+
+    run_ahead = [torch.cuda.Event() for _ in range(3)]
+    issued = {"n": 0, "wait_s": 0.0}
+
+    def throttle():   # the host runs at most two steps ahead of the device (see run_executor)
+        k = issued["n"]
+        if k >= 2:
+            t0 = time.perf_counter()
+            run_ahead[(k - 2) % 3].synchronize()
+            issued["wait_s"] += time.perf_counter() - t0
+
+    plan_flops = {"n": 0, "flops": 0, "valid": 0, "convs": 0, "tokens": 0, "unsup": 0}
+
+    def account():
+        st = nmn.last_plan_stats
+        plan_flops["n"] += 1
+        plan_flops["flops"] += st[8] + st[10]
+        plan_flops["valid"] += st[0]; plan_flops["convs"] += st[1]; plan_flops["tokens"] += st[2]
+
+    def resident_step(i):
+        throttle()
+        out = js.step(resident[i % 2])
+        account()
+        run_ahead[issued["n"] % 3].record()
+        issued["n"] += 1
+        return out
+
+    # ---- warm-up, then a parity check of what is about to be timed: the module network's per-row losses on the programs the
+    # generator just sampled, against the CPU oracle, on a 16-row slice
+    W = max(args.warmup, 3)
+    for i in range(W):
+        resident_step(i)
+    torch.cuda.synchronize()
+    parity = None
+    if rank == 0:
+        from oracle import nmn_oracle
+        last = js.elbo.last_outputs
+        rows = min(16, last["nmn"]["loss"].shape[0])
+        b = resident[(W - 1) % 2]["unsup"]
+        sd_now = {k: v.detach().cpu() for k, v in nmn.state_dict().items()}
+        torch.set_num_threads(os.cpu_count())
+        with torch.no_grad():
+            ref = nmn_oracle.nmn_forward(sd_now, vocab, b["image"][:rows].cpu(), last["program_generator"]["predictions"][:rows].cpu(),
+                                         b["answer"][:rows].cpu())
+        mine = last["nmn"]["loss"][:rows].detach().cpu()
+        err = float((mine - ref["loss"]).abs().max())
+        same_valid = bool(torch.equal(last["nmn"]["predictions"][:rows].cpu() == 28, ref["valid"] == 0))
+        parity = {"rows": rows, "max_abs_nmn_loss_err_vs_oracle": err, "validity_identical": same_valid,
+                  "valid_in_slice": int(ref["valid"].sum())}
+        assert same_valid and err < 5e-3, f"bench parity check failed: {parity}"
+
+    import gc
+    gc.collect()
+    gc.freeze()
+    lib = L.lib()
+    host_ms = (ctypes.c_double * 4)()
+    lib.pnmn_debug_host_times(host_ms)
+    sampler = ClockSampler(local)
+    sampler.start()
+    lib.pnmn_launch_count(1)
+    issued["wait_s"] = 0.0
+    for k in plan_flops:
+        plan_flops[k] = 0
+    ms = timed(resident_step, args.steps)
+    host_issue_ms = timed.host_issue_ms - issued["wait_s"] * 1e3
+    own_launches = int(lib.pnmn_launch_count(1))
+    sampler.stop_flag = True
+    lib.pnmn_debug_host_times(host_ms)
+    host_ms_per_step = {"plan_create": host_ms[0] / args.steps, "issue_total": host_issue_ms / args.steps,
+                        "run_ahead_wait": issued["wait_s"] * 1e3 / args.steps}
+    per_step = {k: plan_flops[k] / max(plan_flops["n"], 1) for k in ("valid", "convs", "tokens")}
+    unsup_rows = sum(h[0].shape[0] for h in host) / 2
+
+    # ---- end to end: pinned host inputs -> device on a side stream, objective read back every step (one step later)
+    feed = DevicePrefetcher(dev, depth=3)
+    n_slots = args.steps + W + 8
+    loss_host = torch.zeros(n_slots, dtype=torch.float32).pin_memory()
+    loss_events = [torch.cuda.Event() for _ in range(n_slots)]
+    loss_values = []
+    total = {"n": 0}
+
+    def read_loss(i):
+        loss_events[i].synchronize()
+        loss_values.append(float(loss_host[i]))
+
+    def e2e_step(i):
+        if i == 0:
+            feed.submit(0, host[0])
+        ts = feed.get(i)
+        if i + 1 < total["n"]:
+            feed.submit(i + 1, host[(i + 1) % 2])
+        out = js.step(as_parts(ts))
+        loss_host[i:i + 1].copy_(out["objective"].reshape(1), non_blocking=True)
+        loss_events[i].record()
+        if i >= 1:
+            read_loss(i - 1)
+
+    total["n"] = W + args.steps
+    for i in range(W):
+        e2e_step(i)
+    loss_values.clear()
+    ms_e2e = timed(lambda j: e2e_step(W + j), args.steps, lambda: read_loss(total["n"] - 1))
+    assert len(loss_values) == args.steps + 1 and all(v == v for v in loss_values), "every step's objective must have been read back"
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(3):
+        resident[0]["unsup"]["image"].copy_(host[0][1], non_blocking=True)
+    ev1.record()
+    torch.cuda.synchronize()
+    h2d_ms = ev0.elapsed_time(ev1) / 3
+
+    # ---- per-kernel device time of a few profiled steps (CUDA events around the library's launches, same stream)
+    prof_steps = min(args.steps, 5)
+    kinds = ["elementwise", "exec_kernel", "conv_tc<1,3>", "wgrad_tc", "bias_grad", "pack_weights", "nchw_to_planes", "other"]
+    for k in plan_flops:
+        plan_flops[k] = 0
+    lib.pnmn_profile_enable(1)
+    for i in range(prof_steps):
+        resident_step(i)
+    pms, pln = (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)()
+    lib.pnmn_profile_read(pms, pln)
+    lib.pnmn_profile_enable(0)
+    kernel_ms = {k: pms[i] / prof_steps for i, k in enumerate(kinds) if pms[i] > 0}
+    conv_flops = plan_flops["flops"] / prof_steps
+    conv_ms = pms[1] / prof_steps
+    achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    peak, peak_src, _ = load_peaks()
+
+    # ---- phases of the step, each timed alone on the device (diagnostics for DESIGN.md; not part of `value`)
+    phases = joint_phases(js, resident, timed) if not args.no_extras else None
+
+    value = world * args.batch * args.steps / (ms * 1e-3)
+    e2e_value = world * args.batch * args.steps / (ms_e2e * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f16", "data": "synthetic", "config": joint_config(args, world), "clocks": sampler.summary(),
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                "ms_per_step": ms_e2e / args.steps, "h2d_copy_alone_ms": h2d_ms,
+                "pipeline": "input pipeline splits the batch on the host (joint.split_batch: features of supervised rows are not "
+                            "needed by the step) into pinned buffers; the copy of step i+1 runs on a side stream during step i "
+                            "(feed.DevicePrefetcher); every step's objective is copied to pinned host memory and read one step later"},
+        "gpu_launches": own_launches,
+        "roofline": {
+            "bound": "tensor", "kernel": "exec_kernel (persistent tcgen05 kind::f16 shift-GEMM executor: forward + dgrad launches)",
+            "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "peak_source": peak_src,
+            "note": "fp16 operands, fp32 accumulation in TMEM; peak is the bf16 cuBLAS figure; the kernel's time includes its "
+                    "CUDA-core tasks and dependency waits; M is padded 196 -> 256 rows per sample (ceiling 0.766 of peak)",
+            "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms, "launches_per_step": pln[1] / prof_steps,
+            "m_padding_ceiling": 196.0 / 256.0, "traffic": traffic_per_launch(),
+        },
+        "kernel_ms_per_step": kernel_ms, "host_ms_per_step": host_ms_per_step,
+        "programs_per_step": {"unsupervised_rows": unsup_rows, "executable": per_step["valid"],
+                              "conv3x3_instances": per_step["convs"], "module_tokens": per_step["tokens"]},
+        "optimizer_launches_per_step": js.optimizer.launches_last_step,
+        "parity_check": parity, "phases_ms": phases,
+        "classifier_math": "split bf16 x2 (library tensor-core GEMMs over the 3x contraction, fp32 accumulate)",
+    }
+    if not args.no_extras:
+        sub = argparse.Namespace(**vars(args))
+        sub.steps = max(5, min(args.steps, 30))
+        ex = run_executor(sub, ctx, extra=True)
+        line["extra"] = {"executor": {k: ex[k] for k in ("metric", "value", "ms_per_step", "steps", "e2e", "roofline", "kernel_ms_per_step", "host_ms_per_step", "plan")},
+                         "pg": pg_leg(args, ctx, vocab, timed)}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_joint_baseline(args, best_of=2)
+    return line
+
+
+def joint_phases(js, resident, timed):
+    """device time of the step's parts run one after the other on ONE stream (no overlap), forward + backward each"""
+    pg, qr, nmn, prior = js.program_generator, js.question_reconstructor, js.nmn, js.program_prior
+    b = resident[0]
+    un, su = b["unsup"], b["sup"]
+    with torch.no_grad():
+        programs = pg(un["question"], decoding_strategy="sampling")["predictions"]
     res = {}
-    for name, fn in (("pg", pg_step), ("joint", joint_step)):
-        for i in range(3):
-            fn(i)
-        steps = max(3, min(args.steps, 10))
-        ms = timed(fn, steps)
-        world = int(os.environ.get("WORLD_SIZE", "1"))
-        res[name] = {"value": world * B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps}
-    res["pg"]["workload"] = ("question_coding_ours.yml mix at batch %d: %d rows teacher-forced + %d rows sampled (26 steps), "
-                             "questions <= 40 tokens, fwd+bwd (BASELINE.json configs[2])" % (B, half, B - half))
-    res["joint"]["workload"] = ("joint step at batch %d: ProgramGenerator sampling fwd+bwd + NMN fwd+bwd on GT-style programs + "
-                                "REINFORCE-weighted objective (BASELINE.json configs[3] restricted to the hot path)" % B)
+
+    def run(name, fn, steps=10):
+        for _ in range(2):
+            fn(0)
+        res[name] = timed(fn, steps) / steps
+
+    def pg_unsup(i):
+        pg.zero_grad(); pg(un["question"], decoding_strategy="sampling")["loss"].mean().backward()
+
+    def qr_unsup(i):
+        qr.zero_grad(); qr(programs, un["question"], decoding_strategy="sampling")["loss"].mean().backward()
+
+    def pg_sup(i):
+        pg.zero_grad(); pg(su["question"], su["program"], decoding_strategy="sampling")["loss"].mean().backward()
+
+    def qr_sup(i):
+        qr.zero_grad(); qr(su["program"], su["question"], decoding_strategy="sampling")["loss"].mean().backward()
+
+    def nmn_fb(i):
+        nmn.zero_grad(); nmn(un["image"], programs, un["answer"])["loss"].mean().backward()
+
+    def prior_f(i):
+        with torch.no_grad():
+            prior(programs)
+
+    def opt(i):
+        js.optimizer.step()
+
+    run("program_generator_sampling_fwd_bwd", pg_unsup); run("question_reconstructor_unsup_fwd_bwd", qr_unsup)
+    run("program_generator_supervised_fwd_bwd", pg_sup); run("question_reconstructor_supervised_fwd_bwd", qr_sup)
+    run("nmn_fwd_bwd", nmn_fb); run("program_prior_fwd", prior_f)
+    js.optimizer.zero_grad(); js.do_iteration(b)
+    run("clamp_adam", opt)
     return res
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU path of the joint step (oracle ports): cpu_baseline and --impl reference
+# ---------------------------------------------------------------------------------------------------------
+def cpu_joint_setup(args, rows):
+    from oracle import joint_oracle
+    from probnmn_clevr_b200.synthetic import make_joint_batch
+    from probnmn_clevr_b200.vocabulary import Vocabulary
+    vocab = Vocabulary.clevr()
+    sds = {name: {k: v.clone().requires_grad_(name != "program_prior") for k, v in sd.items()}
+           for name, sd in joint_state_dicts(vocab).items()}
+    sds["program_prior"]["_output_layer.weight"] = sds["program_prior"]["_embedder.token_embedder_programs.weight"]
+    batch = {k: v[:rows] for k, v in make_joint_batch(vocab, args.batch, seed=0).items()}
+    opt = torch.optim.Adam(joint_oracle.trained_parameters(sds), lr=JOINT["lr"], weight_decay=JOINT["weight_decay"])
+    state = joint_oracle.ElboState()
+    gen = torch.Generator().manual_seed(0)
+
+    def step():
+        opt.zero_grad()
+        out = joint_oracle.joint_iteration(sds, vocab, batch, state, alpha=JOINT["alpha"], beta=JOINT["beta"], gamma=JOINT["gamma"],
+                                           delta=JOINT["delta"], objective=JOINT["objective"], generator=gen)
+        joint_oracle.clamp_and_step(sds, opt, JOINT["clamp"])
+        return out
+    return step, batch
+
+
+def cpu_joint_baseline(args, best_of=2):
+    torch.set_num_threads(os.cpu_count())
+    rows = args.cpu_sample
+    step, batch = cpu_joint_setup(args, rows)
+    step()
+    best = 1e30
+    for _ in range(best_of):
+        t0 = time.perf_counter()
+        out = step()
+        best = min(best, time.perf_counter() - t0)
+    return {"value": rows / best, "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{rows} rows of the batch-{args.batch} workload ({int(batch['supervision'].sum())} supervised), one full joint "
+                      f"iteration (fwd+bwd+clamp+Adam) on the CPU oracle ports, best of {best_of} after 1 warm-up; "
+                      f"{int(out['rows']['nmn_valid'].sum())} of {len(out['rows']['nmn_valid'])} sampled programs executable"}
+
+
+def run_reference_joint(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    torch.set_num_threads(os.cpu_count())
+    rows = args.cpu_sample
+    step, batch = cpu_joint_setup(args, rows)
+    warm = min(args.warmup, 1)
+    for _ in range(warm):
+        step()
+    steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = rows * steps / dt
+    sample = (f"{rows} rows of the batch-{args.batch} workload per step ({int(batch['supervision'].sum())} supervised), full joint "
+              f"iteration on the CPU oracle ports (fwd+bwd+clamp+Adam), {steps} steps")
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": joint_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    ctx = init_ours()
+    if args.workload == "joint":
+        line = run_joint(args, ctx)
+    else:
+        line = run_executor(args, ctx)
+    if ctx["rank"] == 0:
+        print(json.dumps(line))
+    if ctx["world"] > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
     a = parse()
     if a.impl == "reference":
-        run_reference(a)
+        run_reference_joint(a) if a.workload == "joint" else run_reference(a)
     else:
         run_ours(a)

@@ -67,6 +67,12 @@ class JointTrainingStep:
         params = [p for m in trained for p in m.parameters()]
         self.optimizer = FusedClampAdam(params, lr=lr, weight_decay=weight_decay, clamp=clamp, modules=trained)
         self.concurrent = concurrent
+        if concurrent:
+            # passes on side streams accumulate into parameters whose AccumulateGrad node lives on another stream: intended
+            try:
+                torch.autograd.graph.set_warn_on_accumulate_grad_stream_mismatch(False)
+            except AttributeError:
+                pass
         self.group = group
         self._sup_stream: Optional[torch.cuda.Stream] = None
         self.iteration = -1

@@ -35,7 +35,7 @@ class _Range:
         self.exp_avg: Optional[torch.Tensor] = None
         self.exp_avg_sq: Optional[torch.Tensor] = None
         self.step = 0
-        self.step_tensor: Optional[torch.Tensor] = None   # shared "step" entry of every parameter while the counts agree
+        self.synced = True   # the per-parameter "step" tensors of the optimizer state agree with self.step
         self.pflat: Optional[torch.Tensor] = None
         self.uniform = True
         self.calls = 0
@@ -130,12 +130,22 @@ class FusedClampAdam(torch.optim.Optimizer):
                 r.step = max(steps)
                 r.uniform = len(steps) == 1
                 r.pflat = r.flat(r.params)
-                if r.uniform:   # one shared counter object: a step then costs one increment, not one per parameter
-                    r.step_tensor = torch.tensor(float(r.step))
-                    for p in r.params:
-                        self.state[p]["step"] = r.step_tensor
         self._ranges = groups
         self._range_key = self._layout_key()
+
+    def _sync_steps(self, r: _Range) -> None:
+        if not r.synced:
+            for p in r.params:
+                self.state[p]["step"].fill_(float(r.step))
+            r.synced = True
+
+    def state_dict(self):
+        """``torch.optim.Adam``'s format.  While a range is stepped as a whole its step count is kept once; the
+        per-parameter ``"step"`` entries are refreshed here (read ``optimizer.state`` through this method)."""
+        for ranges in self._ranges or []:
+            for r in ranges:
+                self._sync_steps(r)
+        return super().state_dict()
 
     def load_state_dict(self, state_dict):
         super().load_state_dict(state_dict)
@@ -169,12 +179,10 @@ class FusedClampAdam(torch.optim.Optimizer):
                                                     r.numel, r.step, lr, b1, b2, eps, wd, self.clamp,
                                                     1 if self.write_clamped_grad else 0, stream), "pnmn_clamp_adam")
                         launches += 1
-                        r.step_tensor += 1
+                        r.synced = False   # (the 222 per-parameter "step" tensors are brought up to date on demand)
                         continue
                     # per-tensor launches (gradients not in one flat buffer, some missing, or unequal step counts)
-                    if r.uniform:
-                        for p in r.params:   # the counts may diverge from here on: one counter per parameter again
-                            self.state[p]["step"] = torch.tensor(float(r.step))
+                    self._sync_steps(r)
                     r.uniform = False
                     for p, grad in zip(r.params, grads):
                         if grad is None:
@@ -195,9 +203,6 @@ class FusedClampAdam(torch.optim.Optimizer):
                     steps = {int(self.state[p]["step"]) for p in r.params}
                     if len(steps) == 1:
                         r.uniform, r.step = True, steps.pop()
-                        r.step_tensor = torch.tensor(float(r.step))
-                        for p in r.params:
-                            self.state[p]["step"] = r.step_tensor
         self.launches_last_step = launches
         return loss
 
