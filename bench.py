@@ -661,8 +661,12 @@ def run_joint(args, ctx):
     # ---- warm-up, then a parity check of what is about to be timed: the module network's per-row losses on the programs the
     # generator just sampled, against the CPU oracle, on a 16-row slice
     W = max(args.warmup, 3)
-    for i in range(W):
+    for i in range(W - 1):
         resident_step(i)
+    # (weights as the last warm-up step sees them: its optimizer update moves every weight by ~lr along sign(gradient), which
+    # shifts the logits by ~1e-2 -- the oracle must run on the weights the forward pass used)
+    sd_now = {k: v.detach().cpu().clone() for k, v in nmn.state_dict().items()} if rank == 0 else None
+    resident_step(W - 1)
     torch.cuda.synchronize()
     parity = None
     if rank == 0:
@@ -670,7 +674,6 @@ def run_joint(args, ctx):
         last = js.elbo.last_outputs
         rows = min(16, last["nmn"]["loss"].shape[0])
         b = resident[(W - 1) % 2]["unsup"]
-        sd_now = {k: v.detach().cpu() for k, v in nmn.state_dict().items()}
         torch.set_num_threads(os.cpu_count())
         with torch.no_grad():
             ref = nmn_oracle.nmn_forward(sd_now, vocab, b["image"][:rows].cpu(), last["program_generator"]["predictions"][:rows].cpu(),

@@ -76,17 +76,20 @@ T* at(void* ws, int64_t off) { return reinterpret_cast<T*>(static_cast<uint8_t*>
 
 // tokens: [B][T] zero-padded -> [B][T+2] = @start@ p_1..p_m @end@ 0..  (AllenNLP add_sentence_boundary_token_ids,
 // program_prior.py:104-107); len[b] = m + 2 (the LSTM runs over the whole boundary-added sequence, :112-117)
-__global__ void prior_tokens_kernel(const int64_t* __restrict__ programs, int B, int T, int V, int* __restrict__ tok,
-                                    int* __restrict__ len) {
+__global__ void prior_tokens_kernel(const int64_t* __restrict__ programs, int B, int rows, int T, int V,
+                                    unsigned long long seed, unsigned long long* __restrict__ seed_out,
+                                    int* __restrict__ tok, int* __restrict__ len) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) seed_out[0] = seed;
   if (b >= B) return;
+  const bool real = b < rows;   // padding rows of the last 128-row tile: empty programs, never read back
   const int Ts = T + 2;
   int m = 0;
-  for (int s = 0; s < T; ++s) m += programs[static_cast<size_t>(b) * T + s] != kPad;
+  for (int s = 0; real && s < T; ++s) m += programs[static_cast<size_t>(b) * T + s] != kPad;
   int* row = tok + static_cast<size_t>(b) * Ts;
   row[0] = kStart;
   for (int s = 0; s < T; ++s) {
-    const int64_t v = programs[static_cast<size_t>(b) * T + s];
+    const int64_t v = real ? programs[static_cast<size_t>(b) * T + s] : 0;
     row[1 + s] = (v < 0 || v >= V) ? 1 : static_cast<int>(v);
   }
   row[T + 1] = kPad;
@@ -128,7 +131,7 @@ __device__ __forceinline__ float philox_uniform(unsigned long long seed, uint32_
 // categorical prediction (:119-137).  grid = (T + 1, B); 4 warps, warp w handles vocabulary entries w, w+4, ...
 __global__ void __launch_bounds__(128) prior_head_kernel(const float* __restrict__ enc, const float* __restrict__ fold,
                                                          const int* __restrict__ tok, int B, int Ts, int V,
-                                                         unsigned long long seed, float* __restrict__ nll,
+                                                         const unsigned long long* __restrict__ seed_ptr, float* __restrict__ nll,
                                                          int64_t* __restrict__ predictions, float* __restrict__ logits_out) {
   __shared__ float sh[kSH], slg[kSMaxV], sp[kSMaxV];
   const int t = blockIdx.x, b = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -164,7 +167,7 @@ __global__ void __launch_bounds__(128) prior_head_kernel(const float* __restrict
     // multinomial over softmax with pad / unk / start zeroed, then "* mask" (:139)
     float total = 0.f;
     for (int v = kStart + 1; v < V; ++v) total += sp[v];
-    const float u = philox_uniform(seed, static_cast<uint32_t>(b), static_cast<uint32_t>(t)) * total;
+    const float u = philox_uniform(seed_ptr[0], static_cast<uint32_t>(b), static_cast<uint32_t>(t)) * total;
     float cum = 0.f;
     int pred = V - 1;
     for (int v = kStart + 1; v < V; ++v) {
@@ -195,7 +198,7 @@ __global__ void prior_loss_kernel(const float* __restrict__ nll, const int* __re
 extern "C" int64_t pnmn_prior_workspace_bytes(const pnmn_prior_desc* m, int batch, int length) {
   if (check(m, batch, length)) return -1;
   const PriorLayout L = prior_layout(m, batch, length);
-  return L.total + 4ll * L.Bp * (L.Ts - 1) + 256;   // + per-position nll
+  return L.total + 4ll * L.Bp * (L.Ts - 1) + 256;   // + per-position nll + the Philox key
 }
 
 extern "C" int pnmn_prior_forward(const pnmn_prior_desc* m, const float* params, const int64_t* programs, int batch,
@@ -209,8 +212,13 @@ extern "C" int pnmn_prior_forward(const pnmn_prior_desc* m, const float* params,
   __half* packed = at<__half>(ws, L.packed);
   float* nll = at<float>(ws, L.total);
 
-  prior_tokens_kernel<<<(L.B + 127) / 128, 128, 0, st>>>(programs, L.B, L.T, L.V, at<int>(ws, L.tok), at<int>(ws, L.len));
+  unsigned long long* seed_dev = reinterpret_cast<unsigned long long*>(nll + static_cast<size_t>(L.Bp) * (L.Ts - 1));
+  prior_tokens_kernel<<<(L.Bp + 127) / 128, 128, 0, st>>>(programs, L.Bp, L.B, L.T, L.V, seed, seed_dev, at<int>(ws, L.tok),
+                                                          at<int>(ws, L.len));
   CUDA_OK(cudaGetLastError());
+  // the LSTM over whole 128-row tiles: one CUDA graph per (workspace, parameters, shape), see seq2seq_api.cu
+  GraphKey key{ws, params, 0, 4, L.Bp, L.T, 0, 0, 0, 0, 0, L.V, L.V};
+  const int rc = run_graphed_pass(key, st, [&](cudaStream_t st) -> int {
   {
     PackJobs J;
     std::memset(&J, 0, sizeof(J));
@@ -242,7 +250,7 @@ extern "C" int pnmn_prior_forward(const pnmn_prior_desc* m, const float* params,
   }
   GemmArgs g;
   std::memset(&g, 0, sizeof(g));
-  g.B = L.B; g.chunks_per_src = 4; g.a_K[0] = g.a_K[1] = kSH; g.a_lo[0] = g.a_lo[1] = L.slotf; g.h_op_lo = L.slotf;
+  g.B = L.Bp; g.chunks_per_src = 4; g.a_K[0] = g.a_K[1] = kSH; g.a_lo[0] = g.a_lo[1] = L.slotf; g.h_op_lo = L.slotf;
   g.out_op_lo = L.slotf;
   g.len = at<int>(ws, L.len);
   for (int t = 0; t < L.Ts; ++t) {   // layer 0
@@ -269,8 +277,11 @@ extern "C" int pnmn_prior_forward(const pnmn_prior_desc* m, const float* params,
     g.out_op = nullptr;
     CUDA_OK(launch_step_gemm(g, EPI_LSTM, kSG / 64, MT, false, st));
   }
+    return 0;
+  });
+  if (rc) return rc;
   prior_head_kernel<<<dim3(L.Ts - 1, L.B), 128, 0, st>>>(at<float>(ws, L.enc), at<float>(ws, L.fold), at<int>(ws, L.tok), L.B,
-                                                         L.Ts, L.V, seed, nll, predictions, logits_out);
+                                                         L.Ts, L.V, seed_dev, nll, predictions, logits_out);
   CUDA_OK(cudaGetLastError());
   prior_loss_kernel<<<(L.B + 127) / 128, 128, 0, st>>>(nll, at<int>(ws, L.tok), L.B, L.Ts, loss);
   CUDA_OK(cudaGetLastError());

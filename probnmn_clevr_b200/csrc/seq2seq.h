@@ -147,8 +147,10 @@ struct SeqDims {
 };
 
 // token preparation (AllenNLP add_sentence_boundary_token_ids + seq2seq_base.py:128-141)
-cudaError_t launch_prepare_tokens(const int64_t* source, const int64_t* target, SeqDims d, int* src, int* src_len,
-                                  int* tgt, cudaStream_t st);
+// d.B rows are prepared; rows >= `rows` (padding up to the tile size) become empty sequences.  Also stores the call's
+// Philox key in device memory (seed_out), so that the launches that follow do not depend on it (CUDA graph replay).
+cudaError_t launch_prepare_tokens(const int64_t* source, const int64_t* target, SeqDims d, int rows, unsigned long long seed,
+                                  unsigned long long* seed_out, int* src, int* src_len, int* tgt, cudaStream_t st);
 
 struct DecRowArgs {
   SeqDims d;
@@ -166,12 +168,13 @@ struct DecRowArgs {
   float* attn_p;          // [S][B][Ts]
   __half* att_op;         // [S][operand Bp x 256] (hi; lo at + att_lo), step stride att_step
   int64_t att_lo, att_step;
-  unsigned long long seed;
+  const unsigned long long* seed;   // device: Philox key of this call
 };
 cudaError_t launch_dec_row(const DecRowArgs& a, cudaStream_t st);
 
 struct FinalizeArgs {
   SeqDims d;
+  int rows;               // real batch rows (<= d.B); only these are written to the caller's outputs
   const int* pred; const float* logp; const float* logits; const float* lse; const int* tgt;
   int64_t* raw_out; int64_t* pred_out; float* loss; float* logits_out;
   float* coef;            // [S][B] d(loss_b)/d(-logprob or nll at step t), before the incoming gradient
@@ -229,5 +232,23 @@ cudaError_t launch_table_grad(const TableGradArgs& a, cudaStream_t st);
 cudaError_t launch_bias_from_table(const float* dP, int V, float* db0, float* db1, cudaStream_t st);
 // scale[0] = 2^k with max|g| * 2^k in [2^9, 2^10), scale[1] = 1 / scale[0]
 cudaError_t launch_seq_loss_scale(const float* grad_loss, int B, float* scale, cudaStream_t st);
+// staged[b] = b < rows ? grad_loss[b] : 0 for b < padded (the padding rows of a tile carry no gradient)
+cudaError_t launch_stage_grad_loss(const float* grad_loss, int rows, int padded, float* staged, cudaStream_t st);
+// dst[i] += src[i]
+cudaError_t launch_accumulate(float* dst, const float* src, int64_t n, cudaStream_t st);
+
+// CUDA-graph cache of a pass (seq2seq_api.cu): `body` issues the launches of the pass on the stream it is given; after one
+// plain run per key they are captured once and replayed with a single cudaGraphLaunch on `st`.  pass: 0 forward, 1 backward,
+// 2 / 3 the CUDA-core twins, 4 ProgramPrior forward.
+struct GraphKey {
+  const void* ws; const void* params; int device, pass, Bp, Tq, Tp, S, sampling, teacher, need_grad, Vs, Vt;
+};
 
 }  // namespace pnmn
+
+#ifdef __CUDACC__
+#include <functional>
+namespace pnmn {
+int run_graphed_pass(const GraphKey& key, cudaStream_t st, const std::function<int(cudaStream_t)>& body);
+}
+#endif

@@ -8,7 +8,12 @@
 // row, seq2seq_base.py:188,286).
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
+#include <tuple>
+#include <algorithm>
+#include <functional>
 
 #include "../../include/pnmn.h"
 #include "seq2seq.h"
@@ -49,8 +54,11 @@ struct Layout {
   int64_t h1f, c1f, h1op, g1, enc;         // encoder layer 1 (+ decoder slots appended to h1f / h1op)
   int64_t cdf, attop, gd;                  // decoder
   int64_t dh, dc, datt, denc, dout0, dgd, dg1, dg0, scale;
+  int64_t seed, gstage, gws, extent;   // Philox key; incoming gradient padded to Bp; parameter gradients of this call
   int64_t total;
 };
+
+int64_t param_extent(const pnmn_pg_desc* m);
 
 Layout make_layout(const pnmn_pg_desc* m, int B, int Tq, int Tp, int S, bool need_grad) {
   Layout L;
@@ -89,7 +97,11 @@ Layout make_layout(const pnmn_pg_desc* m, int B, int Tq, int Tp, int S, bool nee
   L.enc = take(4ll * Bq * d.Ts * kSH);
   L.cdf = take(4 * L.slotf * (S + 1)); L.attop = take(2 * L.slotop * S);
   L.scale = take(256);
+  L.seed = take(256);
+  L.extent = param_extent(m);
   if (need_grad) {
+    L.gstage = take(4ll * d.Bp);
+    L.gws = take(4 * L.extent);
     L.g0 = take(4 * L.slotg * d.Ts); L.g1 = take(4 * L.slotg * d.Ts); L.gd = take(4 * L.slotg * S);
     L.dlogits = take(4ll * S * d.Bp * d.Vt);
     L.dP0 = take(4ll * d.Vs * kSG); L.dPd = take(4ll * d.Vt * kSG); L.dP1 = take(4ll * kSG);
@@ -117,7 +129,99 @@ int check_dims(const pnmn_pg_desc* m, int B, int Tq, int Tp, int S, bool teacher
 template <class T>
 T* at(void* ws, int64_t off) { return reinterpret_cast<T*>(static_cast<uint8_t*>(ws) + off); }
 
+// floats spanned by the model's parameters inside the flat buffer (the layout is the caller's; only the offsets are known)
+int64_t param_extent(const pnmn_pg_desc* m) {
+  const int64_t H = m->hidden, G = 4 * H;
+  int64_t e = 0;
+  auto up = [&](int64_t off, int64_t n) { e = std::max(e, off + n); };
+  up(m->src_embed, m->vocab_src * H); up(m->tgt_embed, m->vocab_tgt * H);
+  for (int l = 0; l < 2; ++l) { up(m->enc_w_ih[l], G * H); up(m->enc_w_hh[l], G * H); up(m->enc_b_ih[l], G); up(m->enc_b_hh[l], G); }
+  up(m->dec_w_ih, G * 2 * H); up(m->dec_w_hh, G * H); up(m->dec_b_ih, G); up(m->dec_b_hh, G);
+  up(m->out_w, m->vocab_tgt * H); up(m->out_b, m->vocab_tgt);
+  return (e + 63) / 64 * 64;
+}
+
+// ---- CUDA graphs --------------------------------------------------------------------------------------------------------
+// A pass is ~190 (forward) / ~250 (backward) dependent launches of 4-16 us kernels: issued one by one they cost the host
+// ~3.5 us each, and the joint-training step (four such passes per iteration) becomes host-bound.  Everything between the
+// token preparation and the finalisation touches only the workspace and the flat parameter buffer and depends on the
+// call only through data in the workspace (tokens, lengths, the Philox key, the staged incoming gradient), so the launch
+// sequence is captured ONCE per (workspace, parameters, shape) into a CUDA graph -- on a private stream, with the same
+// programmatic-dependent-launch edges -- and replayed with one cudaGraphLaunch on the caller's stream afterwards.
+// PNMN_PG_NOGRAPH=1 disables it; a failed capture falls back to plain launches for that key.
+struct KeyLess {
+  bool operator()(const GraphKey& a, const GraphKey& o) const {
+    return std::tie(a.ws, a.params, a.device, a.pass, a.Bp, a.Tq, a.Tp, a.S, a.sampling, a.teacher, a.need_grad, a.Vs, a.Vt) <
+           std::tie(o.ws, o.params, o.device, o.pass, o.Bp, o.Tq, o.Tp, o.S, o.sampling, o.teacher, o.need_grad, o.Vs, o.Vt);
+  }
+};
+struct GraphEntry { int calls = 0; cudaGraphExec_t exec = nullptr; bool failed = false; };
+std::mutex g_graph_mutex;
+std::map<GraphKey, GraphEntry, KeyLess> g_graphs;
+std::map<int, cudaStream_t> g_capture_streams;
+
+bool graphs_enabled() {
+  static const bool v = std::getenv("PNMN_PG_NOGRAPH") == nullptr;
+  return v;
+}
+
+int run_graphed(GraphKey key, cudaStream_t st, const std::function<int(cudaStream_t)>& body) {
+  if (!graphs_enabled()) return body(st);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return body(st);
+  key.device = dev;
+  GraphEntry* e;
+  cudaStream_t cap;
+  {
+    std::lock_guard<std::mutex> lock(g_graph_mutex);
+    if (g_graphs.size() > 256) {   // bounded: forget everything (workspaces of dead shapes), graphs are re-captured on demand
+      for (auto& kv : g_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      g_graphs.clear();
+    }
+    e = &g_graphs[key];
+    cudaStream_t& c = g_capture_streams[dev];
+    if (!c && cudaStreamCreateWithFlags(&c, cudaStreamNonBlocking) != cudaSuccess) { cudaGetLastError(); e->failed = true; }
+    cap = c;
+  }
+  if (e->failed) return body(st);
+  if (e->exec) {
+    CUDA_OK(cudaGraphLaunch(e->exec, st));
+    return 0;
+  }
+  if (e->calls++ == 0) return body(st);   // first call: plain launches (one-time function attributes are set here)
+  if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+    cudaGetLastError();
+    e->failed = true;
+    return body(st);
+  }
+  const int rc = body(cap);
+  cudaGraph_t graph = nullptr;
+  const cudaError_t err = cudaStreamEndCapture(cap, &graph);
+  if (rc != 0 || err != cudaSuccess || !graph) {
+    cudaGetLastError();
+    if (graph) cudaGraphDestroy(graph);
+    e->failed = true;
+    return body(st);
+  }
+  const cudaError_t ierr = cudaGraphInstantiate(&e->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ierr != cudaSuccess) {
+    cudaGetLastError();
+    e->exec = nullptr;
+    e->failed = true;
+    return body(st);
+  }
+  CUDA_OK(cudaGraphLaunch(e->exec, st));
+  return 0;
+}
+
 }  // namespace
+
+namespace pnmn {
+int run_graphed_pass(const GraphKey& key, cudaStream_t st, const std::function<int(cudaStream_t)>& body) {
+  return run_graphed(key, st, body);
+}
+}  // namespace pnmn
 
 extern "C" int64_t pnmn_pg_workspace_bytes(const pnmn_pg_desc* m, int batch, int tq, int tp, int steps, int need_grad) {
   if (check_dims(m, batch, tq, tp, steps, false)) return -1;
@@ -150,7 +254,13 @@ extern "C" int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const
   const int MT = d.Bp / 128;
   __half* packed = at<__half>(ws, L.packed);
 
-  CUDA_OK(launch_prepare_tokens(source, target, d, at<int>(ws, L.src), at<int>(ws, L.src_len), at<int>(ws, L.tgt), st));
+  const int rows = batch;
+  d.B = d.Bp;   // every kernel runs on whole 128-row tiles; rows >= `rows` are empty sequences (launch_prepare_tokens)
+  CUDA_OK(launch_prepare_tokens(source, target, d, rows, seed, at<unsigned long long>(ws, L.seed), at<int>(ws, L.src),
+                                at<int>(ws, L.src_len), at<int>(ws, L.tgt), st));
+  GraphKey key{ws, params, 0, 0, d.Bp, d.Tq, d.Tp, d.S, d.sampling, d.teacher, need_grad != 0, d.Vs, d.Vt};
+  if (simt) key.pass = 2;
+  const int rc = run_graphed(key, st, [&](cudaStream_t st) -> int {
 
   // ---- weights -> split fp16 tiles ------------------------------------------------------------------------
   {
@@ -227,7 +337,7 @@ extern "C" int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const
   r.logits = at<float>(ws, L.logits); r.lse = at<float>(ws, L.lse); r.pred = at<int>(ws, L.pred);
   r.logp = at<float>(ws, L.logp); r.inp = at<int>(ws, L.inp); r.attn_p = at<float>(ws, L.attn_p);
   r.att_op = at<__half>(ws, L.attop); r.att_lo = L.slotf; r.att_step = L.slotop;
-  r.seed = seed;
+  r.seed = at<unsigned long long>(ws, L.seed);
   g.len = nullptr; g.out_f = nullptr; g.out_op = nullptr;
   for (int t = 0; t <= d.S; ++t) {
     r.t = t;
@@ -243,9 +353,12 @@ extern "C" int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const
     g.gates = need_grad ? at<float>(ws, L.gd) + t * L.slotg : nullptr;
     CUDA_OK(launch_step_gemm(g, EPI_LSTM, kSG / 64, MT, simt, st));
   }
+    return 0;
+  });
+  if (rc) return rc;
   FinalizeArgs f;
   std::memset(&f, 0, sizeof(f));
-  f.d = d;
+  f.d = d; f.rows = rows;
   f.pred = at<int>(ws, L.pred); f.logp = at<float>(ws, L.logp); f.logits = at<float>(ws, L.logits); f.lse = at<float>(ws, L.lse);
   f.tgt = teacher ? at<int>(ws, L.tgt) : nullptr;
   f.raw_out = raw_predictions; f.pred_out = predictions; f.loss = loss; f.logits_out = logits_out;
@@ -268,7 +381,16 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
   const __half* packed = at<__half>(ws, L.packed);
   float* scale = at<float>(ws, L.scale);
 
-  CUDA_OK(launch_seq_loss_scale(grad_loss, d.B, scale, st));
+  const int rows = batch;
+  d.B = d.Bp;
+  float* gstage = at<float>(ws, L.gstage);
+  float* gws = at<float>(ws, L.gws);
+  CUDA_OK(launch_stage_grad_loss(grad_loss, rows, d.Bp, gstage, st));
+  GraphKey key{ws, params, 0, 1, d.Bp, d.Tq, d.Tp, d.S, 0, d.teacher, 1, d.Vs, d.Vt};
+  if (simt) key.pass = 3;
+  const int rc = run_graphed(key, st, [&](cudaStream_t st) -> int {
+  CUDA_OK(launch_seq_loss_scale(gstage, d.B, scale, st));
+  CUDA_OK(cudaMemsetAsync(gws, 0, 4 * L.extent, st));
   CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dh), 0, 4 * L.slotf, st));
   CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dc), 0, 4 * L.slotf, st));
   CUDA_OK(cudaMemsetAsync(at<float>(ws, L.datt), 0, 4 * L.slotf, st));
@@ -286,7 +408,7 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
   DecBwdRowArgs r;
   std::memset(&r, 0, sizeof(r));
   r.d = d;
-  r.grad_loss = grad_loss; r.coef = at<float>(ws, L.coef); r.label = at<int>(ws, L.label);
+  r.grad_loss = gstage; r.coef = at<float>(ws, L.coef); r.label = at<int>(ws, L.label);
   r.logits = at<float>(ws, L.logits); r.lse = at<float>(ws, L.lse); r.out_w = params + m->out_w;
   r.h_dec = at<float>(ws, L.h1f) + d.Ts * L.slotf; r.c_dec = at<float>(ws, L.cdf); r.gates = at<float>(ws, L.gd);
   r.enc = at<float>(ws, L.enc); r.src_len = at<int>(ws, L.src_len); r.attn_p = at<float>(ws, L.attn_p);
@@ -344,17 +466,17 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
   std::memset(&w, 0, sizeof(w));
   w.dg_lo = L.slotg; w.dg_step = L.slotdg; w.x_lo = L.slotf; w.x_step = L.slotop; w.m_tiles = MT; w.scale = scale;
   w.dg = at<__half>(ws, L.dg0); w.T = d.Ts;
-  w.x = at<__half>(ws, L.h0op); w.dw = grads + m->enc_w_hh[0]; w.ld = kSH;
+  w.x = at<__half>(ws, L.h0op); w.dw = gws + m->enc_w_hh[0]; w.ld = kSH;
   CUDA_OK(launch_wgrad_seq(w, simt, st));
   w.dg = at<__half>(ws, L.dg1);
-  w.x = at<__half>(ws, L.out0op); w.dw = grads + m->enc_w_ih[1];
+  w.x = at<__half>(ws, L.out0op); w.dw = gws + m->enc_w_ih[1];
   CUDA_OK(launch_wgrad_seq(w, simt, st));
-  w.x = at<__half>(ws, L.h1op); w.dw = grads + m->enc_w_hh[1];
+  w.x = at<__half>(ws, L.h1op); w.dw = gws + m->enc_w_hh[1];
   CUDA_OK(launch_wgrad_seq(w, simt, st));
   w.dg = at<__half>(ws, L.dgd); w.T = d.S;
-  w.x = at<__half>(ws, L.attop); w.dw = grads + m->dec_w_ih; w.ld = 2 * kSH;
+  w.x = at<__half>(ws, L.attop); w.dw = gws + m->dec_w_ih; w.ld = 2 * kSH;
   CUDA_OK(launch_wgrad_seq(w, simt, st));
-  w.x = at<__half>(ws, L.h1op) + d.Ts * L.slotop; w.dw = grads + m->dec_w_hh; w.ld = kSH;
+  w.x = at<__half>(ws, L.h1op) + d.Ts * L.slotop; w.dw = gws + m->dec_w_hh; w.ld = kSH;
   CUDA_OK(launch_wgrad_seq(w, simt, st));
 
   // ---- tables -> biases, embeddings, input-projection weights ------------------------------------------------------------
@@ -369,36 +491,40 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
   tg.dg = at<__half>(ws, L.dgd); tg.T = d.S; tg.V = d.Vt; tg.tok = at<int>(ws, L.inp); tg.tok_step = d.B; tg.tok_stride = 1;
   tg.dP = at<float>(ws, L.dPd);
   CUDA_OK(launch_table_grad(tg, st));
-  CUDA_OK(launch_bias_from_table(at<float>(ws, L.dP0), d.Vs, grads + m->enc_b_ih[0], grads + m->enc_b_hh[0], st));
-  CUDA_OK(launch_bias_from_table(at<float>(ws, L.dP1), 1, grads + m->enc_b_ih[1], grads + m->enc_b_hh[1], st));
-  CUDA_OK(launch_bias_from_table(at<float>(ws, L.dPd), d.Vt, grads + m->dec_b_ih, grads + m->dec_b_hh, st));
+  CUDA_OK(launch_bias_from_table(at<float>(ws, L.dP0), d.Vs, gws + m->enc_b_ih[0], gws + m->enc_b_hh[0], st));
+  CUDA_OK(launch_bias_from_table(at<float>(ws, L.dP1), 1, gws + m->enc_b_ih[1], gws + m->enc_b_hh[1], st));
+  CUDA_OK(launch_bias_from_table(at<float>(ws, L.dPd), d.Vt, gws + m->dec_b_ih, gws + m->dec_b_hh, st));
   {
     SimtGemm s;
     std::memset(&s, 0, sizeof(s));
     s.alpha = 1.f; s.accumulate = 1;
     // dEmb_src[v][e] += sum_g dP0[v][g] * W_ih0[g][e]
     s.A = at<float>(ws, L.dP0); s.sam = kSG; s.sak = 1; s.M = d.Vs; s.K = kSG;
-    s.B = params + m->enc_w_ih[0]; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = grads + m->src_embed; s.ldc = kSH;
+    s.B = params + m->enc_w_ih[0]; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = gws + m->src_embed; s.ldc = kSH;
     CUDA_OK(launch_simt_gemm(s, st));
     // dW_ih0[g][e] += sum_v dP0[v][g] * Emb_src[v][e]
     s.A = at<float>(ws, L.dP0); s.sam = 1; s.sak = kSG; s.M = kSG; s.K = d.Vs;
-    s.B = params + m->src_embed; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = grads + m->enc_w_ih[0]; s.ldc = kSH;
+    s.B = params + m->src_embed; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = gws + m->enc_w_ih[0]; s.ldc = kSH;
     CUDA_OK(launch_simt_gemm(s, st));
     // dEmb_tgt[v][e] += sum_g dPd[v][g] * W_dec_ih[g][256 + e]
     s.A = at<float>(ws, L.dPd); s.sam = kSG; s.sak = 1; s.M = d.Vt; s.K = kSG;
-    s.B = params + m->dec_w_ih + kSH; s.sbk = 2 * kSH; s.sbn = 1; s.N = kSH; s.C = grads + m->tgt_embed; s.ldc = kSH;
+    s.B = params + m->dec_w_ih + kSH; s.sbk = 2 * kSH; s.sbn = 1; s.N = kSH; s.C = gws + m->tgt_embed; s.ldc = kSH;
     CUDA_OK(launch_simt_gemm(s, st));
     // dW_dec_ih[g][256 + e] += sum_v dPd[v][g] * Emb_tgt[v][e]
     s.A = at<float>(ws, L.dPd); s.sam = 1; s.sak = kSG; s.M = kSG; s.K = d.Vt;
-    s.B = params + m->tgt_embed; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = grads + m->dec_w_ih + kSH; s.ldc = 2 * kSH;
+    s.B = params + m->tgt_embed; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = gws + m->dec_w_ih + kSH; s.ldc = 2 * kSH;
     CUDA_OK(launch_simt_gemm(s, st));
     // output projection: dW_o[v][j] += sum_{t,b} dlogits[t][b][v] * h_t[b][j];  db_o[v] += sum dlogits
     s.A = at<float>(ws, L.dlogits); s.sam = 1; s.sak = d.Vt; s.M = d.Vt; s.K = d.S * d.Bp;
-    s.B = at<float>(ws, L.h1f) + (d.Ts + 1) * L.slotf; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = grads + m->out_w; s.ldc = kSH;
+    s.B = at<float>(ws, L.h1f) + (d.Ts + 1) * L.slotf; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = gws + m->out_w; s.ldc = kSH;
     CUDA_OK(launch_simt_gemm(s, st));
-    s.B = scale + 2; s.sbk = 0; s.sbn = 0; s.N = 1; s.C = grads + m->out_b; s.ldc = 1;
+    s.B = scale + 2; s.sbk = 0; s.sbn = 0; s.N = 1; s.C = gws + m->out_b; s.ldc = 1;
     CUDA_OK(launch_simt_gemm(s, st));
   }
+    return 0;
+  });
+  if (rc) return rc;
+  CUDA_OK(launch_accumulate(grads, gws, L.extent, st));
   pnmn::count_launches(1 + 2 * d.S + 1 + 4 * d.Ts + 5 + 3 + 3 + 6);   // scale, decoder, encoder, wgrads, tables, biases, small GEMMs
   return 0;
 }

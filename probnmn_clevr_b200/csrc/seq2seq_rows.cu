@@ -70,14 +70,18 @@ __device__ __forceinline__ float philox_uniform(unsigned long long seed, uint32_
 // out-of-vocabulary ids map to @@UNKNOWN@@ (the reference's embedding lookup would raise instead)
 __device__ __forceinline__ int clamp_tok(int64_t v, int V) { return (v < 0 || v >= V) ? 1 : static_cast<int>(v); }
 
-__global__ void prepare_tokens_kernel(const int64_t* __restrict__ source, const int64_t* __restrict__ target, SeqDims d,
+__global__ void prepare_tokens_kernel(const int64_t* __restrict__ source, const int64_t* __restrict__ target, SeqDims d, int rows,
+                                      unsigned long long seed, unsigned long long* __restrict__ seed_out,
                                       int* __restrict__ src, int* __restrict__ src_len, int* __restrict__ tgt) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) seed_out[0] = seed;
   if (b >= d.B) return;
+  const bool real = b < rows;   // padding rows of the last tile: empty source / target (their loss is never read, their
+                                // incoming gradient is zero, so they contribute nothing)
   int n = 0;
-  for (int s = 0; s < d.Tq; ++s) n += source[static_cast<size_t>(b) * d.Tq + s] != kPad;
+  for (int s = 0; real && s < d.Tq; ++s) n += source[static_cast<size_t>(b) * d.Tq + s] != kPad;
   for (int s = 0; s < d.Ts; ++s)
-    src[static_cast<size_t>(b) * d.Ts + s] = s < d.Tq ? clamp_tok(source[static_cast<size_t>(b) * d.Tq + s], d.Vs) : kPad;
+    src[static_cast<size_t>(b) * d.Ts + s] = (real && s < d.Tq) ? clamp_tok(source[static_cast<size_t>(b) * d.Tq + s], d.Vs) : kPad;
   src[static_cast<size_t>(b) * d.Ts + n] = kEnd;
   int len = 0;
   for (int s = 0; s < d.Ts; ++s) len += src[static_cast<size_t>(b) * d.Ts + s] != kPad;
@@ -85,16 +89,43 @@ __global__ void prepare_tokens_kernel(const int64_t* __restrict__ source, const 
   if (target) {
     const int W = d.Tp + 2;
     int m = 0;
-    for (int s = 0; s < d.Tp; ++s) m += target[static_cast<size_t>(b) * d.Tp + s] != kPad;
+    for (int s = 0; real && s < d.Tp; ++s) m += target[static_cast<size_t>(b) * d.Tp + s] != kPad;
     tgt[static_cast<size_t>(b) * W] = kStart;
-    for (int s = 0; s < d.Tp; ++s) tgt[static_cast<size_t>(b) * W + 1 + s] = clamp_tok(target[static_cast<size_t>(b) * d.Tp + s], d.Vt);
+    for (int s = 0; s < d.Tp; ++s)
+      tgt[static_cast<size_t>(b) * W + 1 + s] = real ? clamp_tok(target[static_cast<size_t>(b) * d.Tp + s], d.Vt) : kPad;
     tgt[static_cast<size_t>(b) * W + d.Tp + 1] = kPad;
     tgt[static_cast<size_t>(b) * W + m + 1] = kEnd;
   }
 }
-cudaError_t launch_prepare_tokens(const int64_t* source, const int64_t* target, SeqDims d, int* src, int* src_len, int* tgt,
-                                  cudaStream_t st) {
-  prepare_tokens_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(source, target, d, src, src_len, tgt);
+cudaError_t launch_prepare_tokens(const int64_t* source, const int64_t* target, SeqDims d, int rows, unsigned long long seed,
+                                  unsigned long long* seed_out, int* src, int* src_len, int* tgt, cudaStream_t st) {
+  prepare_tokens_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(source, target, d, rows, seed, seed_out, src, src_len, tgt);
+  return cudaGetLastError();
+}
+
+__global__ void stage_grad_loss_kernel(const float* __restrict__ g, int rows, int padded, float* __restrict__ staged) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < padded) staged[b] = b < rows ? g[b] : 0.f;
+}
+cudaError_t launch_stage_grad_loss(const float* grad_loss, int rows, int padded, float* staged, cudaStream_t st) {
+  stage_grad_loss_kernel<<<(padded + 127) / 128, 128, 0, st>>>(grad_loss, rows, padded, staged);
+  return cudaGetLastError();
+}
+
+__global__ void accumulate_kernel(float* __restrict__ dst, const float* __restrict__ src, int64_t n4) {
+  const int64_t stride = static_cast<int64_t>(gridDim.x) * blockDim.x;
+  for (int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 a = reinterpret_cast<float4*>(dst)[i];
+    const float4 b = reinterpret_cast<const float4*>(src)[i];
+    a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+    reinterpret_cast<float4*>(dst)[i] = a;
+  }
+}
+cudaError_t launch_accumulate(float* dst, const float* src, int64_t n, cudaStream_t st) {
+  // n is a multiple of 64 (flat parameter layout), both buffers 16-byte aligned
+  const int64_t n4 = n / 4;
+  const int blocks = static_cast<int>(n4 / 256 + 1 < 148 * 4 ? n4 / 256 + 1 : 148 * 4);
+  accumulate_kernel<<<blocks, 256, 0, st>>>(dst, src, n4);
   return cudaGetLastError();
 }
 
@@ -170,7 +201,7 @@ __global__ void __launch_bounds__(256) dec_row_kernel(const DecRowArgs a) {
         if (lane == 0) {
           float total = 0.f;
           for (int v = 0; v < d.Vt; ++v) total += satt[v];
-          const float u = philox_uniform(a.seed, static_cast<uint32_t>(b), static_cast<uint32_t>(tp)) * total;
+          const float u = philox_uniform(a.seed[0], static_cast<uint32_t>(b), static_cast<uint32_t>(tp)) * total;
           float cum = 0.f;
           int last = kEnd;
           pred = -1;
@@ -273,6 +304,7 @@ __global__ void finalize_kernel(const FinalizeArgs a) {
   const SeqDims& d = a.d;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= d.B) return;
+  const bool real = b < a.rows;   // (padding rows still get their coef / label entries: the backward pass reads them)
   int first_end = -1;
   for (int t = 0; t < d.S; ++t)
     if (a.pred[static_cast<size_t>(t) * d.B + b] == kEnd) { first_end = t; break; }
@@ -283,14 +315,16 @@ __global__ void finalize_kernel(const FinalizeArgs a) {
     if (first_end < 0) keep = raw;                     // no @end@: row unchanged
     else if (first_end == 0) keep = kPad;              // @end@ first: the whole row becomes padding
     else keep = t <= first_end ? raw : kPad;
-    a.raw_out[static_cast<size_t>(b) * d.S + t] = raw;
-    a.pred_out[static_cast<size_t>(b) * d.S + t] = keep;
+    if (real) {
+      a.raw_out[static_cast<size_t>(b) * d.S + t] = raw;
+      a.pred_out[static_cast<size_t>(b) * d.S + t] = keep;
+    }
     const float pm = keep != kPad ? 1.f : 0.f;
     lp_sum += a.logp[static_cast<size_t>(t) * d.B + b] * pm;
     cnt += pm;
   }
   if (!d.teacher) {
-    a.loss[b] = -(lp_sum / (cnt + 1e-12f));
+    if (real) a.loss[b] = -(lp_sum / (cnt + 1e-12f));
     for (int t = 0; t < d.S; ++t) {
       const int raw = a.pred[static_cast<size_t>(t) * d.B + b];
       const bool kept = first_end < 0 ? raw != kPad : (first_end > 0 && t <= first_end && raw != kPad);
@@ -310,9 +344,9 @@ __global__ void finalize_kernel(const FinalizeArgs a) {
       a.coef[static_cast<size_t>(t) * d.B + b] = m / (n + 1e-13f);
       a.label[static_cast<size_t>(t) * d.B + b] = lab;
     }
-    a.loss[b] = tot / (n + 1e-13f);
+    if (real) a.loss[b] = tot / (n + 1e-13f);
   }
-  if (a.logits_out)
+  if (a.logits_out && real)
     for (int t = 0; t < d.S; ++t)
       for (int v = 0; v < d.Vt; ++v)
         a.logits_out[(static_cast<size_t>(b) * d.S + t) * d.Vt + v] = a.logits[(static_cast<size_t>(t) * d.B + b) * d.Vt + v];

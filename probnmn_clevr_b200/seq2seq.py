@@ -227,6 +227,7 @@ class Seq2SeqBase(nn.Module):
         self._layout: Optional[List[Tuple[str, int, int, torch.Size]]] = None
         self._desc = None
         self._calls = 0
+        self._teacher_calls = 0
         # per-instance salt of the sampling stream: construction order within the process (deterministic for a given script,
         # unlike id(self)), so that two runs with the same torch.manual_seed draw the same samples
         Seq2SeqBase._instances += 1
@@ -323,10 +324,18 @@ class Seq2SeqBase(nn.Module):
         predictions = torch.empty(B, S, dtype=torch.int64, device=dev)
         loss = torch.empty(B, dtype=torch.float32, device=dev)
         logits = torch.empty(B, S, self._vt, dtype=torch.float32, device=dev) if self.return_logits else None
-        self._calls += 1
         # Philox key of this call: (torch.manual_seed value, construction-order salt of the module, per-module call counter).
-        # The counter advances on EVERY forward (validation passes included), as the global generator does in the reference.
-        seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + self._calls * 0xD1B54A32D192ED03 + self._salt * 0x2545F4914F6CDD1D) % (1 << 64)
+        # Free-running and teacher-forced calls count separately (the draws of a teacher-forced call only decide its
+        # "predictions", never its loss), so the samples of the free-running pass do not depend on whether the supervised
+        # pass of the same step was issued before or after it.  The counters advance on EVERY forward (validation passes
+        # included), as the global generator does in the reference.
+        if teacher:
+            self._teacher_calls += 1
+            counter = 2 * self._teacher_calls + 1
+        else:
+            self._calls += 1
+            counter = 2 * self._calls
+        seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + counter * 0xD1B54A32D192ED03 + self._salt * 0x2545F4914F6CDD1D) % (1 << 64)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         L.check(lib.pnmn_pg_forward(
             ctypes.byref(self._desc), ctypes.c_void_p(self._flat.data_ptr()), ctypes.c_void_p(source.data_ptr()),
