@@ -177,6 +177,17 @@ int64_t pnmn_pg_workspace_bytes(const pnmn_pg_desc* m, int batch, int tq, int tp
 int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const int64_t* source, const int64_t* target, int batch,
                     int tq, int tp, int steps, int sampling, uint64_t seed, int need_grad, void* workspace,
                     int64_t* raw_predictions, int64_t* predictions, float* loss, float* logits, void* stream);
+/* The same pass over teacher-forced AND free-running rows at once (the reference calls the generator once for the rows
+ * without program supervision, free-running, and once for the rows with it, teacher-forced:
+ * trainers/joint_training_trainer.py:139-144,164-168 / modules/elbo.py:230-233): rows with row_teacher[b] != 0 (device,
+ * [batch] bytes) are teacher-forced on target[b]; the others decode freely by categorical sampling for free_steps steps and
+ * take the sampled-sequence loss (their target row is ignored, predictions beyond free_steps are padding).  Decoding runs
+ * tp + 1 steps; outputs are [batch][tp + 1].  Per row the results equal those of the two separate calls; the backward pass
+ * is pnmn_pg_backward with steps = tp + 1, teacher = 1. */
+int pnmn_pg_forward_mixed(const pnmn_pg_desc* m, const float* params, const int64_t* source, const int64_t* target,
+                          const uint8_t* row_teacher, int free_steps, int batch, int tq, int tp, uint64_t seed, int need_grad,
+                          void* workspace, int64_t* raw_predictions, int64_t* predictions, float* loss, float* logits,
+                          void* stream);
 /* autograd of the above: grad_loss is d(objective)/d(loss) [batch]; parameter gradients are ACCUMULATED into grads
  * (same offsets as params).  Must follow a pnmn_pg_forward with need_grad = 1 on the same workspace and sizes. */
 int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, float* grads, const float* grad_loss, int batch, int tq,
@@ -245,6 +256,9 @@ int64_t pnmn_debug_plan_meta(const pnmn_plan* p, int pass, int32_t* out, int64_t
  * sample's program in execution order, token id, map unit}; after pnmn_nmn_forward map unit u is the top-left 14 x 14 block
  * of the 16 x 16 fp32 grid at pnmn_buffers.maps + 256 * u.  Returns the number of records (host only). */
 int64_t pnmn_debug_plan_maps(const pnmn_plan* p, int32_t* out, int64_t cap_records);
+/* CUDA-graph cache of the LSTM passes: {cached keys, keys with an instantiated graph, keys whose capture failed (plain
+ * launches are used for those), graph launches so far} */
+int pnmn_debug_graph_stats(int64_t* out /* [4] */);
 /* accumulated host-side milliseconds spent in {pnmn_plan_create, pnmn_nmn_forward, pnmn_nmn_backward} and the
  * number of plans created since the last call (reading clears) */
 int pnmn_debug_host_times(double* ms);

@@ -107,8 +107,8 @@ EXPORTS = [
     "pnmn_plan_create", "pnmn_plan_destroy", "pnmn_plan_upload", "pnmn_plan_valid", "pnmn_plan_sizes", "pnmn_plan_stats",
     "pnmn_nmn_forward", "pnmn_nmn_backward", "pnmn_debug_launch_conv", "pnmn_debug_launch_wgrad",
     "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt", "pnmn_profile_enable",
-    "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times", "pnmn_debug_plan_meta", "pnmn_debug_plan_maps",
-    "pnmn_split3_bf16", "pnmn_relu_pool_fwd", "pnmn_relu_pool_bwd", "pnmn_relu_pool_bwd_split", "pnmn_relu_pool_fwd_bias", "pnmn_split2_bf16", "pnmn_launch_count", "pnmn_pg_workspace_bytes", "pnmn_pg_forward", "pnmn_pg_backward", "pnmn_pg_debug_layout",
+    "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times", "pnmn_debug_plan_meta", "pnmn_debug_plan_maps", "pnmn_debug_graph_stats",
+    "pnmn_split3_bf16", "pnmn_relu_pool_fwd", "pnmn_relu_pool_bwd", "pnmn_relu_pool_bwd_split", "pnmn_relu_pool_fwd_bias", "pnmn_split2_bf16", "pnmn_launch_count", "pnmn_pg_workspace_bytes", "pnmn_pg_forward", "pnmn_pg_backward", "pnmn_pg_debug_layout", "pnmn_pg_forward_mixed",
     "pnmn_prior_workspace_bytes", "pnmn_prior_forward", "pnmn_clamp_adam", "pnmn_elbo_glue",
 ]
 
@@ -162,10 +162,13 @@ def lib() -> ctypes.CDLL:
     L.pnmn_debug_plan_meta.argtypes = [c_void_p, c_int, c_void_p, c_int64]
     L.pnmn_debug_plan_maps.restype = c_int64
     L.pnmn_debug_plan_maps.argtypes = [c_void_p, c_void_p, c_int64]
+    L.pnmn_debug_graph_stats.argtypes = [POINTER(c_int64)]
     L.pnmn_pg_workspace_bytes.restype = c_int64
     L.pnmn_pg_workspace_bytes.argtypes = [POINTER(PgDesc), c_int, c_int, c_int, c_int, c_int]
     L.pnmn_pg_forward.argtypes = [POINTER(PgDesc), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                   ctypes.c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    L.pnmn_pg_forward_mixed.argtypes = [POINTER(PgDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int,
+                                        ctypes.c_uint64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     L.pnmn_pg_backward.argtypes = [POINTER(PgDesc), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int,
                                    c_void_p, c_void_p]
     L.pnmn_pg_debug_layout.argtypes = [POINTER(PgDesc), c_int, c_int, c_int, c_int, c_int, POINTER(c_int64)]

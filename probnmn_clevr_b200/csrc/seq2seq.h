@@ -144,13 +144,17 @@ struct SeqDims {
   int B, Bp, Tq, Ts, Tp, S, Vs, Vt;
   int teacher;   // targets given
   int sampling;  // 1 = categorical sampling, 0 = greedy
+  int free_S;    // decoding steps of FREE-RUNNING rows (== S unless teacher-forced and free-running rows share one call)
 };
 
 // token preparation (AllenNLP add_sentence_boundary_token_ids + seq2seq_base.py:128-141)
 // d.B rows are prepared; rows >= `rows` (padding up to the tile size) become empty sequences.  Also stores the call's
 // Philox key in device memory (seed_out), so that the launches that follow do not depend on it (CUDA graph replay).
-cudaError_t launch_prepare_tokens(const int64_t* source, const int64_t* target, SeqDims d, int rows, unsigned long long seed,
-                                  unsigned long long* seed_out, int* src, int* src_len, int* tgt, cudaStream_t st);
+// row_teacher (device, [rows] bytes, may be nullptr = every row follows d.teacher) -> row_mode[d.B] ints in the workspace:
+// 1 = the row is teacher-forced, 0 = it decodes freely for d.free_S steps.
+cudaError_t launch_prepare_tokens(const int64_t* source, const int64_t* target, const uint8_t* row_teacher, SeqDims d, int rows,
+                                  unsigned long long seed, unsigned long long* seed_out, int* src, int* src_len, int* tgt,
+                                  int* row_mode, cudaStream_t st);
 
 struct DecRowArgs {
   SeqDims d;
@@ -159,6 +163,7 @@ struct DecRowArgs {
   const float* enc;       // fp32 [B][Ts][256]
   const int* src_len;
   const int* tgt;         // [B][Tp+2] or nullptr
+  const int* row_mode;    // [B] 1 = teacher-forced row, 0 = free-running row
   const float* out_w; const float* out_b;   // [Vt][256], [Vt]
   float* logits;          // [S][B][Vt]
   float* lse;             // [S][B]
@@ -176,6 +181,7 @@ struct FinalizeArgs {
   SeqDims d;
   int rows;               // real batch rows (<= d.B); only these are written to the caller's outputs
   const int* pred; const float* logp; const float* logits; const float* lse; const int* tgt;
+  const int* row_mode;    // [B] as in DecRowArgs
   int64_t* raw_out; int64_t* pred_out; float* loss; float* logits_out;
   float* coef;            // [S][B] d(loss_b)/d(-logprob or nll at step t), before the incoming gradient
   int* label;             // [S][B] class whose one-hot enters dlogits

@@ -54,7 +54,7 @@ struct Layout {
   int64_t h1f, c1f, h1op, g1, enc;         // encoder layer 1 (+ decoder slots appended to h1f / h1op)
   int64_t cdf, attop, gd;                  // decoder
   int64_t dh, dc, datt, denc, dout0, dgd, dg1, dg0, scale;
-  int64_t seed, gstage, gws, extent;   // Philox key; incoming gradient padded to Bp; parameter gradients of this call
+  int64_t seed, gstage, gws, extent, rowmode;   // Philox key; incoming gradient padded to Bp; parameter gradients of this call
   int64_t total;
 };
 
@@ -98,6 +98,7 @@ Layout make_layout(const pnmn_pg_desc* m, int B, int Tq, int Tp, int S, bool nee
   L.cdf = take(4 * L.slotf * (S + 1)); L.attop = take(2 * L.slotop * S);
   L.scale = take(256);
   L.seed = take(256);
+  L.rowmode = take(4ll * d.Bp);
   L.extent = param_extent(m);
   if (need_grad) {
     L.gstage = take(4ll * d.Bp);
@@ -156,9 +157,11 @@ struct KeyLess {
   }
 };
 struct GraphEntry { int calls = 0; cudaGraphExec_t exec = nullptr; bool failed = false; };
+
 std::mutex g_graph_mutex;
 std::map<GraphKey, GraphEntry, KeyLess> g_graphs;
 std::map<int, cudaStream_t> g_capture_streams;
+long long g_graph_launches = 0;
 
 bool graphs_enabled() {
   static const bool v = std::getenv("PNMN_PG_NOGRAPH") == nullptr;
@@ -186,6 +189,7 @@ int run_graphed(GraphKey key, cudaStream_t st, const std::function<int(cudaStrea
   if (e->failed) return body(st);
   if (e->exec) {
     CUDA_OK(cudaGraphLaunch(e->exec, st));
+    ++g_graph_launches;
     return 0;
   }
   if (e->calls++ == 0) return body(st);   // first call: plain launches (one-time function attributes are set here)
@@ -217,6 +221,14 @@ int run_graphed(GraphKey key, cudaStream_t st, const std::function<int(cudaStrea
 
 }  // namespace
 
+// {cached keys, keys with an instantiated graph, keys whose capture failed, graph launches so far}
+extern "C" int pnmn_debug_graph_stats(int64_t* out) {
+  std::lock_guard<std::mutex> lock(g_graph_mutex);
+  out[0] = static_cast<int64_t>(g_graphs.size()); out[1] = 0; out[2] = 0; out[3] = g_graph_launches;
+  for (auto& kv : g_graphs) { out[1] += kv.second.exec != nullptr; out[2] += kv.second.failed; }
+  return 0;
+}
+
 namespace pnmn {
 int run_graphed_pass(const GraphKey& key, cudaStream_t st, const std::function<int(cudaStream_t)>& body) {
   return run_graphed(key, st, body);
@@ -238,10 +250,10 @@ extern "C" int pnmn_pg_debug_layout(const pnmn_pg_desc* m, int batch, int tq, in
   return 0;
 }
 
-extern "C" int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const int64_t* source, const int64_t* target,
-                               int batch, int tq, int tp, int steps, int sampling, uint64_t seed, int need_grad,
-                               void* ws, int64_t* raw_predictions, int64_t* predictions, float* loss, float* logits_out,
-                               void* stream) {
+static int pg_forward_impl(const pnmn_pg_desc* m, const float* params, const int64_t* source, const int64_t* target,
+                           const uint8_t* row_teacher, int free_steps, int batch, int tq, int tp, int steps, int sampling,
+                           uint64_t seed, int need_grad, void* ws, int64_t* raw_predictions, int64_t* predictions, float* loss,
+                           float* logits_out, void* stream) {
   const bool teacher = target != nullptr;
   if (check_dims(m, batch, tq, tp, steps, teacher)) return 1;
   if (!params || !source || !ws || !raw_predictions || !predictions || !loss) return fail("pnmn_pg_forward: NULL buffer");
@@ -250,14 +262,15 @@ extern "C" int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const
   SeqDims& d = L.d;
   d.teacher = teacher ? 1 : 0;
   d.sampling = sampling ? 1 : 0;
+  d.free_S = row_teacher ? free_steps : d.S;
   const bool simt = use_simt();
   const int MT = d.Bp / 128;
   __half* packed = at<__half>(ws, L.packed);
 
   const int rows = batch;
   d.B = d.Bp;   // every kernel runs on whole 128-row tiles; rows >= `rows` are empty sequences (launch_prepare_tokens)
-  CUDA_OK(launch_prepare_tokens(source, target, d, rows, seed, at<unsigned long long>(ws, L.seed), at<int>(ws, L.src),
-                                at<int>(ws, L.src_len), at<int>(ws, L.tgt), st));
+  CUDA_OK(launch_prepare_tokens(source, target, row_teacher, d, rows, seed, at<unsigned long long>(ws, L.seed), at<int>(ws, L.src),
+                                at<int>(ws, L.src_len), at<int>(ws, L.tgt), at<int>(ws, L.rowmode), st));
   GraphKey key{ws, params, 0, 0, d.Bp, d.Tq, d.Tp, d.S, d.sampling, d.teacher, need_grad != 0, d.Vs, d.Vt};
   if (simt) key.pass = 2;
   const int rc = run_graphed(key, st, [&](cudaStream_t st) -> int {
@@ -333,6 +346,7 @@ extern "C" int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const
   r.d = d;
   r.h_dec = at<float>(ws, L.h1f) + d.Ts * L.slotf;
   r.enc = at<float>(ws, L.enc); r.src_len = at<int>(ws, L.src_len); r.tgt = teacher ? at<int>(ws, L.tgt) : nullptr;
+  r.row_mode = at<int>(ws, L.rowmode);
   r.out_w = params + m->out_w; r.out_b = params + m->out_b;
   r.logits = at<float>(ws, L.logits); r.lse = at<float>(ws, L.lse); r.pred = at<int>(ws, L.pred);
   r.logp = at<float>(ws, L.logp); r.inp = at<int>(ws, L.inp); r.attn_p = at<float>(ws, L.attn_p);
@@ -361,11 +375,34 @@ extern "C" int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const
   f.d = d; f.rows = rows;
   f.pred = at<int>(ws, L.pred); f.logp = at<float>(ws, L.logp); f.logits = at<float>(ws, L.logits); f.lse = at<float>(ws, L.lse);
   f.tgt = teacher ? at<int>(ws, L.tgt) : nullptr;
+  f.row_mode = at<int>(ws, L.rowmode);
   f.raw_out = raw_predictions; f.pred_out = predictions; f.loss = loss; f.logits_out = logits_out;
   f.coef = at<float>(ws, L.coef); f.label = at<int>(ws, L.label);
   CUDA_OK(launch_finalize(f, st));
   pnmn::count_launches(6 + 2 * d.Ts + 2 * d.S + 1);   // prepare, pack, 3 tables, encoder steps, decoder row + step kernels, finalize
   return 0;
+}
+
+extern "C" int pnmn_pg_forward(const pnmn_pg_desc* m, const float* params, const int64_t* source, const int64_t* target,
+                               int batch, int tq, int tp, int steps, int sampling, uint64_t seed, int need_grad,
+                               void* ws, int64_t* raw_predictions, int64_t* predictions, float* loss, float* logits_out,
+                               void* stream) {
+  return pg_forward_impl(m, params, source, target, nullptr, steps, batch, tq, tp, steps, sampling, seed, need_grad, ws,
+                         raw_predictions, predictions, loss, logits_out, stream);
+}
+
+// One pass over teacher-forced AND free-running rows (the supervised and unsupervised rows of a joint-training batch:
+// joint_training_trainer.py:139-144 and :164-168 call the generator once for each kind): rows with row_teacher[b] != 0 are
+// teacher-forced on target[b], the others decode freely (categorical sampling) for free_steps steps and take the
+// sampled-sequence loss; per row the results are those of the two separate calls.  steps must be tp + 1 >= free_steps.
+extern "C" int pnmn_pg_forward_mixed(const pnmn_pg_desc* m, const float* params, const int64_t* source, const int64_t* target,
+                                     const uint8_t* row_teacher, int free_steps, int batch, int tq, int tp, uint64_t seed,
+                                     int need_grad, void* ws, int64_t* raw_predictions, int64_t* predictions, float* loss,
+                                     float* logits_out, void* stream) {
+  if (!target || !row_teacher) return fail("pnmn_pg_forward_mixed: target and row_teacher are required");
+  if (free_steps < 1 || free_steps > tp + 1) return fail("pnmn_pg_forward_mixed: free_steps must be in [1, tp + 1]");
+  return pg_forward_impl(m, params, source, target, row_teacher, free_steps, batch, tq, tp, tp + 1, 1, seed, need_grad, ws,
+                         raw_predictions, predictions, loss, logits_out, stream);
 }
 
 extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, float* grads, const float* grad_loss, int batch,

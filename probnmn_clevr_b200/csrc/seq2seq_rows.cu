@@ -70,13 +70,16 @@ __device__ __forceinline__ float philox_uniform(unsigned long long seed, uint32_
 // out-of-vocabulary ids map to @@UNKNOWN@@ (the reference's embedding lookup would raise instead)
 __device__ __forceinline__ int clamp_tok(int64_t v, int V) { return (v < 0 || v >= V) ? 1 : static_cast<int>(v); }
 
-__global__ void prepare_tokens_kernel(const int64_t* __restrict__ source, const int64_t* __restrict__ target, SeqDims d, int rows,
+__global__ void prepare_tokens_kernel(const int64_t* __restrict__ source, const int64_t* __restrict__ target,
+                                      const uint8_t* __restrict__ row_teacher, SeqDims d, int rows,
                                       unsigned long long seed, unsigned long long* __restrict__ seed_out,
-                                      int* __restrict__ src, int* __restrict__ src_len, int* __restrict__ tgt) {
+                                      int* __restrict__ src, int* __restrict__ src_len, int* __restrict__ tgt,
+                                      int* __restrict__ row_mode) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b == 0) seed_out[0] = seed;
   if (b >= d.B) return;
-  const bool real = b < rows;   // padding rows of the last tile: empty source / target (their loss is never read, their
+  const bool real = b < rows;
+  row_mode[b] = (real && row_teacher) ? (row_teacher[b] != 0) : d.teacher;   // padding rows of the last tile: empty source / target (their loss is never read, their
                                 // incoming gradient is zero, so they contribute nothing)
   int n = 0;
   for (int s = 0; real && s < d.Tq; ++s) n += source[static_cast<size_t>(b) * d.Tq + s] != kPad;
@@ -97,9 +100,11 @@ __global__ void prepare_tokens_kernel(const int64_t* __restrict__ source, const 
     tgt[static_cast<size_t>(b) * W + m + 1] = kEnd;
   }
 }
-cudaError_t launch_prepare_tokens(const int64_t* source, const int64_t* target, SeqDims d, int rows, unsigned long long seed,
-                                  unsigned long long* seed_out, int* src, int* src_len, int* tgt, cudaStream_t st) {
-  prepare_tokens_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(source, target, d, rows, seed, seed_out, src, src_len, tgt);
+cudaError_t launch_prepare_tokens(const int64_t* source, const int64_t* target, const uint8_t* row_teacher, SeqDims d, int rows,
+                                  unsigned long long seed, unsigned long long* seed_out, int* src, int* src_len, int* tgt,
+                                  int* row_mode, cudaStream_t st) {
+  prepare_tokens_kernel<<<(d.B + 127) / 128, 128, 0, st>>>(source, target, row_teacher, d, rows, seed, seed_out, src, src_len, tgt,
+                                                          row_mode);
   return cudaGetLastError();
 }
 
@@ -231,7 +236,7 @@ __global__ void __launch_bounds__(256) dec_row_kernel(const DecRowArgs a) {
 
   // ---- input token of step t: gold token under teacher forcing, else the previous prediction ----------
   if (tid == 0) {
-    const int tok = d.teacher ? a.tgt[static_cast<size_t>(b) * (d.Tp + 2) + t] : (t == 0 ? kStart : s_pred);
+    const int tok = a.row_mode[b] ? a.tgt[static_cast<size_t>(b) * (d.Tp + 2) + t] : (t == 0 ? kStart : s_pred);
     a.inp[static_cast<size_t>(t) * d.B + b] = tok;
   }
   // ---- dot-product attention ---------------------------------------------------------------------------
@@ -305,14 +310,17 @@ __global__ void finalize_kernel(const FinalizeArgs a) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= d.B) return;
   const bool real = b < a.rows;   // (padding rows still get their coef / label entries: the backward pass reads them)
+  const bool tf = a.row_mode[b] != 0;
+  const int Se = tf ? d.S : d.free_S;   // a free-running row of a mixed call stops after free_S steps
   int first_end = -1;
-  for (int t = 0; t < d.S; ++t)
+  for (int t = 0; t < Se; ++t)
     if (a.pred[static_cast<size_t>(t) * d.B + b] == kEnd) { first_end = t; break; }
   float lp_sum = 0.f, cnt = 0.f;
   for (int t = 0; t < d.S; ++t) {
-    const int raw = a.pred[static_cast<size_t>(t) * d.B + b];
+    const int raw = t < Se ? a.pred[static_cast<size_t>(t) * d.B + b] : kPad;
     int keep;
-    if (first_end < 0) keep = raw;                     // no @end@: row unchanged
+    if (t >= Se) keep = kPad;
+    else if (first_end < 0) keep = raw;                // no @end@: row unchanged
     else if (first_end == 0) keep = kPad;              // @end@ first: the whole row becomes padding
     else keep = t <= first_end ? raw : kPad;
     if (real) {
@@ -323,11 +331,11 @@ __global__ void finalize_kernel(const FinalizeArgs a) {
     lp_sum += a.logp[static_cast<size_t>(t) * d.B + b] * pm;
     cnt += pm;
   }
-  if (!d.teacher) {
+  if (!tf) {
     if (real) a.loss[b] = -(lp_sum / (cnt + 1e-12f));
     for (int t = 0; t < d.S; ++t) {
       const int raw = a.pred[static_cast<size_t>(t) * d.B + b];
-      const bool kept = first_end < 0 ? raw != kPad : (first_end > 0 && t <= first_end && raw != kPad);
+      const bool kept = t < Se && (first_end < 0 ? raw != kPad : (first_end > 0 && t <= first_end && raw != kPad));
       a.coef[static_cast<size_t>(t) * d.B + b] = kept ? 1.f / (cnt + 1e-12f) : 0.f;
       a.label[static_cast<size_t>(t) * d.B + b] = raw;
     }

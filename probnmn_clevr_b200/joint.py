@@ -14,6 +14,11 @@ What is different is only HOW the work is issued:
 * independent passes run on separate CUDA streams: the teacher-forced passes over the supervised rows on one, the
   question reconstructor + program prior over the sampled programs on another, while this thread compiles the sampled
   programs for the module executor; autograd replays each pass on its own stream;
+* rows of both kinds share passes (``fused=True``, the default): the program generator runs ONCE over all rows -- the
+  unsupervised ones decode freely, the supervised ones are teacher-forced (``Seq2SeqBase.forward_mixed``) -- and the
+  question reconstructor runs ONCE over the sampled and the ground-truth programs together (both calls are teacher-forced
+  on the questions).  An LSTM pass is a chain of ~450 dependent kernels whose duration hardly depends on the number of
+  rows, so two passes instead of four halve the recurrent part of the step; per row the arithmetic is unchanged;
 * the gradient clamp is fused into the optimizer (``optim.FusedClampAdam``); with more than one process the gradients are
   averaged over NCCL before it (clamp AFTER the reduction, as ``nn.DataParallel`` + ``clamp_`` does in the reference).
 """
@@ -55,7 +60,8 @@ class JointTrainingStep:
 
     def __init__(self, program_generator, question_reconstructor, nmn, program_prior, alpha: float = 100.0,
                  beta: float = 0.1, gamma: float = 1.0, delta: float = 0.99, objective: str = "ours", lr: float = 1e-6,
-                 weight_decay: float = 0.0, clamp: Optional[float] = 5.0, concurrent: bool = True, group=None):
+                 weight_decay: float = 0.0, clamp: Optional[float] = 5.0, concurrent: bool = True, fused: bool = True,
+                 group=None):
         self.program_generator, self.question_reconstructor = program_generator, question_reconstructor
         self.nmn, self.program_prior = nmn, program_prior
         program_prior.eval()
@@ -67,6 +73,8 @@ class JointTrainingStep:
         params = [p for m in trained for p in m.parameters()]
         self.optimizer = FusedClampAdam(params, lr=lr, weight_decay=weight_decay, clamp=clamp, modules=trained)
         self.concurrent = concurrent
+        self.fused = fused
+        self._qr_stream: Optional[torch.cuda.Stream] = None
         if concurrent:
             # passes on side streams accumulate into parameters whose AccumulateGrad node lives on another stream: intended
             try:
@@ -100,6 +108,8 @@ class JointTrainingStep:
         to = lambda t: t if t.device == dev else t.to(dev, non_blocking=True)
         ours = self.objective == "ours"
         main = torch.cuda.current_stream(dev)
+        if self.fused and ours and un["question"].shape[0] > 0 and su["question"].shape[0] > 0:
+            return self._do_iteration_fused(un, su, dev, to, main)
 
         sup_out = None
         if ours:
@@ -135,6 +145,65 @@ class JointTrainingStep:
             out["loss"].update({"question_reconstruction_gt": qr_sup.detach(), "program_generation_gt": pg_sup.detach()})
         out["objective"] = loss_objective.detach()
         return out
+
+    def _do_iteration_fused(self, un, su, dev, to, main) -> Dict[str, Any]:
+        """The same objective with the rows of both kinds sharing one generator pass and one reconstructor pass."""
+        from .seq2seq import _handover
+        pg_m, qr_m = self.program_generator, self.question_reconstructor
+        q_u, img, ans = to(un["question"]), to(un["image"]), to(un["answer"])
+        q_s, p_s = to(su["question"]), to(su["program"])
+        nu, ns = q_u.shape[0], q_s.shape[0]
+        free = pg_m._max_decoding_steps
+        width = max(p_s.shape[1], free - 1)
+        q_all = torch.cat([q_u, q_s])
+        targets = torch.zeros(nu + ns, width, dtype=torch.int64, device=dev)
+        targets[nu:, : p_s.shape[1]] = p_s
+        teacher_rows = torch.zeros(nu + ns, dtype=torch.uint8, device=dev)
+        teacher_rows[nu:] = 1
+
+        pg = pg_m.forward_mixed(q_all, targets, teacher_rows, free_steps=free)       # elbo.py:230-233 + trainer :164-168
+        sampled = pg["predictions"][:nu, :free].contiguous()
+        if pg_m.handover_predictions:
+            _handover(sampled)                                                         # the module network compiles on the host
+        pwidth = max(free, p_s.shape[1])
+        programs_all = torch.zeros(nu + ns, pwidth, dtype=torch.int64, device=dev)
+        programs_all[:nu, :free] = sampled
+        programs_all[nu:, : p_s.shape[1]] = p_s
+
+        def reconstruct():
+            qr = qr_m(programs_all, q_all, decoding_strategy="sampling")              # elbo.py:236-238 + trainer :169-173
+            prior = self.program_prior(sampled)                                        # elbo.py:256
+            return qr, prior
+
+        if self.concurrent:
+            if self._qr_stream is None or self._qr_stream.device != dev:
+                self._qr_stream = torch.cuda.Stream(dev)
+            side = self._qr_stream
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                qr, prior = reconstruct()
+            nmn = self.nmn(img, sampled, ans)                                          # elbo.py:239
+            main.wait_stream(side)
+            for t in (qr["loss"], prior["loss"], programs_all):
+                t.record_stream(main if t is not programs_all else side)
+        else:
+            qr, prior = reconstruct()
+            nmn = self.nmn(img, sampled, ans)
+
+        pg_loss_u, qr_loss_u = pg["loss"][:nu], qr["loss"][:nu]
+        elbo_output_dict = self.elbo._glue(pg_loss_u, qr_loss_u, prior["loss"], nmn["loss"], self.gamma, 0)
+        nmn_loss = elbo_output_dict.pop("nmn_loss")
+        pg_sup, qr_sup = pg["loss"][nu:].mean(), qr["loss"][nu:].mean()
+        loss_objective = self.gamma * nmn_loss - elbo_output_dict["elbo"] + self.alpha * (pg_sup + qr_sup)
+        loss_objective.backward()
+
+        self.elbo.last_outputs = {
+            "program_generator": {"predictions": sampled, "loss": pg_loss_u,
+                                  "raw_predictions": pg["raw_predictions"][:nu, :free] if "raw_predictions" in pg else None},
+            "question_reconstructor": {"loss": qr_loss_u}, "nmn": nmn, "program_prior": prior}
+        return {"loss": {"nmn": nmn_loss.detach(), "question_reconstruction_gt": qr_sup.detach(),
+                         "program_generation_gt": pg_sup.detach()},
+                "elbo": {k: v.detach() for k, v in elbo_output_dict.items()}, "objective": loss_objective.detach()}
 
     def _supervised(self, questions, programs):
         """alpha * (log q(z'|x') + log p(x'|z')) over the rows with ground-truth programs (:152-176)."""

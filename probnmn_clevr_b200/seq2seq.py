@@ -293,7 +293,27 @@ class Seq2SeqBase(nn.Module):
         with torch.cuda.device(source_tokens.device):  # the library launches on the thread's current device
             return self._forward(source_tokens, target_tokens, decoding_strategy)
 
-    def _forward(self, source_tokens, target_tokens, decoding_strategy):
+    def forward_mixed(self, source_tokens: torch.Tensor, target_tokens: torch.Tensor, teacher_rows: torch.Tensor,
+                      free_steps: Optional[int] = None) -> Dict[str, torch.Tensor]:
+        r"""
+        ONE pass over rows of both kinds (no counterpart in the reference, which calls the model once per kind --
+        trainers/joint_training_trainer.py:139-144,164-168): rows with ``teacher_rows[b]`` true are teacher-forced on
+        ``target_tokens[b]`` exactly as ``forward(source, target)`` would, the others decode freely by categorical
+        sampling for ``free_steps`` (default ``max_decoding_steps``) steps exactly as ``forward(source)`` would, their
+        target row is ignored.  Returns ``predictions`` (B, T_tgt + 1) -- columns beyond ``free_steps`` of a free-running
+        row are padding -- and ``loss`` (B,).  Per row the values equal those of the separate calls (rows are
+        independent); the sampled tokens differ because the Philox stream is indexed by the row's position in the call.
+        """
+        if not source_tokens.is_cuda:
+            raise RuntimeError("Seq2SeqBase (B200) needs CUDA tensors; there is no CPU fallback")
+        free_steps = self._max_decoding_steps if free_steps is None else int(free_steps)
+        if target_tokens.shape[1] + 1 < free_steps:
+            raise ValueError("target_tokens must have at least free_steps - 1 columns (pad with zeros)")
+        with torch.cuda.device(source_tokens.device):
+            return self._forward(source_tokens, target_tokens, "sampling",
+                                 teacher_rows.to(source_tokens.device, torch.uint8).contiguous(), free_steps)
+
+    def _forward(self, source_tokens, target_tokens, decoding_strategy, teacher_rows=None, free_steps=0):
         lib = L.lib()
         self._ensure_flat()
         dev = source_tokens.device
@@ -337,13 +357,21 @@ class Seq2SeqBase(nn.Module):
             counter = 2 * self._calls
         seed = (torch.initial_seed() * 0x9E3779B97F4A7C15 + counter * 0xD1B54A32D192ED03 + self._salt * 0x2545F4914F6CDD1D) % (1 << 64)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        L.check(lib.pnmn_pg_forward(
-            ctypes.byref(self._desc), ctypes.c_void_p(self._flat.data_ptr()), ctypes.c_void_p(source.data_ptr()),
-            ctypes.c_void_p(target.data_ptr()) if teacher else None, B, Tq, Tp, S,
-            1 if decoding_strategy == "sampling" else 0, ctypes.c_uint64(seed), 1 if need_grad else 0,
-            ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(raw.data_ptr()), ctypes.c_void_p(predictions.data_ptr()),
-            ctypes.c_void_p(loss.data_ptr()), ctypes.c_void_p(logits.data_ptr()) if logits is not None else None, stream),
-            "pnmn_pg_forward")
+        if teacher_rows is not None:
+            L.check(lib.pnmn_pg_forward_mixed(
+                ctypes.byref(self._desc), ctypes.c_void_p(self._flat.data_ptr()), ctypes.c_void_p(source.data_ptr()),
+                ctypes.c_void_p(target.data_ptr()), ctypes.c_void_p(teacher_rows.data_ptr()), free_steps, B, Tq, Tp,
+                ctypes.c_uint64(seed), 1 if need_grad else 0, ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(raw.data_ptr()),
+                ctypes.c_void_p(predictions.data_ptr()), ctypes.c_void_p(loss.data_ptr()),
+                ctypes.c_void_p(logits.data_ptr()) if logits is not None else None, stream), "pnmn_pg_forward_mixed")
+        else:
+            L.check(lib.pnmn_pg_forward(
+                ctypes.byref(self._desc), ctypes.c_void_p(self._flat.data_ptr()), ctypes.c_void_p(source.data_ptr()),
+                ctypes.c_void_p(target.data_ptr()) if teacher else None, B, Tq, Tp, S,
+                1 if decoding_strategy == "sampling" else 0, ctypes.c_uint64(seed), 1 if need_grad else 0,
+                ctypes.c_void_p(ws.data_ptr()), ctypes.c_void_p(raw.data_ptr()), ctypes.c_void_p(predictions.data_ptr()),
+                ctypes.c_void_p(loss.data_ptr()), ctypes.c_void_p(logits.data_ptr()) if logits is not None else None, stream),
+                "pnmn_pg_forward")
         if need_grad:
             params = [p for _, p in self.named_parameters()]
             slices = [(o, n, shape) for _, o, n, shape in self._layout]
@@ -351,12 +379,12 @@ class Seq2SeqBase(nn.Module):
         else:
             run.close()
 
-        if self.handover_predictions:
+        if self.handover_predictions and teacher_rows is None:
             _handover(predictions)
         output_dict = {"predictions": predictions, "loss": loss}
         if self.return_logits:
             output_dict["logits"], output_dict["raw_predictions"] = logits, raw
-        if teacher and not self.training:
+        if teacher and not self.training and teacher_rows is None:
             self._record_metrics(predictions, target, loss)   # seq2seq_base.py:258-274
         return output_dict
 

@@ -201,9 +201,11 @@ def _state(module):
     return {k: v.detach().cpu().clone().requires_grad_(True) for k, v in module.state_dict().items()}
 
 
-def test_joint_iteration_matches_oracle(trained):
+@pytest.mark.parametrize("fused", [True, False], ids=["fused_passes", "one_pass_per_call"])
+def test_joint_iteration_matches_oracle(trained, fused):
     vocab, pg, qr, nmn, prior, _ = trained
-    step = JointTrainingStep(pg, qr, nmn, prior, alpha=100.0, beta=0.1, gamma=1.0, delta=0.99, lr=1e-6, concurrent=True)
+    step = JointTrainingStep(pg, qr, nmn, prior, alpha=100.0, beta=0.1, gamma=1.0, delta=0.99, lr=1e-6, concurrent=True,
+                             fused=fused)
     pg.return_logits = True
     # a larger batch first: the compared iteration then runs in workspaces whose padding rows hold stale data
     step.optimizer.zero_grad()
@@ -264,10 +266,16 @@ def test_concurrent_streams_and_handover_change_nothing(trained):
     vocab, pg, qr, nmn, prior, _ = trained
     batch = make_joint_batch(vocab, 40, seed=21)
     results = []
+    for fused in (False, True):
+        _compare_variants(vocab, pg, qr, nmn, prior, batch, fused)
+
+
+def _compare_variants(vocab, pg, qr, nmn, prior, batch, fused):
+    results = []
     for concurrent, handover in ((True, True), (False, True), (False, False)):
-        step = JointTrainingStep(pg, qr, nmn, prior, lr=1e-6, concurrent=concurrent)
+        step = JointTrainingStep(pg, qr, nmn, prior, lr=1e-6, concurrent=concurrent, fused=fused)
         pg.handover_predictions = handover
-        pg._calls = qr._calls = prior._calls = 100          # same Philox keys for every variant
+        pg._calls = qr._calls = prior._calls = pg._teacher_calls = qr._teacher_calls = 100   # same Philox keys for every variant
         step.optimizer.zero_grad()
         out = step.do_iteration(batch)
         torch.cuda.synchronize()
@@ -328,6 +336,6 @@ def test_device_prefetcher_slot_reuse_and_ordering():
     feed2 = DevicePrefetcher(dev, depth=2)
     feed2.submit("a", (torch.ones(16).pin_memory(),))
     (a,) = feed2.get("a")
-    feed2.submit("b", (torch.ones(32).pin_memory() * 2,))   # other shape: slot re-allocated
+    feed2.submit("b", ((torch.ones(32) * 2).pin_memory(),))   # other shape: slot re-allocated
     (b,) = feed2.get("b")
     assert float(a.sum()) == 16 and float(b.sum()) == 64
