@@ -84,6 +84,18 @@ class JointTrainingStep:
         self.group = group
         self._sup_stream: Optional[torch.cuda.Stream] = None
         self.iteration = -1
+        self.trace = None   # diagnostics: a list collects (label, CUDA event) marks of one step (scripts/joint_timeline.py)
+
+    def _streams(self, dev):
+        if getattr(self, "_side_streams", None) is None or self._side_streams[0].device != dev:
+            self._side_streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
+        return self._side_streams
+
+    def _mark(self, label: str) -> None:
+        if self.trace is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            self.trace.append((label, ev))
 
     @classmethod
     def from_config(cls, config, program_generator, question_reconstructor, nmn, program_prior, **kw):
@@ -161,33 +173,52 @@ class JointTrainingStep:
         teacher_rows = torch.zeros(nu + ns, dtype=torch.uint8, device=dev)
         teacher_rows[nu:] = 1
 
-        pg = pg_m.forward_mixed(q_all, targets, teacher_rows, free_steps=free)       # elbo.py:230-233 + trainer :164-168
-        sampled = pg["predictions"][:nu, :free].contiguous()
-        if pg_m.handover_predictions:
-            _handover(sampled)                                                         # the module network compiles on the host
-        pwidth = max(free, p_s.shape[1])
-        programs_all = torch.zeros(nu + ns, pwidth, dtype=torch.int64, device=dev)
-        programs_all[:nu, :free] = sampled
-        programs_all[nu:, : p_s.shape[1]] = p_s
-
-        def reconstruct():
-            qr = qr_m(programs_all, q_all, decoding_strategy="sampling")              # elbo.py:236-238 + trainer :169-173
-            prior = self.program_prior(sampled)                                        # elbo.py:256
-            return qr, prior
-
-        if self.concurrent:
-            if self._qr_stream is None or self._qr_stream.device != dev:
-                self._qr_stream = torch.cuda.Stream(dev)
-            side = self._qr_stream
-            side.wait_stream(main)
-            with torch.cuda.stream(side):
-                qr, prior = reconstruct()
+        self._mark("start")
+        # Streams: the generator, the reconstructor and the prior each get their own, the module network stays on the
+        # caller's.  Autograd replays every pass on the stream its forward ran on, so the three backward passes (generator,
+        # reconstructor, module network) are concurrent as well instead of queueing behind one another.
+        streams = self._streams(dev) if self.concurrent else None
+        if streams is not None:
+            s_pg, s_qr, s_prior = streams
+            s_pg.wait_stream(main)
+            with torch.cuda.stream(s_pg):
+                pg = pg_m.forward_mixed(q_all, targets, teacher_rows, free_steps=free)   # elbo.py:230-233 + trainer :164-168
+                sampled = pg["predictions"][:nu, :free].contiguous()
+                if pg_m.handover_predictions:
+                    _handover(sampled)                                                 # the module network compiles on the host
+                pwidth = max(free, p_s.shape[1])
+                programs_all = torch.zeros(nu + ns, pwidth, dtype=torch.int64, device=dev)
+                programs_all[:nu, :free] = sampled
+                programs_all[nu:, : p_s.shape[1]] = p_s
+                self._mark("pg_fwd_end(pg)")
+            s_qr.wait_stream(s_pg)
+            s_prior.wait_stream(s_pg)
+            main.wait_stream(s_pg)
+            with torch.cuda.stream(s_qr):
+                qr = qr_m(programs_all, q_all, decoding_strategy="sampling")          # elbo.py:236-238 + trainer :169-173
+                self._mark("qr_fwd_end(qr)")
+            with torch.cuda.stream(s_prior):
+                prior = self.program_prior(sampled)                                    # elbo.py:256
+                self._mark("prior_fwd_end(prior)")
             nmn = self.nmn(img, sampled, ans)                                          # elbo.py:239
-            main.wait_stream(side)
-            for t in (qr["loss"], prior["loss"], programs_all):
-                t.record_stream(main if t is not programs_all else side)
+            self._mark("nmn_fwd_end")
+            main.wait_stream(s_qr)
+            main.wait_stream(s_prior)
+            for t in (pg["loss"], pg["predictions"], sampled, programs_all, qr["loss"], prior["loss"]):
+                t.record_stream(main)
+            programs_all.record_stream(s_qr)
+            sampled.record_stream(s_prior)
         else:
-            qr, prior = reconstruct()
+            pg = pg_m.forward_mixed(q_all, targets, teacher_rows, free_steps=free)
+            sampled = pg["predictions"][:nu, :free].contiguous()
+            if pg_m.handover_predictions:
+                _handover(sampled)
+            pwidth = max(free, p_s.shape[1])
+            programs_all = torch.zeros(nu + ns, pwidth, dtype=torch.int64, device=dev)
+            programs_all[:nu, :free] = sampled
+            programs_all[nu:, : p_s.shape[1]] = p_s
+            qr = qr_m(programs_all, q_all, decoding_strategy="sampling")
+            prior = self.program_prior(sampled)
             nmn = self.nmn(img, sampled, ans)
 
         pg_loss_u, qr_loss_u = pg["loss"][:nu], qr["loss"][:nu]
@@ -195,7 +226,9 @@ class JointTrainingStep:
         nmn_loss = elbo_output_dict.pop("nmn_loss")
         pg_sup, qr_sup = pg["loss"][nu:].mean(), qr["loss"][nu:].mean()
         loss_objective = self.gamma * nmn_loss - elbo_output_dict["elbo"] + self.alpha * (pg_sup + qr_sup)
+        self._mark("objective")
         loss_objective.backward()
+        self._mark("backward_end")
 
         self.elbo.last_outputs = {
             "program_generator": {"predictions": sampled, "loss": pg_loss_u,
@@ -223,5 +256,6 @@ class JointTrainingStep:
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             self.allreduce_gradients()
         self.optimizer.step()
+        self._mark("optimizer_end")
         self.iteration += 1
         return out
