@@ -10,7 +10,7 @@ import subprocess
 from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpnmn.so")
+LIB_PATH = os.environ.get("PNMN_LIB") or os.path.join(_HERE, "libpnmn.so")   # (PNMN_LIB: experiments with build variants)
 CSRC = os.path.join(_HERE, "csrc")
 
 NSMAX = 2

@@ -653,7 +653,11 @@ cudaError_t launch_exec(const uint8_t* d_tasks, const TaskMeta* d_meta, int n_ta
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  const int grid = n_tasks < kExCtasPerSM * sms ? n_tasks : kExCtasPerSM * sms;
+  // PNMN_EXEC_CTAS caps the persistent grid (default: two CTAs per SM).  With fewer CTAs than 2 x SMs some SMs keep enough
+  // shared memory free for the kernels of OTHER streams (the LSTM passes of the joint-training step) to run alongside.
+  static const int cap = std::getenv("PNMN_EXEC_CTAS") ? std::atoi(std::getenv("PNMN_EXEC_CTAS")) : 0;
+  int grid = n_tasks < kExCtasPerSM * sms ? n_tasks : kExCtasPerSM * sms;
+  if (cap > 0 && grid > cap) grid = cap;
   static const int dbg = std::getenv("PNMN_EXEC_DBG") ? std::atoi(std::getenv("PNMN_EXEC_DBG")) : 0;  // timing experiments only
   if (d_trace) exec_kernel<true><<<grid, kExThreads, kExSmem, stream>>>(d_tasks, d_meta, n_tasks, d_cfgs, d_counter, d_done, d_trace, dbg);
   else exec_kernel<false><<<grid, kExThreads, kExSmem, stream>>>(d_tasks, d_meta, n_tasks, d_cfgs, d_counter, d_done, d_trace, dbg);

@@ -23,7 +23,10 @@ bool seq_use_pdl() {
 }
 
 constexpr int kGThreads = 256;
-constexpr int kGStages = 4;
+#ifndef PNMN_PG_STAGES
+#define PNMN_PG_STAGES 4
+#endif
+constexpr int kGStages = PNMN_PG_STAGES;
 constexpr int kGABytes = 128 * 64 * 2;   // one 64-deep K chunk of a 128-row activation tile (hi or lo)
 constexpr int kGWBytes = 64 * 64 * 2;    // the same of a 64-row weight tile
 constexpr int kGStage = 2 * kGABytes + 2 * kGWBytes;

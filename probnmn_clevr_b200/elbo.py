@@ -61,6 +61,15 @@ class _ElboGlueFn(torch.autograd.Function):
         return d_pg, d_qr, None, d_nmn, None, None, None, None, None
 
 
+def elbo_glue(pg_loss, qr_loss, prior_loss, nmn_loss, baseline, beta, gamma, decay, mode=0):
+    """``pnmn_elbo_glue`` without autograd: returns ``(stats[5], centered[n])`` and updates ``baseline`` in place.  For callers
+    that apply the closed-form gradients of the objective themselves (``joint.JointTrainingStep``): with lp = -loss,
+    d(-elbo)/d(pg_loss) = (beta - centered) / n, d(-elbo)/d(qr_loss) = 1 / n (elbo.py:61-89)."""
+    return _ElboGlueFn.apply(pg_loss.detach(), None if qr_loss is None else qr_loss.detach(),
+                             None if prior_loss is None else prior_loss.detach(),
+                             None if nmn_loss is None else nmn_loss.detach(), baseline, beta, gamma, decay, mode)
+
+
 class Reinforce(nn.Module):
     r"""REINFORCE with a decaying moving-average baseline (elbo.py:12-34): ``forward(inputs, reward)`` returns
     ``inputs * (reward.detach() - baseline)`` and then moves the baseline by ``decay * mean(reward - baseline)`` -- not a

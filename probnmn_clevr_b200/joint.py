@@ -27,7 +27,7 @@ from typing import Any, Dict, Optional
 import torch
 import torch.distributed as dist
 
-from .elbo import JointTrainingElbo
+from .elbo import JointTrainingElbo, elbo_glue
 from .optim import FusedClampAdam
 
 
@@ -174,69 +174,93 @@ class JointTrainingStep:
         teacher_rows[nu:] = 1
 
         self._mark("start")
-        # Streams: the generator, the reconstructor and the prior each get their own, the module network stays on the
-        # caller's.  Autograd replays every pass on the stream its forward ran on, so the three backward passes (generator,
-        # reconstructor, module network) are concurrent as well instead of queueing behind one another.
-        streams = self._streams(dev) if self.concurrent else None
-        if streams is not None:
-            s_pg, s_qr, s_prior = streams
+        # The objective is  gamma * mean(nmn_loss) - elbo + alpha * (mean(pg_loss_sup) + mean(qr_loss_sup))  with
+        # -elbo = mean(qr_loss_u + (beta - centered) * pg_loss_u)  over the unsupervised rows (lp = -loss, elbo.py:61-89) and
+        # centered = detached reward - baseline.  Its gradient w.r.t. every per-row loss is therefore known in closed form:
+        #     d/d nmn_loss[b] = gamma / nu        d/d qr_loss[b] = 1 / nu (unsupervised), alpha / ns (supervised)
+        #     d/d pg_loss[b]  = (beta - centered[b]) / nu (unsupervised), alpha / ns (supervised)
+        # Only the generator's depends on the other models' outputs, so the reconstructor's and the module network's
+        # backward passes are started right behind their forward passes instead of after the whole forward phase.
+        # Streams: generator, reconstructor and prior each get their own, the module network stays on the caller's; autograd
+        # replays every pass on the stream its forward ran on.
+        nu_f, ns_f = float(nu), float(ns)
+        coef_qr = torch.empty(nu + ns, dtype=torch.float32, device=dev)
+        coef_qr[:nu] = 1.0 / nu_f
+        coef_qr[nu:] = self.alpha / ns_f
+        coef_nmn = torch.full((nu,), self.gamma / nu_f, dtype=torch.float32, device=dev)
+        pwidth = max(free, p_s.shape[1])
+        streams = self._streams(dev) if self.concurrent else (main, main, main)
+        s_pg, s_qr, s_prior = streams
+        if self.concurrent:
             s_pg.wait_stream(main)
-            with torch.cuda.stream(s_pg):
-                pg = pg_m.forward_mixed(q_all, targets, teacher_rows, free_steps=free)   # elbo.py:230-233 + trainer :164-168
-                sampled = pg["predictions"][:nu, :free].contiguous()
-                if pg_m.handover_predictions:
-                    _handover(sampled)                                                 # the module network compiles on the host
-                pwidth = max(free, p_s.shape[1])
-                programs_all = torch.zeros(nu + ns, pwidth, dtype=torch.int64, device=dev)
-                programs_all[:nu, :free] = sampled
-                programs_all[nu:, : p_s.shape[1]] = p_s
-                self._mark("pg_fwd_end(pg)")
-            s_qr.wait_stream(s_pg)
-            s_prior.wait_stream(s_pg)
-            main.wait_stream(s_pg)
-            with torch.cuda.stream(s_qr):
-                qr = qr_m(programs_all, q_all, decoding_strategy="sampling")          # elbo.py:236-238 + trainer :169-173
-                self._mark("qr_fwd_end(qr)")
-            with torch.cuda.stream(s_prior):
-                prior = self.program_prior(sampled)                                    # elbo.py:256
-                self._mark("prior_fwd_end(prior)")
-            nmn = self.nmn(img, sampled, ans)                                          # elbo.py:239
-            self._mark("nmn_fwd_end")
-            main.wait_stream(s_qr)
-            main.wait_stream(s_prior)
-            for t in (pg["loss"], pg["predictions"], sampled, programs_all, qr["loss"], prior["loss"]):
-                t.record_stream(main)
-            programs_all.record_stream(s_qr)
-            sampled.record_stream(s_prior)
-        else:
-            pg = pg_m.forward_mixed(q_all, targets, teacher_rows, free_steps=free)
+        with torch.cuda.stream(s_pg):
+            pg = pg_m.forward_mixed(q_all, targets, teacher_rows, free_steps=free)       # elbo.py:230-233 + trainer :164-168
             sampled = pg["predictions"][:nu, :free].contiguous()
             if pg_m.handover_predictions:
-                _handover(sampled)
-            pwidth = max(free, p_s.shape[1])
+                _handover(sampled)                                                     # the module network compiles on the host
             programs_all = torch.zeros(nu + ns, pwidth, dtype=torch.int64, device=dev)
             programs_all[:nu, :free] = sampled
             programs_all[nu:, : p_s.shape[1]] = p_s
-            qr = qr_m(programs_all, q_all, decoding_strategy="sampling")
-            prior = self.program_prior(sampled)
-            nmn = self.nmn(img, sampled, ans)
-
-        pg_loss_u, qr_loss_u = pg["loss"][:nu], qr["loss"][:nu]
-        elbo_output_dict = self.elbo._glue(pg_loss_u, qr_loss_u, prior["loss"], nmn["loss"], self.gamma, 0)
-        nmn_loss = elbo_output_dict.pop("nmn_loss")
-        pg_sup, qr_sup = pg["loss"][nu:].mean(), qr["loss"][nu:].mean()
-        loss_objective = self.gamma * nmn_loss - elbo_output_dict["elbo"] + self.alpha * (pg_sup + qr_sup)
+            self._mark("pg_fwd_end(pg)")
+        if self.concurrent:
+            s_qr.wait_stream(s_pg)
+            s_prior.wait_stream(s_pg)
+            main.wait_stream(s_pg)
+        with torch.cuda.stream(s_qr):
+            qr = qr_m(programs_all, q_all, decoding_strategy="sampling")              # elbo.py:236-238 + trainer :169-173
+            qr_loss = qr["loss"].detach()
+            qr_fwd_done = torch.cuda.Event()
+            qr_fwd_done.record()
+            self._mark("qr_fwd_end(qr)")
+            torch.autograd.backward([qr["loss"]], [coef_qr])
+            self._mark("qr_bwd_end(qr)")
+        with torch.cuda.stream(s_prior):
+            prior = self.program_prior(sampled)                                        # elbo.py:256
+            self._mark("prior_fwd_end(prior)")
+        nmn = self.nmn(img, sampled, ans)                                              # elbo.py:239
+        self._mark("nmn_fwd_end")
+        nmn_loss_rows = nmn["loss"].detach()
+        torch.autograd.backward([nmn["loss"]], [coef_nmn])
+        self._mark("nmn_bwd_end")
+        if self.concurrent:
+            main.wait_event(qr_fwd_done)
+            main.wait_stream(s_prior)
+        pg_loss = pg["loss"].detach()
+        pg_loss_u, qr_loss_u = pg_loss[:nu], qr_loss[:nu]
+        baseline = self.elbo._reinforce.baseline_on(dev)
+        stats, centered = elbo_glue(pg_loss_u, qr_loss_u, prior["loss"], nmn_loss_rows, baseline, self.elbo._beta, self.gamma,
+                                    self.elbo._reinforce._baseline_decay, 0)
+        coef_pg = torch.empty(nu + ns, dtype=torch.float32, device=dev)
+        coef_pg[:nu] = (self.elbo._beta - centered) / nu_f
+        coef_pg[nu:] = self.alpha / ns_f
+        pg_sup, qr_sup = pg_loss[nu:].mean(), qr_loss[nu:].mean()
+        loss_objective = self.gamma * stats[4] - stats[2] + self.alpha * (pg_sup + qr_sup)
         self._mark("objective")
-        loss_objective.backward()
+        if self.concurrent:
+            s_pg.wait_stream(main)
+        with torch.cuda.stream(s_pg):
+            torch.autograd.backward([pg["loss"]], [coef_pg])
+            self._mark("pg_bwd_end(pg)")
+        if self.concurrent:
+            main.wait_stream(s_pg)
+            main.wait_stream(s_qr)
+            for t in (pg["loss"], pg["predictions"], sampled, programs_all, qr["loss"], prior["loss"], coef_pg, coef_qr, pg_loss,
+                      qr_loss):
+                t.record_stream(main)
+            programs_all.record_stream(s_qr)
+            coef_qr.record_stream(s_qr)
+            coef_pg.record_stream(s_pg)
+            sampled.record_stream(s_prior)
         self._mark("backward_end")
 
         self.elbo.last_outputs = {
             "program_generator": {"predictions": sampled, "loss": pg_loss_u,
                                   "raw_predictions": pg["raw_predictions"][:nu, :free] if "raw_predictions" in pg else None},
             "question_reconstructor": {"loss": qr_loss_u}, "nmn": nmn, "program_prior": prior}
-        return {"loss": {"nmn": nmn_loss.detach(), "question_reconstruction_gt": qr_sup.detach(),
-                         "program_generation_gt": pg_sup.detach()},
-                "elbo": {k: v.detach() for k, v in elbo_output_dict.items()}, "objective": loss_objective.detach()}
+        return {"loss": {"nmn": stats[4], "question_reconstruction_gt": qr_sup, "program_generation_gt": pg_sup},
+                "elbo": {"reconstruction_likelihood": stats[0], "kl_divergence": stats[1], "elbo": stats[2],
+                         "reinforce_reward": stats[3]},
+                "objective": loss_objective}
 
     def _supervised(self, questions, programs):
         """alpha * (log q(z'|x') + log p(x'|z')) over the rows with ground-truth programs (:152-176)."""
