@@ -220,8 +220,6 @@ class JointTrainingStep:
         nmn = self.nmn(img, sampled, ans)                                              # elbo.py:239
         self._mark("nmn_fwd_end")
         nmn_loss_rows = nmn["loss"].detach()
-        torch.autograd.backward([nmn["loss"]], [coef_nmn])
-        self._mark("nmn_bwd_end")
         if self.concurrent:
             main.wait_event(qr_fwd_done)
             main.wait_stream(s_prior)
@@ -233,14 +231,17 @@ class JointTrainingStep:
         coef_pg = torch.empty(nu + ns, dtype=torch.float32, device=dev)
         coef_pg[:nu] = (self.elbo._beta - centered) / nu_f
         coef_pg[nu:] = self.alpha / ns_f
-        pg_sup, qr_sup = pg_loss[nu:].mean(), qr_loss[nu:].mean()
-        loss_objective = self.gamma * stats[4] - stats[2] + self.alpha * (pg_sup + qr_sup)
         self._mark("objective")
+        # the generator's backward pass first (it is the longest chain still to run), then the module network's
         if self.concurrent:
             s_pg.wait_stream(main)
         with torch.cuda.stream(s_pg):
             torch.autograd.backward([pg["loss"]], [coef_pg])
             self._mark("pg_bwd_end(pg)")
+        torch.autograd.backward([nmn["loss"]], [coef_nmn])
+        self._mark("nmn_bwd_end")
+        pg_sup, qr_sup = pg_loss[nu:].mean(), qr_loss[nu:].mean()
+        loss_objective = self.gamma * stats[4] - stats[2] + self.alpha * (pg_sup + qr_sup)
         if self.concurrent:
             main.wait_stream(s_pg)
             main.wait_stream(s_qr)
