@@ -253,29 +253,38 @@ extern "C" int pnmn_prior_forward(const pnmn_prior_desc* m, const float* params,
   g.B = L.Bp; g.chunks_per_src = 4; g.a_K[0] = g.a_K[1] = kSH; g.a_lo[0] = g.a_lo[1] = L.slotf; g.h_op_lo = L.slotf;
   g.out_op_lo = L.slotf;
   g.len = at<int>(ws, L.len);
-  for (int t = 0; t < L.Ts; ++t) {   // layer 0
-    g.t = t; g.K = kSH;
-    g.a[0] = at<__half>(ws, L.h0op) + t * L.slotop; g.a[1] = nullptr;
-    g.w = packed + L.pk_hh0; g.w_lo = static_cast<int64_t>(kSG) * kSH;
-    g.table = at<float>(ws, L.P0); g.tok = at<int>(ws, L.tok) + t; g.tok_stride = L.Ts;
-    g.h_prev = at<float>(ws, L.h0f) + t * L.slotf; g.c_prev = at<float>(ws, L.c0f) + t * L.slotf;
-    g.h_out = at<float>(ws, L.h0f) + (t + 1) * L.slotf; g.c_out = at<float>(ws, L.c0f) + (t + 1) * L.slotf;
-    g.h_op = at<__half>(ws, L.h0op) + (t + 1) * L.slotop;
-    g.gates = nullptr; g.out_f = nullptr; g.out_op = at<__half>(ws, L.out0op) + t * L.slotop;
-    CUDA_OK(launch_step_gemm(g, EPI_LSTM, kSG / 64, MT, false, st));
-  }
-  for (int t = 0; t < L.Ts; ++t) {   // layer 1
-    g.t = t; g.K = 2 * kSH;
-    g.a[0] = at<__half>(ws, L.out0op) + t * L.slotop; g.a[1] = at<__half>(ws, L.h1op) + t * L.slotop;
-    g.w = packed + L.pk_1; g.w_lo = static_cast<int64_t>(kSG) * 2 * kSH;
-    g.table = at<float>(ws, L.P1); g.tok = nullptr; g.tok_stride = 0;
-    g.h_prev = at<float>(ws, L.h1f) + t * L.slotf; g.c_prev = at<float>(ws, L.c1f) + t * L.slotf;
-    g.h_out = at<float>(ws, L.h1f) + (t + 1) * L.slotf; g.c_out = at<float>(ws, L.c1f) + (t + 1) * L.slotf;
-    g.h_op = at<__half>(ws, L.h1op) + (t + 1) * L.slotop;
-    g.gates = nullptr;
-    g.out_f = at<float>(ws, L.enc) + static_cast<int64_t>(t) * kSH; g.out_stride = static_cast<int64_t>(L.Ts) * kSH;
-    g.out_op = nullptr;
-    CUDA_OK(launch_step_gemm(g, EPI_LSTM, kSG / 64, MT, false, st));
+  auto l0 = [&](int t) {
+    GemmArgs a = g;
+    a.t = t; a.K = kSH;
+    a.a[0] = at<__half>(ws, L.h0op) + t * L.slotop; a.a[1] = nullptr;
+    a.w = packed + L.pk_hh0; a.w_lo = static_cast<int64_t>(kSG) * kSH;
+    a.table = at<float>(ws, L.P0); a.tok = at<int>(ws, L.tok) + t; a.tok_stride = L.Ts;
+    a.h_prev = at<float>(ws, L.h0f) + t * L.slotf; a.c_prev = at<float>(ws, L.c0f) + t * L.slotf;
+    a.h_out = at<float>(ws, L.h0f) + (t + 1) * L.slotf; a.c_out = at<float>(ws, L.c0f) + (t + 1) * L.slotf;
+    a.h_op = at<__half>(ws, L.h0op) + (t + 1) * L.slotop;
+    a.gates = nullptr; a.out_f = nullptr; a.out_op = at<__half>(ws, L.out0op) + t * L.slotop;
+    return a;
+  };
+  auto l1 = [&](int t) {
+    GemmArgs a = g;
+    a.t = t; a.K = 2 * kSH;
+    a.a[0] = at<__half>(ws, L.out0op) + t * L.slotop; a.a[1] = at<__half>(ws, L.h1op) + t * L.slotop;
+    a.w = packed + L.pk_1; a.w_lo = static_cast<int64_t>(kSG) * 2 * kSH;
+    a.table = at<float>(ws, L.P1); a.tok = nullptr; a.tok_stride = 0;
+    a.h_prev = at<float>(ws, L.h1f) + t * L.slotf; a.c_prev = at<float>(ws, L.c1f) + t * L.slotf;
+    a.h_out = at<float>(ws, L.h1f) + (t + 1) * L.slotf; a.c_out = at<float>(ws, L.c1f) + (t + 1) * L.slotf;
+    a.h_op = at<__half>(ws, L.h1op) + (t + 1) * L.slotop;
+    a.gates = nullptr;
+    a.out_f = at<float>(ws, L.enc) + static_cast<int64_t>(t) * kSH; a.out_stride = static_cast<int64_t>(L.Ts) * kSH;
+    a.out_op = nullptr;
+    return a;
+  };
+  for (int k = 0; k <= L.Ts; ++k) {   // wavefront over the two layers (seq2seq_api.cu)
+    GemmPair pr;
+    pr.m_tiles = MT; pr.n_tiles[0] = pr.n_tiles[1] = kSG / 64;
+    if (k < L.Ts && k >= 1) { pr.count = 2; pr.g[0] = l0(k); pr.g[1] = l1(k - 1); }
+    else { pr.count = 1; pr.g[0] = k < L.Ts ? l0(k) : l1(k - 1); pr.g[1] = pr.g[0]; }
+    CUDA_OK(launch_step_gemm_pair(pr, EPI_LSTM, false, st));
   }
     return 0;
   });
@@ -285,6 +294,6 @@ extern "C" int pnmn_prior_forward(const pnmn_prior_desc* m, const float* params,
   CUDA_OK(cudaGetLastError());
   prior_loss_kernel<<<(L.B + 127) / 128, 128, 0, st>>>(nll, at<int>(ws, L.tok), L.B, L.Ts, loss);
   CUDA_OK(cudaGetLastError());
-  pnmn::count_launches(1 + 1 + 3 + 2 * L.Ts + 2);
+  pnmn::count_launches(1 + 1 + 3 + (L.Ts + 1) + 2);
   return 0;
 }

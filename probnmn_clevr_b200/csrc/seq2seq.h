@@ -102,6 +102,16 @@ struct GemmArgs {
 };
 
 cudaError_t launch_step_gemm(const GemmArgs& g, int epilogue, int n_tiles, int m_tiles, bool simt, cudaStream_t st);
+// Up to two independent step GEMMs in ONE launch (blockIdx.y = which * m_tiles + m tile): step k of LSTM layer 0 together
+// with step k-1 of layer 1 (a wavefront over the two encoder layers: Ts + 1 dependent launches instead of 2 Ts), and the
+// same for their data-gradient GEMMs in the backward pass.
+struct GemmPair {
+  GemmArgs g[2];
+  int n_tiles[2];
+  int m_tiles;
+  int count;   // 1 or 2
+};
+cudaError_t launch_step_gemm_pair(const GemmPair& p, int epilogue, bool simt, cudaStream_t st);
 
 // ---- weight-gradient GEMM (contraction over batch rows and time) ------------------------------------
 //   dW[g][k] += scale[1] * sum_{t, b} dG[t][b][g] * X[t][b][k]
@@ -224,6 +234,8 @@ struct EncCellBwdArgs {
   const float* scale;
 };
 cudaError_t launch_enc_cell_bwd(const EncCellBwdArgs& a, cudaStream_t st);
+struct EncCellBwdPair { EncCellBwdArgs a[2]; int count; };   // blockIdx.y selects: the two encoder layers in one launch
+cudaError_t launch_enc_cell_bwd_pair(const EncCellBwdPair& p, cudaStream_t st);
 
 // dP[v][g] (+)= scale[1] * sum_{(t,b): tok == v} dG[t][b][g];  tok == nullptr: everything goes to row 0
 struct TableGradArgs {

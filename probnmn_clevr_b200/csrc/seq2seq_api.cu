@@ -53,7 +53,7 @@ struct Layout {
   int64_t h0f, c0f, h0op, out0op, g0;      // encoder layer 0
   int64_t h1f, c1f, h1op, g1, enc;         // encoder layer 1 (+ decoder slots appended to h1f / h1op)
   int64_t cdf, attop, gd;                  // decoder
-  int64_t dh, dc, datt, denc, dout0, dgd, dg1, dg0, scale;
+  int64_t dh, dc, dh0, dc0, datt, denc, dout0, dgd, dg1, dg0, scale;
   int64_t seed, gstage, gws, extent, rowmode;   // Philox key; incoming gradient padded to Bp; parameter gradients of this call
   int64_t total;
 };
@@ -107,6 +107,7 @@ Layout make_layout(const pnmn_pg_desc* m, int B, int Tq, int Tp, int S, bool nee
     L.dlogits = take(4ll * S * d.Bp * d.Vt);
     L.dP0 = take(4ll * d.Vs * kSG); L.dPd = take(4ll * d.Vt * kSG); L.dP1 = take(4ll * kSG);
     L.dh = take(4 * L.slotf); L.dc = take(4 * L.slotf); L.datt = take(4 * L.slotf);
+    L.dh0 = take(4 * L.slotf); L.dc0 = take(4 * L.slotf);
     L.denc = take(4ll * Bq * d.Ts * kSH); L.dout0 = take(4 * L.slotf * d.Ts);
     L.dgd = take(2 * L.slotdg * S); L.dg1 = take(2 * L.slotdg * d.Ts); L.dg0 = take(2 * L.slotdg * d.Ts);
   }
@@ -313,32 +314,41 @@ static int pg_forward_impl(const pnmn_pg_desc* m, const float* params, const int
   g.B = d.B; g.chunks_per_src = 4; g.a_K[0] = g.a_K[1] = kSH; g.a_lo[0] = g.a_lo[1] = L.slotf; g.h_op_lo = L.slotf;
   g.out_op_lo = L.slotf;
   g.len = at<int>(ws, L.src_len);
-  // ---- encoder layer 0 ------------------------------------------------------------------------------------
-  for (int t = 0; t < d.Ts; ++t) {
-    g.t = t; g.K = kSH;
-    g.a[0] = at<__half>(ws, L.h0op) + t * L.slotop; g.a[1] = nullptr;
-    g.w = packed + L.pk_hh0; g.w_lo = static_cast<int64_t>(kSG) * kSH;
-    g.table = at<float>(ws, L.P0); g.tok = at<int>(ws, L.src) + t; g.tok_stride = d.Ts;
-    g.h_prev = at<float>(ws, L.h0f) + t * L.slotf; g.c_prev = at<float>(ws, L.c0f) + t * L.slotf;
-    g.h_out = at<float>(ws, L.h0f) + (t + 1) * L.slotf; g.c_out = at<float>(ws, L.c0f) + (t + 1) * L.slotf;
-    g.h_op = at<__half>(ws, L.h0op) + (t + 1) * L.slotop;
-    g.gates = need_grad ? at<float>(ws, L.g0) + t * L.slotg : nullptr;
-    g.out_f = nullptr; g.out_op = at<__half>(ws, L.out0op) + t * L.slotop;
-    CUDA_OK(launch_step_gemm(g, EPI_LSTM, kSG / 64, MT, simt, st));
-  }
-  // ---- encoder layer 1 ------------------------------------------------------------------------------------
-  for (int t = 0; t < d.Ts; ++t) {
-    g.t = t; g.K = 2 * kSH;
-    g.a[0] = at<__half>(ws, L.out0op) + t * L.slotop; g.a[1] = at<__half>(ws, L.h1op) + t * L.slotop;
-    g.w = packed + L.pk_1; g.w_lo = static_cast<int64_t>(kSG) * 2 * kSH;
-    g.table = at<float>(ws, L.P1); g.tok = nullptr; g.tok_stride = 0;
-    g.h_prev = at<float>(ws, L.h1f) + t * L.slotf; g.c_prev = at<float>(ws, L.c1f) + t * L.slotf;
-    g.h_out = at<float>(ws, L.h1f) + (t + 1) * L.slotf; g.c_out = at<float>(ws, L.c1f) + (t + 1) * L.slotf;
-    g.h_op = at<__half>(ws, L.h1op) + (t + 1) * L.slotop;
-    g.gates = need_grad ? at<float>(ws, L.g1) + t * L.slotg : nullptr;
-    g.out_f = at<float>(ws, L.enc) + static_cast<int64_t>(t) * kSH; g.out_stride = static_cast<int64_t>(d.Ts) * kSH;
-    g.out_op = nullptr;
-    CUDA_OK(launch_step_gemm(g, EPI_LSTM, kSG / 64, MT, simt, st));
+  // ---- encoder: the two layers as a wavefront -- tick k runs step k of layer 0 and step k-1 of layer 1 in ONE launch
+  // (layer 1 at step k-1 needs layer 0's output of step k-1 and its own state of step k-2, both written by earlier ticks)
+  auto enc_l0 = [&](int t) {
+    GemmArgs a = g;
+    a.t = t; a.K = kSH;
+    a.a[0] = at<__half>(ws, L.h0op) + t * L.slotop; a.a[1] = nullptr;
+    a.w = packed + L.pk_hh0; a.w_lo = static_cast<int64_t>(kSG) * kSH;
+    a.table = at<float>(ws, L.P0); a.tok = at<int>(ws, L.src) + t; a.tok_stride = d.Ts;
+    a.h_prev = at<float>(ws, L.h0f) + t * L.slotf; a.c_prev = at<float>(ws, L.c0f) + t * L.slotf;
+    a.h_out = at<float>(ws, L.h0f) + (t + 1) * L.slotf; a.c_out = at<float>(ws, L.c0f) + (t + 1) * L.slotf;
+    a.h_op = at<__half>(ws, L.h0op) + (t + 1) * L.slotop;
+    a.gates = need_grad ? at<float>(ws, L.g0) + t * L.slotg : nullptr;
+    a.out_f = nullptr; a.out_op = at<__half>(ws, L.out0op) + t * L.slotop;
+    return a;
+  };
+  auto enc_l1 = [&](int t) {
+    GemmArgs a = g;
+    a.t = t; a.K = 2 * kSH;
+    a.a[0] = at<__half>(ws, L.out0op) + t * L.slotop; a.a[1] = at<__half>(ws, L.h1op) + t * L.slotop;
+    a.w = packed + L.pk_1; a.w_lo = static_cast<int64_t>(kSG) * 2 * kSH;
+    a.table = at<float>(ws, L.P1); a.tok = nullptr; a.tok_stride = 0;
+    a.h_prev = at<float>(ws, L.h1f) + t * L.slotf; a.c_prev = at<float>(ws, L.c1f) + t * L.slotf;
+    a.h_out = at<float>(ws, L.h1f) + (t + 1) * L.slotf; a.c_out = at<float>(ws, L.c1f) + (t + 1) * L.slotf;
+    a.h_op = at<__half>(ws, L.h1op) + (t + 1) * L.slotop;
+    a.gates = need_grad ? at<float>(ws, L.g1) + t * L.slotg : nullptr;
+    a.out_f = at<float>(ws, L.enc) + static_cast<int64_t>(t) * kSH; a.out_stride = static_cast<int64_t>(d.Ts) * kSH;
+    a.out_op = nullptr;
+    return a;
+  };
+  for (int k = 0; k <= d.Ts; ++k) {
+    GemmPair pr;
+    pr.m_tiles = MT; pr.n_tiles[0] = pr.n_tiles[1] = kSG / 64;
+    if (k < d.Ts && k >= 1) { pr.count = 2; pr.g[0] = enc_l0(k); pr.g[1] = enc_l1(k - 1); }
+    else { pr.count = 1; pr.g[0] = k < d.Ts ? enc_l0(k) : enc_l1(k - 1); pr.g[1] = pr.g[0]; }
+    CUDA_OK(launch_step_gemm_pair(pr, EPI_LSTM, simt, st));
   }
   // ---- decoder: h_0 = encoder output at the last valid position = frozen final layer-1 state, c_0 = 0 -------
   DecRowArgs r;
@@ -379,7 +389,7 @@ static int pg_forward_impl(const pnmn_pg_desc* m, const float* params, const int
   f.raw_out = raw_predictions; f.pred_out = predictions; f.loss = loss; f.logits_out = logits_out;
   f.coef = at<float>(ws, L.coef); f.label = at<int>(ws, L.label);
   CUDA_OK(launch_finalize(f, st));
-  pnmn::count_launches(6 + 2 * d.Ts + 2 * d.S + 1);   // prepare, pack, 3 tables, encoder steps, decoder row + step kernels, finalize
+  pnmn::count_launches(6 + (d.Ts + 1) + 2 * d.S + 1);   // prepare, pack, 3 tables, encoder ticks, decoder row + step kernels, finalize
   return 0;
 }
 
@@ -464,38 +474,72 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
   r.t = -1; r.do_attn = 1;
   CUDA_OK(launch_dec_bwd_row(r, st));   // attention of step 0 -> d(initial decoder state), d(encoder outputs)
 
-  // ---- encoder layer 1: dh carries d(final state); dc restarts (the decoder's c_0 is a constant) ------------------
+  // ---- encoder, both layers as a wavefront: tick j runs layer 1 at t = Ts-1-j and layer 0 at t = Ts-j (which needs
+  // d(layer-0 output) of step Ts-j, written by layer 1's data-gradient GEMM in tick j-1); two launches per tick.
+  // Layer 1: dh carries d(final state) from the decoder, dc restarts (the decoder's c_0 is a constant); layer 0 has its own
+  // carried dh / dc.
   CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dc), 0, 4 * L.slotf, st));
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dh0), 0, 4 * L.slotf, st));
+  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dc0), 0, 4 * L.slotf, st));
   EncCellBwdArgs e;
   std::memset(&e, 0, sizeof(e));
   e.B = d.B; e.Bp = d.Bp; e.Ts = d.Ts; e.src_len = at<int>(ws, L.src_len);
-  e.dh = at<float>(ws, L.dh); e.dc = at<float>(ws, L.dc); e.dg_lo = L.slotg; e.scale = scale;
+  e.dg_lo = L.slotg; e.scale = scale;
   g.len = at<int>(ws, L.src_len);
-  g.w = packed + L.pkT_1; g.w_lo = static_cast<int64_t>(2 * kSH) * kSG;
-  g.out[1] = at<float>(ws, L.dh); g.keep_masked[0] = 0; g.keep_masked[1] = 1;
-  for (int t = d.Ts - 1; t >= 0; --t) {
-    e.t = t; e.gates = at<float>(ws, L.g1) + t * L.slotg;
-    e.c_prev = at<float>(ws, L.c1f) + t * L.slotf; e.c_cur = at<float>(ws, L.c1f) + (t + 1) * L.slotf;
-    e.dext = at<float>(ws, L.denc) + static_cast<int64_t>(t) * kSH; e.dext_stride = static_cast<int64_t>(d.Ts) * kSH;
-    e.dg_op = at<__half>(ws, L.dg1) + t * L.slotdg;
-    CUDA_OK(launch_enc_cell_bwd(e, st));
-    g.t = t; g.a[0] = at<__half>(ws, L.dg1) + t * L.slotdg;
-    g.out[0] = at<float>(ws, L.dout0) + t * L.slotf;
-    CUDA_OK(launch_step_gemm(g, EPI_DGRAD, 2 * kSH / 64, MT, simt, st));
-  }
-  // ---- encoder layer 0 ---------------------------------------------------------------------------------------------
-  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dh), 0, 4 * L.slotf, st));
-  CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dc), 0, 4 * L.slotf, st));
-  g.w = packed + L.pkT_0; g.w_lo = static_cast<int64_t>(kSH) * kSG;
-  g.out[0] = at<float>(ws, L.dh); g.out[1] = nullptr; g.keep_masked[0] = 1;
-  for (int t = d.Ts - 1; t >= 0; --t) {
-    e.t = t; e.gates = at<float>(ws, L.g0) + t * L.slotg;
-    e.c_prev = at<float>(ws, L.c0f) + t * L.slotf; e.c_cur = at<float>(ws, L.c0f) + (t + 1) * L.slotf;
-    e.dext = at<float>(ws, L.dout0) + t * L.slotf; e.dext_stride = kSH;
-    e.dg_op = at<__half>(ws, L.dg0) + t * L.slotdg;
-    CUDA_OK(launch_enc_cell_bwd(e, st));
-    g.t = t; g.a[0] = at<__half>(ws, L.dg0) + t * L.slotdg;
-    CUDA_OK(launch_step_gemm(g, EPI_DGRAD, kSH / 64, MT, simt, st));
+  auto cell1 = [&](int t) {
+    EncCellBwdArgs a = e;
+    a.dh = at<float>(ws, L.dh); a.dc = at<float>(ws, L.dc);
+    a.t = t; a.gates = at<float>(ws, L.g1) + t * L.slotg;
+    a.c_prev = at<float>(ws, L.c1f) + t * L.slotf; a.c_cur = at<float>(ws, L.c1f) + (t + 1) * L.slotf;
+    a.dext = at<float>(ws, L.denc) + static_cast<int64_t>(t) * kSH; a.dext_stride = static_cast<int64_t>(d.Ts) * kSH;
+    a.dg_op = at<__half>(ws, L.dg1) + t * L.slotdg;
+    return a;
+  };
+  auto cell0 = [&](int t) {
+    EncCellBwdArgs a = e;
+    a.dh = at<float>(ws, L.dh0); a.dc = at<float>(ws, L.dc0);
+    a.t = t; a.gates = at<float>(ws, L.g0) + t * L.slotg;
+    a.c_prev = at<float>(ws, L.c0f) + t * L.slotf; a.c_cur = at<float>(ws, L.c0f) + (t + 1) * L.slotf;
+    a.dext = at<float>(ws, L.dout0) + t * L.slotf; a.dext_stride = kSH;
+    a.dg_op = at<__half>(ws, L.dg0) + t * L.slotdg;
+    return a;
+  };
+  auto dgrad1 = [&](int t) {
+    GemmArgs a = g;
+    a.w = packed + L.pkT_1; a.w_lo = static_cast<int64_t>(2 * kSH) * kSG;
+    a.out[0] = at<float>(ws, L.dout0) + t * L.slotf; a.out[1] = at<float>(ws, L.dh);
+    a.keep_masked[0] = 0; a.keep_masked[1] = 1;
+    a.t = t; a.a[0] = at<__half>(ws, L.dg1) + t * L.slotdg;
+    return a;
+  };
+  auto dgrad0 = [&](int t) {
+    GemmArgs a = g;
+    a.w = packed + L.pkT_0; a.w_lo = static_cast<int64_t>(kSH) * kSG;
+    a.out[0] = at<float>(ws, L.dh0); a.out[1] = nullptr; a.keep_masked[0] = 1; a.keep_masked[1] = 1;
+    a.t = t; a.a[0] = at<__half>(ws, L.dg0) + t * L.slotdg;
+    return a;
+  };
+  for (int j = 0; j <= d.Ts; ++j) {
+    const int t1 = d.Ts - 1 - j, t0 = d.Ts - j;
+    const bool has1 = j < d.Ts, has0 = j >= 1;
+    EncCellBwdPair cp;
+    GemmPair gp;
+    gp.m_tiles = MT;
+    if (has1 && has0) {
+      cp.count = gp.count = 2;
+      cp.a[0] = cell1(t1); cp.a[1] = cell0(t0);
+      gp.g[0] = dgrad1(t1); gp.g[1] = dgrad0(t0); gp.n_tiles[0] = 2 * kSH / 64; gp.n_tiles[1] = kSH / 64;
+    } else if (has1) {
+      cp.count = gp.count = 1;
+      cp.a[0] = cp.a[1] = cell1(t1);
+      gp.g[0] = gp.g[1] = dgrad1(t1); gp.n_tiles[0] = gp.n_tiles[1] = 2 * kSH / 64;
+    } else {
+      cp.count = gp.count = 1;
+      cp.a[0] = cp.a[1] = cell0(t0);
+      gp.g[0] = gp.g[1] = dgrad0(t0); gp.n_tiles[0] = gp.n_tiles[1] = kSH / 64;
+    }
+    CUDA_OK(launch_enc_cell_bwd_pair(cp, st));
+    CUDA_OK(launch_step_gemm_pair(gp, EPI_DGRAD, simt, st));
   }
 
   // ---- weight gradients: contraction over batch rows x time on the tensor cores ---------------------------------------
@@ -562,6 +606,6 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
   });
   if (rc) return rc;
   CUDA_OK(launch_accumulate(grads, gws, L.extent, st));
-  pnmn::count_launches(1 + 2 * d.S + 1 + 4 * d.Ts + 5 + 3 + 3 + 6);   // scale, decoder, encoder, wgrads, tables, biases, small GEMMs
+  pnmn::count_launches(2 + 2 * d.S + 1 + 2 * (d.Ts + 1) + 5 + 3 + 3 + 6 + 1);   // stage + scale, decoder, encoder ticks, wgrads, tables, biases, small GEMMs, accumulate
   return 0;
 }

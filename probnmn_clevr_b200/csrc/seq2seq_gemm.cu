@@ -140,12 +140,18 @@ __device__ __forceinline__ void epi_dgrad(const GemmArgs& g, int b, int nt, cons
 
 // ---- tensor-core kernel ------------------------------------------------------------------------------
 template <int EPI>
-__global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmArgs g) {
+__global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmPair pr) {
   extern __shared__ __align__(1024) uint8_t smem[];
   GemmHeader* hdr = reinterpret_cast<GemmHeader*>(smem);
   uint8_t* ring = smem + kGHeader;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nt = blockIdx.x, mt = blockIdx.y;
+  const int which = blockIdx.y >= pr.m_tiles ? 1 : 0;
+  const int nt = blockIdx.x, mt = blockIdx.y - which * pr.m_tiles;
+  if (nt >= pr.n_tiles[which]) {   // the two GEMMs of a pair may have different widths
+    pdl_launch_dependents();
+    return;
+  }
+  const GemmArgs& g = pr.g[which];
   // K chunks [kc_lo, kc_hi) of this CTA (EPI_DGRAD splits K over blockIdx.z; EPI_LSTM runs with gridDim.z == 1)
   const int kc_lo = (g.K / 64) * blockIdx.z / gridDim.z, kc_hi = (g.K / 64) * (blockIdx.z + 1) / gridDim.z;
   const int n_chunks = kc_hi - kc_lo;
@@ -245,8 +251,11 @@ __global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmAr
 
 // ---- CUDA-core twin (bring-up): thread = batch row, 64 fp32 accumulators ------------------------------
 template <int EPI>
-__global__ void __launch_bounds__(128) step_gemm_simt_kernel(const GemmArgs g) {
-  const int nt = blockIdx.x, mt = blockIdx.y;
+__global__ void __launch_bounds__(128) step_gemm_simt_kernel(const GemmPair pr) {
+  const int which = blockIdx.y >= pr.m_tiles ? 1 : 0;
+  const int nt = blockIdx.x, mt = blockIdx.y - which * pr.m_tiles;
+  if (nt >= pr.n_tiles[which]) return;
+  const GemmArgs& g = pr.g[which];
   const int b = mt * 128 + threadIdx.x;
   float acc[64];
 #pragma unroll
@@ -266,12 +275,13 @@ __global__ void __launch_bounds__(128) step_gemm_simt_kernel(const GemmArgs g) {
   else epi_dgrad(g, b, nt, acc);
 }
 
-cudaError_t launch_step_gemm(const GemmArgs& g, int epilogue, int n_tiles, int m_tiles, bool simt, cudaStream_t st) {
+cudaError_t launch_step_gemm_pair(const GemmPair& p, int epilogue, bool simt, cudaStream_t st) {
   // the data-gradient GEMMs have K = 1024 and few output tiles: split K four ways (partial sums are reduced with atomics)
-  const dim3 grid(n_tiles, m_tiles, (epilogue == EPI_DGRAD && !simt) ? 4 : 1);
+  const int nx = p.count > 1 && p.n_tiles[1] > p.n_tiles[0] ? p.n_tiles[1] : p.n_tiles[0];
+  const dim3 grid(nx, p.m_tiles * p.count, (epilogue == EPI_DGRAD && !simt) ? 4 : 1);
   if (simt) {
-    if (epilogue == EPI_LSTM) step_gemm_simt_kernel<EPI_LSTM><<<grid, 128, 0, st>>>(g);
-    else step_gemm_simt_kernel<EPI_DGRAD><<<grid, 128, 0, st>>>(g);
+    if (epilogue == EPI_LSTM) step_gemm_simt_kernel<EPI_LSTM><<<grid, 128, 0, st>>>(p);
+    else step_gemm_simt_kernel<EPI_DGRAD><<<grid, 128, 0, st>>>(p);
     return cudaGetLastError();
   }
   static bool attr_done = false;
@@ -283,8 +293,15 @@ cudaError_t launch_step_gemm(const GemmArgs& g, int epilogue, int n_tiles, int m
     attr_done = true;
   }
   const bool pdl = seq_use_pdl();
-  if (epilogue == EPI_LSTM) return launch_pdl(step_gemm_tc_kernel<EPI_LSTM>, grid, dim3(kGThreads), kGSmem, st, pdl, g);
-  return launch_pdl(step_gemm_tc_kernel<EPI_DGRAD>, grid, dim3(kGThreads), kGSmem, st, pdl, g);
+  if (epilogue == EPI_LSTM) return launch_pdl(step_gemm_tc_kernel<EPI_LSTM>, grid, dim3(kGThreads), kGSmem, st, pdl, p);
+  return launch_pdl(step_gemm_tc_kernel<EPI_DGRAD>, grid, dim3(kGThreads), kGSmem, st, pdl, p);
+}
+
+cudaError_t launch_step_gemm(const GemmArgs& g, int epilogue, int n_tiles, int m_tiles, bool simt, cudaStream_t st) {
+  GemmPair p;
+  p.g[0] = g; p.g[1] = g;
+  p.n_tiles[0] = p.n_tiles[1] = n_tiles; p.m_tiles = m_tiles; p.count = 1;
+  return launch_step_gemm_pair(p, epilogue, simt, st);
 }
 
 // =====================================================================================================

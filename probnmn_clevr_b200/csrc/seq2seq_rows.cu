@@ -480,8 +480,9 @@ cudaError_t launch_dec_bwd_row(const DecBwdRowArgs& a, cudaStream_t st) {
 }
 
 // encoder: LSTM cell backward of one (layer, step); rows beyond their length carry dh / dc through unchanged
-__global__ void __launch_bounds__(256) enc_cell_bwd_kernel(const EncCellBwdArgs a) {
+__global__ void __launch_bounds__(256) enc_cell_bwd_kernel(const EncCellBwdPair pr) {
   __shared__ __align__(16) float s_dg[kSG];
+  const EncCellBwdArgs& a = pr.a[blockIdx.y];
   const int b = blockIdx.x, tid = threadIdx.x;
   pdl_launch_dependents();
   pdl_wait();
@@ -501,8 +502,13 @@ __global__ void __launch_bounds__(256) enc_cell_bwd_kernel(const EncCellBwdArgs 
   __syncthreads();
   if (tid < kSG / 8) store_op8(a.dg_op, a.dg_lo, b, tid * 8, kSG, s_dg + tid * 8, a.scale[0]);
 }
+cudaError_t launch_enc_cell_bwd_pair(const EncCellBwdPair& p, cudaStream_t st) {
+  return launch_pdl(enc_cell_bwd_kernel, dim3(p.a[0].Bp, p.count), dim3(256), 0, st, seq_use_pdl(), p);
+}
 cudaError_t launch_enc_cell_bwd(const EncCellBwdArgs& a, cudaStream_t st) {
-  return launch_pdl(enc_cell_bwd_kernel, dim3(a.Bp), dim3(256), 0, st, seq_use_pdl(), a);
+  EncCellBwdPair p;
+  p.a[0] = a; p.a[1] = a; p.count = 1;
+  return launch_enc_cell_bwd_pair(p, st);
 }
 
 // =====================================================================================================
