@@ -278,7 +278,8 @@ __global__ void __launch_bounds__(128) step_gemm_simt_kernel(const GemmPair pr) 
 cudaError_t launch_step_gemm_pair(const GemmPair& p, int epilogue, bool simt, cudaStream_t st) {
   // the data-gradient GEMMs have K = 1024 and few output tiles: split K four ways (partial sums are reduced with atomics)
   const int nx = p.count > 1 && p.n_tiles[1] > p.n_tiles[0] ? p.n_tiles[1] : p.n_tiles[0];
-  const dim3 grid(nx, p.m_tiles * p.count, (epilogue == EPI_DGRAD && !simt) ? 4 : 1);
+  static const int ksplit = std::getenv("PNMN_PG_DGRAD_SPLIT") ? std::atoi(std::getenv("PNMN_PG_DGRAD_SPLIT")) : 4;
+  const dim3 grid(nx, p.m_tiles * p.count, (epilogue == EPI_DGRAD && !simt) ? ksplit : 1);
   if (simt) {
     if (epilogue == EPI_LSTM) step_gemm_simt_kernel<EPI_LSTM><<<grid, 128, 0, st>>>(p);
     else step_gemm_simt_kernel<EPI_DGRAD><<<grid, 128, 0, st>>>(p);
