@@ -184,8 +184,10 @@ struct DecRowArgs {
   __half* att_op;         // [S][operand Bp x 256] (hi; lo at + att_lo), step stride att_step
   int64_t att_lo, att_step;
   const unsigned long long* seed;   // device: Philox key of this call
+  int defer_out;          // 1: the per-step launches skip the output projection (launch_dec_out computes all steps at once)
 };
 cudaError_t launch_dec_row(const DecRowArgs& a, cudaStream_t st);
+cudaError_t launch_dec_out(const DecRowArgs& a, cudaStream_t st);
 
 struct FinalizeArgs {
   SeqDims d;

@@ -362,9 +362,11 @@ static int pg_forward_impl(const pnmn_pg_desc* m, const float* params, const int
   r.logp = at<float>(ws, L.logp); r.inp = at<int>(ws, L.inp); r.attn_p = at<float>(ws, L.attn_p);
   r.att_op = at<__half>(ws, L.attop); r.att_lo = L.slotf; r.att_step = L.slotop;
   r.seed = at<unsigned long long>(ws, L.seed);
+  r.defer_out = (teacher && !row_teacher) ? 1 : 0;   // no free-running rows: outputs of all steps in one launch after the loop
   g.len = nullptr; g.out_f = nullptr; g.out_op = nullptr;
   for (int t = 0; t <= d.S; ++t) {
     r.t = t;
+    if (t == d.S && r.defer_out) { CUDA_OK(launch_dec_out(r, st)); break; }
     CUDA_OK(launch_dec_row(r, st));
     if (t == d.S) break;
     g.t = t; g.K = 2 * kSH;

@@ -140,19 +140,10 @@ cudaError_t launch_accumulate(float* dst, const float* src, int64_t n, cudaStrea
 //       (seq2seq_base.py:201-220), (b) t < S: choose the input token of step t (:188-198), dot-product
 //       attention over the encoder outputs with AllenNLP's masked_softmax, attended vector -> operand copy.
 // =====================================================================================================
-__global__ void __launch_bounds__(256) dec_row_kernel(const DecRowArgs a) {
-  __shared__ float sh[kSH], satt[kSH], slg[kSMaxV], ssc[kSMaxT], sp[kSMaxT];
-  __shared__ int s_pred;
-  const SeqDims& d = a.d;
-  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int t = a.t;
-  pdl_launch_dependents();
-  pdl_wait();
-  sh[tid] = a.h_dec[(static_cast<size_t>(t) * d.Bp + b) * kSH + tid];
-  __syncthreads();
-
-  if (t > 0) {
-    const int tp = t - 1;
+// output projection of decoding step tp from its hidden state `sh` (shared, 256 floats): logits, log-sum-exp, the chosen
+// token (greedy max or categorical sampling, seq2seq_base.py:201-220) and its log-probability.  Called by a whole CTA.
+__device__ __forceinline__ void dec_output_step(const DecRowArgs& a, const SeqDims& d, int b, int tp, const float* sh,
+                                                float* slg, float* satt, int* s_pred, int warp, int lane) {
     for (int v = warp; v < d.Vt; v += 8) {
       const float4 w0 = *reinterpret_cast<const float4*>(a.out_w + static_cast<size_t>(v) * kSH + lane * 8);
       const float4 w1 = *reinterpret_cast<const float4*>(a.out_w + static_cast<size_t>(v) * kSH + lane * 8 + 4);
@@ -202,24 +193,37 @@ __global__ void __launch_bounds__(256) dec_row_kernel(const DecRowArgs a) {
           if (v < d.Vt) satt[v] = v <= kStart ? 0.f : e[i] / sum;
         }
         __syncwarp();
-        pred = 0;
-        if (lane == 0) {
-          float total = 0.f;
-          for (int v = 0; v < d.Vt; ++v) total += satt[v];
-          const float u = philox_uniform(a.seed[0], static_cast<uint32_t>(b), static_cast<uint32_t>(tp)) * total;
-          float cum = 0.f;
-          int last = kEnd;
-          pred = -1;
-          for (int v = 0; v < d.Vt; ++v) {
-            if (satt[v] > 0.f) {
-              last = v;
-              cum += satt[v];
-              if (cum > u) { pred = v; break; }
-            }
-          }
-          if (pred < 0) pred = last;
+        // inverse-CDF walk over the vocabulary in index order, warp-parallel: lane l owns entries [4l, 4l+4)
+        float p4[4], run = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int v = 4 * lane + i;
+          p4[i] = v < d.Vt ? satt[v] : 0.f;
+          run += p4[i];
         }
-        pred = __shfl_sync(0xffffffffu, pred, 0);
+        float incl = run;   // inclusive scan of the lanes' sums
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const float up = __shfl_up_sync(0xffffffffu, incl, o);
+          if (lane >= o) incl += up;
+        }
+        const float total = __shfl_sync(0xffffffffu, incl, 31);
+        const float u = philox_uniform(a.seed[0], static_cast<uint32_t>(b), static_cast<uint32_t>(tp)) * total;
+        float cum = incl - run;
+        int hit = -1, last = -1;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (p4[i] > 0.f) {
+            last = 4 * lane + i;
+            cum += p4[i];
+            if (hit < 0 && cum > u) hit = 4 * lane + i;
+          }
+        }
+        const unsigned hits = __ballot_sync(0xffffffffu, hit >= 0);
+        const unsigned lasts = __ballot_sync(0xffffffffu, last >= 0);
+        if (hits) pred = __shfl_sync(0xffffffffu, hit, __ffs(hits) - 1);
+        else if (lasts) pred = __shfl_sync(0xffffffffu, last, 31 - __clz(lasts));   // rounding: the last drawable token
+        else pred = kEnd;
       }
       const float lse = m + logf(sum);
       for (int v = lane; v < d.Vt; v += 32) a.logits[(static_cast<size_t>(tp) * d.B + b) * d.Vt + v] = slg[v];
@@ -227,11 +231,26 @@ __global__ void __launch_bounds__(256) dec_row_kernel(const DecRowArgs a) {
         a.lse[static_cast<size_t>(tp) * d.B + b] = lse;
         a.pred[static_cast<size_t>(tp) * d.B + b] = pred;
         a.logp[static_cast<size_t>(tp) * d.B + b] = slg[pred] - lse;
-        s_pred = pred;
+        *s_pred = pred;
       }
     }
     __syncthreads();
-  }
+}
+
+__global__ void __launch_bounds__(256) dec_row_kernel(const DecRowArgs a) {
+  __shared__ float sh[kSH], satt[kSH], slg[kSMaxV], ssc[kSMaxT], sp[kSMaxT];
+  __shared__ int s_pred;
+  const SeqDims& d = a.d;
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int t = a.t;
+  pdl_launch_dependents();
+  pdl_wait();
+  sh[tid] = a.h_dec[(static_cast<size_t>(t) * d.Bp + b) * kSH + tid];
+  __syncthreads();
+
+  // the output of step t-1 feeds the recurrence only through a free-running row's next input token: a call whose rows are
+  // all teacher-forced computes every step's output after the loop, in one launch over (step, row) (dec_out_kernel)
+  if (t > 0 && !a.defer_out) dec_output_step(a, d, b, t - 1, sh, slg, satt, &s_pred, warp, lane);
   if (t >= d.S) return;
 
   // ---- input token of step t: gold token under teacher forcing, else the previous prediction ----------
@@ -302,21 +321,40 @@ cudaError_t launch_dec_row(const DecRowArgs& a, cudaStream_t st) {
   return launch_pdl(dec_row_kernel, dim3(a.d.B), dim3(256), 0, st, seq_use_pdl(), a);
 }
 
+// every step's output of a teacher-forced pass at once: grid = (rows, steps)
+__global__ void __launch_bounds__(256) dec_out_kernel(const DecRowArgs a) {
+  __shared__ float sh[kSH], satt[kSH], slg[kSMaxV];
+  __shared__ int s_pred;
+  const SeqDims& d = a.d;
+  const int b = blockIdx.x, tp = blockIdx.y, tid = threadIdx.x;
+  sh[tid] = a.h_dec[(static_cast<size_t>(tp + 1) * d.Bp + b) * kSH + tid];
+  __syncthreads();
+  dec_output_step(a, d, b, tp, sh, slg, satt, &s_pred, tid >> 5, tid & 31);
+}
+cudaError_t launch_dec_out(const DecRowArgs& a, cudaStream_t st) {
+  dec_out_kernel<<<dim3(a.d.B, a.d.S), 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 // =====================================================================================================
 // trimming (seq2seq_base.py:278-293), per-row losses (:235-254, :333-341) and the dlogits coefficients
 // =====================================================================================================
-__global__ void finalize_kernel(const FinalizeArgs a) {
+// one WARP per row (lanes over the decoding steps; a thread per row walked its <= 46 steps serially: 46-70 us per call)
+__global__ void __launch_bounds__(256) finalize_kernel(const FinalizeArgs a) {
   const SeqDims& d = a.d;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= d.B) return;
   const bool real = b < a.rows;   // (padding rows still get their coef / label entries: the backward pass reads them)
   const bool tf = a.row_mode[b] != 0;
   const int Se = tf ? d.S : d.free_S;   // a free-running row of a mixed call stops after free_S steps
-  int first_end = -1;
-  for (int t = 0; t < Se; ++t)
+  int first_end = 0x7fffffff;
+  for (int t = lane; t < Se; t += 32)
     if (a.pred[static_cast<size_t>(t) * d.B + b] == kEnd) { first_end = t; break; }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) first_end = min(first_end, __shfl_xor_sync(0xffffffffu, first_end, o));
+  if (first_end == 0x7fffffff) first_end = -1;
   float lp_sum = 0.f, cnt = 0.f;
-  for (int t = 0; t < d.S; ++t) {
+  for (int t = lane; t < d.S; t += 32) {
     const int raw = t < Se ? a.pred[static_cast<size_t>(t) * d.B + b] : kPad;
     int keep;
     if (t >= Se) keep = kPad;
@@ -331,9 +369,11 @@ __global__ void finalize_kernel(const FinalizeArgs a) {
     lp_sum += a.logp[static_cast<size_t>(t) * d.B + b] * pm;
     cnt += pm;
   }
+  lp_sum = warp_sum(lp_sum);
+  cnt = warp_sum(cnt);
   if (!tf) {
-    if (real) a.loss[b] = -(lp_sum / (cnt + 1e-12f));
-    for (int t = 0; t < d.S; ++t) {
+    if (real && lane == 0) a.loss[b] = -(lp_sum / (cnt + 1e-12f));
+    for (int t = lane; t < d.S; t += 32) {
       const int raw = a.pred[static_cast<size_t>(t) * d.B + b];
       const bool kept = t < Se && (first_end < 0 ? raw != kPad : (first_end > 0 && t <= first_end && raw != kPad));
       a.coef[static_cast<size_t>(t) * d.B + b] = kept ? 1.f / (cnt + 1e-12f) : 0.f;
@@ -343,24 +383,30 @@ __global__ void finalize_kernel(const FinalizeArgs a) {
     // sequence_cross_entropy_with_logits(average=None): sum(nll * mask) / (sum(mask) + 1e-13) per row
     const int W = d.Tp + 2;
     float n = 0.f, tot = 0.f;
-    for (int t = 0; t < d.S; ++t) n += a.tgt[static_cast<size_t>(b) * W + t + 1] != kPad ? 1.f : 0.f;
-    for (int t = 0; t < d.S; ++t) {
+    for (int t = lane; t < d.S; t += 32) {
       const int lab = a.tgt[static_cast<size_t>(b) * W + t + 1];
       const float m = lab != kPad ? 1.f : 0.f;
       const float nll = a.lse[static_cast<size_t>(t) * d.B + b] - a.logits[(static_cast<size_t>(t) * d.B + b) * d.Vt + lab];
       tot += nll * m;
-      a.coef[static_cast<size_t>(t) * d.B + b] = m / (n + 1e-13f);
+      n += m;
+    }
+    n = warp_sum(n);
+    tot = warp_sum(tot);
+    for (int t = lane; t < d.S; t += 32) {
+      const int lab = a.tgt[static_cast<size_t>(b) * W + t + 1];
+      a.coef[static_cast<size_t>(t) * d.B + b] = (lab != kPad ? 1.f : 0.f) / (n + 1e-13f);
       a.label[static_cast<size_t>(t) * d.B + b] = lab;
     }
-    if (real) a.loss[b] = tot / (n + 1e-13f);
+    if (real && lane == 0) a.loss[b] = tot / (n + 1e-13f);
   }
   if (a.logits_out && real)
-    for (int t = 0; t < d.S; ++t)
-      for (int v = 0; v < d.Vt; ++v)
-        a.logits_out[(static_cast<size_t>(b) * d.S + t) * d.Vt + v] = a.logits[(static_cast<size_t>(t) * d.B + b) * d.Vt + v];
+    for (int i = lane; i < d.S * d.Vt; i += 32) {
+      const int t = i / d.Vt, v = i - t * d.Vt;
+      a.logits_out[(static_cast<size_t>(b) * d.S + t) * d.Vt + v] = a.logits[(static_cast<size_t>(t) * d.B + b) * d.Vt + v];
+    }
 }
 cudaError_t launch_finalize(const FinalizeArgs& a, cudaStream_t st) {
-  finalize_kernel<<<(a.d.B + 63) / 64, 64, 0, st>>>(a);
+  finalize_kernel<<<(a.d.B * 32 + 255) / 256, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 
@@ -513,33 +559,62 @@ cudaError_t launch_enc_cell_bwd(const EncCellBwdArgs& a, cudaStream_t st) {
 
 // =====================================================================================================
 // table gradient: dP[v][g] += scale[1] * sum over (t, b) with token v of dG[t][b][g]
-// CTA = 32 gate columns x a slice of the time range; thread = (batch row, 8-column group): 16-byte loads that
-// are contiguous across a warp's 32 rows; per-token partial sums in shared memory.
+// CTA = 32 gate columns x a slice of the time range; lane = column.  Rows are OWNED by warps through their token
+// (token % 8 == warp): a warp is the only writer of its tokens' partial sums in shared memory, so the scatter needs no
+// atomics and has no bank conflicts (32 lanes, 32 consecutive floats).  Every warp scans the slice's tokens (one coalesced
+// load per 32 rows + a ballot) and touches only its own rows' gradients.  Without a token table (the layer-1 bias: every
+// row goes to entry 0) the rows are dealt round-robin to the warps, which sum them in registers.
+// (The first version let all 256 threads atomicAdd into shared memory, thread = (row, 8 columns): rows with the same
+// token -- padding, frequent words -- hit the same addresses, 32-way conflicts; 70-290 us per launch in profiles/r2.)
 // =====================================================================================================
 __global__ void __launch_bounds__(256) table_grad_kernel(const TableGradArgs a) {
   __shared__ float acc[kSMaxV * 32];
-  const int tid = threadIdx.x;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < a.V * 32; i += 256) acc[i] = 0.f;
   __syncthreads();
   const int g0 = blockIdx.x * 32;
   const int t0 = static_cast<int>((static_cast<long long>(a.T) * blockIdx.y) / gridDim.y);
   const int t1 = static_cast<int>((static_cast<long long>(a.T) * (blockIdx.y + 1)) / gridDim.y);
-  const int grp = tid >> 6, r = tid & 63;   // 4 column groups x 64 rows per pass
-  for (int t = t0; t < t1; ++t) {
-    const __half* dg = a.dg + static_cast<size_t>(t) * a.dg_step;
-    for (int b = r; b < a.B; b += 64) {
-      const int v = a.tok ? a.tok[static_cast<size_t>(t) * a.tok_step + static_cast<size_t>(b) * a.tok_stride] : 0;
-      const size_t off = op_off(b, g0 + grp * 8, kSG);
-      const uint4 hi = *reinterpret_cast<const uint4*>(dg + off);
-      const uint4 lo = *reinterpret_cast<const uint4*>(dg + a.dg_lo + off);
-      const __half2* h2 = reinterpret_cast<const __half2*>(&hi);
-      const __half2* l2 = reinterpret_cast<const __half2*>(&lo);
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 hf = __half22float2(h2[e]), lf = __half22float2(l2[e]);
-        const float x0 = hf.x + lf.x, x1 = hf.y + lf.y;
-        if (x0 != 0.f) atomicAdd(&acc[v * 32 + grp * 8 + 2 * e], x0);
-        if (x1 != 0.f) atomicAdd(&acc[v * 32 + grp * 8 + 2 * e + 1], x1);
+  const int col = g0 + lane;
+  const size_t col_off = static_cast<size_t>(col >> 3) * 1024 + (col & 7);   // op_off(b, col, kSG) minus the row part
+  auto row_off = [](int b) { return static_cast<size_t>(b >> 7) * (kSG >> 3) * 1024 + static_cast<size_t>(b & 127) * 8; };
+  if (!a.tok) {
+    float r = 0.f;
+    for (int t = t0; t < t1; ++t) {
+      const __half* dg = a.dg + static_cast<size_t>(t) * a.dg_step;
+#pragma unroll 4
+      for (int b = warp; b < a.B; b += 8) {
+        const size_t off = row_off(b) + col_off;
+        r += __half2float(dg[off]) + __half2float(dg[a.dg_lo + off]);
+      }
+    }
+    atomicAdd(&acc[lane], r);
+  } else {
+    for (int t = t0; t < t1; ++t) {
+      const __half* dg = a.dg + static_cast<size_t>(t) * a.dg_step;
+      for (int b0 = 0; b0 < a.B; b0 += 32) {
+        const int b = b0 + lane;
+        const int v = b < a.B ? a.tok[static_cast<size_t>(t) * a.tok_step + static_cast<size_t>(b) * a.tok_stride] : -1;
+        unsigned mine = __ballot_sync(0xffffffffu, v >= 0 && (v & 7) == warp);
+        while (mine) {
+          // two rows per iteration: their loads are independent, the shared-memory updates follow
+          const int s0 = __ffs(mine) - 1;
+          mine &= mine - 1;
+          const int s1 = mine ? __ffs(mine) - 1 : -1;
+          if (s1 >= 0) mine &= mine - 1;
+          const int v0 = __shfl_sync(0xffffffffu, v, s0);
+          const size_t o0 = row_off(b0 + s0) + col_off;
+          float x0 = __half2float(dg[o0]) + __half2float(dg[a.dg_lo + o0]);
+          float x1 = 0.f;
+          int v1 = 0;
+          if (s1 >= 0) {
+            v1 = __shfl_sync(0xffffffffu, v, s1);
+            const size_t o1 = row_off(b0 + s1) + col_off;
+            x1 = __half2float(dg[o1]) + __half2float(dg[a.dg_lo + o1]);
+          }
+          acc[v0 * 32 + lane] += x0;
+          if (s1 >= 0) acc[v1 * 32 + lane] += x1;
+        }
       }
     }
   }
