@@ -272,7 +272,8 @@ static int pg_forward_impl(const pnmn_pg_desc* m, const float* params, const int
   d.B = d.Bp;   // every kernel runs on whole 128-row tiles; rows >= `rows` are empty sequences (launch_prepare_tokens)
   CUDA_OK(launch_prepare_tokens(source, target, row_teacher, d, rows, seed, at<unsigned long long>(ws, L.seed), at<int>(ws, L.src),
                                 at<int>(ws, L.src_len), at<int>(ws, L.tgt), at<int>(ws, L.rowmode), st));
-  GraphKey key{ws, params, 0, 0, d.Bp, d.Tq, d.Tp, d.S, d.sampling, d.teacher, need_grad != 0, d.Vs, d.Vt};
+  // (a mixed call launches different kernels than a purely teacher-forced one of the same shape: part of the key)
+  GraphKey key{ws, params, 0, 0, d.Bp, d.Tq, d.Tp, d.S, d.sampling | (row_teacher ? 2 : 0), d.teacher, need_grad != 0, d.Vs, d.Vt};
   if (simt) key.pass = 2;
   const int rc = run_graphed(key, st, [&](cudaStream_t st) -> int {
 

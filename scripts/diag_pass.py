@@ -24,7 +24,8 @@ def timeit(fn, n=10):
     return f / n, b / n
 
 
-for B in (64, 123, 128, 200, 256):
+SIZES = [int(x) for x in sys.argv[1:]] or [64, 123, 128, 200, 256]
+for B in SIZES:
     bt = make_joint_batch(vocab, B, seed=0, with_images=False)
     q, p = bt["question"].cuda(), bt["program"].cuda()
     rows = torch.zeros(B, dtype=torch.uint8, device="cuda"); rows[B // 2:] = 1

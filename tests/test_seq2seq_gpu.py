@@ -187,3 +187,38 @@ def test_edge_cases(vocab):
 @pytest.mark.skipif(os.environ.get("PNMN_PG_SIMT") is not None, reason="already the CUDA-core twin")
 def test_reports_native_library_loaded():
     assert os.path.exists(L.LIB_PATH)
+
+
+def test_mixed_rows_equal_separate_calls_and_share_no_graph(vocab):
+    """forward_mixed (teacher-forced and free-running rows in one pass) against the two separate calls: teacher-forced rows
+    must give the same loss and gradients; called right after a purely teacher-forced pass of the SAME shape (the two must
+    not replay one another's CUDA graph: the mixed pass computes the per-step outputs inside the loop, the other after it)."""
+    model, sd = build(vocab, 5)
+    model.train()
+    q, p = inputs(vocab, 48, 9)
+    q, p = q.cuda(), p.cuda()
+    rows = torch.zeros(48, dtype=torch.uint8, device="cuda")
+    rows[20:] = 1
+    outs = []
+    for _ in range(3):                      # (the third call of each kind replays its captured graph)
+        model.zero_grad()
+        t = model(q, p, decoding_strategy="sampling")
+        t["loss"][20:].sum().backward()
+        g_t = torch.cat([x.grad.flatten() for x in model.parameters()]).clone()
+        model.zero_grad()
+        m = model.forward_mixed(q, p, rows)
+        m["loss"][20:].sum().backward()
+        g_m = torch.cat([x.grad.flatten() for x in model.parameters()]).clone()
+        outs.append((t, m, g_t, g_m))
+    for t, m, g_t, g_m in outs:
+        assert torch.allclose(t["loss"][20:], m["loss"][20:], rtol=1e-6, atol=1e-6)
+        assert float((g_t - g_m).abs().max()) <= 1e-5 * float(g_t.abs().max())
+        free = m["predictions"][:20]
+        assert free.shape[1] == 27 and int(free[:, 26].abs().sum()) == 0          # free rows stop after 26 steps
+        assert int(free.max()) < vocab.get_vocab_size("programs") and torch.isfinite(m["loss"]).all()
+    # free-running rows: the loss is the sampled-sequence loss of their own predictions (oracle replay of the raw samples)
+    t, m, _, _ = outs[-1]
+    with torch.no_grad():
+        ref = O.seq2seq_forward(sd, q[:20].cpu(), None, "sampling", 26, forced_choices=m["raw_predictions"][:20, :26].cpu())
+    assert torch.equal(ref["predictions"], m["predictions"][:20, :26].cpu())
+    assert rel(m["loss"][:20].detach().cpu(), ref["loss"]) < 1e-3
