@@ -559,65 +559,75 @@ cudaError_t launch_enc_cell_bwd(const EncCellBwdArgs& a, cudaStream_t st) {
 
 // =====================================================================================================
 // table gradient: dP[v][g] += scale[1] * sum over (t, b) with token v of dG[t][b][g]
-// CTA = 32 gate columns x a slice of the time range; lane = column.  Rows are OWNED by warps through their token
-// (token % 8 == warp): a warp is the only writer of its tokens' partial sums in shared memory, so the scatter needs no
-// atomics and has no bank conflicts (32 lanes, 32 consecutive floats).  Every warp scans the slice's tokens (one coalesced
-// load per 32 rows + a ballot) and touches only its own rows' gradients.  Without a token table (the layer-1 bias: every
-// row goes to entry 0) the rows are dealt round-robin to the warps, which sum them in registers.
+// CTA = 32 gate columns x a slice of the time range.  128 rows x 32 columns of gradients are staged in shared memory with
+// coalesced 16-byte loads (many in flight); the scatter then runs out of shared memory with lane = column: rows are OWNED
+// by warps through their token (token % 8 == warp), so a warp is the only writer of its tokens' partial sums -- no atomics,
+// no bank conflicts.  Without a token table (the layer-1 bias: every row goes to entry 0) the warps sum rows in registers.
 // (The first version let all 256 threads atomicAdd into shared memory, thread = (row, 8 columns): rows with the same
 // token -- padding, frequent words -- hit the same addresses, 32-way conflicts; 70-290 us per launch in profiles/r2.)
 // =====================================================================================================
+constexpr int kTGRows = 128;                 // rows staged per pass
+constexpr int kTGStride = 33;                // padded row stride of the staged tile (conflict-free column access)
 __global__ void __launch_bounds__(256) table_grad_kernel(const TableGradArgs a) {
   __shared__ float acc[kSMaxV * 32];
+  __shared__ float tile[kTGRows * kTGStride];
+  __shared__ int stok[kTGRows];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   for (int i = tid; i < a.V * 32; i += 256) acc[i] = 0.f;
-  __syncthreads();
   const int g0 = blockIdx.x * 32;
   const int t0 = static_cast<int>((static_cast<long long>(a.T) * blockIdx.y) / gridDim.y);
   const int t1 = static_cast<int>((static_cast<long long>(a.T) * (blockIdx.y + 1)) / gridDim.y);
-  const int col = g0 + lane;
-  const size_t col_off = static_cast<size_t>(col >> 3) * 1024 + (col & 7);   // op_off(b, col, kSG) minus the row part
-  auto row_off = [](int b) { return static_cast<size_t>(b >> 7) * (kSG >> 3) * 1024 + static_cast<size_t>(b & 127) * 8; };
-  if (!a.tok) {
-    float r = 0.f;
-    for (int t = t0; t < t1; ++t) {
-      const __half* dg = a.dg + static_cast<size_t>(t) * a.dg_step;
-#pragma unroll 4
-      for (int b = warp; b < a.B; b += 8) {
-        const size_t off = row_off(b) + col_off;
-        r += __half2float(dg[off]) + __half2float(dg[a.dg_lo + off]);
-      }
-    }
-    atomicAdd(&acc[lane], r);
-  } else {
-    for (int t = t0; t < t1; ++t) {
-      const __half* dg = a.dg + static_cast<size_t>(t) * a.dg_step;
-      for (int b0 = 0; b0 < a.B; b0 += 32) {
-        const int b = b0 + lane;
-        const int v = b < a.B ? a.tok[static_cast<size_t>(t) * a.tok_step + static_cast<size_t>(b) * a.tok_stride] : -1;
-        unsigned mine = __ballot_sync(0xffffffffu, v >= 0 && (v & 7) == warp);
-        while (mine) {
-          // two rows per iteration: their loads are independent, the shared-memory updates follow
-          const int s0 = __ffs(mine) - 1;
-          mine &= mine - 1;
-          const int s1 = mine ? __ffs(mine) - 1 : -1;
-          if (s1 >= 0) mine &= mine - 1;
-          const int v0 = __shfl_sync(0xffffffffu, v, s0);
-          const size_t o0 = row_off(b0 + s0) + col_off;
-          float x0 = __half2float(dg[o0]) + __half2float(dg[a.dg_lo + o0]);
-          float x1 = 0.f;
-          int v1 = 0;
-          if (s1 >= 0) {
-            v1 = __shfl_sync(0xffffffffu, v, s1);
-            const size_t o1 = row_off(b0 + s1) + col_off;
-            x1 = __half2float(dg[o1]) + __half2float(dg[a.dg_lo + o1]);
+  float r = 0.f;   // (no token table: column sums in registers)
+  for (int t = t0; t < t1; ++t) {
+    const __half* dg = a.dg + static_cast<size_t>(t) * a.dg_step;
+    for (int b0 = 0; b0 < a.B; b0 += kTGRows) {
+      __syncthreads();   // the previous tile has been consumed (and acc is zeroed on the first pass)
+      // stage 128 rows x 32 columns: thread = (row, 8-column group), 16-byte loads that are contiguous across a warp's rows
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int i = tid + 256 * k, row = i & (kTGRows - 1), grp = i >> 7;   // grp in 0..3
+        const int b = b0 + row;
+        float x[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (b < a.B) {
+          const size_t off = op_off(b, g0 + grp * 8, kSG);
+          const uint4 hi = *reinterpret_cast<const uint4*>(dg + off);
+          const uint4 lo = *reinterpret_cast<const uint4*>(dg + a.dg_lo + off);
+          const __half2* h2 = reinterpret_cast<const __half2*>(&hi);
+          const __half2* l2 = reinterpret_cast<const __half2*>(&lo);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 hf = __half22float2(h2[e]), lf = __half22float2(l2[e]);
+            x[2 * e] = hf.x + lf.x; x[2 * e + 1] = hf.y + lf.y;
           }
-          acc[v0 * 32 + lane] += x0;
-          if (s1 >= 0) acc[v1 * 32 + lane] += x1;
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) tile[row * kTGStride + grp * 8 + e] = x[e];
+      }
+      if (tid < kTGRows) {
+        const int b = b0 + tid;
+        stok[tid] = (a.tok && b < a.B) ? a.tok[static_cast<size_t>(t) * a.tok_step + static_cast<size_t>(b) * a.tok_stride] : 0;
+      }
+      __syncthreads();
+      if (!a.tok) {
+        for (int row = warp; row < kTGRows; row += 8) r += tile[row * kTGStride + lane];
+      } else {
+        // scatter by token; warp w is the only writer of the tokens with v % 8 == w.  Padding tokens are skipped: a padded
+        // position carries no gradient (masked encoder steps; decoder steps behind the end of the target have weight 0)
+#pragma unroll
+        for (int q = 0; q < kTGRows / 32; ++q) {
+          const int v = stok[q * 32 + lane];
+          unsigned mine = __ballot_sync(0xffffffffu, v > 0 && (v & 7) == warp);
+          while (mine) {
+            const int s0 = __ffs(mine) - 1;
+            mine &= mine - 1;
+            const int v0 = __shfl_sync(0xffffffffu, v, s0);
+            acc[v0 * 32 + lane] += tile[(q * 32 + s0) * kTGStride + lane];
+          }
         }
       }
     }
   }
+  if (!a.tok) atomicAdd(&acc[lane], r);
   __syncthreads();
   const float unscale = a.scale[1];
   for (int i = tid; i < a.V * 32; i += 256) {

@@ -35,6 +35,7 @@ TAG=${TAG:-r2}
 timeout 1200 ncu --profile-from-start off --metrics gpu__time_duration.sum,launch__grid_size --clock-control none --csv \
     --log-file gpurun_out/launches_${TAG}.csv python /tmp/one_joint_step.py > gpurun_out/ncu_list.log 2>&1
 tail -2 gpurun_out/ncu_list.log
+[ -n "$ONLY_LIST" ] && exit 0
 timeout 900 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:exec_kernel -c 2 \
     -f -o gpurun_out/exec_${TAG} python /tmp/one_joint_step.py > gpurun_out/ncu_exec.log 2>&1; tail -2 gpurun_out/ncu_exec.log
 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:wgrad_tc -c 1 \
