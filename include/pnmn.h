@@ -140,6 +140,14 @@ int pnmn_relu_pool_fwd_bias(const float* y, const float* bias, float* pooled, vo
 /* dst[2][n] bf16 = (hi, lo) split of src[n] fp32, n % 4 == 0 */
 int pnmn_split2_bf16(const float* src, void* dst, int64_t n, void* stream);
 
+/* SM partition for concurrent streams (no counterpart in the reference, which runs its models one after the other:
+ * modules/elbo.py:230-275).  The module executor (pnmn_nmn_forward / _backward: exec_kernel, wgrad_tc_kernel) is
+ * persistent and would otherwise own every SM for the length of a pass; with n > 0 its CTAs keep off the n highest-numbered
+ * SMs, which stay available to kernels that other streams launch meanwhile (the LSTM passes of the joint-training step,
+ * probnmn_clevr_b200/joint.py).  n is clamped to 3/4 of the device; 0 (default) = the executor uses the whole device.
+ * Process-wide; returns the previous value.  Results do not depend on it. */
+int pnmn_set_reserved_sms(int n);
+
 /* kernels launched by the library so far (reset != 0 clears the counter); bench.py reports it as "gpu_launches" */
 long long pnmn_launch_count(int reset);
 

@@ -129,7 +129,11 @@ template <bool kTrace>
 __global__ void __launch_bounds__(kExThreads, kExCtasPerSM)
 exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ metas, int n_tasks,
             const ConvCfg* __restrict__ cfgs, int* __restrict__ counter, int* __restrict__ done,
-            long long* __restrict__ trace, int dbg) {
+            long long* __restrict__ trace, int dbg, int sm_limit) {
+  // SM partition (pnmn_set_reserved_sms): a CTA that lands on one of the reserved SMs leaves at once -- tasks are pulled
+  // from a global counter, so the CTAs on the other SMs simply run the whole list -- and the SM stays free for the
+  // kernels of other streams (the LSTM passes of the joint-training step, which cannot share an SM with two executor CTAs)
+  if (smid() >= sm_limit) return;
   extern __shared__ __align__(1024) uint8_t smem[];
   ExHeader* hdr = reinterpret_cast<ExHeader*>(smem);
   uint8_t* w_ring = smem + kExHeader;
@@ -639,6 +643,10 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
   if (warp == 2) tmem_dealloc<kExMaxAcc * 128>(tmem_base);
 }
 
+static int g_reserved_sms = std::getenv("PNMN_RESERVE_SMS") ? std::atoi(std::getenv("PNMN_RESERVE_SMS")) : 0;
+void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
+int reserved_sms() { return g_reserved_sms; }
+
 cudaError_t launch_exec(const uint8_t* d_tasks, const TaskMeta* d_meta, int n_tasks, const ConvCfg* d_cfgs,
                         int* d_counter, int* d_done, long long* d_trace, cudaStream_t stream) {
   if (n_tasks <= 0) return cudaSuccess;
@@ -659,8 +667,10 @@ cudaError_t launch_exec(const uint8_t* d_tasks, const TaskMeta* d_meta, int n_ta
   int grid = n_tasks < kExCtasPerSM * sms ? n_tasks : kExCtasPerSM * sms;
   if (cap > 0 && grid > cap) grid = cap;
   static const int dbg = std::getenv("PNMN_EXEC_DBG") ? std::atoi(std::getenv("PNMN_EXEC_DBG")) : 0;  // timing experiments only
-  if (d_trace) exec_kernel<true><<<grid, kExThreads, kExSmem, stream>>>(d_tasks, d_meta, n_tasks, d_cfgs, d_counter, d_done, d_trace, dbg);
-  else exec_kernel<false><<<grid, kExThreads, kExSmem, stream>>>(d_tasks, d_meta, n_tasks, d_cfgs, d_counter, d_done, d_trace, dbg);
+  // at least a quarter of the SMs always stay with the executor
+  const int sm_limit = sms - (g_reserved_sms < sms * 3 / 4 ? g_reserved_sms : sms * 3 / 4);
+  if (d_trace) exec_kernel<true><<<grid, kExThreads, kExSmem, stream>>>(d_tasks, d_meta, n_tasks, d_cfgs, d_counter, d_done, d_trace, dbg, sm_limit);
+  else exec_kernel<false><<<grid, kExThreads, kExSmem, stream>>>(d_tasks, d_meta, n_tasks, d_cfgs, d_counter, d_done, d_trace, dbg, sm_limit);
   return cudaGetLastError();
 }
 

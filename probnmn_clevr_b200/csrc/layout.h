@@ -30,7 +30,8 @@ cudaError_t launch_pack(const PackTask* d_tasks, int n_tasks, int total_tiles, c
 cudaError_t launch_nchw_to_planes(const float* src, float* dst, int B, int C, const int64_t* dst_off,
                                   cudaStream_t stream);
 cudaError_t launch_conv_simt(const ConvTask* d_tasks, int n_tasks, const ConvCfg* d_cfgs, cudaStream_t stream);
-cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, cudaStream_t stream);
+// d_counter: zeroed device int (tasks are then pulled by one persistent CTA per SM), or nullptr (one CTA per task)
+cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, int* d_counter, cudaStream_t stream);
 cudaError_t launch_bias_grad(const void* d_tasks, int n_tasks, int split, cudaStream_t stream);
 cudaError_t launch_elt(const EltTask* d_tasks, int n_tasks, cudaStream_t stream);
 cudaError_t launch_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int stack_rows, int second_low,

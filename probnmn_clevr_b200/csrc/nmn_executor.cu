@@ -125,6 +125,13 @@ void set_last_error(const std::string& s) { g_err = s; }
 static long long g_launch_count = 0;   // kernels launched by the library (bench.py "gpu_launches")
 void count_launches(int n) { g_launch_count += n; }
 }
+namespace pnmn { void set_reserved_sms(int n); int reserved_sms(); }
+extern "C" int pnmn_set_reserved_sms(int n) {
+  const int prev = pnmn::reserved_sms();
+  pnmn::set_reserved_sms(n);
+  return prev;
+}
+
 extern "C" long long pnmn_launch_count(int reset) {
   const long long v = pnmn::g_launch_count;
   if (reset) pnmn::g_launch_count = 0;
@@ -545,7 +552,7 @@ struct pnmn_plan {
   void* uploaded_to = nullptr;  // device buffer that already holds this plan's task tables (pnmn_plan_upload)
   std::vector<TaskRec> ftask, btask;
   std::vector<TaskMeta> fmeta, bmeta;
-  int64_t off_ftask = 0, off_fmeta = 0, off_fsync = 0, off_btask = 0, off_bmeta = 0, off_bsync = 0;
+  int64_t off_ftask = 0, off_fmeta = 0, off_fsync = 0, off_btask = 0, off_bmeta = 0, off_bsync = 0, off_wsync = 0;
   // blob layout (bytes)
   int64_t off_cfg = 0, off_xin = 0, off_pack = 0, off_fconv = 0, off_felt = 0, off_bconv = 0, off_belt = 0, off_inst = 0,
           off_wt = 0, off_bt = 0, blob_bytes = 0;
@@ -1337,6 +1344,7 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
   p.off_bmeta = o; o = align(o + static_cast<int64_t>(p.bmeta.size() * sizeof(TaskMeta)));
   p.off_fsync = o; o = align(o + 4 * static_cast<int64_t>(p.ftask.size() + 1));
   p.off_bsync = o; o = align(o + 4 * static_cast<int64_t>(p.btask.size() + 1));
+  p.off_wsync = o; o = align(o + 4);   // task counter of the weight-gradient kernel
   p.blob_bytes = std::max<int64_t>(o, 256);
   // instance pointers inside wgrad/bias tasks were relative to the instance table
   for (auto& t : p.wtasks)
@@ -1556,7 +1564,8 @@ int run_launches(const pnmn_plan& p, const std::vector<LaunchItem>& ls, const ui
       CUDA_OK(cudaStreamWaitEvent(ss->s, ss->fork, 0));
       CUDA_OK(launch_bias_grad(blob + p.off_bt, ls[1].count, kBiasSplit, ss->s));
       CUDA_OK(cudaEventRecord(ss->join, ss->s));
-      CUDA_OK(launch_wgrad(reinterpret_cast<const WgradTask*>(blob + p.off_wt), ls[0].count, 0, st));
+      CUDA_OK(launch_wgrad(reinterpret_cast<const WgradTask*>(blob + p.off_wt), ls[0].count, 0,
+                           reinterpret_cast<int*>(const_cast<uint8_t*>(blob) + p.off_wsync), st));
       CUDA_OK(cudaStreamWaitEvent(st, ss->join, 0));
       return 0;
     }
@@ -1569,7 +1578,8 @@ int run_launches(const pnmn_plan& p, const std::vector<LaunchItem>& ls, const ui
       case LK_ELT: CUDA_OK(launch_elt(elt + l.off, l.count, st)); break;
       case LK_CONV0:
       case LK_CONV1: CUDA_OK(launch_conv_simt(conv + l.off, l.count, cfgs, st)); break;
-      case LK_WGRAD: CUDA_OK(launch_wgrad(reinterpret_cast<const WgradTask*>(blob + p.off_wt), l.count, p.persistent ? 0 : 1, st)); break;
+      case LK_WGRAD: CUDA_OK(launch_wgrad(reinterpret_cast<const WgradTask*>(blob + p.off_wt), l.count, p.persistent ? 0 : 1,
+                                          p.persistent ? reinterpret_cast<int*>(const_cast<uint8_t*>(blob) + p.off_wsync) : nullptr, st)); break;
       case LK_BIAS: CUDA_OK(launch_bias_grad(blob + p.off_bt, l.count, kBiasSplit, st)); break;
       default: break;
     }
@@ -1869,7 +1879,7 @@ extern "C" int pnmn_debug_launch_wgrad(const void* tasks_host, int n_tasks, cons
   for (auto& x : t) x.inst = di + reinterpret_cast<uint64_t>(x.inst);
   WgradTask* dt = nullptr;
   if (upload(t.data(), t.size(), &dt)) return 1;
-  CUDA_OK(launch_wgrad(dt, n_tasks, impl_simt, static_cast<cudaStream_t>(stream)));
+  CUDA_OK(launch_wgrad(dt, n_tasks, impl_simt, nullptr, static_cast<cudaStream_t>(stream)));
   CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   cudaFree(dt); cudaFree(di);
   return 0;

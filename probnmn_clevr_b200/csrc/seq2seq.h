@@ -214,6 +214,7 @@ struct DecBwdRowArgs {
   const float* enc; const int* src_len;
   const float* attn_p;
   float* dlogits;         // [S][B][Vt]
+  float* dhp;             // [S][Bp][256] d(h_t) through the output projection (launch_dec_bwd_proj, all steps at once)
   float* dh; float* dc;   // carried gradients [Bp][256]
   const float* datt;      // [Bp][256] (written by the dgrad GEMM of step t+1)
   float* denc;            // [B][Ts][256]
@@ -222,6 +223,7 @@ struct DecBwdRowArgs {
   const float* scale;
 };
 cudaError_t launch_dec_bwd_row(const DecBwdRowArgs& a, cudaStream_t st);
+cudaError_t launch_dec_bwd_proj(const DecBwdRowArgs& a, cudaStream_t st);
 
 struct EncCellBwdArgs {
   int B, Bp, t, Ts;

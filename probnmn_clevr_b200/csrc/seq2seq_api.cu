@@ -53,7 +53,7 @@ struct Layout {
   int64_t h0f, c0f, h0op, out0op, g0;      // encoder layer 0
   int64_t h1f, c1f, h1op, g1, enc;         // encoder layer 1 (+ decoder slots appended to h1f / h1op)
   int64_t cdf, attop, gd;                  // decoder
-  int64_t dh, dc, dh0, dc0, datt, denc, dout0, dgd, dg1, dg0, scale;
+  int64_t dh, dc, dh0, dc0, datt, denc, dout0, dgd, dg1, dg0, scale, dhp;
   int64_t seed, gstage, gws, extent, rowmode;   // Philox key; incoming gradient padded to Bp; parameter gradients of this call
   int64_t total;
 };
@@ -105,6 +105,7 @@ Layout make_layout(const pnmn_pg_desc* m, int B, int Tq, int Tp, int S, bool nee
     L.gws = take(4 * L.extent);
     L.g0 = take(4 * L.slotg * d.Ts); L.g1 = take(4 * L.slotg * d.Ts); L.gd = take(4 * L.slotg * S);
     L.dlogits = take(4ll * S * d.Bp * d.Vt);
+    L.dhp = take(4 * L.slotf * S);
     L.dP0 = take(4ll * d.Vs * kSG); L.dPd = take(4ll * d.Vt * kSG); L.dP1 = take(4ll * kSG);
     L.dh = take(4 * L.slotf); L.dc = take(4 * L.slotf); L.datt = take(4 * L.slotf);
     L.dh0 = take(4 * L.slotf); L.dc0 = take(4 * L.slotf);
@@ -462,12 +463,13 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
   r.logits = at<float>(ws, L.logits); r.lse = at<float>(ws, L.lse); r.out_w = params + m->out_w;
   r.h_dec = at<float>(ws, L.h1f) + d.Ts * L.slotf; r.c_dec = at<float>(ws, L.cdf); r.gates = at<float>(ws, L.gd);
   r.enc = at<float>(ws, L.enc); r.src_len = at<int>(ws, L.src_len); r.attn_p = at<float>(ws, L.attn_p);
-  r.dlogits = at<float>(ws, L.dlogits); r.dh = at<float>(ws, L.dh); r.dc = at<float>(ws, L.dc);
+  r.dlogits = at<float>(ws, L.dlogits); r.dhp = at<float>(ws, L.dhp); r.dh = at<float>(ws, L.dh); r.dc = at<float>(ws, L.dc);
   r.datt = at<float>(ws, L.datt); r.denc = at<float>(ws, L.denc);
   r.dg_op = at<__half>(ws, L.dgd); r.dg_lo = L.slotg; r.dg_step = L.slotdg; r.scale = scale;
   g.len = nullptr;
   g.w = packed + L.pkT_d; g.w_lo = static_cast<int64_t>(2 * kSH) * kSG;
   g.out[0] = at<float>(ws, L.datt); g.out[1] = at<float>(ws, L.dh);
+  CUDA_OK(launch_dec_bwd_proj(r, st));
   for (int t = d.S - 1; t >= 0; --t) {
     r.t = t; r.do_attn = t < d.S - 1 ? 1 : 0;
     CUDA_OK(launch_dec_bwd_row(r, st));
@@ -609,6 +611,6 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
   });
   if (rc) return rc;
   CUDA_OK(launch_accumulate(grads, gws, L.extent, st));
-  pnmn::count_launches(2 + 2 * d.S + 1 + 2 * (d.Ts + 1) + 5 + 3 + 3 + 6 + 1);   // stage + scale, decoder, encoder ticks, wgrads, tables, biases, small GEMMs, accumulate
+  pnmn::count_launches(3 + 2 * d.S + 1 + 2 * (d.Ts + 1) + 5 + 3 + 3 + 6 + 1);   // stage + scale, decoder, encoder ticks, wgrads, tables, biases, small GEMMs, accumulate
   return 0;
 }

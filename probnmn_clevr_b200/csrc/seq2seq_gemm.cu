@@ -23,6 +23,8 @@ bool seq_use_pdl() {
 }
 
 constexpr int kGThreads = 256;
+// Ring depth.  With 2 stages (97 KB) two CTAs fit on an SM (the kernel stays below 128 registers); measured on the
+// joint-training step that halves the SMs a pass occupies but costs 17 % per pass (1.42 -> 1.67 ms forward), so 4 it is.
 #ifndef PNMN_PG_STAGES
 #define PNMN_PG_STAGES 4
 #endif
@@ -34,13 +36,43 @@ constexpr int kGHeader = 1024;
 constexpr int kGSmem = kGHeader + kGStages * kGStage;
 static_assert(kGSmem <= 227 * 1024, "step GEMM smem");
 
+// ---- optional per-launch phase stamps (make TRACE=1; scripts/pg_step_trace.py): globaltimer ns of CTA (0, 0, 0) ----
+#ifdef PNMN_PG_TRACE
+constexpr int kPgTrW = 16, kPgTrCap = 8192;
+__device__ long long g_pgtr[kPgTrW * kPgTrCap];
+__device__ int g_pgtr_n;
+__device__ __forceinline__ long long pg_gtime() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define PGT(slot) do { if (trace_on && tr_slot < kPgTrCap) g_pgtr[tr_slot * kPgTrW + (slot)] = pg_gtime(); } while (0)
+#else
+#define PGT(slot) do { } while (0)
+#endif
+
 struct GemmHeader {
   uint64_t full[kGStages], empty[kGStages];
   uint64_t tmem_full;
   uint32_t tmem_base;
+  int tr_slot;
 };
 
-__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+// Gate non-linearities from the fast exponential and reciprocal (MUFU.EX2 / MUFU.RCP, ~2 ulp each): absolute error below
+// 2e-7, against a parity bar of 1e-3.  The IEEE expf / division / tanhf versions cost 2.4 us of a 13 us step (27 slow-path
+// calls and 35 divergence regions in the SASS of the epilogue; scripts/pg_step_trace.py).
+__device__ __forceinline__ float sigmoidf_(float x) {
+  x = fminf(fmaxf(x, -30.f), 30.f);
+  return __fdividef(1.f, 1.f + __expf(-x));
+}
+__device__ __forceinline__ float tanhf_(float x) {
+  // |x| < 0.2: odd Taylor polynomial (next term 62/2835 x^9: < 6e-8 relative), else 1 - 2 / (1 + e^2x)
+  const float xc = fminf(fmaxf(x, -15.f), 15.f);
+  const float big = 1.f - __fdividef(2.f, 1.f + __expf(2.f * xc));
+  const float x2 = x * x;
+  const float small = x * fmaf(x2, fmaf(x2, fmaf(x2, -17.f / 315.f, 2.f / 15.f), -1.f / 3.f), 1.f);
+  return fabsf(x) < 0.2f ? small : big;
+}
 
 __device__ __forceinline__ uint4 pack8(const __half* h) {
   uint4 r;
@@ -51,96 +83,114 @@ __device__ __forceinline__ uint4 pack8(const __half* h) {
   return r;
 }
 
-// write 16 consecutive features [j0, j0+16) of row b into an operand buffer with K = 256
-__device__ __forceinline__ void store_op16(__half* op, int64_t lo_off, int b, int j0, const float* x) {
-  __half hi[16], lo[16];
+// write 8 consecutive features [j0, j0+8) of row b into an operand buffer with K = 256: one 16-byte group of the hi and of
+// the lo operand
+__device__ __forceinline__ void store_op8(__half* op, int64_t lo_off, int b, int j0, const float* x) {
+  __half hi[8], lo[8];
 #pragma unroll
-  for (int u = 0; u < 16; ++u) split_f16(x[u], hi[u], lo[u]);
-#pragma unroll
-  for (int gidx = 0; gidx < 2; ++gidx) {
-    const size_t off = op_off(b, j0 + 8 * gidx, kSH);
-    *reinterpret_cast<uint4*>(op + off) = pack8(hi + 8 * gidx);
-    *reinterpret_cast<uint4*>(op + lo_off + off) = pack8(lo + 8 * gidx);
-  }
+  for (int u = 0; u < 8; ++u) split_f16(x[u], hi[u], lo[u]);
+  const size_t off = op_off(b, j0, kSH);
+  *reinterpret_cast<uint4*>(op + off) = pack8(hi);
+  *reinterpret_cast<uint4*>(op + lo_off + off) = pack8(lo);
 }
 
 // ---- epilogues (shared by the tensor-core kernel and its CUDA-core twin) ----------------------------
-// acc[n], n = gate*16 + u  <->  pre-activation of gate `gate` of hidden unit j = nt*16 + u of row b
-__device__ __forceinline__ void epi_lstm(const GemmArgs& g, int b, int nt, const float* acc) {
+// LSTM cell of 8 hidden units j = nt*16 + hf*8 + e of row b.  Everything the cell reads besides the accumulator -- the
+// additive table row of the row's token (a dependent load behind the token), the previous cell / hidden state -- is
+// fetched by lstm_preload BEFORE the accumulator is waited for, so that these loads (two dependent L2 round trips) hide
+// under the operand stream and the MMAs; measured per launch (scripts/pg_step_trace.py): the epilogue took 7.4 us of a
+// 13 us step when four warps did loads, math and stores for 16 units each after the accumulator had arrived.
+struct LstmPre {
+  float tab[4][8];   // gate (i, f, g, o) x unit
+  float c[8], h[8];
+  bool valid;
+};
+__device__ __forceinline__ void ld8(const float* p, float* d) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+}
+__device__ __forceinline__ void st8(float* p, const float* d) {
+  *reinterpret_cast<float4*>(p) = make_float4(d[0], d[1], d[2], d[3]);
+  *reinterpret_cast<float4*>(p + 4) = make_float4(d[4], d[5], d[6], d[7]);
+}
+__device__ __forceinline__ void lstm_preload(const GemmArgs& g, int b, int nt, int hf, LstmPre& p) {
   if (b >= g.B) return;
-  const int j0 = nt * 16;
-  const float* tab = g.table + static_cast<size_t>(g.tok ? g.tok[static_cast<size_t>(b) * g.tok_stride] : 0) * kSG;
-  const bool valid = !g.len || g.t < g.len[b];
-  float hn[16], cn[16], ov[16], gi[16], gf[16], gg[16], go[16];
+  const int j0 = nt * 16 + hf * 8;
+  const float* tab = g.table + static_cast<size_t>(g.tok ? g.tok[static_cast<size_t>(b) * g.tok_stride] : 0) * kSG + j0;
+  p.valid = !g.len || g.t < g.len[b];
 #pragma unroll
-  for (int q4 = 0; q4 < 4; ++q4) {
-    const float4 ti = *reinterpret_cast<const float4*>(tab + j0 + 4 * q4);
-    const float4 tf = *reinterpret_cast<const float4*>(tab + kSH + j0 + 4 * q4);
-    const float4 tg = *reinterpret_cast<const float4*>(tab + 2 * kSH + j0 + 4 * q4);
-    const float4 to = *reinterpret_cast<const float4*>(tab + 3 * kSH + j0 + 4 * q4);
-    const float4 cp = *reinterpret_cast<const float4*>(g.c_prev + static_cast<size_t>(b) * kSH + j0 + 4 * q4);
-    const float4 hp = *reinterpret_cast<const float4*>(g.h_prev + static_cast<size_t>(b) * kSH + j0 + 4 * q4);
-    const float tis[4] = {ti.x, ti.y, ti.z, ti.w}, tfs[4] = {tf.x, tf.y, tf.z, tf.w};
-    const float tgs[4] = {tg.x, tg.y, tg.z, tg.w}, tos[4] = {to.x, to.y, to.z, to.w};
-    const float cps[4] = {cp.x, cp.y, cp.z, cp.w}, hps[4] = {hp.x, hp.y, hp.z, hp.w};
+  for (int gate = 0; gate < 4; ++gate) ld8(tab + gate * kSH, p.tab[gate]);
+  ld8(g.c_prev + static_cast<size_t>(b) * kSH + j0, p.c);
+  if (!p.valid) ld8(g.h_prev + static_cast<size_t>(b) * kSH + j0, p.h);   // only carried through a masked step
+}
+// acc[gate][e]: pre-activation (recurrent part) of gate `gate` of unit e.  (Staging the fp32 results in shared memory and
+// writing them with four lanes per 64-byte row segment was tried: slower, 2.5 us for the store loop against ~1.1 us for
+// the direct thread = row stores below.)
+__device__ __forceinline__ void epi_lstm_half(const GemmArgs& g, int b, int nt, int hf, const LstmPre& p,
+                                              const float (&acc)[4][8]) {
+  if (b >= g.B) return;
+  const int j0 = nt * 16 + hf * 8;
+  float gi[8], gf[8], gg[8], go[8], hn[8], cn[8], ov[8];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int u = 4 * q4 + e;
-      const float i_ = sigmoidf_(acc[u] + tis[e]);
-      const float f_ = sigmoidf_(acc[16 + u] + tfs[e]);
-      const float g_ = tanhf(acc[32 + u] + tgs[e]);
-      const float o_ = sigmoidf_(acc[48 + u] + tos[e]);
-      const float c2 = f_ * cps[e] + i_ * g_;
-      const float h2 = o_ * tanhf(c2);
-      gi[u] = i_; gf[u] = f_; gg[u] = g_; go[u] = o_;
-      hn[u] = valid ? h2 : hps[e];
-      cn[u] = valid ? c2 : cps[e];
-      ov[u] = valid ? h2 : 0.f;
-    }
+  for (int e = 0; e < 8; ++e) {
+    const float i_ = sigmoidf_(acc[0][e] + p.tab[0][e]);
+    const float f_ = sigmoidf_(acc[1][e] + p.tab[1][e]);
+    const float g_ = tanhf_(acc[2][e] + p.tab[2][e]);
+    const float o_ = sigmoidf_(acc[3][e] + p.tab[3][e]);
+    const float c2 = f_ * p.c[e] + i_ * g_;
+    const float h2 = o_ * tanhf_(c2);
+    gi[e] = i_; gf[e] = f_; gg[e] = g_; go[e] = o_;
+    hn[e] = p.valid ? h2 : p.h[e];
+    cn[e] = p.valid ? c2 : p.c[e];
+    ov[e] = p.valid ? h2 : 0.f;
   }
-  float* hd = g.h_out + static_cast<size_t>(b) * kSH + j0;
-  float* cd = g.c_out + static_cast<size_t>(b) * kSH + j0;
-#pragma unroll
-  for (int q4 = 0; q4 < 4; ++q4) {
-    *reinterpret_cast<float4*>(hd + 4 * q4) = make_float4(hn[4 * q4], hn[4 * q4 + 1], hn[4 * q4 + 2], hn[4 * q4 + 3]);
-    *reinterpret_cast<float4*>(cd + 4 * q4) = make_float4(cn[4 * q4], cn[4 * q4 + 1], cn[4 * q4 + 2], cn[4 * q4 + 3]);
-  }
-  store_op16(g.h_op, g.h_op_lo, b, j0, hn);
+  // the operand copies are [k/8][row][8]: consecutive rows are consecutive 16-byte groups, thread = row is coalesced
+  store_op8(g.h_op, g.h_op_lo, b, j0, hn);
+  if (g.out_op) store_op8(g.out_op, g.out_op_lo, b, j0, ov);
+  st8(g.h_out + static_cast<size_t>(b) * kSH + j0, hn);
+  st8(g.c_out + static_cast<size_t>(b) * kSH + j0, cn);
+  if (g.out_f) st8(g.out_f + static_cast<size_t>(b) * g.out_stride + j0, ov);
   if (g.gates) {
     float* gd = g.gates + static_cast<size_t>(b) * kSG + j0;
-#pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4) {
-      *reinterpret_cast<float4*>(gd + 4 * q4) = make_float4(gi[4 * q4], gi[4 * q4 + 1], gi[4 * q4 + 2], gi[4 * q4 + 3]);
-      *reinterpret_cast<float4*>(gd + kSH + 4 * q4) = make_float4(gf[4 * q4], gf[4 * q4 + 1], gf[4 * q4 + 2], gf[4 * q4 + 3]);
-      *reinterpret_cast<float4*>(gd + 2 * kSH + 4 * q4) = make_float4(gg[4 * q4], gg[4 * q4 + 1], gg[4 * q4 + 2], gg[4 * q4 + 3]);
-      *reinterpret_cast<float4*>(gd + 3 * kSH + 4 * q4) = make_float4(go[4 * q4], go[4 * q4 + 1], go[4 * q4 + 2], go[4 * q4 + 3]);
-    }
+    st8(gd, gi); st8(gd + kSH, gf); st8(gd + 2 * kSH, gg); st8(gd + 3 * kSH, go);
   }
-  if (g.out_f) {
-    float* od = g.out_f + static_cast<size_t>(b) * g.out_stride + j0;
+}
+// whole 64-column tile of one row (CUDA-core twin): acc[n], n = gate*16 + u
+__device__ __forceinline__ void epi_lstm(const GemmArgs& g, int b, int nt, const float* acc) {
 #pragma unroll
-    for (int q4 = 0; q4 < 4; ++q4)
-      *reinterpret_cast<float4*>(od + 4 * q4) = make_float4(ov[4 * q4], ov[4 * q4 + 1], ov[4 * q4 + 2], ov[4 * q4 + 3]);
+  for (int hf = 0; hf < 2; ++hf) {
+    LstmPre p;
+    lstm_preload(g, b, nt, hf, p);
+    float a4[4][8];
+#pragma unroll
+    for (int gate = 0; gate < 4; ++gate)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a4[gate][e] = acc[gate * 16 + hf * 8 + e];
+    epi_lstm_half(g, b, nt, hf, p, a4);
   }
-  if (g.out_op) store_op16(g.out_op, g.out_op_lo, b, j0, ov);
 }
 
 // acc[c], c in [0, 64): column n = nt*64 + c of [dA1 | dA2].  The K range is split over blockIdx.z, so the partial
 // sums are ADDED (fire-and-forget reductions) into buffers whose consumers left them zeroed; masked rows (beyond the
 // sequence length) contribute nothing: carried state stays, per-step outputs stay zero.
-__device__ __forceinline__ void epi_dgrad(const GemmArgs& g, int b, int nt, const float* acc) {
+__device__ __forceinline__ void epi_dgrad_cols(const GemmArgs& g, int b, int nt, int c0, int nc, const float* acc) {
   if (b >= g.B) return;
   if (g.len && g.t >= g.len[b]) return;
   const int n0 = nt * 64, which = n0 >> 8, col0 = n0 & 255;
   const float s = g.scale[1];
-  float* od = g.out[which] + static_cast<size_t>(b) * kSH + col0;
+  float* od = g.out[which] + static_cast<size_t>(b) * kSH + col0 + c0;
 #pragma unroll
-  for (int c = 0; c < 64; ++c) red_add_f32(od + c, acc[c] * s);
+  for (int c = 0; c < 32; c += 4)
+    if (c < nc) red_add_f32x4(od + c, acc[c] * s, acc[c + 1] * s, acc[c + 2] * s, acc[c + 3] * s);
+}
+__device__ __forceinline__ void epi_dgrad(const GemmArgs& g, int b, int nt, const float* acc) {
+  epi_dgrad_cols(g, b, nt, 0, 32, acc);
+  epi_dgrad_cols(g, b, nt, 32, 32, acc + 32);
 }
 
 // ---- tensor-core kernel ------------------------------------------------------------------------------
 template <int EPI>
-__global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmPair pr) {
+__global__ void __launch_bounds__(kGThreads, kGStages <= 2 ? 2 : 1) step_gemm_tc_kernel(const GemmPair pr) {
   extern __shared__ __align__(1024) uint8_t smem[];
   GemmHeader* hdr = reinterpret_cast<GemmHeader*>(smem);
   uint8_t* ring = smem + kGHeader;
@@ -156,6 +206,16 @@ __global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmPa
   const int kc_lo = (g.K / 64) * blockIdx.z / gridDim.z, kc_hi = (g.K / 64) * (blockIdx.z + 1) / gridDim.z;
   const int n_chunks = kc_hi - kc_lo;
   pdl_launch_dependents();
+#ifdef PNMN_PG_TRACE
+  const bool trace_on = blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  if (trace_on && threadIdx.x == 0) {
+    hdr->tr_slot = atomicAdd(&g_pgtr_n, 1);
+    if (hdr->tr_slot < kPgTrCap) {
+      g_pgtr[hdr->tr_slot * kPgTrW + 0] = pg_gtime();
+      g_pgtr[hdr->tr_slot * kPgTrW + 15] = EPI * 1000000 + g.K * 1000 + gridDim.x * gridDim.y * gridDim.z;
+    }
+  }
+#endif
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kGStages; ++i) {
@@ -170,84 +230,132 @@ __global__ void __launch_bounds__(kGThreads, 1) step_gemm_tc_kernel(const GemmPa
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
+#ifdef PNMN_PG_TRACE
+  const int tr_slot = hdr->tr_slot;
+  if (threadIdx.x == 0) PGT(1);
+#endif
 
-  if (warp == 0) {
-    if (lane == 0) {
-      // the packed weights were written long before the previous step: prefetch them for the first ring pass, THEN wait
-      // for the previous kernel (whose epilogue produces this step's activation operand)
-      const int pre = n_chunks < kGStages ? n_chunks : kGStages;
-      for (int it = 0; it < pre; ++it) {
-        const uint32_t bar = smem_u32(&hdr->full[it]);
+  // Roles: lane 0 of warp 0 streams the operands, lane 0 of warp 1 issues the MMAs; then ALL eight warps run the epilogue:
+  // warp w owns TMEM lane quarter q = w % 4 (rows q*32 + lane) and column half hf = w / 4 (EPI_LSTM: hidden units
+  // hf*8 .. hf*8+7 of the tile, EPI_DGRAD: columns hf*32 .. hf*32+31).
+  const int q = warp & 3, hf = warp >> 2;
+  const int b = mt * 128 + q * 32 + lane;
+  if (warp == 0 && lane == 0) {
+    // the packed weights were written long before the previous step: prefetch them for the first ring pass, THEN wait
+    // for the previous kernel (whose epilogue produces this step's activation operand)
+    const int pre = n_chunks < kGStages ? n_chunks : kGStages;
+    for (int it = 0; it < pre; ++it) {
+      const uint32_t bar = smem_u32(&hdr->full[it]);
+      mbar_arrive_expect_tx(bar, kGStage);
+      const __half* w = g.w + (static_cast<size_t>(nt) * (g.K >> 3) + (kc_lo + it) * 8) * 512;
+      const uint32_t dst = smem_u32(ring + it * kGStage);
+      bulk_g2s(dst + 2 * kGABytes, w, kGWBytes, bar);
+      bulk_g2s(dst + 2 * kGABytes + kGWBytes, w + g.w_lo, kGWBytes, bar);
+    }
+  }
+  pdl_wait();   // everything below reads what the previous step's kernel wrote
+  LstmPre lp;
+  // (the producer thread first gets the operand stream going, then fetches its own row's epilogue inputs)
+  if (EPI == EPI_LSTM && !(warp == 0 && lane == 0)) lstm_preload(g, b, nt, hf, lp);
+  if (warp == 0 && lane == 0) {
+    PGT(2);
+    const int pre = n_chunks < kGStages ? n_chunks : kGStages;
+    for (int it = 0; it < n_chunks; ++it) {
+      const int kc = kc_lo + it;
+      const int st = it % kGStages;
+      const uint32_t bar = smem_u32(&hdr->full[st]);
+      const uint32_t dst = smem_u32(ring + st * kGStage);
+      if (it >= pre) {
+        mbar_wait(smem_u32(&hdr->empty[st]), ((it / kGStages) & 1) ^ 1);
         mbar_arrive_expect_tx(bar, kGStage);
-        const __half* w = g.w + (static_cast<size_t>(nt) * (g.K >> 3) + (kc_lo + it) * 8) * 512;
-        const uint32_t dst = smem_u32(ring + it * kGStage);
+        const __half* w = g.w + (static_cast<size_t>(nt) * (g.K >> 3) + kc * 8) * 512;
         bulk_g2s(dst + 2 * kGABytes, w, kGWBytes, bar);
         bulk_g2s(dst + 2 * kGABytes + kGWBytes, w + g.w_lo, kGWBytes, bar);
       }
-      pdl_wait();
-      for (int it = 0; it < n_chunks; ++it) {
-        const int kc = kc_lo + it;
-        const int st = it % kGStages;
-        const uint32_t bar = smem_u32(&hdr->full[st]);
-        const uint32_t dst = smem_u32(ring + st * kGStage);
-        if (it >= pre) {
-          mbar_wait(smem_u32(&hdr->empty[st]), ((it / kGStages) & 1) ^ 1);
-          mbar_arrive_expect_tx(bar, kGStage);
-          const __half* w = g.w + (static_cast<size_t>(nt) * (g.K >> 3) + kc * 8) * 512;
-          bulk_g2s(dst + 2 * kGABytes, w, kGWBytes, bar);
-          bulk_g2s(dst + 2 * kGABytes + kGWBytes, w + g.w_lo, kGWBytes, bar);
-        }
-        const int si = kc / g.chunks_per_src, cj = kc % g.chunks_per_src;
-        const __half* a = g.a[si] + (static_cast<size_t>(mt) * (g.a_K[si] >> 3) + cj * 8) * 1024;
-        bulk_g2s(dst, a, kGABytes, bar);
-        bulk_g2s(dst + kGABytes, a + g.a_lo[si], kGABytes, bar);
-      }
+      const int si = kc / g.chunks_per_src, cj = kc % g.chunks_per_src;
+      const __half* a = g.a[si] + (static_cast<size_t>(mt) * (g.a_K[si] >> 3) + cj * 8) * 1024;
+      bulk_g2s(dst, a, kGABytes, bar);
+      bulk_g2s(dst + kGABytes, a + g.a_lo[si], kGABytes, bar);
+      if (EPI == EPI_LSTM && it + 1 == (n_chunks < kGStages ? n_chunks : kGStages)) lstm_preload(g, b, nt, hf, lp);
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(128, 64, 0, 0);
-      // K-major, no swizzle: LBO = distance between the two 8-deep halves of a k16 step (one plane), SBO = 128 B
-      const uint64_t a_hi = make_smem_desc(0, 128 * 16, 128) & 0xFFFFFFFFFFFFC000ull;
-      const uint64_t w_hi = make_smem_desc(0, 64 * 16, 128) & 0xFFFFFFFFFFFFC000ull;
-      for (int kc = 0; kc < n_chunks; ++kc) {   // kc counts this CTA's chunks
-        const int st = kc % kGStages;
-        mbar_wait(smem_u32(&hdr->full[st]), (kc / kGStages) & 1);
-        tc_fence_after();
-        const uint32_t base = smem_u32(ring + st * kGStage);
+    PGT(3);
+  } else if (warp == 1 && lane == 0) {
+    const uint32_t idesc = make_idesc_f16(128, 64, 0, 0);
+    // K-major, no swizzle: LBO = distance between the two 8-deep halves of a k16 step (one plane), SBO = 128 B
+    const uint64_t a_hi = make_smem_desc(0, 128 * 16, 128) & 0xFFFFFFFFFFFFC000ull;
+    const uint64_t w_hi = make_smem_desc(0, 64 * 16, 128) & 0xFFFFFFFFFFFFC000ull;
+    for (int kc = 0; kc < n_chunks; ++kc) {   // kc counts this CTA's chunks
+      const int st = kc % kGStages;
+      mbar_wait(smem_u32(&hdr->full[st]), (kc / kGStages) & 1);
+      tc_fence_after();
+      if (kc == 0) PGT(4);
+      if (kc == n_chunks - 1) PGT(5);
+      const uint32_t base = smem_u32(ring + st * kGStage);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const uint64_t ah = a_hi | (((base + i * 2 * 2048) >> 4) & 0x3FFF);
-          const uint64_t al = a_hi | (((base + kGABytes + i * 2 * 2048) >> 4) & 0x3FFF);
-          const uint64_t wh = w_hi | (((base + 2 * kGABytes + i * 2 * 1024) >> 4) & 0x3FFF);
-          const uint64_t wl = w_hi | (((base + 2 * kGABytes + kGWBytes + i * 2 * 1024) >> 4) & 0x3FFF);
-          umma_f16(tmem_base, ah, wh, idesc, (kc | i) != 0);
-          umma_f16(tmem_base, al, wh, idesc, 1);
-          umma_f16(tmem_base, ah, wl, idesc, 1);
-        }
-        umma_commit(smem_u32(&hdr->empty[st]));
+      for (int i = 0; i < 4; ++i) {
+        const uint64_t ah = a_hi | (((base + i * 2 * 2048) >> 4) & 0x3FFF);
+        const uint64_t al = a_hi | (((base + kGABytes + i * 2 * 2048) >> 4) & 0x3FFF);
+        const uint64_t wh = w_hi | (((base + 2 * kGABytes + i * 2 * 1024) >> 4) & 0x3FFF);
+        const uint64_t wl = w_hi | (((base + 2 * kGABytes + kGWBytes + i * 2 * 1024) >> 4) & 0x3FFF);
+        umma_f16(tmem_base, ah, wh, idesc, (kc | i) != 0);
+        umma_f16(tmem_base, al, wh, idesc, 1);
+        umma_f16(tmem_base, ah, wl, idesc, 1);
       }
-      umma_commit(smem_u32(&hdr->tmem_full));
+      umma_commit(smem_u32(&hdr->empty[st]));
     }
-  } else if (warp >= 4) {
-    const int q = warp & 3;
-    const int b = mt * 128 + q * 32 + lane;
-    pdl_wait();   // the epilogue reads state written by the previous step's kernel
-    mbar_wait(smem_u32(&hdr->tmem_full), 0);
-    tc_fence_after();
-    uint32_t v0[32], v1[32];
-    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16), v0);
-    tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + 32, v1);
-    tmem_ld_wait();
-    float acc[64];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) { acc[i] = __uint_as_float(v0[i]); acc[32 + i] = __uint_as_float(v1[i]); }
-    if (EPI == EPI_LSTM) epi_lstm(g, b, nt, acc);
-    else epi_dgrad(g, b, nt, acc);
+    umma_commit(smem_u32(&hdr->tmem_full));
+    PGT(6);
   }
+  __syncwarp();
+  mbar_wait(smem_u32(&hdr->tmem_full), 0);
+  tc_fence_after();
+  if (threadIdx.x == 128) PGT(7);
+  const uint32_t lane_addr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+  if (EPI == EPI_LSTM) {
+    uint32_t v[4][8];
+#pragma unroll
+    for (int gate = 0; gate < 4; ++gate) tmem_ld8(lane_addr + gate * 16 + hf * 8, v[gate]);
+    tmem_ld_wait();
+    if (threadIdx.x == 128) PGT(8);
+    float acc[4][8];
+#pragma unroll
+    for (int gate = 0; gate < 4; ++gate)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[gate][e] = __uint_as_float(v[gate][e]);
+    epi_lstm_half(g, b, nt, hf, lp, acc);
+  } else {
+    uint32_t v[32];
+    tmem_ld32(lane_addr + hf * 32, v);
+    tmem_ld_wait();
+    if (threadIdx.x == 128) PGT(8);
+    float acc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) acc[i] = __uint_as_float(v[i]);
+    epi_dgrad_cols(g, b, nt, hf * 32, 32, acc);
+  }
+  if (threadIdx.x == 128) PGT(9);
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) PGT(10);
   if (warp == 2) tmem_dealloc<64>(tmem_base);
 }
+
+#ifdef PNMN_PG_TRACE
+}  // namespace pnmn
+// trace builds only: copies the stamps of the launches recorded so far ([n][16] int64) and clears the counter
+extern "C" int pnmn_debug_pg_trace(long long* out, int cap) {
+  int n = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&n, pnmn::g_pgtr_n, sizeof(int));
+  if (n > pnmn::kPgTrCap) n = pnmn::kPgTrCap;
+  if (n > cap) n = cap;
+  if (n > 0) cudaMemcpyFromSymbol(out, pnmn::g_pgtr, sizeof(long long) * pnmn::kPgTrW * n);
+  const int zero = 0;
+  cudaMemcpyToSymbol(pnmn::g_pgtr_n, &zero, sizeof(int));
+  return n;
+}
+namespace pnmn {
+#endif
 
 // ---- CUDA-core twin (bring-up): thread = batch row, 64 fp32 accumulators ------------------------------
 template <int EPI>
@@ -408,8 +516,9 @@ __global__ void __launch_bounds__(kGThreads, 1) wgrad_seq_tc_kernel(const WgradS
       tmem_ld_wait();
       if (total > 0) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
-          atomicAdd(a.dw + static_cast<size_t>(grow) * a.ld + nt * 128 + chunk * 32 + j, __uint_as_float(v[j]) * unscale);
+        for (int j = 0; j < 32; j += 4)
+          red_add_f32x4(a.dw + static_cast<size_t>(grow) * a.ld + nt * 128 + chunk * 32 + j, __uint_as_float(v[j]) * unscale,
+                        __uint_as_float(v[j + 1]) * unscale, __uint_as_float(v[j + 2]) * unscale, __uint_as_float(v[j + 3]) * unscale);
       }
     }
   }

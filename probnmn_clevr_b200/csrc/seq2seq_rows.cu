@@ -144,15 +144,29 @@ cudaError_t launch_accumulate(float* dst, const float* src, int64_t n, cudaStrea
 // token (greedy max or categorical sampling, seq2seq_base.py:201-220) and its log-probability.  Called by a whole CTA.
 __device__ __forceinline__ void dec_output_step(const DecRowArgs& a, const SeqDims& d, int b, int tp, const float* sh,
                                                 float* slg, float* satt, int* s_pred, int warp, int lane) {
-    for (int v = warp; v < d.Vt; v += 8) {
-      const float4 w0 = *reinterpret_cast<const float4*>(a.out_w + static_cast<size_t>(v) * kSH + lane * 8);
-      const float4 w1 = *reinterpret_cast<const float4*>(a.out_w + static_cast<size_t>(v) * kSH + lane * 8 + 4);
+    // four vocabulary entries per round, their eight 16-byte loads issued before the first reduction
+    for (int v0 = warp; v0 < d.Vt; v0 += 32) {
+      float4 w0[4], w1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int v = v0 + 8 * k;
+        if (v < d.Vt) {
+          w0[k] = __ldg(reinterpret_cast<const float4*>(a.out_w + static_cast<size_t>(v) * kSH + lane * 8));
+          w1[k] = __ldg(reinterpret_cast<const float4*>(a.out_w + static_cast<size_t>(v) * kSH + lane * 8 + 4));
+        }
+      }
       const float* h = sh + lane * 8;
-      float acc = w0.x * h[0];
-      acc = fmaf(w0.y, h[1], acc); acc = fmaf(w0.z, h[2], acc); acc = fmaf(w0.w, h[3], acc);
-      acc = fmaf(w1.x, h[4], acc); acc = fmaf(w1.y, h[5], acc); acc = fmaf(w1.z, h[6], acc); acc = fmaf(w1.w, h[7], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) slg[v] = acc + a.out_b[v];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int v = v0 + 8 * k;
+        if (v < d.Vt) {
+          float acc = w0[k].x * h[0];
+          acc = fmaf(w0[k].y, h[1], acc); acc = fmaf(w0[k].z, h[2], acc); acc = fmaf(w0[k].w, h[3], acc);
+          acc = fmaf(w1[k].x, h[4], acc); acc = fmaf(w1[k].y, h[5], acc); acc = fmaf(w1[k].z, h[6], acc); acc = fmaf(w1[k].w, h[7], acc);
+          acc = warp_sum(acc);
+          if (lane == 0) slg[v] = acc + __ldg(a.out_b + v);
+        }
+      }
     }
     __syncthreads();
     if (warp == 0) {
@@ -238,6 +252,7 @@ __device__ __forceinline__ void dec_output_step(const DecRowArgs& a, const SeqDi
 }
 
 __global__ void __launch_bounds__(256) dec_row_kernel(const DecRowArgs a) {
+  extern __shared__ __align__(16) float s_enc[];   // [Ts][256]: the row's encoder outputs, fetched once for scores AND context
   __shared__ float sh[kSH], satt[kSH], slg[kSMaxV], ssc[kSMaxT], sp[kSMaxT];
   __shared__ int s_pred;
   const SeqDims& d = a.d;
@@ -261,15 +276,33 @@ __global__ void __launch_bounds__(256) dec_row_kernel(const DecRowArgs a) {
   // ---- dot-product attention ---------------------------------------------------------------------------
   const float* enc = a.enc + static_cast<size_t>(b) * d.Ts * kSH;
   const int len = a.src_len[b];
-  for (int s = warp; s < d.Ts; s += 8) {
-    const float4 e0 = *reinterpret_cast<const float4*>(enc + static_cast<size_t>(s) * kSH + lane * 8);
-    const float4 e1 = *reinterpret_cast<const float4*>(enc + static_cast<size_t>(s) * kSH + lane * 8 + 4);
+  // warp w takes positions w, w+8, ...: all of its (<= 8) row loads are issued before the first dot product, and the rows
+  // are kept in shared memory for the context vector below (they used to be re-read from L2 by a loop of dependent loads:
+  // ~3 us of this ~13 us kernel)
+  {
+    float4 e0[kSMaxT / 8], e1[kSMaxT / 8];
+#pragma unroll
+    for (int k = 0; k < kSMaxT / 8; ++k) {
+      const int s = warp + 8 * k;
+      if (s < d.Ts) {
+        e0[k] = __ldg(reinterpret_cast<const float4*>(enc + static_cast<size_t>(s) * kSH + lane * 8));
+        e1[k] = __ldg(reinterpret_cast<const float4*>(enc + static_cast<size_t>(s) * kSH + lane * 8 + 4));
+      }
+    }
     const float* h = sh + lane * 8;
-    float acc = e0.x * h[0];
-    acc = fmaf(e0.y, h[1], acc); acc = fmaf(e0.z, h[2], acc); acc = fmaf(e0.w, h[3], acc);
-    acc = fmaf(e1.x, h[4], acc); acc = fmaf(e1.y, h[5], acc); acc = fmaf(e1.z, h[6], acc); acc = fmaf(e1.w, h[7], acc);
-    acc = warp_sum(acc);
-    if (lane == 0) ssc[s] = acc;
+#pragma unroll
+    for (int k = 0; k < kSMaxT / 8; ++k) {
+      const int s = warp + 8 * k;
+      if (s < d.Ts) {
+        *reinterpret_cast<float4*>(s_enc + s * kSH + lane * 8) = e0[k];
+        *reinterpret_cast<float4*>(s_enc + s * kSH + lane * 8 + 4) = e1[k];
+        float acc = e0[k].x * h[0];
+        acc = fmaf(e0[k].y, h[1], acc); acc = fmaf(e0[k].z, h[2], acc); acc = fmaf(e0[k].w, h[3], acc);
+        acc = fmaf(e1[k].x, h[4], acc); acc = fmaf(e1[k].y, h[5], acc); acc = fmaf(e1[k].z, h[6], acc); acc = fmaf(e1[k].w, h[7], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) ssc[s] = acc;
+      }
+    }
   }
   __syncthreads();
   if (warp == 0) {
@@ -311,14 +344,21 @@ __global__ void __launch_bounds__(256) dec_row_kernel(const DecRowArgs a) {
   __syncthreads();
   {
     float acc = 0.f;
-    for (int s = 0; s < len; ++s) acc = fmaf(sp[s], enc[static_cast<size_t>(s) * kSH + tid], acc);
+    for (int s = 0; s < len; ++s) acc = fmaf(sp[s], s_enc[s * kSH + tid], acc);
     satt[tid] = acc;
   }
   __syncthreads();
   if (tid < kSH / 8) store_op8(a.att_op + static_cast<size_t>(t) * a.att_step, a.att_lo, b, tid * 8, kSH, satt + tid * 8, 1.f);
 }
 cudaError_t launch_dec_row(const DecRowArgs& a, cudaStream_t st) {
-  return launch_pdl(dec_row_kernel, dim3(a.d.B), dim3(256), 0, st, seq_use_pdl(), a);
+  const size_t smem = static_cast<size_t>(a.d.Ts) * kSH * sizeof(float);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(dec_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSMaxT * kSH * sizeof(float)));
+    if (e != cudaSuccess) return e;
+    attr_smem = kSMaxT * kSH * sizeof(float);
+  }
+  return launch_pdl(dec_row_kernel, dim3(a.d.B), dim3(256), smem, st, seq_use_pdl(), a);
 }
 
 // every step's output of a teacher-forced pass at once: grid = (rows, steps)
@@ -426,7 +466,8 @@ __device__ __forceinline__ void cell_bwd(float dh, float dc_in, float i_, float 
 }
 
 __global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a) {
-  __shared__ float s_datt[kSH], s_dp[kSMaxT], s_ds[kSMaxT], s_p[kSMaxT], s_dl[kSMaxV];
+  extern __shared__ __align__(16) float s_enc[];   // [Ts][256] (as in dec_row_kernel)
+  __shared__ float s_datt[kSH], s_dp[kSMaxT], s_ds[kSMaxT], s_p[kSMaxT];
   __shared__ __align__(16) float s_dg[kSG];
   const SeqDims& d = a.d;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -444,7 +485,6 @@ __global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a)
         *reinterpret_cast<uint4*>(op + off) = z;
         *reinterpret_cast<uint4*>(op + a.dg_lo + off) = z;
       }
-      if (tid < d.Vt) a.dlogits[(static_cast<size_t>(t) * d.Bp + b) * d.Vt + tid] = 0.f;
     }
     return;
   }
@@ -464,15 +504,30 @@ __global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a)
     s_datt[tid] = datt;
     if (tid < d.Ts) s_p[tid] = a.attn_p[(static_cast<size_t>(ta) * d.B + b) * d.Ts + tid];
     __syncthreads();
-    for (int s = warp; s < len; s += 8) {
-      const float4 e0 = *reinterpret_cast<const float4*>(enc + static_cast<size_t>(s) * kSH + lane * 8);
-      const float4 e1 = *reinterpret_cast<const float4*>(enc + static_cast<size_t>(s) * kSH + lane * 8 + 4);
+    {
+      float4 e0[kSMaxT / 8], e1[kSMaxT / 8];
+#pragma unroll
+      for (int k = 0; k < kSMaxT / 8; ++k) {
+        const int s = warp + 8 * k;
+        if (s < len) {
+          e0[k] = __ldg(reinterpret_cast<const float4*>(enc + static_cast<size_t>(s) * kSH + lane * 8));
+          e1[k] = __ldg(reinterpret_cast<const float4*>(enc + static_cast<size_t>(s) * kSH + lane * 8 + 4));
+        }
+      }
       const float* g = s_datt + lane * 8;
-      float acc = e0.x * g[0];
-      acc = fmaf(e0.y, g[1], acc); acc = fmaf(e0.z, g[2], acc); acc = fmaf(e0.w, g[3], acc);
-      acc = fmaf(e1.x, g[4], acc); acc = fmaf(e1.y, g[5], acc); acc = fmaf(e1.z, g[6], acc); acc = fmaf(e1.w, g[7], acc);
-      acc = warp_sum(acc);
-      if (lane == 0) s_dp[s] = acc;
+#pragma unroll
+      for (int k = 0; k < kSMaxT / 8; ++k) {
+        const int s = warp + 8 * k;
+        if (s < len) {
+          *reinterpret_cast<float4*>(s_enc + s * kSH + lane * 8) = e0[k];
+          *reinterpret_cast<float4*>(s_enc + s * kSH + lane * 8 + 4) = e1[k];
+          float acc = e0[k].x * g[0];
+          acc = fmaf(e0[k].y, g[1], acc); acc = fmaf(e0[k].z, g[2], acc); acc = fmaf(e0[k].w, g[3], acc);
+          acc = fmaf(e1[k].x, g[4], acc); acc = fmaf(e1[k].y, g[5], acc); acc = fmaf(e1[k].z, g[6], acc); acc = fmaf(e1[k].w, g[7], acc);
+          acc = warp_sum(acc);
+          if (lane == 0) s_dp[s] = acc;
+        }
+      }
     }
     __syncthreads();
     if (warp == 0) {
@@ -482,11 +537,20 @@ __global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a)
       for (int s = lane; s < d.Ts; s += 32) s_ds[s] = s < len ? s_p[s] * (s_dp[s] - G) : 0.f;
     }
     __syncthreads();
+    // eight positions at a time, every load before the first store: `denc` may alias `enc` as far as the compiler knows,
+    // and with one read-modify-write per iteration the loop was a chain of up to Ts dependent L2 round trips
     float acc = 0.f;
-    for (int s = 0; s < len; ++s) {
-      const float e = enc[static_cast<size_t>(s) * kSH + tid];
-      acc = fmaf(s_ds[s], e, acc);
-      denc[static_cast<size_t>(s) * kSH + tid] += s_p[s] * datt + s_ds[s] * hq;
+    for (int s0 = 0; s0 < len; s0 += 8) {
+      float dv[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (s0 + k < len) dv[k] = denc[static_cast<size_t>(s0 + k) * kSH + tid];
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (s0 + k < len) {
+          acc = fmaf(s_ds[s0 + k], s_enc[(s0 + k) * kSH + tid], acc);
+          denc[static_cast<size_t>(s0 + k) * kSH + tid] = dv[k] + s_p[s0 + k] * datt + s_ds[s0 + k] * hq;
+        }
     }
     dh += acc;
   }
@@ -495,21 +559,8 @@ __global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a)
     return;
   }
 
-  // ---- output projection + (log-)softmax backward of step t ---------------------------------------------
-  const float cf = a.grad_loss[b] * a.coef[static_cast<size_t>(t) * d.B + b];
-  if (tid < d.Vt) {
-    const float lg = a.logits[(static_cast<size_t>(t) * d.B + b) * d.Vt + tid];
-    const float p = expf(lg - a.lse[static_cast<size_t>(t) * d.B + b]);
-    const float dl = cf * (p - (tid == a.label[static_cast<size_t>(t) * d.B + b] ? 1.f : 0.f));
-    s_dl[tid] = dl;
-    a.dlogits[(static_cast<size_t>(t) * d.Bp + b) * d.Vt + tid] = dl;
-  }
-  __syncthreads();
-  if (cf != 0.f) {
-    float acc = 0.f;
-    for (int v = 0; v < d.Vt; ++v) acc = fmaf(a.out_w[static_cast<size_t>(v) * kSH + tid], s_dl[v], acc);
-    dh += acc;
-  }
+  // ---- output projection + (log-)softmax backward of step t: precomputed for every step (dec_bwd_proj_kernel) ----------
+  dh += a.dhp[(static_cast<size_t>(t) * d.Bp + b) * kSH + tid];
   // ---- LSTM cell backward ---------------------------------------------------------------------------------
   const float* gt = a.gates + (static_cast<size_t>(t) * d.Bp + b) * kSG;
   float da[4], dc_prev;
@@ -521,8 +572,44 @@ __global__ void __launch_bounds__(256) dec_bwd_row_kernel(const DecBwdRowArgs a)
   __syncthreads();
   if (tid < kSG / 8) store_op8(a.dg_op + static_cast<size_t>(t) * a.dg_step, a.dg_lo, b, tid * 8, kSG, s_dg + tid * 8, a.scale[0]);
 }
+// d(loss)/d(logits) of EVERY step and its image under the output projection, dhp[t][b][j] = sum_v W_o[v][j] * dlogits[t][b][v]:
+// neither depends on the backward recurrence (the coefficients, logits and labels are the forward pass's), so they are
+// computed in one launch over (row, step) instead of inside each of the S dependent row kernels (~2 us of each step)
+__global__ void __launch_bounds__(256) dec_bwd_proj_kernel(const DecBwdRowArgs a) {
+  __shared__ float s_dl[kSMaxV];
+  const SeqDims& d = a.d;
+  const int b = blockIdx.x, t = blockIdx.y, tid = threadIdx.x;
+  const float cf = b < d.B ? a.grad_loss[b] * a.coef[static_cast<size_t>(t) * d.B + b] : 0.f;
+  if (tid < d.Vt) {
+    float dl = 0.f;
+    if (cf != 0.f) {
+      const float lg = a.logits[(static_cast<size_t>(t) * d.B + b) * d.Vt + tid];
+      const float p = expf(lg - a.lse[static_cast<size_t>(t) * d.B + b]);
+      dl = cf * (p - (tid == a.label[static_cast<size_t>(t) * d.B + b] ? 1.f : 0.f));
+    }
+    s_dl[tid] = dl;
+    a.dlogits[(static_cast<size_t>(t) * d.Bp + b) * d.Vt + tid] = dl;
+  }
+  __syncthreads();
+  float acc = 0.f;
+  if (cf != 0.f)
+    for (int v = 0; v < d.Vt; ++v) acc = fmaf(__ldg(a.out_w + static_cast<size_t>(v) * kSH + tid), s_dl[v], acc);
+  a.dhp[(static_cast<size_t>(t) * d.Bp + b) * kSH + tid] = acc;
+}
+cudaError_t launch_dec_bwd_proj(const DecBwdRowArgs& a, cudaStream_t st) {
+  dec_bwd_proj_kernel<<<dim3(a.d.Bp, a.d.S), 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_dec_bwd_row(const DecBwdRowArgs& a, cudaStream_t st) {
-  return launch_pdl(dec_bwd_row_kernel, dim3(a.d.Bp), dim3(256), 0, st, seq_use_pdl(), a);
+  const size_t smem = static_cast<size_t>(a.d.Ts) * kSH * sizeof(float);
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    cudaError_t e = cudaFuncSetAttribute(dec_bwd_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSMaxT * kSH * sizeof(float)));
+    if (e != cudaSuccess) return e;
+    attr_smem = kSMaxT * kSH * sizeof(float);
+  }
+  return launch_pdl(dec_bwd_row_kernel, dim3(a.d.Bp), dim3(256), smem, st, seq_use_pdl(), a);
 }
 
 // encoder: LSTM cell backward of one (layer, step); rows beyond their length carry dh / dc through unchanged

@@ -37,23 +37,36 @@ struct WgSmemHeader {
   uint64_t empty[kWgStages];
   uint64_t tmem_full;
   uint32_t tmem_base;
+  int task_idx;
 };
 
+__device__ __forceinline__ int wg_smid() {
+  int v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+  return v;
+}
+
+// counter == nullptr: CTA i runs task i (bring-up entry point).  Otherwise every CTA PULLS tasks from *counter until the list
+// is exhausted, and CTAs that land on an SM >= sm_limit leave at once: the kernel keeps off the SMs reserved for other
+// streams (pnmn_set_reserved_sms) exactly like the executor.  The grid still has one CTA per task: a CTA needs a whole SM
+// (227 KB of shared memory, all 512 TMEM columns), and when kernels of other streams come and go on the device only a
+// steady supply of pending CTAs gets hold of every SM that falls free (one persistent CTA per SM, placed once at launch,
+// ended up on a fraction of the SMs); CTAs that start after the list has run dry return before setting anything up.
 __global__ void __launch_bounds__(kWgThreads, 1)
-wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
+wgrad_tc_kernel(const WgradTask* __restrict__ tasks, int n_tasks, int* __restrict__ counter, int sm_limit) {
+  if (counter && wg_smid() >= sm_limit) return;
   extern __shared__ __align__(1024) uint8_t smem[];
   WgSmemHeader* hdr = reinterpret_cast<WgSmemHeader*>(smem);
   uint8_t* ring = smem + kWgHeader;
-  const WgradTask t = tasks[blockIdx.x];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
-  const int halo = t.ntaps_x == 3 ? t.dil : 0;
-  const int xs = kWgChunk + 2 * halo;                 // X slots per half plane per stage
-  const int n_valid = kHW * t.S;                      // slots that can carry a non-zero dZ
-  const int n_chunks = (n_valid + kWgChunk - 1) / kWgChunk;
-  const int row_shift = t.ntaps_x == 3 ? (t.tap_row - 1) * t.dil * t.S : 0;
-  const uint32_t dz_bytes = kHP * kWgChunk * 16;
-  const int total = t.n_inst * n_chunks;
+  int task_idx = static_cast<int>(blockIdx.x);
+  if (counter) {
+    if (threadIdx.x == 0) hdr->task_idx = atomicAdd(counter, 1);
+    __syncthreads();
+    task_idx = hdr->task_idx;
+    if (task_idx >= n_tasks) return;
+  }
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kWgStages; ++i) {
@@ -69,14 +82,27 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
   tc_fence_after();
   const uint32_t tmem_base = hdr->tmem_base;
 
+  // ring iterations / tasks this CTA has completed so far (the same in every role): barrier phases carry over
+  uint32_t git = 0, n_done = 0;
+  while (task_idx < n_tasks) {
+  const WgradTask t = tasks[task_idx];
+
+  const int halo = t.ntaps_x == 3 ? t.dil : 0;
+  const int xs = kWgChunk + 2 * halo;                 // X slots per half plane per stage
+  const int n_valid = kHW * t.S;                      // slots that can carry a non-zero dZ
+  const int n_chunks = (n_valid + kWgChunk - 1) / kWgChunk;
+  const int row_shift = t.ntaps_x == 3 ? (t.tap_row - 1) * t.dil * t.S : 0;
+  const uint32_t dz_bytes = kHP * kWgChunk * 16;
+  const int total = t.n_inst * n_chunks;
+
   if (warp == 0) {
     // producer: lane = half plane index (lanes 16..31 idle).  The instance table is read 32 entries at a time into
     // registers (one entry per lane) and broadcast with shuffles: a dependent global load per ring stage would put an
     // L2 round trip on the issue path of every stage.
     unsigned long long my_dz = 0, my_x = 0;
     for (int it = 0; it < total; ++it) {
-      const int st = it % kWgStages;
-      const uint32_t ph = (it / kWgStages) & 1;
+      const int st = (git + it) % kWgStages;
+      const uint32_t ph = ((git + it) / kWgStages) & 1;
       const int inst = it / n_chunks, ch = it % n_chunks;
       if (ch == 0 && (inst & 31) == 0) {
         const int mine = inst + lane;
@@ -116,8 +142,8 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
       const uint32_t lbo = (128u >> 4) << 16;
       const uint32_t ring_lo = smem_u32(ring) >> 4;
       for (int it = 0; it < total; ++it) {
-        const int st = it % kWgStages;
-        mbar_wait(smem_u32(&hdr->full[st]), (it / kWgStages) & 1);
+        const int st = (git + it) % kWgStages;
+        mbar_wait(smem_u32(&hdr->full[st]), ((git + it) / kWgStages) & 1);
         tc_fence_after();
         const uint32_t a_lo0 = ring_lo + st * (kWgStageBytes >> 4) + lbo;
         const uint32_t b_lo0 = a_lo0 + (dz_bytes >> 4);
@@ -141,7 +167,7 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
   } else if (warp >= 4) {
     const int q = warp & 3;
     const int cout = q * 32 + lane;
-    mbar_wait(smem_u32(&hdr->tmem_full), 0);
+    mbar_wait(smem_u32(&hdr->tmem_full), n_done & 1);
     tc_fence_after();
     const int kk = t.ksize * t.ksize;
     const float unscale = t.scale ? __ldg(t.scale + 1) : 1.f;
@@ -162,6 +188,17 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks) {
       }
     }
   }
+  git += static_cast<uint32_t>(total);
+  ++n_done;
+  if (!counter) break;
+  if (threadIdx.x == 0) hdr->task_idx = atomicAdd(counter, 1);
+  // the epilogue has read the accumulators before the next task's first MMA overwrites them
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  task_idx = hdr->task_idx;
+  }
+
   tc_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc<512>(tmem_base);
@@ -237,7 +274,9 @@ __global__ void __launch_bounds__(128) bias_grad_kernel(const BiasGradTask* __re
   }
 }
 
-cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, cudaStream_t stream) {
+int reserved_sms();   // exec.cu
+
+cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, int* d_counter, cudaStream_t stream) {
   if (n_tasks <= 0) return cudaSuccess;
   if (impl_simt) {
     wgrad_simt_kernel<<<n_tasks, 256, 0, stream>>>(d_tasks);
@@ -249,7 +288,16 @@ cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, c
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  wgrad_tc_kernel<<<n_tasks, kWgThreads, kWgSmemTotal, stream>>>(d_tasks);
+  if (!d_counter) {
+    wgrad_tc_kernel<<<n_tasks, kWgThreads, kWgSmemTotal, stream>>>(d_tasks, n_tasks, nullptr, 0);
+    return cudaGetLastError();
+  }
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int r = reserved_sms();
+  const int sm_limit = sms - (r < sms * 3 / 4 ? r : sms * 3 / 4);
+  wgrad_tc_kernel<<<n_tasks, kWgThreads, kWgSmemTotal, stream>>>(d_tasks, n_tasks, d_counter, sm_limit);
   return cudaGetLastError();
 }
 

@@ -22,6 +22,7 @@ What is different is only HOW the work is issued:
 * the gradient clamp is fused into the optimizer (``optim.FusedClampAdam``); with more than one process the gradients are
   averaged over NCCL before it (clamp AFTER the reduction, as ``nn.DataParallel`` + ``clamp_`` does in the reference).
 """
+import os
 from typing import Any, Dict, Optional
 
 import torch
@@ -61,7 +62,7 @@ class JointTrainingStep:
     def __init__(self, program_generator, question_reconstructor, nmn, program_prior, alpha: float = 100.0,
                  beta: float = 0.1, gamma: float = 1.0, delta: float = 0.99, objective: str = "ours", lr: float = 1e-6,
                  weight_decay: float = 0.0, clamp: Optional[float] = 5.0, concurrent: bool = True, fused: bool = True,
-                 group=None):
+                 group=None, reserved_sms: Optional[int] = None):
         self.program_generator, self.question_reconstructor = program_generator, question_reconstructor
         self.nmn, self.program_prior = nmn, program_prior
         program_prior.eval()
@@ -74,6 +75,10 @@ class JointTrainingStep:
         self.optimizer = FusedClampAdam(params, lr=lr, weight_decay=weight_decay, clamp=clamp, modules=trained)
         self.concurrent = concurrent
         self.fused = fused
+        # SMs the module executor leaves to the LSTM passes running next to it (pnmn_set_reserved_sms, include/pnmn.h)
+        if reserved_sms is None:
+            reserved_sms = int(os.environ.get("PNMN_JOINT_RESERVE_SMS", "0"))
+        self.reserved_sms = reserved_sms if concurrent else 0
         self._qr_stream: Optional[torch.cuda.Stream] = None
         if concurrent:
             # passes on side streams accumulate into parameters whose AccumulateGrad node lives on another stream: intended
@@ -88,7 +93,10 @@ class JointTrainingStep:
 
     def _streams(self, dev):
         if getattr(self, "_side_streams", None) is None or self._side_streams[0].device != dev:
-            self._side_streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
+            # high priority: a pending CTA of an LSTM step kernel (a chain of ~100 dependent launches per pass) is placed
+            # before pending CTAs of the module network's bulk kernels whenever an SM has room
+            prio = -1 if os.environ.get("PNMN_JOINT_PRIORITY", "1") != "0" else 0
+            self._side_streams = tuple(torch.cuda.Stream(dev, priority=prio) for _ in range(3))
         return self._side_streams
 
     def _mark(self, label: str) -> None:
@@ -277,7 +285,15 @@ class JointTrainingStep:
     def step(self, batch: Dict[str, Any]) -> Dict[str, Any]:
         """``_Trainer.step`` (trainers/_trainer.py:172-196) without the dataloader / tensorboard parts."""
         self.optimizer.zero_grad(set_to_none=True)
-        out = self.do_iteration(batch)
+        if self.reserved_sms:
+            from . import _lib as L
+            prev = L.lib().pnmn_set_reserved_sms(self.reserved_sms)
+            try:
+                out = self.do_iteration(batch)
+            finally:
+                L.lib().pnmn_set_reserved_sms(prev)
+        else:
+            out = self.do_iteration(batch)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             self.allreduce_gradients()
         self.optimizer.step()
