@@ -8,9 +8,12 @@
  *   - all functions returning int: 0 = ok, non-zero = error; pnmn_last_error() has the text
  *   - the product entry points allocate NO device memory: the caller owns every device buffer (sizes are reported by
  *     pnmn_plan_sizes / pnmn_model_packed_floats / pnmn_pg_workspace_bytes).  What the library does own: a small pool of
- *     page-locked HOST staging buffers for task tables (recycled, bounded) and, per device, one non-blocking side stream
- *     with two events (bias gradients run underneath the weight-gradient kernel).  Only the pnmn_debug_* bring-up entry
- *     points allocate (and free) device scratch of their own.
+ *     page-locked HOST staging buffers for task tables (recycled, bounded) and, per device, a handful of non-blocking
+ *     streams and events: one side stream with two events for the module network (bias gradients run underneath the
+ *     weight-gradient kernel); for the seq2seq passes a capture stream, four branch streams with twelve events (independent
+ *     launches of a pass run as parallel branches) and the instantiated CUDA graphs of the passes seen so far (at most 256
+ *     keys; a graph's device-side footprint is the driver's).  Only the pnmn_debug_* bring-up entry points allocate (and
+ *     free) device scratch of their own.
  *   - every launch goes to the device that is current on the calling thread; the python layer makes the tensors'
  *     device current around each call
  *   - no CPU fallback exists: without a CUDA device every compute entry point fails
@@ -31,6 +34,9 @@ typedef struct pnmn_model pnmn_model;
 typedef struct pnmn_plan pnmn_plan;
 
 int pnmn_version(void);
+/* 1 when the library was built with the CUDA-core bring-up twins of the tensor-core kernels (make BRINGUP=1); the release
+ * build has none and the impl_simt / PNMN_PG_SIMT / PNMN_EXEC=levels switches fail with "not supported" */
+int pnmn_has_bringup_kernels(void);
 const char* pnmn_last_error(void);
 
 /* How NeuralModuleNetwork.__init__/forward classify a program token

@@ -18,6 +18,10 @@
 
 namespace pnmn {
 
+// CUDA-core twin of the tensor-core convolution tasks: bring-up / cross-check builds only (make BRINGUP=1).  The release
+// library carries no second implementation of a hot op.
+#ifdef PNMN_BRINGUP
+
 __device__ __forceinline__ int tap_shift(const ConvCfg& c, int tap) {
   return c.ntaps == 9 ? ((tap / 3 - 1) * c.S_in + (tap % 3 - 1)) * c.dil : 0;
 }
@@ -120,5 +124,11 @@ cudaError_t launch_conv_simt(const ConvTask* d_tasks, int n_tasks, const ConvCfg
   conv_simt_kernel<<<n_tasks, 256, 0, stream>>>(d_tasks, d_cfgs);
   return cudaGetLastError();
 }
+#else
+cudaError_t launch_conv_simt(const ConvTask* d_tasks, int n_tasks, const ConvCfg* d_cfgs, cudaStream_t stream) {
+  (void)d_tasks; (void)n_tasks; (void)d_cfgs; (void)stream;
+  return cudaErrorNotSupported;   // built without the bring-up kernels
+}
+#endif
 
 }  // namespace pnmn

@@ -139,6 +139,13 @@ extern "C" long long pnmn_launch_count(int reset) {
 }
 
 extern "C" int pnmn_version(void) { return PNMN_VERSION; }
+extern "C" int pnmn_has_bringup_kernels(void) {
+#ifdef PNMN_BRINGUP
+  return 1;
+#else
+  return 0;
+#endif
+}
 extern "C" const char* pnmn_last_error(void) { return g_err.c_str(); }
 
 extern "C" pnmn_model* pnmn_model_create(int vocab_size, const int32_t* token_kind,
@@ -741,9 +748,15 @@ struct HostTimer {
 long long* g_trace = nullptr;   // optional device buffer for per-task timestamps (pnmn_debug_set_trace)
 int64_t g_trace_cap = 0;        // capacity in tasks
 
+// one persistent executor launch per pass (exec.cu).  Bring-up builds (make BRINGUP=1) can also run the task lists level by
+// level on the CUDA-core twin kernels (PNMN_EXEC=levels); the release library has no second implementation.
 bool exec_persistent() {
+#ifdef PNMN_BRINGUP
   const char* e = std::getenv("PNMN_EXEC");
   return !(e && std::string(e) == "levels");
+#else
+  return true;
+#endif
 }
 
 }  // namespace

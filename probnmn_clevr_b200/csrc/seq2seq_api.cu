@@ -35,9 +35,14 @@ int fail(const std::string& s) {
     if (e_ != cudaSuccess) return fail(std::string(#x) + ": " + cudaGetErrorString(e_)); \
   } while (0)
 
+// CUDA-core twins of the LSTM GEMMs exist in bring-up builds only (make BRINGUP=1, then PNMN_PG_SIMT=1 selects them)
 bool use_simt() {
+#ifdef PNMN_BRINGUP
   static const bool v = std::getenv("PNMN_PG_SIMT") != nullptr;
   return v;
+#else
+  return false;
+#endif
 }
 
 // byte offsets into the caller's workspace (all 256-byte aligned)
@@ -165,6 +170,56 @@ std::map<GraphKey, GraphEntry, KeyLess> g_graphs;
 std::map<int, cudaStream_t> g_capture_streams;
 long long g_graph_launches = 0;
 
+// ---- independent branches of a pass ---------------------------------------------------------------------------------------
+// The tail of the backward pass (five weight-gradient GEMMs, three table gradients, the small embedding / projection GEMMs) and
+// the table / packing prologue of the forward pass are mutually independent launches of 15-60 us that do not fill the device
+// one at a time.  They are issued on library-owned side streams forked from / joined back into the pass's stream with events:
+// captured, that makes parallel branches of the CUDA graph; issued directly (first call, PNMN_PG_NOGRAPH=1) it is plain
+// multi-stream concurrency.  PNMN_PG_NOFORK=1 keeps everything on the caller's stream.
+constexpr int kForkStreams = 4, kForkEvents = 12;
+struct ForkSet {
+  cudaStream_t s[kForkStreams];
+  cudaEvent_t ev[kForkEvents];
+};
+std::map<int, ForkSet*> g_forks;
+ForkSet* fork_set() {
+  static const bool off = std::getenv("PNMN_PG_NOFORK") != nullptr;
+  if (off) return nullptr;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+  std::lock_guard<std::mutex> lock(g_graph_mutex);
+  auto it = g_forks.find(dev);
+  if (it != g_forks.end()) return it->second;
+  ForkSet* f = new ForkSet();
+  bool ok = true;
+  for (int i = 0; i < kForkStreams; ++i) ok = ok && cudaStreamCreateWithFlags(&f->s[i], cudaStreamNonBlocking) == cudaSuccess;
+  for (int i = 0; i < kForkEvents; ++i) ok = ok && cudaEventCreateWithFlags(&f->ev[i], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) { cudaGetLastError(); delete f; f = nullptr; }
+  g_forks[dev] = f;
+  return f;
+}
+// side stream i continues from everything issued on `st` so far / `st` continues after everything issued on side stream i
+struct Forker {
+  ForkSet* f;
+  cudaStream_t st;
+  int next_ev = 0;
+  cudaStream_t fork(int i) {
+    if (!f || next_ev >= kForkEvents) return st;
+    cudaEvent_t e = f->ev[next_ev++];
+    if (cudaEventRecord(e, st) != cudaSuccess || cudaStreamWaitEvent(f->s[i], e, 0) != cudaSuccess) return st;
+    return f->s[i];
+  }
+  int join(cudaStream_t side) {
+    if (side == st) return 0;
+    if (!f || next_ev >= kForkEvents) return 1;
+    cudaEvent_t e = f->ev[next_ev++];
+    if (cudaEventRecord(e, side) != cudaSuccess || cudaStreamWaitEvent(st, e, 0) != cudaSuccess) return 1;
+    return 0;
+  }
+};
+
+std::mutex g_capture_mutex;   // one capture at a time (the capture stream and the fork streams are per device, not per caller)
+
 bool graphs_enabled() {
   static const bool v = std::getenv("PNMN_PG_NOGRAPH") == nullptr;
   return v;
@@ -195,6 +250,7 @@ int run_graphed(GraphKey key, cudaStream_t st, const std::function<int(cudaStrea
     return 0;
   }
   if (e->calls++ == 0) return body(st);   // first call: plain launches (one-time function attributes are set here)
+  std::lock_guard<std::mutex> capture_lock(g_capture_mutex);
   if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
     cudaGetLastError();
     e->failed = true;
@@ -277,6 +333,8 @@ static int pg_forward_impl(const pnmn_pg_desc* m, const float* params, const int
   GraphKey key{ws, params, 0, 0, d.Bp, d.Tq, d.Tp, d.S, d.sampling | (row_teacher ? 2 : 0), d.teacher, need_grad != 0, d.Vs, d.Vt};
   if (simt) key.pass = 2;
   const int rc = run_graphed(key, st, [&](cudaStream_t st) -> int {
+  Forker fk{fork_set(), st};
+  cudaStream_t s_p0 = fk.fork(0), s_pd = fk.fork(1);
 
   // ---- weights -> split fp16 tiles ------------------------------------------------------------------------
   {
@@ -294,7 +352,8 @@ static int pg_forward_impl(const pnmn_pg_desc* m, const float* params, const int
     J.j[5] = job(2 * kSH, kSG, 1, kSH, m->dec_w_ih, 2 * kSH, m->dec_w_hh, kSH, L.pkT_d);
     CUDA_OK(launch_pack_seq(J, need_grad ? 6 : 3, params, packed, st));
   }
-  // ---- input-projection tables: P[v] = Emb[v] . W_ih^T + b_ih + b_hh ----------------------------------------
+  // ---- input-projection tables: P[v] = Emb[v] . W_ih^T + b_ih + b_hh (side branches, next to the weight packing; the
+  // decoder's table is only needed after the encoder) ---------------------------------------------------------------
   {
     SimtGemm g;
     std::memset(&g, 0, sizeof(g));
@@ -302,15 +361,16 @@ static int pg_forward_impl(const pnmn_pg_desc* m, const float* params, const int
     g.A = params + m->src_embed; g.sam = kSH; g.M = d.Vs; g.K = kSH;
     g.B = params + m->enc_w_ih[0]; g.sbn = kSH;
     g.bias0 = params + m->enc_b_ih[0]; g.bias1 = params + m->enc_b_hh[0]; g.C = at<float>(ws, L.P0);
-    CUDA_OK(launch_simt_gemm(g, st));
+    CUDA_OK(launch_simt_gemm(g, s_p0));
     g.A = params + m->tgt_embed; g.M = d.Vt;
     g.B = params + m->dec_w_ih + kSH; g.sbn = 2 * kSH;
     g.bias0 = params + m->dec_b_ih; g.bias1 = params + m->dec_b_hh; g.C = at<float>(ws, L.Pd);
-    CUDA_OK(launch_simt_gemm(g, st));
+    CUDA_OK(launch_simt_gemm(g, s_pd));
     g.M = 1; g.K = 0; g.bias0 = params + m->enc_b_ih[1]; g.bias1 = params + m->enc_b_hh[1]; g.C = at<float>(ws, L.P1);
-    CUDA_OK(launch_simt_gemm(g, st));
+    CUDA_OK(launch_simt_gemm(g, s_p0));
   }
 
+  if (fk.join(s_p0)) return fail("pnmn_pg_forward: stream join failed");
   GemmArgs g;
   std::memset(&g, 0, sizeof(g));
   g.B = d.B; g.chunks_per_src = 4; g.a_K[0] = g.a_K[1] = kSH; g.a_lo[0] = g.a_lo[1] = L.slotf; g.h_op_lo = L.slotf;
@@ -353,6 +413,7 @@ static int pg_forward_impl(const pnmn_pg_desc* m, const float* params, const int
     CUDA_OK(launch_step_gemm_pair(pr, EPI_LSTM, simt, st));
   }
   // ---- decoder: h_0 = encoder output at the last valid position = frozen final layer-1 state, c_0 = 0 -------
+  if (fk.join(s_pd)) return fail("pnmn_pg_forward: stream join failed");
   DecRowArgs r;
   std::memset(&r, 0, sizeof(r));
   r.d = d;
@@ -440,6 +501,7 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
   GraphKey key{ws, params, 0, 1, d.Bp, d.Tq, d.Tp, d.S, 0, d.teacher, 1, d.Vs, d.Vt};
   if (simt) key.pass = 3;
   const int rc = run_graphed(key, st, [&](cudaStream_t st) -> int {
+  Forker fk{fork_set(), st};
   CUDA_OK(launch_seq_loss_scale(gstage, d.B, scale, st));
   CUDA_OK(cudaMemsetAsync(gws, 0, 4 * L.extent, st));
   CUDA_OK(cudaMemsetAsync(at<float>(ws, L.dh), 0, 4 * L.slotf, st));
@@ -475,6 +537,45 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
     CUDA_OK(launch_dec_bwd_row(r, st));
     g.t = t; g.a[0] = at<__half>(ws, L.dgd) + t * L.slotdg;
     CUDA_OK(launch_step_gemm(g, EPI_DGRAD, 2 * kSH / 64, MT, simt, st));
+  }
+  // ---- decoder-side parameter gradients: everything they read is final once the decoder loop is through; they run on a
+  // side branch underneath the encoder's time loop (which occupies 32-64 SMs)
+  WgradSeqArgs wbase;
+  std::memset(&wbase, 0, sizeof(wbase));
+  wbase.dg_lo = L.slotg; wbase.dg_step = L.slotdg; wbase.x_lo = L.slotf; wbase.x_step = L.slotop; wbase.m_tiles = MT; wbase.scale = scale;
+  TableGradArgs tgbase;
+  std::memset(&tgbase, 0, sizeof(tgbase));
+  tgbase.dg_lo = L.slotg; tgbase.dg_step = L.slotdg; tgbase.B = d.B; tgbase.scale = scale;
+  cudaStream_t s_dec = fk.fork(0);
+  {
+    WgradSeqArgs w = wbase;
+    w.dg = at<__half>(ws, L.dgd); w.T = d.S;
+    w.x = at<__half>(ws, L.attop); w.dw = gws + m->dec_w_ih; w.ld = 2 * kSH;
+    CUDA_OK(launch_wgrad_seq(w, simt, s_dec));
+    w.x = at<__half>(ws, L.h1op) + d.Ts * L.slotop; w.dw = gws + m->dec_w_hh; w.ld = kSH;
+    CUDA_OK(launch_wgrad_seq(w, simt, s_dec));
+    TableGradArgs tg = tgbase;
+    tg.dg = at<__half>(ws, L.dgd); tg.T = d.S; tg.V = d.Vt; tg.tok = at<int>(ws, L.inp); tg.tok_step = d.B; tg.tok_stride = 1;
+    tg.dP = at<float>(ws, L.dPd);
+    CUDA_OK(launch_table_grad(tg, s_dec));
+    CUDA_OK(launch_bias_from_table(at<float>(ws, L.dPd), d.Vt, gws + m->dec_b_ih, gws + m->dec_b_hh, s_dec));
+    SimtGemm sg;
+    std::memset(&sg, 0, sizeof(sg));
+    sg.alpha = 1.f; sg.accumulate = 1;
+    // dEmb_tgt[v][e] += sum_g dPd[v][g] * W_dec_ih[g][256 + e]
+    sg.A = at<float>(ws, L.dPd); sg.sam = kSG; sg.sak = 1; sg.M = d.Vt; sg.K = kSG;
+    sg.B = params + m->dec_w_ih + kSH; sg.sbk = 2 * kSH; sg.sbn = 1; sg.N = kSH; sg.C = gws + m->tgt_embed; sg.ldc = kSH;
+    CUDA_OK(launch_simt_gemm(sg, s_dec));
+    // dW_dec_ih[g][256 + e] += sum_v dPd[v][g] * Emb_tgt[v][e]
+    sg.A = at<float>(ws, L.dPd); sg.sam = 1; sg.sak = kSG; sg.M = kSG; sg.K = d.Vt;
+    sg.B = params + m->tgt_embed; sg.sbk = kSH; sg.sbn = 1; sg.N = kSH; sg.C = gws + m->dec_w_ih + kSH; sg.ldc = 2 * kSH;
+    CUDA_OK(launch_simt_gemm(sg, s_dec));
+    // output projection: dW_o[v][j] += sum_{t,b} dlogits[t][b][v] * h_t[b][j];  db_o[v] += sum dlogits
+    sg.A = at<float>(ws, L.dlogits); sg.sam = 1; sg.sak = d.Vt; sg.M = d.Vt; sg.K = d.S * d.Bp;
+    sg.B = at<float>(ws, L.h1f) + (d.Ts + 1) * L.slotf; sg.sbk = kSH; sg.sbn = 1; sg.N = kSH; sg.C = gws + m->out_w; sg.ldc = kSH;
+    CUDA_OK(launch_simt_gemm(sg, s_dec));
+    sg.B = scale + 2; sg.sbk = 0; sg.sbn = 0; sg.N = 1; sg.C = gws + m->out_b; sg.ldc = 1;
+    CUDA_OK(launch_simt_gemm(sg, s_dec));
   }
   r.t = -1; r.do_attn = 1;
   CUDA_OK(launch_dec_bwd_row(r, st));   // attention of step 0 -> d(initial decoder state), d(encoder outputs)
@@ -547,65 +648,41 @@ extern "C" int pnmn_pg_backward(const pnmn_pg_desc* m, const float* params, floa
     CUDA_OK(launch_step_gemm_pair(gp, EPI_DGRAD, simt, st));
   }
 
-  // ---- weight gradients: contraction over batch rows x time on the tensor cores ---------------------------------------
-  WgradSeqArgs w;
-  std::memset(&w, 0, sizeof(w));
-  w.dg_lo = L.slotg; w.dg_step = L.slotdg; w.x_lo = L.slotf; w.x_step = L.slotop; w.m_tiles = MT; w.scale = scale;
-  w.dg = at<__half>(ws, L.dg0); w.T = d.Ts;
-  w.x = at<__half>(ws, L.h0op); w.dw = gws + m->enc_w_hh[0]; w.ld = kSH;
-  CUDA_OK(launch_wgrad_seq(w, simt, st));
-  w.dg = at<__half>(ws, L.dg1);
-  w.x = at<__half>(ws, L.out0op); w.dw = gws + m->enc_w_ih[1];
-  CUDA_OK(launch_wgrad_seq(w, simt, st));
-  w.x = at<__half>(ws, L.h1op); w.dw = gws + m->enc_w_hh[1];
-  CUDA_OK(launch_wgrad_seq(w, simt, st));
-  w.dg = at<__half>(ws, L.dgd); w.T = d.S;
-  w.x = at<__half>(ws, L.attop); w.dw = gws + m->dec_w_ih; w.ld = 2 * kSH;
-  CUDA_OK(launch_wgrad_seq(w, simt, st));
-  w.x = at<__half>(ws, L.h1op) + d.Ts * L.slotop; w.dw = gws + m->dec_w_hh; w.ld = kSH;
-  CUDA_OK(launch_wgrad_seq(w, simt, st));
-
-  // ---- tables -> biases, embeddings, input-projection weights ------------------------------------------------------------
-  TableGradArgs tg;
-  std::memset(&tg, 0, sizeof(tg));
-  tg.dg_lo = L.slotg; tg.dg_step = L.slotdg; tg.B = d.B; tg.scale = scale;
-  tg.dg = at<__half>(ws, L.dg0); tg.T = d.Ts; tg.V = d.Vs; tg.tok = at<int>(ws, L.src); tg.tok_step = 1; tg.tok_stride = d.Ts;
-  tg.dP = at<float>(ws, L.dP0);
-  CUDA_OK(launch_table_grad(tg, st));
-  tg.dg = at<__half>(ws, L.dg1); tg.V = 1; tg.tok = nullptr; tg.dP = at<float>(ws, L.dP1);
-  CUDA_OK(launch_table_grad(tg, st));
-  tg.dg = at<__half>(ws, L.dgd); tg.T = d.S; tg.V = d.Vt; tg.tok = at<int>(ws, L.inp); tg.tok_step = d.B; tg.tok_stride = 1;
-  tg.dP = at<float>(ws, L.dPd);
-  CUDA_OK(launch_table_grad(tg, st));
-  CUDA_OK(launch_bias_from_table(at<float>(ws, L.dP0), d.Vs, gws + m->enc_b_ih[0], gws + m->enc_b_hh[0], st));
-  CUDA_OK(launch_bias_from_table(at<float>(ws, L.dP1), 1, gws + m->enc_b_ih[1], gws + m->enc_b_hh[1], st));
-  CUDA_OK(launch_bias_from_table(at<float>(ws, L.dPd), d.Vt, gws + m->dec_b_ih, gws + m->dec_b_hh, st));
+  // ---- encoder-side parameter gradients: three weight-gradient GEMMs, two table gradients and their small GEMMs, all
+  // independent of each other: main stream + three side branches (the decoder-side ones already run on a fourth branch,
+  // forked right behind the decoder loop, underneath the encoder's time loop)
   {
-    SimtGemm s;
-    std::memset(&s, 0, sizeof(s));
-    s.alpha = 1.f; s.accumulate = 1;
+    cudaStream_t s1 = fk.fork(1), s2 = fk.fork(2), s3 = fk.fork(3);
+    WgradSeqArgs w = wbase;
+    w.dg = at<__half>(ws, L.dg0); w.T = d.Ts;
+    w.x = at<__half>(ws, L.h0op); w.dw = gws + m->enc_w_hh[0]; w.ld = kSH;
+    CUDA_OK(launch_wgrad_seq(w, simt, st));
+    w.dg = at<__half>(ws, L.dg1);
+    w.x = at<__half>(ws, L.out0op); w.dw = gws + m->enc_w_ih[1];
+    CUDA_OK(launch_wgrad_seq(w, simt, s1));
+    w.x = at<__half>(ws, L.h1op); w.dw = gws + m->enc_w_hh[1];
+    CUDA_OK(launch_wgrad_seq(w, simt, s2));
+
+    TableGradArgs tg = tgbase;
+    tg.dg = at<__half>(ws, L.dg0); tg.T = d.Ts; tg.V = d.Vs; tg.tok = at<int>(ws, L.src); tg.tok_step = 1; tg.tok_stride = d.Ts;
+    tg.dP = at<float>(ws, L.dP0);
+    CUDA_OK(launch_table_grad(tg, s3));
+    CUDA_OK(launch_bias_from_table(at<float>(ws, L.dP0), d.Vs, gws + m->enc_b_ih[0], gws + m->enc_b_hh[0], s3));
+    SimtGemm sg;
+    std::memset(&sg, 0, sizeof(sg));
+    sg.alpha = 1.f; sg.accumulate = 1;
     // dEmb_src[v][e] += sum_g dP0[v][g] * W_ih0[g][e]
-    s.A = at<float>(ws, L.dP0); s.sam = kSG; s.sak = 1; s.M = d.Vs; s.K = kSG;
-    s.B = params + m->enc_w_ih[0]; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = gws + m->src_embed; s.ldc = kSH;
-    CUDA_OK(launch_simt_gemm(s, st));
+    sg.A = at<float>(ws, L.dP0); sg.sam = kSG; sg.sak = 1; sg.M = d.Vs; sg.K = kSG;
+    sg.B = params + m->enc_w_ih[0]; sg.sbk = kSH; sg.sbn = 1; sg.N = kSH; sg.C = gws + m->src_embed; sg.ldc = kSH;
+    CUDA_OK(launch_simt_gemm(sg, s3));
     // dW_ih0[g][e] += sum_v dP0[v][g] * Emb_src[v][e]
-    s.A = at<float>(ws, L.dP0); s.sam = 1; s.sak = kSG; s.M = kSG; s.K = d.Vs;
-    s.B = params + m->src_embed; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = gws + m->enc_w_ih[0]; s.ldc = kSH;
-    CUDA_OK(launch_simt_gemm(s, st));
-    // dEmb_tgt[v][e] += sum_g dPd[v][g] * W_dec_ih[g][256 + e]
-    s.A = at<float>(ws, L.dPd); s.sam = kSG; s.sak = 1; s.M = d.Vt; s.K = kSG;
-    s.B = params + m->dec_w_ih + kSH; s.sbk = 2 * kSH; s.sbn = 1; s.N = kSH; s.C = gws + m->tgt_embed; s.ldc = kSH;
-    CUDA_OK(launch_simt_gemm(s, st));
-    // dW_dec_ih[g][256 + e] += sum_v dPd[v][g] * Emb_tgt[v][e]
-    s.A = at<float>(ws, L.dPd); s.sam = 1; s.sak = kSG; s.M = kSG; s.K = d.Vt;
-    s.B = params + m->tgt_embed; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = gws + m->dec_w_ih + kSH; s.ldc = 2 * kSH;
-    CUDA_OK(launch_simt_gemm(s, st));
-    // output projection: dW_o[v][j] += sum_{t,b} dlogits[t][b][v] * h_t[b][j];  db_o[v] += sum dlogits
-    s.A = at<float>(ws, L.dlogits); s.sam = 1; s.sak = d.Vt; s.M = d.Vt; s.K = d.S * d.Bp;
-    s.B = at<float>(ws, L.h1f) + (d.Ts + 1) * L.slotf; s.sbk = kSH; s.sbn = 1; s.N = kSH; s.C = gws + m->out_w; s.ldc = kSH;
-    CUDA_OK(launch_simt_gemm(s, st));
-    s.B = scale + 2; s.sbk = 0; s.sbn = 0; s.N = 1; s.C = gws + m->out_b; s.ldc = 1;
-    CUDA_OK(launch_simt_gemm(s, st));
+    sg.A = at<float>(ws, L.dP0); sg.sam = 1; sg.sak = kSG; sg.M = kSG; sg.K = d.Vs;
+    sg.B = params + m->src_embed; sg.sbk = kSH; sg.sbn = 1; sg.N = kSH; sg.C = gws + m->enc_w_ih[0]; sg.ldc = kSH;
+    CUDA_OK(launch_simt_gemm(sg, s3));
+    tg.dg = at<__half>(ws, L.dg1); tg.V = 1; tg.tok = nullptr; tg.dP = at<float>(ws, L.dP1);
+    CUDA_OK(launch_table_grad(tg, s3));
+    CUDA_OK(launch_bias_from_table(at<float>(ws, L.dP1), 1, gws + m->enc_b_ih[1], gws + m->enc_b_hh[1], s3));
+    if (fk.join(s1) || fk.join(s2) || fk.join(s3) || fk.join(s_dec)) return fail("pnmn_pg_backward: stream join failed");
   }
     return 0;
   });

@@ -155,6 +155,7 @@ __device__ __forceinline__ void epi_lstm_half(const GemmArgs& g, int b, int nt, 
     st8(gd, gi); st8(gd + kSH, gf); st8(gd + 2 * kSH, gg); st8(gd + 3 * kSH, go);
   }
 }
+#ifdef PNMN_BRINGUP
 // whole 64-column tile of one row (CUDA-core twin): acc[n], n = gate*16 + u
 __device__ __forceinline__ void epi_lstm(const GemmArgs& g, int b, int nt, const float* acc) {
 #pragma unroll
@@ -170,6 +171,8 @@ __device__ __forceinline__ void epi_lstm(const GemmArgs& g, int b, int nt, const
   }
 }
 
+#endif
+
 // acc[c], c in [0, 64): column n = nt*64 + c of [dA1 | dA2].  The K range is split over blockIdx.z, so the partial
 // sums are ADDED (fire-and-forget reductions) into buffers whose consumers left them zeroed; masked rows (beyond the
 // sequence length) contribute nothing: carried state stays, per-step outputs stay zero.
@@ -183,10 +186,12 @@ __device__ __forceinline__ void epi_dgrad_cols(const GemmArgs& g, int b, int nt,
   for (int c = 0; c < 32; c += 4)
     if (c < nc) red_add_f32x4(od + c, acc[c] * s, acc[c + 1] * s, acc[c + 2] * s, acc[c + 3] * s);
 }
+#ifdef PNMN_BRINGUP
 __device__ __forceinline__ void epi_dgrad(const GemmArgs& g, int b, int nt, const float* acc) {
   epi_dgrad_cols(g, b, nt, 0, 32, acc);
   epi_dgrad_cols(g, b, nt, 32, 32, acc + 32);
 }
+#endif
 
 // ---- tensor-core kernel ------------------------------------------------------------------------------
 template <int EPI>
@@ -357,6 +362,7 @@ extern "C" int pnmn_debug_pg_trace(long long* out, int cap) {
 namespace pnmn {
 #endif
 
+#ifdef PNMN_BRINGUP
 // ---- CUDA-core twin (bring-up): thread = batch row, 64 fp32 accumulators ------------------------------
 template <int EPI>
 __global__ void __launch_bounds__(128) step_gemm_simt_kernel(const GemmPair pr) {
@@ -383,15 +389,21 @@ __global__ void __launch_bounds__(128) step_gemm_simt_kernel(const GemmPair pr) 
   else epi_dgrad(g, b, nt, acc);
 }
 
+#endif
+
 cudaError_t launch_step_gemm_pair(const GemmPair& p, int epilogue, bool simt, cudaStream_t st) {
   // the data-gradient GEMMs have K = 1024 and few output tiles: split K four ways (partial sums are reduced with atomics)
   const int nx = p.count > 1 && p.n_tiles[1] > p.n_tiles[0] ? p.n_tiles[1] : p.n_tiles[0];
   static const int ksplit = std::getenv("PNMN_PG_DGRAD_SPLIT") ? std::atoi(std::getenv("PNMN_PG_DGRAD_SPLIT")) : 4;
   const dim3 grid(nx, p.m_tiles * p.count, (epilogue == EPI_DGRAD && !simt) ? ksplit : 1);
   if (simt) {
+#ifdef PNMN_BRINGUP
     if (epilogue == EPI_LSTM) step_gemm_simt_kernel<EPI_LSTM><<<grid, 128, 0, st>>>(p);
     else step_gemm_simt_kernel<EPI_DGRAD><<<grid, 128, 0, st>>>(p);
     return cudaGetLastError();
+#else
+    return cudaErrorNotSupported;   // built without the bring-up kernels (make BRINGUP=1)
+#endif
   }
   static bool attr_done = false;
   if (!attr_done) {
@@ -527,6 +539,7 @@ __global__ void __launch_bounds__(kGThreads, 1) wgrad_seq_tc_kernel(const WgradS
   if (warp == 2) tmem_dealloc<128>(tmem_base);
 }
 
+#ifdef PNMN_BRINGUP
 __global__ void __launch_bounds__(256) wgrad_seq_simt_kernel(const WgradSeqArgs a) {
   const int k = blockIdx.x * 16 + (threadIdx.x & 15);
   const int grow = blockIdx.y * 16 + (threadIdx.x >> 4);
@@ -542,11 +555,17 @@ __global__ void __launch_bounds__(256) wgrad_seq_simt_kernel(const WgradSeqArgs 
   atomicAdd(a.dw + static_cast<size_t>(grow) * a.ld + k, acc * a.scale[1]);
 }
 
+#endif
+
 cudaError_t launch_wgrad_seq(const WgradSeqArgs& a, bool simt, cudaStream_t st) {
   if (a.T <= 0) return cudaSuccess;
   if (simt) {
+#ifdef PNMN_BRINGUP
     wgrad_seq_simt_kernel<<<dim3(kSH / 16, kSG / 16), 256, 0, st>>>(a);
     return cudaGetLastError();
+#else
+    return cudaErrorNotSupported;
+#endif
   }
   static bool attr_done = false;
   if (!attr_done) {

@@ -204,6 +204,7 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks, int n_tasks, int* __restric
   if (warp == 2) tmem_dealloc<512>(tmem_base);
 }
 
+#ifdef PNMN_BRINGUP
 // CUDA-core twin with identical task semantics (bring-up / debugging only, PNMN_CONV_IMPL=simt).
 __global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgradTask* __restrict__ tasks) {
   const WgradTask t = tasks[blockIdx.x];
@@ -228,6 +229,8 @@ __global__ void __launch_bounds__(256) wgrad_simt_kernel(const WgradTask* __rest
       red_add_f32(t.dw + (static_cast<size_t>(cout) * t.cin_total + t.cin0 + cin) * kk + tap, acc * unscale);
   }
 }
+
+#endif
 
 // db[n] += sum over instances and slots of dZ[n][slot]      (one CTA per weight tensor)
 struct BiasGradTask {
@@ -279,8 +282,12 @@ int reserved_sms();   // exec.cu
 cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, int* d_counter, cudaStream_t stream) {
   if (n_tasks <= 0) return cudaSuccess;
   if (impl_simt) {
+#ifdef PNMN_BRINGUP
     wgrad_simt_kernel<<<n_tasks, 256, 0, stream>>>(d_tasks);
     return cudaGetLastError();
+#else
+    return cudaErrorNotSupported;   // built without the bring-up kernels (make BRINGUP=1)
+#endif
   }
   static bool attr_done = false;
   if (!attr_done) {
