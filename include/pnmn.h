@@ -146,6 +146,20 @@ int pnmn_relu_pool_fwd_bias(const float* y, const float* bias, float* pooled, vo
 /* dst[2][n] bf16 = (hi, lo) split of src[n] fp32, n % 4 == 0 */
 int pnmn_split2_bf16(const float* src, void* dst, int64_t n, void* stream);
 
+/* Answer head behind the classifier (probnmn/models/nmn.py:245-269) in one launch: per row the predicted answer (first
+ * maximum of the logits; unknown_index for a row whose program is invalid), the loss (cross entropy against answers[b], or
+ * -max log-probability when answers is NULL; the constant 3.33 for an invalid row) and, when correct != NULL, the number of
+ * rows with prediction == answer ADDED to *correct (int64, device).  xin = the plan's per-sample stem-input table inside its
+ * task-table blob (int64 [batch] at byte offset pnmn_plan_stats[15]; < 0 = invalid program); invalid [batch] receives the
+ * 0 / 1 mask (the table itself is recycled with the plan).  The backward entry point writes
+ * d(sum_b grad_loss[b] * loss[b]) / d(logits) [batch][num_answers]; invalid rows get zeros (their loss is a constant: the
+ * in-place writes of nmn.py:258,268). */
+int pnmn_answer_loss_forward(const float* logits, const int64_t* answers, const int64_t* xin, int batch, int num_answers,
+                             int64_t unknown_index, int64_t* predictions, float* loss, uint8_t* invalid, int64_t* correct,
+                             void* stream);
+int pnmn_answer_loss_backward(const float* logits, const int64_t* answers, const uint8_t* invalid, const int64_t* predictions,
+                              const float* grad_loss, int batch, int num_answers, float* grad_logits, void* stream);
+
 /* SM partition for concurrent streams (no counterpart in the reference, which runs its models one after the other:
  * modules/elbo.py:230-275).  The module executor (pnmn_nmn_forward / _backward: exec_kernel, wgrad_tc_kernel) is
  * persistent and would otherwise own every SM for the length of a pass; with n > 0 its CTAs keep off the n highest-numbered

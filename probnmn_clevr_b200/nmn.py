@@ -586,18 +586,16 @@ class NeuralModuleNetwork(nn.Module):
         else:
             with torch.no_grad():
                 final = _ExecutorFn.forward(_NullCtx(), features, None, run, self)
-        # validity mask on the device: read from the plan's task tables (per-sample stem-input offset, < 0 = invalid) rather than
-        # uploaded -- a host -> device copy queued here would wait behind whatever the copy engine is doing (the next batch's
-        # 205 MB of features in a pipelined loop: 3.7 ms) and stall the whole stream.  Read BEFORE the run is closed: closing
-        # hands a pre-uploaded table buffer back to the pool, where a look-ahead compile may overwrite it.
+        # The validity mask is read on the device from the plan's task tables (per-sample stem-input offset, < 0 = invalid)
+        # rather than uploaded -- a host -> device copy queued here would wait behind whatever the copy engine is doing (the
+        # next batch's 205 MB of features in a pipelined loop: 3.7 ms) and stall the whole stream.  The answer head reads it
+        # BEFORE the run is closed: closing hands a pre-uploaded table buffer back to the pool, where a look-ahead compile may
+        # overwrite it.
         xin_off = int(stats[15])
-        invalid = run.blob[xin_off:xin_off + 8 * B].view(torch.int64) < 0
         if self.capture_attention_maps:
             self.last_attention_maps = self._read_attention_maps(plan, ws)
-        if not need_grad:
-            run.close()
 
-        # classifier + loss (nmn.py:241-269); masking done on the device instead of CPU-tensor indexing
+        # classifier (nmn.py:241-244)
         if self.classifier_math == "split":
             answer_logits = self._classifier_split(final)
         elif self.classifier_tf32:
@@ -606,17 +604,14 @@ class NeuralModuleNetwork(nn.Module):
             answer_logits = _MatmulPrecision.apply(self.classifier(final), prev, True)
         else:
             answer_logits = self.classifier(final)
-        answer_logprobs = F.log_softmax(answer_logits, dim=-1)
-        best_logprobs, answer_predictions = torch.max(answer_logprobs, dim=1)
-        answer_predictions = answer_predictions.masked_fill(invalid, self._unknown_answer)
-        if answers is not None:
-            loss = F.cross_entropy(answer_logits, answers, reduction="none")
-        else:
-            loss = -best_logprobs
-        loss = loss.masked_fill(invalid, 3.33)  # constant, carries no gradient (in-place write in the reference)
+        # answer head (nmn.py:245-269): predictions, masking of invalid programs, per-row loss, correct count -- one kernel
+        correct = torch.zeros((), dtype=torch.int64, device=features.device) if answers is not None else None
+        answer_predictions, loss = _AnswerLoss.apply(answer_logits, answers, run.blob, xin_off, self._unknown_answer, correct)
+        if not need_grad:
+            run.close()
         if answers is not None:
             # the correct count stays on the device until a metric is read: no synchronisation inside forward
-            self._answer_accuracy((answer_predictions == answers).sum(), B)
+            self._answer_accuracy(correct, B)
             self._average_invalid_programs(int((valid_host == 0).sum()))
 
         output_dict = {"predictions": answer_predictions, "loss": loss}
@@ -790,6 +785,49 @@ class NeuralModuleNetwork(nn.Module):
 
 class _NullCtx:
     pass
+
+
+class _AnswerLoss(torch.autograd.Function):
+    """(predictions, loss) = answer head over the classifier's logits (``pnmn_answer_loss_forward`` / ``_backward``,
+    csrc/loss.cu; nmn.py:245-269).  ``blob`` / ``xin_off``: the plan's task-table buffer and the byte offset of its per-row
+    validity table; ``correct``: optional device int64 scalar that receives the number of correct predictions."""
+
+    @staticmethod
+    def forward(ctx, logits, answers, blob, xin_off, unknown, correct):
+        logits = logits.contiguous().float()
+        B, A = logits.shape
+        dev = logits.device
+        if answers is not None:
+            answers = answers.detach().to(dev, torch.int64).contiguous()
+        predictions = torch.empty(B, dtype=torch.int64, device=dev)
+        loss = torch.empty(B, dtype=torch.float32, device=dev)
+        invalid = torch.empty(B, dtype=torch.uint8, device=dev)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        L.check(L.lib().pnmn_answer_loss_forward(
+            ctypes.c_void_p(logits.data_ptr()), ctypes.c_void_p(answers.data_ptr()) if answers is not None else None,
+            ctypes.c_void_p(blob.data_ptr() + xin_off), B, A, int(unknown), ctypes.c_void_p(predictions.data_ptr()),
+            ctypes.c_void_p(loss.data_ptr()), ctypes.c_void_p(invalid.data_ptr()),
+            ctypes.c_void_p(correct.data_ptr()) if correct is not None else None, stream), "pnmn_answer_loss_forward")
+        ctx.save_for_backward(logits, predictions, invalid)
+        ctx.answers = answers
+        ctx.mark_non_differentiable(predictions)
+        return predictions, loss
+
+    @staticmethod
+    def backward(ctx, _grad_predictions, grad_loss):
+        logits, predictions, invalid = ctx.saved_tensors
+        answers = ctx.answers
+        B, A = logits.shape
+        grad_loss = grad_loss.contiguous().float()
+        dlogits = torch.empty_like(logits)
+        with torch.cuda.device(logits.device):
+            stream = ctypes.c_void_p(torch.cuda.current_stream(logits.device).cuda_stream)
+            L.check(L.lib().pnmn_answer_loss_backward(
+                ctypes.c_void_p(logits.data_ptr()), ctypes.c_void_p(answers.data_ptr()) if answers is not None else None,
+                ctypes.c_void_p(invalid.data_ptr()), ctypes.c_void_p(predictions.data_ptr()),
+                ctypes.c_void_p(grad_loss.data_ptr()), B, A, ctypes.c_void_p(dlogits.data_ptr()), stream),
+                "pnmn_answer_loss_backward")
+        return dlogits, None, None, None, None, None
 
 
 _COMPILE_POOL = None

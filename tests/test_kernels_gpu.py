@@ -383,3 +383,41 @@ def test_nchw_to_planes_writes_the_fp16_shadow():
     want = tf32.half().view(B, C // 8, 8, 14, 14).permute(0, 1, 3, 4, 2)
     assert torch.equal(shadow[:, :, :14, :14, :], want)
     assert shadow[:, :, 14:].abs().max().item() == 0.0 and shadow[:, :, :, 14:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("with_answers", [True, False], ids=["cross_entropy", "max_logprob"])
+def test_answer_loss_head_matches_torch(with_answers):
+    """pnmn_answer_loss_forward / _backward against the eager ops of the reference's answer head (nmn.py:245-269): first-maximum
+    predictions (ties included), @@UNKNOWN@@ and the constant 3.33 for invalid rows, per-row losses, correct count, and the
+    gradient of a weighted sum of the losses (zero rows for invalid programs)"""
+    from probnmn_clevr_b200.nmn import _AnswerLoss
+    torch.manual_seed(3)
+    B, A, unknown = 77, 28, 1
+    logits = torch.randn(B, A, device="cuda") * 3
+    logits[5, 7] = logits[5, 3] = logits[5].max() + 1.0          # a tie: the lower index wins
+    answers = torch.randint(0, A, (B,), device="cuda")
+    answers[5] = 3
+    xin = torch.arange(B, dtype=torch.int64, device="cuda") * 4096
+    bad = torch.zeros(B, dtype=torch.bool, device="cuda")
+    bad[[2, 5 + 1, 40, 76]] = True
+    xin[bad] = -1
+    blob = torch.cat([torch.zeros(256, dtype=torch.uint8, device="cuda"), xin.view(torch.uint8)])
+    w = torch.rand(B, device="cuda")
+    x = logits.clone().requires_grad_(True)
+    correct = torch.zeros((), dtype=torch.int64, device="cuda") if with_answers else None
+    pred, loss = _AnswerLoss.apply(x, answers if with_answers else None, blob, 256, unknown, correct)
+    (loss * w).sum().backward()
+
+    y = logits.clone().requires_grad_(True)
+    logp = torch.log_softmax(y, dim=-1)
+    best, ref_pred = torch.max(logp, dim=1)
+    ref_pred = ref_pred.masked_fill(bad, unknown)
+    ref_loss = torch.nn.functional.cross_entropy(y, answers, reduction="none") if with_answers else -best
+    ref_loss = ref_loss.masked_fill(bad, 3.33)
+    (ref_loss * w).sum().backward()
+    assert torch.equal(pred, ref_pred) and int(pred[5]) == 3
+    assert torch.allclose(loss, ref_loss, rtol=1e-6, atol=1e-6)
+    assert torch.allclose(x.grad, y.grad, rtol=1e-5, atol=1e-7)
+    assert float(x.grad[bad].abs().max()) == 0.0
+    if with_answers:
+        assert int(correct) == int((ref_pred == answers).sum())
