@@ -122,6 +122,12 @@ typedef struct pnmn_buffers {
  * programs, nmn.py:236).  stream: cudaStream_t. */
 int pnmn_nmn_forward(pnmn_plan* p, const pnmn_buffers* bufs, const float* features, float* final_out,
                      void* stream);
+/* The same with features that are already fp16 [B][C][14][14] -- the operand precision the executor keeps of its input
+ * (tf32 rounding, then a saturating fp16 copy): features produced by pnmn_round_features_f16 (dst[i] = that value of
+ * src[i], n % 4 == 0; e.g. a device-resident feature cache filled once, data/readers.py:63-108) give results identical to
+ * the fp32 call, at half the bytes per step. */
+int pnmn_nmn_forward_f16(pnmn_plan* plan, const pnmn_buffers* bufs, const void* features_f16, float* final_out, void* stream);
+int pnmn_round_features_f16(const float* src, void* dst, int64_t n, void* stream);
 /* Backward of the same: grad_final_out is d(loss)/d(final_out) [B][128][14][14]; gradients of all
  * stem and module parameters are ACCUMULATED into bufs->grads (autograd semantics). */
 int pnmn_nmn_backward(pnmn_plan* p, const pnmn_buffers* bufs, const float* grad_final_out, void* stream);

@@ -56,16 +56,32 @@ cudaError_t launch_pack(const PackTask* d_tasks, int n_tasks, int total_tiles, c
 // weight gradient take the shadow), so only the shadow is written: 103 MB instead of 371 MB per 256 samples.
 // dst_off[b] = float offset of sample b's unit inside `dst`, or < 0 to skip the sample (invalid program: its stem is
 // never executed).  One block per (sample, 8 channels): 16-byte stores, one per pixel slot.
-__global__ void __launch_bounds__(256) nchw_to_planes_kernel(const float* __restrict__ src, float* __restrict__ dst,
+// T = float: features as the reference passes them.  T = __half: features that already went through
+// round_features_f16_kernel (a device-resident feature cache, probnmn_clevr_b200/feed.py): the values are taken as they are,
+// which makes the two paths bit-identical.
+template <class T>
+__global__ void __launch_bounds__(256) nchw_to_planes_kernel(const T* __restrict__ src, float* __restrict__ dst,
                                                              int C, const int64_t* __restrict__ dst_off) {
   const int b = blockIdx.y;
   const int hp = blockIdx.x;  // half plane = 8 channels
   const int64_t off = dst_off[b];
   if (off < 0) return;
-  const float* s = src + (static_cast<size_t>(b) * C + hp * 8) * 196;
+  const T* s = src + (static_cast<size_t>(b) * C + hp * 8) * 196;
   __shared__ float tile[8 * 196];
-  for (int i = threadIdx.x; i < 8 * 196 / 4; i += 256)
-    reinterpret_cast<float4*>(tile)[i] = reinterpret_cast<const float4*>(s)[i];  // (8 * 196 floats, 16-byte aligned)
+  if (sizeof(T) == 4) {
+    for (int i = threadIdx.x; i < 8 * 196 / 4; i += 256)
+      reinterpret_cast<float4*>(tile)[i] = reinterpret_cast<const float4*>(s)[i];  // (8 * 196 floats, 16-byte aligned)
+  } else {
+    for (int i = threadIdx.x; i < 8 * 196 / 8; i += 256) {                          // (8 * 196 halves, 16-byte aligned)
+      const uint4 v = reinterpret_cast<const uint4*>(s)[i];
+      const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(h[e]);
+        tile[8 * i + 2 * e] = f.x; tile[8 * i + 2 * e + 1] = f.y;
+      }
+    }
+  }
   __syncthreads();
   if (threadIdx.x < 196) {
     const int p = threadIdx.x, slot = (p / kHW) * 16 + (p % kHW);
@@ -82,10 +98,31 @@ __global__ void __launch_bounds__(256) nchw_to_planes_kernel(const float* __rest
   }
 }
 
-cudaError_t launch_nchw_to_planes(const float* src, float* dst, int B, int C, const int64_t* dst_off,
+cudaError_t launch_nchw_to_planes(const void* src, int src_is_half, float* dst, int B, int C, const int64_t* dst_off,
                                   cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  nchw_to_planes_kernel<<<dim3(C / 8, B), 256, 0, stream>>>(src, dst, C, dst_off);
+  if (src_is_half) nchw_to_planes_kernel<__half><<<dim3(C / 8, B), 256, 0, stream>>>(static_cast<const __half*>(src), dst, C, dst_off);
+  else nchw_to_planes_kernel<float><<<dim3(C / 8, B), 256, 0, stream>>>(static_cast<const float*>(src), dst, C, dst_off);
+  return cudaGetLastError();
+}
+
+// dst[i] = the fp16 operand value the executor derives from an fp32 feature (tf32 rounding, then the saturating fp16 copy):
+// what a feature cache stores, 2 bytes per value, so that cached and freshly uploaded features give identical results
+__global__ void round_features_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n4) {
+  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const float4 v = reinterpret_cast<const float4*>(src)[i];
+    const __half2 a = __floats2half2_rn(fminf(to_tf32(v.x), 65504.f), fminf(to_tf32(v.y), 65504.f));
+    const __half2 b = __floats2half2_rn(fminf(to_tf32(v.z), 65504.f), fminf(to_tf32(v.w), 65504.f));
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&a); o.y = *reinterpret_cast<const uint32_t*>(&b);
+    reinterpret_cast<uint2*>(dst)[i] = o;
+  }
+}
+cudaError_t launch_round_features_f16(const float* src, void* dst, int64_t n, cudaStream_t stream) {
+  if (n <= 0) return cudaSuccess;
+  const int64_t n4 = n / 4;
+  const int blocks = static_cast<int>(n4 / 256 + 1 < 148 * 16 ? n4 / 256 + 1 : 148 * 16);
+  round_features_f16_kernel<<<blocks, 256, 0, stream>>>(src, static_cast<__half*>(dst), n4);
   return cudaGetLastError();
 }
 

@@ -1602,8 +1602,24 @@ int run_launches(const pnmn_plan& p, const std::vector<LaunchItem>& ls, const ui
 
 }  // namespace
 
+static int nmn_forward_impl(pnmn_plan* pp, const pnmn_buffers* bufs, const void* features, int features_half, float* final_out,
+                            void* stream);
 extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const float* features, float* final_out,
                                 void* stream) {
+  return nmn_forward_impl(pp, bufs, features, 0, final_out, stream);
+}
+extern "C" int pnmn_nmn_forward_f16(pnmn_plan* pp, const pnmn_buffers* bufs, const void* features_f16, float* final_out,
+                                    void* stream) {
+  return nmn_forward_impl(pp, bufs, features_f16, 1, final_out, stream);
+}
+extern "C" int pnmn_round_features_f16(const float* src, void* dst, int64_t n, void* stream) {
+  if (n % 4) return fail("pnmn_round_features_f16: n must be a multiple of 4");
+  CUDA_OK(launch_round_features_f16(src, dst, n, static_cast<cudaStream_t>(stream)));
+  pnmn::count_launches(1);
+  return 0;
+}
+static int nmn_forward_impl(pnmn_plan* pp, const pnmn_buffers* bufs, const void* features, int features_half, float* final_out,
+                            void* stream) {
   HostTimer timer(1);
   pnmn_plan& p = *pp;
   const pnmn_model& m = *p.m;
@@ -1656,7 +1672,7 @@ extern "C" int pnmn_nmn_forward(pnmn_plan* pp, const pnmn_buffers* bufs, const f
   // features -> planes for every valid sample
   {
     ProfScope prof_layout(PK_LAYOUT, st);
-    CUDA_OK(launch_nchw_to_planes(features, bufs->ain, p.B, m.in_ch,
+    CUDA_OK(launch_nchw_to_planes(features, features_half, bufs->ain, p.B, m.in_ch,
                                   reinterpret_cast<const int64_t*>(static_cast<const uint8_t*>(bufs->blob) + p.off_xin), st));
   }
   if (p.persistent) {
@@ -1912,7 +1928,7 @@ extern "C" int pnmn_debug_nchw_to_planes(const float* src, float* dst, int batch
   for (int b = 0; b < batch; ++b) off[b] = b * dst_sample_stride;
   int64_t* d = nullptr;
   if (upload(off.data(), off.size(), &d)) return 1;
-  CUDA_OK(launch_nchw_to_planes(src, dst, batch, channels, d, static_cast<cudaStream_t>(stream)));
+  CUDA_OK(launch_nchw_to_planes(src, 0, dst, batch, channels, d, static_cast<cudaStream_t>(stream)));
   CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   cudaFree(d);
   return 0;

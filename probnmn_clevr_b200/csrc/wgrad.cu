@@ -37,7 +37,7 @@ struct WgSmemHeader {
   uint64_t empty[kWgStages];
   uint64_t tmem_full;
   uint32_t tmem_base;
-  int task_idx;
+  int task_idx[2];   // double-buffered: a slot is rewritten two barriers after its last reader
 };
 
 __device__ __forceinline__ int wg_smid() {
@@ -62,9 +62,9 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks, int n_tasks, int* __restric
 
   int task_idx = static_cast<int>(blockIdx.x);
   if (counter) {
-    if (threadIdx.x == 0) hdr->task_idx = atomicAdd(counter, 1);
+    if (threadIdx.x == 0) hdr->task_idx[0] = atomicAdd(counter, 1);
     __syncthreads();
-    task_idx = hdr->task_idx;
+    task_idx = hdr->task_idx[0];
     if (task_idx >= n_tasks) return;
   }
 
@@ -191,12 +191,13 @@ wgrad_tc_kernel(const WgradTask* __restrict__ tasks, int n_tasks, int* __restric
   git += static_cast<uint32_t>(total);
   ++n_done;
   if (!counter) break;
-  if (threadIdx.x == 0) hdr->task_idx = atomicAdd(counter, 1);
+  // (thread 0 may be a whole -- short -- task ahead of a thread that has not read the previous index yet: two slots)
+  if (threadIdx.x == 0) hdr->task_idx[n_done & 1] = atomicAdd(counter, 1);
   // the epilogue has read the accumulators before the next task's first MMA overwrites them
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  task_idx = hdr->task_idx;
+  task_idx = hdr->task_idx[n_done & 1];
   }
 
   tc_fence_before();

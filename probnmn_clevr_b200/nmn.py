@@ -295,8 +295,9 @@ class _ExecutorFn(torch.autograd.Function):
         B = features.shape[0]
         final = torch.empty(B, 128, 14, 14, dtype=torch.float32, device=features.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(features.device).cuda_stream)
-        L.check(L.lib().pnmn_nmn_forward(run.plan, ctypes.byref(run.bufs), ctypes.c_void_p(features.data_ptr()),
-                                         ctypes.c_void_p(final.data_ptr()), stream), "pnmn_nmn_forward")
+        entry = L.lib().pnmn_nmn_forward_f16 if features.dtype == torch.float16 else L.lib().pnmn_nmn_forward
+        L.check(entry(run.plan, ctypes.byref(run.bufs), ctypes.c_void_p(features.data_ptr()),
+                      ctypes.c_void_p(final.data_ptr()), stream), "pnmn_nmn_forward")
         ctx.run, ctx.model = run, model
         return final
 
@@ -521,7 +522,8 @@ class NeuralModuleNetwork(nn.Module):
     def forward(self, features: torch.Tensor, programs: torch.Tensor, answers: Optional[torch.Tensor] = None):
         r"""
         Same contract as the reference (nmn.py:139-275): ``features`` (B, C, 14, 14) float, ``programs``
-        (B, L) prefix-order token ids, optional ``answers`` (B,).  Returns ``{"predictions": (B,) int64,
+        (B, L) prefix-order token ids, optional ``answers`` (B,).  ``features`` may also be ``torch.float16`` when they come
+        from ``feed.ImageFeatureCache`` (same results, half the bytes).  Returns ``{"predictions": (B,) int64,
         "loss": (B,) float32}`` plus ``"metrics"`` in training mode.  A program the reference could not
         execute never raises: its prediction is ``@@UNKNOWN@@`` and its loss the constant 3.33.
         """
@@ -535,7 +537,9 @@ class NeuralModuleNetwork(nn.Module):
     def _forward(self, features: torch.Tensor, programs: torch.Tensor, answers: Optional[torch.Tensor]):
         lib = L.lib()
         self._ensure_flat()
-        features = features.contiguous().float()
+        # fp16 features are taken as they are: they come from a feature cache that already holds the executor's operand
+        # values (feed.ImageFeatureCache / pnmn_round_features_f16); anything else is read as fp32 like the reference does
+        features = features.contiguous() if features.dtype == torch.float16 else features.contiguous().float()
         B, Lp = programs.shape
         # The program compiler runs on the host: programs that are already host tensors cost no synchronisation
         # (the reference accepts them too, it calls ``programs[n].cpu()``, nmn.py:203); device tensors cost the

@@ -370,3 +370,36 @@ def test_backward_tighter_than_tf32_rounding_noise():
           f"tf32 oracle vs fp32 oracle: global {l2_o:.2e}, worst tensor {worst_o[0]:.2e} ({worst_o[1]})")
     assert l2_c < l2_o, "the CUDA gradient is further from the tf32 oracle than tf32 rounding itself moves the gradient"
     assert l2_c < 3e-2
+
+
+def test_feature_cache_gives_identical_results():
+    """feed.ImageFeatureCache (device-resident fp16 features keyed by image index, readers.py:63-108) + the fp16 entry point:
+    logits, predictions, losses and gradients are IDENTICAL to the ones for the fp32 features of the same images"""
+    from probnmn_clevr_b200.feed import ImageFeatureCache
+    from probnmn_clevr_b200.synthetic import ProgramSampler, make_answers, make_features, make_nmn_state_dict
+    images = make_features(12, 11)                                   # 12 "images"
+    cache = ImageFeatureCache(images.double().numpy(), "cuda:0", split="train", chunk_images=5)
+    assert len(cache) == 12 and cache.split == "train" and cache.features.dtype == torch.float16
+    index = torch.tensor([3, 3, 0, 11, 7, 3, 5, 0, 9, 1])           # questions share images
+    vocab = Vocabulary.clevr()
+    model = NeuralModuleNetwork(vocab)
+    model.load_state_dict(make_nmn_state_dict(vocab, 0))
+    model = model.cuda().train()
+    programs = ProgramSampler(vocab, seed=5).sample(10, 26).cuda()
+    answers = make_answers(10, 5).cuda()
+    outs, grads, logits = [], [], []
+    hook = model.classifier.register_forward_hook(lambda m, i, o: logits.append(o.detach().clone()))
+    for feats in (images[index].cuda(), cache.gather(index)):
+        model.zero_grad()
+        out = model(feats, programs, answers)
+        out["loss"].mean().backward()
+        outs.append(out)
+        grads.append(torch.cat([p.grad.flatten() for p in model.stem.parameters()]).clone())
+    hook.remove()
+    assert torch.equal(logits[0], logits[1])
+    assert torch.equal(outs[0]["predictions"], outs[1]["predictions"]) and torch.equal(outs[0]["loss"], outs[1]["loss"])
+    # (weight gradients are summed with fp32 atomics: equal up to the summation order)
+    assert float((grads[0] - grads[1]).abs().max()) <= 1e-5 * float(grads[0].abs().max())
+    item = cache[3]
+    assert item.dtype.name == "float32" and item.shape == (1024, 14, 14)
+    assert float(torch.as_tensor(item).sub(images[3]).abs().max()) <= 2e-3 * float(images[3].abs().max())
