@@ -560,6 +560,39 @@ def pg_leg(args, ctx, vocab, timed):
                          "questions <= 40 tokens, fwd+bwd (BASELINE.json configs[2])" % (B, half, B - half))}
 
 
+def eval_leg(args, ctx, vocab, timed, pg, nmn):
+    """Validation-shaped pass (evaluators/joint_training_evaluator.py:98-103 under _evaluator.py:67-115): eval mode, no
+    gradients, the generator decodes greedily (teacher-forced on the ground-truth program, as the evaluator calls it) and the
+    module network executes its predictions; metrics accumulate on the device and are read once at the end."""
+    from probnmn_clevr_b200.synthetic import make_joint_batch
+    B, dev = args.batch, ctx["dev"]
+    batches = []
+    for i in range(2):
+        b = make_joint_batch(vocab, B, seed=900 + i)
+        batches.append({k: b[k].to(dev) for k in ("question", "program", "image", "answer")})
+    was_training = pg.training, nmn.training
+    pg.eval(); nmn.eval()
+
+    def eval_step(i):
+        b = batches[i % 2]
+        with torch.no_grad():
+            g = pg(b["question"], b["program"], decoding_strategy="greedy")
+            nmn(b["image"], g["predictions"], b["answer"])
+
+    for i in range(3):
+        eval_step(i)
+    nmn.get_metrics(reset=True); pg.get_metrics(reset=True)
+    steps = max(3, min(args.steps, 10))
+    ms = timed(eval_step, steps)
+    metrics = {**{k: float(v) for k, v in nmn.get_metrics(reset=True).items()},
+               **{k: float(v) for k, v in pg.get_metrics(reset=True).items() if k in ("sequence_accuracy", "perplexity")}}
+    pg.train(was_training[0]); nmn.train(was_training[1])
+    return {"value": ctx["world"] * B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "metrics": metrics,
+            "workload": "joint_training evaluator iteration at batch %d: ProgramGenerator greedy (teacher-forced) -> "
+                        "NeuralModuleNetwork on its predictions, eval mode, no_grad; inputs resident" % B}
+
+
 # ---------------------------------------------------------------------------------------------------------
 # the joint_training iteration (headline)
 # ---------------------------------------------------------------------------------------------------------
@@ -799,7 +832,8 @@ def run_joint(args, ctx):
         sub.steps = max(5, min(args.steps, 30))
         ex = run_executor(sub, ctx, extra=True)
         line["extra"] = {"executor": {k: ex[k] for k in ("metric", "value", "ms_per_step", "steps", "e2e", "roofline", "kernel_ms_per_step", "host_ms_per_step", "plan")},
-                         "pg": pg_leg(args, ctx, vocab, timed)}
+                         "pg": pg_leg(args, ctx, vocab, timed),
+                         "eval": eval_leg(args, ctx, vocab, timed, models["program_generator"], nmn)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_joint_baseline(args, best_of=2)
     return line

@@ -72,6 +72,12 @@ int64_t pnmn_model_packed_floats(const pnmn_model* m);
  * Validity follows the reference's bare-except semantics exactly. */
 pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* programs_host, int batch, int length,
                             int need_grad);
+/* The same with flags.  PNMN_PLAN_INPUT_BY_ROW: the stem input of sample n is unit n of pnmn_buffers.ain whether or not its
+ * program is valid (default: the units of the valid samples are packed) -- for a forward pass whose program-independent part
+ * ran ahead of the programs (pnmn_nmn_prestage). */
+#define PNMN_PLAN_INPUT_BY_ROW 1
+pnmn_plan* pnmn_plan_create_ex(const pnmn_model* m, const int64_t* programs_host, int batch, int length, int need_grad,
+                               int flags);
 void pnmn_plan_destroy(pnmn_plan* p);
 /* Optional: copy the plan's task tables into `device_blob` (PNMN_SZ_BLOB bytes, caller-owned) on `stream` ahead of time;
  * a pnmn_nmn_forward whose pnmn_buffers.blob is the same pointer then skips its own upload (the caller orders the
@@ -126,6 +132,17 @@ int pnmn_nmn_forward(pnmn_plan* p, const pnmn_buffers* bufs, const float* featur
  * (tf32 rounding, then a saturating fp16 copy): features produced by pnmn_round_features_f16 (dst[i] = that value of
  * src[i], n % 4 == 0; e.g. a device-resident feature cache filled once, data/readers.py:63-108) give results identical to
  * the fp32 call, at half the bytes per step. */
+/* Program-independent part of the forward pass, for callers that have a batch's features before its programs (in the
+ * joint-training step the programs are SAMPLED by the generator's forward pass, modules/elbo.py:230-239; the weights and
+ * the features are known when the step starts): packs the current weights into `packed` and lays out the features of all
+ * `batch` rows in `ain` (pnmn_model_ain_floats(m, batch) floats, zero-filled once).  pack_table_dev: device copy of the
+ * model's static pack-task table (pnmn_model_pack_table_bytes bytes, fetched once with pnmn_model_pack_table).  The forward
+ * pass itself is then pnmn_nmn_forward(plan created with PNMN_PLAN_INPUT_BY_ROW, same packed / ain, features = NULL). */
+int64_t pnmn_model_pack_table_bytes(const pnmn_model* m);
+int pnmn_model_pack_table(const pnmn_model* m, void* host_out);
+int64_t pnmn_model_ain_floats(const pnmn_model* m, int batch);
+int pnmn_nmn_prestage(const pnmn_model* m, const void* pack_table_dev, const float* params, void* packed,
+                      const void* features, int features_half, float* ain, int batch, void* stream);
 int pnmn_nmn_forward_f16(pnmn_plan* plan, const pnmn_buffers* bufs, const void* features_f16, float* final_out, void* stream);
 int pnmn_round_features_f16(const float* src, void* dst, int64_t n, void* stream);
 /* Backward of the same: grad_final_out is d(loss)/d(final_out) [B][128][14][14]; gradients of all

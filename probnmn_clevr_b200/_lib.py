@@ -102,6 +102,8 @@ class PriorDesc(Structure):
     ]
 
 
+PLAN_INPUT_BY_ROW = 1   # PNMN_PLAN_INPUT_BY_ROW
+
 EXPORTS = [
     "pnmn_version", "pnmn_last_error", "pnmn_model_create", "pnmn_model_destroy", "pnmn_model_packed_floats",
     "pnmn_plan_create", "pnmn_plan_destroy", "pnmn_plan_upload", "pnmn_plan_valid", "pnmn_plan_sizes", "pnmn_plan_stats",
@@ -109,7 +111,7 @@ EXPORTS = [
     "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt", "pnmn_profile_enable",
     "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times", "pnmn_debug_plan_meta", "pnmn_debug_plan_maps", "pnmn_debug_graph_stats",
     "pnmn_split3_bf16", "pnmn_relu_pool_fwd", "pnmn_relu_pool_bwd", "pnmn_relu_pool_bwd_split", "pnmn_relu_pool_fwd_bias", "pnmn_split2_bf16", "pnmn_launch_count", "pnmn_pg_workspace_bytes", "pnmn_pg_forward", "pnmn_pg_backward", "pnmn_pg_debug_layout", "pnmn_pg_forward_mixed",
-    "pnmn_prior_workspace_bytes", "pnmn_prior_forward", "pnmn_clamp_adam", "pnmn_elbo_glue", "pnmn_set_reserved_sms", "pnmn_has_bringup_kernels", "pnmn_answer_loss_forward", "pnmn_answer_loss_backward", "pnmn_nmn_forward_f16", "pnmn_round_features_f16",
+    "pnmn_prior_workspace_bytes", "pnmn_prior_forward", "pnmn_clamp_adam", "pnmn_elbo_glue", "pnmn_set_reserved_sms", "pnmn_has_bringup_kernels", "pnmn_answer_loss_forward", "pnmn_answer_loss_backward", "pnmn_nmn_forward_f16", "pnmn_round_features_f16", "pnmn_plan_create_ex", "pnmn_model_pack_table_bytes", "pnmn_model_pack_table", "pnmn_model_ain_floats", "pnmn_nmn_prestage",
 ]
 
 
@@ -150,6 +152,14 @@ def lib() -> ctypes.CDLL:
     L.pnmn_plan_sizes.argtypes = [c_void_p, POINTER(c_int64)]
     L.pnmn_plan_stats.argtypes = [c_void_p, POINTER(c_int64)]
     L.pnmn_nmn_forward.argtypes = [c_void_p, POINTER(Buffers), c_void_p, c_void_p, c_void_p]
+    L.pnmn_plan_create_ex.restype = c_void_p
+    L.pnmn_plan_create_ex.argtypes = [c_void_p, POINTER(c_int64), c_int, c_int, c_int, c_int]
+    L.pnmn_model_pack_table_bytes.restype = c_int64
+    L.pnmn_model_pack_table_bytes.argtypes = [c_void_p]
+    L.pnmn_model_pack_table.argtypes = [c_void_p, c_void_p]
+    L.pnmn_model_ain_floats.restype = c_int64
+    L.pnmn_model_ain_floats.argtypes = [c_void_p, c_int]
+    L.pnmn_nmn_prestage.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p]
     L.pnmn_nmn_forward_f16.argtypes = [c_void_p, POINTER(Buffers), c_void_p, c_void_p, c_void_p]
     L.pnmn_round_features_f16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     L.pnmn_nmn_backward.argtypes = [c_void_p, POINTER(Buffers), c_void_p, c_void_p]

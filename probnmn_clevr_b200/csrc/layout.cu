@@ -59,12 +59,14 @@ cudaError_t launch_pack(const PackTask* d_tasks, int n_tasks, int total_tiles, c
 // T = float: features as the reference passes them.  T = __half: features that already went through
 // round_features_f16_kernel (a device-resident feature cache, probnmn_clevr_b200/feed.py): the values are taken as they are,
 // which makes the two paths bit-identical.
+// dst_off == nullptr: sample b goes to unit b (off = guard_floats + b * unit_floats), whatever its program (pnmn_nmn_prestage).
 template <class T>
 __global__ void __launch_bounds__(256) nchw_to_planes_kernel(const T* __restrict__ src, float* __restrict__ dst,
-                                                             int C, const int64_t* __restrict__ dst_off) {
+                                                             int C, const int64_t* __restrict__ dst_off, int64_t guard_floats,
+                                                             int64_t unit_floats) {
   const int b = blockIdx.y;
   const int hp = blockIdx.x;  // half plane = 8 channels
-  const int64_t off = dst_off[b];
+  const int64_t off = dst_off ? dst_off[b] : guard_floats + b * unit_floats;
   if (off < 0) return;
   const T* s = src + (static_cast<size_t>(b) * C + hp * 8) * 196;
   __shared__ float tile[8 * 196];
@@ -99,10 +101,12 @@ __global__ void __launch_bounds__(256) nchw_to_planes_kernel(const T* __restrict
 }
 
 cudaError_t launch_nchw_to_planes(const void* src, int src_is_half, float* dst, int B, int C, const int64_t* dst_off,
-                                  cudaStream_t stream) {
+                                  int64_t guard_floats, int64_t unit_floats, cudaStream_t stream) {
   if (B <= 0) return cudaSuccess;
-  if (src_is_half) nchw_to_planes_kernel<__half><<<dim3(C / 8, B), 256, 0, stream>>>(static_cast<const __half*>(src), dst, C, dst_off);
-  else nchw_to_planes_kernel<float><<<dim3(C / 8, B), 256, 0, stream>>>(static_cast<const float*>(src), dst, C, dst_off);
+  if (src_is_half)
+    nchw_to_planes_kernel<__half><<<dim3(C / 8, B), 256, 0, stream>>>(static_cast<const __half*>(src), dst, C, dst_off, guard_floats, unit_floats);
+  else
+    nchw_to_planes_kernel<float><<<dim3(C / 8, B), 256, 0, stream>>>(static_cast<const float*>(src), dst, C, dst_off, guard_floats, unit_floats);
   return cudaGetLastError();
 }
 

@@ -28,7 +28,7 @@ struct BiasGradTaskH {  // mirrors BiasGradTask in wgrad.cu
 cudaError_t launch_pack(const PackTask* d_tasks, int n_tasks, int total_tiles, const float* params,
                         void* packed, cudaStream_t stream);
 cudaError_t launch_nchw_to_planes(const void* src, int src_is_half, float* dst, int B, int C, const int64_t* dst_off,
-                                  cudaStream_t stream);
+                                  int64_t guard_floats, int64_t unit_floats, cudaStream_t stream);
 cudaError_t launch_round_features_f16(const float* src, void* dst, int64_t n, cudaStream_t stream);
 cudaError_t launch_conv_simt(const ConvTask* d_tasks, int n_tasks, const ConvCfg* d_cfgs, cudaStream_t stream);
 // d_counter: zeroed device int (tasks are then pulled by one persistent CTA per SM), or nullptr (one CTA per task)

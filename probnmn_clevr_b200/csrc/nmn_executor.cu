@@ -556,6 +556,7 @@ struct pnmn_plan {
   std::vector<int> xin_unit;  // per sample, -1 if the stem is skipped (invalid program)
   std::vector<int32_t> map_trace;  // {sample, module call index, token, map unit} of every 1-channel module output
   bool persistent = true;     // one persistent executor launch per pass (exec.cu) vs one launch per level
+  bool input_by_row = false;  // stem-input unit of sample n is n (pnmn_nmn_prestage), not the running count of valid samples
   void* uploaded_to = nullptr;  // device buffer that already holds this plan's task tables (pnmn_plan_upload)
   std::vector<TaskRec> ftask, btask;
   std::vector<TaskMeta> fmeta, bmeta;
@@ -761,13 +762,14 @@ bool exec_persistent() {
 
 }  // namespace
 
-static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs, int B, int L, int need_grad,
+static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs, int B, int L, int need_grad, int flags,
                                    bool allow_strands, bool* overflow) {
   HostTimer timer(0);
   { std::lock_guard<std::mutex> lock(g_host_ms_mutex); g_host_ms[3] += 1; }
   auto* plan = new pnmn_plan();
   pnmn_plan& p = *plan;
   p.m = m; p.B = B; p.L = L; p.need_grad = need_grad != 0;
+  p.input_by_row = (flags & PNMN_PLAN_INPUT_BY_ROW) != 0;
   p.valid.assign(B, 0);
   p.xin_unit.assign(B, -1);
   Builder bd(p);
@@ -863,7 +865,7 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
     p.stats[0]++;
 
     // ---------------- stem (nmn.py:67-72,183) ----------------
-    const int xin = n_ain++;
+    const int xin = p.input_by_row ? n : n_ain++;   // by row: the features were laid out before the programs were known
     p.xin_unit[n] = xin;
     y1s_unit[n] = bd.alloc16();
     feat_unit[n] = bd.alloc16();
@@ -1436,12 +1438,35 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
   return plan;
 }
 
-extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* programs, int B, int L, int need_grad) {
+extern "C" pnmn_plan* pnmn_plan_create_ex(const pnmn_model* m, const int64_t* programs, int B, int L, int need_grad, int flags) {
   bool overflow = false;
-  pnmn_plan* p = plan_create_impl(m, programs, B, L, need_grad, true, &overflow);
+  pnmn_plan* p = plan_create_impl(m, programs, B, L, need_grad, flags, true, &overflow);
   // joins of concurrent strands can exceed a task's dependency slots on exotic batches: compile those with one chain per sample
-  if (!p && overflow) p = plan_create_impl(m, programs, B, L, need_grad, false, &overflow);
+  if (!p && overflow) p = plan_create_impl(m, programs, B, L, need_grad, flags, false, &overflow);
   return p;
+}
+extern "C" pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* programs, int B, int L, int need_grad) {
+  return pnmn_plan_create_ex(m, programs, B, L, need_grad, 0);
+}
+
+// ---- program-independent part of the forward pass ---------------------------------------------------------------------
+extern "C" int64_t pnmn_model_pack_table_bytes(const pnmn_model* m) { return static_cast<int64_t>(m->pack.size() * sizeof(PackTask)); }
+extern "C" int pnmn_model_pack_table(const pnmn_model* m, void* host_out) {
+  std::memcpy(host_out, m->pack.data(), m->pack.size() * sizeof(PackTask));
+  return 0;
+}
+extern "C" int64_t pnmn_model_ain_floats(const pnmn_model* m, int batch) {
+  return (2 * kGuard + std::max<int64_t>(batch, 1) * (static_cast<int64_t>(m->in_ch / 4) * 256 * 16 * 3 / 2)) / 4;
+}
+extern "C" int pnmn_nmn_prestage(const pnmn_model* m, const void* pack_table_dev, const float* params, void* packed,
+                                 const void* features, int features_half, float* ain, int batch, void* stream) {
+  if (!m || !pack_table_dev || !params || !packed || !features || !ain || batch < 1) return fail("pnmn_nmn_prestage: bad arguments");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  CUDA_OK(launch_pack(static_cast<const PackTask*>(pack_table_dev), static_cast<int>(m->pack.size()), m->total_tiles, params, packed, st));
+  const int64_t unit = static_cast<int64_t>(m->in_ch / 4) * 256 * 16 * 3 / 2;
+  CUDA_OK(launch_nchw_to_planes(features, features_half, ain, batch, m->in_ch, nullptr, kGuard / 4, unit / 4, st));
+  pnmn::count_launches(2);
+  return 0;
 }
 
 // Optional early upload of a plan's task tables (input pipelines): copies the page-locked tables into `device_blob`
@@ -1484,6 +1509,7 @@ extern "C" int pnmn_plan_sizes(const pnmn_plan* p, int64_t* s) {
   {
     int64_t n_valid = 0;
     for (uint8_t v : p->valid) n_valid += v;
+    if (p->input_by_row) n_valid = p->B;
     s[PNMN_SZ_AIN] = (2 * kGuard + std::max<int64_t>(n_valid, 1) * (static_cast<int64_t>(p->m->in_ch / 4) * 256 * 16 * 3 / 2)) / 4;
   }
   return 0;
@@ -1662,18 +1688,20 @@ static int nmn_forward_impl(pnmn_plan* pp, const pnmn_buffers* bufs, const void*
   }
   CUDA_OK(cudaMemcpyAsync(bufs->blob, p.host_blob.data(), static_cast<size_t>(fwd_bytes), cudaMemcpyHostToDevice, st));
   }
+  if (!features && !p.input_by_row)
+    return fail("pnmn_nmn_forward: features == NULL needs a plan created with PNMN_PLAN_INPUT_BY_ROW (after pnmn_nmn_prestage)");
   // pack weights (fp16 MMA tile order); the pack-task table is part of the plan's blob (uploaded above)
-  {
+  if (features) {
     ProfScope prof(PK_PACK, st);
     CUDA_OK(launch_pack(reinterpret_cast<const PackTask*>(static_cast<const uint8_t*>(bufs->blob) + p.off_pack),
                         static_cast<int>(m.pack.size()), m.total_tiles, bufs->params, bufs->packed, st));
   }
   fill_ones_map_kernel<<<1, 256, 0, st>>>(bufs->maps);
   // features -> planes for every valid sample
-  {
+  if (features) {
     ProfScope prof_layout(PK_LAYOUT, st);
     CUDA_OK(launch_nchw_to_planes(features, features_half, bufs->ain, p.B, m.in_ch,
-                                  reinterpret_cast<const int64_t*>(static_cast<const uint8_t*>(bufs->blob) + p.off_xin), st));
+                                  reinterpret_cast<const int64_t*>(static_cast<const uint8_t*>(bufs->blob) + p.off_xin), 0, 0, st));
   }
   if (p.persistent) {
     uint8_t* blob = static_cast<uint8_t*>(bufs->blob);
@@ -1928,7 +1956,7 @@ extern "C" int pnmn_debug_nchw_to_planes(const float* src, float* dst, int batch
   for (int b = 0; b < batch; ++b) off[b] = b * dst_sample_stride;
   int64_t* d = nullptr;
   if (upload(off.data(), off.size(), &d)) return 1;
-  CUDA_OK(launch_nchw_to_planes(src, 0, dst, batch, channels, d, static_cast<cudaStream_t>(stream)));
+  CUDA_OK(launch_nchw_to_planes(src, 0, dst, batch, channels, d, 0, 0, static_cast<cudaStream_t>(stream)));
   CUDA_OK(cudaStreamSynchronize(static_cast<cudaStream_t>(stream)));
   cudaFree(d);
   return 0;

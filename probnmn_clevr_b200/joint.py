@@ -79,6 +79,7 @@ class JointTrainingStep:
         if reserved_sms is None:
             reserved_sms = int(os.environ.get("PNMN_JOINT_RESERVE_SMS", "0"))
         self.reserved_sms = reserved_sms if concurrent else 0
+        self.prestage = os.environ.get("PNMN_JOINT_PRESTAGE", "1") != "0"
         self._qr_stream: Optional[torch.cuda.Stream] = None
         if concurrent:
             # passes on side streams accumulate into parameters whose AccumulateGrad node lives on another stream: intended
@@ -93,9 +94,10 @@ class JointTrainingStep:
 
     def _streams(self, dev):
         if getattr(self, "_side_streams", None) is None or self._side_streams[0].device != dev:
-            # high priority: a pending CTA of an LSTM step kernel (a chain of ~100 dependent launches per pass) is placed
-            # before pending CTAs of the module network's bulk kernels whenever an SM has room
-            prio = -1 if os.environ.get("PNMN_JOINT_PRIORITY", "1") != "0" else 0
+            # (PNMN_JOINT_PRIORITY=1 gives the LSTM passes' streams high priority -- a pending CTA of a step kernel is then
+            # placed before pending CTAs of the module network's bulk kernels.  Measured: the passes finish earlier, the
+            # module network later, the step 0.2-0.3 ms slower: 6.87 vs 7.08 ms.  Default off.)
+            prio = -1 if os.environ.get("PNMN_JOINT_PRIORITY", "0") == "1" else 0
             self._side_streams = tuple(torch.cuda.Stream(dev, priority=prio) for _ in range(3))
         return self._side_streams
 
@@ -201,6 +203,10 @@ class JointTrainingStep:
         s_pg, s_qr, s_prior = streams
         if self.concurrent:
             s_pg.wait_stream(main)
+        # the module network's weights and features are known now, its programs only after the generator's forward pass:
+        # weight packing and feature layout run here, on the caller's stream, next to that pass
+        if self.prestage and nu > 0:
+            self.nmn.prestage(img)
         with torch.cuda.stream(s_pg):
             pg = pg_m.forward_mixed(q_all, targets, teacher_rows, free_steps=free)       # elbo.py:230-233 + trainer :164-168
             sampled = pg["predictions"][:nu, :free].contiguous()
@@ -296,6 +302,7 @@ class JointTrainingStep:
             out = self.do_iteration(batch)
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             self.allreduce_gradients()
+            self._mark("allreduce_end")
         self.optimizer.step()
         self._mark("optimizer_end")
         self.iteration += 1

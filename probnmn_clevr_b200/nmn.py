@@ -296,7 +296,8 @@ class _ExecutorFn(torch.autograd.Function):
         final = torch.empty(B, 128, 14, 14, dtype=torch.float32, device=features.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(features.device).cuda_stream)
         entry = L.lib().pnmn_nmn_forward_f16 if features.dtype == torch.float16 else L.lib().pnmn_nmn_forward
-        L.check(entry(run.plan, ctypes.byref(run.bufs), ctypes.c_void_p(features.data_ptr()),
+        # (features = NULL: NeuralModuleNetwork.prestage already packed the weights and laid the features out)
+        L.check(entry(run.plan, ctypes.byref(run.bufs), None if getattr(run, "staged", False) else ctypes.c_void_p(features.data_ptr()),
                       ctypes.c_void_p(final.data_ptr()), stream), "pnmn_nmn_forward")
         ctx.run, ctx.model = run, model
         return final
@@ -386,6 +387,8 @@ class NeuralModuleNetwork(nn.Module):
         self._grad_overlap = None
         self._upload_stream = None
         self._precompiled: list = []  # pending (programs, need_grad, future of a plan) entries, see precompile()
+        self._prestaged = None        # (features tensor, workspace) of a prestage() call the next forward may use
+        self._pack_table: Optional[torch.Tensor] = None
         # parity tests: keep every 1-channel module output (attention map) of the last forward, see _read_attention_maps
         self.capture_attention_maps = False
         self.last_attention_maps = None
@@ -553,10 +556,16 @@ class NeuralModuleNetwork(nn.Module):
         else:
             programs_host = programs.detach().to("cpu", torch.int64).contiguous()
         need_grad = torch.is_grad_enabled() and any(p.requires_grad for p in self._exec_params)
-        pre = self._take_precompiled(programs_host, need_grad)
+        # a prestage() of exactly these features (same memory, same weights buffer): skip the pack / layout kernels
+        staged, self._prestaged = self._prestaged, None
+        if staged is not None and not (staged[0].data_ptr() == features.data_ptr() and staged[0].shape == features.shape
+                                       and staged[0].dtype == features.dtype and staged[2] == self._flat.data_ptr()):
+            _POOL.release(staged[1])
+            staged = None
+        pre = self._take_precompiled(programs_host, need_grad) if staged is None else None
         pre_blob = pre_event = None
         if pre is None:
-            plan = self._compile(programs_host, need_grad, None)
+            plan = self._compile(programs_host, need_grad, None, by_row=staged is not None)
         else:
             plan, pre_blob, pre_event = pre
         valid_host = torch.empty(B, dtype=torch.uint8)
@@ -567,7 +576,7 @@ class NeuralModuleNetwork(nn.Module):
         lib.pnmn_plan_stats(plan, stats)
         self.last_plan_stats = list(stats)
 
-        ws = _POOL.acquire(features.device)
+        ws = staged[1] if staged is not None else _POOL.acquire(features.device)
         ws.ensure(sizes)
         if self._packed is None or self._packed.device != features.device:
             self._packed = torch.empty(lib.pnmn_model_packed_floats(self._model_handle), dtype=torch.float32,
@@ -583,6 +592,7 @@ class NeuralModuleNetwork(nn.Module):
                          blob.data_ptr(), self._packed.data_ptr(), self._flat.data_ptr(), None,
                          ws.t["ain"].data_ptr(), ws.scratch.data_ptr())
         run = _Run(plan, ws, bufs, self._gflat_box)
+        run.staged = staged is not None
         run.blob = blob
         run.pool_blob = pre_blob  # goes back to the pool when the run is closed (after the backward pass)
         if need_grad:
@@ -645,15 +655,16 @@ class NeuralModuleNetwork(nn.Module):
         return [(int(rec[i, 0]), int(rec[i, 1]), int(rec[i, 2]), maps[i]) for i in range(n)]
 
     # ---- program compiler -------------------------------------------------------------------------------------------
-    def _compile(self, programs_host: torch.Tensor, need_grad: bool, device):
+    def _compile(self, programs_host: torch.Tensor, need_grad: bool, device, by_row: bool = False):
         lib = L.lib()
         B, Lp = programs_host.shape
         ptr = ctypes.cast(programs_host.data_ptr(), ctypes.POINTER(ctypes.c_int64))
+        flags = L.PLAN_INPUT_BY_ROW if by_row else 0
         if device is not None:  # helper thread: the pinned staging buffers and their events belong to this device
             with torch.cuda.device(device):
-                plan = lib.pnmn_plan_create(self._model_handle, ptr, B, Lp, 1 if need_grad else 0)
+                plan = lib.pnmn_plan_create_ex(self._model_handle, ptr, B, Lp, 1 if need_grad else 0, flags)
         else:
-            plan = lib.pnmn_plan_create(self._model_handle, ptr, B, Lp, 1 if need_grad else 0)
+            plan = lib.pnmn_plan_create_ex(self._model_handle, ptr, B, Lp, 1 if need_grad else 0, flags)
         if not plan:
             raise RuntimeError("pnmn_plan_create failed: " + lib.pnmn_last_error().decode())
         return plan
@@ -679,6 +690,47 @@ class NeuralModuleNetwork(nn.Module):
         except Exception:
             lib.pnmn_plan_destroy(plan)
             raise
+
+    def prestage(self, features: torch.Tensor) -> None:
+        """Optional: run the part of ``forward`` that does not depend on the programs -- packing the weights into MMA tiles
+        and laying out the image features -- NOW, on the current stream.  In the joint-training step the programs are
+        sampled by the program generator's forward pass (modules/elbo.py:230-239) while the features and the weights are
+        known from the start: the ``forward`` that follows (same ``features`` tensor) then goes straight from the program
+        compiler to the executor.  The reference has no counterpart; results are identical with or without it."""
+        if not features.is_cuda:
+            raise RuntimeError("NeuralModuleNetwork (B200) needs CUDA tensors; there is no CPU fallback")
+        self._drop_prestaged()
+        with torch.cuda.device(features.device):
+            self._ensure_flat()
+            lib = L.lib()
+            dev = features.device
+            feats = features.contiguous() if features.dtype == torch.float16 else features.contiguous().float()
+            B = feats.shape[0]
+            if B == 0:
+                return
+            if self._packed is None or self._packed.device != dev:
+                self._packed = torch.empty(lib.pnmn_model_packed_floats(self._model_handle), dtype=torch.float32, device=dev)
+            if self._pack_table is None or self._pack_table.device != dev:
+                host = torch.empty(max(int(lib.pnmn_model_pack_table_bytes(self._model_handle)), 1), dtype=torch.uint8)
+                lib.pnmn_model_pack_table(self._model_handle, ctypes.c_void_p(host.data_ptr()))
+                self._pack_table = host.to(dev)
+            ws = _POOL.acquire(dev)
+            need = int(lib.pnmn_model_ain_floats(self._model_handle, B))
+            cur = ws.t.get("ain")
+            if cur is None or cur.numel() < need:
+                ws.t["ain"] = None
+                ws.t["ain"] = torch.zeros(int(need * 1.25) + 1024, dtype=torch.float32, device=dev)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            L.check(lib.pnmn_nmn_prestage(self._model_handle, ctypes.c_void_p(self._pack_table.data_ptr()),
+                                          ctypes.c_void_p(self._flat.data_ptr()), ctypes.c_void_p(self._packed.data_ptr()),
+                                          ctypes.c_void_p(feats.data_ptr()), 1 if feats.dtype == torch.float16 else 0,
+                                          ctypes.c_void_p(ws.t["ain"].data_ptr()), B, stream), "pnmn_nmn_prestage")
+            self._prestaged = (feats, ws, self._flat.data_ptr())
+
+    def _drop_prestaged(self) -> None:
+        if self._prestaged is not None:
+            _POOL.release(self._prestaged[1])
+            self._prestaged = None
 
     def precompile(self, programs: torch.Tensor, need_grad: Optional[bool] = None) -> None:
         """Optional look-ahead for input pipelines: start compiling ``programs`` (host tensor, (B, L) token ids) into an

@@ -237,6 +237,7 @@ class Seq2SeqBase(nn.Module):
         # a NeuralModuleNetwork that is handed this tensor (modules/elbo.py:233-239, joint_training_evaluator.py:98-103)
         # compiles the programs on the host and would otherwise synchronise the whole compute stream to read them
         self.handover_predictions = True
+        self._pending_metrics: list = []
         self._metrics = {"loss_sum": 0.0, "loss_n": 0, "seq_correct": 0, "seq_n": 0, "recall_sum": 0.0, "recall_n": 0,
                          "bleu_match": Counter(), "bleu_total": Counter(), "bleu_pred_len": 0, "bleu_ref_len": 0}
 
@@ -385,7 +386,9 @@ class Seq2SeqBase(nn.Module):
         if self.return_logits:
             output_dict["logits"], output_dict["raw_predictions"] = logits, raw
         if teacher and not self.training and teacher_rows is None:
-            self._record_metrics(predictions, target, loss)   # seq2seq_base.py:258-274
+            # seq2seq_base.py:258-274.  The statistics are host-side (n-gram counts); the batch is only queued here and
+            # processed when a metric is read, so that a validation loop does not synchronise once per batch
+            self._pending_metrics.append((predictions.detach(), target, loss.detach()))
         return output_dict
 
     # ---- metrics (validation only; host side) -------------------------------------------------------------------------
@@ -425,6 +428,9 @@ class Seq2SeqBase(nn.Module):
         """``{"BLEU", "perplexity", "sequence_accuracy", "word_error_rate"}`` in evaluation mode, ``{}`` while training
         (seq2seq_base.py:343-375)."""
         out: Dict[str, float] = {}
+        pending, self._pending_metrics = self._pending_metrics, []
+        for predictions, target, loss in pending:
+            self._record_metrics(predictions, target, loss)
         if not self.training:
             m = self._metrics
             if m["bleu_pred_len"] == 0 or any(m["bleu_match"][n] == 0 for n in range(1, 5)):

@@ -403,3 +403,35 @@ def test_feature_cache_gives_identical_results():
     item = cache[3]
     assert item.dtype.name == "float32" and item.shape == (1024, 14, 14)
     assert float(torch.as_tensor(item).sub(images[3]).abs().max()) <= 2e-3 * float(images[3].abs().max())
+
+
+def test_prestage_changes_nothing():
+    """NeuralModuleNetwork.prestage (weights packed and features laid out before the programs are known, stem inputs indexed
+    by row) followed by forward gives the same logits / predictions / losses / gradients as forward alone, invalid programs
+    included; a prestage for other features is ignored"""
+    vocab = Vocabulary.clevr()
+    model = NeuralModuleNetwork(vocab)
+    model.load_state_dict(make_nmn_state_dict(vocab, 0))
+    model = model.cuda().train()
+    sampler = ProgramSampler(vocab, seed=9)
+    programs = torch.cat([sampler.sample(5, 26), sampler.garbage(2, 26), sampler.sample(6, 26)]).cuda()
+    feats, answers = make_features(13, 9).cuda(), make_answers(13, 9).cuda()
+    other = make_features(13, 10).cuda()
+    results = []
+    for mode in ("plain", "prestaged", "stale"):
+        logits = []
+        hook = model.classifier.register_forward_hook(lambda m, i, o: logits.append(o.detach().clone()))
+        model.zero_grad()
+        if mode == "prestaged":
+            model.prestage(feats)
+        elif mode == "stale":
+            model.prestage(other)           # not the features of the forward that follows: must be dropped
+        out = model(feats, programs, answers)
+        out["loss"].mean().backward()
+        hook.remove()
+        g = torch.cat([p.grad.flatten() for p in model.stem.parameters()]).clone()
+        results.append((logits[0], out["predictions"].clone(), out["loss"].detach().clone(), g))
+    for r in results[1:]:
+        assert torch.equal(r[0], results[0][0]) and torch.equal(r[1], results[0][1]) and torch.equal(r[2], results[0][2])
+        assert float((r[3] - results[0][3]).abs().max()) <= 1e-5 * float(results[0][3].abs().max())
+    assert int((results[0][1] == 28).sum()) == 2
