@@ -7,7 +7,7 @@ out = open(f"profiles/{tag}_summary.md", "w")
 def P(*a):
     print(*a, file=out)
 
-P(f"# {tag}: ncu / trace summaries (B200, bench workload: batch 256, programs <= 40 tokens, one fwd+bwd step)\n")
+P(f"# {tag}: ncu / trace summaries (B200, bench workload: one joint-training step at batch 256 -- see scripts/gpu_profile_r2.sh)\n")
 # ---- launch list ----------------------------------------------------------------------------------------
 src = f"gpurun_out/launches_{tag}.csv"
 if os.path.exists(src):
@@ -52,7 +52,7 @@ for rep in sorted(f for f in os.listdir("gpurun_out") if f.endswith(f"_{tag}.ncu
             if k in hdr:
                 P(f"| {k} | {r[hdr.index(k)]} | {units[hdr.index(k)]} |")
         P("")
-for f in ("trace.txt", "profile_step.txt"):
+for f in (f"trace_{tag}.txt", f"profile_step_{tag}.txt", f"joint_timeline_{tag}.txt", f"pg_step_trace_{tag}.txt"):
     if os.path.exists(f"gpurun_out/{f}"):
         P(f"\n## {f}\n\n```")
         P(open(f"gpurun_out/{f}").read()[-9000:])
