@@ -136,13 +136,15 @@ def allreduce_gradients(models: Iterable[torch.nn.Module], group: Optional[dist.
     with unequal shard sizes reproduce the single-process global-batch mean exactly (SURVEY.md §8e caveat)."""
     world = dist.get_world_size(group)
     buckets = gradient_buckets(models)
+    avg = dist.get_backend(group) == "nccl"   # NCCL averages inside the collective; gloo only sums
     handles = []
     for b in buckets:
         if weight != 1.0:
             b.mul_(weight)
-        handles.append(dist.all_reduce(b, op=dist.ReduceOp.SUM, group=group, async_op=True))
+        handles.append(dist.all_reduce(b, op=dist.ReduceOp.AVG if avg else dist.ReduceOp.SUM, group=group, async_op=True))
     for h in handles:
         h.wait()
-    for b in buckets:
-        b.div_(world)
+    if not avg:
+        for b in buckets:
+            b.div_(world)
     return len(buckets)

@@ -88,6 +88,7 @@ class JointTrainingStep:
             except AttributeError:
                 pass
         self.group = group
+        self._reduced: set = set()
         self._sup_stream: Optional[torch.cuda.Stream] = None
         self.iteration = -1
         self.trace = None   # diagnostics: a list collects (label, CUDA event) marks of one step (scripts/joint_timeline.py)
@@ -228,6 +229,7 @@ class JointTrainingStep:
             self._mark("qr_fwd_end(qr)")
             torch.autograd.backward([qr["loss"]], [coef_qr])
             self._mark("qr_bwd_end(qr)")
+            self._reduce_early([qr_m])
         with torch.cuda.stream(s_prior):
             prior = self.program_prior(sampled)                                        # elbo.py:256
             self._mark("prior_fwd_end(prior)")
@@ -254,6 +256,12 @@ class JointTrainingStep:
             self._mark("pg_bwd_end(pg)")
         torch.autograd.backward([nmn["loss"]], [coef_nmn])
         self._mark("nmn_bwd_end")
+        # gradient averaging, issued in the order in which the gradients become final (NCCL runs a communicator's collectives
+        # in issue order): reconstructor (above), module network -- its classifier gradients are already travelling, started
+        # by hooks inside its backward pass --, generator last (its backward pass is the last to finish)
+        self._reduce_early([self.nmn])
+        with torch.cuda.stream(s_pg):
+            self._reduce_early([pg_m])
         pg_sup, qr_sup = pg_loss[nu:].mean(), qr_loss[nu:].mean()
         loss_objective = self.gamma * stats[4] - stats[2] + self.alpha * (pg_sup + qr_sup)
         if self.concurrent:
@@ -283,10 +291,32 @@ class JointTrainingStep:
         qr = self.question_reconstructor(programs, questions, decoding_strategy="sampling")
         return pg["loss"].mean(), qr["loss"].mean()
 
-    def allreduce_gradients(self) -> None:
+    def _distributed(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _reduce_early(self, models) -> None:
+        """Data-parallel runs: average the gradients of ``models`` NOW, on the current stream (which waits for the
+        collective; the host does not), instead of after the whole backward phase.  Remembered so that ``step`` does not
+        reduce them again."""
+        if not self._distributed():
+            return
         from .dist import allreduce_gradients
-        self.nmn.allreduce_gradients(group=self.group)
-        allreduce_gradients([self.program_generator, self.question_reconstructor], group=self.group)
+        for m in models:
+            if m is self.nmn:
+                self.nmn.allreduce_gradients(group=self.group)
+            else:
+                allreduce_gradients([m], group=self.group)
+            self._reduced.add(id(m))
+
+    def allreduce_gradients(self) -> None:
+        """Average whatever ``do_iteration`` has not averaged already (everything, on the unfused path)."""
+        from .dist import allreduce_gradients
+        if id(self.nmn) not in self._reduced:
+            self.nmn.allreduce_gradients(group=self.group)
+        rest = [m for m in (self.program_generator, self.question_reconstructor) if id(m) not in self._reduced]
+        if rest:
+            allreduce_gradients(rest, group=self.group)
+        self._reduced.clear()
 
     def step(self, batch: Dict[str, Any]) -> Dict[str, Any]:
         """``_Trainer.step`` (trainers/_trainer.py:172-196) without the dataloader / tensorboard parts."""
@@ -300,7 +330,7 @@ class JointTrainingStep:
                 L.lib().pnmn_set_reserved_sms(prev)
         else:
             out = self.do_iteration(batch)
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        if self._distributed():
             self.allreduce_gradients()
             self._mark("allreduce_end")
         self.optimizer.step()
