@@ -79,6 +79,10 @@ pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* programs_host, i
 pnmn_plan* pnmn_plan_create_ex(const pnmn_model* m, const int64_t* programs_host, int batch, int length, int need_grad,
                                int flags);
 void pnmn_plan_destroy(pnmn_plan* p);
+/* Cap the executor's persistent grid for this plan (0 = two CTAs per SM, the default).  A batch may be compiled as several
+ * independent plans -- on several host threads, which is what shortens the time between knowing the programs and launching
+ * the executor -- whose passes then run side by side on different streams and share the device's CTA slots. */
+int pnmn_plan_set_exec_ctas(pnmn_plan* p, int max_ctas);
 /* Optional: copy the plan's task tables into `device_blob` (PNMN_SZ_BLOB bytes, caller-owned) on `stream` ahead of time;
  * a pnmn_nmn_forward whose pnmn_buffers.blob is the same pointer then skips its own upload (the caller orders the
  * forward's stream after this one).  Lets an input pipeline keep every host -> device copy off the compute stream. */

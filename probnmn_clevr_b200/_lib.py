@@ -111,7 +111,7 @@ EXPORTS = [
     "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt", "pnmn_profile_enable",
     "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times", "pnmn_debug_plan_meta", "pnmn_debug_plan_maps", "pnmn_debug_graph_stats",
     "pnmn_split3_bf16", "pnmn_relu_pool_fwd", "pnmn_relu_pool_bwd", "pnmn_relu_pool_bwd_split", "pnmn_relu_pool_fwd_bias", "pnmn_split2_bf16", "pnmn_launch_count", "pnmn_pg_workspace_bytes", "pnmn_pg_forward", "pnmn_pg_backward", "pnmn_pg_debug_layout", "pnmn_pg_forward_mixed",
-    "pnmn_prior_workspace_bytes", "pnmn_prior_forward", "pnmn_clamp_adam", "pnmn_elbo_glue", "pnmn_set_reserved_sms", "pnmn_has_bringup_kernels", "pnmn_answer_loss_forward", "pnmn_answer_loss_backward", "pnmn_nmn_forward_f16", "pnmn_round_features_f16", "pnmn_plan_create_ex", "pnmn_model_pack_table_bytes", "pnmn_model_pack_table", "pnmn_model_ain_floats", "pnmn_nmn_prestage",
+    "pnmn_prior_workspace_bytes", "pnmn_prior_forward", "pnmn_clamp_adam", "pnmn_elbo_glue", "pnmn_set_reserved_sms", "pnmn_has_bringup_kernels", "pnmn_answer_loss_forward", "pnmn_answer_loss_backward", "pnmn_nmn_forward_f16", "pnmn_round_features_f16", "pnmn_plan_create_ex", "pnmn_plan_set_exec_ctas", "pnmn_model_pack_table_bytes", "pnmn_model_pack_table", "pnmn_model_ain_floats", "pnmn_nmn_prestage",
 ]
 
 
@@ -154,6 +154,7 @@ def lib() -> ctypes.CDLL:
     L.pnmn_nmn_forward.argtypes = [c_void_p, POINTER(Buffers), c_void_p, c_void_p, c_void_p]
     L.pnmn_plan_create_ex.restype = c_void_p
     L.pnmn_plan_create_ex.argtypes = [c_void_p, POINTER(c_int64), c_int, c_int, c_int, c_int]
+    L.pnmn_plan_set_exec_ctas.argtypes = [c_void_p, c_int]
     L.pnmn_model_pack_table_bytes.restype = c_int64
     L.pnmn_model_pack_table_bytes.argtypes = [c_void_p]
     L.pnmn_model_pack_table.argtypes = [c_void_p, c_void_p]

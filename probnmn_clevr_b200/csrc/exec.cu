@@ -648,7 +648,7 @@ void set_reserved_sms(int n) { g_reserved_sms = n < 0 ? 0 : n; }
 int reserved_sms() { return g_reserved_sms; }
 
 cudaError_t launch_exec(const uint8_t* d_tasks, const TaskMeta* d_meta, int n_tasks, const ConvCfg* d_cfgs,
-                        int* d_counter, int* d_done, long long* d_trace, cudaStream_t stream) {
+                        int* d_counter, int* d_done, long long* d_trace, int max_ctas, cudaStream_t stream) {
   if (n_tasks <= 0) return cudaSuccess;
   static bool attr_done = false;
   if (!attr_done) {
@@ -666,6 +666,7 @@ cudaError_t launch_exec(const uint8_t* d_tasks, const TaskMeta* d_meta, int n_ta
   static const int cap = std::getenv("PNMN_EXEC_CTAS") ? std::atoi(std::getenv("PNMN_EXEC_CTAS")) : 0;
   int grid = n_tasks < kExCtasPerSM * sms ? n_tasks : kExCtasPerSM * sms;
   if (cap > 0 && grid > cap) grid = cap;
+  if (max_ctas > 0 && grid > max_ctas) grid = max_ctas;
   static const int dbg = std::getenv("PNMN_EXEC_DBG") ? std::atoi(std::getenv("PNMN_EXEC_DBG")) : 0;  // timing experiments only
   // at least a quarter of the SMs always stay with the executor
   const int sm_limit = sms - (g_reserved_sms < sms * 3 / 4 ? g_reserved_sms : sms * 3 / 4);

@@ -19,7 +19,8 @@ struct TaskMeta {
 };
 static_assert(sizeof(TaskMeta) == 48, "TaskMeta must stay 48 bytes");
 
+// max_ctas > 0 caps the persistent grid (several task lists running side by side share the SMs' CTA slots)
 cudaError_t launch_exec(const uint8_t* d_tasks, const TaskMeta* d_meta, int n_tasks, const ConvCfg* d_cfgs,
-                        int* d_counter, int* d_done, long long* d_trace, cudaStream_t stream);
+                        int* d_counter, int* d_done, long long* d_trace, int max_ctas, cudaStream_t stream);
 
 }  // namespace pnmn

@@ -556,6 +556,7 @@ struct pnmn_plan {
   std::vector<int> xin_unit;  // per sample, -1 if the stem is skipped (invalid program)
   std::vector<int32_t> map_trace;  // {sample, module call index, token, map unit} of every 1-channel module output
   bool persistent = true;     // one persistent executor launch per pass (exec.cu) vs one launch per level
+  int exec_ctas = 0;          // > 0: cap of the executor's persistent grid for this plan (pnmn_plan_set_exec_ctas)
   bool input_by_row = false;  // stem-input unit of sample n is n (pnmn_nmn_prestage), not the running count of valid samples
   void* uploaded_to = nullptr;  // device buffer that already holds this plan's task tables (pnmn_plan_upload)
   std::vector<TaskRec> ftask, btask;
@@ -1487,6 +1488,12 @@ extern "C" int pnmn_plan_upload(pnmn_plan* pp, void* device_blob, void* stream) 
   return 0;
 }
 
+extern "C" int pnmn_plan_set_exec_ctas(pnmn_plan* p, int max_ctas) {
+  if (!p) return fail("pnmn_plan_set_exec_ctas: NULL plan");
+  p->exec_ctas = max_ctas > 0 ? max_ctas : 0;
+  return 0;
+}
+
 extern "C" void pnmn_plan_destroy(pnmn_plan* p) {
   if (p) pin_release(p->pin);
   delete p;
@@ -1710,7 +1717,7 @@ static int nmn_forward_impl(pnmn_plan* pp, const pnmn_buffers* bufs, const void*
     CUDA_OK(launch_exec(blob + p.off_ftask, reinterpret_cast<const TaskMeta*>(blob + p.off_fmeta),
                         static_cast<int>(p.ftask.size()), reinterpret_cast<const ConvCfg*>(blob + p.off_cfg),
                         reinterpret_cast<int*>(blob + p.off_fsync), reinterpret_cast<int*>(blob + p.off_fsync) + 1,
-                        (g_trace && static_cast<int64_t>(p.ftask.size()) <= g_trace_cap) ? g_trace : nullptr, st));
+                        (g_trace && static_cast<int64_t>(p.ftask.size()) <= g_trace_cap) ? g_trace : nullptr, p.exec_ctas, st));
     return 0;
   }
   return run_launches(p, p.flaunch, static_cast<const uint8_t*>(bufs->blob), false, st);
@@ -1766,7 +1773,7 @@ extern "C" int pnmn_nmn_backward(pnmn_plan* pp, const pnmn_buffers* bufs, const 
                           static_cast<int>(p.btask.size()), reinterpret_cast<const ConvCfg*>(blob + p.off_cfg),
                           reinterpret_cast<int*>(blob + p.off_bsync), reinterpret_cast<int*>(blob + p.off_bsync) + 1,
                           (g_trace && static_cast<int64_t>(p.ftask.size() + p.btask.size()) <= g_trace_cap)
-                              ? g_trace + kTraceW * p.ftask.size() : nullptr, st));
+                              ? g_trace + kTraceW * p.ftask.size() : nullptr, p.exec_ctas, st));
     }
   }
   return run_launches(p, p.blaunch, static_cast<const uint8_t*>(bufs->blob), true, st);
@@ -1919,7 +1926,7 @@ extern "C" int pnmn_debug_launch_conv(const void* tasks_host, int n_tasks, const
     if (upload(metas.data(), metas.size(), &dm)) return 1;
     CUDA_OK(cudaMalloc(&sync, 4 * (n_tasks + 1)));
     CUDA_OK(cudaMemsetAsync(sync, 0, 4 * (n_tasks + 1), st));
-    CUDA_OK(launch_exec(reinterpret_cast<const uint8_t*>(dt), dm, n_tasks, dc, sync, sync + 1, nullptr, st));
+    CUDA_OK(launch_exec(reinterpret_cast<const uint8_t*>(dt), dm, n_tasks, dc, sync, sync + 1, nullptr, 0, st));
     CUDA_OK(cudaStreamSynchronize(st));
     cudaFree(dm); cudaFree(sync);
   }

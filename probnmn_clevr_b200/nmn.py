@@ -261,8 +261,12 @@ _BLOBS = _BlobPool()
 class _Run:
     """One forward's plan + workspace; released after backward (or when dropped)."""
 
-    def __init__(self, plan, ws, bufs, gflat_box=None):
+    def __init__(self, plan, ws, bufs, gflat_box=None, lo=0, hi=0, stream=None, staged=False, extra_ws=None):
         self.plan, self.ws, self.bufs, self.gflat_box = plan, ws, bufs, gflat_box
+        self.lo, self.hi, self.stream, self.staged = lo, hi, stream, staged   # rows of the batch, side stream, prestaged inputs
+        self.extra_ws = extra_ws    # workspace that holds the prestaged inputs of ALL chunks (released with this run)
+        self.blob = None
+        self.xin_off = 0
 
     def close(self):
         if self.plan is not None:
@@ -274,6 +278,9 @@ class _Run:
         if self.ws is not None:
             _POOL.release(self.ws)
             self.ws = None
+        if self.extra_ws is not None:
+            _POOL.release(self.extra_ws)
+            self.extra_ws = None
 
     def __del__(self):
         try:
@@ -291,32 +298,66 @@ class _ExecutorFn(torch.autograd.Function):
     that makes autograd call ``backward``."""
 
     @staticmethod
-    def forward(ctx, features, anchor, run, model):
+    def forward(ctx, features, anchor, runs, model):
         B = features.shape[0]
-        final = torch.empty(B, 128, 14, 14, dtype=torch.float32, device=features.device)
-        stream = ctypes.c_void_p(torch.cuda.current_stream(features.device).cuda_stream)
+        dev = features.device
+        final = torch.empty(B, 128, 14, 14, dtype=torch.float32, device=dev)
         entry = L.lib().pnmn_nmn_forward_f16 if features.dtype == torch.float16 else L.lib().pnmn_nmn_forward
-        # (features = NULL: NeuralModuleNetwork.prestage already packed the weights and laid the features out)
-        L.check(entry(run.plan, ctypes.byref(run.bufs), None if getattr(run, "staged", False) else ctypes.c_void_p(features.data_ptr()),
-                      ctypes.c_void_p(final.data_ptr()), stream), "pnmn_nmn_forward")
-        ctx.run, ctx.model = run, model
+        row_bytes = features[0].numel() * features.element_size() if B else 0
+        current = torch.cuda.current_stream(dev)
+        fork = None
+        for run in runs:
+            # a batch compiled as several plans (NeuralModuleNetwork.compile_chunks): every plan runs on its own stream, from
+            # its own rows of `features` into its own rows of `final`
+            st = current
+            if run.stream is not None:
+                if fork is None:
+                    fork = torch.cuda.Event()
+                    fork.record(current)
+                run.stream.wait_event(fork)
+                st = run.stream
+            # (features = NULL: NeuralModuleNetwork.prestage already packed the weights and laid the features out)
+            fptr = None if run.staged else ctypes.c_void_p(features.data_ptr() + run.lo * row_bytes)
+            L.check(entry(run.plan, ctypes.byref(run.bufs), fptr, ctypes.c_void_p(final.data_ptr() + run.lo * 128 * 196 * 4),
+                          ctypes.c_void_p(st.cuda_stream)), "pnmn_nmn_forward")
+            if run.stream is not None:
+                done = torch.cuda.Event()
+                done.record(run.stream)
+                current.wait_event(done)
+        ctx.runs, ctx.model = runs, model
         return final
 
     @staticmethod
     def backward(ctx, grad_final):
-        run, model = ctx.run, ctx.model
-        if run.plan is None:
+        runs, model = ctx.runs, ctx.model
+        if any(run.plan is None for run in runs):
             raise RuntimeError("NeuralModuleNetwork backward called twice (the plan was already released)")
         grad_final = grad_final.contiguous()
+        dev = grad_final.device
         target, finish = model._attach_grads()
-        run.bufs.grads = target.data_ptr()
-        with torch.cuda.device(grad_final.device):  # (the autograd thread's current device is not necessarily the tensors')
-            stream = ctypes.c_void_p(torch.cuda.current_stream(grad_final.device).cuda_stream)
-            L.check(L.lib().pnmn_nmn_backward(run.plan, ctypes.byref(run.bufs), ctypes.c_void_p(grad_final.data_ptr()),
-                                              stream), "pnmn_nmn_backward")
+        with torch.cuda.device(dev):  # (the autograd thread's current device is not necessarily the tensors')
+            current = torch.cuda.current_stream(dev)
+            fork = None
+            for run in runs:
+                run.bufs.grads = target.data_ptr()
+                st = current
+                if run.stream is not None:
+                    if fork is None:
+                        fork = torch.cuda.Event()
+                        fork.record(current)
+                    run.stream.wait_event(fork)
+                    st = run.stream
+                L.check(L.lib().pnmn_nmn_backward(run.plan, ctypes.byref(run.bufs),
+                                                  ctypes.c_void_p(grad_final.data_ptr() + run.lo * 128 * 196 * 4),
+                                                  ctypes.c_void_p(st.cuda_stream)), "pnmn_nmn_backward")
+                if run.stream is not None:
+                    done = torch.cuda.Event()
+                    done.record(run.stream)
+                    current.wait_event(done)
         if finish is not None:
             finish()
-        run.close()
+        for run in runs:
+            run.close()
         return None, None, None, None
 
 
@@ -388,6 +429,9 @@ class NeuralModuleNetwork(nn.Module):
         self._upload_stream = None
         self._precompiled: list = []  # pending (programs, need_grad, future of a plan) entries, see precompile()
         self._prestaged = None        # (features tensor, workspace) of a prestage() call the next forward may use
+        # > 1: a batch's programs are compiled as this many independent plans on as many host threads (_chunked_runs)
+        self.compile_chunks = int(os.environ.get("PNMN_COMPILE_CHUNKS", "1"))
+        self._chunk_streams = None
         self._pack_table: Optional[torch.Tensor] = None
         # parity tests: keep every 1-channel module output (attention map) of the last forward, see _read_attention_maps
         self.capture_attention_maps = False
@@ -562,20 +606,79 @@ class NeuralModuleNetwork(nn.Module):
                                        and staged[0].dtype == features.dtype and staged[2] == self._flat.data_ptr()):
             _POOL.release(staged[1])
             staged = None
+        k = self.compile_chunks
+        chunked = (k > 1 and B >= 16 * k and not self.capture_attention_maps
+                   and not (staged is None and self._precompiled))
+        if chunked:
+            runs, valid_host, stats = self._chunked_runs(features, programs_host, need_grad, staged, k)
+        else:
+            runs, valid_host, stats = self._single_run(features, programs_host, need_grad, staged)
+        self.last_plan_stats = stats
+        if need_grad:
+            final = _ExecutorFn.apply(features, self._anchor, runs, self)
+        else:
+            with torch.no_grad():
+                final = _ExecutorFn.forward(_NullCtx(), features, None, runs, self)
+        # The validity mask is read on the device from the plans' task tables (per-sample stem-input offset, < 0 = invalid)
+        # rather than uploaded -- a host -> device copy queued here would wait behind whatever the copy engine is doing (the
+        # next batch's 205 MB of features in a pipelined loop: 3.7 ms) and stall the whole stream.  The answer head reads it
+        # BEFORE a run is closed: closing hands a pre-uploaded table buffer back to the pool, where a look-ahead compile may
+        # overwrite it.
+        if self.capture_attention_maps:
+            self.last_attention_maps = self._read_attention_maps(runs[0].plan, runs[0].ws)
+
+        # classifier (nmn.py:241-244)
+        if self.classifier_math == "split":
+            answer_logits = self._classifier_split(final)
+        elif self.classifier_tf32:
+            prev = torch.backends.cuda.matmul.allow_tf32
+            final = _MatmulPrecision.apply(final, True, prev)
+            answer_logits = _MatmulPrecision.apply(self.classifier(final), prev, True)
+        else:
+            answer_logits = self.classifier(final)
+        # answer head (nmn.py:245-269): predictions, masking of invalid programs, per-row loss, correct count -- one kernel
+        correct = torch.zeros((), dtype=torch.int64, device=features.device) if answers is not None else None
+        tables = [(run.blob, run.xin_off, run.lo, run.hi) for run in runs]
+        answer_predictions, loss = _AnswerLoss.apply(answer_logits, answers, tables, self._unknown_answer, correct)
+        if not need_grad:
+            for run in runs:
+                run.close()
+        if answers is not None:
+            # the correct count stays on the device until a metric is read: no synchronisation inside forward
+            self._answer_accuracy(correct, B)
+            self._average_invalid_programs(int((valid_host == 0).sum()))
+
+        output_dict = {"predictions": answer_predictions, "loss": loss}
+        if self.training:
+            # same values as the reference's ``self.get_metrics(reset=True)`` (nmn.py:274): the accumulators are
+            # snapshotted and reset NOW, the numbers are produced when the dict is first read
+            acc_state = self._answer_accuracy.snapshot(reset=True)
+            invalid_now = self._average_invalid_programs.get_metric(reset=True)
+            output_dict["metrics"] = _LazyMetrics({"answer_accuracy": lambda: _Accuracy.value(acc_state),
+                                                   "average_invalid": lambda: invalid_now})
+        return output_dict
+
+    def _plan_info(self, plan, rows):
+        lib = L.lib()
+        valid = torch.empty(rows, dtype=torch.uint8)
+        lib.pnmn_plan_valid(plan, ctypes.cast(valid.data_ptr(), ctypes.POINTER(ctypes.c_uint8)))
+        sizes = (ctypes.c_int64 * L.SZ_COUNT)()
+        lib.pnmn_plan_sizes(plan, sizes)
+        stats = (ctypes.c_int64 * 16)()
+        lib.pnmn_plan_stats(plan, stats)
+        return valid, sizes, list(stats)
+
+    def _single_run(self, features, programs_host, need_grad, staged):
+        """One plan for the whole batch, on the caller's stream."""
+        lib = L.lib()
+        B = programs_host.shape[0]
         pre = self._take_precompiled(programs_host, need_grad) if staged is None else None
         pre_blob = pre_event = None
         if pre is None:
             plan = self._compile(programs_host, need_grad, None, by_row=staged is not None)
         else:
             plan, pre_blob, pre_event = pre
-        valid_host = torch.empty(B, dtype=torch.uint8)
-        lib.pnmn_plan_valid(plan, ctypes.cast(valid_host.data_ptr(), ctypes.POINTER(ctypes.c_uint8)))
-        sizes = (ctypes.c_int64 * L.SZ_COUNT)()
-        lib.pnmn_plan_sizes(plan, sizes)
-        stats = (ctypes.c_int64 * 16)()
-        lib.pnmn_plan_stats(plan, stats)
-        self.last_plan_stats = list(stats)
-
+        valid_host, sizes, stats = self._plan_info(plan, B)
         ws = staged[1] if staged is not None else _POOL.acquire(features.device)
         ws.ensure(sizes)
         if self._packed is None or self._packed.device != features.device:
@@ -591,52 +694,57 @@ class NeuralModuleNetwork(nn.Module):
                          ws.t["maps"].data_ptr(), ws.t["dmaps"].data_ptr(), ws.t["idx"].data_ptr(),
                          blob.data_ptr(), self._packed.data_ptr(), self._flat.data_ptr(), None,
                          ws.t["ain"].data_ptr(), ws.scratch.data_ptr())
-        run = _Run(plan, ws, bufs, self._gflat_box)
-        run.staged = staged is not None
+        run = _Run(plan, ws, bufs, self._gflat_box, lo=0, hi=B, staged=staged is not None)
         run.blob = blob
+        run.xin_off = int(stats[15])
         run.pool_blob = pre_blob  # goes back to the pool when the run is closed (after the backward pass)
-        if need_grad:
-            final = _ExecutorFn.apply(features, self._anchor, run, self)
-        else:
-            with torch.no_grad():
-                final = _ExecutorFn.forward(_NullCtx(), features, None, run, self)
-        # The validity mask is read on the device from the plan's task tables (per-sample stem-input offset, < 0 = invalid)
-        # rather than uploaded -- a host -> device copy queued here would wait behind whatever the copy engine is doing (the
-        # next batch's 205 MB of features in a pipelined loop: 3.7 ms) and stall the whole stream.  The answer head reads it
-        # BEFORE the run is closed: closing hands a pre-uploaded table buffer back to the pool, where a look-ahead compile may
-        # overwrite it.
-        xin_off = int(stats[15])
-        if self.capture_attention_maps:
-            self.last_attention_maps = self._read_attention_maps(plan, ws)
+        return [run], valid_host, stats
 
-        # classifier (nmn.py:241-244)
-        if self.classifier_math == "split":
-            answer_logits = self._classifier_split(final)
-        elif self.classifier_tf32:
-            prev = torch.backends.cuda.matmul.allow_tf32
-            final = _MatmulPrecision.apply(final, True, prev)
-            answer_logits = _MatmulPrecision.apply(self.classifier(final), prev, True)
-        else:
-            answer_logits = self.classifier(final)
-        # answer head (nmn.py:245-269): predictions, masking of invalid programs, per-row loss, correct count -- one kernel
-        correct = torch.zeros((), dtype=torch.int64, device=features.device) if answers is not None else None
-        answer_predictions, loss = _AnswerLoss.apply(answer_logits, answers, run.blob, xin_off, self._unknown_answer, correct)
-        if not need_grad:
-            run.close()
-        if answers is not None:
-            # the correct count stays on the device until a metric is read: no synchronisation inside forward
-            self._answer_accuracy(correct, B)
-            self._average_invalid_programs(int((valid_host == 0).sum()))
-
-        output_dict = {"predictions": answer_predictions, "loss": loss}
-        if self.training:
-            # same values as the reference's ``self.get_metrics(reset=True)`` (nmn.py:274): the accumulators are
-            # snapshotted and reset NOW, the numbers are produced when the dict is first read
-            acc_state = self._answer_accuracy.snapshot(reset=True)
-            invalid_now = self._average_invalid_programs.get_metric(reset=True)
-            output_dict["metrics"] = _LazyMetrics({"answer_accuracy": lambda: _Accuracy.value(acc_state),
-                                                   "average_invalid": lambda: invalid_now})
-        return output_dict
+    def _chunked_runs(self, features, programs_host, need_grad, staged, k):
+        """The batch as ``k`` independent plans over contiguous row ranges, compiled on ``k`` host threads (ctypes releases
+        the GIL around the C++ compiler) and executed side by side on ``k`` streams, each with 1/k of the executor's CTA slots.
+        What it buys is TIME TO LAUNCH: the compiler is sequential per plan (~12 us per program), and when the programs only
+        become known inside the step (joint training: they are sampled by the generator, modules/elbo.py:230-239) that time
+        sits on the step's critical path; the executor itself is bound by the length of its dependency chains, not by the
+        number of rows, so k smaller passes in parallel take about as long as one.  Weight packing and feature layout are
+        shared (``prestage``); results are those of the single plan up to the summation order of the weight gradients."""
+        lib = L.lib()
+        dev = features.device
+        B = programs_host.shape[0]
+        if staged is None:
+            self.prestage(features)
+            staged, self._prestaged = self._prestaged, None
+        ws_main = staged[1]
+        bounds = [B * i // k for i in range(k + 1)]
+        pool = _compile_pool()
+        futures = [pool.submit(self._compile, programs_host[lo:hi], need_grad, dev, True)
+                   for lo, hi in zip(bounds[:-1], bounds[1:])]
+        if self._chunk_streams is None or len(self._chunk_streams) < k or self._chunk_streams[0].device != dev:
+            self._chunk_streams = [torch.cuda.Stream(dev) for _ in range(k)]
+        sms = torch.cuda.get_device_properties(dev).multi_processor_count
+        unit_bytes = self._in_channels // 4 * 256 * 16 * 3 // 2
+        runs, valids, total = [], [], [0] * 16
+        for i, fut in enumerate(futures):
+            lo, hi = bounds[i], bounds[i + 1]
+            plan = fut.result()
+            lib.pnmn_plan_set_exec_ctas(plan, max(2 * sms // k, 16))
+            valid, sizes, stats = self._plan_info(plan, hi - lo)
+            sizes[L.SZ_AIN] = 0                      # the stem inputs of every chunk live in the prestaged workspace
+            ws = _POOL.acquire(dev)
+            ws.ensure(sizes)
+            bufs = L.Buffers(ws.t["arena16"].data_ptr(), ws.t["arena18"].data_ptr(), ws.t["arena22"].data_ptr(),
+                             ws.t["maps"].data_ptr(), ws.t["dmaps"].data_ptr(), ws.t["idx"].data_ptr(),
+                             ws.t["blob"].data_ptr(), self._packed.data_ptr(), self._flat.data_ptr(), None,
+                             ws_main.t["ain"].data_ptr() + lo * unit_bytes, ws.scratch.data_ptr())
+            run = _Run(plan, ws, bufs, self._gflat_box, lo=lo, hi=hi, stream=self._chunk_streams[i], staged=True,
+                       extra_ws=ws_main if i == 0 else None)
+            run.blob = ws.t["blob"]
+            run.xin_off = int(stats[15])
+            run.pool_blob = None
+            runs.append(run)
+            valids.append(valid)
+            total = [a + b for a, b in zip(total, stats)]
+        return runs, torch.cat(valids), total
 
     @staticmethod
     def _read_attention_maps(plan, ws):
@@ -846,10 +954,11 @@ class _NullCtx:
 class _AnswerLoss(torch.autograd.Function):
     """(predictions, loss) = answer head over the classifier's logits (``pnmn_answer_loss_forward`` / ``_backward``,
     csrc/loss.cu; nmn.py:245-269).  ``blob`` / ``xin_off``: the plan's task-table buffer and the byte offset of its per-row
-    validity table; ``correct``: optional device int64 scalar that receives the number of correct predictions."""
+    validity table -- ``tables`` lists (blob, offset, first row, end row) per plan; ``correct``: optional device int64 scalar
+    that receives the number of correct predictions."""
 
     @staticmethod
-    def forward(ctx, logits, answers, blob, xin_off, unknown, correct):
+    def forward(ctx, logits, answers, tables, unknown, correct):
         logits = logits.contiguous().float()
         B, A = logits.shape
         dev = logits.device
@@ -859,11 +968,15 @@ class _AnswerLoss(torch.autograd.Function):
         loss = torch.empty(B, dtype=torch.float32, device=dev)
         invalid = torch.empty(B, dtype=torch.uint8, device=dev)
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        L.check(L.lib().pnmn_answer_loss_forward(
-            ctypes.c_void_p(logits.data_ptr()), ctypes.c_void_p(answers.data_ptr()) if answers is not None else None,
-            ctypes.c_void_p(blob.data_ptr() + xin_off), B, A, int(unknown), ctypes.c_void_p(predictions.data_ptr()),
-            ctypes.c_void_p(loss.data_ptr()), ctypes.c_void_p(invalid.data_ptr()),
-            ctypes.c_void_p(correct.data_ptr()) if correct is not None else None, stream), "pnmn_answer_loss_forward")
+        for blob, xin_off, lo, hi in tables:       # one validity table per plan (a batch may be compiled in chunks of rows)
+            if hi <= lo:
+                continue
+            L.check(L.lib().pnmn_answer_loss_forward(
+                ctypes.c_void_p(logits.data_ptr() + 4 * A * lo),
+                ctypes.c_void_p(answers.data_ptr() + 8 * lo) if answers is not None else None,
+                ctypes.c_void_p(blob.data_ptr() + xin_off), hi - lo, A, int(unknown), ctypes.c_void_p(predictions.data_ptr() + 8 * lo),
+                ctypes.c_void_p(loss.data_ptr() + 4 * lo), ctypes.c_void_p(invalid.data_ptr() + lo),
+                ctypes.c_void_p(correct.data_ptr()) if correct is not None else None, stream), "pnmn_answer_loss_forward")
         ctx.save_for_backward(logits, predictions, invalid)
         ctx.answers = answers
         ctx.mark_non_differentiable(predictions)
@@ -883,7 +996,7 @@ class _AnswerLoss(torch.autograd.Function):
                 ctypes.c_void_p(invalid.data_ptr()), ctypes.c_void_p(predictions.data_ptr()),
                 ctypes.c_void_p(grad_loss.data_ptr()), B, A, ctypes.c_void_p(dlogits.data_ptr()), stream),
                 "pnmn_answer_loss_backward")
-        return dlogits, None, None, None, None, None
+        return dlogits, None, None, None, None
 
 
 _COMPILE_POOL = None
@@ -895,7 +1008,7 @@ def _compile_pool():
     global _COMPILE_POOL
     if _COMPILE_POOL is None:
         from concurrent.futures import ThreadPoolExecutor
-        _COMPILE_POOL = ThreadPoolExecutor(max_workers=2, thread_name_prefix="pnmn-plan")
+        _COMPILE_POOL = ThreadPoolExecutor(max_workers=4, thread_name_prefix="pnmn-plan")
     return _COMPILE_POOL
 
 

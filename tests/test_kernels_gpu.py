@@ -405,7 +405,7 @@ def test_answer_loss_head_matches_torch(with_answers):
     w = torch.rand(B, device="cuda")
     x = logits.clone().requires_grad_(True)
     correct = torch.zeros((), dtype=torch.int64, device="cuda") if with_answers else None
-    pred, loss = _AnswerLoss.apply(x, answers if with_answers else None, blob, 256, unknown, correct)
+    pred, loss = _AnswerLoss.apply(x, answers if with_answers else None, [(blob, 256, 0, B)], unknown, correct)
     (loss * w).sum().backward()
 
     y = logits.clone().requires_grad_(True)

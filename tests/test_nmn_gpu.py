@@ -435,3 +435,36 @@ def test_prestage_changes_nothing():
         assert torch.equal(r[0], results[0][0]) and torch.equal(r[1], results[0][1]) and torch.equal(r[2], results[0][2])
         assert float((r[3] - results[0][3]).abs().max()) <= 1e-5 * float(results[0][3].abs().max())
     assert int((results[0][1] == 28).sum()) == 2
+
+
+def test_compile_chunks_change_nothing():
+    """a batch compiled as 4 independent plans on 4 host threads and executed on 4 streams (NeuralModuleNetwork.compile_chunks)
+    gives the same logits / predictions / losses as the single plan, and the same gradients up to summation order; invalid
+    programs land in different chunks"""
+    vocab = Vocabulary.clevr()
+    sampler = ProgramSampler(vocab, seed=21)
+    B = 70
+    programs = sampler.sample(B, 26)
+    programs[[3, 40, 69]] = sampler.garbage(3, 26)
+    programs = programs.cuda()
+    feats, answers = make_features(B, 21).cuda(), make_answers(B, 21).cuda()
+    results = []
+    for chunks in (1, 4):
+        model = NeuralModuleNetwork(vocab)
+        model.load_state_dict(make_nmn_state_dict(vocab, 0))
+        model = model.cuda().train()
+        model.compile_chunks = chunks
+        logits = []
+        hook = model.classifier.register_forward_hook(lambda m, i, o: logits.append(o.detach().clone()))
+        for _ in range(2):                      # second pass: recycled workspaces
+            logits.clear()
+            model.zero_grad()
+            out = model(feats, programs, answers)
+            out["loss"].mean().backward()
+        hook.remove()
+        g = torch.cat([p.grad.flatten() for n, p in model.named_parameters() if not n.startswith("classifier.")]).clone()
+        results.append((logits[0], out["predictions"].clone(), out["loss"].detach().clone(), g, model.last_plan_stats[0]))
+    a, b = results
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2])
+    assert float((a[3] - b[3]).abs().max()) <= 2e-5 * float(a[3].abs().max())
+    assert a[4] == b[4] == B - 3 and int((a[1] == 28).sum()) == 3
