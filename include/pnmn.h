@@ -153,25 +153,24 @@ int pnmn_round_features_f16(const float* src, void* dst, int64_t n, void* stream
  * stem and module parameters are ACCUMULATED into bufs->grads (autograd semantics). */
 int pnmn_nmn_backward(pnmn_plan* p, const pnmn_buffers* bufs, const float* grad_final_out, void* stream);
 
-/* Classifier helper (probnmn/models/nmn.py:75-83 are plain library GEMMs): splits an fp32 matrix [rows][cols] (device) into
- * bf16 hi / lo parts and writes the three chunks of the split contraction, side by side (stack_rows = 0: [rows][3*cols])
- * or stacked (stack_rows = 1: [3*rows][cols]); chunk order (hi, lo, hi) if second_low else (hi, hi, lo). */
-int pnmn_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int stack_rows, int second_low, void* stream);
-
 /* Classifier helper: ReLU -> MaxPool2d(2,2) -> flatten (probnmn/models/nmn.py:77-79, nmn_modules.py:250-251) on the
  * channels-last output y [B][14*14][C] of the 1x1 convolution (device, fp32, bias included): pooled [B][C*7*7] in the
  * reference's (C, 7, 7) flatten order, code [B][C*7*7] bytes (argmax position | 4 if active) for the backward pass, which
  * writes gy [B][14*14][C] from g [B][C*7*7].  C must be a multiple of 64. */
 int pnmn_relu_pool_fwd(const float* y, float* pooled, void* code, int64_t B, int64_t C, void* stream);
 int pnmn_relu_pool_bwd(const float* g, const void* code, float* gy, int64_t B, int64_t C, void* stream);
-/* same routing, output as the bf16 (hi, lo) pair g2[2][B*196][C] (hi = bf16(gy), lo = bf16(gy - hi)) that the
- * split-precision classifier GEMMs consume; the fp32 gradient is never materialised (db: see below) */
-int pnmn_relu_pool_bwd_split(const float* g, const void* code, void* g2, float* db, int64_t B, int64_t C, void* stream);
-/* pnmn_relu_pool_fwd with the 1x1 conv's bias[C] added to y first (y = the bias-free GEMM output); in
- * pnmn_relu_pool_bwd_split, db (optional, [C], zeroed by the caller) receives that bias's gradient */
+/* pnmn_relu_pool_fwd with the 1x1 conv's bias[C] added to y first (y = the bias-free GEMM output) */
 int pnmn_relu_pool_fwd_bias(const float* y, const float* bias, float* pooled, void* code, int64_t B, int64_t C, void* stream);
-/* dst[2][n] bf16 = (hi, lo) split of src[n] fp32, n % 4 == 0 */
-int pnmn_split2_bf16(const float* src, void* dst, int64_t n, void* stream);
+/* Classifier GEMMs (probnmn/models/nmn.py:75-83 and their gradients): C[M][N] (row stride ldc) = (accumulate ? C : 0) +
+ * sum_k A(m, k) * B(n, k) (+ bias[n]) with A(m, k) = A[m*a_rs + k*a_ks], B(n, k) = B[n*b_rs + k*b_ks] -- any strides, so that
+ * x.w^T, g.w and g^T.x are the same entry point -- fp32 in, fp32 out, computed on the tensor cores from bf16 (hi, lo) splits
+ * (three tcgen05 MMAs per k step, ~16 mantissa bits per operand); csrc/gemm.cu.  Replaces the cuBLAS / cuDNN calls under
+ * nn.Conv2d(k=1) and nn.Linear.  workspace: pnmn_gemm_split_workspace(M, N, K) floats, 16-byte aligned (packed operands +
+ * the partial results of a split contraction, which are added in a fixed order: results are deterministic). */
+int64_t pnmn_gemm_split_workspace(int M, int N, int K);
+int pnmn_gemm_split(const float* A, int64_t a_rs, int64_t a_ks, const float* B, int64_t b_rs, int64_t b_ks, float* C,
+                    int64_t ldc, int M, int N, int K, const float* bias, int accumulate, float* workspace,
+                    int64_t workspace_floats, void* stream);
 
 /* Answer head behind the classifier (probnmn/models/nmn.py:245-269) in one launch: per row the predicted answer (first
  * maximum of the logits; unknown_index for a row whose program is invalid), the loss (cross entropy against answers[b], or

@@ -110,8 +110,8 @@ EXPORTS = [
     "pnmn_nmn_forward", "pnmn_nmn_backward", "pnmn_debug_launch_conv", "pnmn_debug_launch_wgrad",
     "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt", "pnmn_profile_enable",
     "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times", "pnmn_debug_plan_meta", "pnmn_debug_plan_maps", "pnmn_debug_graph_stats",
-    "pnmn_split3_bf16", "pnmn_relu_pool_fwd", "pnmn_relu_pool_bwd", "pnmn_relu_pool_bwd_split", "pnmn_relu_pool_fwd_bias", "pnmn_split2_bf16", "pnmn_launch_count", "pnmn_pg_workspace_bytes", "pnmn_pg_forward", "pnmn_pg_backward", "pnmn_pg_debug_layout", "pnmn_pg_forward_mixed",
-    "pnmn_prior_workspace_bytes", "pnmn_prior_forward", "pnmn_clamp_adam", "pnmn_elbo_glue", "pnmn_set_reserved_sms", "pnmn_has_bringup_kernels", "pnmn_answer_loss_forward", "pnmn_answer_loss_backward", "pnmn_nmn_forward_f16", "pnmn_round_features_f16", "pnmn_plan_create_ex", "pnmn_plan_set_exec_ctas", "pnmn_model_pack_table_bytes", "pnmn_model_pack_table", "pnmn_model_ain_floats", "pnmn_nmn_prestage",
+    "pnmn_relu_pool_fwd", "pnmn_relu_pool_bwd", "pnmn_relu_pool_fwd_bias", "pnmn_launch_count", "pnmn_pg_workspace_bytes", "pnmn_pg_forward", "pnmn_pg_backward", "pnmn_pg_debug_layout", "pnmn_pg_forward_mixed",
+    "pnmn_prior_workspace_bytes", "pnmn_prior_forward", "pnmn_clamp_adam", "pnmn_elbo_glue", "pnmn_set_reserved_sms", "pnmn_has_bringup_kernels", "pnmn_answer_loss_forward", "pnmn_answer_loss_backward", "pnmn_gemm_split", "pnmn_gemm_split_workspace", "pnmn_nmn_forward_f16", "pnmn_round_features_f16", "pnmn_plan_create_ex", "pnmn_plan_set_exec_ctas", "pnmn_model_pack_table_bytes", "pnmn_model_pack_table", "pnmn_model_ain_floats", "pnmn_nmn_prestage",
 ]
 
 
@@ -194,16 +194,17 @@ def lib() -> ctypes.CDLL:
                                   c_double, c_double, c_double, c_int, c_void_p]
     L.pnmn_elbo_glue.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_float, c_int,
                                  c_void_p, c_void_p, c_void_p, c_void_p]
-    L.pnmn_split3_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int, c_int, c_void_p]
     L.pnmn_relu_pool_fwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
     L.pnmn_relu_pool_bwd.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
-    L.pnmn_relu_pool_bwd_split.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
     L.pnmn_relu_pool_fwd_bias.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int64, c_void_p]
-    L.pnmn_split2_bf16.argtypes = [c_void_p, c_void_p, c_int64, c_void_p]
     L.pnmn_launch_count.restype = ctypes.c_longlong
     L.pnmn_launch_count.argtypes = [c_int]
     L.pnmn_profile_enable.argtypes = [c_int]
     L.pnmn_set_reserved_sms.argtypes = [c_int]
+    L.pnmn_gemm_split.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_int, c_int, c_int,
+                                  c_void_p, c_int, c_void_p, c_int64, c_void_p]
+    L.pnmn_gemm_split_workspace.restype = c_int64
+    L.pnmn_gemm_split_workspace.argtypes = [c_int, c_int, c_int]
     L.pnmn_answer_loss_forward.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                            c_void_p]
     L.pnmn_answer_loss_backward.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p]

@@ -131,40 +131,6 @@ cudaError_t launch_round_features_f16(const float* src, void* dst, int64_t n, cu
 }
 
 
-// x ~= hi + lo in bf16 (16 mantissa bits); writes the three chunks of the split contraction in one pass:
-//   stack_rows == 0: dst [rows][3*cols] = [hi | a | b]      stack_rows == 1: dst [3*rows][cols] = [hi ; a ; b]
-//   (a, b) = (lo, hi) when second_low else (hi, lo).  Contracting a second_low tensor with a !second_low tensor over the
-//   tripled dimension yields hi*hi + lo*hi + hi*lo.  Used by the classifier's library GEMMs (nmn.py, _SplitLinear).
-__global__ void split3_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t rows, int64_t cols,
-                                   int stack_rows, int second_low) {
-  const int64_t n4 = rows * cols / 4;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(src)[i];
-    const float x[4] = {v.x, v.y, v.z, v.w};
-    __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      hi[e] = __float2bfloat16_rn(x[e]);
-      lo[e] = __float2bfloat16_rn(x[e] - __bfloat162float(hi[e]));
-    }
-    const int64_t r = (i * 4) / cols, c = (i * 4) % cols;
-    const int64_t chunk = stack_rows ? rows * cols : cols;
-    const int64_t base = stack_rows ? r * cols + c : r * 3 * cols + c;
-    const uint2 H = *reinterpret_cast<const uint2*>(hi), Lw = *reinterpret_cast<const uint2*>(lo);
-    *reinterpret_cast<uint2*>(dst + base) = H;
-    *reinterpret_cast<uint2*>(dst + base + chunk) = second_low ? Lw : H;
-    *reinterpret_cast<uint2*>(dst + base + 2 * chunk) = second_low ? H : Lw;
-  }
-}
-cudaError_t launch_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int stack_rows, int second_low,
-                               cudaStream_t st) {
-  if (rows * cols == 0) return cudaSuccess;
-  const int64_t n4 = rows * cols / 4;
-  const int blocks = static_cast<int>(n4 / 256 + 1 < 148 * 16 ? n4 / 256 + 1 : 148 * 16);
-  split3_bf16_kernel<<<blocks, 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), rows, cols, stack_rows, second_low);
-  return cudaGetLastError();
-}
-
 // ---- classifier: ReLU + 2x2 max-pool + (C,7,7) flatten of the channels-last 1x1-conv output (nmn.py:77-79, nmn_modules.py:250)
 // y: [B][196][C] fp32 (bias already added), pooled: [B][C*49] fp32, code: [B][C*49] bytes = argmax position in the
 // window (bits 0-1: dy*2 + dx, first maximum in scan order like ATen's max_pool2d) | 4 if the pooled value is > 0.
@@ -211,80 +177,6 @@ __global__ void __launch_bounds__(256) relu_pool_bwd_kernel(const float* __restr
     const int cd = ctile[cw * 49 + w];
     gb[static_cast<size_t>(p) * C] = (cd == (pos | 4)) ? tile[cw * 49 + w] : 0.f;
   }
-}
-// Same routing, but the gradient leaves as the bf16 (hi, lo) pair the classifier's split-precision GEMMs consume:
-// g2[0][B*196][C] = bf16(gy), g2[1][B*196][C] = bf16(gy - hi).  The fp32 tensor (205 MB at batch 256) is never written and
-// the two split passes that used to read it back (dgrad and wgrad layouts, 0.5 GB each) disappear.
-// `db` (optional, [C], zeroed by the caller) receives the bias gradient: a window's gradient reaches exactly one pixel, and
-// only if its maximum was positive (code bit 2), so db[c] is a sum over the pooled gradient (one atomic per block and channel).
-__global__ void __launch_bounds__(256) relu_pool_bwd_split_kernel(const float* __restrict__ g, const uint8_t* __restrict__ code,
-                                                                  __nv_bfloat16* __restrict__ g2, float* __restrict__ db,
-                                                                  int C, size_t plane) {
-  __shared__ float tile[kPoolCB * 49];
-  __shared__ uint8_t ctile[kPoolCB * 49];
-  __shared__ float part[4][kPoolCB];
-  const int b = blockIdx.y, c0 = blockIdx.x * kPoolCB;
-  const size_t o = static_cast<size_t>(b) * C * 49 + static_cast<size_t>(c0) * 49;
-  for (int i = threadIdx.x; i < kPoolCB * 49; i += 256) { tile[i] = g[o + i]; ctile[i] = code[o + i]; }
-  __syncthreads();
-  if (db) {
-    const int ch = threadIdx.x % kPoolCB, q = threadIdx.x / kPoolCB;
-    float s = 0.f;
-    for (int w = q; w < 49; w += 4) s += (ctile[ch * 49 + w] & 4) ? tile[ch * 49 + w] : 0.f;
-    part[q][ch] = s;
-    __syncthreads();
-    if (threadIdx.x < kPoolCB)
-      atomicAdd(db + c0 + threadIdx.x, part[0][threadIdx.x] + part[1][threadIdx.x] + part[2][threadIdx.x] + part[3][threadIdx.x]);
-  }
-  // thread = (channel pair cp = tid % 32, pixel phase pq = tid / 32): 4-byte bf16x2 stores, 128 contiguous bytes per warp
-  const int cp = threadIdx.x % (kPoolCB / 2), pq = threadIdx.x / (kPoolCB / 2);
-  __nv_bfloat16* gb = g2 + (static_cast<size_t>(b) * 196) * C + c0 + 2 * cp;
-  for (int p = pq; p < 196; p += 256 / (kPoolCB / 2)) {
-    const int yy = p / 14, xx = p - yy * 14;
-    const int w = (yy >> 1) * 7 + (xx >> 1), pos = (yy & 1) * 2 + (xx & 1);
-    float v[2];
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int cd = ctile[(2 * cp + e) * 49 + w];
-      v[e] = (cd == (pos | 4)) ? tile[(2 * cp + e) * 49 + w] : 0.f;
-    }
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(v[0]), h1 = __float2bfloat16_rn(v[1]);
-    const __nv_bfloat162 hi = __halves2bfloat162(h0, h1);
-    const __nv_bfloat162 lo = __halves2bfloat162(__float2bfloat16_rn(v[0] - __bfloat162float(h0)),
-                                                 __float2bfloat16_rn(v[1] - __bfloat162float(h1)));
-    *reinterpret_cast<__nv_bfloat162*>(gb + static_cast<size_t>(p) * C) = hi;
-    *reinterpret_cast<__nv_bfloat162*>(gb + plane + static_cast<size_t>(p) * C) = lo;
-  }
-}
-
-// x ~= hi + lo in bf16: dst[0][n] = hi, dst[1][n] = lo (one pass; the operands of the classifier's shared-split GEMMs)
-__global__ void split2_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int64_t n) {
-  const int64_t n4 = n / 4;
-  for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < n4; i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
-    const float4 v = reinterpret_cast<const float4*>(src)[i];
-    const float x[4] = {v.x, v.y, v.z, v.w};
-    __nv_bfloat16 hi[4], lo[4];
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      hi[e] = __float2bfloat16_rn(x[e]);
-      lo[e] = __float2bfloat16_rn(x[e] - __bfloat162float(hi[e]));
-    }
-    *reinterpret_cast<uint2*>(dst + i * 4) = *reinterpret_cast<const uint2*>(hi);
-    *reinterpret_cast<uint2*>(dst + n + i * 4) = *reinterpret_cast<const uint2*>(lo);
-  }
-}
-cudaError_t launch_split2_bf16(const float* src, void* dst, int64_t n, cudaStream_t st) {
-  if (n == 0) return cudaSuccess;
-  const int64_t n4 = n / 4;
-  const int blocks = static_cast<int>(n4 / 256 + 1 < 148 * 16 ? n4 / 256 + 1 : 148 * 16);
-  split2_bf16_kernel<<<blocks, 256, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), n);
-  return cudaGetLastError();
-}
-cudaError_t launch_relu_pool_bwd_split(const float* g, const uint8_t* code, void* g2, float* db, int B, int C, cudaStream_t st) {
-  if (B <= 0) return cudaSuccess;
-  relu_pool_bwd_split_kernel<<<dim3(C / kPoolCB, B), 256, 0, st>>>(g, code, static_cast<__nv_bfloat16*>(g2), db, C,
-                                                                   static_cast<size_t>(B) * 196 * C);
-  return cudaGetLastError();
 }
 cudaError_t launch_relu_pool_fwd(const float* y, const float* bias, float* pooled, uint8_t* code, int B, int C, cudaStream_t st) {
   if (B <= 0) return cudaSuccess;

@@ -35,14 +35,10 @@ cudaError_t launch_conv_simt(const ConvTask* d_tasks, int n_tasks, const ConvCfg
 cudaError_t launch_wgrad(const WgradTask* d_tasks, int n_tasks, int impl_simt, int* d_counter, cudaStream_t stream);
 cudaError_t launch_bias_grad(const void* d_tasks, int n_tasks, int split, cudaStream_t stream);
 cudaError_t launch_elt(const EltTask* d_tasks, int n_tasks, cudaStream_t stream);
-cudaError_t launch_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int stack_rows, int second_low,
-                               cudaStream_t stream);
 cudaError_t launch_loss_scale(const float* grad, size_t n, float* scale, cudaStream_t stream);
 
 // classifier: ReLU + 2x2/2 max-pool + (C,7,7) flatten of a channels-last [B][14*14][C] tensor, and its backward (layout.cu)
 cudaError_t launch_relu_pool_fwd(const float* y, const float* bias, float* pooled, uint8_t* code, int B, int C, cudaStream_t st);
 cudaError_t launch_relu_pool_bwd(const float* g, const uint8_t* code, float* gy, int B, int C, cudaStream_t st);
-cudaError_t launch_relu_pool_bwd_split(const float* g, const uint8_t* code, void* g2, float* db, int B, int C, cudaStream_t st);
-cudaError_t launch_split2_bf16(const float* src, void* dst, int64_t n, cudaStream_t st);
 
 }  // namespace pnmn

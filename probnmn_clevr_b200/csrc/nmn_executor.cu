@@ -1842,13 +1842,6 @@ extern "C" int pnmn_profile_read(double* ms, int64_t* launches) {
 }
 
 // bf16 hi/lo split of an fp32 matrix for the classifier's split-precision library GEMMs (see layout.cu)
-extern "C" int pnmn_split3_bf16(const float* src, void* dst, int64_t rows, int64_t cols, int stack_rows, int second_low,
-                                void* stream) {
-  if (!src || !dst || rows < 0 || cols < 0 || cols % 4 != 0) return fail("pnmn_split3_bf16: bad arguments (cols must be a multiple of 4)");
-  CUDA_OK(launch_split3_bf16(src, dst, rows, cols, stack_rows, second_low, static_cast<cudaStream_t>(stream)));
-  pnmn::count_launches(1);
-  return 0;
-}
 
 // ReLU + 2x2 max-pool + flatten between the classifier's two GEMMs (nmn.py:77-79) and its backward (see layout.cu)
 extern "C" int pnmn_relu_pool_fwd(const float* y, float* pooled, void* code, int64_t B, int64_t C, void* stream) {
@@ -1872,19 +1865,7 @@ extern "C" int pnmn_relu_pool_bwd(const float* g, const void* code, float* gy, i
 }
 
 // the same backward with the gradient written as the bf16 (hi, lo) pair [2][B*196][C] of the split-precision GEMMs
-extern "C" int pnmn_relu_pool_bwd_split(const float* g, const void* code, void* g2, float* db, int64_t B, int64_t C, void* stream) {
-  if (!g || !g2 || !code || B < 0 || C <= 0 || C % 64 != 0) return fail("pnmn_relu_pool_bwd_split: bad arguments (C must be a multiple of 64)");
-  CUDA_OK(launch_relu_pool_bwd_split(g, static_cast<const uint8_t*>(code), g2, db, static_cast<int>(B), static_cast<int>(C), static_cast<cudaStream_t>(stream)));
-  pnmn::count_launches(1);
-  return 0;
-}
 // bf16 (hi, lo) pair [2][n] of an fp32 array (n a multiple of 4)
-extern "C" int pnmn_split2_bf16(const float* src, void* dst, int64_t n, void* stream) {
-  if (!src || !dst || n < 0 || n % 4 != 0) return fail("pnmn_split2_bf16: bad arguments (n must be a multiple of 4)");
-  CUDA_OK(launch_split2_bf16(src, dst, n, static_cast<cudaStream_t>(stream)));
-  pnmn::count_launches(1);
-  return 0;
-}
 
 // ---- bring-up entry points -----------------------------------------------------------------------
 namespace {

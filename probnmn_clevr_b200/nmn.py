@@ -882,28 +882,21 @@ class NeuralModuleNetwork(nn.Module):
             self._destroy_pending(self._precompiled.pop())
 
     def _classifier_split(self, final: torch.Tensor) -> torch.Tensor:
-        """nmn.py:75-83 with the two large GEMMs (1x1 conv 128->1024 over B*196 pixels, Linear 50176->1024) as
-        split-bf16 tensor-core products; ReLU / max-pool / the 1024->28 Linear stay plain fp32 ops."""
+        """nmn.py:75-83 on the repo's own kernels: every product (1x1 conv 128->1024 over the B*196 pixels, Linear
+        50176->1024, Linear 1024->num_answers, and their gradients) is ``pnmn_gemm_split``; ReLU / MaxPool2d(2,2) / flatten
+        between the first two is one pass over the conv output."""
         conv, fc1, fc2 = self.classifier[0], self.classifier[4], self.classifier[6]
         B, C, H, W = final.shape
         x = final.permute(0, 2, 3, 1).reshape(B * H * W, C)
-        if H == 14 and W == 14 and conv.out_channels % 64 == 0 and C % 4 == 0 and fc1.in_features % 4 == 0 and self._classifier_fused:
-            # conv + ReLU + MaxPool2d(2,2) + the (C,7,7) flatten as one node, then the big Linear with a shared weight split
-            y = _ConvReluPool.apply(x, conv.weight.view(conv.out_channels, C), conv.bias, B)
-            z = F.relu(_BigLinear.apply(y, fc1.weight, fc1.bias))
-            logits = F.linear(z, fc2.weight, fc2.bias)
-            for hook in self.classifier._forward_hooks.values():  # tests / tools observe the classifier through hooks
-                hook(self.classifier, (final,), logits)
-            return logits
-        y = _SplitLinear.apply(x, conv.weight.view(conv.out_channels, C), conv.bias)   # channels-last, pre-activation
         if H == 14 and W == 14 and conv.out_channels % 64 == 0:
-            y = _ReluPoolFlatten.apply(y, B)  # ReLU + MaxPool2d(2,2) + (C,7,7) flatten in one pass (nmn.py:77-79)
+            y = _ConvReluPool.apply(x, conv.weight.view(conv.out_channels, C), conv.bias, B)
         else:
+            y = _SplitLinear.apply(x, conv.weight.view(conv.out_channels, C), conv.bias)   # channels-last, pre-activation
             y = F.relu(y).view(B, H, W, conv.out_channels).permute(0, 3, 1, 2)  # NCHW view of channels-last data
             y = F.max_pool2d(y, kernel_size=2, stride=2)
             y = y.contiguous(memory_format=torch.contiguous_format).reshape(B, -1)  # (C, 7, 7) order, nmn_modules.py:250
         z = F.relu(_SplitLinear.apply(y, fc1.weight, fc1.bias))
-        logits = F.linear(z, fc2.weight, fc2.bias)
+        logits = _SplitLinear.apply(z, fc2.weight, fc2.bias)
         for hook in self.classifier._forward_hooks.values():  # tests / tools observe the classifier through hooks
             hook(self.classifier, (final,), logits)
         return logits
@@ -1012,78 +1005,67 @@ def _compile_pool():
     return _COMPILE_POOL
 
 
-def _split3(x: torch.Tensor, dim: int, second_low: bool) -> torch.Tensor:
-    """x ~= hi + lo in bf16; returns cat([hi, lo, hi]) (second_low) or cat([hi, hi, lo]) along ``dim``: contracting two
-    such tensors over ``dim`` yields hi*hi + lo*hi + hi*lo, i.e. the product to ~16 mantissa bits per operand.  One pass
-    over the data (``pnmn_split3_bf16``)."""
-    x = x.contiguous()
-    rows, cols = x.shape
-    out = torch.empty((rows, 3 * cols) if dim == 1 else (3 * rows, cols), dtype=torch.bfloat16, device=x.device)
-    stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-    L.check(L.lib().pnmn_split3_bf16(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), rows, cols,
-                                     1 if dim == 0 else 0, 1 if second_low else 0, stream), "pnmn_split3_bf16")
+def _gemm(A: torch.Tensor, a_rs: int, a_ks: int, Bm: torch.Tensor, b_rs: int, b_ks: int, M: int, N: int, K: int,
+          bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """C (M, N) = sum_k A(m, k) * B(n, k) (+ bias) with A(m, k) = A.flat[m*a_rs + k*a_ks], B likewise: ``pnmn_gemm_split``
+    (csrc/gemm.cu) -- fp32 in / out, bf16 (hi, lo) split products on the tensor cores, operands read in their home layout."""
+    out = torch.empty((M, N), dtype=torch.float32, device=A.device)
+    lib = L.lib()
+    with torch.cuda.device(A.device):
+        ws_floats = int(lib.pnmn_gemm_split_workspace(M, N, K))   # > 0: the contraction is split; partial tiles are added in order
+        ws = torch.empty(ws_floats, dtype=torch.float32, device=A.device) if ws_floats else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(A.device).cuda_stream)
+        L.check(lib.pnmn_gemm_split(ctypes.c_void_p(A.data_ptr()), a_rs, a_ks, ctypes.c_void_p(Bm.data_ptr()), b_rs, b_ks,
+                                    ctypes.c_void_p(out.data_ptr()), N, M, N, K,
+                                    ctypes.c_void_p(bias.data_ptr()) if bias is not None else None, 0,
+                                    ctypes.c_void_p(ws.data_ptr()) if ws is not None else None, ws_floats, stream), "pnmn_gemm_split")
     return out
 
 
 class _SplitLinear(torch.autograd.Function):
-    """y = x @ w.T + b with fp32 inputs / outputs, computed by ONE bf16 tensor-core GEMM (fp32 accumulate) over the
-    3x-long split contraction; same for both gradient GEMMs.  Library call (cuBLAS), used for the classifier only."""
+    """y = x @ w.T + b (x: (M, K), w: (N, K)) and its three gradient products, all through ``pnmn_gemm_split``: the weight --
+    205 MB for classifier[4] -- is read in place by every product (w as stored for y and dw, w with swapped strides for dx),
+    no split or transposed copy of it is ever written."""
 
     @staticmethod
     def forward(ctx, x, w, b):
+        x, w = x.contiguous(), w.contiguous()
         ctx.save_for_backward(x, w)
-        return torch.addmm(b, _split3(x, 1, True), _split3(w, 1, False).t(), out_dtype=torch.float32)
+        M, K = x.shape
+        return _gemm(x, K, 1, w, K, 1, M, w.shape[0], K, bias=b.contiguous() if b is not None else None)
 
     @staticmethod
     def backward(ctx, g):
         x, w = ctx.saved_tensors
         g = g.contiguous()
+        M, K = x.shape
+        N = w.shape[0]
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
-            dx = torch.mm(_split3(g, 1, True), _split3(w, 0, False), out_dtype=torch.float32)
-        if ctx.needs_input_grad[1]:
-            dw = torch.mm(_split3(g, 0, True).t(), _split3(x, 0, False), out_dtype=torch.float32)
-        if ctx.needs_input_grad[2]:
-            db = g.sum(0)
+        with torch.cuda.device(g.device):
+            if ctx.needs_input_grad[0]:
+                dx = _gemm(g, N, 1, w, 1, K, M, K, N)          # dx[m][k] = sum_n g[m][n] * w[n][k]
+            if ctx.needs_input_grad[1]:
+                dw = _gemm(g, 1, N, x, 1, K, N, K, M)          # dw[n][k] = sum_m g[m][n] * x[m][k]
+            if ctx.needs_input_grad[2]:
+                db = g.sum(0)
         return dx, dw, db
-
-
-def _split2(x: torch.Tensor) -> torch.Tensor:
-    """x ~= hi + lo in bf16, returned as one (2, *x.shape) tensor [hi, lo] (``pnmn_split2_bf16``, one pass)."""
-    x = x.contiguous()
-    out = torch.empty((2,) + tuple(x.shape), dtype=torch.bfloat16, device=x.device)
-    stream = ctypes.c_void_p(torch.cuda.current_stream(x.device).cuda_stream)
-    L.check(L.lib().pnmn_split2_bf16(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(out.data_ptr()), x.numel(), stream),
-            "pnmn_split2_bf16")
-    return out
-
-
-def _mm3(a2: torch.Tensor, b2: torch.Tensor, ta: bool = False) -> torch.Tensor:
-    """hi*hi + lo*hi + hi*lo of two (hi, lo) pairs as three library GEMMs accumulating into one fp32 result (used where the
-    result is small next to the operands, so that re-reading it costs nothing and no operand has to be re-laid-out)."""
-    A = (lambda i: a2[i].t()) if ta else (lambda i: a2[i])
-    out = torch.mm(A(0), b2[0], out_dtype=torch.float32)
-    out = torch.addmm(out, A(1), b2[0], out_dtype=torch.float32)
-    return torch.addmm(out, A(0), b2[1], out_dtype=torch.float32)
 
 
 class _ConvReluPool(torch.autograd.Function):
     """classifier[0:4] (nmn.py:75-79): 1x1 conv as a GEMM over the B*196 pixels + ReLU + MaxPool2d(2,2) + flatten, as ONE
-    autograd node.  Forward: the split-bf16 GEMM of ``_SplitLinear`` and ``pnmn_relu_pool_fwd``.  Backward: the pooled
-    gradient is routed straight into the bf16 (hi, lo) pair of d(conv output) (``pnmn_relu_pool_bwd_split``): the 205 MB
-    fp32 gradient is never written and never re-read by split passes (it used to be split twice, once per GEMM layout);
-    the bias gradient is summed from the pooled gradient (4x smaller)."""
+    autograd node: ``pnmn_gemm_split`` for the products, ``pnmn_relu_pool_fwd_bias`` / ``pnmn_relu_pool_bwd`` for the pooling
+    pass (the conv bias is added inside it: max(v) + b == max(v + b))."""
 
     @staticmethod
     def forward(ctx, x, w, b, B):
-        # (the bias is added inside the pooling pass: addmm would first broadcast it into the 205 MB output)
-        y = torch.mm(_split3(x, 1, True), _split3(w, 1, False).t(), out_dtype=torch.float32)
+        x, w = x.contiguous(), w.contiguous()
+        M, K = x.shape
         C = w.shape[0]
+        y = _gemm(x, K, 1, w, K, 1, M, C, K)
         pooled = torch.empty((B, C * 49), dtype=torch.float32, device=y.device)
         code = torch.empty((B, C * 49), dtype=torch.uint8, device=y.device)
         stream = ctypes.c_void_p(torch.cuda.current_stream(y.device).cuda_stream)
-        bias = b.contiguous()
-        L.check(L.lib().pnmn_relu_pool_fwd_bias(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(bias.data_ptr()),
+        L.check(L.lib().pnmn_relu_pool_fwd_bias(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(b.contiguous().data_ptr()),
                                                 ctypes.c_void_p(pooled.data_ptr()), ctypes.c_void_p(code.data_ptr()), B, C,
                                                 stream), "pnmn_relu_pool_fwd_bias")
         ctx.save_for_backward(x, w, code)
@@ -1093,56 +1075,22 @@ class _ConvReluPool(torch.autograd.Function):
     @staticmethod
     def backward(ctx, g):
         x, w, code = ctx.saved_tensors
-        B, M, C = ctx.B, x.shape[0], w.shape[0]
+        B, M, K, C = ctx.B, x.shape[0], x.shape[1], w.shape[0]
         g = g.contiguous()
-        g2 = torch.empty((2, M, C), dtype=torch.bfloat16, device=g.device)
-        stream = ctypes.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
-        db = torch.zeros(C, dtype=torch.float32, device=g.device) if ctx.needs_input_grad[2] else None
-        L.check(L.lib().pnmn_relu_pool_bwd_split(ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(code.data_ptr()),
-                                                 ctypes.c_void_p(g2.data_ptr()),
-                                                 ctypes.c_void_p(db.data_ptr() if db is not None else None), B, C, stream),
-                "pnmn_relu_pool_bwd_split")
-        dx = dw = None
-        if ctx.needs_input_grad[0]:
-            dx = _mm3(g2, _split2(w))                 # (M, C) x (C, Cin)
-        if ctx.needs_input_grad[1]:
-            dw = _mm3(g2, _split2(x), ta=True)        # (C, M) x (M, Cin)
-        return dx, dw, db, None
-
-
-class _BigLinear(torch.autograd.Function):
-    """Linear whose WEIGHT is the big operand (classifier[4]: 1024 x 50176, 205 MB).  Its bf16 (hi, lo) pair is made once
-    per step and shared by the forward and the data-gradient GEMM (two layout-specific split passes of 0.5 GB each
-    before).  The forward multiplies [x_hi; x_lo] with [w_hi; w_lo]^T in ONE pass over the weight -- split over the
-    contraction into a batched GEMM, because cuBLAS runs the plain (256 x 1024 x 150528) product on 128 CTAs at a quarter
-    of the HBM rate -- and adds up the four blocks of the result (lo*lo included: it is free)."""
-
-    @staticmethod
-    def forward(ctx, x, w, b):
-        w2 = _split2(w)                                # (2, N, K)
-        x2 = _split2(x)                                # (2, M, K)
-        M, K = x.shape
-        N = w.shape[0]
-        S = next((s for s in (8, 7, 4, 2) if K % (8 * s) == 0 and K // s >= 1024), 1)
-        Kc = K // S
-        P = torch.bmm(x2.view(2 * M, S, Kc).transpose(0, 1), w2.view(2 * N, S, Kc).permute(1, 2, 0), out_dtype=torch.float32)
-        P = P.sum(0) if S > 1 else P[0]                # (2M, 2N)
-        y = P[:M, :N] + P[:M, N:] + P[M:, :N] + P[M:, N:] + b
-        ctx.save_for_backward(x, w2)
-        return y
-
-    @staticmethod
-    def backward(ctx, g):
-        x, w2 = ctx.saved_tensors
         dx = dw = db = None
-        g = g.contiguous()
-        if ctx.needs_input_grad[0]:
-            dx = _mm3(_split2(g), w2)                  # (M, N) x (N, K)
-        if ctx.needs_input_grad[1]:
-            dw = torch.mm(_split3(g, 0, True).t(), _split3(x, 0, False), out_dtype=torch.float32)
-        if ctx.needs_input_grad[2]:
-            db = g.sum(0)
-        return dx, dw, db
+        with torch.cuda.device(g.device):
+            gy = torch.empty((M, C), dtype=torch.float32, device=g.device)
+            stream = ctypes.c_void_p(torch.cuda.current_stream(g.device).cuda_stream)
+            L.check(L.lib().pnmn_relu_pool_bwd(ctypes.c_void_p(g.data_ptr()), ctypes.c_void_p(code.data_ptr()),
+                                               ctypes.c_void_p(gy.data_ptr()), B, C, stream), "pnmn_relu_pool_bwd")
+            if ctx.needs_input_grad[0]:
+                dx = _gemm(gy, C, 1, w, 1, K, M, K, C)
+            if ctx.needs_input_grad[1]:
+                dw = _gemm(gy, 1, C, x, 1, K, C, K, M)
+            if ctx.needs_input_grad[2]:
+                # a pooled gradient reaches the bias when its window's maximum was positive (bit 2 of the code)
+                db = (g.view(B, C, 49) * ((code.view(B, C, 49) & 4) != 0)).sum((0, 2))
+        return dx, dw, db, None
 
 
 class _ReluPoolFlatten(torch.autograd.Function):

@@ -292,72 +292,76 @@ def test_relu_pool_flatten(B, C):
 
 
 @pytest.mark.parametrize("B,C", [(3, 64), (5, 1024)])
-def test_relu_pool_bwd_split_and_split2(B, C):
-    """pnmn_relu_pool_bwd_split writes the routed gradient as the bf16 (hi, lo) pair of the split-precision GEMMs:
-    hi is bit-exactly bf16(gy) of the fp32 kernel, lo bit-exactly bf16(gy - hi); pnmn_split2_bf16 does the same for a
-    plain array."""
+def test_relu_pool_fwd_with_bias(B, C):
+    """pnmn_relu_pool_fwd_bias: the conv bias added inside the pooling pass (max(v) + b == max(v + b))"""
     import ctypes
     from probnmn_clevr_b200 import _lib as L
-    from probnmn_clevr_b200.nmn import _ReluPoolFlatten, _split2
-    g = torch.Generator(device="cuda").manual_seed(9)
+    g = torch.Generator(device="cuda").manual_seed(6)
     y = torch.randn((B * 196, C), generator=g, device="cuda")
-    y[::5] = -y[::5].abs()
-    y1 = y.clone().requires_grad_(True)
-    out = _ReluPoolFlatten.apply(y1, B)
-    go = torch.randn(out.shape, generator=g, device="cuda")
-    out.backward(go)
-    gy = y1.grad
-    # the byte codes of the forward kernel
-    pooled = torch.empty_like(out); code = torch.empty(out.shape, dtype=torch.uint8, device="cuda")
-    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    L.check(L.lib().pnmn_relu_pool_fwd(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(pooled.data_ptr()),
-                                       ctypes.c_void_p(code.data_ptr()), B, C, st), "fwd")
-    g2 = torch.full((2, B * 196, C), float("nan"), dtype=torch.bfloat16, device="cuda")
-    db = torch.zeros(C, device="cuda")
-    L.check(L.lib().pnmn_relu_pool_bwd_split(ctypes.c_void_p(go.data_ptr()), ctypes.c_void_p(code.data_ptr()),
-                                             ctypes.c_void_p(g2.data_ptr()), ctypes.c_void_p(db.data_ptr()), B, C, st), "bwd_split")
-    hi = gy.bfloat16()
-    lo = (gy - hi.float()).bfloat16()
-    assert torch.equal(g2[0], hi) and torch.equal(g2[1], lo)
-    s2 = _split2(gy)
-    assert torch.equal(s2[0], hi) and torch.equal(s2[1], lo)
-    # bias gradient, summed inside the same pass from the pooled gradient alone
-    assert torch.allclose(db, gy.sum(0), rtol=1e-4, atol=1e-4)
-    # forward with the bias folded in: identical to adding it first
     bias = torch.randn(C, generator=g, device="cuda")
-    p2 = torch.empty_like(out); c2 = torch.empty_like(code)
+    p2 = torch.empty((B, C * 49), device="cuda")
+    c2 = torch.empty((B, C * 49), dtype=torch.uint8, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
     L.check(L.lib().pnmn_relu_pool_fwd_bias(ctypes.c_void_p(y.data_ptr()), ctypes.c_void_p(bias.data_ptr()), ctypes.c_void_p(p2.data_ptr()),
                                             ctypes.c_void_p(c2.data_ptr()), B, C, st), "fwd_bias")
     ref = F.max_pool2d(F.relu(y + bias).view(B, 14, 14, C).permute(0, 3, 1, 2), 2, 2).contiguous().reshape(B, -1)
     assert torch.equal(p2, ref)
 
 
-def test_fused_classifier_nodes_match_the_plain_split_path():
-    """_ConvReluPool + _BigLinear (shared weight split, gradient never materialised in fp32) against the one-GEMM-per-op
-    _SplitLinear path: same logits and gradients up to fp32 summation order."""
+@pytest.mark.parametrize("M,N,K", [(256, 1024, 50176), (123, 28, 1024), (24108, 1024, 128), (300, 200, 77), (128, 128, 32)])
+def test_gemm_split_matches_fp64(M, N, K):
+    """pnmn_gemm_split (tcgen05 MMAs over on-the-fly bf16 (hi, lo) splits) against a float64 product, for the three operand
+    layouts the classifier uses -- x.w^T (both k-contiguous), g.w (B row-contiguous) and g^T.x (both row-contiguous) --
+    with ragged tiles, a split contraction, the bias.  Tolerance: 16 mantissa bits per operand -> ~2e-5 relative L2, far inside
+    the 1e-3 bar on the logits; plain fp32 rounding noise of the same product is ~1e-6."""
+    from probnmn_clevr_b200.nmn import _gemm
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    x = torch.randn((M, K), generator=g, device="cuda")
+    w = torch.randn((N, K), generator=g, device="cuda") * 0.05
+    bias = torch.randn(N, generator=g, device="cuda")
+    rel = lambda a, b: float((a.double() - b).norm() / (b.norm() + 1e-300))
+    y = _gemm(x, K, 1, w, K, 1, M, N, K, bias=bias)                                  # y = x w^T + b
+    assert rel(y, x.double() @ w.double().t() + bias.double()) < 3e-5
+    gy = torch.randn((M, N), generator=g, device="cuda") * 1e-4                       # (gradient-sized values)
+    dx = _gemm(gy, N, 1, w, 1, K, M, K, N)                                           # dx = g w
+    assert rel(dx, gy.double() @ w.double()) < 3e-5
+    if M * N * K <= 256 * 1024 * 50176:
+        dw = _gemm(gy, 1, N, x, 1, K, N, K, M)                                       # dw = g^T x
+        assert rel(dw, gy.double().t() @ x.double()) < 3e-5
+
+
+def test_classifier_matches_fp32_modules():
+    """the classifier on pnmn_gemm_split + the pooling pass against the plain nn.Sequential in IEEE fp32 (cuBLAS / cuDNN, TF32
+    off): logits and every gradient"""
     from probnmn_clevr_b200.nmn import NeuralModuleNetwork
     from probnmn_clevr_b200.synthetic import make_nmn_state_dict
     from probnmn_clevr_b200.vocabulary import Vocabulary
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
     vocab = Vocabulary.clevr()
     m = NeuralModuleNetwork(vocab)
     m.load_state_dict(make_nmn_state_dict(vocab, 0))
     m = m.cuda()
     g = torch.Generator(device="cuda").manual_seed(3)
-    final = torch.randn((6, 128, 14, 14), generator=g, device="cuda").relu_()
+    final = torch.randn((37, 128, 14, 14), generator=g, device="cuda").relu_()
     res = {}
-    for fused in (True, False):
-        m._classifier_fused = fused
+    for native in (True, False):
         m.zero_grad(set_to_none=True)
         f = final.clone().requires_grad_(True)
-        logits = m._classifier_split(f)
+        logits = m._classifier_split(f) if native else m.classifier(f)
         logits.square().sum().backward()
-        res[fused] = (logits.detach(), f.grad, [p.grad.clone() for p in m.classifier.parameters()])
+        res[native] = (logits.detach(), f.grad, [p.grad.clone() for p in m.classifier.parameters()])
     rel = lambda a, b: float((a - b).norm() / (b.norm() + 1e-30))
-    # (both paths carry ~16 mantissa bits per operand; they differ in fp32 summation order and in the lo*lo term of the
-    # big Linear, which only the fused path includes: measured 2e-5 relative L2)
     assert rel(res[True][0], res[False][0]) < 1e-4
-    assert rel(res[True][1], res[False][1]) < 1e-4
-    for a, b in zip(res[True][2], res[False][2]):
+    # gradients: a 2x2 window whose two largest pre-activations differ by less than the products' rounding noise routes its
+    # gradient to the other pixel (max-pool is discontinuous there) -- a handful of such windows out of 37 * 50176 give
+    # ~2e-3 relative L2 on d(input) and on the conv's gradients; everything downstream of the pooling (both Linear layers)
+    # agrees to 1e-4
+    assert rel(res[True][1], res[False][1]) < 1e-2
+    grads = list(zip(res[True][2], res[False][2]))
+    for a, b in grads[:2]:
+        assert rel(a, b) < 1e-2
+    for a, b in grads[2:]:
         assert rel(a, b) < 1e-4
 
 
