@@ -499,8 +499,8 @@ def run_executor(args, ctx, extra=False):
         "kernel_ms_per_step": kernel_ms, "host_ms_per_step": host_ms_per_step,
         "plan": {"valid_programs": stats[0], "conv3x3_instances": stats[1], "module_tokens": stats[2],
                  "forward_launches": stats[3], "backward_launches": stats[4], "wgrad_flops": stats[12]},
-        "classifier_math": {"split": "split bf16 x2 (one cuBLAS tensor-core GEMM over the 3x contraction, fp32 accumulate)",
-                            "tf32": "tf32 (cuBLAS/cuDNN)", "ieee": "ieee fp32 (cuBLAS/cuDNN)"}[model.classifier_math],
+        "classifier_math": {"split": "pnmn_gemm_split: bf16 (hi, lo) split operands, three tcgen05 MMAs per k step, fp32 accumulate (no library GEMM)",
+                            "tf32": "tf32 (cuBLAS/cuDNN, comparison only)", "ieee": "ieee fp32 (cuBLAS/cuDNN, comparison only)"}[model.classifier_math],
     }
     model._drop_precompiled()
     if extra:
@@ -825,7 +825,7 @@ def run_joint(args, ctx):
                               "conv3x3_instances": per_step["convs"], "module_tokens": per_step["tokens"]},
         "optimizer_launches_per_step": js.optimizer.launches_last_step,
         "parity_check": parity, "phases_ms": phases,
-        "classifier_math": "split bf16 x2 (library tensor-core GEMMs over the 3x contraction, fp32 accumulate)",
+        "classifier_math": "pnmn_gemm_split: bf16 (hi, lo) split operands, three tcgen05 MMAs per k step, fp32 accumulate (no library GEMM)",
     }
     if not args.no_extras:
         sub = argparse.Namespace(**vars(args))

@@ -436,16 +436,14 @@ class NeuralModuleNetwork(nn.Module):
         # parity tests: keep every 1-channel module output (attention map) of the last forward, see _read_attention_maps
         self.capture_attention_maps = False
         self.last_attention_maps = None
-        # classifier GEMMs (plain library GEMMs, nmn.py:75-83): "split" (default) = every fp32 operand split into two bf16
-        # halves (pnmn_split3_bf16, one pass), one cuBLAS tensor-core GEMM over the 3x contraction with fp32 accumulation
-        # (~16 mantissa bits per operand); "ieee" = cuBLAS/cuDNN fp32 SIMT like the reference; "tf32" = 10-bit operands
-        # (misses the gradient parity bar, kept for comparison only)
+        # classifier products (nmn.py:75-83): "split" (default) = pnmn_gemm_split, the repo's tcgen05 GEMM over bf16 (hi, lo)
+        # split operands (~16 mantissa bits per operand, fp32 accumulation).  "ieee" / "tf32" run the plain nn.Sequential on
+        # cuBLAS / cuDNN instead -- comparison runs only (scripts/classifier_bench.py): IEEE is 3.6x slower, TF32 misses the
+        # gradient parity bar
         self.classifier_math = os.environ.get("PNMN_CLASSIFIER", "tf32" if os.environ.get("PNMN_CLASSIFIER_TF32") == "1" else "split")
         if self.classifier_math not in ("split", "ieee", "tf32"):
             raise ValueError("PNMN_CLASSIFIER must be split, ieee or tf32")
         self.classifier_tf32 = self.classifier_math == "tf32"
-        # "split" runs through the fused nodes (_ConvReluPool, _BigLinear) unless PNMN_CLASSIFIER_FUSED=0 (comparison runs)
-        self._classifier_fused = os.environ.get("PNMN_CLASSIFIER_FUSED", "1") != "0"
 
     @classmethod
     def from_config(cls, config):
