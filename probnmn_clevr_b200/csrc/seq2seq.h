@@ -188,6 +188,7 @@ struct DecRowArgs {
 };
 cudaError_t launch_dec_row(const DecRowArgs& a, cudaStream_t st);
 cudaError_t launch_dec_out(const DecRowArgs& a, cudaStream_t st);
+cudaError_t launch_dec_out_post(const DecRowArgs& a, cudaStream_t st);   // logits already in a.logits (tensor-core GEMM)
 
 struct FinalizeArgs {
   SeqDims d;

@@ -59,7 +59,7 @@ struct Layout {
   int64_t h1f, c1f, h1op, g1, enc;         // encoder layer 1 (+ decoder slots appended to h1f / h1op)
   int64_t cdf, attop, gd;                  // decoder
   int64_t dh, dc, dh0, dc0, datt, denc, dout0, dgd, dg1, dg0, scale, dhp;
-  int64_t seed, gstage, gws, extent, rowmode;   // Philox key; incoming gradient padded to Bp; parameter gradients of this call
+  int64_t seed, gstage, gws, extent, rowmode, gemm_ws, gemm_ws_floats;   // Philox key; incoming gradient padded to Bp; parameter gradients of this call
   int64_t total;
 };
 
@@ -104,6 +104,9 @@ Layout make_layout(const pnmn_pg_desc* m, int B, int Tq, int Tp, int S, bool nee
   L.scale = take(256);
   L.seed = take(256);
   L.rowmode = take(4ll * d.Bp);
+  // scratch of the one tensor-core GEMM that computes the logits of every step of a teacher-forced pass (pnmn_gemm_split)
+  L.gemm_ws_floats = pnmn_gemm_split_workspace(S * d.Bp, d.Vt, kSH);
+  L.gemm_ws = take(4 * L.gemm_ws_floats);
   L.extent = param_extent(m);
   if (need_grad) {
     L.gstage = take(4ll * d.Bp);
@@ -429,7 +432,15 @@ static int pg_forward_impl(const pnmn_pg_desc* m, const float* params, const int
   g.len = nullptr; g.out_f = nullptr; g.out_op = nullptr;
   for (int t = 0; t <= d.S; ++t) {
     r.t = t;
-    if (t == d.S && r.defer_out) { CUDA_OK(launch_dec_out(r, st)); break; }
+    if (t == d.S && r.defer_out) {
+      // every step's logits in ONE tensor-core GEMM, [S * Bp, 256] x [Vt, 256]^T + bias (the per-(row, step) projection
+      // kernel re-read the whole output matrix in each of its 10 k CTAs: 180 us for the reconstructor's 41 steps)
+      if (pnmn_gemm_split(r.h_dec + L.slotf, kSH, 1, r.out_w, kSH, 1, r.logits, d.Vt, d.S * d.B, d.Vt, kSH, r.out_b, 0,
+                          at<float>(ws, L.gemm_ws), L.gemm_ws_floats, st))
+        return 1;
+      CUDA_OK(launch_dec_out_post(r, st));
+      break;
+    }
     CUDA_OK(launch_dec_row(r, st));
     if (t == d.S) break;
     g.t = t; g.K = 2 * kSH;

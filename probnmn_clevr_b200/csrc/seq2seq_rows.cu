@@ -140,36 +140,10 @@ cudaError_t launch_accumulate(float* dst, const float* src, int64_t n, cudaStrea
 //       (seq2seq_base.py:201-220), (b) t < S: choose the input token of step t (:188-198), dot-product
 //       attention over the encoder outputs with AllenNLP's masked_softmax, attended vector -> operand copy.
 // =====================================================================================================
-// output projection of decoding step tp from its hidden state `sh` (shared, 256 floats): logits, log-sum-exp, the chosen
-// token (greedy max or categorical sampling, seq2seq_base.py:201-220) and its log-probability.  Called by a whole CTA.
-__device__ __forceinline__ void dec_output_step(const DecRowArgs& a, const SeqDims& d, int b, int tp, const float* sh,
-                                                float* slg, float* satt, int* s_pred, int warp, int lane) {
-    // four vocabulary entries per round, their eight 16-byte loads issued before the first reduction
-    for (int v0 = warp; v0 < d.Vt; v0 += 32) {
-      float4 w0[4], w1[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int v = v0 + 8 * k;
-        if (v < d.Vt) {
-          w0[k] = __ldg(reinterpret_cast<const float4*>(a.out_w + static_cast<size_t>(v) * kSH + lane * 8));
-          w1[k] = __ldg(reinterpret_cast<const float4*>(a.out_w + static_cast<size_t>(v) * kSH + lane * 8 + 4));
-        }
-      }
-      const float* h = sh + lane * 8;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int v = v0 + 8 * k;
-        if (v < d.Vt) {
-          float acc = w0[k].x * h[0];
-          acc = fmaf(w0[k].y, h[1], acc); acc = fmaf(w0[k].z, h[2], acc); acc = fmaf(w0[k].w, h[3], acc);
-          acc = fmaf(w1[k].x, h[4], acc); acc = fmaf(w1[k].y, h[5], acc); acc = fmaf(w1[k].z, h[6], acc); acc = fmaf(w1[k].w, h[7], acc);
-          acc = warp_sum(acc);
-          if (lane == 0) slg[v] = acc + __ldg(a.out_b + v);
-        }
-      }
-    }
-    __syncthreads();
-    if (warp == 0) {
+// softmax / log-softmax over the Vt logits in `slg`, the chosen token (greedy max or categorical sampling,
+// seq2seq_base.py:201-220) and its log-probability, by ONE warp; `satt` = Vt floats of scratch
+__device__ __forceinline__ void pick_token(const DecRowArgs& a, const SeqDims& d, int b, int tp, const float* slg, float* satt,
+                                           int* s_pred, int lane, bool write_logits) {
       float m = -INFINITY;
       for (int v = lane; v < d.Vt; v += 32) m = fmaxf(m, slg[v]);
       m = warp_max(m);
@@ -240,14 +214,46 @@ __device__ __forceinline__ void dec_output_step(const DecRowArgs& a, const SeqDi
         else pred = kEnd;
       }
       const float lse = m + logf(sum);
-      for (int v = lane; v < d.Vt; v += 32) a.logits[(static_cast<size_t>(tp) * d.B + b) * d.Vt + v] = slg[v];
+      if (write_logits)
+        for (int v = lane; v < d.Vt; v += 32) a.logits[(static_cast<size_t>(tp) * d.B + b) * d.Vt + v] = slg[v];
       if (lane == 0) {
         a.lse[static_cast<size_t>(tp) * d.B + b] = lse;
         a.pred[static_cast<size_t>(tp) * d.B + b] = pred;
         a.logp[static_cast<size_t>(tp) * d.B + b] = slg[pred] - lse;
         *s_pred = pred;
       }
+}
+
+// output projection of decoding step tp from its hidden state `sh` (shared, 256 floats): logits, log-sum-exp, the chosen
+// token and its log-probability.  Called by a whole CTA.
+__device__ __forceinline__ void dec_output_step(const DecRowArgs& a, const SeqDims& d, int b, int tp, const float* sh,
+                                                float* slg, float* satt, int* s_pred, int warp, int lane) {
+    // four vocabulary entries per round, their eight 16-byte loads issued before the first reduction
+    for (int v0 = warp; v0 < d.Vt; v0 += 32) {
+      float4 w0[4], w1[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int v = v0 + 8 * k;
+        if (v < d.Vt) {
+          w0[k] = __ldg(reinterpret_cast<const float4*>(a.out_w + static_cast<size_t>(v) * kSH + lane * 8));
+          w1[k] = __ldg(reinterpret_cast<const float4*>(a.out_w + static_cast<size_t>(v) * kSH + lane * 8 + 4));
+        }
+      }
+      const float* h = sh + lane * 8;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int v = v0 + 8 * k;
+        if (v < d.Vt) {
+          float acc = w0[k].x * h[0];
+          acc = fmaf(w0[k].y, h[1], acc); acc = fmaf(w0[k].z, h[2], acc); acc = fmaf(w0[k].w, h[3], acc);
+          acc = fmaf(w1[k].x, h[4], acc); acc = fmaf(w1[k].y, h[5], acc); acc = fmaf(w1[k].z, h[6], acc); acc = fmaf(w1[k].w, h[7], acc);
+          acc = warp_sum(acc);
+          if (lane == 0) slg[v] = acc + __ldg(a.out_b + v);
+        }
+      }
     }
+    __syncthreads();
+    if (warp == 0) pick_token(a, d, b, tp, slg, satt, s_pred, lane, true);
     __syncthreads();
 }
 
@@ -373,6 +379,25 @@ __global__ void __launch_bounds__(256) dec_out_kernel(const DecRowArgs a) {
 }
 cudaError_t launch_dec_out(const DecRowArgs& a, cudaStream_t st) {
   dec_out_kernel<<<dim3(a.d.B, a.d.S), 256, 0, st>>>(a);
+  return cudaGetLastError();
+}
+
+// the same with the logits of every step already computed (one tensor-core GEMM over all (step, row) pairs,
+// pnmn_gemm_split in pnmn_pg_forward): one WARP per (row, step) does the softmax, the prediction and its log-probability
+__global__ void __launch_bounds__(256) dec_out_post_kernel(const DecRowArgs a) {
+  __shared__ float slg[8][kSMaxV], satt[8][kSMaxV];
+  __shared__ int s_pred[8];
+  const SeqDims& d = a.d;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * 8 + warp;
+  if (item >= d.B * d.S) return;
+  const int tp = item / d.B, b = item - tp * d.B;
+  for (int v = lane; v < d.Vt; v += 32) slg[warp][v] = a.logits[(static_cast<size_t>(tp) * d.B + b) * d.Vt + v];
+  __syncwarp();
+  pick_token(a, d, b, tp, slg[warp], satt[warp], &s_pred[warp], lane, false);
+}
+cudaError_t launch_dec_out_post(const DecRowArgs& a, cudaStream_t st) {
+  dec_out_post_kernel<<<(a.d.B * a.d.S + 7) / 8, 256, 0, st>>>(a);
   return cudaGetLastError();
 }
 
