@@ -42,4 +42,6 @@ timeout 600 ncu --profile-from-start off --set full --clock-control none --impor
     -f -o gpurun_out/wgradtc_${TAG} python /tmp/one_joint_step.py > gpurun_out/ncu_wgrad.log 2>&1; tail -2 gpurun_out/ncu_wgrad.log
 timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:step_gemm_tc -s 40 -c 2 \
     -f -o gpurun_out/stepgemm_${TAG} python /tmp/one_joint_step.py > gpurun_out/ncu_stepgemm.log 2>&1; tail -2 gpurun_out/ncu_stepgemm.log
+timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k regex:gemm_split_tc -c 3 \
+    -f -o gpurun_out/gemm_${TAG} python /tmp/one_joint_step.py > gpurun_out/ncu_gemm.log 2>&1; tail -2 gpurun_out/ncu_gemm.log
 ls -la gpurun_out/*.ncu-rep

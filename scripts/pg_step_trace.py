@@ -30,13 +30,12 @@ print("launches traced:", n, "graphs:", os.environ.get("PNMN_PG_NOGRAPH") is Non
 names = ["setup", "pdl_wait", "issued", "stage0", "stageN", "mma_done_issue", "acc_full", "tmem_ld", "epi_done", "cta_done"]
 kinds = {}
 for i in range(n):
-    key = int(tr[i, 15])
+    key = int(tr[i, 15])   # EPI * 1e6 + K * 1e3 + CTAs of the launch (K = 1024 of the data-gradient GEMMs overflows into EPI)
     rel = (tr[i, 1:11] - tr[i, 0]) / 1e3
-    extra = (tr[i, 11:14] - tr[i, 0]) / 1e3
     gap = (tr[i + 1, 0] - tr[i, 0]) / 1e3 if i + 1 < n else np.nan
-    kinds.setdefault(key, []).append(np.concatenate([rel, [gap], extra]))
+    kinds.setdefault(key, []).append(np.concatenate([rel, [gap]]))
 for key, rows in sorted(kinds.items()):
     a = np.array(rows)
     med = np.nanmedian(a, axis=0)
     print(f"EPI {key // 1000000} K {key // 1000 % 1000} CTAs {key % 1000}: {len(rows)} launches")
-    print("   " + "  ".join(f"{nm} {v:5.2f}" for nm, v in zip(names + ["next_start", "epi_math_done", "epi_barrier", "preloads_landed"], med)))
+    print("   " + "  ".join(f"{nm} {v:5.2f}" for nm, v in zip(names + ["next_start"], med)))
