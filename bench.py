@@ -544,19 +544,27 @@ def pg_leg(args, ctx, vocab, timed):
     gt_programs = ProgramSampler(vocab, seed=0).sample(B, 26).to(dev)
     half = B // 2
 
+    # question_coding "ours" mix (question_coding_trainer.py:120-152): the supervised half is teacher-forced, the rest is
+    # sampled.  The reference calls the model once per kind; here both kinds share ONE pass (Seq2SeqBase.forward_mixed: per
+    # row the results of the separate calls), as in the joint-training step
+    free = pg._max_decoding_steps
+    width = max(gt_programs.shape[1], free - 1)
+    targets = torch.zeros(B, width, dtype=torch.int64, device=dev)
+    targets[:half, : gt_programs.shape[1]] = gt_programs[:half]
+    teacher_rows = torch.zeros(B, dtype=torch.uint8, device=dev)
+    teacher_rows[:half] = 1
+
     def pg_step(i):
-        # question_coding "ours" mix (question_coding_trainer.py:120-152): supervised half teacher-forced, rest sampled
         pg.zero_grad(set_to_none=True)
-        sup = pg(questions[:half], gt_programs[:half], decoding_strategy="sampling")
-        uns = pg(questions[half:], decoding_strategy="sampling")
-        (sup["loss"].mean() + uns["loss"].mean()).backward()
+        out = pg.forward_mixed(questions, targets, teacher_rows, free_steps=free)
+        (out["loss"][:half].mean() + out["loss"][half:].mean()).backward()
 
     for i in range(3):
         pg_step(i)
     steps = max(3, min(args.steps, 10))
     ms = timed(pg_step, steps)
     return {"value": ctx["world"] * B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
-            "workload": ("question_coding_ours.yml mix at batch %d: %d rows teacher-forced + %d rows sampled (26 steps), "
+            "workload": ("question_coding_ours.yml mix at batch %d: %d rows teacher-forced + %d rows sampled (26 steps) in one mixed pass, "
                          "questions <= 40 tokens, fwd+bwd (BASELINE.json configs[2])" % (B, half, B - half))}
 
 
