@@ -9,7 +9,8 @@ Parity status: the ELBO / REINFORCE arithmetic is PINNED -- ``oracle/make_elbo_g
 ``probnmn/modules/elbo.py`` (unmodified source, loaded by path over a stub of ``probnmn.models``) on seeded per-row
 losses and stores inputs, outputs, gradients and the baseline trajectory in ``tests/golden/elbo_golden.npz``;
 ``tests/test_joint_cpu.py`` checks this restatement against it.  The trainer's ~40 lines are restated and cited.
-The model oracles keep their own status (NMN pinned; seq2seq / prior unpinned, AllenNLP absent).
+The model oracles keep their own status (NMN pinned; seq2seq / prior pinned against the reference's own files run over a
+shim of the absent AllenNLP, whose ~60 restated lines stay unpinned).
 """
 from typing import Dict, Optional
 

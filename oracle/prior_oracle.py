@@ -3,9 +3,11 @@
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may import this file.
 
-PARITY UNPINNED for the same reason as ``seq2seq_oracle.py``: the embedding / packed-LSTM wrapper / boundary-token /
-sequence-cross-entropy helpers are AllenNLP 0.9.0's (``requirements.txt:1``, absent here); they are restated from its
-published behaviour.  The in-repo logic is cited line by line.
+PINNED against the reference's own ``program_prior.py``, imported verbatim by ``oracle/make_seq2seq_golden.py`` and run
+over ``oracle/ref_shim/allennlp`` (``tests/golden/seq2seq_golden.npz``, key ``prior.*``; tests/test_seq2seq_oracle.py).
+The shim wraps torch's own ``nn.LSTM`` on packed sequences; its boundary-token / sequence-cross-entropy helpers are
+restated from AllenNLP 0.9.0's published source (``requirements.txt:1``, absent here) and stay unpinned against AllenNLP
+itself.  The in-repo logic is cited line by line.
 
 State-dict keys (AllenNLP names): ``_embedder.token_embedder_programs.weight`` (V,256, row 0 = padding),
 ``_encoder._module.{weight,bias}_{ih,hh}_l{0,1}``, ``_projection_layer.weight`` (256,256), ``_output_layer.weight``

@@ -42,3 +42,20 @@ def load_reference_nmn(root: str = "/root/reference"):
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)
     return mod.NeuralModuleNetwork
+
+
+def load_reference_seq2seq(root: str = "/root/reference"):
+    """Returns the reference's ``(ProgramGenerator, QuestionReconstructor, ProgramPrior)`` classes, imported normally
+    from ``root`` -- ``probnmn/modules/seq2seq_base.py``, ``probnmn/models/{program_generator,question_reconstructor,
+    program_prior}.py`` run VERBATIM -- over ``oracle/ref_shim/allennlp``, a restatement of the AllenNLP 0.9.0 classes
+    those files build on (``SimpleSeq2Seq._encode / _init_decoder_state / _prepare_output_projections``,
+    ``PytorchSeq2SeqWrapper`` around the real ``torch.nn.LSTM`` on packed sequences, ``DotProductAttention`` +
+    ``masked_softmax``, ``Embedding``, ``add_sentence_boundary_token_ids``, ``sequence_cross_entropy_with_logits``)."""
+    for p in (REPO, SHIM, root):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    load_reference_nmn(root)   # (patches SameModule.forward for torch 2.x before probnmn.models imports nmn.py)
+    pg = importlib.import_module("probnmn.models.program_generator")
+    qr = importlib.import_module("probnmn.models.question_reconstructor")
+    pr = importlib.import_module("probnmn.models.program_prior")
+    return pg.ProgramGenerator, qr.QuestionReconstructor, pr.ProgramPrior

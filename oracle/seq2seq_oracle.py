@@ -4,11 +4,16 @@ in plain fp32 PyTorch.
 
 Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may import this file.
 
-PARITY UNPINNED.  The token-choice / loss logic restated here is in the reference repository and is cited
-line by line (seq2seq_base.py).  The encoder, attention, decoder cell and the boundary-token / masked-softmax /
-sequence-cross-entropy helpers live in ``allennlp==0.9.0`` (``requirements.txt:1``), which is neither vendored
-under ``/root/reference`` nor installable here (no network), and the reference has no tests or golden vectors for
-them.  Their arithmetic is restated from AllenNLP 0.9.0's published behaviour:
+PINNING.  Everything that lives in the reference repository -- ``Seq2SeqBase.forward`` / ``_forward_loop`` /
+``_trim_predictions`` / ``_get_loss`` (seq2seq_base.py:101-341, cited line by line below) and the ProgramGenerator /
+QuestionReconstructor wrappers -- is PINNED: ``oracle/make_seq2seq_golden.py`` imports those files VERBATIM from
+/root/reference, runs them on seeded weights / inputs and records ``tests/golden/seq2seq_golden.npz``; this restatement
+reproduces those vectors to <= 1e-6 (logits, both losses, greedy tokens, gradients; tests/test_seq2seq_oracle.py).
+What those files build on lives in ``allennlp==0.9.0`` (``requirements.txt:1``), which is neither vendored under
+``/root/reference`` nor installable here (no network); the golden run supplies it through ``oracle/ref_shim/allennlp``:
+torch's own ``nn.LSTM`` on packed sequences and ``nn.LSTMCell`` (so the LSTM arithmetic is pinned to torch), plus ~60
+lines restated from AllenNLP 0.9.0's published source, which therefore remain PARITY UNPINNED against AllenNLP itself
+(SURVEY.md appendix C):
 
   * ``add_sentence_boundary_token_ids``: ``[@start@, w_1..w_n, @end@, 0...]``               (nn/util.py)
   * ``_encode``: mask = tokens != 0; embedding (padding_index 0); ``PytorchSeq2SeqWrapper(nn.LSTM)``: packed

@@ -191,6 +191,15 @@ class JointTrainingStep:
         teacher_rows = torch.zeros(nu + ns, dtype=torch.uint8, device=dev)
         teacher_rows[nu:] = 1
 
+        # (diagnostics, PNMN_DIAG_STALE_PROGRAMS=1: the module network runs an EARLIER step's sampled programs, compiled
+        # ahead of time -- what the step's timeline would be if the program compiler took no time.  Not the objective.)
+        stale = None
+        if os.environ.get("PNMN_DIAG_STALE_PROGRAMS") == "1":
+            if getattr(self, "_stale", None) is None:
+                self._stale = {}
+            stale = self._stale.get(nu)
+            if stale is not None:
+                self.nmn.precompile(stale)
         self._mark("start")
         # The objective is  gamma * mean(nmn_loss) - elbo + alpha * (mean(pg_loss_sup) + mean(qr_loss_sup))  with
         # -elbo = mean(qr_loss_u + (beta - centered) * pg_loss_u)  over the unsupervised rows (lp = -loss, elbo.py:61-89) and
@@ -240,7 +249,7 @@ class JointTrainingStep:
         with torch.cuda.stream(s_prior):
             prior = self.program_prior(sampled)                                        # elbo.py:256
             self._mark("prior_fwd_end(prior)")
-        nmn = self.nmn(img, sampled, ans)                                              # elbo.py:239
+        nmn = self.nmn(img, sampled if stale is None else stale, ans)                  # elbo.py:239
         self._mark("nmn_fwd_end")
         nmn_loss_rows = nmn["loss"].detach()
         if self.concurrent:
@@ -282,6 +291,9 @@ class JointTrainingStep:
             coef_pg.record_stream(s_pg)
             sampled.record_stream(s_prior)
         self._mark("backward_end")
+        if os.environ.get("PNMN_DIAG_STALE_PROGRAMS") == "1" and getattr(sampled, "_pnmn_host", None) is not None:
+            sampled._pnmn_host[1].synchronize()
+            self._stale[nu] = sampled._pnmn_host[0].clone()
 
         self.elbo.last_outputs = {
             "program_generator": {"predictions": sampled, "loss": pg_loss_u,

@@ -1,9 +1,9 @@
 """GPU parity of the CUDA ProgramGenerator (pnmn_pg_forward / pnmn_pg_backward through the nn.Module drop-in) against
 the CPU oracle ``oracle/seq2seq_oracle.py`` on the same seeded inputs.
 
-The oracle's AllenNLP-resident arithmetic is PARITY UNPINNED (allennlp==0.9.0 is absent; see the oracle's header);
-its LSTM / LSTMCell restatement is cross-checked against torch.nn.LSTM (packed) and nn.LSTMCell in
-tests/test_seq2seq_oracle.py.  Tolerances: logits / losses / encoder outputs 1e-3 relative (BASELINE.json north_star;
+The oracle is pinned against the reference's own seq2seq_base.py run verbatim over a shim of the absent allennlp==0.9.0
+(tests/golden/seq2seq_golden.npz, see the oracle's header); the last tests of this file compare the CUDA path with those
+golden vectors directly.  Tolerances: logits / losses / encoder outputs 1e-3 relative (BASELINE.json north_star;
 the split-fp16 GEMMs land around 1e-6), greedy tokens bit-exact, gradients 1e-3 relative in the global L2 sense.
 """
 import ctypes
@@ -222,3 +222,78 @@ def test_mixed_rows_equal_separate_calls_and_share_no_graph(vocab):
         ref = O.seq2seq_forward(sd, q[:20].cpu(), None, "sampling", 26, forced_choices=m["raw_predictions"][:20, :26].cpu())
     assert torch.equal(ref["predictions"], m["predictions"][:20, :26].cpu())
     assert rel(m["loss"][:20].detach().cpu(), ref["loss"]) < 1e-3
+
+
+# ---- against the reference's OWN seq2seq_base.py (tests/golden/seq2seq_golden.npz) -----------------------------------------
+import numpy as np  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "seq2seq_golden.npz")
+# (case, class, weight seed, gain) -- oracle/make_seq2seq_golden.py CASES; weights and inputs are regenerated from their seeds
+GOLDEN_CASES = [("pg", ProgramGenerator, 0, 1.0), ("pg_sharp", ProgramGenerator, 3, 4.0),
+                ("qr", QuestionReconstructor, 1, 1.0), ("qr_sharp", QuestionReconstructor, 2, 4.0)]
+
+
+@pytest.mark.parametrize("case,cls,seed,gain", GOLDEN_CASES)
+def test_cuda_path_matches_reference_golden(vocab, case, cls, seed, gain):
+    """The CUDA path against vectors recorded from the reference's own files (probnmn/modules/seq2seq_base.py etc., run
+    verbatim over the AllenNLP shim by oracle/make_seq2seq_golden.py): teacher-forced logits / loss 1e-3 (max-norm
+    relative), teacher-forced gradients 2e-3 per tensor (L2 where the whole tensor is stored, max-norm on the stored
+    slice otherwise), free-running greedy tokens IDENTICAL on the cases with realistic decision margins, loss 1e-3.
+    Includes an empty source row, an empty target row and a full-length row."""
+    g = np.load(GOLDEN)
+    model, sd = build(vocab, seed, gain=gain, cls=cls)
+    src, tgt = torch.from_numpy(g[f"{case}.source"]).cuda(), torch.from_numpy(g[f"{case}.target"]).cuda()
+    w = torch.from_numpy(g[f"{case}.weights"]).cuda()
+    model.train()
+    out = model(src, tgt, decoding_strategy="sampling")
+    e_logits = rel(out["logits"].detach().cpu(), torch.from_numpy(g[f"{case}.tf.logits"]))
+    e_loss = rel(out["loss"].detach().cpu(), torch.from_numpy(g[f"{case}.tf.loss"]))
+    assert e_logits < 1e-3 and e_loss < 1e-3
+    (out["loss"] * w).sum().backward()
+    worst = 0.0
+    for k, v in grads_of(model).items():
+        norm = float(g[f"{case}.tf.gradnorm.{k}"])
+        assert abs(float(v.double().norm()) - norm) <= 2e-3 * norm + 1e-9, k
+        if f"{case}.tf.grad.{k}" in g:
+            want = torch.from_numpy(g[f"{case}.tf.grad.{k}"])
+            e = float((v - want).norm() / (want.norm() + 1e-12))
+        else:
+            want = torch.from_numpy(g[f"{case}.tf.gradsub.{k}"])
+            e = float((v.reshape(-1)[::997] - want).abs().max() / (want.abs().max() + 1e-12))
+        worst = max(worst, e)
+        assert e < 2e-3, (k, e)
+    model.eval()
+    with torch.no_grad():
+        tf = model(src, tgt, decoding_strategy="greedy")
+        free = model(src, decoding_strategy="greedy")
+    agree = float((free["raw_predictions"].cpu() == torch.from_numpy(g[f"{case}.greedy.raw_predictions"])).float().mean())
+    print(f"{case}: logits {e_logits:.1e} loss {e_loss:.1e} worst gradient {worst:.1e} free-running token agreement {agree:.4f}")
+    assert torch.equal(tf["predictions"].cpu(), torch.from_numpy(g[f"{case}.tf.greedy_predictions"]))
+    if gain > 1.0:
+        assert torch.equal(free["raw_predictions"].cpu(), torch.from_numpy(g[f"{case}.greedy.raw_predictions"]))
+        assert torch.equal(free["predictions"].cpu(), torch.from_numpy(g[f"{case}.greedy.predictions"]))
+        assert rel(free["loss"].cpu(), torch.from_numpy(g[f"{case}.greedy.loss"])) < 1e-3
+        assert rel(free["logits"].cpu(), torch.from_numpy(g[f"{case}.greedy.logits"])) < 1e-3
+    else:
+        assert agree > 0.9
+
+
+def test_cuda_path_matches_reference_golden_edge_and_prior(vocab):
+    from probnmn_clevr_b200.program_prior import ProgramPrior
+    from probnmn_clevr_b200.synthetic import make_prior_state_dict
+    g = np.load(GOLDEN)
+    model, sd = build(vocab, 4)
+    sd["_output_projection_layer.bias"][3] = 50.0
+    model.load_state_dict(sd)
+    model.eval()
+    with torch.no_grad():
+        out = model(torch.from_numpy(g["end_first.source"]).cuda(), decoding_strategy="greedy")
+    assert torch.equal(out["predictions"].cpu(), torch.from_numpy(g["end_first.predictions"]))
+    assert float((out["loss"].cpu() - torch.from_numpy(g["end_first.loss"])).abs().max()) < 1e-6
+    prior = ProgramPrior(vocab)
+    prior.load_state_dict(make_prior_state_dict(44, hidden=256, seed=0), strict=True)
+    prior = prior.cuda().eval()
+    with torch.no_grad():
+        out = prior(torch.from_numpy(g["prior.programs"]).cuda())
+    np.testing.assert_allclose(out["loss"].cpu().numpy(), g["prior.loss"], rtol=1e-4, atol=1e-5)
+    assert list(out["predictions"].shape) == g["prior.predictions_shape"].tolist()

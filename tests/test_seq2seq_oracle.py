@@ -1,7 +1,7 @@
-"""CPU checks of the seq2seq oracle (oracle/seq2seq_oracle.py).  AllenNLP 0.9.0 is absent, so the oracle's restatement
-is PARITY UNPINNED against the reference itself; what CAN be pinned here is that its LSTM arithmetic equals the
-torch modules AllenNLP wraps (nn.LSTM over a packed sequence inside PytorchSeq2SeqWrapper, nn.LSTMCell) and that the
-in-repo logic (seq2seq_base.py:203-293) is restated faithfully on hand-checked cases."""
+"""CPU checks of the seq2seq oracle (oracle/seq2seq_oracle.py): against golden vectors recorded from the reference's OWN
+seq2seq_base.py / program_prior.py run verbatim over a shim of the absent AllenNLP 0.9.0 (second half of this file),
+against the torch modules AllenNLP wraps (nn.LSTM over a packed sequence inside PytorchSeq2SeqWrapper, nn.LSTMCell),
+and on hand-checked cases of the in-repo logic (seq2seq_base.py:203-293)."""
 import torch
 from torch import nn
 
@@ -63,3 +63,99 @@ def test_losses_on_a_hand_checked_case():
         assert abs(float(out["loss"][b]) - want) < 1e-5
     free = O.seq2seq_forward(sd, q, None, decoding_strategy="greedy", max_decoding_steps=7)
     assert free["predictions"].shape == (4, 7) and free["loss"].shape == (4,)
+
+
+# ---- pinned against the reference's own files (tests/golden/seq2seq_golden.npz, oracle/make_seq2seq_golden.py) ---------------
+import os  # noqa: E402
+
+import numpy as np  # noqa: E402
+import pytest  # noqa: E402
+
+from oracle import prior_oracle  # noqa: E402
+from probnmn_clevr_b200.synthetic import make_prior_state_dict  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "seq2seq_golden.npz")
+# (case, model kind, weight seed, gain, free-running steps) -- as in oracle/make_seq2seq_golden.py CASES
+GOLDEN_CASES = [("pg", "pg", 0, 1.0, 26), ("pg_sharp", "pg", 3, 4.0, 26), ("qr", "qr", 1, 1.0, 45), ("qr_sharp", "qr", 2, 4.0, 45)]
+
+
+def _rel(a, b):
+    return float((a - b).abs().max() / (b.abs().max() + 1e-12)) if a.numel() else 0.0
+
+
+def _golden_state_dict(kind, seed, gain):
+    vs, vt = (93, 44) if kind == "pg" else (44, 93)
+    return make_seq2seq_state_dict(vs, vt, seed=seed, gain=gain)
+
+
+def _check_grads(g, prefix, sd, tol):
+    for k, v in sd.items():
+        got = v.grad if v.grad is not None else torch.zeros_like(v)
+        norm = float(g[f"{prefix}.gradnorm.{k}"])
+        assert abs(float(got.double().norm()) - norm) <= tol * max(norm, 1e-12), k
+        if f"{prefix}.grad.{k}" in g:
+            want = torch.from_numpy(g[f"{prefix}.grad.{k}"])
+        else:
+            want, got = torch.from_numpy(g[f"{prefix}.gradsub.{k}"]), got.reshape(-1)[::997]
+        assert float((got - want).abs().max()) <= tol * (float(want.abs().max()) + 1e-12) + 1e-9, k
+
+
+@pytest.mark.parametrize("case,kind,seed,gain,steps", GOLDEN_CASES)
+def test_oracle_matches_reference_seq2seq_golden(case, kind, seed, gain, steps):
+    """The restatement against what the reference's OWN seq2seq_base.py computed (verbatim, over the AllenNLP shim) on
+    the same seeded weights and inputs: teacher-forced logits / loss / gradients, free-running greedy tokens / loss,
+    and the REINFORCE loss / gradients on the reference's sampled tokens."""
+    g = np.load(GOLDEN)
+    sd = {k: v.requires_grad_(True) for k, v in _golden_state_dict(kind, seed, gain).items()}
+    src, tgt = torch.from_numpy(g[f"{case}.source"]), torch.from_numpy(g[f"{case}.target"])
+    w = torch.from_numpy(g[f"{case}.weights"])
+    out = O.seq2seq_forward(sd, src, tgt, "greedy")
+    assert _rel(out["logits"].detach(), torch.from_numpy(g[f"{case}.tf.logits"])) < 1e-5
+    assert _rel(out["loss"].detach(), torch.from_numpy(g[f"{case}.tf.loss"])) < 1e-5
+    assert torch.equal(out["predictions"], torch.from_numpy(g[f"{case}.tf.greedy_predictions"]))
+    (out["loss"] * w).sum().backward()
+    _check_grads(g, f"{case}.tf", sd, 1e-4)
+    with torch.no_grad():
+        out = O.seq2seq_forward(sd, src, None, "greedy", steps)
+    assert torch.equal(out["raw_predictions"], torch.from_numpy(g[f"{case}.greedy.raw_predictions"]))
+    assert torch.equal(out["predictions"], torch.from_numpy(g[f"{case}.greedy.predictions"]))
+    assert _rel(out["loss"], torch.from_numpy(g[f"{case}.greedy.loss"])) < 1e-5
+    assert _rel(out["logits"], torch.from_numpy(g[f"{case}.greedy.logits"])) < 1e-5
+    for v in sd.values():
+        v.grad = None
+    raw = torch.from_numpy(g[f"{case}.sampled.raw_predictions"])
+    out = O.seq2seq_forward(sd, src, None, "sampling", steps, forced_choices=raw)
+    assert torch.equal(out["predictions"], torch.from_numpy(g[f"{case}.sampled.predictions"]))
+    assert _rel(out["loss"].detach(), torch.from_numpy(g[f"{case}.sampled.loss"])) < 1e-5
+    (out["loss"] * w).sum().backward()
+    _check_grads(g, f"{case}.sampled", sd, 1e-4)
+
+
+def test_oracle_matches_reference_golden_edge_and_prior():
+    g = np.load(GOLDEN)
+    sd = make_seq2seq_state_dict(93, 44, seed=4)
+    sd["_output_projection_layer.bias"][3] = 50.0
+    out = O.seq2seq_forward(sd, torch.from_numpy(g["end_first.source"]), None, "greedy", 26)
+    assert torch.equal(out["predictions"], torch.from_numpy(g["end_first.predictions"])) and int(out["predictions"].abs().sum()) == 0
+    assert torch.equal(out["loss"], torch.from_numpy(g["end_first.loss"]))
+    sdp = make_prior_state_dict(44, hidden=256, seed=0)
+    out = prior_oracle.prior_forward(sdp, torch.from_numpy(g["prior.programs"]))
+    assert _rel(out["loss"], torch.from_numpy(g["prior.loss"])) < 1e-5
+    assert list(out["predictions"].shape) == g["prior.predictions_shape"].tolist()
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/probnmn/modules/seq2seq_base.py"), reason="reference tree absent")
+def test_reference_files_run_verbatim_over_the_shim():
+    """Build container only: the reference's classes load the synthetic state dict strictly (same parameter names and
+    shapes as the drop-ins) and reproduce one golden number live."""
+    from oracle.ref_loader import load_reference_seq2seq
+    from probnmn_clevr_b200.vocabulary import Vocabulary
+    RefPG, RefQR, RefPrior = load_reference_seq2seq()
+    g = np.load(GOLDEN)
+    ref = RefPG(Vocabulary.clevr())
+    ref.load_state_dict(_golden_state_dict("pg", 0, 1.0), strict=True)
+    ref.eval()
+    with torch.no_grad():
+        out = ref(torch.from_numpy(g["pg.source"]), None, decoding_strategy="greedy")
+    assert torch.equal(out["predictions"], torch.from_numpy(g["pg.greedy.predictions"]))
+    assert _rel(out["loss"], torch.from_numpy(g["pg.greedy.loss"])) < 1e-6
