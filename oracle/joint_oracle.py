@@ -8,7 +8,12 @@ Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may imp
 Parity status: the ELBO / REINFORCE arithmetic is PINNED -- ``oracle/make_elbo_golden.py`` runs the reference's own
 ``probnmn/modules/elbo.py`` (unmodified source, loaded by path over a stub of ``probnmn.models``) on seeded per-row
 losses and stores inputs, outputs, gradients and the baseline trajectory in ``tests/golden/elbo_golden.npz``;
-``tests/test_joint_cpu.py`` checks this restatement against it.  The trainer's ~40 lines are restated and cited.
+``tests/test_joint_cpu.py`` checks this restatement against it.  The whole iteration is PINNED as well:
+``oracle/make_joint_golden.py`` calls the reference's own ``JointTrainingTrainer._do_iteration``
+(joint_training_trainer.py:128-198, loaded by path, unmodified) over the reference's own elbo.py and four model classes
+on seeded weights / batches and records ``tests/golden/joint_golden.npz`` (sampled programs, output dictionary, baseline
+over two iterations, clamped gradients of the three trained models); ``joint_iteration`` below reproduces it to 3e-6
+when it replays the sampled programs.
 The model oracles keep their own status (NMN pinned; seq2seq / prior pinned against the reference's own files run over a
 shim of the absent AllenNLP, whose ~60 restated lines stay unpinned).
 """

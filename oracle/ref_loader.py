@@ -32,12 +32,14 @@ def load_reference_nmn(root: str = "/root/reference"):
         if p not in sys.path:
             sys.path.insert(0, p)
     mods = importlib.import_module("probnmn.modules.nmn_modules")
-    src = textwrap.dedent(inspect.getsource(mods.SameModule.forward))
-    assert "the_idx[0, 0, 0, 0] / size" in src, "reference SameModule.forward changed"
-    ns = {}
-    exec(compile(src.replace("the_idx[0, 0, 0, 0] / size", "the_idx[0, 0, 0, 0] // size"), "<SameModule.forward //>", "exec"),
-         vars(mods), ns)
-    mods.SameModule.forward = ns["forward"]
+    if not getattr(mods.SameModule, "_pnmn_floor_div", False):   # (idempotent: the loaders below call this one too)
+        src = textwrap.dedent(inspect.getsource(mods.SameModule.forward))
+        assert "the_idx[0, 0, 0, 0] / size" in src, "reference SameModule.forward changed"
+        ns = {}
+        exec(compile(src.replace("the_idx[0, 0, 0, 0] / size", "the_idx[0, 0, 0, 0] // size"), "<SameModule.forward //>", "exec"),
+             vars(mods), ns)
+        mods.SameModule.forward = ns["forward"]
+        mods.SameModule._pnmn_floor_div = True
     spec = importlib.util.spec_from_file_location("probnmn_reference_nmn", os.path.join(root, "probnmn", "models", "nmn.py"))
     mod = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(mod)

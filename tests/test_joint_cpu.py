@@ -100,3 +100,49 @@ def test_synthetic_joint_batch_and_host_split():
     assert torch.equal(parts["unsup"]["question"], batch["question"][~sup]) and torch.equal(parts["sup"]["program"], batch["program"][sup])
     assert parts["unsup"]["image"].shape[0] == int((~sup).sum()) and "image" not in parts["sup"]
     assert 16 < int(sup.sum()) < 48
+
+
+# ---- the whole iteration against the reference's own trainer code (tests/golden/joint_golden.npz) ---------------------------
+JOINT_GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "joint_golden.npz")
+
+
+def test_joint_iteration_restatement_matches_reference_golden():
+    """oracle/joint_oracle.joint_iteration against what the reference's OWN ``JointTrainingTrainer._do_iteration`` computed
+    (joint_training_trainer.py:128-198 over the reference's JointTrainingElbo, ProgramGenerator, QuestionReconstructor,
+    ProgramPrior and NeuralModuleNetwork, all verbatim: oracle/make_joint_golden.py) on the same seeded weights and
+    batches, replaying the programs the reference sampled: output dictionary, REINFORCE baseline over two iterations,
+    clamped gradients of all three trained models."""
+    from oracle import joint_oracle
+    from oracle.make_joint_golden import BATCH, BATCH_SEEDS, CLAMP, HYPER, SUB, state_dicts
+    from probnmn_clevr_b200.synthetic import make_joint_batch
+    from probnmn_clevr_b200.vocabulary import Vocabulary
+    g = np.load(JOINT_GOLDEN)
+    vocab = Vocabulary.clevr()
+    torch.set_num_threads(os.cpu_count())
+    sds = {name: {k: v.clone().requires_grad_(True) for k, v in sd.items()} for name, sd in state_dicts(vocab).items()}
+    sds["program_prior"]["_output_layer.weight"] = sds["program_prior"]["_embedder.token_embedder_programs.weight"]
+    state = joint_oracle.ElboState(0.0)
+    for it, seed in enumerate(BATCH_SEEDS):
+        batch = make_joint_batch(vocab, BATCH, seed=seed)
+        for p in joint_oracle.trained_parameters(sds):
+            p.grad = None
+        raw = torch.from_numpy(g[f"it{it}.raw_programs"])
+        out = joint_oracle.joint_iteration(sds, vocab, batch, state, objective="ours", forced_programs=raw, **HYPER)
+        assert int(out["rows"]["nmn_valid"].sum()) == raw.shape[0]      # the pre-trained generator's samples are executable
+        for p in joint_oracle.trained_parameters(sds):
+            if p.grad is not None:
+                p.grad.clamp_(min=-CLAMP, max=CLAMP)
+        for group in ("elbo", "loss"):
+            for k, v in out[group].items():
+                want = float(g[f"it{it}.{group}.{k}"])
+                assert abs(v.item() - want) <= 1e-5 * max(1.0, abs(want)), (it, group, k)
+        assert abs(out["objective"].item() - float(g[f"it{it}.objective"])) <= 1e-5 * abs(float(g[f"it{it}.objective"]))
+        assert abs(state.baseline - float(g[f"it{it}.baseline"])) <= 1e-5 * abs(float(g[f"it{it}.baseline"]))
+        for name in ("program_generator", "question_reconstructor", "nmn"):
+            for k, p in sds[name].items():
+                got = torch.zeros_like(p) if p.grad is None else p.grad
+                norm = float(g[f"it{it}.gradnorm.{name}.{k}"])
+                assert abs(float(got.double().norm()) - norm) <= 2e-4 * norm + 1e-9, (it, name, k)
+                want = torch.from_numpy(g[f"it{it}.gradsub.{name}.{k}"])
+                sub = got.reshape(-1)[::(SUB if got.numel() > 4096 else 1)]
+                assert float((sub - want).abs().max()) <= 2e-4 * float(want.abs().max()) + 1e-9, (it, name, k)
