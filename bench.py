@@ -563,7 +563,17 @@ def pg_leg(args, ctx, vocab, timed):
         pg_step(i)
     steps = max(3, min(args.steps, 10))
     ms = timed(pg_step, steps)
+    # the LSTM is bound by its chain of dependent steps, not by a roofline -- reported as achieved
+    # FLOP/s (algorithmic forward FLOPs per sample: encoder 2 layers x (T_q + 1) x 2 x (256 + 256) x 1024, decoder
+    # steps x [2 x 768 x 1024 + 2 x 2 x T_src x 256 + 2 x 256 x 44]; forward + backward = 3 x forward) and as time per
+    # dependent step (encoder ticks + decoder steps, forward and backward)
+    t_src, dec_steps = 41, free
+    f_fwd = 2 * t_src * 2 * 512 * 1024 + dec_steps * (2 * 768 * 1024 + 4 * t_src * 256 + 2 * 256 * 44)
+    chain = 2 * ((t_src + 1) + dec_steps)     # wavefront of the two encoder layers + decoder steps, both directions
     return {"value": ctx["world"] * B * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps, "steps": steps,
+            "achieved_tflops": 3.0 * f_fwd * B / (ms / steps * 1e-3) / 1e12,
+            "dependent_steps_per_pass": chain, "us_per_dependent_step": 1e3 * (ms / steps) / chain,
+            "bound": "latency (chain of dependent steps; SURVEY.md 8d: no roofline fraction target)",
             "workload": ("question_coding_ours.yml mix at batch %d: %d rows teacher-forced + %d rows sampled (26 steps) in one mixed pass, "
                          "questions <= 40 tokens, fwd+bwd (BASELINE.json configs[2])" % (B, half, B - half))}
 

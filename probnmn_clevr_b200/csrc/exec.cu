@@ -162,6 +162,15 @@ exec_kernel(const uint8_t* __restrict__ tasks, const TaskMeta* __restrict__ meta
   // of every barrier it waits on as one bit per stage: "full" bits (the MMA issuer) start at 0, "empty" bits (the
   // producers) at 1 (= passes on a fresh barrier); a bit flips each time its stage is used.
   uint32_t pf_a = 0, pf_w = 0, pe_a = 0xfu, pe_w = 0x7u, n_conv = 0;
+  // Tried and dropped in round 2 (both parity-green, both measured on the 256-row workload, 1.278 ms before):
+  //  * task prefetch -- a convolution task claims its successor (atomicAdd on the list counter) and pulls its record into a
+  //    second record buffer with a bulk copy while its own MMAs drain, taking the counter round trip and the dependent
+  //    record load (~1 us) out of the CTA's serial chain: 1.325 ms.  A task claimed ~4 us early sits behind its claimer's
+  //    epilogue while another CTA is idle, and its dependency-independent prologue (first ring-full of weights) starts later.
+  //  * two MMA-issuing warps (2 and 4; two accumulators: one each; one accumulator: the six MMAs of a weight stage split
+  //    three / three into TMEM slots 0 and 1 that the epilogue adds; "empty" barriers with two arrivals): 1.305 ms.  The
+  //    issuing thread's ~110 cycles per MMA are not what bounds the issue phase -- the tensor pipe is shared with the
+  //    second resident CTA, and the extra waits / commits of a second issuer cost more than its parallel issue saves.
 
   for (;;) {
     // ---------------- scheduler: fetch the next task ----------------

@@ -80,6 +80,8 @@ class JointTrainingStep:
             reserved_sms = int(os.environ.get("PNMN_JOINT_RESERVE_SMS", "0"))
         self.reserved_sms = reserved_sms if concurrent else 0
         self.prestage = os.environ.get("PNMN_JOINT_PRESTAGE", "1") != "0"
+        # issue order of the backward passes (experiment, see _do_iteration_fused): 0 = each right behind its forward pass
+        self.order = int(os.environ.get("PNMN_JOINT_ORDER", "0"))
         # PNMN_JOINT_CHUNKS=k: the sampled programs are compiled as k independent plans on k host threads (the compile sits
         # between the generator's forward pass and the module network's: NeuralModuleNetwork._chunked_runs).  Measured at
         # k = 4: the module network's forward pass ends 0.23 ms earlier, the step is no faster (6.77 vs 6.94 ms) -- the step is
@@ -211,6 +213,7 @@ class JointTrainingStep:
         # Streams: generator, reconstructor and prior each get their own, the module network stays on the caller's; autograd
         # replays every pass on the stream its forward ran on.
         nu_f, ns_f = float(nu), float(ns)
+        order = self.order
         coef_qr = torch.empty(nu + ns, dtype=torch.float32, device=dev)
         coef_qr[:nu] = 1.0 / nu_f
         coef_qr[nu:] = self.alpha / ns_f
@@ -243,14 +246,32 @@ class JointTrainingStep:
             qr_fwd_done = torch.cuda.Event()
             qr_fwd_done.record()
             self._mark("qr_fwd_end(qr)")
-            torch.autograd.backward([qr["loss"]], [coef_qr])
-            self._mark("qr_bwd_end(qr)")
-            self._reduce_early([qr_m])
+            if order == 0:
+                torch.autograd.backward([qr["loss"]], [coef_qr])
+                self._mark("qr_bwd_end(qr)")
+                self._reduce_early([qr_m])
         with torch.cuda.stream(s_prior):
             prior = self.program_prior(sampled)                                        # elbo.py:256
             self._mark("prior_fwd_end(prior)")
         nmn = self.nmn(img, sampled if stale is None else stale, ans)                  # elbo.py:239
         self._mark("nmn_fwd_end")
+        if order:
+            # the reconstructor's backward pass waits for the module network's forward pass: an LSTM pass and the
+            # persistent executor only take turns on the SMs, while two LSTM passes run side by side
+            nmn_fwd_done = torch.cuda.Event()
+            nmn_fwd_done.record()
+            if order == 2:
+                torch.autograd.backward([nmn["loss"]], [coef_nmn])
+                self._mark("nmn_bwd_end")
+                self._reduce_early([self.nmn])
+                nmn_fwd_done = torch.cuda.Event()
+                nmn_fwd_done.record()
+            with torch.cuda.stream(s_qr):
+                if self.concurrent:
+                    s_qr.wait_event(nmn_fwd_done)
+                torch.autograd.backward([qr["loss"]], [coef_qr])
+                self._mark("qr_bwd_end(qr)")
+                self._reduce_early([qr_m])
         nmn_loss_rows = nmn["loss"].detach()
         if self.concurrent:
             main.wait_event(qr_fwd_done)
@@ -270,12 +291,17 @@ class JointTrainingStep:
         with torch.cuda.stream(s_pg):
             torch.autograd.backward([pg["loss"]], [coef_pg])
             self._mark("pg_bwd_end(pg)")
-        torch.autograd.backward([nmn["loss"]], [coef_nmn])
-        self._mark("nmn_bwd_end")
+        if order == 1 and self.concurrent:
+            main.wait_stream(s_pg)
+            main.wait_stream(s_qr)
+        if order != 2:
+            torch.autograd.backward([nmn["loss"]], [coef_nmn])
+            self._mark("nmn_bwd_end")
         # gradient averaging, issued in the order in which the gradients become final (NCCL runs a communicator's collectives
         # in issue order): reconstructor (above), module network -- its classifier gradients are already travelling, started
         # by hooks inside its backward pass --, generator last (its backward pass is the last to finish)
-        self._reduce_early([self.nmn])
+        if order != 2:
+            self._reduce_early([self.nmn])
         with torch.cuda.stream(s_pg):
             self._reduce_early([pg_m])
         pg_sup, qr_sup = pg_loss[nu:].mean(), qr_loss[nu:].mean()
