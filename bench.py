@@ -879,6 +879,9 @@ def run_joint(args, ctx):
                     "CUDA-core tasks and dependency waits; M is padded 196 -> 256 rows per sample (ceiling 0.766 of peak)",
             "flops_per_step": conv_flops, "kernel_ms_per_step": conv_ms, "launches_per_step": pln[1] / prof_steps,
             "m_padding_ceiling": 196.0 / 256.0, "traffic": traffic_per_launch(),
+            # in the joint step the executor's persistent CTAs leave some SMs to the LSTM passes that run next to it
+            # (JointTrainingStep.reserved_sms): `frac` stays against the whole chip's peak
+            "sms_left_to_other_streams": js.reserved_sms,
         },
         "kernel_ms_per_step": kernel_ms, "host_ms_per_step": host_ms_per_step,
         "programs_per_step": {"unsupervised_rows": unsup_rows, "executable": per_step["valid"],

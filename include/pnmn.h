@@ -76,6 +76,13 @@ pnmn_plan* pnmn_plan_create(const pnmn_model* m, const int64_t* programs_host, i
  * program is valid (default: the units of the valid samples are packed) -- for a forward pass whose program-independent part
  * ran ahead of the programs (pnmn_nmn_prestage). */
 #define PNMN_PLAN_INPUT_BY_ROW 1
+/* PNMN_PLAN_FORWARD_HALF (with need_grad = 0): the plan stands in for the FORWARD pass of the need_grad = 1 plan of the same
+ * programs and flags -- every forward tensor has the same place in the arenas in both, and pnmn_plan_sizes of this plan
+ * covers what the full plan's backward pass will allocate -- so a caller whose programs only become known inside the step
+ * (joint training: they are sampled by the generator, modules/elbo.py:230-239) can launch pnmn_nmn_forward from this plan,
+ * which compiles in half the time, compile the full plan meanwhile on another thread, and run pnmn_nmn_backward from that
+ * one on the same buffers, `blob` pointing to the full plan's uploaded tables. */
+#define PNMN_PLAN_FORWARD_HALF 2
 pnmn_plan* pnmn_plan_create_ex(const pnmn_model* m, const int64_t* programs_host, int batch, int length, int need_grad,
                                int flags);
 void pnmn_plan_destroy(pnmn_plan* p);
@@ -305,6 +312,9 @@ int pnmn_debug_set_trace(void* device_buffer, int64_t capacity_tasks);
  * {type, n_deps, deps[10], conv: n_samp, n_mt, MMAs per accumulator, flags | elementwise: op, part, 0, 0};
  * returns the number of tasks (host only, no device work) */
 int64_t pnmn_debug_plan_meta(const pnmn_plan* p, int pass, int32_t* out, int64_t cap_tasks);
+/* Raw records of a plan: pass 0 / 1 = the 128-byte task records of the forward / backward list (device pointers still
+ * symbolic), pass 2 = the 48-byte convolution configurations.  Returns the count; `out` may be NULL. */
+int64_t pnmn_debug_plan_records(const pnmn_plan* p, int pass, void* out, int64_t cap_records);
 /* attention maps (1-channel module outputs; probnmn/modules/nmn_modules.py:82-87,160-168,200-208 and the 1-channel results
  * of And / Or, :25-27,43-45) of a plan, for parity tests: 4 int32 per record {sample, index of the module call inside the
  * sample's program in execution order, token id, map unit}; after pnmn_nmn_forward map unit u is the top-left 14 x 14 block

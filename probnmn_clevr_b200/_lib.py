@@ -103,13 +103,14 @@ class PriorDesc(Structure):
 
 
 PLAN_INPUT_BY_ROW = 1   # PNMN_PLAN_INPUT_BY_ROW
+PLAN_FORWARD_HALF = 2   # PNMN_PLAN_FORWARD_HALF
 
 EXPORTS = [
     "pnmn_version", "pnmn_last_error", "pnmn_model_create", "pnmn_model_destroy", "pnmn_model_packed_floats",
     "pnmn_plan_create", "pnmn_plan_destroy", "pnmn_plan_upload", "pnmn_plan_valid", "pnmn_plan_sizes", "pnmn_plan_stats",
     "pnmn_nmn_forward", "pnmn_nmn_backward", "pnmn_debug_launch_conv", "pnmn_debug_launch_wgrad",
     "pnmn_debug_pack", "pnmn_debug_nchw_to_planes", "pnmn_debug_launch_elt", "pnmn_profile_enable",
-    "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times", "pnmn_debug_plan_meta", "pnmn_debug_plan_maps", "pnmn_debug_graph_stats",
+    "pnmn_profile_read", "pnmn_debug_set_trace", "pnmn_debug_host_times", "pnmn_debug_plan_meta", "pnmn_debug_plan_records", "pnmn_debug_plan_maps", "pnmn_debug_graph_stats",
     "pnmn_relu_pool_fwd", "pnmn_relu_pool_bwd", "pnmn_relu_pool_fwd_bias", "pnmn_launch_count", "pnmn_pg_workspace_bytes", "pnmn_pg_forward", "pnmn_pg_backward", "pnmn_pg_debug_layout", "pnmn_pg_forward_mixed",
     "pnmn_prior_workspace_bytes", "pnmn_prior_forward", "pnmn_clamp_adam", "pnmn_elbo_glue", "pnmn_set_reserved_sms", "pnmn_has_bringup_kernels", "pnmn_answer_loss_forward", "pnmn_answer_loss_backward", "pnmn_gemm_split", "pnmn_gemm_split_workspace", "pnmn_nmn_forward_f16", "pnmn_round_features_f16", "pnmn_plan_create_ex", "pnmn_plan_set_exec_ctas", "pnmn_model_pack_table_bytes", "pnmn_model_pack_table", "pnmn_model_ain_floats", "pnmn_nmn_prestage",
 ]
@@ -173,6 +174,8 @@ def lib() -> ctypes.CDLL:
     L.pnmn_debug_host_times.argtypes = [POINTER(ctypes.c_double)]
     L.pnmn_debug_plan_meta.restype = c_int64
     L.pnmn_debug_plan_meta.argtypes = [c_void_p, c_int, c_void_p, c_int64]
+    L.pnmn_debug_plan_records.restype = c_int64
+    L.pnmn_debug_plan_records.argtypes = [c_void_p, c_int, c_void_p, c_int64]
     L.pnmn_debug_plan_maps.restype = c_int64
     L.pnmn_debug_plan_maps.argtypes = [c_void_p, c_void_p, c_int64]
     L.pnmn_debug_graph_stats.argtypes = [POINTER(c_int64)]

@@ -558,6 +558,10 @@ struct pnmn_plan {
   bool persistent = true;     // one persistent executor launch per pass (exec.cu) vs one launch per level
   int exec_ctas = 0;          // > 0: cap of the executor's persistent grid for this plan (pnmn_plan_set_exec_ctas)
   bool input_by_row = false;  // stem-input unit of sample n is n (pnmn_nmn_prestage), not the running count of valid samples
+  // PNMN_PLAN_FORWARD_HALF: a need_grad = 0 plan that stands in for the forward pass of the need_grad = 1 plan of the same
+  // programs; its arena sizes include an upper bound of what that plan's backward pass allocates (units of P16 / P18 / P22)
+  bool forward_half = false;
+  int64_t bwd_bound16 = 0, bwd_bound18 = 0, bwd_bound22 = 0;
   void* uploaded_to = nullptr;  // device buffer that already holds this plan's task tables (pnmn_plan_upload)
   std::vector<TaskRec> ftask, btask;
   std::vector<TaskMeta> fmeta, bmeta;
@@ -771,6 +775,7 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
   pnmn_plan& p = *plan;
   p.m = m; p.B = B; p.L = L; p.need_grad = need_grad != 0;
   p.input_by_row = (flags & PNMN_PLAN_INPUT_BY_ROW) != 0;
+  p.forward_half = (flags & PNMN_PLAN_FORWARD_HALF) != 0 && !p.need_grad;
   p.valid.assign(B, 0);
   p.xin_unit.assign(B, -1);
   Builder bd(p);
@@ -805,6 +810,13 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
 
   std::vector<int> feat_unit(B, -1), y1s_unit(B, -1), dfeat_unit(B, -1);
   int64_t n_conv3 = 0, n_tokens = 0, flops = 0;
+  // The forward stages of ALL samples are emitted first, the backward stages in a second pass: every forward tensor then
+  // has the same arena unit (and every forward configuration the same id) whether or not the plan has a backward pass, so
+  // that a forward pass run from a need_grad = 0 plan (PNMN_PLAN_FORWARD_HALF, compiled in half the time) can be followed
+  // by the backward pass of the full plan of the same programs, compiled meanwhile.
+  struct SampleRec { int n; std::vector<OpRec> ops; int out, feat_val, xin; bool par; };
+  std::vector<SampleRec> emitted;
+  if (p.need_grad) emitted.reserve(B);
 
   for (int n = 0; n < B; ++n) {
     // ---------------- symbolic execution (nmn.py:198-233) ----------------
@@ -1012,8 +1024,30 @@ static pnmn_plan* plan_create_impl(const pnmn_model* m, const int64_t* programs,
       g.o = sym<float>(AR_FINAL, static_cast<int64_t>(n) * 128 * 196 * 4);
       fs.add_elt(bd.vals[out].strand >= 0 ? bd.vals[out].strand : st_f, g);
     }
+    if (p.forward_half) {
+      // upper bound of the units the backward stages of this sample will allocate (checked against the full plan in
+      // tests/test_plan_cpu.py): d(feat) twice, the stem's dZ, the output's gradient; per module the dZ / dX buffers of its
+      // convolutions and one gradient buffer per 128-channel value
+      p.bwd_bound16 += 4;
+      for (const OpRec& r : ops) {
+        switch (r.kind) {
+          case PNMN_TOK_AND: case PNMN_TOK_OR: p.bwd_bound16 += 3; break;
+          case PNMN_TOK_COMPARE: p.bwd_bound16 += 5; break;
+          case PNMN_TOK_RELATE: p.bwd_bound16 += 4; p.bwd_bound18 += 1; p.bwd_bound22 += 1; break;
+          case PNMN_TOK_SAME: break;
+          default: p.bwd_bound16 += 4; break;   // ATTENTION / QUERY
+        }
+      }
+    }
     if (!p.need_grad) continue;
+    emitted.push_back(SampleRec{n, std::move(ops), out, feat_val, xin, par});
+  }
 
+  for (SampleRec& sr : emitted) {
+    const int n = sr.n, out = sr.out, feat_val = sr.feat_val, xin = sr.xin;
+    const bool par = sr.par;
+    std::vector<OpRec>& ops = sr.ops;
+    const float* featp = bd.p16(feat_unit[n]);
     // ---------------- liveness / consumer counts ----------------
     bd.vals[out].live = true; bd.vals[out].ncons = 1;
     for (int k = static_cast<int>(ops.size()) - 1; k >= 0; --k) {
@@ -1506,9 +1540,9 @@ extern "C" int pnmn_plan_valid(const pnmn_plan* p, uint8_t* valid) {
 
 extern "C" int pnmn_plan_sizes(const pnmn_plan* p, int64_t* s) {
   for (int i = 0; i < PNMN_SZ_COUNT; ++i) s[i] = 0;
-  s[PNMN_SZ_ARENA16] = (2 * kGuard + std::max<int64_t>(p->n16, 1) * kUnit16) / 4;
-  s[PNMN_SZ_ARENA18] = (2 * kGuard + std::max<int64_t>(p->n18, 1) * kUnit18) / 4;
-  s[PNMN_SZ_ARENA22] = (2 * kGuard + std::max<int64_t>(p->n22, 1) * kUnit22) / 4;
+  s[PNMN_SZ_ARENA16] = (2 * kGuard + std::max<int64_t>(p->n16 + p->bwd_bound16, 1) * kUnit16) / 4;
+  s[PNMN_SZ_ARENA18] = (2 * kGuard + std::max<int64_t>(p->n18 + p->bwd_bound18, 1) * kUnit18) / 4;
+  s[PNMN_SZ_ARENA22] = (2 * kGuard + std::max<int64_t>(p->n22 + p->bwd_bound22, 1) * kUnit22) / 4;
   s[PNMN_SZ_MAPS] = p->nmaps * 256;
   s[PNMN_SZ_DMAPS] = p->nmaps * 256;
   s[PNMN_SZ_IDX] = std::max<int64_t>(p->nidx, 1);
@@ -1805,6 +1839,21 @@ extern "C" int64_t pnmn_debug_plan_meta(const pnmn_plan* p, int pass, int32_t* o
       o[12] = t.op; o[13] = t.part; o[14] = 0; o[15] = 0;
     }
   }
+  return n;
+}
+
+// The raw (unresolved) records of a plan: pass 0 / 1 = the 128-byte task records of the forward / backward list, pass 2 =
+// the convolution configurations.  Returns the record count; `out` (may be NULL) receives min(count, cap) records.  Tests
+// use it to check that a PNMN_PLAN_FORWARD_HALF plan and the full plan of the same programs agree record for record.
+extern "C" int64_t pnmn_debug_plan_records(const pnmn_plan* p, int pass, void* out, int64_t cap_records) {
+  if (pass == 2) {
+    const int64_t n = static_cast<int64_t>(p->cfgs.size());
+    if (out) std::memcpy(out, p->cfgs.data(), static_cast<size_t>(std::min(n, cap_records)) * sizeof(ConvCfg));
+    return n;
+  }
+  const std::vector<TaskRec>& r = pass ? p->btask : p->ftask;
+  const int64_t n = static_cast<int64_t>(r.size());
+  if (out) std::memcpy(out, r.data(), static_cast<size_t>(std::min(n, cap_records)) * sizeof(TaskRec));
   return n;
 }
 

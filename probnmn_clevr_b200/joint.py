@@ -75,9 +75,11 @@ class JointTrainingStep:
         self.optimizer = FusedClampAdam(params, lr=lr, weight_decay=weight_decay, clamp=clamp, modules=trained)
         self.concurrent = concurrent
         self.fused = fused
-        # SMs the module executor leaves to the LSTM passes running next to it (pnmn_set_reserved_sms, include/pnmn.h)
+        # SMs the module executor's persistent kernels leave to the LSTM passes running next to them
+        # (pnmn_set_reserved_sms, include/pnmn.h).  Measured with bench.py (two runs each, 1 x B200): 0 SMs 6.83 / 6.86 ms
+        # per step, 8: 6.74 / 6.72, 12: 6.69 / 6.69, 16: 6.65 / 6.66, 20: 6.68 / 6.69, 32: 6.95, 40: 7.36.
         if reserved_sms is None:
-            reserved_sms = int(os.environ.get("PNMN_JOINT_RESERVE_SMS", "0"))
+            reserved_sms = int(os.environ.get("PNMN_JOINT_RESERVE_SMS", "16"))
         self.reserved_sms = reserved_sms if concurrent else 0
         self.prestage = os.environ.get("PNMN_JOINT_PRESTAGE", "1") != "0"
         # issue order of the backward passes (experiment, see _do_iteration_fused): 0 = each right behind its forward pass

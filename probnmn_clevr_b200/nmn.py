@@ -267,8 +267,28 @@ class _Run:
         self.extra_ws = extra_ws    # workspace that holds the prestaged inputs of ALL chunks (released with this run)
         self.blob = None
         self.xin_off = 0
+        # split compile (NeuralModuleNetwork._single_run): `plan` is the forward half, `full` the future of
+        # (full plan, its uploaded task tables, upload event) that the backward pass runs from
+        self.full = None
+
+    def take_full(self):
+        """(full plan, device blob, upload event) of a split compile; the run owns them from here on."""
+        plan, blob, event = self.full.result()
+        self.full = None
+        if self.plan is not None:
+            L.lib().pnmn_plan_destroy(self.plan)
+        self.plan = plan
+        if getattr(self, "pool_blob", None) is not None:
+            _BLOBS.release(self.pool_blob)
+        self.pool_blob = blob
+        return plan, blob, event
 
     def close(self):
+        if self.full is not None:    # the backward pass never ran: the full plan still has to be collected
+            try:
+                self.take_full()
+            except Exception:
+                self.full = None
         if self.plan is not None:
             L.lib().pnmn_plan_destroy(self.plan)
             self.plan = None
@@ -340,6 +360,13 @@ class _ExecutorFn(torch.autograd.Function):
             fork = None
             for run in runs:
                 run.bufs.grads = target.data_ptr()
+                if run.full is not None:
+                    # split compile: the forward pass ran from the forward-half plan; the full plan of the same programs
+                    # (same arena layout) was compiled and uploaded meanwhile on a helper thread
+                    plan, blob, event = run.take_full()
+                    current.wait_event(event)
+                    run.bufs.blob = blob.data_ptr()
+                    model.last_plan_stats = model._plan_info(plan, run.hi - run.lo)[2]
                 st = current
                 if run.stream is not None:
                     if fork is None:
@@ -432,6 +459,9 @@ class NeuralModuleNetwork(nn.Module):
         # > 1: a batch's programs are compiled as this many independent plans on as many host threads (_chunked_runs)
         self.compile_chunks = int(os.environ.get("PNMN_COMPILE_CHUNKS", "1"))
         self._chunk_streams = None
+        # a training-mode forward whose programs were not compiled ahead (precompile) launches from the forward-half plan and
+        # takes its backward pass from the full plan compiled meanwhile (_single_run); PNMN_SPLIT_COMPILE=0: one plan, inline
+        self.split_compile = os.environ.get("PNMN_SPLIT_COMPILE", "1") != "0"
         self._pack_table: Optional[torch.Tensor] = None
         # parity tests: keep every 1-channel module output (attention map) of the last forward, see _read_attention_maps
         self.capture_attention_maps = False
@@ -672,8 +702,19 @@ class NeuralModuleNetwork(nn.Module):
         B = programs_host.shape[0]
         pre = self._take_precompiled(programs_host, need_grad) if staged is None else None
         pre_blob = pre_event = None
+        full = None
         if pre is None:
-            plan = self._compile(programs_host, need_grad, None, by_row=staged is not None)
+            if need_grad and self.split_compile:
+                # The programs have only just become known and the executor waits for this thread: compile the forward
+                # half alone (a third of the time), let a helper thread compile + upload the full plan while the forward
+                # pass runs, and take the backward pass from that one (PNMN_PLAN_FORWARD_HALF, include/pnmn.h).
+                dev = features.device
+                if self._upload_stream is None or self._upload_stream.device != dev:
+                    self._upload_stream = torch.cuda.Stream(dev)
+                full = _compile_pool().submit(self._compile_and_upload, programs_host, True, dev, staged is not None)
+                plan = self._compile(programs_host, False, None, by_row=staged is not None, forward_half=True)
+            else:
+                plan = self._compile(programs_host, need_grad, None, by_row=staged is not None)
         else:
             plan, pre_blob, pre_event = pre
         valid_host, sizes, stats = self._plan_info(plan, B)
@@ -696,6 +737,7 @@ class NeuralModuleNetwork(nn.Module):
         run.blob = blob
         run.xin_off = int(stats[15])
         run.pool_blob = pre_blob  # goes back to the pool when the run is closed (after the backward pass)
+        run.full = full
         return [run], valid_host, stats
 
     def _chunked_runs(self, features, programs_host, need_grad, staged, k):
@@ -761,11 +803,11 @@ class NeuralModuleNetwork(nn.Module):
         return [(int(rec[i, 0]), int(rec[i, 1]), int(rec[i, 2]), maps[i]) for i in range(n)]
 
     # ---- program compiler -------------------------------------------------------------------------------------------
-    def _compile(self, programs_host: torch.Tensor, need_grad: bool, device, by_row: bool = False):
+    def _compile(self, programs_host: torch.Tensor, need_grad: bool, device, by_row: bool = False, forward_half: bool = False):
         lib = L.lib()
         B, Lp = programs_host.shape
         ptr = ctypes.cast(programs_host.data_ptr(), ctypes.POINTER(ctypes.c_int64))
-        flags = L.PLAN_INPUT_BY_ROW if by_row else 0
+        flags = (L.PLAN_INPUT_BY_ROW if by_row else 0) | (L.PLAN_FORWARD_HALF if forward_half else 0)
         if device is not None:  # helper thread: the pinned staging buffers and their events belong to this device
             with torch.cuda.device(device):
                 plan = lib.pnmn_plan_create_ex(self._model_handle, ptr, B, Lp, 1 if need_grad else 0, flags)
@@ -775,11 +817,11 @@ class NeuralModuleNetwork(nn.Module):
             raise RuntimeError("pnmn_plan_create failed: " + lib.pnmn_last_error().decode())
         return plan
 
-    def _compile_and_upload(self, programs_host: torch.Tensor, need_grad: bool, device):
+    def _compile_and_upload(self, programs_host: torch.Tensor, need_grad: bool, device, by_row: bool = False):
         """Helper-thread half of ``precompile``: compile, then copy the task tables to the device on the upload stream, so
         that the forward pass itself issues no host -> device copy (one queued inside forward would wait for the compute
         stream and then find the copy engine busy with the next batch's features)."""
-        plan = self._compile(programs_host, need_grad, device)
+        plan = self._compile(programs_host, need_grad, device, by_row=by_row)
         if device is None or os.environ.get("PNMN_NO_EARLY_UPLOAD"):  # (switch: comparison runs)
             return plan, None, None
         lib = L.lib()

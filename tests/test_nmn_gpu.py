@@ -223,6 +223,44 @@ def test_precompile_lookahead_changes_nothing(model):
         assert float((g - gref).abs().max()) <= 1e-5 * float(gref.abs().max())
 
 
+def test_split_compile_changes_nothing(model):
+    """Training-mode forward without a precompiled plan: the forward pass launches from the forward-half plan
+    (PNMN_PLAN_FORWARD_HALF) and the backward pass runs from the full plan compiled meanwhile on a helper thread.  Same
+    bits forward, same gradients to rounding as one plan compiled inline; with a prestaged input as well; and a forward
+    pass whose backward never runs still collects its full plan."""
+    vocab = model.vocabulary
+    sampler = ProgramSampler(vocab, seed=29)
+    programs = torch.cat([sampler.sample(44, 26), sampler.garbage(4, 26)])
+    feats, answers = make_features(48, 6).cuda(), make_answers(48, 6).cuda()
+    model.train()
+
+    def step(split, prestage=False):
+        model.split_compile = split
+        model.zero_grad()
+        if prestage:
+            model.prestage(feats)
+        out = model(feats, programs, answers)
+        stats_fwd = list(model.last_plan_stats)
+        out["loss"].mean().backward()
+        g = torch.cat([p.grad.flatten() for p in model.parameters() if p.grad is not None])
+        return out, g.clone(), stats_fwd, list(model.last_plan_stats)
+
+    try:
+        ref, gref, _, stats_ref = step(False)
+        for prestage in (False, True):
+            out, g, stats_fwd, stats_full = step(True, prestage)
+            assert torch.equal(out["predictions"], ref["predictions"]) and torch.equal(out["loss"], ref["loss"])
+            assert float((g - gref).abs().max()) <= 1e-5 * float(gref.abs().max())
+            assert stats_fwd[10] == 0 and stats_full[8] == stats_ref[8] and stats_full[10] == stats_ref[10] > 0
+        model.split_compile = True
+        out = model(feats, programs, answers)     # never backpropagated
+        del out
+        out, g, _, _ = step(True)
+        assert torch.equal(out["loss"], ref["loss"])
+    finally:
+        model.split_compile = True
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # attention maps (north_star: "within 1e-3 ... (answer logits, attention maps)")
 # ---------------------------------------------------------------------------------------------------------------------

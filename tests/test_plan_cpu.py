@@ -110,3 +110,47 @@ def test_malformed_binary_programs_fall_back_to_one_chain(model):
     _check_list(fwd)
     _check_list(bwd)
     assert valid.all()
+
+
+def _records(plan, which, width):
+    lib = L.lib()
+    n = lib.pnmn_debug_plan_records(plan, which, None, 0)
+    buf = np.zeros((n, width), dtype=np.uint8)
+    if n:
+        lib.pnmn_debug_plan_records(plan, which, buf.ctypes.data, n)
+    return buf
+
+
+@pytest.mark.parametrize("flags", [0, L.PLAN_INPUT_BY_ROW])
+def test_forward_half_plan_is_the_forward_pass_of_the_full_plan(model, flags):
+    """PNMN_PLAN_FORWARD_HALF (include/pnmn.h): the need_grad = 0 stand-in must agree with the full plan of the same
+    programs record for record -- same forward task list (same arena units, same configuration ids, same dependencies),
+    same validity -- and its arena sizes must cover what the full plan's backward pass allocates."""
+    lib = L.lib()
+    vocab = model.vocabulary
+    for seed in range(12):
+        sampler = ProgramSampler(vocab, seed=seed)
+        programs = torch.cat([sampler.sample(40 + 9 * seed, 26), sampler.garbage(6, 26)]).contiguous()
+        B, Lp = programs.shape
+        ptr = ctypes.cast(programs.data_ptr(), ctypes.POINTER(ctypes.c_int64))
+        half = lib.pnmn_plan_create_ex(model._model_handle, ptr, B, Lp, 0, flags | L.PLAN_FORWARD_HALF)
+        full = lib.pnmn_plan_create_ex(model._model_handle, ptr, B, Lp, 1, flags)
+        try:
+            rec_h, rec_f = _records(half, 0, 128), _records(full, 0, 128)
+            assert rec_h.shape == rec_f.shape and (rec_h == rec_f).all()
+            cfg_h, cfg_f = _records(half, 2, 48), _records(full, 2, 48)
+            assert len(cfg_h) <= len(cfg_f) and (cfg_h == cfg_f[: len(cfg_h)]).all()
+            sizes_h, sizes_f = (ctypes.c_int64 * L.SZ_COUNT)(), (ctypes.c_int64 * L.SZ_COUNT)()
+            lib.pnmn_plan_sizes(half, sizes_h)
+            lib.pnmn_plan_sizes(full, sizes_f)
+            for slot in (L.SZ_ARENA16, L.SZ_ARENA18, L.SZ_ARENA22, L.SZ_MAPS, L.SZ_DMAPS, L.SZ_IDX, L.SZ_AIN):
+                assert sizes_h[slot] >= sizes_f[slot], (seed, slot)
+            assert sizes_h[L.SZ_ARENA16] < 2 * sizes_f[L.SZ_ARENA16]      # ... without doubling the footprint
+            valid_h, valid_f = np.zeros(B, np.uint8), np.zeros(B, np.uint8)
+            lib.pnmn_plan_valid(half, valid_h.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+            lib.pnmn_plan_valid(full, valid_f.ctypes.data_as(ctypes.POINTER(ctypes.c_uint8)))
+            assert (valid_h == valid_f).all()
+            assert lib.pnmn_debug_plan_records(half, 1, None, 0) == 0
+        finally:
+            lib.pnmn_plan_destroy(half)
+            lib.pnmn_plan_destroy(full)
