@@ -153,7 +153,10 @@ class FusedClampAdam(torch.optim.Optimizer):
 
     # ---- step ----------------------------------------------------------------------------------------------------------
     @torch.no_grad()
-    def step(self, closure=None):
+    def step(self, closure=None, only=None):
+        """``only``: an optional ``nn.Module`` -- step just the parameter ranges that belong to it (a caller that knows when
+        each model's gradients are final can update that model right away, on the stream its backward pass ran on)."""
+        mine = None if only is None else {id(p) for p in only.parameters()}
         loss = None
         if closure is not None:
             with torch.enable_grad():
@@ -166,6 +169,8 @@ class FusedClampAdam(torch.optim.Optimizer):
             lr, (b1, b2), eps, wd = g["lr"], g["betas"], g["eps"], g["weight_decay"]
             for r in ranges:
                 p0 = r.params[0]
+                if mine is not None and id(p0) not in mine:
+                    continue
                 grads = [p.grad for p in r.params]
                 pflat = r.pflat if r.uniform else None
                 r.calls += 1
@@ -203,7 +208,7 @@ class FusedClampAdam(torch.optim.Optimizer):
                     steps = {int(self.state[p]["step"]) for p in r.params}
                     if len(steps) == 1:
                         r.uniform, r.step = True, steps.pop()
-        self.launches_last_step = launches
+        self.launches_last_step = launches if only is None else self.launches_last_step + launches
         return loss
 
     def zero_grad(self, set_to_none: bool = True) -> None:
