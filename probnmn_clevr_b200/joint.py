@@ -116,8 +116,9 @@ class JointTrainingStep:
             # (PNMN_JOINT_PRIORITY=1 gives the LSTM passes' streams high priority -- a pending CTA of a step kernel is then
             # placed before pending CTAs of the module network's bulk kernels.  Measured: the passes finish earlier, the
             # module network later, the step 0.2-0.3 ms slower: 6.87 vs 7.08 ms.  Default off.)
-            prio = -1 if os.environ.get("PNMN_JOINT_PRIORITY", "0") == "1" else 0
-            self._side_streams = tuple(torch.cuda.Stream(dev, priority=prio) for _ in range(3))
+            mode = os.environ.get("PNMN_JOINT_PRIORITY", "0")   # "2": the generator's stream only (its backward pass ends the step)
+            prios = {"1": (-1, -1, -1), "2": (-1, 0, 0)}.get(mode, (0, 0, 0))
+            self._side_streams = tuple(torch.cuda.Stream(dev, priority=pr) for pr in prios)
         return self._side_streams
 
     def _mark(self, label: str) -> None:
