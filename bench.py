@@ -627,6 +627,9 @@ def joint_config(args, world):
                    "synthetic question->program mapping (probnmn_clevr_b200/assets/pg_synthetic_fp16.npz, scripts/pretrain_pg.py)",
         "l2": "inputs larger than L2 (~103 MB of features per step, two alternating batches)",
         "parallelism": f"dp{world}",
+        "step_pipelining": "the module network's backward pass, gradient average and clamp + Adam of step i are issued at the "
+                           "start of step i+1, next to the generator's forward pass (JointTrainingStep(defer_nmn=True); same "
+                           "arithmetic, flushed inside every timed region; PNMN_JOINT_DEFER_NMN=0 switches it off)",
     }
 
 
@@ -669,8 +672,12 @@ def run_joint(args, ctx):
         models[name] = m.to(dev).train()
     if world > 1 and os.environ.get("PNMN_NO_GRAD_OVERLAP") is None:
         models["nmn"].enable_gradient_overlap()
+    # defer_nmn: the module network's backward pass + update of step i is issued with step i + 1 (same arithmetic;
+    # JointTrainingStep.flush() issues what is pending -- the timed regions below start and end with a flush, so each holds
+    # exactly K forward and K backward passes of every model).  PNMN_JOINT_DEFER_NMN=0: every step complete in itself
     js = JointTrainingStep(models["program_generator"], models["question_reconstructor"], models["nmn"],
-                           models["program_prior"], concurrent=os.environ.get("PNMN_NO_STREAMS") is None, **JOINT)
+                           models["program_prior"], concurrent=os.environ.get("PNMN_NO_STREAMS") is None,
+                           defer_nmn=os.environ.get("PNMN_JOINT_DEFER_NMN", "1") != "0", **JOINT)
     nmn = models["nmn"]
 
     # two alternating batches per rank, split on the host the way an input pipeline would (joint.split_batch), pinned
@@ -698,8 +705,15 @@ def run_joint(args, ctx):
     def account():
         st = nmn.last_plan_stats
         plan_flops["n"] += 1
-        plan_flops["flops"] += st[8] + st[10]
+        plan_flops["flops"] += st[8]      # forward convolution FLOPs of the plan the forward pass just ran from
         plan_flops["valid"] += st[0]; plan_flops["convs"] += st[1]; plan_flops["tokens"] += st[2]
+
+    def account_backward(st):
+        # (called when a backward pass of the module network is launched -- with a deferred backward pass that is one step
+        # later than its forward pass, and with the split compile the forward plan does not know the backward FLOPs)
+        plan_flops["flops"] += st[10]
+
+    nmn.backward_stats_hook = account_backward
 
     def resident_step(i):
         throttle()
@@ -716,6 +730,7 @@ def run_joint(args, ctx):
         resident_step(i)
     # (weights as the last warm-up step sees them: its optimizer update moves every weight by ~lr along sign(gradient), which
     # shifts the logits by ~1e-2 -- the oracle must run on the weights the forward pass used)
+    js.flush()   # (a deferred update of the module network belongs to the weights "as the last warm-up step sees them")
     sd_now = {k: v.detach().cpu().clone() for k, v in nmn.state_dict().items()} if rank == 0 else None
     resident_step(W - 1)
     torch.cuda.synchronize()
@@ -748,7 +763,10 @@ def run_joint(args, ctx):
     issued["wait_s"] = 0.0
     for k in plan_flops:
         plan_flops[k] = 0
-    ms = timed(resident_step, args.steps)
+    # (JointTrainingStep.defer_nmn: a step may leave the module network's backward pass + update to be issued with the next
+    # step; what is pending is issued BEFORE the timer starts and again before it stops, so the region holds exactly K of them)
+    js.flush()
+    ms = timed(resident_step, args.steps, js.flush)
     host_issue_ms = timed.host_issue_ms - issued["wait_s"] * 1e3
     own_launches = int(lib.pnmn_launch_count(1))
     sampler.stop_flag = True
@@ -786,7 +804,8 @@ def run_joint(args, ctx):
     for i in range(W):
         e2e_step(i)
     loss_values.clear()
-    ms_e2e = timed(lambda j: e2e_step(W + j), args.steps, lambda: read_loss(total["n"] - 1))
+    js.flush()
+    ms_e2e = timed(lambda j: e2e_step(W + j), args.steps, lambda: (js.flush(), read_loss(total["n"] - 1)))
     assert len(loss_values) == args.steps + 1 and all(v == v for v in loss_values), "every step's objective must have been read back"
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     torch.cuda.synchronize()
@@ -832,7 +851,8 @@ def run_joint(args, ctx):
         for i in range(W):
             cached_step(i)
         loss_values.clear()
-        ms_c = timed(lambda j: cached_step(W + j), args.steps, lambda: read_loss(total["n"] - 1))
+        js.flush()
+        ms_c = timed(lambda j: cached_step(W + j), args.steps, lambda: (js.flush(), read_loss(total["n"] - 1)))
         e2e_cached = {"value": world * args.batch * args.steps / (ms_c * 1e-3), "unit": UNIT, "ms_per_step": ms_c / args.steps,
                       "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host_idx[0]), "d2h_bytes_per_step": 4,
                       "cache_bytes": cache.features.numel() * 2,
@@ -845,9 +865,11 @@ def run_joint(args, ctx):
     kinds = ["elementwise", "exec_kernel", "conv_tc<1,3>", "wgrad_tc", "bias_grad", "pack_weights", "nchw_to_planes", "other"]
     for k in plan_flops:
         plan_flops[k] = 0
+    js.flush()
     lib.pnmn_profile_enable(1)
     for i in range(prof_steps):
         resident_step(i)
+    js.flush()   # (the last step's deferred backward pass belongs to the profiled steps)
     pms, pln = (ctypes.c_double * 8)(), (ctypes.c_int64 * 8)()
     lib.pnmn_profile_read(pms, pln)
     lib.pnmn_profile_enable(0)

@@ -360,13 +360,20 @@ class _ExecutorFn(torch.autograd.Function):
             fork = None
             for run in runs:
                 run.bufs.grads = target.data_ptr()
+                split_stats = None
                 if run.full is not None:
                     # split compile: the forward pass ran from the forward-half plan; the full plan of the same programs
                     # (same arena layout) was compiled and uploaded meanwhile on a helper thread
                     plan, blob, event = run.take_full()
                     current.wait_event(event)
                     run.bufs.blob = blob.data_ptr()
-                    model.last_plan_stats = model._plan_info(plan, run.hi - run.lo)[2]
+                    _, sizes, model.last_plan_stats = model._plan_info(plan, run.hi - run.lo)
+                    split_stats = model.last_plan_stats
+                    # (the forward half's arena sizes are an upper bound of the full plan's by construction -- every
+                    # backward allocation site of the compiler is counted, tests/test_plan_cpu.py; never write past an arena)
+                    for slot, name in _Workspace.ARENAS.items():
+                        if name != "ain" and int(sizes[slot]) > run.ws.t[name].numel():
+                            raise RuntimeError(f"internal error: the full plan needs a larger {name} arena than its forward half reserved")
                 st = current
                 if run.stream is not None:
                     if fork is None:
@@ -374,6 +381,9 @@ class _ExecutorFn(torch.autograd.Function):
                         fork.record(current)
                     run.stream.wait_event(fork)
                     st = run.stream
+                if model.backward_stats_hook is not None:   # (benchmarks: FLOP accounting of the pass being launched)
+                    model.backward_stats_hook(split_stats if split_stats is not None
+                                              else model._plan_info(run.plan, run.hi - run.lo)[2])
                 L.check(L.lib().pnmn_nmn_backward(run.plan, ctypes.byref(run.bufs),
                                                   ctypes.c_void_p(grad_final.data_ptr() + run.lo * 128 * 196 * 4),
                                                   ctypes.c_void_p(st.cuda_stream)), "pnmn_nmn_backward")
@@ -462,6 +472,7 @@ class NeuralModuleNetwork(nn.Module):
         # a training-mode forward whose programs were not compiled ahead (precompile) launches from the forward-half plan and
         # takes its backward pass from the full plan compiled meanwhile (_single_run); PNMN_SPLIT_COMPILE=0: one plan, inline
         self.split_compile = os.environ.get("PNMN_SPLIT_COMPILE", "1") != "0"
+        self.backward_stats_hook = None   # optional callable(plan stats) invoked when a backward pass is launched
         self._pack_table: Optional[torch.Tensor] = None
         # parity tests: keep every 1-channel module output (attention map) of the last forward, see _read_attention_maps
         self.capture_attention_maps = False
@@ -711,7 +722,8 @@ class NeuralModuleNetwork(nn.Module):
                 dev = features.device
                 if self._upload_stream is None or self._upload_stream.device != dev:
                     self._upload_stream = torch.cuda.Stream(dev)
-                full = _compile_pool().submit(self._compile_and_upload, programs_host, True, dev, staged is not None)
+                # (the helper gets its own copy: `programs_host` may alias a host tensor the caller goes on to modify)
+                full = _compile_pool().submit(self._compile_and_upload, programs_host.clone(), True, dev, staged is not None)
                 plan = self._compile(programs_host, False, None, by_row=staged is not None, forward_half=True)
             else:
                 plan = self._compile(programs_host, need_grad, None, by_row=staged is not None)

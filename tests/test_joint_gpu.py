@@ -307,6 +307,47 @@ def test_full_step_runs_and_learns(trained):
     assert last < 0.85 * first
 
 
+def test_deferred_module_network_backward_changes_nothing(trained):
+    """JointTrainingStep(defer_nmn=True): the module network's backward pass + update of step i is issued with step i + 1
+    (flush() issues the last one).  Same objective every step and the same models afterwards as with every step complete in
+    itself: the sampling streams are replayed (same call counters), so both runs see the same programs."""
+    vocab, pg, qr, nmn, prior, _ = trained
+    models = (pg, qr, nmn)
+    start = [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in models]
+    counters = [(m._calls, m._teacher_calls) for m in (pg, qr)]
+    batches = [make_joint_batch(vocab, 40, seed=30 + i) for i in range(3)]
+
+    def run(defer):
+        for m, sd in zip(models, start):
+            m.load_state_dict(sd)
+        for m, (c, t) in zip((pg, qr), counters):
+            m._calls, m._teacher_calls = c, t
+        step = JointTrainingStep(pg, qr, nmn, prior, alpha=100.0, beta=0.1, gamma=1.0, delta=0.99, lr=1e-4, defer_nmn=defer)
+        objectives = [float(step.step(b)["objective"]) for b in batches]
+        assert (step._pending_nmn is not None) == defer
+        step.flush()
+        assert step._pending_nmn is None
+        torch.cuda.synchronize()
+        nmn_steps = {int(step.optimizer.state_dict()["state"][i]["step"]) for i in step.optimizer.state_dict()["state"]}
+        return objectives, [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in models], nmn_steps
+
+    try:
+        obj_a, sd_a, steps_a = run(False)
+        obj_b, sd_b, steps_b = run(True)
+    finally:
+        for m, sd in zip(models, start):
+            m.load_state_dict(sd)
+    assert steps_a == steps_b == {3}                       # every parameter of every model was stepped three times
+    np.testing.assert_allclose(obj_a, obj_b, rtol=2e-4)
+    for name, a, b, s0 in zip(("program_generator", "question_reconstructor", "nmn"), sd_a, sd_b, start):
+        # (L2 over all parameters: Adam's first steps move every element by ~lr * sign(gradient), and the weight-gradient
+        # kernels' atomics make the sign of a near-zero gradient entry a coin toss from run to run)
+        moved = sum(float((a[k] - s0[k]).double().pow(2).sum()) for k in a) ** 0.5
+        diff = sum(float((a[k] - b[k]).double().pow(2).sum()) for k in a) ** 0.5
+        print(f"{name}: parameters moved by {moved:.3e} (L2), deferred vs complete steps differ by {diff:.3e}")
+        assert moved > 0 and diff <= 0.05 * moved
+
+
 def test_device_prefetcher_slot_reuse_and_ordering():
     """feed.DevicePrefetcher: batches come back in order with the right contents while copies of later batches are in
     flight; a slot is only overwritten after its tenant was released; re-allocation on a shape change"""
