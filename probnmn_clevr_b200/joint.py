@@ -163,6 +163,9 @@ class JointTrainingStep:
         main = torch.cuda.current_stream(dev)
         if self.fused and ours and un["question"].shape[0] > 0 and su["question"].shape[0] > 0:
             return self._do_iteration_fused(un, su, dev, to, main)
+        # (a module-network backward pass + update deferred by the previous step: this path runs the passes one by one,
+        # nothing to overlap it with -- issue it first)
+        self._issue_pending_nmn()
 
         sup_out = None
         if ours:
