@@ -100,6 +100,12 @@ class JointTrainingStep:
             defer_nmn = os.environ.get("PNMN_JOINT_DEFER_NMN", "0") == "1"
         self.defer_nmn = bool(defer_nmn) and fused
         self._pending_nmn = None
+        # PNMN_JOINT_DEFER_QR=1 (with defer_nmn): the question reconstructor's backward pass + update are deferred the same
+        # way, onto the reconstructor's stream at the start of the next step (its next forward pass queues behind them).
+        # Same results (tests/test_joint_gpu.py), no gain: 5.94 against 5.82 ms per step -- the reconstructor's next
+        # forward pass, which the objective waits for, then starts later.  Default off.
+        self.defer_qr = self.defer_nmn and os.environ.get("PNMN_JOINT_DEFER_QR", "0") == "1"
+        self._pending_qr = None
         # issue order of the backward passes (experiment, see _do_iteration_fused): 0 = each right behind its forward pass
         self.order = int(os.environ.get("PNMN_JOINT_ORDER", "0"))
         # PNMN_JOINT_CHUNKS=k: the sampled programs are compiled as k independent plans on k host threads (the compile sits
@@ -165,6 +171,7 @@ class JointTrainingStep:
             return self._do_iteration_fused(un, su, dev, to, main)
         # (a module-network backward pass + update deferred by the previous step: this path runs the passes one by one,
         # nothing to overlap it with -- issue it first)
+        self._issue_pending_qr(main)
         self._issue_pending_nmn()
 
         sup_out = None
@@ -256,8 +263,9 @@ class JointTrainingStep:
             programs_all[:nu, :free] = sampled
             programs_all[nu:, : p_s.shape[1]] = p_s
             self._mark("pg_fwd_end(pg)")
-        # (deferred module-network backward of the previous step: on the caller's stream, which the generator's forward pass
-        # does not wait for)
+        # (deferred backward passes of the previous step: the reconstructor's on its own stream, the module network's on the
+        # caller's; the generator's forward pass waits for neither)
+        self._issue_pending_qr(s_qr)
         self._issue_pending_nmn()
         # the module network's weights and features are known now, its programs only after the generator's forward pass:
         # weight packing and feature layout run here, on the caller's stream, next to that pass
@@ -273,7 +281,11 @@ class JointTrainingStep:
             qr_fwd_done = torch.cuda.Event()
             qr_fwd_done.record()
             self._mark("qr_fwd_end(qr)")
-            if order == 0:
+            if order == 0 and self._stepping and self.defer_qr:
+                self._pending_qr = (qr["loss"], coef_qr)
+                self._reduced.add(id(qr_m))
+                self._updated.add(id(qr_m))
+            elif order == 0:
                 torch.autograd.backward([qr["loss"]], [coef_qr])
                 self._mark("qr_bwd_end(qr)")
                 self._reduce_early([qr_m])
@@ -385,9 +397,33 @@ class JointTrainingStep:
         self.optimizer.step(only=self.nmn)
         self.nmn.zero_grad(set_to_none=True)
 
+    def _issue_pending_qr(self, stream) -> None:
+        """Backward pass, gradient average and clamp + Adam of the question reconstructor for the step that deferred them,
+        on ``stream``."""
+        pending, self._pending_qr = self._pending_qr, None
+        if pending is None:
+            return
+        loss, coef = pending
+        qr_m = self.question_reconstructor
+        with torch.cuda.stream(stream):
+            torch.autograd.backward([loss], [coef])
+            self._mark("qr_bwd_end(deferred)")
+            if self._distributed():
+                from .dist import allreduce_gradients
+                allreduce_gradients([qr_m], group=self.group)
+            self.optimizer.step(only=qr_m)
+            qr_m.zero_grad(set_to_none=True)
+
     def flush(self) -> None:
         """Issue whatever step() deferred (``defer_nmn``).  After it the models and their optimizer state are what the
         reference's step leaves behind."""
+        if self._pending_qr is not None:
+            dev = self.nmn.stem[0].weight.device
+            with torch.cuda.device(dev):
+                main = torch.cuda.current_stream(dev)
+                s_qr = self._streams(dev)[1] if self.concurrent else main
+                self._issue_pending_qr(s_qr)
+                main.wait_stream(s_qr)
         if self._pending_nmn is not None:
             dev = self.nmn.stem[0].weight.device
             with torch.cuda.device(dev):
@@ -436,13 +472,16 @@ class JointTrainingStep:
 
     def step(self, batch: Dict[str, Any]) -> Dict[str, Any]:
         """``_Trainer.step`` (trainers/_trainer.py:172-196) without the dataloader / tensorboard parts."""
-        if self._pending_nmn is None:
+        if self._pending_nmn is None and self._pending_qr is None:
             self.optimizer.zero_grad(set_to_none=True)
         else:
-            # the module network's gradients of the previous step are still to be computed and applied (_issue_pending_nmn
-            # clears them afterwards); the other two models start from zero as usual
+            # a deferred model's gradients of the previous step are still to be computed and applied (_issue_pending_*
+            # clears them afterwards); the others start from zero as usual
             self.program_generator.zero_grad(set_to_none=True)
-            self.question_reconstructor.zero_grad(set_to_none=True)
+            if self._pending_qr is None:
+                self.question_reconstructor.zero_grad(set_to_none=True)
+            if self._pending_nmn is None:
+                self.nmn.zero_grad(set_to_none=True)
         self._stepping, self._updated = True, set()
         self.optimizer.launches_last_step = 0
         try:

@@ -323,10 +323,11 @@ def test_deferred_module_network_backward_changes_nothing(trained):
         for m, (c, t) in zip((pg, qr), counters):
             m._calls, m._teacher_calls = c, t
         step = JointTrainingStep(pg, qr, nmn, prior, alpha=100.0, beta=0.1, gamma=1.0, delta=0.99, lr=1e-4, defer_nmn=defer)
+        step.defer_qr = defer       # (the reconstructor's backward pass + update likewise, PNMN_JOINT_DEFER_QR)
         objectives = [float(step.step(b)["objective"]) for b in batches]
-        assert (step._pending_nmn is not None) == defer
+        assert (step._pending_nmn is not None) == defer and (step._pending_qr is not None) == defer
         step.flush()
-        assert step._pending_nmn is None
+        assert step._pending_nmn is None and step._pending_qr is None
         torch.cuda.synchronize()
         nmn_steps = {int(step.optimizer.state_dict()["state"][i]["step"]) for i in step.optimizer.state_dict()["state"]}
         return objectives, [{k: v.detach().clone() for k, v in m.state_dict().items()} for m in models], nmn_steps
